@@ -1,0 +1,52 @@
+"""Deterministic, platform-independent weights for parity tests (TEST INFRASTRUCTURE).
+
+The golden vectors under tests/golden/ were produced by loading exactly these tensors into the reference
+modules (oracle/make_golden.py).  They are regenerated from a {key: shape} spec with numpy's legacy
+RandomState (bit-stable by numpy policy), so 275 MB of checkpoints never needs to be committed.
+"""
+import zlib
+
+import numpy as np
+import torch
+
+
+def _rs(key, seed):
+    return np.random.RandomState((zlib.crc32(key.encode()) ^ (seed * 0x9E3779B1)) & 0x7FFFFFFF)
+
+
+def make_tensor(key, shape, seed=0):
+    rs = _rs(key, seed)
+    shape = tuple(int(s) for s in shape)
+    leaf = key.rsplit(".", 1)[-1]
+    if leaf == "num_batches_tracked":
+        return torch.zeros(shape, dtype=torch.int64)
+    if leaf == "running_mean":
+        return torch.from_numpy((0.1 * rs.standard_normal(shape)).astype(np.float32))
+    if leaf == "running_var":
+        return torch.from_numpy((1.0 + 0.1 * np.abs(rs.standard_normal(shape))).astype(np.float32))
+    if len(shape) >= 2:
+        if "embed" in key:
+            std = 1.0
+        else:
+            fan_in = int(np.prod(shape[1:]))
+            std = (2.0 / fan_in) ** 0.5
+        return torch.from_numpy((std * rs.standard_normal(shape)).astype(np.float32))
+    # 1-D: batch-norm scale (".1.weight"-style keys sit next to a running_mean) is decided by the caller
+    return torch.from_numpy((0.1 * rs.standard_normal(shape)).astype(np.float32))
+
+
+def make_state(spec, seed=0):
+    """spec: {key: shape}.  1-D `weight` tensors that belong to a norm layer (a sibling running_mean exists)
+    are drawn around 1, every other 1-D tensor around 0."""
+    out = {}
+    for key, shape in spec.items():
+        t = make_tensor(key, shape, seed)
+        if key.endswith(".weight") and len(shape) == 1 and key[:-len("weight")] + "running_mean" in spec:
+            t = t + 1.0
+        out[key] = t
+    return out
+
+
+def spec_of(module_or_state):
+    sd = module_or_state.state_dict() if hasattr(module_or_state, "state_dict") else module_or_state
+    return {k: list(v.shape) for k, v in sd.items()}
