@@ -1,0 +1,420 @@
+// extern "C" surface of libaffgw (see include/affgw.h).  Validates arguments, builds geometry, picks the kernel.
+#include <stdarg.h>
+#include <string.h>
+
+#include <atomic>
+
+#include "../../include/affgw.h"
+#include "common.cuh"
+
+// ---- implemented in the other translation units -------------------------------------------------------------
+int conv_fwd_simt(const void* x, int x_dt, const void* w, int w_dt, const float* bias, const void* addend, void* y,
+                  int y_dt, const ConvGeom& g, cudaStream_t st);
+int conv_wgrad_simt(const void* x, int x_dt, const void* dy, int dy_dt, float* dw, const ConvGeom& g, cudaStream_t st);
+int conv_fold(const void* dxp, const void* xin, void* dx, int dt, int N, int H, int W, int C, int pad, int pad_mode, int up,
+              int pre_act, cudaStream_t st);
+int colsum(const void* a, int dt, float* out, long long M, int C, int pitch, cudaStream_t st);
+int pack_weight(const float* w, void* out, int out_dt, int Cout, int Cin, int KH, int KW, int ipad, int transpose_flip,
+                cudaStream_t st);
+// conv_tc.cu
+int conv_tc_block_n(const ConvGeom& g, int x_dt, int w_dt);
+int conv_fwd_tc(const void* x, const void* w_tiles, const float* bias, const void* addend, void* y, int y_dt,
+                const ConvGeom& g, cudaStream_t st);
+int pack_weight_tc(const float* w, void* out, int Cout, int Cin, int KH, int KW, int ipad, int transpose_flip, int block_n,
+                   cudaStream_t st);
+long long pack_weight_tc_bytes(int Cout, int Cin, int KH, int KW, int ipad, int transpose_flip, int block_n);
+// norm.cu
+int norm_stats(const void* x, int dt, float* ws, float* mean, float* rstd, float* var_unbiased, int G, long long P, int C,
+               float eps, int unbiased, cudaStream_t st);
+int norm_apply(const void* x, int dt, const float* mean, const float* rstd, const float* gamma, const float* beta,
+               const void* residual, void* y, int G, long long P, int C, int act, int affine_per_group, cudaStream_t st);
+int norm_bwd(const void* dy, const void* x, int dt, const float* mean, const float* rstd, const float* gamma,
+             const float* beta, float* s1, float* s2, void* dx, int G, long long P, int C, int act, int affine_per_group,
+             int batch_stats, int unbiased, cudaStream_t st);
+int bn_update_running(float* rm, float* rv, long long* nbt, const float* mean, const float* var_unbiased, int C,
+                      float momentum, cudaStream_t st);
+int bn_eval_stats(const float* rm, const float* rv, float* mean, float* rstd, int C, float eps, cudaStream_t st);
+// pointwise.cu
+int maxpool2_fwd(const void* x, void* y, int dt, int N, int H, int W, int C, cudaStream_t st);
+int maxpool2_bwd(const void* dy, const void* x, void* dx, int dt, int N, int H, int W, int C, cudaStream_t st);
+int avgpool3s2_fwd(const void* x, void* y, int dt, int N, int H, int W, int C, cudaStream_t st);
+int avgpool3s2_bwd(const void* dy, void* dx, int dt, int N, int H, int W, int C, cudaStream_t st);
+int gate_fwd(const void* x, const void* r, const void* xl, const void* xg, void* y, int dt, int N, long long P, int C,
+             cudaStream_t st);
+int gate_bwd(const void* dy, const void* x, const void* r, const void* xl, const void* xg, void* dx, void* dr, void* dxl,
+             void* dxg, int dt, int N, long long P, int C, cudaStream_t st);
+int gap_fwd(const void* x, void* out, int dt, int N, long long P, int C, cudaStream_t st);
+int bcast_add(const void* a, const void* v, void* out, int dt, int N, long long P, int C, float scale, cudaStream_t st);
+int add2(const void* a, const void* b, void* out, int dt, long long n, cudaStream_t st);
+int act_bwd(const void* dy, const void* y, void* dz, int dt, long long n, int act, cudaStream_t st);
+int resize_nearest_fwd(const void* x, void* y, int dt, int N, int H, int W, int C, int Ho, int Wo, cudaStream_t st);
+int resize_nearest_bwd(const void* dy, void* dx, int dt, int N, int H, int W, int C, int Ho, int Wo, cudaStream_t st);
+int embedding_fwd(const long long* ids, const float* table, void* out, int dt, long long n_ids, int E, int V, int* err,
+                  cudaStream_t st);
+int embedding_bwd(const long long* ids, const void* dout, float* dtable, int dt, long long n_ids, int E, int V,
+                  cudaStream_t st);
+int text_tile_fwd(const void* chars, void* out, int dt, int B, int H, int W, int C, int ts, int reps, cudaStream_t st);
+int text_tile_bwd(const void* dout, void* dchars, int dt, int B, int H, int W, int C, int ts, int reps, cudaStream_t st);
+int bce_logits_fwd(const void* x, int dt, float target, float* loss, long long n, cudaStream_t st);
+int bce_logits_bwd(const void* x, int dt, float target, const float* gout, void* dx, long long n, cudaStream_t st);
+int softmax_ce_fwd(const void* x, int dt, const long long* y, float* loss, int B, int C, int* err, cudaStream_t st);
+int softmax_ce_bwd(const void* x, int dt, const long long* y, const float* gout, void* dx, int B, int C, cudaStream_t st);
+int nchw_to_nhwc(const float* x, void* y, int dt, int N, int C, long long HW, int cpad, cudaStream_t st);
+int nhwc_to_nchw(const void* x, float* y, int dt, int N, int C, long long HW, int cpad, cudaStream_t st);
+int cast_dtype(const void* x, int in_dt, void* y, int out_dt, long long n, cudaStream_t st);
+int concat2(void* a, void* b, void* out, int dt, long long rows, int ca, int cb, int to_out, cudaStream_t st);
+
+// ---- error string + launch counter --------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void affgw_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+void affgw_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+static inline cudaStream_t S(void* s) { return (cudaStream_t)s; }
+static inline bool dt_ok(int dt) { return dt == AFFGW_F32 || dt == AFFGW_BF16; }
+static inline size_t dt_size(int dt) { return dt == AFFGW_F32 ? 4 : 2; }
+
+static int make_geom(const affgw_conv_desc* d, ConvGeom& g, int zero_insert = 1) {
+    AFFGW_CHECK(d != nullptr, "conv: null descriptor");
+    AFFGW_CHECK(d->N > 0 && d->H > 0 && d->W > 0 && d->Cin > 0 && d->Cout > 0 && d->KH > 0 && d->KW > 0,
+                "conv: non-positive extent");
+    AFFGW_CHECK(d->stride >= 1 && d->pad >= 0, "conv: bad stride/pad");
+    AFFGW_CHECK(d->upsample == 1 || d->upsample == 2, "conv: upsample must be 1 or 2");
+    AFFGW_CHECK(d->pad_mode >= 0 && d->pad_mode <= 2, "conv: bad pad_mode");
+    AFFGW_CHECK(dt_ok(d->x_dtype) && dt_ok(d->w_dtype) && dt_ok(d->y_dtype), "conv: bad dtype");
+    AFFGW_CHECK(d->in_pitch >= d->Cin && d->out_pitch >= d->Cout, "conv: pitch smaller than channel count");
+    g.N = d->N; g.H = d->H; g.W = d->W; g.Cin = d->Cin;
+    g.Cout = d->Cout; g.KH = d->KH; g.KW = d->KW;
+    g.stride = d->stride; g.pad = d->pad; g.pad_mode = d->pad_mode; g.up = d->upsample; g.zi = zero_insert;
+    g.Ho = d->Ho; g.Wo = d->Wo;
+    g.in_pitch = d->in_pitch; g.out_pitch = d->out_pitch;
+    g.pre_act = d->pre_act; g.post_act = d->post_act;
+    g.Hv = d->H * d->upsample; g.Wv = d->W * d->upsample;
+    g.Ktot = d->KH * d->KW * d->Cin;
+    g.M = (long long)d->N * d->Ho * d->Wo;
+    const int eh = (g.Hv + 2 * d->pad - d->KH) / d->stride + 1, ew = (g.Wv + 2 * d->pad - d->KW) / d->stride + 1;
+    AFFGW_CHECK(eh == d->Ho && ew == d->Wo, "conv: output extent %dx%d does not match the geometry (%dx%d)", d->Ho, d->Wo,
+                eh, ew);
+    if (d->pad_mode == PAD_REFLECT) AFFGW_CHECK(d->pad < g.Hv && d->pad < g.Wv, "conv: reflect pad >= input extent");
+    return 0;
+}
+
+extern "C" {
+
+int affgw_version(void) { return AFFGW_VERSION; }
+const char* affgw_last_error(void) { return g_err; }
+long long affgw_launch_count(void) { return g_launches.load(); }
+
+int affgw_device_ok(void) {
+    int dev = 0;
+    cudaDeviceProp p;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&p, dev) != cudaSuccess) {
+        affgw_set_error("no CUDA device");
+        return 0;
+    }
+    if (p.major != 10) {
+        affgw_set_error("device sm_%d%d is not sm_100", p.major, p.minor);
+        return 0;
+    }
+    return 1;
+}
+
+int affgw_pack_weight(const float* w, void* out, int out_dtype, int Cout, int Cin, int KH, int KW, int i_pad,
+                      int transpose_flip, void* stream) {
+    AFFGW_CHECK(w && out && dt_ok(out_dtype), "pack_weight: bad argument");
+    AFFGW_CHECK(i_pad >= (transpose_flip ? Cout : Cin), "pack_weight: i_pad too small");
+    return pack_weight(w, out, out_dtype, Cout, Cin, KH, KW, i_pad, transpose_flip, S(stream));
+}
+
+long long affgw_pack_weight_tc_bytes(int Cout, int Cin, int KH, int KW, int i_pad, int transpose_flip, int block_n) {
+    return pack_weight_tc_bytes(Cout, Cin, KH, KW, i_pad, transpose_flip, block_n);
+}
+int affgw_pack_weight_tc(const float* w, void* out, int Cout, int Cin, int KH, int KW, int i_pad, int transpose_flip,
+                         int block_n, void* stream) {
+    AFFGW_CHECK(w && out, "pack_weight_tc: null pointer");
+    return pack_weight_tc(w, out, Cout, Cin, KH, KW, i_pad, transpose_flip, block_n, S(stream));
+}
+int affgw_conv_tc_block_n(const affgw_conv_desc* d) {
+    ConvGeom g;
+    if (make_geom(d, g)) return 0;
+    return conv_tc_block_n(g, d->x_dtype, d->w_dtype);
+}
+
+int affgw_conv2d_fwd(const void* x, const void* w, const float* bias, const void* addend, void* y,
+                     const affgw_conv_desc* d, void* stream) {
+    ConvGeom g;
+    if (int rc = make_geom(d, g)) return rc;
+    AFFGW_CHECK(x && w && y, "conv2d_fwd: null pointer");
+    if (d->algo == AFFGW_ALGO_TCGEN05) {
+        AFFGW_CHECK(conv_tc_block_n(g, d->x_dtype, d->w_dtype) > 0, "conv2d_fwd: shape not supported by the tcgen05 kernel");
+        return conv_fwd_tc(x, w, bias, addend, y, d->y_dtype, g, S(stream));
+    }
+    return conv_fwd_simt(x, d->x_dtype, w, d->w_dtype, bias, addend, y, d->y_dtype, g, S(stream));
+}
+
+// geometry of the dgrad convolution: input dY [N,Ho,Wo,Cout] (zero-inserted by stride), weights [Cin][K][K][Cout]
+static int make_dgrad(const affgw_conv_desc* d, affgw_conv_desc& dd, bool& direct, int& Hp, int& Wp) {
+    AFFGW_CHECK(d->KH == d->KW, "conv2d_dgrad: square kernels only");
+    AFFGW_CHECK(d->x_dtype == d->y_dtype, "conv2d_dgrad: x and y dtypes must match");
+    direct = d->pad_mode == PAD_ZERO && d->upsample == 1 && d->pre_act == ACT_NONE && d->pad <= d->KH - 1;
+    Hp = d->H * d->upsample + 2 * d->pad;
+    Wp = d->W * d->upsample + 2 * d->pad;
+    dd = *d;
+    dd.N = d->N; dd.H = d->Ho; dd.W = d->Wo; dd.Cin = d->Cout; dd.Cout = d->Cin;
+    dd.stride = 1; dd.pad_mode = PAD_ZERO; dd.upsample = 1;
+    dd.pad = direct ? d->KH - 1 - d->pad : d->KH - 1;
+    dd.Ho = direct ? d->H : Hp;
+    dd.Wo = direct ? d->W : Wp;
+    dd.in_pitch = d->out_pitch;
+    dd.out_pitch = direct ? d->in_pitch : d->Cin;
+    dd.pre_act = ACT_NONE; dd.post_act = ACT_NONE;
+    dd.x_dtype = d->y_dtype; dd.y_dtype = d->x_dtype;
+    return 0;
+}
+
+long long affgw_conv2d_dgrad_ws_bytes(const affgw_conv_desc* d) {
+    affgw_conv_desc dd;
+    bool direct;
+    int Hp, Wp;
+    if (!d || make_dgrad(d, dd, direct, Hp, Wp)) return -1;
+    return direct ? 0 : (long long)d->N * Hp * Wp * d->Cin * (long long)dt_size(d->x_dtype);
+}
+
+int affgw_conv2d_dgrad(const void* dy, const void* wt, const void* x, void* dx, void* workspace,
+                       const affgw_conv_desc* d, void* stream) {
+    AFFGW_CHECK(d && dy && wt && dx, "conv2d_dgrad: null pointer");
+    affgw_conv_desc dd;
+    bool direct;
+    int Hp, Wp;
+    if (int rc = make_dgrad(d, dd, direct, Hp, Wp)) return rc;
+    ConvGeom g;
+    // build geometry by hand: the virtual input is dY zero-inserted by the forward stride
+    g.N = dd.N; g.H = dd.H; g.W = dd.W; g.Cin = dd.Cin; g.Cout = dd.Cout; g.KH = dd.KH; g.KW = dd.KW;
+    g.stride = 1; g.pad = dd.pad; g.pad_mode = PAD_ZERO; g.up = 1; g.zi = d->stride;
+    g.Ho = dd.Ho; g.Wo = dd.Wo; g.in_pitch = dd.in_pitch; g.out_pitch = dd.out_pitch;
+    g.pre_act = ACT_NONE; g.post_act = ACT_NONE;
+    g.Hv = (dd.H - 1) * d->stride + 1; g.Wv = (dd.W - 1) * d->stride + 1;
+    g.Ktot = g.KH * g.KW * g.Cin;
+    g.M = (long long)g.N * g.Ho * g.Wo;
+    void* out = direct ? dx : workspace;
+    AFFGW_CHECK(out != nullptr, "conv2d_dgrad: workspace required for this geometry");
+    int rc;
+    if (d->algo == AFFGW_ALGO_TCGEN05) {
+        AFFGW_CHECK(conv_tc_block_n(g, dd.x_dtype, d->w_dtype) > 0, "conv2d_dgrad: shape not supported by the tcgen05 kernel");
+        rc = conv_fwd_tc(dy, wt, nullptr, nullptr, out, dd.y_dtype, g, S(stream));
+    } else {
+        rc = conv_fwd_simt(dy, dd.x_dtype, wt, d->w_dtype, nullptr, nullptr, out, dd.y_dtype, g, S(stream));
+    }
+    if (rc) return rc;
+    if (!direct) {
+        AFFGW_CHECK(d->pre_act == ACT_NONE || x != nullptr, "conv2d_dgrad: x needed for the pre-activation derivative");
+        AFFGW_CHECK(d->in_pitch == d->Cin, "conv2d_dgrad: folded path needs a dense x");
+        return conv_fold(workspace, x, dx, d->x_dtype, d->N, d->H, d->W, d->Cin, d->pad, d->pad_mode, d->upsample, d->pre_act,
+                         S(stream));
+    }
+    return 0;
+}
+
+int affgw_conv_tc_dgrad_block_n(const affgw_conv_desc* d) {
+    affgw_conv_desc dd;
+    bool direct;
+    int Hp, Wp;
+    if (!d || make_dgrad(d, dd, direct, Hp, Wp)) return 0;
+    ConvGeom g;
+    g.N = dd.N; g.H = dd.H; g.W = dd.W; g.Cin = dd.Cin; g.Cout = dd.Cout; g.KH = dd.KH; g.KW = dd.KW;
+    g.stride = 1; g.pad = dd.pad; g.pad_mode = PAD_ZERO; g.up = 1; g.zi = d->stride;
+    g.Ho = dd.Ho; g.Wo = dd.Wo; g.in_pitch = dd.in_pitch; g.out_pitch = dd.out_pitch;
+    g.pre_act = g.post_act = ACT_NONE;
+    g.Hv = (dd.H - 1) * d->stride + 1; g.Wv = (dd.W - 1) * d->stride + 1;
+    g.Ktot = g.KH * g.KW * g.Cin;
+    g.M = (long long)g.N * g.Ho * g.Wo;
+    return conv_tc_block_n(g, dd.x_dtype, d->w_dtype);
+}
+
+int affgw_conv2d_wgrad(const void* x, const void* dy, float* dw, const affgw_conv_desc* d, void* stream) {
+    ConvGeom g;
+    if (int rc = make_geom(d, g)) return rc;
+    AFFGW_CHECK(x && dy && dw, "conv2d_wgrad: null pointer");
+    return conv_wgrad_simt(x, d->x_dtype, dy, d->y_dtype, dw, g, S(stream));
+}
+
+int affgw_colsum(const void* a, int dtype, float* out, long long M, int C, int pitch, void* stream) {
+    AFFGW_CHECK(a && out && dt_ok(dtype) && M > 0 && C > 0 && pitch >= C, "colsum: bad argument");
+    return colsum(a, dtype, out, M, C, pitch, S(stream));
+}
+
+int affgw_norm_stats(const void* x, int dtype, float* ws, float* mean, float* rstd, float* var_unbiased, int G, long long P,
+                     int C, float eps, int unbiased, void* stream) {
+    AFFGW_CHECK(x && ws && mean && rstd && dt_ok(dtype) && G > 0 && P > 0 && C > 0, "norm_stats: bad argument");
+    return norm_stats(x, dtype, ws, mean, rstd, var_unbiased, G, P, C, eps, unbiased, S(stream));
+}
+int affgw_norm_apply(const void* x, int dtype, const float* mean, const float* rstd, const float* gamma, const float* beta,
+                     const void* residual, void* y, int G, long long P, int C, int act, int affine_per_group, void* stream) {
+    AFFGW_CHECK(x && y && mean && rstd && dt_ok(dtype) && G > 0 && P > 0 && C > 0, "norm_apply: bad argument");
+    AFFGW_CHECK((gamma == nullptr) == (beta == nullptr), "norm_apply: gamma and beta must be given together");
+    return norm_apply(x, dtype, mean, rstd, gamma, beta, residual, y, G, P, C, act, affine_per_group, S(stream));
+}
+int affgw_norm_bwd(const void* dy, const void* x, int dtype, const float* mean, const float* rstd, const float* gamma,
+                   const float* beta, float* s1, float* s2, void* dx, int G, long long P, int C, int act,
+                   int affine_per_group, int batch_stats, int unbiased, void* stream) {
+    AFFGW_CHECK(dy && x && dx && mean && rstd && s1 && s2 && dt_ok(dtype) && G > 0 && P > 0 && C > 0, "norm_bwd: bad argument");
+    AFFGW_CHECK(act != ACT_TANH, "norm_bwd: tanh is not a fused norm activation");
+    return norm_bwd(dy, x, dtype, mean, rstd, gamma, beta, s1, s2, dx, G, P, C, act, affine_per_group, batch_stats, unbiased, S(stream));
+}
+int affgw_bn_update_running(float* rm, float* rv, long long* nbt, const float* mean, const float* var_unbiased, int C,
+                            float momentum, void* stream) {
+    AFFGW_CHECK(rm && rv && mean && var_unbiased && C > 0, "bn_update_running: bad argument");
+    return bn_update_running(rm, rv, nbt, mean, var_unbiased, C, momentum, S(stream));
+}
+int affgw_bn_eval_stats(const float* rm, const float* rv, float* mean, float* rstd, int C, float eps, void* stream) {
+    AFFGW_CHECK(rm && rv && mean && rstd && C > 0, "bn_eval_stats: bad argument");
+    return bn_eval_stats(rm, rv, mean, rstd, C, eps, S(stream));
+}
+
+#define REQ(cond, name) AFFGW_CHECK(cond, name ": bad argument")
+int affgw_maxpool2_fwd(const void* x, void* y, int dt, int N, int H, int W, int C, void* s) {
+    REQ(x && y && dt_ok(dt) && N > 0 && H > 1 && W > 1 && C > 0, "maxpool2_fwd");
+    return maxpool2_fwd(x, y, dt, N, H, W, C, S(s));
+}
+int affgw_maxpool2_bwd(const void* dy, const void* x, void* dx, int dt, int N, int H, int W, int C, void* s) {
+    REQ(dy && x && dx && dt_ok(dt) && N > 0 && H > 1 && W > 1 && C > 0, "maxpool2_bwd");
+    return maxpool2_bwd(dy, x, dx, dt, N, H, W, C, S(s));
+}
+int affgw_avgpool3s2_fwd(const void* x, void* y, int dt, int N, int H, int W, int C, void* s) {
+    REQ(x && y && dt_ok(dt) && N > 0 && H > 1 && W > 1 && C > 0, "avgpool3s2_fwd");
+    return avgpool3s2_fwd(x, y, dt, N, H, W, C, S(s));
+}
+int affgw_avgpool3s2_bwd(const void* dy, void* dx, int dt, int N, int H, int W, int C, void* s) {
+    REQ(dy && dx && dt_ok(dt) && N > 0 && H > 1 && W > 1 && C > 0, "avgpool3s2_bwd");
+    return avgpool3s2_bwd(dy, dx, dt, N, H, W, C, S(s));
+}
+int affgw_resize_nearest_fwd(const void* x, void* y, int dt, int N, int H, int W, int C, int Ho, int Wo, void* s) {
+    REQ(x && y && dt_ok(dt) && N > 0 && H > 0 && W > 0 && C > 0 && Ho > 0 && Wo > 0, "resize_nearest_fwd");
+    return resize_nearest_fwd(x, y, dt, N, H, W, C, Ho, Wo, S(s));
+}
+int affgw_resize_nearest_bwd(const void* dy, void* dx, int dt, int N, int H, int W, int C, int Ho, int Wo, void* s) {
+    REQ(dy && dx && dt_ok(dt) && N > 0 && H > 0 && W > 0 && C > 0 && Ho > 0 && Wo > 0, "resize_nearest_bwd");
+    return resize_nearest_bwd(dy, dx, dt, N, H, W, C, Ho, Wo, S(s));
+}
+int affgw_gate_fwd(const void* x, const void* r, const void* xl, const void* xg, void* y, int dt, int N, long long P, int C,
+                   void* s) {
+    REQ(x && r && xl && xg && y && dt_ok(dt) && N > 0 && P > 0 && C > 0, "gate_fwd");
+    return gate_fwd(x, r, xl, xg, y, dt, N, P, C, S(s));
+}
+int affgw_gate_bwd(const void* dy, const void* x, const void* r, const void* xl, const void* xg, void* dx, void* dr,
+                   void* dxl, void* dxg, int dt, int N, long long P, int C, void* s) {
+    REQ(dy && x && r && xl && xg && dx && dr && dxl && dxg && dt_ok(dt) && N > 0 && P > 0 && C > 0, "gate_bwd");
+    return gate_bwd(dy, x, r, xl, xg, dx, dr, dxl, dxg, dt, N, P, C, S(s));
+}
+int affgw_gap_fwd(const void* x, void* out, int dt, int N, long long P, int C, void* s) {
+    REQ(x && out && dt_ok(dt) && N > 0 && P > 0 && C > 0, "gap_fwd");
+    return gap_fwd(x, out, dt, N, P, C, S(s));
+}
+int affgw_bcast_add(const void* a, const void* v, void* out, int dt, int N, long long P, int C, float scale, void* s) {
+    REQ(v && out && dt_ok(dt) && N > 0 && P > 0 && C > 0, "bcast_add");
+    return bcast_add(a, v, out, dt, N, P, C, scale, S(s));
+}
+int affgw_add2(const void* a, const void* b, void* out, int dt, long long n, void* s) {
+    REQ(a && b && out && dt_ok(dt) && n > 0, "add2");
+    return add2(a, b, out, dt, n, S(s));
+}
+int affgw_act_bwd(const void* dy, const void* y, void* dz, int dt, long long n, int act, void* s) {
+    REQ(dy && y && dz && dt_ok(dt) && n > 0 && act >= 0 && act <= 3, "act_bwd");
+    return act_bwd(dy, y, dz, dt, n, act, S(s));
+}
+int affgw_embedding_fwd(const long long* ids, const float* table, void* out, int dt, long long n_ids, int E, int V, int* err,
+                        void* s) {
+    REQ(ids && table && out && err && dt_ok(dt) && n_ids > 0 && E > 0 && V > 0, "embedding_fwd");
+    return embedding_fwd(ids, table, out, dt, n_ids, E, V, err, S(s));
+}
+int affgw_embedding_bwd(const long long* ids, const void* dout, float* dtable, int dt, long long n_ids, int E, int V, void* s) {
+    REQ(ids && dout && dtable && dt_ok(dt) && n_ids > 0 && E > 0 && V > 0, "embedding_bwd");
+    return embedding_bwd(ids, dout, dtable, dt, n_ids, E, V, S(s));
+}
+int affgw_text_tile_fwd(const void* chars, void* out, int dt, int B, int H, int W, int C, int ts, int reps, void* s) {
+    REQ(chars && out && dt_ok(dt) && B > 0 && H > 0 && W > 0 && C > 0 && ts > 0 && reps > 0, "text_tile_fwd");
+    return text_tile_fwd(chars, out, dt, B, H, W, C, ts, reps, S(s));
+}
+int affgw_text_tile_bwd(const void* dout, void* dchars, int dt, int B, int H, int W, int C, int ts, int reps, void* s) {
+    REQ(dout && dchars && dt_ok(dt) && B > 0 && H > 0 && W > 0 && C > 0 && ts > 0 && reps > 0, "text_tile_bwd");
+    return text_tile_bwd(dout, dchars, dt, B, H, W, C, ts, reps, S(s));
+}
+int affgw_bce_logits_fwd(const void* x, int dt, float target, float* loss, long long n, void* s) {
+    REQ(x && loss && dt_ok(dt) && n > 0, "bce_logits_fwd");
+    return bce_logits_fwd(x, dt, target, loss, n, S(s));
+}
+int affgw_bce_logits_bwd(const void* x, int dt, float target, const float* gout, void* dx, long long n, void* s) {
+    REQ(x && gout && dx && dt_ok(dt) && n > 0, "bce_logits_bwd");
+    return bce_logits_bwd(x, dt, target, gout, dx, n, S(s));
+}
+int affgw_softmax_ce_fwd(const void* x, int dt, const long long* y, float* loss, int B, int C, int* err, void* s) {
+    REQ(x && y && loss && err && dt_ok(dt) && B > 0 && C > 0, "softmax_ce_fwd");
+    return softmax_ce_fwd(x, dt, y, loss, B, C, err, S(s));
+}
+int affgw_softmax_ce_bwd(const void* x, int dt, const long long* y, const float* gout, void* dx, int B, int C, void* s) {
+    REQ(x && y && gout && dx && dt_ok(dt) && B > 0 && C > 0, "softmax_ce_bwd");
+    return softmax_ce_bwd(x, dt, y, gout, dx, B, C, S(s));
+}
+int affgw_nchw_to_nhwc(const float* x, void* y, int dt, int N, int C, long long HW, int c_pad, void* s) {
+    REQ(x && y && dt_ok(dt) && N > 0 && C > 0 && HW > 0 && c_pad >= C, "nchw_to_nhwc");
+    return nchw_to_nhwc(x, y, dt, N, C, HW, c_pad, S(s));
+}
+int affgw_nhwc_to_nchw(const void* x, float* y, int dt, int N, int C, long long HW, int c_pad, void* s) {
+    REQ(x && y && dt_ok(dt) && N > 0 && C > 0 && HW > 0 && c_pad >= C, "nhwc_to_nchw");
+    return nhwc_to_nchw(x, y, dt, N, C, HW, c_pad, S(s));
+}
+int affgw_concat_channels(const void* a, const void* b, void* out, int dt, long long rows, int ca, int cb, void* s) {
+    REQ(a && b && out && dt_ok(dt) && rows > 0 && ca > 0 && cb > 0, "concat_channels");
+    return concat2(const_cast<void*>(a), const_cast<void*>(b), out, dt, rows, ca, cb, 1, S(s));
+}
+int affgw_split_channels(const void* in, void* a, void* b, int dt, long long rows, int ca, int cb, void* s) {
+    REQ(a && b && in && dt_ok(dt) && rows > 0 && ca > 0 && cb > 0, "split_channels");
+    return concat2(a, b, const_cast<void*>(in), dt, rows, ca, cb, 0, S(s));
+}
+int affgw_cast(const void* x, int in_dt, void* y, int out_dt, long long n, void* s) {
+    REQ(x && y && dt_ok(in_dt) && dt_ok(out_dt) && n > 0, "cast");
+    return cast_dtype(x, in_dt, y, out_dt, n, S(s));
+}
+
+
+}  // extern "C"
+
+// ---- gradient bucket pack / unpack (one block column per tensor) ---------------------------------------------
+namespace {
+__global__ void bucket_pack_kernel(const float* const* ptrs, const long long* sizes, const long long* offsets, float* bucket) {
+    const float* src = ptrs[blockIdx.y];
+    float* dst = bucket + offsets[blockIdx.y];
+    const long long n = sizes[blockIdx.y];
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        dst[i] = src[i];
+}
+__global__ void bucket_unpack_kernel(float* const* ptrs, const long long* sizes, const long long* offsets,
+                                     const float* bucket, float scale) {
+    float* dst = ptrs[blockIdx.y];
+    const float* src = bucket + offsets[blockIdx.y];
+    const long long n = sizes[blockIdx.y];
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        dst[i] = src[i] * scale;
+}
+}  // namespace
+
+extern "C" int affgw_bucket_pack(const float* const* ptrs, const long long* sizes, const long long* offsets, int n,
+                                 float* bucket, void* stream) {
+    AFFGW_CHECK(ptrs && sizes && offsets && bucket && n > 0 && n <= 65535, "bucket_pack: bad argument");
+    bucket_pack_kernel<<<dim3(32, n), 256, 0, S(stream)>>>(ptrs, sizes, offsets, bucket);
+    AFFGW_LAUNCH_CHECK("bucket_pack");
+    return 0;
+}
+extern "C" int affgw_bucket_unpack(float* const* ptrs, const long long* sizes, const long long* offsets, int n,
+                                   const float* bucket, float scale, void* stream) {
+    AFFGW_CHECK(ptrs && sizes && offsets && bucket && n > 0 && n <= 65535, "bucket_unpack: bad argument");
+    bucket_unpack_kernel<<<dim3(32, n), 256, 0, S(stream)>>>(ptrs, sizes, offsets, bucket, scale);
+    AFFGW_LAUNCH_CHECK("bucket_unpack");
+    return 0;
+}

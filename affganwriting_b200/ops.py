@@ -1,0 +1,707 @@
+"""Autograd-visible operators over the libaffgw C ABI.
+
+Every operator takes / returns ordinary torch tensors with the reference's logical shapes (N, C, H, W), stored
+channels-last (NHWC in memory) so that no layout copies happen between operators.  PyTorch is used for tensor
+allocation, streams and the autograd graph only: all arithmetic below runs in libaffgw kernels.
+"""
+import collections
+import ctypes as C
+
+import torch
+from torch.autograd import Function
+
+from . import _lib as L  # noqa: N812
+
+_state = {"mode": "fp32", "force_simt": False}
+_err_flag = {}
+
+
+def set_precision(mode):
+    """'fp32' : fp32 storage + CUDA-core FFMA convolutions (<= 1e-4 against the CPU reference)
+       'bf16' : bf16 storage + tcgen05 tensor-core convolutions with fp32 accumulation (<= 2e-2)."""
+    if mode not in ("fp32", "bf16"):
+        raise ValueError("precision must be 'fp32' or 'bf16'")
+    _state["mode"] = mode
+
+
+def precision():
+    return _state["mode"]
+
+
+def act_dtype():
+    return torch.bfloat16 if _state["mode"] == "bf16" else torch.float32
+
+
+def force_simt(flag=True):
+    """Route every convolution through the CUDA-core kernel (used by tests to cross-check tcgen05)."""
+    _state["force_simt"] = bool(flag)
+
+
+def _err_tensor(device):
+    key = (device.type, device.index)
+    if key not in _err_flag:
+        _err_flag[key] = torch.zeros(1, dtype=torch.int32, device=device)
+    return _err_flag[key]
+
+
+def check_device_errors(device=None):
+    """Raise if any kernel flagged an out-of-range label / writer id since the last check (one host sync)."""
+    for key, t in _err_flag.items():
+        if int(t.item()) != 0:
+            t.zero_()
+            raise RuntimeError("libaffgw: out-of-range token or class index")
+
+
+# ------------------------------------------------------------------------------------------------ layout helpers
+def _pitch4(x):
+    """(N, C, H, W, pitch) if the 4-D tensor is addressable as NHWC with a channel pitch, else None."""
+    n, c, h, w = x.shape
+    sn, sc, sh, sw = x.stride()
+    if w > 1:
+        pitch = sw
+    elif h > 1:
+        pitch = sh
+    elif n > 1:
+        pitch = sn
+    else:
+        pitch = c
+    ok = (c == 1 or sc == 1) and pitch >= c and (w == 1 or sw == pitch) and (h == 1 or sh == w * pitch) and \
+         (n == 1 or sn == h * w * pitch)
+    return (n, c, h, w, pitch) if ok else None
+
+
+def empty_cl(n, c, h, w, dtype, device, zero=False):
+    """NCHW-shaped tensor stored NHWC."""
+    base = (torch.zeros if zero else torch.empty)((n, h, w, c), dtype=dtype, device=device)
+    return base.permute(0, 3, 1, 2)
+
+
+def to_internal(x, c_pad=None, dtype=None):
+    """Bring a caller tensor (typically NCHW fp32, network_tro.py:30-36) to the internal layout / dtype.
+    c_pad zero-pads the channel dimension (the 50 -> 64 style-image planes of the first VGG conv)."""
+    L.require_cuda(x)
+    dtype = dtype or act_dtype()
+    if x.dim() != 4:
+        if x.dtype == dtype and x.is_contiguous():
+            return x
+        return _cast(x.contiguous(), dtype)
+    n, c, h, w = x.shape
+    cp = c_pad or c
+    g = _pitch4(x)
+    if g is not None and g[4] == c and cp == c:
+        return x if x.dtype == dtype else _cast(x, dtype)
+    if x.dtype != torch.float32 or not x.is_contiguous():
+        x = x.float().contiguous()
+    out = empty_cl(n, cp, h, w, dtype, x.device)
+    L.call("affgw_nchw_to_nhwc", x.data_ptr(), out.data_ptr(), L.dt(out), n, c, h * w, cp, L.stream())
+    return out
+
+
+def _cast(x, dtype):
+    out = torch.empty_like(x, dtype=dtype)
+    L.call("affgw_cast", x.data_ptr(), L.dt(x), out.data_ptr(), L.dt(out), x.numel(), L.stream())
+    return out
+
+
+def _dense_cl(t, dtype=None):
+    """Dense NHWC tensor (pitch == C) of the requested dtype; used on incoming gradients."""
+    if t.dim() == 4:
+        g = _pitch4(t)
+        if g is None or g[4] != g[1]:
+            t = to_internal(t if t.dtype == torch.float32 else t.float(), dtype=dtype or t.dtype)
+    elif not t.is_contiguous():
+        t = t.contiguous()
+    if dtype is not None and t.dtype != dtype:
+        t = _cast(t, dtype)
+    return t
+
+
+class _ToInternal(Function):
+    """Boundary conversion for inputs that require grad (dis_update real images, network_tro.py:108-109)."""
+
+    @staticmethod
+    def forward(ctx, x, c_pad, dtype):
+        ctx.shape = x.shape
+        return to_internal(x.detach(), c_pad, dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        n, c, h, w = ctx.shape
+        g = _dense_cl(g)
+        out = torch.empty((n, c, h, w), dtype=torch.float32, device=g.device)
+        L.call("affgw_nhwc_to_nchw", g.data_ptr(), out.data_ptr(), L.dt(g), n, c, h * w, g.shape[1], L.stream())
+        return out, None, None
+
+
+def _is_internal(x, c_pad, dtype):
+    if x.dtype != dtype or not x.is_cuda:
+        return False
+    if x.dim() != 4:
+        return x.dim() == 0 or x.stride(-1) == 1
+    return _pitch4(x) is not None and (c_pad is None or c_pad == x.shape[1])
+
+
+def input_to_internal(x, c_pad=None, dtype=None):
+    """Identity for tensors our own operators produced; converts caller tensors at the boundary."""
+    dtype = dtype or act_dtype()
+    if _is_internal(x, c_pad, dtype):
+        return x
+    if x.requires_grad and torch.is_grad_enabled():
+        return _ToInternal.apply(x, c_pad, dtype)
+    return to_internal(x, c_pad, dtype)
+
+
+# ------------------------------------------------------------------------------------------------ convolution
+ConvCfg = collections.namedtuple("ConvCfg", "stride pad pad_mode upsample pre_act post_act out_dtype")
+
+
+class _WeightCache:
+    """Packed operand copies of a parameter, rebuilt when the parameter's version counter moves."""
+
+    @staticmethod
+    def get(weight, kind, builder):
+        cache = weight.__dict__.setdefault("_affgw_packed", {})
+        ent = cache.get(kind)
+        ver = weight._version
+        if ent is None or ent[0] != ver or ent[1] != weight.data_ptr():
+            ent = (ver, weight.data_ptr(), builder())
+            cache[kind] = ent
+        return ent[2]
+
+
+def _w4(weight):
+    return weight if weight.dim() == 4 else weight.view(weight.shape[0], weight.shape[1], 1, 1)
+
+
+def _pack(weight, dtype, ipad, flip):
+    w4 = _w4(weight.detach())
+    co, ci, kh, kw = w4.shape
+
+    def build():
+        rows = ci if flip else co
+        out = torch.empty((rows, kh, kw, ipad), dtype=dtype, device=weight.device)
+        L.call("affgw_pack_weight", w4.contiguous().data_ptr(), out.data_ptr(), L.dt(out), co, ci, kh, kw, ipad,
+               int(flip), L.stream())
+        return out
+    return _WeightCache.get(weight, ("plain", dtype, ipad, flip), build)
+
+
+def _pack_tc(weight, ipad, flip, bn):
+    w4 = _w4(weight.detach())
+    co, ci, kh, kw = w4.shape
+
+    def build():
+        nbytes = L.lib().affgw_pack_weight_tc_bytes(co, ci, kh, kw, ipad, int(flip), bn)
+        if nbytes <= 0:
+            raise RuntimeError("affgw_pack_weight_tc_bytes: " + L.last_error())
+        out = torch.empty(nbytes // 2, dtype=torch.bfloat16, device=weight.device)
+        L.call("affgw_pack_weight_tc", w4.contiguous().data_ptr(), out.data_ptr(), co, ci, kh, kw, ipad, int(flip), bn,
+               L.stream())
+        return out
+    return _WeightCache.get(weight, ("tc", ipad, flip, bn), build)
+
+
+def _conv_geom(x, weight, cfg):
+    """-> dict(N,H,W,Cx,pitch,Cout,Cin,KH,KW,Ho,Wo, two_d)"""
+    w4 = _w4(weight)
+    co, ci, kh, kw = w4.shape
+    if x.dim() == 2:
+        n, cx = x.shape
+        h = w = 1
+        pitch = x.stride(0) if n > 1 else max(cx, x.stride(0))
+        if x.stride(1) != 1:
+            raise RuntimeError("conv2d: 2-D input must have unit inner stride")
+    else:
+        g = _pitch4(x)
+        if g is None:
+            raise RuntimeError("conv2d: input is not channels-last addressable (call ops.to_internal first)")
+        n, cx, h, w, pitch = g
+    if cx < ci:
+        raise RuntimeError(f"conv2d: input has {cx} channels, weight expects {ci}")
+    hv, wv = h * cfg.upsample, w * cfg.upsample
+    ho = (hv + 2 * cfg.pad - kh) // cfg.stride + 1
+    wo = (wv + 2 * cfg.pad - kw) // cfg.stride + 1
+    return dict(N=n, H=h, W=w, Cx=cx, pitch=pitch, Cout=co, Cin=ci, KH=kh, KW=kw, Ho=ho, Wo=wo, two_d=x.dim() == 2)
+
+
+def _desc(g, cfg, cin, x_dt, w_dt, y_dt, algo, out_pitch=None):
+    d = L.ConvDesc()
+    d.N, d.H, d.W, d.Cin = g["N"], g["H"], g["W"], cin
+    d.Cout, d.KH, d.KW = g["Cout"], g["KH"], g["KW"]
+    d.stride, d.pad, d.pad_mode, d.upsample = cfg.stride, cfg.pad, L.PAD[cfg.pad_mode], cfg.upsample
+    d.Ho, d.Wo = g["Ho"], g["Wo"]
+    d.in_pitch, d.out_pitch = g["pitch"], out_pitch or g["Cout"]
+    d.pre_act, d.post_act = L.ACT[cfg.pre_act], L.ACT[cfg.post_act]
+    d.x_dtype, d.w_dtype, d.y_dtype = x_dt, w_dt, y_dt
+    d.algo = algo
+    return d
+
+
+def _tc_ok(d):
+    if _state["mode"] != "bf16" or _state["force_simt"]:
+        return 0
+    return L.lib().affgw_conv_tc_block_n(C.byref(d))
+
+
+class _Conv2d(Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, addend, cfg):
+        L.require_cuda(x, weight)
+        g = _conv_geom(x, weight, cfg)
+        y_dtype = cfg.out_dtype or x.dtype
+        x_dt, y_dt = L.dt(x), (L.F32 if y_dtype == torch.float32 else L.BF16)
+        w_dt = L.BF16 if x.dtype == torch.bfloat16 else L.F32
+        # tensor-core route: gather 64-channel slices, so the channel count seen by the kernel is the stored one
+        d = _desc(g, cfg, g["Cx"], x_dt, w_dt, y_dt, L.ALGO_TC)
+        bn = _tc_ok(d) if g["Cx"] == g["pitch"] else 0
+        if bn:
+            wp = _pack_tc(weight, g["Cx"], False, bn)
+        else:
+            d = _desc(g, cfg, g["Cin"], x_dt, w_dt, y_dt, L.ALGO_SIMT)
+            wp = _pack(weight, torch.bfloat16 if w_dt == L.BF16 else torch.float32, g["Cin"], False)
+        if g["two_d"]:
+            y = torch.empty((g["N"], g["Cout"]), dtype=y_dtype, device=x.device)
+        else:
+            y = empty_cl(g["N"], g["Cout"], g["Ho"], g["Wo"], y_dtype, x.device)
+        if addend is not None:
+            addend = _dense_cl(addend, y_dtype)
+        b32 = None if bias is None else bias.detach()
+        L.call("affgw_conv2d_fwd", x.data_ptr(), wp.data_ptr(), L.ptr(b32), L.ptr(addend), y.data_ptr(), C.byref(d),
+               L.stream())
+        ctx.cfg, ctx.g = cfg, g
+        ctx.has_bias, ctx.has_addend = bias is not None, addend is not None
+        ctx.save_for_backward(x, weight, y if cfg.post_act != "none" else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, y = ctx.saved_tensors
+        cfg, g = ctx.cfg, ctx.g
+        need_x, need_w, need_b, need_a = ctx.needs_input_grad[:4]
+        y_dtype = cfg.out_dtype or x.dtype
+        dz = _dense_cl(dy, y_dtype)
+        if cfg.post_act != "none":
+            t = torch.empty_like(dz)
+            L.call("affgw_act_bwd", dz.data_ptr(), y.data_ptr(), t.data_ptr(), L.dt(dz), dz.numel(), L.ACT[cfg.post_act],
+                   L.stream())
+            dz = t
+        st = L.stream()
+        x_dt, y_dt = L.dt(x), L.dt(dz)
+        w_dt = L.BF16 if x.dtype == torch.bfloat16 else L.F32
+        M = g["N"] * g["Ho"] * g["Wo"]
+        db = dw = dx = None
+        if ctx.has_bias and need_b:
+            db = torch.zeros(g["Cout"], dtype=torch.float32, device=x.device)
+            L.call("affgw_colsum", dz.data_ptr(), y_dt, db.data_ptr(), M, g["Cout"], g["Cout"], st)
+        fwd_cfg = cfg._replace(post_act="none")
+        if need_w:
+            dw = torch.zeros(weight.shape, dtype=torch.float32, device=x.device)
+            d = _desc(g, fwd_cfg, g["Cin"], x_dt, w_dt, y_dt, L.ALGO_SIMT)
+            L.call("affgw_conv2d_wgrad", x.data_ptr(), dz.data_ptr(), dw.data_ptr(), C.byref(d), st)
+        if need_x:
+            if x.dtype != dz.dtype:
+                dz_x = _cast(dz, x.dtype)
+            else:
+                dz_x = dz
+            cin = g["Cin"]
+            if g["Cx"] != cin and not (cfg.pad_mode == "zero" and cfg.upsample == 1 and cfg.pre_act == "none"):
+                raise RuntimeError("conv2d backward: channel-padded input needs a zero-pad, stride-1 convolution")
+            dense = g["pitch"] == cin
+            if g["two_d"]:
+                base = torch.empty((g["N"], cin), dtype=x.dtype, device=x.device) if dense else \
+                    torch.zeros((g["N"], g["pitch"]), dtype=x.dtype, device=x.device)
+                dx = base if dense else base[:, :g["Cx"]]
+            else:
+                base = empty_cl(g["N"], g["pitch"], g["H"], g["W"], x.dtype, x.device, zero=not dense)
+                dx = base if dense else base[:, :g["Cx"]]
+            d = _desc(g, fwd_cfg, cin, L.dt(x), w_dt, L.dt(x), L.ALGO_TC)
+            bn = 0
+            if _state["mode"] == "bf16" and not _state["force_simt"]:
+                bn = L.lib().affgw_conv_tc_dgrad_block_n(C.byref(d))
+            if bn:
+                wt = _pack_tc(weight, g["Cout"], True, bn)
+            else:
+                d.algo = L.ALGO_SIMT
+                wt = _pack(weight, torch.bfloat16 if w_dt == L.BF16 else torch.float32, g["Cout"], True)
+            ws_bytes = L.lib().affgw_conv2d_dgrad_ws_bytes(C.byref(d))
+            if ws_bytes < 0:
+                raise RuntimeError("conv2d_dgrad_ws_bytes: " + L.last_error())
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device) if ws_bytes else None
+            L.call("affgw_conv2d_dgrad", dz_x.data_ptr(), wt.data_ptr(), x.data_ptr(), base.data_ptr(), L.ptr(ws),
+                   C.byref(d), st)
+        da = dz if (ctx.has_addend and need_a) else None
+        return dx, dw, db, da, None
+
+
+def conv2d(x, weight, bias=None, stride=1, pad=0, pad_mode="zero", upsample=1, pre_act="none", post_act="none",
+           addend=None, out_dtype=None):
+    """pad -> [nearest x2] -> conv -> +bias -> +addend -> activation   (blocks.py:150-163, modules_tro.py:594-598)"""
+    cfg = ConvCfg(int(stride), int(pad), pad_mode, int(upsample), pre_act, post_act, out_dtype)
+    return _Conv2d.apply(x, weight, bias, addend, cfg)
+
+
+def linear(x, weight, bias=None, post_act="none", out_dtype=None):
+    """nn.Linear as a 1x1 convolution over the leading dimensions (modules_tro.py:222,252-259,272-282)."""
+    lead = x.shape[:-1]
+    x2 = x if x.dim() == 2 else x.reshape(-1, x.shape[-1])
+    y = conv2d(x2, weight, bias, post_act=post_act, out_dtype=out_dtype)
+    return y if x.dim() == 2 else y.view(*lead, y.shape[-1])
+
+
+# ------------------------------------------------------------------------------------------------ normalisation
+def _stats(x, G, P, Cc, eps, unbiased, want_var=False):
+    dev = x.device
+    ws = torch.empty(2 * G * Cc, dtype=torch.float32, device=dev)
+    mean = torch.empty(G * Cc, dtype=torch.float32, device=dev)
+    rstd = torch.empty(G * Cc, dtype=torch.float32, device=dev)
+    var = torch.empty(G * Cc, dtype=torch.float32, device=dev) if want_var else None
+    L.call("affgw_norm_stats", x.data_ptr(), L.dt(x), ws.data_ptr(), mean.data_ptr(), rstd.data_ptr(), L.ptr(var), G, P, Cc,
+           float(eps), int(unbiased), L.stream())
+    return mean, rstd, var
+
+
+def _gpc(x, per_sample):
+    if x.dim() == 4:
+        n, c, h, w = x.shape
+        return (n, h * w, c) if per_sample else (1, n * h * w, c)
+    n, c = x.shape
+    return (n, 1, c) if per_sample else (1, n, c)
+
+
+class _InstanceNorm(Function):
+    """Per-(n, c) normalisation with optional per-(n, c) affine, activation and residual:
+    nn.InstanceNorm2d (+ReLU), AdaptiveInstanceNorm2d's F.batch_norm trick (blocks.py:197-204), mean_variance_norm."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, residual, act, eps, unbiased):
+        x = _dense_cl(x)
+        G, P, Cc = _gpc(x, True)
+        mean, rstd, _ = _stats(x, G, P, Cc, eps, unbiased)
+        if gamma is not None:
+            gamma, beta = gamma.detach().float().contiguous(), beta.detach().float().contiguous()
+        if residual is not None:
+            residual = _dense_cl(residual, x.dtype)
+        y = torch.empty_like(x)
+        L.call("affgw_norm_apply", x.data_ptr(), L.dt(x), mean.data_ptr(), rstd.data_ptr(), L.ptr(gamma), L.ptr(beta),
+               L.ptr(residual), y.data_ptr(), G, P, Cc, L.ACT[act], 1, L.stream())
+        ctx.act, ctx.unbiased, ctx.affine, ctx.has_res = act, unbiased, gamma is not None, residual is not None
+        ctx.save_for_backward(x, mean, rstd, gamma, beta)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, mean, rstd, gamma, beta = ctx.saved_tensors
+        G, P, Cc = _gpc(x, True)
+        dy = _dense_cl(dy, x.dtype)
+        s1 = torch.empty(G * Cc, dtype=torch.float32, device=x.device)
+        s2 = torch.empty(G * Cc, dtype=torch.float32, device=x.device)
+        dx = torch.empty_like(x)
+        L.call("affgw_norm_bwd", dy.data_ptr(), x.data_ptr(), L.dt(x), mean.data_ptr(), rstd.data_ptr(), L.ptr(gamma),
+               L.ptr(beta), s1.data_ptr(), s2.data_ptr(), dx.data_ptr(), G, P, Cc, L.ACT[ctx.act], 1, 1, int(ctx.unbiased),
+               L.stream())
+        return dx, (s2 if ctx.affine else None), (s1 if ctx.affine else None), (dy if ctx.has_res else None), None, None, None
+
+
+def instance_norm(x, act="none", gamma=None, beta=None, residual=None, eps=1e-5, unbiased=False):
+    return _InstanceNorm.apply(x, gamma, beta, residual, act, eps, unbiased)
+
+
+class _BatchNorm(Function):
+    """nn.BatchNorm1d / nn.BatchNorm2d (blocks.py:250-281, modules_tro.py:275,278) with fused activation."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, buffers, training, momentum, eps, act):
+        x = _dense_cl(x)
+        G, P, Cc = _gpc(x, False)
+        running_mean, running_var, nbt = buffers
+        if training:
+            if P <= 1:
+                raise ValueError("Expected more than 1 value per channel when training, got input size "
+                                 + str(list(x.shape)))
+            mean, rstd, var = _stats(x, G, P, Cc, eps, False, want_var=True)
+            if running_mean is not None:
+                L.call("affgw_bn_update_running", running_mean.data_ptr(), running_var.data_ptr(), L.ptr(nbt),
+                       mean.data_ptr(), var.data_ptr(), Cc, float(momentum), L.stream())
+        else:
+            mean = torch.empty(Cc, dtype=torch.float32, device=x.device)
+            rstd = torch.empty(Cc, dtype=torch.float32, device=x.device)
+            L.call("affgw_bn_eval_stats", running_mean.data_ptr(), running_var.data_ptr(), mean.data_ptr(),
+                   rstd.data_ptr(), Cc, float(eps), L.stream())
+        w32, b32 = weight.detach(), bias.detach()
+        y = torch.empty_like(x)
+        L.call("affgw_norm_apply", x.data_ptr(), L.dt(x), mean.data_ptr(), rstd.data_ptr(), w32.data_ptr(), b32.data_ptr(),
+               None, y.data_ptr(), G, P, Cc, L.ACT[act], 0, L.stream())
+        ctx.act, ctx.training = act, training
+        ctx.save_for_backward(x, mean, rstd, weight, bias)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, mean, rstd, weight, bias = ctx.saved_tensors
+        G, P, Cc = _gpc(x, False)
+        dy = _dense_cl(dy, x.dtype)
+        s1 = torch.empty(Cc, dtype=torch.float32, device=x.device)
+        s2 = torch.empty(Cc, dtype=torch.float32, device=x.device)
+        dx = torch.empty_like(x)
+        L.call("affgw_norm_bwd", dy.data_ptr(), x.data_ptr(), L.dt(x), mean.data_ptr(), rstd.data_ptr(),
+               weight.detach().data_ptr(), bias.detach().data_ptr(), s1.data_ptr(), s2.data_ptr(), dx.data_ptr(), G, P, Cc,
+               L.ACT[ctx.act], 0, int(ctx.training), 0, L.stream())
+        return dx, s2, s1, None, None, None, None, None
+
+
+def batch_norm(x, bn, act="none"):
+    """`bn` is an nn.BatchNorm{1,2}d used purely as the parameter / buffer container (state_dict keys)."""
+    use_batch = bn.training or bn.running_mean is None
+    bufs = (bn.running_mean if bn.training else bn.running_mean, bn.running_var, bn.num_batches_tracked)
+    return _BatchNorm.apply(x, bn.weight, bn.bias, bufs, use_batch, bn.momentum, bn.eps, act)
+
+
+# ------------------------------------------------------------------------------------------------ pooling / resize
+class _MaxPool2(Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = _dense_cl(x)
+        n, c, h, w = x.shape
+        y = empty_cl(n, c, h // 2, w // 2, x.dtype, x.device)
+        L.call("affgw_maxpool2_fwd", x.data_ptr(), y.data_ptr(), L.dt(x), n, h, w, c, L.stream())
+        ctx.save_for_backward(x)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        n, c, h, w = x.shape
+        dy = _dense_cl(dy, x.dtype)
+        dx = torch.empty_like(x)
+        L.call("affgw_maxpool2_bwd", dy.data_ptr(), x.data_ptr(), dx.data_ptr(), L.dt(x), n, h, w, c, L.stream())
+        return dx
+
+
+def max_pool2(x):
+    return _MaxPool2.apply(x)
+
+
+class _AvgPool3s2Reflect(Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = _dense_cl(x)
+        n, c, h, w = x.shape
+        y = empty_cl(n, c, (h - 1) // 2 + 1, (w - 1) // 2 + 1, x.dtype, x.device)
+        L.call("affgw_avgpool3s2_fwd", x.data_ptr(), y.data_ptr(), L.dt(x), n, h, w, c, L.stream())
+        ctx.shape = (n, c, h, w)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        n, c, h, w = ctx.shape
+        dy = _dense_cl(dy)
+        dx = empty_cl(n, c, h, w, dy.dtype, dy.device)
+        L.call("affgw_avgpool3s2_bwd", dy.data_ptr(), dx.data_ptr(), L.dt(dy), n, h, w, c, L.stream())
+        return dx
+
+
+def avg_pool3s2_reflect(x):
+    """nn.ReflectionPad2d(1) + nn.AvgPool2d(3, 2) (modules_tro.py:133-134)."""
+    return _AvgPool3s2Reflect.apply(x)
+
+
+class _ResizeNearest(Function):
+    @staticmethod
+    def forward(ctx, x, ho, wo):
+        x = _dense_cl(x)
+        n, c, h, w = x.shape
+        y = empty_cl(n, c, ho, wo, x.dtype, x.device)
+        L.call("affgw_resize_nearest_fwd", x.data_ptr(), y.data_ptr(), L.dt(x), n, h, w, c, ho, wo, L.stream())
+        ctx.shape = (n, c, h, w, ho, wo)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        n, c, h, w, ho, wo = ctx.shape
+        dy = _dense_cl(dy)
+        dx = empty_cl(n, c, h, w, dy.dtype, dy.device)
+        L.call("affgw_resize_nearest_bwd", dy.data_ptr(), dx.data_ptr(), L.dt(dy), n, h, w, c, ho, wo, L.stream())
+        return dx, None, None
+
+
+def resize_nearest(x, ho, wo):
+    if x.shape[2] == ho and x.shape[3] == wo:
+        return x
+    return _ResizeNearest.apply(x, ho, wo)
+
+
+# ------------------------------------------------------------------------------------------------ iAFF pieces
+class _Gate(Function):
+    @staticmethod
+    def forward(ctx, x, r, xl, xg):
+        x, r, xl = _dense_cl(x), _dense_cl(r, x.dtype), _dense_cl(xl, x.dtype)
+        xg = _dense_cl(xg, x.dtype)
+        n, c, h, w = x.shape
+        y = torch.empty_like(x)
+        L.call("affgw_gate_fwd", x.data_ptr(), r.data_ptr(), xl.data_ptr(), xg.data_ptr(), y.data_ptr(), L.dt(x), n, h * w, c,
+               L.stream())
+        ctx.save_for_backward(x, r, xl, xg)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, r, xl, xg = ctx.saved_tensors
+        n, c, h, w = x.shape
+        dy = _dense_cl(dy, x.dtype)
+        dx, dr, dxl, dxg = torch.empty_like(x), torch.empty_like(x), torch.empty_like(x), torch.empty_like(xg)
+        L.call("affgw_gate_bwd", dy.data_ptr(), x.data_ptr(), r.data_ptr(), xl.data_ptr(), xg.data_ptr(), dx.data_ptr(),
+               dr.data_ptr(), dxl.data_ptr(), dxg.data_ptr(), L.dt(x), n, h * w, c, L.stream())
+        return dx, dr, dxl, dxg
+
+
+def iaff_gate(x, r, xl, xg):
+    """x * w + r * (1 - w), w = sigmoid(xl + xg)  (blocks.py:289-292, 296-298)."""
+    return _Gate.apply(x, r, xl, xg)
+
+
+class _Gap(Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = _dense_cl(x)
+        n, c, h, w = x.shape
+        y = empty_cl(n, c, 1, 1, x.dtype, x.device)
+        L.call("affgw_gap_fwd", x.data_ptr(), y.data_ptr(), L.dt(x), n, h * w, c, L.stream())
+        ctx.shape = (n, c, h, w)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        n, c, h, w = ctx.shape
+        dy = _dense_cl(dy)
+        dx = empty_cl(n, c, h, w, dy.dtype, dy.device)
+        L.call("affgw_bcast_add", None, dy.data_ptr(), dx.data_ptr(), L.dt(dy), n, h * w, c, 1.0 / (h * w), L.stream())
+        return dx
+
+
+def global_avg_pool(x):
+    return _Gap.apply(x)
+
+
+class _Add(Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        a = _dense_cl(a)
+        b = _dense_cl(b, a.dtype)
+        y = torch.empty_like(a)
+        L.call("affgw_add2", a.data_ptr(), b.data_ptr(), y.data_ptr(), L.dt(a), a.numel(), L.stream())
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        return dy, dy
+
+
+def add(a, b):
+    return _Add.apply(a, b)
+
+
+# ------------------------------------------------------------------------------------------------ text encoder pieces
+class _Embedding(Function):
+    @staticmethod
+    def forward(ctx, ids, table, dtype):
+        L.require_cuda(ids, table)
+        if ids.dtype != torch.int64:
+            raise RuntimeError("embedding: token ids must be int64")
+        ids = ids.contiguous()
+        v, e = table.shape
+        out = torch.empty(ids.shape + (e,), dtype=dtype, device=ids.device)
+        L.call("affgw_embedding_fwd", ids.data_ptr(), table.detach().data_ptr(), out.data_ptr(), L.dt(out), ids.numel(), e, v,
+               _err_tensor(ids.device).data_ptr(), L.stream())
+        ctx.save_for_backward(ids)
+        ctx.shape = (v, e)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (ids,) = ctx.saved_tensors
+        v, e = ctx.shape
+        dout = dout.contiguous()
+        dt = torch.zeros((v, e), dtype=torch.float32, device=dout.device)
+        L.call("affgw_embedding_bwd", ids.data_ptr(), dout.data_ptr(), dt.data_ptr(), L.dt(dout), ids.numel(), e, v, L.stream())
+        return None, dt, None
+
+
+def embedding(ids, table, dtype=None):
+    return _Embedding.apply(ids, table, dtype or act_dtype())
+
+
+class _TextTile(Function):
+    @staticmethod
+    def forward(ctx, chars, h, w, reps):
+        chars = chars.contiguous()
+        b, slots, c = chars.shape
+        out = empty_cl(b, c, h, w, chars.dtype, chars.device)
+        L.call("affgw_text_tile_fwd", chars.data_ptr(), out.data_ptr(), L.dt(chars), b, h, w, c, slots - 1, reps, L.stream())
+        ctx.args = (b, slots, c, h, w, reps)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        b, slots, c, h, w, reps = ctx.args
+        dout = _dense_cl(dout)
+        dch = torch.empty((b, slots, c), dtype=dout.dtype, device=dout.device)
+        L.call("affgw_text_tile_bwd", dout.data_ptr(), dch.data_ptr(), L.dt(dout), b, h, w, c, slots - 1, reps, L.stream())
+        return dch, None, None, None
+
+
+def text_tile(chars, h, w, reps):
+    """chars [B, ts+1, C] (last slot = PAD) -> content map [B, C, h, w]  (modules_tro.py:295-317)."""
+    return _TextTile.apply(chars, h, w, reps)
+
+
+# ------------------------------------------------------------------------------------------------ losses
+class _BceLogits(Function):
+    @staticmethod
+    def forward(ctx, x, target):
+        x = x.contiguous()
+        loss = torch.empty((), dtype=torch.float32, device=x.device)
+        L.call("affgw_bce_logits_fwd", x.data_ptr(), L.dt(x), float(target), loss.data_ptr(), x.numel(), L.stream())
+        ctx.save_for_backward(x)
+        ctx.target = float(target)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        g = g.float().contiguous()
+        dx = torch.empty_like(x)
+        L.call("affgw_bce_logits_bwd", x.data_ptr(), L.dt(x), ctx.target, g.data_ptr(), dx.data_ptr(), x.numel(), L.stream())
+        return dx, None
+
+
+def bce_with_logits_const(x, target):
+    """nn.BCEWithLogitsLoss against an all-`target` label tensor (modules_tro.py:152-168)."""
+    return _BceLogits.apply(x, target)
+
+
+class _SoftmaxCe(Function):
+    @staticmethod
+    def forward(ctx, x, y):
+        x = x.contiguous()
+        if y.dtype != torch.int64:
+            raise RuntimeError("cross_entropy: class indices must be int64")
+        y = y.contiguous()
+        b, c = x.shape
+        loss = torch.empty((), dtype=torch.float32, device=x.device)
+        L.call("affgw_softmax_ce_fwd", x.data_ptr(), L.dt(x), y.data_ptr(), loss.data_ptr(), b, c,
+               _err_tensor(x.device).data_ptr(), L.stream())
+        ctx.save_for_backward(x, y)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        x, y = ctx.saved_tensors
+        b, c = x.shape
+        g = g.float().contiguous()
+        dx = torch.empty_like(x)
+        L.call("affgw_softmax_ce_bwd", x.data_ptr(), L.dt(x), y.data_ptr(), g.data_ptr(), dx.data_ptr(), b, c, L.stream())
+        return dx, None
+
+
+def cross_entropy(x, y):
+    return _SoftmaxCe.apply(x, y)

@@ -1,0 +1,156 @@
+/* libaffgw — C ABI of the B200-native (sm_100a) generator / discriminator hot path of AFFGanWriting.
+ *
+ * The reference has no FFI layer of its own (it is pure PyTorch); the interface these entry points
+ * replace is the set of library calls made by the reference's Python classes.  Each function cites the reference
+ * call site (paths relative to /root/reference/GAN_word/) whose arithmetic it takes over.
+ *
+ * Conventions
+ *   - plain pointers + sizes, no torch types.  All pointers are DEVICE pointers unless stated otherwise.
+ *   - activations are NHWC (channels contiguous); dtype codes: 0 = fp32, 1 = bf16.  Math is fp32 everywhere;
+ *     bf16 tensors feed tcgen05 tensor-core MMAs with fp32 (TMEM) accumulation.
+ *   - the caller owns every buffer, including workspaces; the library never allocates or retains pointers.
+ *   - `stream` is a cudaStream_t passed as void*.  Calls are asynchronous on that stream.
+ *   - return 0 on success, negative on failure; affgw_last_error() returns a thread-local message.
+ *   - there is no CPU fallback: a missing device or a failed launch is an error.
+ */
+#ifndef AFFGW_H
+#define AFFGW_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AFFGW_VERSION 100
+
+enum { AFFGW_DT_F32 = 0, AFFGW_DT_BF16 = 1 };
+enum { AFFGW_ACT_NONE = 0, AFFGW_ACT_RELU = 1, AFFGW_ACT_LRELU = 2, AFFGW_ACT_TANH = 3 };
+enum { AFFGW_PAD_ZERO = 0, AFFGW_PAD_REFLECT = 1, AFFGW_PAD_REPLICATE = 2 };
+enum { AFFGW_ALGO_AUTO = 0, AFFGW_ALGO_SIMT = 1, AFFGW_ALGO_TCGEN05 = 2 };
+
+/* One convolution = pad -> conv -> (+bias) -> (+addend) -> activation, i.e. the conv part of Conv2dBlock.forward
+ * (blocks.py:150-163) with the explicit pad module (blocks.py:113-121), nn.Upsample(scale_factor=2)
+ * (modules_tro.py:594) and the activation_first LeakyReLU (blocks.py:151-153) folded into the operand gather. */
+typedef struct affgw_conv_desc {
+    int32_t N, H, W, Cin;        /* stored input [N,H,W,Cin] (before upsampling)                               */
+    int32_t Cout, KH, KW;
+    int32_t stride, pad;         /* pad applies to the (upsampled) input                                      */
+    int32_t pad_mode;            /* AFFGW_PAD_*                                                               */
+    int32_t upsample;            /* 1, or 2 = nearest x2 before padding                                       */
+    int32_t Ho, Wo;              /* output extent                                                             */
+    int32_t in_pitch, out_pitch; /* elements between consecutive pixels of x / y (>= Cin / Cout)              */
+    int32_t pre_act;             /* activation applied to x while gathering (activation_first blocks)         */
+    int32_t post_act;            /* activation applied to the result                                          */
+    int32_t x_dtype, w_dtype, y_dtype;
+    int32_t algo;                /* AFFGW_ALGO_*                                                              */
+} affgw_conv_desc;
+
+int affgw_version(void);
+const char* affgw_last_error(void);
+/* number of kernels this library has launched in the calling process (bench.py's gpu_launches) */
+long long affgw_launch_count(void);
+/* 1 if the device under the current context is sm_100 */
+int affgw_device_ok(void);
+
+/* ---- convolution (replaces nn.Conv2d / nn.Linear: blocks.py:148, vgg_tro_channel3_modi.py:47,
+ *      modules_tro.py:222,252-259,272-282) ---------------------------------------------------------------------- */
+/* OIHW fp32 parameter -> [Cout][KH][KW][cin_pad] (transpose_flip = 0) or the dgrad operand
+ * [Cin][KH][KW][cout_pad] with mirrored taps (transpose_flip = 1), in out_dtype. */
+int affgw_pack_weight(const float* w_oihw, void* out, int out_dtype, int Cout, int Cin, int KH, int KW, int i_pad,
+                      int transpose_flip, void* stream);
+/* same, into the 128B-swizzled shared-memory tile image the tcgen05 kernel bulk-copies (bf16) */
+int affgw_pack_weight_tc(const float* w_oihw, void* out, int Cout, int Cin, int KH, int KW, int i_pad, int transpose_flip,
+                         int block_n, void* stream);
+long long affgw_pack_weight_tc_bytes(int Cout, int Cin, int KH, int KW, int i_pad, int transpose_flip, int block_n);
+int affgw_conv_tc_block_n(const affgw_conv_desc* d);    /* tile width the tcgen05 kernel uses for this conv, 0 = n/a */
+int affgw_conv_tc_dgrad_block_n(const affgw_conv_desc* d); /* same for the dgrad of the forward described by d */
+
+int affgw_conv2d_fwd(const void* x, const void* w_packed, const float* bias, const void* addend, void* y,
+                     const affgw_conv_desc* d, void* stream);
+/* gradient w.r.t. x of the forward described by d.  dy:[N,Ho,Wo,Cout] (y_dtype), w_packed_t from
+ * affgw_pack_weight(..., transpose_flip = 1), x only read when pre_act != NONE.  workspace holds the gradient
+ * w.r.t. the padded/upsampled virtual input before it is folded back (reflect halo, x2 nearest). */
+long long affgw_conv2d_dgrad_ws_bytes(const affgw_conv_desc* d);
+int affgw_conv2d_dgrad(const void* dy, const void* w_packed_t, const void* x, void* dx, void* workspace,
+                       const affgw_conv_desc* d, void* stream);
+/* dw (OIHW fp32) += dY^T * gather(x); caller zeroes dw first */
+int affgw_conv2d_wgrad(const void* x, const void* dy, float* dw_oihw, const affgw_conv_desc* d, void* stream);
+/* out[c] += sum_m a[m][c]  (bias gradient); caller zeroes out */
+int affgw_colsum(const void* a, int dtype, float* out, long long M, int C, int pitch, void* stream);
+
+/* ---- normalisation family (replaces nn.InstanceNorm2d vgg_tro_channel3_modi.py:50 / blocks.py:127-128,
+ *      F.batch_norm blocks.py:197-204, nn.BatchNorm2d blocks.py:250-281, nn.BatchNorm1d modules_tro.py:275,278,
+ *      calc_mean_std blocks.py:227-235).  Tensor view: [G][P][C]. ws: 2*G*C floats. --------------------------- */
+int affgw_norm_stats(const void* x, int dtype, float* ws, float* mean, float* rstd, float* var_unbiased, int G, long long P,
+                     int C, float eps, int unbiased, void* stream);
+/* y = act((x-mean)*rstd*gamma + beta) + residual ; gamma/beta may be NULL; affine_per_group: gamma is [G][C] */
+int affgw_norm_apply(const void* x, int dtype, const float* mean, const float* rstd, const float* gamma, const float* beta,
+                     const void* residual, void* y, int G, long long P, int C, int act, int affine_per_group, void* stream);
+/* s1 = dbeta[G][C], s2 = dgamma[G][C] (always written), dx; batch_stats = 0 for fixed (eval) statistics;
+ * unbiased = 1 when the forward statistics used the unbiased variance (get_key) */
+int affgw_norm_bwd(const void* dy, const void* x, int dtype, const float* mean, const float* rstd, const float* gamma,
+                   const float* beta, float* s1, float* s2, void* dx, int G, long long P, int C, int act,
+                   int affine_per_group, int batch_stats, int unbiased, void* stream);
+int affgw_bn_update_running(float* running_mean, float* running_var, long long* num_batches_tracked, const float* mean,
+                            const float* var_unbiased, int C, float momentum, void* stream);
+int affgw_bn_eval_stats(const float* running_mean, const float* running_var, float* mean, float* rstd, int C, float eps,
+                        void* stream);
+
+/* ---- pooling / resize (nn.MaxPool2d vgg…:45, modules_tro.py:224; ReflectionPad2d(1)+AvgPool2d(3,2)
+ *      modules_tro.py:133-134; F.interpolate nearest blocks.py:214) ------------------------------------------ */
+int affgw_maxpool2_fwd(const void* x, void* y, int dtype, int N, int H, int W, int C, void* stream);
+int affgw_maxpool2_bwd(const void* dy, const void* x, void* dx, int dtype, int N, int H, int W, int C, void* stream);
+int affgw_avgpool3s2_fwd(const void* x, void* y, int dtype, int N, int H, int W, int C, void* stream);
+int affgw_avgpool3s2_bwd(const void* dy, void* dx, int dtype, int N, int H, int W, int C, void* stream);
+int affgw_resize_nearest_fwd(const void* x, void* y, int dtype, int N, int H, int W, int C, int Ho, int Wo, void* stream);
+int affgw_resize_nearest_bwd(const void* dy, void* dx, int dtype, int N, int H, int W, int C, int Ho, int Wo, void* stream);
+
+/* ---- iAFF pieces (blocks.py:286-299) ---------------------------------------------------------------------- */
+/* y = x*w + r*(1-w), w = sigmoid(xl + xg[n,c]) */
+int affgw_gate_fwd(const void* x, const void* r, const void* xl, const void* xg, void* y, int dtype, int N, long long P,
+                   int C, void* stream);
+int affgw_gate_bwd(const void* dy, const void* x, const void* r, const void* xl, const void* xg, void* dx, void* dr,
+                   void* dxl, void* dxg, int dtype, int N, long long P, int C, void* stream);
+int affgw_gap_fwd(const void* x, void* out, int dtype, int N, long long P, int C, void* stream);
+/* out[n,p,c] = (a ? a[n,p,c] : 0) + v[n,c]*scale   (GAP backward, broadcast adds) */
+int affgw_bcast_add(const void* a, const void* v, void* out, int dtype, int N, long long P, int C, float scale, void* stream);
+int affgw_add2(const void* a, const void* b, void* out, int dtype, long long n, void* stream);
+/* dz = dy * act'(.) evaluated from the activation output y (Conv2dBlock activation, blocks.py:161-162; tanh modules_tro.py:602) */
+int affgw_act_bwd(const void* dy, const void* y, void* dz, int dtype, long long n, int act, void* stream);
+
+/* ---- text encoder pieces (modules_tro.py:285-317) --------------------------------------------------------- */
+/* err: device int set to 1 on an out-of-range id (label handling is bit-exact or it is an error) */
+int affgw_embedding_fwd(const long long* ids, const float* table, void* out, int dtype, long long n_ids, int E, int V,
+                        int* err, void* stream);
+int affgw_embedding_bwd(const long long* ids, const void* dout, float* dtable, int dtype, long long n_ids, int E, int V,
+                        void* stream);
+/* chars:[B][ts+1][C] (slot ts = PAD embedding) -> out:[B][H][W][C]; column c takes slot c/reps, columns past ts*reps PAD */
+int affgw_text_tile_fwd(const void* chars, void* out, int dtype, int B, int H, int W, int C, int ts, int reps, void* stream);
+int affgw_text_tile_bwd(const void* dout, void* dchars, int dtype, int B, int H, int W, int C, int ts, int reps, void* stream);
+
+/* ---- losses (nn.BCEWithLogitsLoss modules_tro.py:145,152-168; nn.CrossEntropyLoss modules_tro.py:193-201) -- */
+int affgw_bce_logits_fwd(const void* x, int dtype, float target, float* loss, long long n, void* stream);
+int affgw_bce_logits_bwd(const void* x, int dtype, float target, const float* grad_out, void* dx, long long n, void* stream);
+int affgw_softmax_ce_fwd(const void* x, int dtype, const long long* y, float* loss, int B, int C, int* err, void* stream);
+int affgw_softmax_ce_bwd(const void* x, int dtype, const long long* y, const float* grad_out, void* dx, int B, int C,
+                         void* stream);
+
+/* ---- layout / dtype (the boundary: callers hand NCHW fp32 tensors, network_tro.py:30-36) ------------------- */
+int affgw_nchw_to_nhwc(const float* x, void* y, int dtype, int N, int C, long long HW, int c_pad, void* stream);
+int affgw_nhwc_to_nchw(const void* x, float* y, int dtype, int N, int C, long long HW, int c_pad, void* stream);
+int affgw_cast(const void* x, int in_dtype, void* y, int out_dtype, long long n, void* stream);
+/* out[r] = cat(a[r], b[r]) over rows = N*H*W pixels (torch.cat(dim=1) in GenModel_FC.mix, modules_tro.py:256) and its inverse */
+int affgw_concat_channels(const void* a, const void* b, void* out, int dtype, long long rows, int ca, int cb, void* stream);
+int affgw_split_channels(const void* in, void* a, void* b, int dtype, long long rows, int ca, int cb, void* stream);
+
+/* ---- data-parallel gradient exchange (replaces the nn.DataParallel reduce at modules_tro.py:341-346) ------- */
+/* gather n tensors into one contiguous fp32 bucket (and back) so that one NCCL all-reduce covers the bucket;
+ * ptrs / sizes are DEVICE arrays of length n, offsets are element offsets into bucket. scale is applied on unpack. */
+int affgw_bucket_pack(const float* const* ptrs, const long long* sizes, const long long* offsets, int n, float* bucket,
+                      void* stream);
+int affgw_bucket_unpack(float* const* ptrs, const long long* sizes, const long long* offsets, int n, const float* bucket,
+                        float scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AFFGW_H */
