@@ -1,0 +1,36 @@
+"""Make the reference's own scripts use this implementation without editing them.
+
+    import affganwriting_b200.install as inst; inst.install()          # before `import network_tro` / main_run
+
+replaces, inside the reference's already-importable modules `blocks` and `modules_tro`, the classes that sit on the
+accelerated path by their drop-in counterparts, so `network_tro.ConTranModel`, `main_run.py` and the
+`tt.test_single_writer.*` scripts pick them up through their normal `from modules_tro import ...` statements.
+The reference tree must be on sys.path (it is not shipped here); see INTEGRATION.md.
+"""
+import importlib
+import sys
+
+from . import blocks as _blocks
+from . import modules_tro as _modules
+
+BLOCK_NAMES = ("Conv2dBlock", "ResBlock", "ResBlocks", "ActFirstResBlock", "LinearBlock", "AdaptiveInstanceNorm2d", "iAFF",
+               "get_key", "mean_variance_norm")
+MODULE_NAMES = ("GenModel_FC", "DisModel", "WriterClaModel", "TextEncoder_FC", "ImageEncoder", "Decoder", "MLP",
+                "get_num_adain_params")
+
+
+def install(ref_blocks="blocks", ref_modules="modules_tro"):
+    """Patch the reference modules in place. Returns the list of (module, attribute) pairs that were replaced."""
+    done = []
+    rb = sys.modules.get(ref_blocks) or importlib.import_module(ref_blocks)
+    for n in BLOCK_NAMES:
+        if hasattr(rb, n):
+            setattr(rb, n, getattr(_blocks, n))
+            done.append((ref_blocks, n))
+    rm = sys.modules.get(ref_modules) or importlib.import_module(ref_modules)
+    for n in MODULE_NAMES + BLOCK_NAMES:
+        src = _modules if n in MODULE_NAMES else _blocks
+        if hasattr(rm, n):
+            setattr(rm, n, getattr(src, n))
+            done.append((ref_modules, n))
+    return done

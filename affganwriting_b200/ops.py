@@ -14,6 +14,43 @@ from . import _lib as L  # noqa: N812
 
 _state = {"mode": "fp32", "force_simt": False}
 _err_flag = {}
+_profile = {"records": None}
+
+
+def start_kernel_timing():
+    """Begin recording (name, start_event, end_event, algorithmic_flops) for every convolution launch; the events sit
+    on the launching (current) stream.  Used by bench.py for the roofline numbers; off by default."""
+    _profile["records"] = []
+
+
+def stop_kernel_timing():
+    """-> {name: {"launches", "ms", "flops"}} ; synchronises the device once."""
+    recs, _profile["records"] = _profile["records"] or [], None
+    torch.cuda.synchronize()
+    out = {}
+    for name, e0, e1, fl in recs:
+        d = out.setdefault(name, {"launches": 0, "ms": 0.0, "flops": 0.0})
+        d["launches"] += 1
+        d["ms"] += e0.elapsed_time(e1)
+        d["flops"] += fl
+    return out
+
+
+class _timed:
+    def __init__(self, name, flops):
+        self.on = _profile["records"] is not None
+        self.name, self.flops = name, flops
+
+    def __enter__(self):
+        if self.on:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *a):
+        if self.on:
+            self.e1.record()
+            _profile["records"].append((self.name, self.e0, self.e1, self.flops))
 
 
 def set_precision(mode):
@@ -126,6 +163,9 @@ class _ToInternal(Function):
 
     @staticmethod
     def backward(ctx, g):
+        if len(ctx.shape) != 4:
+            g = g.contiguous()
+            return (g if g.dtype == torch.float32 else _cast(g, torch.float32)), None, None
         n, c, h, w = ctx.shape
         g = _dense_cl(g)
         out = torch.empty((n, c, h, w), dtype=torch.float32, device=g.device)
@@ -266,8 +306,10 @@ class _Conv2d(Function):
         if addend is not None:
             addend = _dense_cl(addend, y_dtype)
         b32 = None if bias is None else bias.detach()
-        L.call("affgw_conv2d_fwd", x.data_ptr(), wp.data_ptr(), L.ptr(b32), L.ptr(addend), y.data_ptr(), C.byref(d),
-               L.stream())
+        flops = 2.0 * g["N"] * g["Ho"] * g["Wo"] * g["Cout"] * g["Cin"] * g["KH"] * g["KW"]
+        with _timed("conv_fwd_tcgen05" if bn else "conv_fwd_simt", flops):
+            L.call("affgw_conv2d_fwd", x.data_ptr(), wp.data_ptr(), L.ptr(b32), L.ptr(addend), y.data_ptr(), C.byref(d),
+                   L.stream())
         ctx.cfg, ctx.g = cfg, g
         ctx.has_bias, ctx.has_addend = bias is not None, addend is not None
         ctx.save_for_backward(x, weight, y if cfg.post_act != "none" else None)
@@ -297,7 +339,9 @@ class _Conv2d(Function):
         if need_w:
             dw = torch.zeros(weight.shape, dtype=torch.float32, device=x.device)
             d = _desc(g, fwd_cfg, g["Cin"], x_dt, w_dt, y_dt, L.ALGO_SIMT)
-            L.call("affgw_conv2d_wgrad", x.data_ptr(), dz.data_ptr(), dw.data_ptr(), C.byref(d), st)
+            flops = 2.0 * M * g["Cout"] * g["Cin"] * g["KH"] * g["KW"]
+            with _timed("conv_wgrad_simt", flops):
+                L.call("affgw_conv2d_wgrad", x.data_ptr(), dz.data_ptr(), dw.data_ptr(), C.byref(d), st)
         if need_x:
             if x.dtype != dz.dtype:
                 dz_x = _cast(dz, x.dtype)
@@ -327,8 +371,10 @@ class _Conv2d(Function):
             if ws_bytes < 0:
                 raise RuntimeError("conv2d_dgrad_ws_bytes: " + L.last_error())
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device) if ws_bytes else None
-            L.call("affgw_conv2d_dgrad", dz_x.data_ptr(), wt.data_ptr(), x.data_ptr(), base.data_ptr(), L.ptr(ws),
-                   C.byref(d), st)
+            flops = 2.0 * M * g["Cout"] * cin * g["KH"] * g["KW"]
+            with _timed("conv_dgrad_tcgen05" if bn else "conv_dgrad_simt", flops):
+                L.call("affgw_conv2d_dgrad", dz_x.data_ptr(), wt.data_ptr(), x.data_ptr(), base.data_ptr(), L.ptr(ws),
+                       C.byref(d), st)
         da = dz if (ctx.has_addend and need_a) else None
         return dx, dw, db, da, None
 

@@ -1,0 +1,313 @@
+"""Benchmark of the hot path: one full GAN training iteration (cla_update -> dis_update -> gen_update, forward + backward
++ Adam, no recogniser) at batch 64 per GPU, 50 style planes, 64x216 synthetic IAM-shaped words, bf16 storage with
+tcgen05 tensor-core convolutions (BASELINE.json configs[1]).
+
+    python bench.py --gpus N --steps K --warmup W            # this implementation (torchrun for N > 1)
+    python bench.py --impl reference ...                      # the reference algorithm on the host cores (CPU oracle port)
+
+Prints ONE JSON line on rank 0 (see DESIGN.md "measurement" for every field).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+BATCH_PER_GPU = 64
+NUM_CHANNEL = 50
+STEP_GFLOP_PER_SAMPLE = 389.7        # cla 6.14 + dis_update 108.4 + gen_update 275.2 (no recogniser)
+METRIC = "train_steps_per_sec"
+WORKLOAD = ("configs[1]: full GAN training step (GenModel_FC + DisModel + WriterClaModel fwd/bwd + Adam, no recogniser), "
+            "bf16, batch 64 per GPU, 50 style planes 64x216, synthetic IAM-shaped words")
+
+
+# --------------------------------------------------------------------------------------------------- synthetic data
+def synthetic_batch(batch, num_channel, seed):
+    """The 9-tuple main_run.sort_batch builds (main_run.py:108-118), filled with seeded synthetic data."""
+    from affganwriting_b200 import load_data as ld
+    g = torch.Generator().manual_seed(seed)
+    rng = np.random.RandomState(seed)
+    letters = list(ld.letter2index)
+
+    def imgs(n, c):
+        x = torch.rand(n, c, ld.IMG_HEIGHT, ld.IMG_WIDTH, generator=g) * 2 - 1
+        widths = torch.randint(40, ld.IMG_WIDTH + 1, (n, c), generator=g)
+        cols = torch.arange(ld.IMG_WIDTH).view(1, 1, 1, -1)
+        return torch.where(cols >= widths.view(n, c, 1, 1), torch.full_like(x, -1.0), x), widths
+
+    def labels(shape):
+        flat = []
+        for _ in range(int(np.prod(shape))):
+            ln = rng.randint(1, ld.MAX_CHARS + 1)
+            flat.append(ld.label_padding("".join(letters[i] for i in rng.randint(0, len(letters), ln))))
+        return torch.tensor(flat, dtype=torch.int64).view(*shape, ld.OUTPUT_MAX_LEN)
+
+    tr_img, widths = imgs(batch, num_channel)
+    img_xt, _ = imgs(batch, 1)
+    return (np.zeros(batch, dtype=np.int64),
+            torch.randint(0, ld.NUM_WRITERS, (batch,), generator=g),
+            np.arange(batch),
+            tr_img, widths, labels((batch, num_channel)), img_xt, labels((batch,)), labels((batch,)))
+
+
+def batch_bytes(batch):
+    return int(sum(t.numel() * t.element_size() for t in batch if torch.is_tensor(t)))
+
+
+# --------------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.stop_flag, self.thread = index, [], threading.Event(), None
+
+    def _run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([c.strip() for c in out.strip().split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def __enter__(self):
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop_flag.set()
+        self.thread.join(6)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for r in self.rows:
+            if len(r) < 7:
+                continue
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------------- CPU reference arm
+def cpu_reference_steps(batch, steps, warmup, threads):
+    """The reference's algorithm for the path (CPU oracle port, oracle/affgw_oracle.py: fp32 PyTorch ops on the host
+    cores), one cla+dis+gen update per step at `batch` samples.  Returns seconds per step."""
+    from oracle import affgw_oracle as O
+    from oracle import weights as W
+    torch.set_num_threads(threads)
+    spec = json.load(open(os.path.join(ROOT, "tests", "golden", "state_spec.json")))
+    full = {}
+    for pre, key in (("gen.", "gen_c50"), ("dis.", "dis"), ("cla.", "cla")):
+        for k, v in W.make_state(spec[key]).items():
+            full[pre + k] = v.clone().requires_grad_(v.is_floating_point())
+    data = O.synthetic_batch(batch, NUM_CHANNEL)
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        for p in full.values():
+            p.grad = None
+        O.cla_update(data, full).backward()
+        l_real, l_fake = O.dis_update(data, full)
+        (l_real + l_fake).backward()
+        O.gen_update(data, full)[0].backward()
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    return sum(times) / len(times)
+
+
+def run_reference_arm(args, rank):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    sample_batch = 4
+    sec = cpu_reference_steps(sample_batch, max(1, args.steps), min(args.warmup, 1), threads)
+    value = (sample_batch / sec) / BATCH_PER_GPU
+    sample = (f"{max(1, args.steps)} timed iterations of the CPU oracle port at batch {sample_batch} (fp32, {threads} threads); "
+              f"steps/s = samples/s / {BATCH_PER_GPU}")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 / value, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD, "batch_per_gpu": BATCH_PER_GPU},
+            "cpu_baseline": {"value": value, "unit": "steps/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------- main arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="affgw", choices=["affgw", "reference"])
+    ap.add_argument("--batch", type=int, default=BATCH_PER_GPU)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "affgw" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank)
+        return
+
+    import torch.distributed as dist
+
+    import affganwriting_b200 as A
+    from affganwriting_b200 import _lib, ops
+    from affganwriting_b200.trainer import Trainer
+
+    assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    assert _lib.lib().affgw_device_ok(), _lib.last_error()
+
+    A.set_precision("bf16")
+    torch.manual_seed(0)
+    trainer = Trainer(num_writers=500, device=dev)
+    B = args.batch
+    host = synthetic_batch(B, NUM_CHANNEL, seed=1234 + rank)
+    host = tuple(t.pin_memory() if torch.is_tensor(t) else t for t in host)
+    resident = tuple(t.to(dev) if torch.is_tensor(t) else t for t in host)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        sync_all()
+        return float(ms.item())
+
+    def step_resident():
+        trainer.train_step(resident)
+
+    def step_e2e():
+        dev_batch = tuple(t.to(dev, non_blocking=True) if torch.is_tensor(t) else t for t in host)
+        losses = trainer.train_step(dev_batch)
+        return float(losses["gen"].item()) + float(losses["dis"].item()) + float(losses["cla"].item())
+
+    for _ in range(args.warmup):
+        step_resident()
+    A.check_device_errors()
+
+    # ---- timed region (inputs resident in HBM), with per-launch CUDA-event timing of the convolution kernels
+    with ClockSampler(local_rank) as clocks:
+        n0 = A.launch_count()
+        ops.start_kernel_timing()
+        ms_total = timed(step_resident, args.steps)
+        kern = ops.stop_kernel_timing()
+        launches = A.launch_count() - n0
+    ms_step = ms_total / args.steps
+    value = world / (ms_step / 1e3)                       # whole-job steps/s: every rank completes one step per step time
+
+    # ---- end to end through the public API: pinned host batch -> H2D -> step -> losses read back
+    step_e2e()
+    ms_e2e = timed(step_e2e, args.steps) / args.steps
+    e2e_value = world / (ms_e2e / 1e3)
+
+    # ---- generation throughput (secondary number of BASELINE.json's metric): style encode + decode per image
+    gen = trainer.model.gen
+    with torch.no_grad():
+        for _ in range(2):
+            gen(resident[3], resident[7])
+        ms_gen = timed(lambda: gen(resident[3], resident[7]), 5) / 5
+    gen_img_s = world * B / (ms_gen / 1e3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    tf_peak = peaks.get("bf16_tflops_sustained", 1400.0)
+    peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if peaks else "fallback 1.4 PF sustained"
+    kernels = {}
+    for name, d in kern.items():
+        tf = d["flops"] / (d["ms"] * 1e-3) / 1e12 if d["ms"] > 0 else 0.0
+        kernels[name] = {"launches_per_step": d["launches"] / args.steps, "ms_per_step": d["ms"] / args.steps,
+                         "share_of_step": d["ms"] / ms_total, "tflops": tf, "frac_of_peak": tf / tf_peak}
+    dominant = max(kernels, key=lambda k: kernels[k]["ms_per_step"]) if kernels else None
+    roofline = None
+    if dominant:
+        k = kernels[dominant]
+        roofline = {"kernel": dominant, "bound": "tensor", "achieved": k["tflops"], "peak": tf_peak, "unit": "TFLOP/s",
+                    "frac": k["frac_of_peak"], "traffic": None, "peak_source": peak_src,
+                    "avg_launch_ms": k["ms_per_step"] / max(k["launches_per_step"], 1e-9)}
+
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        sec = cpu_reference_steps(2, 1, 0, threads)
+        v = (2 / sec) / BATCH_PER_GPU
+        cpu_baseline = {"value": v, "unit": "steps/s", "cores": threads, "kind": "port",
+                        "sample": f"1 iteration of the CPU oracle port at batch 2 ({sec:.1f} s, fp32, {threads} threads); "
+                                  f"steps/s = samples/s / {BATCH_PER_GPU}"}
+
+    h2d = batch_bytes(host)
+    line = {
+        "metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
+                   "l2": "inputs larger than L2: 177 MB of style images are re-read every step (L2 is 126 MB)",
+                   "samples_per_sec": value * B},
+        "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 12,
+                "ms_per_step": ms_e2e},
+        "gpu_launches": launches,
+        "clocks": clocks.summary(),
+        "roofline": roofline,
+        "kernels": kernels,
+        "step_tflops": {"algorithmic_tflop_per_step": STEP_GFLOP_PER_SAMPLE * B / 1e3,
+                        "achieved_tflops": STEP_GFLOP_PER_SAMPLE * B / 1e3 / (ms_step / 1e3),
+                        "frac_of_peak": STEP_GFLOP_PER_SAMPLE * B / 1e3 / (ms_step / 1e3) / tf_peak},
+        "cpu_baseline": cpu_baseline,
+        "extra": {"gen_images_per_sec": gen_img_s, "gen_batch_per_gpu": B, "gen_ms_per_batch": ms_gen,
+                  "gen_frac_of_peak": 62.17e-3 * gen_img_s / tf_peak},
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -52,6 +52,43 @@ def text_column_map(width, ts=OUTPUT_MAX_LEN):
 
 
 # ----------------------------------------------------------------------------------------------
+# storage-precision model.  The product's bf16 mode stores every activation, and feeds every convolution / linear
+# operand, in bfloat16 (fp32 accumulation and fp32 statistics); `storage_model("bf16")` makes the oracle round at exactly
+# those points (straight-through in backward) so that a bf16 run can be checked tightly, while the distance between the
+# two oracle modes measures what bf16 storage itself costs on this network.
+# ----------------------------------------------------------------------------------------------
+_MODEL = {"bf16": False}
+
+
+class storage_model:
+    def __init__(self, kind):
+        assert kind in ("fp32", "bf16")
+        self.kind = kind
+
+    def __enter__(self):
+        self.prev = _MODEL["bf16"]
+        _MODEL["bf16"] = self.kind == "bf16"
+
+    def __exit__(self, *a):
+        _MODEL["bf16"] = self.prev
+
+
+def q(t):
+    """Round to the storage dtype of the active model (identity in fp32), gradient passes straight through."""
+    if not _MODEL["bf16"] or not t.is_floating_point():
+        return t
+    return t + (t.detach().bfloat16().float() - t.detach())
+
+
+def _conv(x, w, b=None, **kw):
+    return F.conv2d(x, q(w), b, **kw)
+
+
+def _linear(x, w, b=None):
+    return F.linear(x, q(w), b)
+
+
+# ----------------------------------------------------------------------------------------------
 # helpers
 # ----------------------------------------------------------------------------------------------
 def _sub(sd, prefix):
@@ -116,21 +153,27 @@ def batch_norm(x, sd, prefix, training, stats=None, momentum=0.1, eps=1e-5):
 # blocks.py
 # ----------------------------------------------------------------------------------------------
 def conv2d_block(x, sd, prefix, ks, st, padding=0, norm="none", activation="relu", pad_type="zero",
-                 activation_first=False, adain=None):
+                 activation_first=False, adain=None, residual=None, addend=None, store=True):
     """blocks.py:150-163.  `adain` = dict(weight, bias, input, training, stats) when norm == 'adain'."""
     w = sd[prefix + "conv.weight"]
     b = sd.get(prefix + "conv.bias")
     if activation_first:
         x = _act(x, activation)
-    x = F.conv2d(_pad(x, padding, pad_type), w, b, stride=st)
+    x = _conv(_pad(x, padding, pad_type), w, b, stride=st)
+    if addend is not None:
+        x = x + addend
+    post = "none" if activation_first else activation
     if norm == "in":
-        x = instance_norm(x)
+        x = q(_act(instance_norm(q(x)), post))
     elif norm == "adain":
-        x = adaptive_instance_norm(x, sd, prefix + "norm.", **adain)
+        x = adaptive_instance_norm(q(x), sd, prefix + "norm.", act=post, residual=residual, **adain)
+        residual = None
     else:
         assert norm == "none", norm
-    if not activation_first:
-        x = _act(x, activation)
+        x = _act(x, post)
+        x = q(x) if store else x
+    if residual is not None:
+        x = q(x + residual)
     return x
 
 
@@ -146,47 +189,48 @@ def get_key(feats, feat):
     h, w = feats.shape[2:]
     r = F.interpolate(feat, (h, w))
     m, s = calc_mean_std(r)
-    return (r - m) / s
+    return q((r - m) / s)
 
 
 def _att_branch(x, sd, prefix, training, stats, glob):
     """blocks.py:246-281 — (GAP) conv1x1 C->C/4, BN, ReLU, conv1x1 C/4->C, BN."""
     o = 1 if glob else 0
     if glob:
-        x = x.mean(dim=(2, 3), keepdim=True)
-    x = F.conv2d(x, sd[f"{prefix}{o}.weight"], sd[f"{prefix}{o}.bias"])
-    x = torch.relu(batch_norm(x, sd, f"{prefix}{o + 1}.", training, stats))
-    x = F.conv2d(x, sd[f"{prefix}{o + 3}.weight"], sd[f"{prefix}{o + 3}.bias"])
-    return batch_norm(x, sd, f"{prefix}{o + 4}.", training, stats)
+        x = q(x.mean(dim=(2, 3), keepdim=True))
+    x = q(_conv(x, sd[f"{prefix}{o}.weight"], sd[f"{prefix}{o}.bias"]))
+    x = q(torch.relu(batch_norm(x, sd, f"{prefix}{o + 1}.", training, stats)))
+    x = q(_conv(x, sd[f"{prefix}{o + 3}.weight"], sd[f"{prefix}{o + 3}.bias"]))
+    return q(batch_norm(x, sd, f"{prefix}{o + 4}.", training, stats))
 
 
 def iaff(x, residual, sd, prefix, training=True, stats=None):
     """blocks.py:286-299.  Round two reuses global_att, not global_att2 (line 295)."""
-    xa = x + residual
+    xa = q(x + residual)
     xl = _att_branch(xa, sd, prefix + "local_att.", training, stats, False)
     xg = _att_branch(xa, sd, prefix + "global_att.", training, stats, True)
     wei = torch.sigmoid(xl + xg)
-    xi = x * wei + residual * (1 - wei)
+    xi = q(x * wei + residual * (1 - wei))
     xl2 = _att_branch(xi, sd, prefix + "local_att2.", training, stats, False)
     xg2 = _att_branch(xi, sd, prefix + "global_att.", training, stats, True)
     wei2 = torch.sigmoid(xl2 + xg2)
-    return x * wei2 + residual * (1 - wei2)
+    return q(x * wei2 + residual * (1 - wei2))
 
 
-def adaptive_instance_norm(x, sd, prefix, weight, bias, input=None, training=True, stats=None, eps=1e-5):
+def adaptive_instance_norm(x, sd, prefix, weight, bias, input=None, training=True, stats=None, eps=1e-5, act="none",
+                           residual=None):
     """blocks.py:188-204.  Instance statistics always (F.batch_norm(..., training=True)), biased variance;
     weight/bias are per-(n, c) activations of length B*C."""
     if input is not None:
         x = iaff(x, get_key(x, input), sd, prefix + "iAff.", training, stats)
     b, c = x.shape[:2]
-    return instance_norm(x, eps) * weight.view(b, c, 1, 1) + bias.view(b, c, 1, 1)
+    y = _act(instance_norm(x, eps) * weight.view(b, c, 1, 1) + bias.view(b, c, 1, 1), act)
+    return q(y if residual is None else y + residual)
 
 
 def res_block(x, sd, prefix, norm, activation, pad_type, adain0=None, adain1=None):
     """blocks.py:21-39."""
     y = conv2d_block(x, sd, prefix + "model.0.", 3, 1, 1, norm, activation, pad_type, adain=adain0)
-    y = conv2d_block(y, sd, prefix + "model.1.", 3, 1, 1, norm, "none", pad_type, adain=adain1)
-    return y + x
+    return conv2d_block(y, sd, prefix + "model.1.", 3, 1, 1, norm, "none", pad_type, adain=adain1, residual=x)
 
 
 def act_first_res_block(x, sd, prefix, fin, fout):
@@ -195,18 +239,17 @@ def act_first_res_block(x, sd, prefix, fin, fout):
     if fin != fout:
         xs = conv2d_block(x, sd, prefix + "conv_s.", 1, 1, activation="none")
     dx = conv2d_block(x, sd, prefix + "conv_0.", 3, 1, 1, "none", "lrelu", "reflect", activation_first=True)
-    dx = conv2d_block(dx, sd, prefix + "conv_1.", 3, 1, 1, "none", "lrelu", "reflect", activation_first=True)
-    return xs + dx
+    return conv2d_block(dx, sd, prefix + "conv_1.", 3, 1, 1, "none", "lrelu", "reflect", activation_first=True, addend=xs)
 
 
 def linear_block(x, sd, prefix, norm="none", activation="relu", training=True, stats=None):
     """blocks.py:68-103."""
-    x = F.linear(x, sd[prefix + "fc.weight"], sd[prefix + "fc.bias"])
+    x = _linear(x, sd[prefix + "fc.weight"], sd[prefix + "fc.bias"])
     if norm == "bn":
-        x = batch_norm(x, sd, prefix + "norm.", training, stats)
+        x = batch_norm(q(x), sd, prefix + "norm.", training, stats)
     elif norm == "in":
         x = F.instance_norm(x.unsqueeze(0)).squeeze(0) if x.dim() == 2 else F.instance_norm(x)
-    return _act(x, activation)
+    return q(_act(x, activation))
 
 
 def mlp(x, sd, prefix, n_blk=3, norm="none", activ="relu", training=True, stats=None):
@@ -240,14 +283,15 @@ def vgg_layers():
 def image_encoder(x, sd, prefix="enc_image."):
     """modules_tro.py:360-374 — six intermediate maps at the slice ends 3/9/16/29/42/end."""
     outs = []
+    x = q(x)
     for kind, idx, _ in vgg_layers():
         if kind == "conv":
-            x = F.conv2d(x, sd[f"{prefix}model.features.{idx}.weight"], sd[f"{prefix}model.features.{idx}.bias"],
-                         padding=1)
+            x = q(_conv(x, sd[f"{prefix}model.features.{idx}.weight"], sd[f"{prefix}model.features.{idx}.bias"],
+                        padding=1))
         elif kind == "in":
             x = instance_norm(x)
         elif kind == "relu":
-            x = torch.relu(x)
+            x = q(torch.relu(x))
         else:
             x = F.max_pool2d(x, 2, 2)
         if idx + 1 in VGG_SLICE_ENDS:
@@ -260,16 +304,16 @@ def image_encoder(x, sd, prefix="enc_image."):
 # ----------------------------------------------------------------------------------------------
 def text_encoder(label, f_xs_shape, sd, prefix="enc_text.", training=True, stats=None):
     """modules_tro.py:285-317 -> (adain params [B,4096], content map [B,512,h,w])."""
-    emb = sd[prefix + "embed.weight"][label]                           # b, t, 64
+    emb = q(sd[prefix + "embed.weight"][label])                        # b, t, 64
     b, ts = emb.shape[:2]
-    h = F.linear(emb.reshape(b, -1), sd[prefix + "fc.0.weight"], sd[prefix + "fc.0.bias"])
-    h = torch.relu(batch_norm(h, sd, prefix + "fc.1.", training, stats))
-    h = F.linear(h, sd[prefix + "fc.3.weight"], sd[prefix + "fc.3.bias"])
-    h = torch.relu(batch_norm(h, sd, prefix + "fc.4.", training, stats))
-    out = F.linear(h, sd[prefix + "fc.6.weight"], sd[prefix + "fc.6.bias"])
-    chars = F.linear(emb, sd[prefix + "linear.weight"], sd[prefix + "linear.bias"])   # b, t, 512
-    pad = F.linear(sd[prefix + "embed.weight"][TOKENS["PAD_TOKEN"]], sd[prefix + "linear.weight"],
-                   sd[prefix + "linear.bias"])
+    h = q(_linear(emb.reshape(b, -1), sd[prefix + "fc.0.weight"], sd[prefix + "fc.0.bias"]))
+    h = q(torch.relu(batch_norm(h, sd, prefix + "fc.1.", training, stats)))
+    h = q(_linear(h, sd[prefix + "fc.3.weight"], sd[prefix + "fc.3.bias"]))
+    h = q(torch.relu(batch_norm(h, sd, prefix + "fc.4.", training, stats)))
+    out = _linear(h, sd[prefix + "fc.6.weight"], sd[prefix + "fc.6.bias"])          # AdaIN parameters stay fp32
+    chars = q(_linear(emb, sd[prefix + "linear.weight"], sd[prefix + "linear.bias"]))  # b, t, 512
+    pad = q(_linear(q(sd[prefix + "embed.weight"][TOKENS["PAD_TOKEN"]]), sd[prefix + "linear.weight"],
+                    sd[prefix + "linear.bias"]))
     cols = [chars[:, c] if c >= 0 else pad.unsqueeze(0).expand(b, -1) for c in text_column_map(f_xs_shape[-1], ts)]
     row = torch.stack(cols, dim=2)                                     # b, 512, w
     return out, row.unsqueeze(2).expand(-1, -1, f_xs_shape[-2], -1).contiguous()
@@ -278,7 +322,7 @@ def text_encoder(label, f_xs_shape, sd, prefix="enc_text.", training=True, stats
 def mix(results, feat_embed, sd, prefix=""):
     """modules_tro.py:252-259 — per-pixel Linear(1024, 512) over cat(style, content)."""
     f = torch.cat([results[-1], feat_embed], dim=1).permute(0, 2, 3, 1)
-    return F.linear(f, sd[prefix + "linear_mix.weight"], sd[prefix + "linear_mix.bias"]).permute(0, 3, 1, 2)
+    return q(_linear(f, sd[prefix + "linear_mix.weight"], sd[prefix + "linear_mix.bias"])).permute(0, 3, 1, 2)
 
 
 def decoder(content, results, adain_params, sd, prefix="dec.", training=True, stats=None, max_pooled3=None):
@@ -298,7 +342,7 @@ def decoder(content, results, adain_params, sd, prefix="dec.", training=True, st
     for i, idx in enumerate((2, 4, 6)):
         x = F.interpolate(x, scale_factor=2)
         x = conv2d_block(x, sd, f"{prefix}model.{idx}.", 5, 1, 2, "in", "relu", "reflect")
-    return conv2d_block(x, sd, f"{prefix}model.7.", 7, 1, 3, "none", "tanh", "reflect")
+    return conv2d_block(x, sd, f"{prefix}model.7.", 7, 1, 3, "none", "tanh", "reflect", store=False)   # fp32 image
 
 
 def gen_forward(tr_img, label, sd, prefix="", training=True, stats=None, results=None):
@@ -327,14 +371,14 @@ def dis_cla_plan(n_layers=6):
 
 
 def dis_features(x, sd, prefix=""):
-    x = conv2d_block(x, sd, prefix + "cnn_f.0.", 7, 1, 3, "none", "none", "reflect")
+    x = conv2d_block(q(x), sd, prefix + "cnn_f.0.", 7, 1, 3, "none", "none", "reflect")
     for kind, idx, fin, fout in dis_cla_plan():
         if kind == "res":
             x = act_first_res_block(x, sd, f"{prefix}cnn_f.{idx}.", fin, fout)
         else:
-            x = F.avg_pool2d(F.pad(x, (1, 1, 1, 1), mode="reflect"), 3, 2)
-    # head: kernel IMG_HEIGHT//32 = 2, stride IMG_WIDTH//32+1 = 7, lrelu first (modules_tro.py:139-142)
-    x = conv2d_block(x, sd, prefix + "cnn_c.0.", 2, 7, 0, "none", "lrelu", "zero", activation_first=True)
+            x = q(F.avg_pool2d(F.pad(x, (1, 1, 1, 1), mode="reflect"), 3, 2))
+    # head: kernel IMG_HEIGHT//32 = 2, stride IMG_WIDTH//32+1 = 7, lrelu first (modules_tro.py:139-142); fp32 logits
+    x = conv2d_block(x, sd, prefix + "cnn_c.0.", 2, 7, 0, "none", "lrelu", "zero", activation_first=True, store=False)
     return x.squeeze(-1).squeeze(-1)
 
 

@@ -15,24 +15,29 @@ def _rs(key, seed):
 
 
 def make_tensor(key, shape, seed=0):
+    """Scales follow the reference's initialisers so that the test network behaves like a freshly constructed one:
+    nn.Conv2d / nn.Linear default (uniform +-1/sqrt(fan_in) for weight and bias), kaiming_normal(fan_out) with zero-ish
+    bias for the VGG encoder (vgg_tro_channel3_modi.py:29-37), N(0, 1) embeddings."""
     rs = _rs(key, seed)
     shape = tuple(int(s) for s in shape)
     leaf = key.rsplit(".", 1)[-1]
+    f32 = np.float32
     if leaf == "num_batches_tracked":
         return torch.zeros(shape, dtype=torch.int64)
     if leaf == "running_mean":
-        return torch.from_numpy((0.1 * rs.standard_normal(shape)).astype(np.float32))
+        return torch.from_numpy((0.1 * rs.standard_normal(shape)).astype(f32))
     if leaf == "running_var":
-        return torch.from_numpy((1.0 + 0.1 * np.abs(rs.standard_normal(shape))).astype(np.float32))
+        return torch.from_numpy((1.0 + 0.1 * np.abs(rs.standard_normal(shape))).astype(f32))
     if len(shape) >= 2:
         if "embed" in key:
-            std = 1.0
-        else:
-            fan_in = int(np.prod(shape[1:]))
-            std = (2.0 / fan_in) ** 0.5
-        return torch.from_numpy((std * rs.standard_normal(shape)).astype(np.float32))
-    # 1-D: batch-norm scale (".1.weight"-style keys sit next to a running_mean) is decided by the caller
-    return torch.from_numpy((0.1 * rs.standard_normal(shape)).astype(np.float32))
+            return torch.from_numpy(rs.standard_normal(shape).astype(f32))
+        if "enc_image" in key:
+            fan_out = shape[0] * int(np.prod(shape[2:]))
+            return torch.from_numpy(((2.0 / fan_out) ** 0.5 * rs.standard_normal(shape)).astype(f32))
+        bound = 1.0 / int(np.prod(shape[1:])) ** 0.5
+        return torch.from_numpy(rs.uniform(-bound, bound, shape).astype(f32))
+    # 1-D tensors: biases and norm scales (the caller shifts norm scales to be centred on 1)
+    return torch.from_numpy((0.05 * rs.standard_normal(shape)).astype(f32))
 
 
 def make_state(spec, seed=0):

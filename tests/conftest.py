@@ -7,8 +7,9 @@ import pytest
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-if ROOT not in sys.path:
-    sys.path.insert(0, ROOT)
+for _p in (ROOT, os.path.join(ROOT, "tests")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 
@@ -45,13 +46,3 @@ def mode(request):
     A.force_simt(False)
     yield request.param
     A.set_precision("fp32")
-
-
-def rel_err(a, b):
-    a, b = a.detach().float().cpu(), b.detach().float().cpu()
-    return float((a - b).abs().max() / max(1.0, float(b.abs().max())))
-
-
-def cosine(a, b):
-    a, b = a.detach().double().reshape(-1).cpu(), b.detach().double().reshape(-1).cpu()
-    return float((a @ b) / (a.norm() * b.norm() + 1e-30))

@@ -6,7 +6,7 @@ import torch
 
 import affganwriting_b200 as A
 from affganwriting_b200 import ops
-from tests.conftest import rel_err
+from affgw_testutil import rel_err
 
 pytestmark = pytest.mark.gpu
 
@@ -42,7 +42,7 @@ def test_tc_matches_simt(case):
             y.float().backward(gy)
             outs[simt] = (y.detach().float(), x.grad.detach().float())
         assert rel_err(outs[False][0], outs[True][0]) <= 1e-2
-        assert rel_err(outs[False][1], outs[True][1]) <= 2e-2
+        assert rel_err(outs[False][1], outs[True][1]) <= 3e-2     # dgrad through a bf16 padded-gradient buffer
         # and against an fp32 torch convolution of the same (bf16-rounded) operands
         xr = x.detach().float()
         if up == 2:
@@ -69,3 +69,47 @@ def test_tc_path_is_taken():
     assert L.lib().affgw_conv_tc_block_n(ctypes.byref(d)) == 64
     d.Cin, d.in_pitch = 50, 50
     assert L.lib().affgw_conv_tc_block_n(ctypes.byref(d)) == 0
+
+
+BLOCKS = [
+    # in, out, k, pad, norm, act, pad_type, H, W
+    (128, 128, 3, 1, "in", "relu", "reflect", 8, 27),
+    (64, 64, 3, 1, "in", "relu", "zero", 16, 54),
+    (256, 128, 5, 2, "in", "relu", "reflect", 8, 27),
+    (128, 64, 1, 0, "none", "none", "zero", 8, 27),
+]
+
+
+@pytest.mark.parametrize("case", BLOCKS)
+def test_tc_conv2dblock_against_bf16_storage_oracle(case):
+    """One Conv2dBlock on tensor-core-eligible channel counts, forward + backward, against the oracle under the bf16
+    storage model: a single block is not chaotic, so this is the tight numerical check of the tcgen05 path
+    (image-level bounds are dominated by the network's own sensitivity, see tests/test_gpu_models.py)."""
+    from affganwriting_b200.blocks import Conv2dBlock
+    from affgw_testutil import cosine
+    from oracle import affgw_oracle as O
+    from oracle import weights as W
+    ci, co, k, p, norm, act, pt, h, w = case
+    A.set_precision("bf16")
+    try:
+        m = Conv2dBlock(ci, co, k, 1, p, norm=norm, activation=act, pad_type=pt)
+        sd = W.make_state({kk: list(v.shape) for kk, v in m.state_dict().items()})
+        m.load_state_dict(sd)
+        m = m.cuda()
+        g = torch.Generator().manual_seed(3)
+        x_cpu = torch.randn(3, ci, h, w, generator=g).bfloat16().float()
+        gy_cpu = torch.randn(3, co, h, w, generator=g)
+        x = x_cpu.cuda().requires_grad_()
+        y = m(x)
+        y.float().backward(gy_cpu.cuda())
+        xo = x_cpu.clone().requires_grad_()
+        sdo = {kk: v.clone().requires_grad_() for kk, v in sd.items()}
+        with O.storage_model("bf16"):
+            yo = O.conv2d_block(xo, sdo, "", k, 1, p, norm, act, pt)
+        yo.backward(gy_cpu)
+        assert rel_err(y, yo) <= 1e-2
+        assert cosine(x.grad, xo.grad) >= 0.999
+        assert cosine(m.conv.weight.grad, sdo["conv.weight"].grad) >= 0.999
+        assert rel_err(m.conv.weight.grad, sdo["conv.weight"].grad) <= 3e-2
+    finally:
+        A.set_precision("fp32")

@@ -1,0 +1,114 @@
+"""CPU: the oracle (oracle/affgw_oracle.py) against vectors produced by the UNMODIFIED reference
+(tests/golden/*.npz, written by oracle/make_golden.py in the build container).  This is the pin that lets the GPU
+tests use the oracle as the stand-in for the reference on a box where /root/reference does not exist."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from affgw_testutil import rel_err
+from oracle import affgw_oracle as O
+from oracle import weights as W
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _t(a):
+    return torch.from_numpy(np.ascontiguousarray(a))
+
+
+def test_generation_report_is_green():
+    rep = json.load(open(os.path.join(GOLDEN, "oracle_vs_reference.json")))
+    assert len(rep) > 80
+    assert all(r["max_abs"] <= r["tol"] for r in rep)
+
+
+@pytest.mark.parametrize("name", ["conv_zero_in_relu", "conv_reflect_none_tanh_k7", "conv_reflect_in_relu_k5",
+                                  "conv_actfirst_lrelu", "conv_head_k2s7", "conv_1x1_nobias", "conv_replicate"])
+def test_conv2dblock_cases(name, specs, golden):
+    g = golden("blocks.npz")
+    sp = specs["blocks." + name]
+    sd = {k: v.requires_grad_() for k, v in W.make_state(sp["spec"]).items()}
+    kw = dict(sp["ctor"])
+    kw.pop("in_dim"), kw.pop("out_dim"), kw.pop("use_bias", None)
+    x = _t(g[name + ".x"]).requires_grad_()
+    y = O.conv2d_block(x, sd, "", **kw)
+    y.backward(_t(g[name + ".gy"]))
+    assert rel_err(y, _t(g[name + ".y"])) <= 1e-5
+    assert rel_err(x.grad, _t(g[name + ".dx"])) <= 1e-4
+    assert rel_err(sd["conv.weight"].grad, _t(g[name + ".dw"])) <= 1e-4
+
+
+@pytest.mark.parametrize("name,train", [("adain_plain", True), ("adain_iaff_train", True), ("adain_iaff_eval", False)])
+def test_adain_iaff(name, train, specs, golden):
+    g = golden("blocks.npz")
+    sd = W.make_state(specs["blocks." + name]["spec"])
+    x = _t(g[name + ".x"]).requires_grad_()
+    style = _t(g[name + ".style"]) if name + ".style" in g.files else None
+    stats = {}
+    y = O.adaptive_instance_norm(x, sd, "", _t(g[name + ".weight"]), _t(g[name + ".bias"]), style, train, stats)
+    y.backward(_t(g[name + ".gy"]))
+    assert rel_err(y, _t(g[name + ".y"])) <= 5e-5
+    assert rel_err(x.grad, _t(g[name + ".dx"])) <= 2e-4
+    if name == "adain_iaff_train":
+        assert int(stats["iAff.global_att.2.num_batches_tracked"]) == 2      # blocks.py:295 reuses global_att
+        assert "iAff.global_att2.2.num_batches_tracked" not in stats
+        for k in ("iAff.global_att.2.running_mean", "iAff.global_att.5.running_var"):
+            assert rel_err(stats[k], _t(g[name + ".post." + k])) <= 1e-5
+
+
+def test_blocks_misc(specs, golden):
+    g = golden("blocks.npz")
+    sd = W.make_state(specs["blocks.resblocks_in"]["spec"])
+    y = _t(g["resblocks_in.x"])
+    for i in range(2):
+        y = O.res_block(y, sd, f"model.{i}.", "in", "relu", "reflect")
+    assert rel_err(y, _t(g["resblocks_in.y"])) <= 1e-5
+    for name, (fin, fout) in {"actfirst_same": (8, 8), "actfirst_grow": (8, 16)}.items():
+        sd = W.make_state(specs["blocks." + name]["spec"])
+        assert rel_err(O.act_first_res_block(_t(g[name + ".x"]), sd, "", fin, fout), _t(g[name + ".y"])) <= 1e-5
+    sd = W.make_state(specs["blocks.mlp"]["spec"])
+    assert rel_err(O.mlp(_t(g["mlp.x"]), sd, "", 3), _t(g["mlp.y"])) <= 1e-5
+    x = torch.empty(2, 8, 8, 27)
+    assert rel_err(O.get_key(x, _t(g["get_key.style"])), _t(g["get_key.y"])) <= 1e-6
+
+
+def test_generator_forward_and_bn_updates(specs, golden):
+    gold = golden("gen_fwd_c15_b4.npz")
+    sd = W.make_state(specs["gen_c15"])
+    batch = O.synthetic_batch(4, 15)
+    stats = {}
+    with torch.no_grad():
+        res = O.image_encoder(batch["tr_img"], sd)
+        for i in range(6):
+            assert tuple(res[i].shape) == tuple(gold[f"result{i}.shape"])
+            assert abs(float(res[i].abs().mean()) - float(gold[f"result{i}.abs_mean"])) <= 1e-4
+        xg = O.gen_forward(None, batch["label_xt"], sd, stats=stats, results=res)
+    assert float((xg - _t(gold["xg"])).abs().max()) <= 1e-4
+    for k in gold.files:
+        if k.startswith("post."):
+            assert rel_err(stats[k[5:]].float(), _t(gold[k]).float()) <= 1e-4, k
+    with torch.no_grad():
+        xe = O.gen_forward(batch["tr_img"][:1], batch["label_xt"][:1], sd, training=False)
+    assert float((xe - _t(gold["xg_eval_b1"])).abs().max()) <= 1e-4
+
+
+def test_dis_cla_losses(specs, golden):
+    gold, gg = golden("dis_cla_b4.npz"), golden("gen_fwd_c15_b4.npz")
+    dsd, csd = W.make_state(specs["dis"]), W.make_state(specs["cla"])
+    batch = O.synthetic_batch(4, 15)
+    xg = _t(gg["xg"])
+    with torch.no_grad():
+        assert rel_err(O.dis_forward(xg, dsd), _t(gold["dis.out"])) <= 1e-4
+        assert abs(float(O.dis_loss(batch["img_xt"], dsd, target=1.0)) - float(gold["dis.real_loss"])) <= 1e-5
+        assert abs(float(O.dis_loss(xg, dsd, target=0.0)) - float(gold["dis.fake_loss"])) <= 1e-5
+        assert abs(float(O.cla_loss(batch["img_xt"], batch["tr_wid"], csd)) - float(gold["cla.loss"])) <= 1e-4
+
+
+def test_train_mode_batch_of_one_raises(specs):
+    sd = W.make_state(specs["gen_c15"])
+    batch = O.synthetic_batch(1, 15)
+    with pytest.raises(ValueError):
+        O.text_encoder(batch["label_xt"], (1, 512, 8, 27), sd, "enc_text.")
