@@ -41,7 +41,8 @@ SIGNATURES = {
     "affgw_conv2d_fwd": [_P, _P, _P, _P, _P, _D, _P],
     "affgw_conv2d_dgrad_ws_bytes": [_D],
     "affgw_conv2d_dgrad": [_P, _P, _P, _P, _P, _D, _P],
-    "affgw_conv2d_wgrad": [_P, _P, _P, _D, _P],
+    "affgw_conv2d_wgrad_ws_bytes": [_D],
+    "affgw_conv2d_wgrad": [_P, _P, _P, _P, _D, _P],
     "affgw_colsum": [_P, _I, _P, _L, _I, _I, _P],
     "affgw_norm_stats": [_P, _I, _P, _P, _P, _P, _I, _L, _I, _F, _I, _P],
     "affgw_norm_apply": [_P, _I, _P, _P, _P, _P, _P, _P, _I, _L, _I, _I, _I, _P],
@@ -77,7 +78,7 @@ SIGNATURES = {
     "affgw_bucket_unpack": [_P, _P, _P, _I, _P, _F, _P],
 }
 _RESTYPE = {"affgw_last_error": C.c_char_p, "affgw_launch_count": _L, "affgw_pack_weight_tc_bytes": _L,
-            "affgw_conv2d_dgrad_ws_bytes": _L}
+            "affgw_conv2d_dgrad_ws_bytes": _L, "affgw_conv2d_wgrad_ws_bytes": _L}
 
 _lib = None
 

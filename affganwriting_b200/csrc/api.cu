@@ -23,6 +23,10 @@ int conv_fwd_tc(const void* x, const void* w_tiles, const float* bias, const voi
 int pack_weight_tc(const float* w, void* out, int Cout, int Cin, int KH, int KW, int ipad, int transpose_flip, int block_n,
                    cudaStream_t st);
 long long pack_weight_tc_bytes(int Cout, int Cin, int KH, int KW, int ipad, int transpose_flip, int block_n);
+// conv_tc_wgrad.cu
+int conv_wgrad_tc_ok(const ConvGeom& g, int x_dt, int dy_dt);
+long long conv_wgrad_tc_ws_bytes(const ConvGeom& g);
+int conv_wgrad_tc(const void* x, const void* dy, float* dw, void* workspace, const ConvGeom& g, int cin_w, cudaStream_t st);
 // norm.cu
 int norm_stats(const void* x, int dt, float* ws, float* mean, float* rstd, float* var_unbiased, int G, long long P, int C,
                float eps, int unbiased, cudaStream_t st);
@@ -237,10 +241,30 @@ int affgw_conv_tc_dgrad_block_n(const affgw_conv_desc* d) {
     return conv_tc_block_n(g, dd.x_dtype, d->w_dtype);
 }
 
-int affgw_conv2d_wgrad(const void* x, const void* dy, float* dw, const affgw_conv_desc* d, void* stream) {
+// tensor-core wgrad sees the STORED channel count of x (in_pitch); padded channels are dropped when unpacking
+static int make_wgrad_tc_geom(const affgw_conv_desc* d, ConvGeom& g) {
+    if (int rc = make_geom(d, g)) return rc;
+    g.Cin = d->in_pitch;
+    g.Ktot = g.KH * g.KW * g.Cin;
+    return 0;
+}
+
+long long affgw_conv2d_wgrad_ws_bytes(const affgw_conv_desc* d) {
+    ConvGeom g;
+    if (!d || d->algo != AFFGW_ALGO_TCGEN05 || make_wgrad_tc_geom(d, g)) return 0;
+    return conv_wgrad_tc_ok(g, d->x_dtype, d->y_dtype) ? conv_wgrad_tc_ws_bytes(g) : 0;
+}
+
+int affgw_conv2d_wgrad(const void* x, const void* dy, float* dw, void* workspace, const affgw_conv_desc* d, void* stream) {
     ConvGeom g;
     if (int rc = make_geom(d, g)) return rc;
     AFFGW_CHECK(x && dy && dw, "conv2d_wgrad: null pointer");
+    if (d->algo == AFFGW_ALGO_TCGEN05) {
+        if (int rc = make_wgrad_tc_geom(d, g)) return rc;
+        AFFGW_CHECK(conv_wgrad_tc_ok(g, d->x_dtype, d->y_dtype), "conv2d_wgrad: shape not supported by the tcgen05 kernel");
+        AFFGW_CHECK(workspace != nullptr, "conv2d_wgrad: the tcgen05 kernel needs affgw_conv2d_wgrad_ws_bytes() of workspace");
+        return conv_wgrad_tc(x, dy, dw, workspace, g, d->Cin, S(stream));
+    }
     return conv_wgrad_simt(x, d->x_dtype, dy, d->y_dtype, dw, g, S(stream));
 }
 

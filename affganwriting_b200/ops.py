@@ -12,7 +12,7 @@ from torch.autograd import Function
 
 from . import _lib as L  # noqa: N812
 
-_state = {"mode": "fp32", "force_simt": False}
+_state = {"mode": "fp32", "force_simt": False, "simt_wgrad": False}
 _err_flag = {}
 _profile = {"records": None}
 
@@ -72,6 +72,11 @@ def act_dtype():
 def force_simt(flag=True):
     """Route every convolution through the CUDA-core kernel (used by tests to cross-check tcgen05)."""
     _state["force_simt"] = bool(flag)
+
+
+def force_simt_wgrad(flag=True):
+    """Keep forward / dgrad on tcgen05 but compute weight gradients on CUDA cores (cross-check of the MN-major path)."""
+    _state["simt_wgrad"] = bool(flag)
 
 
 def _err_tensor(device):
@@ -338,10 +343,19 @@ class _Conv2d(Function):
         fwd_cfg = cfg._replace(post_act="none")
         if need_w:
             dw = torch.zeros(weight.shape, dtype=torch.float32, device=x.device)
-            d = _desc(g, fwd_cfg, g["Cin"], x_dt, w_dt, y_dt, L.ALGO_SIMT)
+            d = _desc(g, fwd_cfg, g["Cin"], x_dt, w_dt, y_dt, L.ALGO_TC)
             flops = 2.0 * M * g["Cout"] * g["Cin"] * g["KH"] * g["KW"]
-            with _timed("conv_wgrad_simt", flops):
-                L.call("affgw_conv2d_wgrad", x.data_ptr(), dz.data_ptr(), dw.data_ptr(), C.byref(d), st)
+            ws_bytes = 0
+            if _state["mode"] == "bf16" and not _state["force_simt"] and not _state["simt_wgrad"]:
+                ws_bytes = L.lib().affgw_conv2d_wgrad_ws_bytes(C.byref(d))
+            if ws_bytes > 0:
+                wsb = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+                with _timed("conv_wgrad_tcgen05", flops):
+                    L.call("affgw_conv2d_wgrad", x.data_ptr(), dz.data_ptr(), dw.data_ptr(), wsb.data_ptr(), C.byref(d), st)
+            else:
+                d.algo = L.ALGO_SIMT
+                with _timed("conv_wgrad_simt", flops):
+                    L.call("affgw_conv2d_wgrad", x.data_ptr(), dz.data_ptr(), dw.data_ptr(), None, C.byref(d), st)
         if need_x:
             if x.dtype != dz.dtype:
                 dz_x = _cast(dz, x.dtype)

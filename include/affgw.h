@@ -72,8 +72,10 @@ int affgw_conv2d_fwd(const void* x, const void* w_packed, const float* bias, con
 long long affgw_conv2d_dgrad_ws_bytes(const affgw_conv_desc* d);
 int affgw_conv2d_dgrad(const void* dy, const void* w_packed_t, const void* x, void* dx, void* workspace,
                        const affgw_conv_desc* d, void* stream);
-/* dw (OIHW fp32) += dY^T * gather(x); caller zeroes dw first */
-int affgw_conv2d_wgrad(const void* x, const void* dy, float* dw_oihw, const affgw_conv_desc* d, void* stream);
+/* dw (OIHW fp32) += dY^T * gather(x); caller zeroes dw first.  With algo = TCGEN05 the split-K partials are reduced in
+ * `workspace` (affgw_conv2d_wgrad_ws_bytes, 0 = the shape is not tensor-core eligible, use algo = SIMT, no workspace). */
+long long affgw_conv2d_wgrad_ws_bytes(const affgw_conv_desc* d);
+int affgw_conv2d_wgrad(const void* x, const void* dy, float* dw_oihw, void* workspace, const affgw_conv_desc* d, void* stream);
 /* out[c] += sum_m a[m][c]  (bias gradient); caller zeroes out */
 int affgw_colsum(const void* a, int dtype, float* out, long long M, int C, int pitch, void* stream);
 

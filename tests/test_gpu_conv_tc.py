@@ -113,3 +113,40 @@ def test_tc_conv2dblock_against_bf16_storage_oracle(case):
         assert rel_err(m.conv.weight.grad, sdo["conv.weight"].grad) <= 3e-2
     finally:
         A.set_precision("fp32")
+
+
+WG_CASES = [
+    # N, H, W, Cin, Cout, k, pad, pad_mode, upsample
+    (2, 8, 27, 64, 64, 3, 1, "zero", 1),          # Cin = 64: two taps share one 128-row M tile, odd tap count
+    (2, 8, 27, 128, 128, 3, 1, "reflect", 1),
+    (3, 16, 54, 64, 128, 3, 1, "zero", 1),
+    (2, 8, 27, 512, 256, 5, 2, "reflect", 2),
+    (2, 8, 27, 1024, 512, 1, 0, "zero", 1),
+    (1, 64, 216, 64, 64, 3, 1, "zero", 1),        # many pixel splits
+    (5, 7, 9, 192, 64, 3, 1, "replicate", 1),
+]
+
+
+@pytest.mark.parametrize("case", WG_CASES)
+def test_tc_wgrad_matches_simt(case):
+    """MN-major tcgen05 weight-gradient kernel vs the CUDA-core wgrad on identical bf16 operands."""
+    from affgw_testutil import cosine
+    n, h, w, ci, co, k, p, pm, up = case
+    A.set_precision("bf16")
+    try:
+        g = torch.Generator(device="cuda").manual_seed(11)
+        x = ops.to_internal(torch.randn(n, ci, h, w, device="cuda", generator=g))
+        wgt = (torch.randn(co, ci, k, k, device="cuda", generator=g) * 0.05).requires_grad_()
+        grads = {}
+        for simt in (True, False):
+            ops.force_simt_wgrad(simt)
+            wgt.grad = None
+            y = ops.conv2d(x, wgt, None, pad=p, pad_mode=pm, upsample=up)
+            gy = torch.randn(y.shape, device="cuda", generator=torch.Generator(device="cuda").manual_seed(5))
+            y.float().backward(gy)
+            grads[simt] = wgt.grad.detach().clone()
+        assert cosine(grads[False], grads[True]) >= 0.99999
+        assert rel_err(grads[False], grads[True]) <= 2e-3
+    finally:
+        ops.force_simt_wgrad(False)
+        A.set_precision("fp32")
