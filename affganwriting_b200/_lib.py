@@ -21,7 +21,7 @@ class ConvDesc(C.Structure):
     """Mirror of `affgw_conv_desc` (include/affgw.h)."""
     _fields_ = [(n, C.c_int32) for n in (
         "N", "H", "W", "Cin", "Cout", "KH", "KW", "stride", "pad", "pad_mode", "upsample", "Ho", "Wo",
-        "in_pitch", "out_pitch", "pre_act", "post_act", "x_dtype", "w_dtype", "y_dtype", "algo")]
+        "in_pitch", "out_pitch", "pre_act", "post_act", "x_dtype", "w_dtype", "y_dtype", "algo", "passes", "grad_dtype")]
 
 
 _P, _I, _L, _F = C.c_void_p, C.c_int, C.c_longlong, C.c_float
@@ -36,8 +36,9 @@ SIGNATURES = {
     "affgw_pack_weight": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "affgw_pack_weight_tc": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "affgw_pack_weight_tc_bytes": [_I, _I, _I, _I, _I, _I, _I],
-    "affgw_conv_tc_block_n": [_D],
-    "affgw_conv_tc_dgrad_block_n": [_D],
+    "affgw_operand_planes_bytes": [_L, _I, _I],
+    "affgw_split_planes": [_P, _I, _P, _L, _I, _I, _I, _I, _I, _P],
+    "affgw_conv_tc_supported": [_D],
     "affgw_conv2d_fwd": [_P, _P, _P, _P, _P, _D, _P],
     "affgw_conv2d_dgrad_ws_bytes": [_D],
     "affgw_conv2d_dgrad": [_P, _P, _P, _P, _P, _D, _P],
@@ -77,7 +78,7 @@ SIGNATURES = {
     "affgw_bucket_pack": [_P, _P, _P, _I, _P, _P],
     "affgw_bucket_unpack": [_P, _P, _P, _I, _P, _F, _P],
 }
-_RESTYPE = {"affgw_last_error": C.c_char_p, "affgw_launch_count": _L, "affgw_pack_weight_tc_bytes": _L,
+_RESTYPE = {"affgw_last_error": C.c_char_p, "affgw_launch_count": _L, "affgw_pack_weight_tc_bytes": _L, "affgw_operand_planes_bytes": _L,
             "affgw_conv2d_dgrad_ws_bytes": _L, "affgw_conv2d_wgrad_ws_bytes": _L}
 
 _lib = None

@@ -17,16 +17,20 @@ int colsum(const void* a, int dt, float* out, long long M, int C, int pitch, cud
 int pack_weight(const float* w, void* out, int out_dt, int Cout, int Cin, int KH, int KW, int ipad, int transpose_flip,
                 cudaStream_t st);
 // conv_tc.cu
-int conv_tc_block_n(const ConvGeom& g, int x_dt, int w_dt);
-int conv_fwd_tc(const void* x, const void* w_tiles, const float* bias, const void* addend, void* y, int y_dt,
-                const ConvGeom& g, cudaStream_t st);
-int pack_weight_tc(const float* w, void* out, int Cout, int Cin, int KH, int KW, int ipad, int transpose_flip, int block_n,
+int conv_tc_block_n(int cout);
+int conv_tc_ok(const ConvGeom& g);
+int conv_fwd_tc(const void* x_planes, long long plane_stride, const void* w_tiles, const float* bias, const void* addend,
+                void* y, int y_dt, const ConvGeom& g, int passes, cudaStream_t st);
+int pack_weight_tc(const float* w, void* out, int Cout, int Cin, int KH, int KW, int ipad, int transpose_flip, int passes,
                    cudaStream_t st);
-long long pack_weight_tc_bytes(int Cout, int Cin, int KH, int KW, int ipad, int transpose_flip, int block_n);
+long long pack_weight_tc_bytes(int Cout, int Cin, int KH, int KW, int ipad, int transpose_flip, int passes);
+int split_planes(const void* x, int x_dt, void* planes, long long rows, int C, int pitch, int c_store, int passes, int pre_act,
+                 cudaStream_t st);
 // conv_tc_wgrad.cu
-int conv_wgrad_tc_ok(const ConvGeom& g, int x_dt, int dy_dt);
+int conv_wgrad_tc_ok(const ConvGeom& g);
 long long conv_wgrad_tc_ws_bytes(const ConvGeom& g);
-int conv_wgrad_tc(const void* x, const void* dy, float* dw, void* workspace, const ConvGeom& g, int cin_w, cudaStream_t st);
+int conv_wgrad_tc(const void* x_planes, long long x_plane, const void* dy_planes, long long dy_plane, float* dw, void* workspace,
+                  const ConvGeom& g, int cin_w, int passes, cudaStream_t st);
 // norm.cu
 int norm_stats(const void* x, int dt, float* ws, float* mean, float* rstd, float* var_unbiased, int G, long long P, int C,
                float eps, int unbiased, cudaStream_t st);
@@ -136,18 +140,42 @@ int affgw_pack_weight(const float* w, void* out, int out_dtype, int Cout, int Ci
     return pack_weight(w, out, out_dtype, Cout, Cin, KH, KW, i_pad, transpose_flip, S(stream));
 }
 
-long long affgw_pack_weight_tc_bytes(int Cout, int Cin, int KH, int KW, int i_pad, int transpose_flip, int block_n) {
-    return pack_weight_tc_bytes(Cout, Cin, KH, KW, i_pad, transpose_flip, block_n);
+static inline bool passes_ok(int p) { return p == 1 || p == 3; }
+
+long long affgw_pack_weight_tc_bytes(int Cout, int Cin, int KH, int KW, int i_pad, int transpose_flip, int passes) {
+    return pack_weight_tc_bytes(Cout, Cin, KH, KW, i_pad, transpose_flip, passes);
 }
 int affgw_pack_weight_tc(const float* w, void* out, int Cout, int Cin, int KH, int KW, int i_pad, int transpose_flip,
-                         int block_n, void* stream) {
+                         int passes, void* stream) {
     AFFGW_CHECK(w && out, "pack_weight_tc: null pointer");
-    return pack_weight_tc(w, out, Cout, Cin, KH, KW, i_pad, transpose_flip, block_n, S(stream));
+    return pack_weight_tc(w, out, Cout, Cin, KH, KW, i_pad, transpose_flip, passes, S(stream));
 }
-int affgw_conv_tc_block_n(const affgw_conv_desc* d) {
+long long affgw_operand_planes_bytes(long long rows, int c_store, int passes) {
+    if (rows <= 0 || c_store <= 0 || c_store % 8 != 0 || !passes_ok(passes)) return -1;
+    return rows * c_store * 2LL * (passes == 3 ? 2 : 1);
+}
+int affgw_split_planes(const void* x, int x_dtype, void* planes, long long rows, int C, int pitch, int c_store, int passes,
+                       int pre_act, void* stream) {
+    AFFGW_CHECK(x && planes && dt_ok(x_dtype) && rows > 0 && C > 0 && pitch >= C, "split_planes: bad argument");
+    AFFGW_CHECK(pre_act >= 0 && pre_act <= 3, "split_planes: bad activation");
+    return split_planes(x, x_dtype, planes, rows, C, pitch, c_store, passes, pre_act, S(stream));
+}
+
+// geometry seen by the tcgen05 kernels: channels = the STORED channel count of the operand planes
+static int make_tc_geom(const affgw_conv_desc* d, ConvGeom& g) {
+    if (int rc = make_geom(d, g)) return rc;
+    AFFGW_CHECK(passes_ok(d->passes), "conv (tcgen05): passes must be 1 or 3");
+    AFFGW_CHECK(d->x_dtype == AFFGW_BF16 && d->w_dtype == AFFGW_BF16, "conv (tcgen05): operands are bf16 planes / tiles");
+    AFFGW_CHECK(d->pre_act == ACT_NONE, "conv (tcgen05): the pre-activation is applied by affgw_split_planes");
+    g.Cin = d->in_pitch;
+    g.Ktot = g.KH * g.KW * g.Cin;
+    return 0;
+}
+
+int affgw_conv_tc_supported(const affgw_conv_desc* d) {
     ConvGeom g;
-    if (make_geom(d, g)) return 0;
-    return conv_tc_block_n(g, d->x_dtype, d->w_dtype);
+    if (!d || make_tc_geom(d, g)) return 0;
+    return conv_tc_ok(g) > 0;
 }
 
 int affgw_conv2d_fwd(const void* x, const void* w, const float* bias, const void* addend, void* y,
@@ -156,8 +184,10 @@ int affgw_conv2d_fwd(const void* x, const void* w, const float* bias, const void
     if (int rc = make_geom(d, g)) return rc;
     AFFGW_CHECK(x && w && y, "conv2d_fwd: null pointer");
     if (d->algo == AFFGW_ALGO_TCGEN05) {
-        AFFGW_CHECK(conv_tc_block_n(g, d->x_dtype, d->w_dtype) > 0, "conv2d_fwd: shape not supported by the tcgen05 kernel");
-        return conv_fwd_tc(x, w, bias, addend, y, d->y_dtype, g, S(stream));
+        if (int rc = make_tc_geom(d, g)) return rc;
+        AFFGW_CHECK(conv_tc_ok(g) > 0, "conv2d_fwd: shape not supported by the tcgen05 kernel");
+        const long long plane = (long long)d->N * d->H * d->W * d->in_pitch;
+        return conv_fwd_tc(x, plane, w, bias, addend, y, d->y_dtype, g, d->passes, S(stream));
     }
     return conv_fwd_simt(x, d->x_dtype, w, d->w_dtype, bias, addend, y, d->y_dtype, g, S(stream));
 }
@@ -165,7 +195,8 @@ int affgw_conv2d_fwd(const void* x, const void* w, const float* bias, const void
 // geometry of the dgrad convolution: input dY [N,Ho,Wo,Cout] (zero-inserted by stride), weights [Cin][K][K][Cout]
 static int make_dgrad(const affgw_conv_desc* d, affgw_conv_desc& dd, bool& direct, int& Hp, int& Wp) {
     AFFGW_CHECK(d->KH == d->KW, "conv2d_dgrad: square kernels only");
-    AFFGW_CHECK(d->x_dtype == d->y_dtype, "conv2d_dgrad: x and y dtypes must match");
+    const bool tc = d->algo == AFFGW_ALGO_TCGEN05;
+    if (!tc) AFFGW_CHECK(d->x_dtype == d->y_dtype, "conv2d_dgrad: x and y dtypes must match");
     direct = d->pad_mode == PAD_ZERO && d->upsample == 1 && d->pre_act == ACT_NONE && d->pad <= d->KH - 1;
     Hp = d->H * d->upsample + 2 * d->pad;
     Wp = d->W * d->upsample + 2 * d->pad;
@@ -176,10 +207,22 @@ static int make_dgrad(const affgw_conv_desc* d, affgw_conv_desc& dd, bool& direc
     dd.Ho = direct ? d->H : Hp;
     dd.Wo = direct ? d->W : Wp;
     dd.in_pitch = d->out_pitch;
-    dd.out_pitch = direct ? d->in_pitch : d->Cin;
+    dd.out_pitch = tc ? d->Cin : (direct ? d->in_pitch : d->Cin);
     dd.pre_act = ACT_NONE; dd.post_act = ACT_NONE;
-    dd.x_dtype = d->y_dtype; dd.y_dtype = d->x_dtype;
+    dd.x_dtype = d->y_dtype; dd.y_dtype = tc ? d->grad_dtype : d->x_dtype;
     return 0;
+}
+
+static void dgrad_geom(const affgw_conv_desc* d, const affgw_conv_desc& dd, ConvGeom& g) {
+    // built by hand: the virtual input is dY zero-inserted by the forward stride
+    g.N = dd.N; g.H = dd.H; g.W = dd.W; g.Cin = dd.Cin; g.Cout = dd.Cout; g.KH = dd.KH; g.KW = dd.KW;
+    g.stride = 1; g.pad = dd.pad; g.pad_mode = PAD_ZERO; g.up = 1; g.zi = d->stride;
+    g.Ho = dd.Ho; g.Wo = dd.Wo; g.in_pitch = dd.in_pitch; g.out_pitch = dd.out_pitch;
+    g.pre_act = ACT_NONE; g.post_act = ACT_NONE;
+    g.Hv = (dd.H - 1) * d->stride + 1; g.Wv = (dd.W - 1) * d->stride + 1;
+    if (d->algo == AFFGW_ALGO_TCGEN05) g.Cin = dd.in_pitch;       // stored channels of the dY planes
+    g.Ktot = g.KH * g.KW * g.Cin;
+    g.M = (long long)g.N * g.Ho * g.Wo;
 }
 
 long long affgw_conv2d_dgrad_ws_bytes(const affgw_conv_desc* d) {
@@ -187,7 +230,8 @@ long long affgw_conv2d_dgrad_ws_bytes(const affgw_conv_desc* d) {
     bool direct;
     int Hp, Wp;
     if (!d || make_dgrad(d, dd, direct, Hp, Wp)) return -1;
-    return direct ? 0 : (long long)d->N * Hp * Wp * d->Cin * (long long)dt_size(d->x_dtype);
+    const int gdt = d->algo == AFFGW_ALGO_TCGEN05 ? d->grad_dtype : d->x_dtype;
+    return direct ? 0 : (long long)d->N * Hp * Wp * d->Cin * (long long)dt_size(gdt);
 }
 
 int affgw_conv2d_dgrad(const void* dy, const void* wt, const void* x, void* dx, void* workspace,
@@ -198,61 +242,44 @@ int affgw_conv2d_dgrad(const void* dy, const void* wt, const void* x, void* dx, 
     int Hp, Wp;
     if (int rc = make_dgrad(d, dd, direct, Hp, Wp)) return rc;
     ConvGeom g;
-    // build geometry by hand: the virtual input is dY zero-inserted by the forward stride
-    g.N = dd.N; g.H = dd.H; g.W = dd.W; g.Cin = dd.Cin; g.Cout = dd.Cout; g.KH = dd.KH; g.KW = dd.KW;
-    g.stride = 1; g.pad = dd.pad; g.pad_mode = PAD_ZERO; g.up = 1; g.zi = d->stride;
-    g.Ho = dd.Ho; g.Wo = dd.Wo; g.in_pitch = dd.in_pitch; g.out_pitch = dd.out_pitch;
-    g.pre_act = ACT_NONE; g.post_act = ACT_NONE;
-    g.Hv = (dd.H - 1) * d->stride + 1; g.Wv = (dd.W - 1) * d->stride + 1;
-    g.Ktot = g.KH * g.KW * g.Cin;
-    g.M = (long long)g.N * g.Ho * g.Wo;
+    dgrad_geom(d, dd, g);
     void* out = direct ? dx : workspace;
     AFFGW_CHECK(out != nullptr, "conv2d_dgrad: workspace required for this geometry");
+    const bool tc = d->algo == AFFGW_ALGO_TCGEN05;
+    const int gdt = tc ? d->grad_dtype : d->x_dtype;
     int rc;
-    if (d->algo == AFFGW_ALGO_TCGEN05) {
-        AFFGW_CHECK(conv_tc_block_n(g, dd.x_dtype, d->w_dtype) > 0, "conv2d_dgrad: shape not supported by the tcgen05 kernel");
-        rc = conv_fwd_tc(dy, wt, nullptr, nullptr, out, dd.y_dtype, g, S(stream));
+    if (tc) {
+        AFFGW_CHECK(passes_ok(d->passes) && dt_ok(d->grad_dtype), "conv2d_dgrad: bad passes / grad_dtype");
+        AFFGW_CHECK(d->y_dtype == AFFGW_BF16 && d->w_dtype == AFFGW_BF16, "conv2d_dgrad (tcgen05): operands are bf16 planes / tiles");
+        AFFGW_CHECK(conv_tc_ok(g) > 0, "conv2d_dgrad: shape not supported by the tcgen05 kernel");
+        const long long plane = (long long)dd.N * dd.H * dd.W * dd.in_pitch;
+        rc = conv_fwd_tc(dy, plane, wt, nullptr, nullptr, out, gdt, g, d->passes, S(stream));
     } else {
         rc = conv_fwd_simt(dy, dd.x_dtype, wt, d->w_dtype, nullptr, nullptr, out, dd.y_dtype, g, S(stream));
     }
     if (rc) return rc;
     if (!direct) {
         AFFGW_CHECK(d->pre_act == ACT_NONE || x != nullptr, "conv2d_dgrad: x needed for the pre-activation derivative");
-        AFFGW_CHECK(d->in_pitch == d->Cin, "conv2d_dgrad: folded path needs a dense x");
-        return conv_fold(workspace, x, dx, d->x_dtype, d->N, d->H, d->W, d->Cin, d->pad, d->pad_mode, d->upsample, d->pre_act,
+        AFFGW_CHECK(tc || d->in_pitch == d->Cin, "conv2d_dgrad: folded path needs a dense x");
+        return conv_fold(workspace, x, dx, gdt, d->N, d->H, d->W, d->Cin, d->pad, d->pad_mode, d->upsample, d->pre_act,
                          S(stream));
     }
     return 0;
 }
 
-int affgw_conv_tc_dgrad_block_n(const affgw_conv_desc* d) {
-    affgw_conv_desc dd;
-    bool direct;
-    int Hp, Wp;
-    if (!d || make_dgrad(d, dd, direct, Hp, Wp)) return 0;
-    ConvGeom g;
-    g.N = dd.N; g.H = dd.H; g.W = dd.W; g.Cin = dd.Cin; g.Cout = dd.Cout; g.KH = dd.KH; g.KW = dd.KW;
-    g.stride = 1; g.pad = dd.pad; g.pad_mode = PAD_ZERO; g.up = 1; g.zi = d->stride;
-    g.Ho = dd.Ho; g.Wo = dd.Wo; g.in_pitch = dd.in_pitch; g.out_pitch = dd.out_pitch;
-    g.pre_act = g.post_act = ACT_NONE;
-    g.Hv = (dd.H - 1) * d->stride + 1; g.Wv = (dd.W - 1) * d->stride + 1;
-    g.Ktot = g.KH * g.KW * g.Cin;
-    g.M = (long long)g.N * g.Ho * g.Wo;
-    return conv_tc_block_n(g, dd.x_dtype, d->w_dtype);
-}
-
-// tensor-core wgrad sees the STORED channel count of x (in_pitch); padded channels are dropped when unpacking
+// tensor-core wgrad sees the STORED channel counts of the x / dY planes; padded channels are dropped when unpacking
 static int make_wgrad_tc_geom(const affgw_conv_desc* d, ConvGeom& g) {
     if (int rc = make_geom(d, g)) return rc;
     g.Cin = d->in_pitch;
     g.Ktot = g.KH * g.KW * g.Cin;
+    g.pre_act = ACT_NONE;       // already applied to the planes by affgw_split_planes
     return 0;
 }
 
 long long affgw_conv2d_wgrad_ws_bytes(const affgw_conv_desc* d) {
     ConvGeom g;
     if (!d || d->algo != AFFGW_ALGO_TCGEN05 || make_wgrad_tc_geom(d, g)) return 0;
-    return conv_wgrad_tc_ok(g, d->x_dtype, d->y_dtype) ? conv_wgrad_tc_ws_bytes(g) : 0;
+    return conv_wgrad_tc_ok(g) ? conv_wgrad_tc_ws_bytes(g) : 0;
 }
 
 int affgw_conv2d_wgrad(const void* x, const void* dy, float* dw, void* workspace, const affgw_conv_desc* d, void* stream) {
@@ -261,9 +288,13 @@ int affgw_conv2d_wgrad(const void* x, const void* dy, float* dw, void* workspace
     AFFGW_CHECK(x && dy && dw, "conv2d_wgrad: null pointer");
     if (d->algo == AFFGW_ALGO_TCGEN05) {
         if (int rc = make_wgrad_tc_geom(d, g)) return rc;
-        AFFGW_CHECK(conv_wgrad_tc_ok(g, d->x_dtype, d->y_dtype), "conv2d_wgrad: shape not supported by the tcgen05 kernel");
+        AFFGW_CHECK(passes_ok(d->passes), "conv2d_wgrad: passes must be 1 or 3");
+        AFFGW_CHECK(d->x_dtype == AFFGW_BF16 && d->y_dtype == AFFGW_BF16, "conv2d_wgrad (tcgen05): operands are bf16 planes");
+        AFFGW_CHECK(conv_wgrad_tc_ok(g), "conv2d_wgrad: shape not supported by the tcgen05 kernel");
         AFFGW_CHECK(workspace != nullptr, "conv2d_wgrad: the tcgen05 kernel needs affgw_conv2d_wgrad_ws_bytes() of workspace");
-        return conv_wgrad_tc(x, dy, dw, workspace, g, d->Cin, S(stream));
+        const long long xpl = (long long)d->N * d->H * d->W * d->in_pitch;
+        const long long ypl = g.M * d->out_pitch;
+        return conv_wgrad_tc(x, xpl, dy, ypl, dw, workspace, g, d->Cin, d->passes, S(stream));
     }
     return conv_wgrad_simt(x, d->x_dtype, dy, d->y_dtype, dw, g, S(stream));
 }

@@ -27,11 +27,20 @@ constexpr int IMG_BYTES = BP * 128;          // one [64 pixels][64 channels] bf1
 constexpr int NUM_PRODUCER_THREADS = 128;
 constexpr int NUM_THREADS = 160;
 
-template <int BN> struct WgCfg {
-    static constexpr int STAGES = (BN == 64) ? 4 : 3;
-    static constexpr int A_BYTES = 2 * IMG_BYTES;
-    static constexpr int B_BYTES = (BN / 64) * IMG_BYTES;
+constexpr int pow2_cols(int n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : n <= 256 ? 256 : 512; }
+
+template <int BN, int NPASS> struct WgCfg {
+    static constexpr int NPL = NPASS == 3 ? 2 : 1;
+    static constexpr int BNI = BN > 64 ? BN / 64 : 1;      // 64-channel dY images per plane
+    static constexpr int A_PLANE = 2 * IMG_BYTES;
+    static constexpr int B_PLANE = BNI * IMG_BYTES;
+    static constexpr int A_BYTES = NPL * A_PLANE;
+    static constexpr int B_BYTES = NPL * B_PLANE;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int BUDGET = NPASS == 3 ? 200 * 1024 : 100 * 1024;
+    static constexpr int STAGES_RAW = BUDGET / STAGE_BYTES;
+    static constexpr int STAGES = STAGES_RAW > 5 ? 5 : (STAGES_RAW < 2 ? 2 : STAGES_RAW);
+    static constexpr int TMEM_COLS = pow2_cols(BN);
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
 };
 
@@ -62,12 +71,23 @@ __device__ __forceinline__ int map_fast(int v, int V, int pad_mode, int up) {
     return up == 2 ? (v >> 1) : v;
 }
 
-template <int BN>
+struct WgArgs {
+    const bf16* x;      // operand planes [NPL][N*H*W][Cin]   (g.Cin = stored channels)
+    long long x_plane;
+    const bf16* dy;     // operand planes [NPL][M][g.out_pitch]
+    long long dy_plane;
+    float* ws;          // [Cout][taps * Cin] fp32 partial sums
+    ConvGeom g;
+    long long m_per_split;
+};
+
+template <int BN, int NPASS>
 __global__ void __launch_bounds__(NUM_THREADS)
-conv_wgrad_tcgen05_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy, float* __restrict__ ws, const ConvGeom g,
-                          const long long m_per_split, const int swap_lbo_sbo) {
-    using Cfg = WgCfg<BN>;
+conv_wgrad_tcgen05_kernel(const __grid_constant__ WgArgs a) {
+    using Cfg = WgCfg<BN, NPASS>;
     constexpr int STAGES = Cfg::STAGES;
+    constexpr int NPL = Cfg::NPL;
+    constexpr int BNI = Cfg::BNI;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
@@ -78,25 +98,13 @@ conv_wgrad_tcgen05_kernel(const bf16* __restrict__ x, const bf16* __restrict__ d
     auto a_smem = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES; };
     auto b_smem = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES + Cfg::A_BYTES; };
 
+    const ConvGeom& g = a.g;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int cblocks = g.Cin / 64;                    // g.Cin is the stored (64-aligned) channel count
-    const int taps = g.KH * g.KW;
-    const int total64 = taps * cblocks;
+    const int ktot = g.KH * g.KW * g.Cin;               // flattened (tap, stored channel) extent = rows of dW^T
     const int n0 = blockIdx.y * BN;
-    const long long mbeg = (long long)blockIdx.z * m_per_split;
-    const long long mend = min(g.M, mbeg + m_per_split);
+    const long long mbeg = (long long)blockIdx.z * a.m_per_split;
+    const long long mend = min(g.M, mbeg + a.m_per_split);
     const int nstages = (int)((mend - mbeg + BP - 1) / BP);
-
-    // the two 64-channel blocks of this CTA's M tile
-    int tap_i[2], cb_i[2];
-    bool valid_i[2];
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-        const int kb = 2 * blockIdx.x + i;
-        valid_i[i] = kb < total64;
-        tap_i[i] = valid_i[i] ? kb / cblocks : 0;
-        cb_i[i] = valid_i[i] ? kb % cblocks : 0;
-    }
 
     if (tid == NUM_PRODUCER_THREADS) {
         for (int s = 0; s < STAGES; ++s) {
@@ -108,7 +116,7 @@ conv_wgrad_tcgen05_kernel(const bf16* __restrict__ x, const bf16* __restrict__ d
     }
     if (warp == 4) {
         __syncwarp();
-        tmem_alloc(tmem_ptr_addr, BN);
+        tmem_alloc(tmem_ptr_addr, Cfg::TMEM_COLS);
     }
     tc_fence_before();
     __syncthreads();
@@ -119,6 +127,21 @@ conv_wgrad_tcgen05_kernel(const bf16* __restrict__ x, const bf16* __restrict__ d
     if (warp < 4) {
         // ============================== producer: gather(x) and dY images ==============================
         const int chunk = tid & 7, slot = tid >> 3;       // rows slot, slot+16, slot+32, slot+48
+        // this thread's 8 consecutive rows of dW^T inside each of the CTA's two 64-row blocks: one tap, 8 channels
+        int dyo[2], dxo[2], coff[2];
+        bool kvalid[2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int kf = (2 * blockIdx.x + i) * 64 + chunk * 8;
+            kvalid[i] = kf < ktot;
+            const int tap = kvalid[i] ? kf / g.Cin : 0;
+            coff[i] = kvalid[i] ? kf - tap * g.Cin : 0;
+            dyo[i] = tap / g.KW - g.pad;
+            dxo[i] = tap % g.KW - g.pad;
+        }
+        bool nvalid[BNI];
+#pragma unroll
+        for (int i = 0; i < BNI; ++i) nvalid[i] = (chunk * 8 < BN) && (n0 + i * 64 + chunk * 8 < g.out_pitch);
         int oy[4], ox[4], nimg[4];
         long long mrow[4];
 #pragma unroll
@@ -129,12 +152,6 @@ conv_wgrad_tcgen05_kernel(const bf16* __restrict__ x, const bf16* __restrict__ d
             const long long t = mm / g.Wo;
             oy[j] = (int)(t % g.Ho);
             nimg[j] = (int)(t / g.Ho);
-        }
-        int dyo[2], dxo[2];
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            dyo[i] = tap_i[i] / g.KW - g.pad;
-            dxo[i] = tap_i[i] % g.KW - g.pad;
         }
         constexpr int LAG = STAGES - 1;
         for (int st = 0; st < nstages; ++st) {
@@ -149,22 +166,24 @@ conv_wgrad_tcgen05_kernel(const bf16* __restrict__ x, const bf16* __restrict__ d
                 const uint32_t soff = r * 128 + ((chunk ^ (r & 7)) << 4);
 #pragma unroll
                 for (int i = 0; i < 2; ++i) {
-                    bool ok = mok && valid_i[i];
+                    bool ok = mok && kvalid[i];
                     int sy = 0, sx = 0;
                     if (ok) {
                         sy = map_fast(oy[j] * g.stride + dyo[i], g.Hv, g.pad_mode, g.up);
                         sx = map_fast(ox[j] * g.stride + dxo[i], g.Wv, g.pad_mode, g.up);
                         ok = sy >= 0 && sx >= 0;
                     }
-                    const bf16* src = ok ? x + ((size_t)((size_t)nimg[j] * g.H * g.W + (size_t)sy * g.W + sx) * g.in_pitch +
-                                                cb_i[i] * 64 + chunk * 8)
-                                         : x;
+                    const bf16* src = ok ? a.x + ((size_t)((size_t)nimg[j] * g.H * g.W + (size_t)sy * g.W + sx) * g.Cin + coff[i])
+                                         : a.x;
                     cp_async_16(a_base + i * IMG_BYTES + soff, src, ok ? 16u : 0u);
+                    if (NPL == 2) cp_async_16(a_base + Cfg::A_PLANE + i * IMG_BYTES + soff, ok ? src + a.x_plane : src, ok ? 16u : 0u);
                 }
 #pragma unroll
-                for (int i = 0; i < BN / 64; ++i) {
-                    const bf16* src = mok ? dy + (size_t)mrow[j] * g.out_pitch + n0 + i * 64 + chunk * 8 : dy;
-                    cp_async_16(b_base + i * IMG_BYTES + soff, src, mok ? 16u : 0u);
+                for (int i = 0; i < BNI; ++i) {
+                    const bool ok = mok && nvalid[i];
+                    const bf16* src = ok ? a.dy + (size_t)mrow[j] * g.out_pitch + n0 + i * 64 + chunk * 8 : a.dy;
+                    cp_async_16(b_base + i * IMG_BYTES + soff, src, ok ? 16u : 0u);
+                    if (NPL == 2) cp_async_16(b_base + Cfg::B_PLANE + i * IMG_BYTES + soff, ok ? src + a.dy_plane : src, ok ? 16u : 0u);
                 }
                 // advance this row slot by one stage (64 pixels)
                 mrow[j] += BP;
@@ -185,29 +204,30 @@ conv_wgrad_tcgen05_kernel(const bf16* __restrict__ x, const bf16* __restrict__ d
         fence_proxy_async();
         for (int st = (nstages > LAG ? nstages - LAG : 0); st < nstages; ++st) mbar_arrive(full_bar(st % STAGES));
 
-        // ============================== epilogue: coalesced fp32 reductions into ws[co][tap][ci] ==============================
+        // ============================== epilogue: coalesced fp32 reductions into ws[co][tap * Cin + ci] ==============================
         mbar_wait(tmem_full_bar, 0);
         tc_fence_after();
         const int row = warp * 32 + lane;
-        const int img = row >> 6, ch = row & 63;
-        const bool rok = valid_i[img];
-        float* wrow = ws + ((size_t)tap_i[img] * g.Cin + cb_i[img] * 64 + ch);
-        const size_t co_stride = (size_t)taps * g.Cin;
+        const int kf = (2 * blockIdx.x) * 64 + row;
+        const bool rok = kf < ktot;
+        float* wrow = a.ws + kf;
 #pragma unroll 1
-        for (int jb = 0; jb < BN / 32; ++jb) {
-            uint32_t raw[32];
-            tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(jb * 32), raw);
+        for (int jb = 0; jb < BN / 16; ++jb) {
+            const int nb = n0 + jb * 16;
+            if (nb >= g.Cout) break;
+            uint32_t raw[16];
+            tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(jb * 16), raw);
             if (rok) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) atomicAdd(wrow + (size_t)(n0 + jb * 32 + i) * co_stride, __uint_as_float(raw[i]));
+                for (int i = 0; i < 16; ++i)
+                    if (nb + i < g.Cout) atomicAdd(wrow + (size_t)(nb + i) * ktot, __uint_as_float(raw[i]));
             }
         }
         tc_fence_before();
     } else if (lane == 0) {
         // ============================== MMA issuer ==============================
         constexpr uint32_t idesc = make_idesc_bf16_mn(BN);
-        const uint32_t lbo = swap_lbo_sbo ? 1024u : (uint32_t)IMG_BYTES;
-        const uint32_t sbo = swap_lbo_sbo ? (uint32_t)IMG_BYTES : 1024u;
+        constexpr uint32_t lbo = (uint32_t)IMG_BYTES, sbo = 1024u;
         for (int st = 0; st < nstages; ++st) {
             const int s = st % STAGES;
             const uint32_t ph = (uint32_t)(st / STAGES) & 1u;
@@ -215,9 +235,15 @@ conv_wgrad_tcgen05_kernel(const bf16* __restrict__ x, const bf16* __restrict__ d
             tc_fence_after();
 #pragma unroll
             for (int k = 0; k < BP / 16; ++k) {      // 16 pixels = two 8-row swizzle atoms = 2048 bytes per K step
-                const uint64_t adesc = make_mnmajor_sw128_desc(a_smem(s) + k * 2048, lbo, sbo);
-                const uint64_t bdesc = make_mnmajor_sw128_desc(b_smem(s) + k * 2048, lbo, sbo);
-                umma_bf16(tmem_base, adesc, bdesc, idesc, (uint32_t)((st | k) != 0));
+                const uint64_t a_hi = make_mnmajor_sw128_desc(a_smem(s) + k * 2048, lbo, sbo);
+                const uint64_t b_hi = make_mnmajor_sw128_desc(b_smem(s) + k * 2048, lbo, sbo);
+                umma_bf16(tmem_base, a_hi, b_hi, idesc, (uint32_t)((st | k) != 0));
+                if (NPASS == 3) {
+                    const uint64_t a_lo = make_mnmajor_sw128_desc(a_smem(s) + Cfg::A_PLANE + k * 2048, lbo, sbo);
+                    const uint64_t b_lo = make_mnmajor_sw128_desc(b_smem(s) + Cfg::B_PLANE + k * 2048, lbo, sbo);
+                    umma_bf16(tmem_base, a_lo, b_hi, idesc, 1u);
+                    umma_bf16(tmem_base, a_hi, b_lo, idesc, 1u);
+                }
             }
             umma_commit(empty_bar(s));
         }
@@ -226,11 +252,11 @@ conv_wgrad_tcgen05_kernel(const bf16* __restrict__ x, const bf16* __restrict__ d
     __syncthreads();
     if (warp == 4) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, BN);
+        tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
     }
 }
 
-// dw_oihw[co][ci][tap] += ws[co][tap][ci]   (ci < Cin_w: channel padding of the stored input is dropped)
+// dw_oihw[co][ci][tap] += ws[co][tap * Cx + ci]   (ci < Cin_w: channel padding of the stored input is dropped)
 __global__ void wgrad_unpack_kernel(const float* __restrict__ ws, float* __restrict__ dw, int Cout, int Cin_w, int Cx, int taps) {
     const long long total = (long long)Cout * Cin_w * taps;
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
@@ -242,11 +268,11 @@ __global__ void wgrad_unpack_kernel(const float* __restrict__ ws, float* __restr
     }
 }
 
-template <int BN>
-int launch_wg(const void* x, const void* dy, float* ws, const ConvGeom& g, int swap, cudaStream_t st) {
-    using Cfg = WgCfg<BN>;
+template <int BN, int NPASS>
+int launch_wg(WgArgs& a, cudaStream_t st) {
+    using Cfg = WgCfg<BN, NPASS>;
     static bool configured = false;
-    auto kern = conv_wgrad_tcgen05_kernel<BN>;
+    auto kern = conv_wgrad_tcgen05_kernel<BN, NPASS>;
     if (!configured) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) != cudaSuccess) {
             affgw_set_error("conv_wgrad_tc: cannot reserve %d bytes of shared memory", Cfg::SMEM_BYTES);
@@ -254,9 +280,11 @@ int launch_wg(const void* x, const void* dy, float* ws, const ConvGeom& g, int s
         }
         configured = true;
     }
-    const int taps = g.KH * g.KW, total64 = taps * (g.Cin / 64);
-    const int gx = (total64 + 1) / 2, gy = g.Cout / BN;
-    long long splits = (2LL * 148 + (long long)gx * gy - 1) / ((long long)gx * gy);
+    const ConvGeom& g = a.g;
+    const int ktot = g.KH * g.KW * g.Cin;
+    const int gx = (ktot + 127) / 128, gy = (g.Cout + BN - 1) / BN;
+    const long long per_wave = 148LL * (NPASS == 3 ? 1 : 2);
+    long long splits = (2 * per_wave + (long long)gx * gy - 1) / ((long long)gx * gy);
     const long long max_splits = (g.M + 511) / 512;
     if (splits > max_splits) splits = max_splits;
     if (splits < 1) splits = 1;
@@ -264,42 +292,55 @@ int launch_wg(const void* x, const void* dy, float* ws, const ConvGeom& g, int s
     long long mps = (g.M + splits - 1) / splits;
     mps = (mps + BP - 1) / BP * BP;
     splits = (g.M + mps - 1) / mps;
+    a.m_per_split = mps;
     dim3 grid(gx, gy, (unsigned)splits);
-    kern<<<grid, NUM_THREADS, Cfg::SMEM_BYTES, st>>>((const bf16*)x, (const bf16*)dy, ws, g, mps, swap);
+    kern<<<grid, NUM_THREADS, Cfg::SMEM_BYTES, st>>>(a);
     AFFGW_LAUNCH_CHECK("conv_wgrad_tcgen05");
     return 0;
 }
 
+template <int BN>
+int launch_wg_p(WgArgs& a, int passes, cudaStream_t st) {
+    return passes == 3 ? launch_wg<BN, 3>(a, st) : launch_wg<BN, 1>(a, st);
+}
+
 }  // namespace
 
-// g.Cin must be the STORED channel count of x (multiple of 64); cin_w the parameter's input channels (<= g.Cin)
-int conv_wgrad_tc_ok(const ConvGeom& g, int x_dt, int dy_dt) {
-    if (x_dt != AFFGW_BF16 || dy_dt != AFFGW_BF16) return 0;
-    if (g.Cin % 64 != 0 || g.in_pitch != g.Cin || g.Cout % 64 != 0 || g.out_pitch != g.Cout) return 0;
+int conv_tc_block_n(int cout);
+
+// g.Cin must be the STORED channel count of the x planes, g.out_pitch that of the dY planes (multiples of 8)
+int conv_wgrad_tc_ok(const ConvGeom& g) {
+    if (g.Cin % 8 != 0 || g.in_pitch != g.Cin || g.out_pitch % 8 != 0 || g.out_pitch < g.Cout) return 0;
     if (g.pre_act != ACT_NONE || g.zi != 1) return 0;
     if ((long long)g.N * g.H * g.W >= (1LL << 31)) return 0;
-    return (g.Cout % 128 == 0) ? 128 : 64;
+    return conv_tc_block_n(g.Cout);
 }
 
 long long conv_wgrad_tc_ws_bytes(const ConvGeom& g) { return (long long)g.Cout * g.KH * g.KW * g.Cin * 4; }
 
-int conv_wgrad_tc(const void* x, const void* dy, float* dw, void* workspace, const ConvGeom& g, int cin_w, cudaStream_t st) {
-    const int bn = conv_wgrad_tc_ok(g, AFFGW_BF16, AFFGW_BF16);
-    if (!bn || !workspace) {
+int conv_wgrad_tc(const void* x_planes, long long x_plane, const void* dy_planes, long long dy_plane, float* dw, void* workspace,
+                  const ConvGeom& g, int cin_w, int passes, cudaStream_t st) {
+    const int bn = conv_wgrad_tc_ok(g);
+    if (!bn || !workspace || (passes != 1 && passes != 3)) {
         affgw_set_error("conv_wgrad_tc: unsupported shape or missing workspace");
         return -1;
-    }
-    static int swap = -1;
-    if (swap < 0) {
-        const char* e = getenv("AFFGW_WGRAD_SWAP_LBO_SBO");
-        swap = (e && e[0] == '1') ? 1 : 0;
     }
     float* ws = (float*)workspace;
     if (cudaMemsetAsync(ws, 0, (size_t)conv_wgrad_tc_ws_bytes(g), st) != cudaSuccess) {
         affgw_set_error("conv_wgrad_tc: memset failed");
         return -2;
     }
-    const int rc = bn == 128 ? launch_wg<128>(x, dy, ws, g, swap, st) : launch_wg<64>(x, dy, ws, g, swap, st);
+    WgArgs a;
+    a.x = (const bf16*)x_planes; a.x_plane = x_plane;
+    a.dy = (const bf16*)dy_planes; a.dy_plane = dy_plane;
+    a.ws = ws; a.g = g; a.m_per_split = 0;
+    int rc;
+    switch (bn) {
+        case 16: rc = launch_wg_p<16>(a, passes, st); break;
+        case 32: rc = launch_wg_p<32>(a, passes, st); break;
+        case 64: rc = launch_wg_p<64>(a, passes, st); break;
+        default: rc = launch_wg_p<128>(a, passes, st); break;
+    }
     if (rc) return rc;
     const int taps = g.KH * g.KW;
     const long long total = (long long)g.Cout * cin_w * taps;

@@ -12,7 +12,7 @@ from torch.autograd import Function
 
 from . import _lib as L  # noqa: N812
 
-_state = {"mode": "fp32", "force_simt": False, "simt_wgrad": False}
+_state = {"mode": "fp32", "passes": 3, "force_simt": False, "simt_wgrad": False}
 _err_flag = {}
 _profile = {"records": None}
 
@@ -54,19 +54,40 @@ class _timed:
 
 
 def set_precision(mode):
-    """'fp32' : fp32 storage + CUDA-core FFMA convolutions (<= 1e-4 against the CPU reference)
-       'bf16' : bf16 storage + tcgen05 tensor-core convolutions with fp32 accumulation (<= 2e-2)."""
-    if mode not in ("fp32", "bf16"):
-        raise ValueError("precision must be 'fp32' or 'bf16'")
+    """Activations, statistics and gradients are stored in fp32 in every mode; the mode selects the convolution engine:
+       'fp32'   : CUDA-core FFMA convolutions (<= 1e-4 against the CPU reference)
+       'bf16'   : tcgen05 tensor-core convolutions on split-bf16 operands, three MMAs per product
+                  (a_hi*w_hi + a_lo*w_hi + a_hi*w_lo, fp32 TMEM accumulation) - the mode that meets the 2e-2 image bar
+       'bf16x1' : tcgen05 with one bf16 MMA per product (fastest; on this network the 2^-9 operand rounding is amplified
+                  to ~2e-1 on the image at random init, see DESIGN.md "precision")."""
+    if mode not in ("fp32", "bf16", "bf16x1"):
+        raise ValueError("precision must be 'fp32', 'bf16' or 'bf16x1'")
     _state["mode"] = mode
+    _state["passes"] = 1 if mode == "bf16x1" else 3
 
 
 def precision():
     return _state["mode"]
 
 
+class conv_passes:
+    """Context manager: run the tensor-core convolutions issued inside with `n` (1 or 3) MMAs per product."""
+
+    def __init__(self, n):
+        assert n in (1, 3)
+        self.n = n
+
+    def __enter__(self):
+        self.prev = _state["passes"]
+        if _state["mode"] != "fp32":
+            _state["passes"] = self.n
+
+    def __exit__(self, *a):
+        _state["passes"] = self.prev
+
+
 def act_dtype():
-    return torch.bfloat16 if _state["mode"] == "bf16" else torch.float32
+    return torch.float32
 
 
 def force_simt(flag=True):
@@ -231,19 +252,32 @@ def _pack(weight, dtype, ipad, flip):
     return _WeightCache.get(weight, ("plain", dtype, ipad, flip), build)
 
 
-def _pack_tc(weight, ipad, flip, bn):
+def _pack_tc(weight, ipad, flip, passes):
     w4 = _w4(weight.detach())
     co, ci, kh, kw = w4.shape
 
     def build():
-        nbytes = L.lib().affgw_pack_weight_tc_bytes(co, ci, kh, kw, ipad, int(flip), bn)
+        nbytes = L.lib().affgw_pack_weight_tc_bytes(co, ci, kh, kw, ipad, int(flip), passes)
         if nbytes <= 0:
-            raise RuntimeError("affgw_pack_weight_tc_bytes: " + L.last_error())
+            raise RuntimeError("affgw_pack_weight_tc_bytes: bad configuration")
         out = torch.empty(nbytes // 2, dtype=torch.bfloat16, device=weight.device)
-        L.call("affgw_pack_weight_tc", w4.contiguous().data_ptr(), out.data_ptr(), co, ci, kh, kw, ipad, int(flip), bn,
+        L.call("affgw_pack_weight_tc", w4.contiguous().data_ptr(), out.data_ptr(), co, ci, kh, kw, ipad, int(flip), passes,
                L.stream())
         return out
-    return _WeightCache.get(weight, ("tc", ipad, flip, bn), build)
+    return _WeightCache.get(weight, ("tc", ipad, flip, passes), build)
+
+
+def _up8(c):
+    return (c + 7) // 8 * 8
+
+
+def _split_planes(x, rows, c, pitch, passes, pre_act="none"):
+    """fp32 activations [rows][pitch] -> bf16 operand planes [1 or 2][rows][c_store] of the tcgen05 kernels."""
+    cs = _up8(c)
+    planes = torch.empty((2 if passes == 3 else 1, rows, cs), dtype=torch.bfloat16, device=x.device)
+    L.call("affgw_split_planes", x.data_ptr(), L.dt(x), planes.data_ptr(), rows, c, pitch, cs, passes, L.ACT[pre_act],
+           L.stream())
+    return planes
 
 
 def _conv_geom(x, weight, cfg):
@@ -269,41 +303,29 @@ def _conv_geom(x, weight, cfg):
     return dict(N=n, H=h, W=w, Cx=cx, pitch=pitch, Cout=co, Cin=ci, KH=kh, KW=kw, Ho=ho, Wo=wo, two_d=x.dim() == 2)
 
 
-def _desc(g, cfg, cin, x_dt, w_dt, y_dt, algo, out_pitch=None):
+def _desc(g, cfg, cin, x_dt, w_dt, y_dt, algo, in_pitch=None, out_pitch=None, passes=1, grad_dt=0, pre_act=None):
     d = L.ConvDesc()
     d.N, d.H, d.W, d.Cin = g["N"], g["H"], g["W"], cin
     d.Cout, d.KH, d.KW = g["Cout"], g["KH"], g["KW"]
     d.stride, d.pad, d.pad_mode, d.upsample = cfg.stride, cfg.pad, L.PAD[cfg.pad_mode], cfg.upsample
     d.Ho, d.Wo = g["Ho"], g["Wo"]
-    d.in_pitch, d.out_pitch = g["pitch"], out_pitch or g["Cout"]
-    d.pre_act, d.post_act = L.ACT[cfg.pre_act], L.ACT[cfg.post_act]
+    d.in_pitch, d.out_pitch = in_pitch or g["pitch"], out_pitch or g["Cout"]
+    d.pre_act, d.post_act = L.ACT[cfg.pre_act if pre_act is None else pre_act], L.ACT[cfg.post_act]
     d.x_dtype, d.w_dtype, d.y_dtype = x_dt, w_dt, y_dt
-    d.algo = algo
+    d.algo, d.passes, d.grad_dtype = algo, passes, grad_dt
     return d
-
-
-def _tc_ok(d):
-    if _state["mode"] != "bf16" or _state["force_simt"]:
-        return 0
-    return L.lib().affgw_conv_tc_block_n(C.byref(d))
 
 
 class _Conv2d(Function):
     @staticmethod
     def forward(ctx, x, weight, bias, addend, cfg):
         L.require_cuda(x, weight)
+        if x.dtype != torch.float32:
+            raise RuntimeError("conv2d: activations are fp32 tensors (operand rounding happens inside the convolution)")
         g = _conv_geom(x, weight, cfg)
-        y_dtype = cfg.out_dtype or x.dtype
-        x_dt, y_dt = L.dt(x), (L.F32 if y_dtype == torch.float32 else L.BF16)
-        w_dt = L.BF16 if x.dtype == torch.bfloat16 else L.F32
-        # tensor-core route: gather 64-channel slices, so the channel count seen by the kernel is the stored one
-        d = _desc(g, cfg, g["Cx"], x_dt, w_dt, y_dt, L.ALGO_TC)
-        bn = _tc_ok(d) if g["Cx"] == g["pitch"] else 0
-        if bn:
-            wp = _pack_tc(weight, g["Cx"], False, bn)
-        else:
-            d = _desc(g, cfg, g["Cin"], x_dt, w_dt, y_dt, L.ALGO_SIMT)
-            wp = _pack(weight, torch.bfloat16 if w_dt == L.BF16 else torch.float32, g["Cin"], False)
+        y_dtype = torch.float32
+        use_tc = _state["mode"] != "fp32" and not _state["force_simt"]
+        passes = _state["passes"]
         if g["two_d"]:
             y = torch.empty((g["N"], g["Cout"]), dtype=y_dtype, device=x.device)
         else:
@@ -312,83 +334,107 @@ class _Conv2d(Function):
             addend = _dense_cl(addend, y_dtype)
         b32 = None if bias is None else bias.detach()
         flops = 2.0 * g["N"] * g["Ho"] * g["Wo"] * g["Cout"] * g["Cin"] * g["KH"] * g["KW"]
-        with _timed("conv_fwd_tcgen05" if bn else "conv_fwd_simt", flops):
-            L.call("affgw_conv2d_fwd", x.data_ptr(), wp.data_ptr(), L.ptr(b32), L.ptr(addend), y.data_ptr(), C.byref(d),
-                   L.stream())
-        ctx.cfg, ctx.g = cfg, g
+        planes = None
+        if use_tc:
+            cs = _up8(g["Cin"])
+            d = _desc(g, cfg, g["Cin"], L.BF16, L.BF16, L.F32, L.ALGO_TC, in_pitch=cs, passes=passes, pre_act="none")
+            if not L.lib().affgw_conv_tc_supported(C.byref(d)):
+                raise RuntimeError("conv2d: tcgen05 kernel refused the shape: " + L.last_error())
+            planes = _split_planes(x, g["N"] * g["H"] * g["W"], g["Cin"], g["pitch"], passes, cfg.pre_act)
+            wp = _pack_tc(weight, cs, False, passes)
+            with _timed("conv_fwd_tcgen05", flops):
+                L.call("affgw_conv2d_fwd", planes.data_ptr(), wp.data_ptr(), L.ptr(b32), L.ptr(addend), y.data_ptr(),
+                       C.byref(d), L.stream())
+        else:
+            d = _desc(g, cfg, g["Cin"], L.F32, L.F32, L.F32, L.ALGO_SIMT)
+            wp = _pack(weight, torch.float32, g["Cin"], False)
+            with _timed("conv_fwd_simt", flops):
+                L.call("affgw_conv2d_fwd", x.data_ptr(), wp.data_ptr(), L.ptr(b32), L.ptr(addend), y.data_ptr(), C.byref(d),
+                       L.stream())
+        ctx.cfg, ctx.g, ctx.use_tc, ctx.passes = cfg, g, use_tc, passes
         ctx.has_bias, ctx.has_addend = bias is not None, addend is not None
-        ctx.save_for_backward(x, weight, y if cfg.post_act != "none" else None)
+        keep_x = (not use_tc) or cfg.pre_act != "none"
+        ctx.save_for_backward(x if keep_x else None, weight, y if cfg.post_act != "none" else None, planes)
+        ctx.x_meta = (x.shape, x.device)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, weight, y = ctx.saved_tensors
-        cfg, g = ctx.cfg, ctx.g
+        x, weight, y, planes = ctx.saved_tensors
+        cfg, g, passes = ctx.cfg, ctx.g, ctx.passes
         need_x, need_w, need_b, need_a = ctx.needs_input_grad[:4]
-        y_dtype = cfg.out_dtype or x.dtype
-        dz = _dense_cl(dy, y_dtype)
+        dev = ctx.x_meta[1]
+        dz = _dense_cl(dy, torch.float32)
         if cfg.post_act != "none":
             t = torch.empty_like(dz)
             L.call("affgw_act_bwd", dz.data_ptr(), y.data_ptr(), t.data_ptr(), L.dt(dz), dz.numel(), L.ACT[cfg.post_act],
                    L.stream())
             dz = t
         st = L.stream()
-        x_dt, y_dt = L.dt(x), L.dt(dz)
-        w_dt = L.BF16 if x.dtype == torch.bfloat16 else L.F32
         M = g["N"] * g["Ho"] * g["Wo"]
+        cin, cout = g["Cin"], g["Cout"]
         db = dw = dx = None
         if ctx.has_bias and need_b:
-            db = torch.zeros(g["Cout"], dtype=torch.float32, device=x.device)
-            L.call("affgw_colsum", dz.data_ptr(), y_dt, db.data_ptr(), M, g["Cout"], g["Cout"], st)
+            db = torch.zeros(cout, dtype=torch.float32, device=dev)
+            L.call("affgw_colsum", dz.data_ptr(), L.F32, db.data_ptr(), M, cout, cout, st)
         fwd_cfg = cfg._replace(post_act="none")
+        flops = 2.0 * M * cout * cin * g["KH"] * g["KW"]
+        use_tc = ctx.use_tc
+        if use_tc and (need_w or need_x):
+            cs, cso = _up8(cin), _up8(cout)
+            dzp = _split_planes(dz, M, cout, cout, passes)
         if need_w:
-            dw = torch.zeros(weight.shape, dtype=torch.float32, device=x.device)
-            d = _desc(g, fwd_cfg, g["Cin"], x_dt, w_dt, y_dt, L.ALGO_TC)
-            flops = 2.0 * M * g["Cout"] * g["Cin"] * g["KH"] * g["KW"]
-            ws_bytes = 0
-            if _state["mode"] == "bf16" and not _state["force_simt"] and not _state["simt_wgrad"]:
+            dw = torch.zeros(weight.shape, dtype=torch.float32, device=dev)
+            if use_tc and not _state["simt_wgrad"]:
+                d = _desc(g, fwd_cfg, cin, L.BF16, L.BF16, L.BF16, L.ALGO_TC, in_pitch=cs, out_pitch=cso, passes=passes)
                 ws_bytes = L.lib().affgw_conv2d_wgrad_ws_bytes(C.byref(d))
-            if ws_bytes > 0:
-                wsb = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+                if ws_bytes <= 0:
+                    raise RuntimeError("conv2d_wgrad: tcgen05 kernel refused the shape: " + L.last_error())
+                wsb = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
                 with _timed("conv_wgrad_tcgen05", flops):
-                    L.call("affgw_conv2d_wgrad", x.data_ptr(), dz.data_ptr(), dw.data_ptr(), wsb.data_ptr(), C.byref(d), st)
+                    L.call("affgw_conv2d_wgrad", planes.data_ptr(), dzp.data_ptr(), dw.data_ptr(), wsb.data_ptr(), C.byref(d), st)
             else:
-                d.algo = L.ALGO_SIMT
+                if x is None:
+                    raise RuntimeError("conv2d backward: the CUDA-core wgrad needs the saved fp32 input")
+                d = _desc(g, fwd_cfg, cin, L.F32, L.F32, L.F32, L.ALGO_SIMT)
                 with _timed("conv_wgrad_simt", flops):
                     L.call("affgw_conv2d_wgrad", x.data_ptr(), dz.data_ptr(), dw.data_ptr(), None, C.byref(d), st)
         if need_x:
-            if x.dtype != dz.dtype:
-                dz_x = _cast(dz, x.dtype)
+            if use_tc:
+                if g["two_d"]:
+                    dx = torch.empty((g["N"], cin), dtype=torch.float32, device=dev)
+                else:
+                    dx = empty_cl(g["N"], cin, g["H"], g["W"], torch.float32, dev)
+                d = _desc(g, fwd_cfg, cin, L.BF16, L.BF16, L.BF16, L.ALGO_TC, in_pitch=cs, out_pitch=cso, passes=passes,
+                          grad_dt=L.F32)
+                wt = _pack_tc(weight, cso, True, passes)
+                base = dx
             else:
-                dz_x = dz
-            cin = g["Cin"]
-            if g["Cx"] != cin and not (cfg.pad_mode == "zero" and cfg.upsample == 1 and cfg.pre_act == "none"):
-                raise RuntimeError("conv2d backward: channel-padded input needs a zero-pad, stride-1 convolution")
-            dense = g["pitch"] == cin
-            if g["two_d"]:
-                base = torch.empty((g["N"], cin), dtype=x.dtype, device=x.device) if dense else \
-                    torch.zeros((g["N"], g["pitch"]), dtype=x.dtype, device=x.device)
-                dx = base if dense else base[:, :g["Cx"]]
-            else:
-                base = empty_cl(g["N"], g["pitch"], g["H"], g["W"], x.dtype, x.device, zero=not dense)
-                dx = base if dense else base[:, :g["Cx"]]
-            d = _desc(g, fwd_cfg, cin, L.dt(x), w_dt, L.dt(x), L.ALGO_TC)
-            bn = 0
-            if _state["mode"] == "bf16" and not _state["force_simt"]:
-                bn = L.lib().affgw_conv_tc_dgrad_block_n(C.byref(d))
-            if bn:
-                wt = _pack_tc(weight, g["Cout"], True, bn)
-            else:
-                d.algo = L.ALGO_SIMT
-                wt = _pack(weight, torch.bfloat16 if w_dt == L.BF16 else torch.float32, g["Cout"], True)
+                if g["Cx"] != cin and not (cfg.pad_mode == "zero" and cfg.upsample == 1 and cfg.pre_act == "none"):
+                    raise RuntimeError("conv2d backward: channel-padded input needs a zero-pad, stride-1 convolution")
+                dense = g["pitch"] == cin
+                if g["two_d"]:
+                    base = torch.empty((g["N"], cin), dtype=torch.float32, device=dev) if dense else \
+                        torch.zeros((g["N"], g["pitch"]), dtype=torch.float32, device=dev)
+                    dx = base if dense else base[:, :g["Cx"]]
+                else:
+                    base = empty_cl(g["N"], g["pitch"], g["H"], g["W"], torch.float32, dev, zero=not dense)
+                    dx = base if dense else base[:, :g["Cx"]]
+                d = _desc(g, fwd_cfg, cin, L.F32, L.F32, L.F32, L.ALGO_SIMT)
+                wt = _pack(weight, torch.float32, cout, True)
             ws_bytes = L.lib().affgw_conv2d_dgrad_ws_bytes(C.byref(d))
             if ws_bytes < 0:
                 raise RuntimeError("conv2d_dgrad_ws_bytes: " + L.last_error())
-            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device) if ws_bytes else None
-            flops = 2.0 * M * g["Cout"] * cin * g["KH"] * g["KW"]
-            with _timed("conv_dgrad_tcgen05" if bn else "conv_dgrad_simt", flops):
-                L.call("affgw_conv2d_dgrad", dz_x.data_ptr(), wt.data_ptr(), x.data_ptr(), base.data_ptr(), L.ptr(ws),
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev) if ws_bytes else None
+            src = dzp if use_tc else dz
+            with _timed("conv_dgrad_tcgen05" if use_tc else "conv_dgrad_simt", flops):
+                L.call("affgw_conv2d_dgrad", src.data_ptr(), wt.data_ptr(), L.ptr(x), base.data_ptr(), L.ptr(ws),
                        C.byref(d), st)
+            if use_tc and g["Cx"] != cin:      # the weight reads only the first `cin` channels of a wider input
+                full = torch.zeros(ctx.x_meta[0], dtype=torch.float32, device=dev).contiguous(memory_format=torch.channels_last) \
+                    if len(ctx.x_meta[0]) == 4 else torch.zeros(ctx.x_meta[0], dtype=torch.float32, device=dev)
+                full[:, :cin] = dx
+                dx = full
         da = dz if (ctx.has_addend and need_a) else None
         return dx, dw, db, da, None
 

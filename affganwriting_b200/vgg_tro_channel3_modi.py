@@ -74,7 +74,8 @@ class VGG(nn.Module):
 
 
 def _pad64(c):
-    return (c + 63) // 64 * 64 if ops.precision() == "bf16" else c
+    # channel padding to the tensor-core gather granule now happens inside the convolution (affgw_split_planes)
+    return c
 
 
 def vgg19_bn(pretrained=False, **kwargs):

@@ -162,6 +162,7 @@ def main():
     ap.add_argument("--impl", default="affgw", choices=["affgw", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="timed steps only (no e2e / generation / CPU legs): the command ncu profiles")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "affgw" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
@@ -237,6 +238,12 @@ def main():
     value = world / (ms_step / 1e3)                       # whole-job steps/s: every rank completes one step per step time
 
     # ---- end to end through the public API: pinned host batch -> H2D -> step -> losses read back
+    if args.quick:
+        if rank == 0:
+            print(json.dumps({"quick": True, "ms_per_step": ms_step, "gpu_launches": launches}), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
     step_e2e()
     ms_e2e = timed(step_e2e, args.steps) / args.steps
     e2e_value = world / (ms_e2e / 1e3)

@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define AFFGW_VERSION 100
+#define AFFGW_VERSION 101
 
 enum { AFFGW_DT_F32 = 0, AFFGW_DT_BF16 = 1 };
 enum { AFFGW_ACT_NONE = 0, AFFGW_ACT_RELU = 1, AFFGW_ACT_LRELU = 2, AFFGW_ACT_TANH = 3 };
@@ -42,6 +42,13 @@ typedef struct affgw_conv_desc {
     int32_t post_act;            /* activation applied to the result                                          */
     int32_t x_dtype, w_dtype, y_dtype;
     int32_t algo;                /* AFFGW_ALGO_*                                                              */
+    /* --- tcgen05 route only (algo = AFFGW_ALGO_TCGEN05) ------------------------------------------------------
+     * Operands are bf16 "operand planes" made by affgw_split_planes: [planes][pixels][c_store], c_store % 8 == 0,
+     * plane 0 = bf16(v), plane 1 = bf16(v - plane0) (present when passes = 3).  x_dtype = w_dtype = BF16, pre_act is
+     * applied by affgw_split_planes (keep it here only for the dgrad fold), in_pitch = c_store of the x planes,
+     * out_pitch = pitch of y (forward) or c_store of the dY planes (dgrad / wgrad).                              */
+    int32_t passes;              /* 1: a_hi*w_hi; 3: split-bf16 a_hi*w_hi + a_lo*w_hi + a_hi*w_lo                */
+    int32_t grad_dtype;          /* dtype of dx (and of x when the fold needs the pre-activation derivative)   */
 } affgw_conv_desc;
 
 int affgw_version(void);
@@ -57,23 +64,29 @@ int affgw_device_ok(void);
  * [Cin][KH][KW][cout_pad] with mirrored taps (transpose_flip = 1), in out_dtype. */
 int affgw_pack_weight(const float* w_oihw, void* out, int out_dtype, int Cout, int Cin, int KH, int KW, int i_pad,
                       int transpose_flip, void* stream);
-/* same, into the 128B-swizzled shared-memory tile image the tcgen05 kernel bulk-copies (bf16) */
+/* same, into the 128B-swizzled shared-memory tile images the tcgen05 kernel bulk-copies (bf16; hi and lo tiles when
+ * passes = 3).  i_pad = c_store of the operand planes the weight will meet (x planes, or dY planes for transpose_flip). */
 int affgw_pack_weight_tc(const float* w_oihw, void* out, int Cout, int Cin, int KH, int KW, int i_pad, int transpose_flip,
-                         int block_n, void* stream);
-long long affgw_pack_weight_tc_bytes(int Cout, int Cin, int KH, int KW, int i_pad, int transpose_flip, int block_n);
-int affgw_conv_tc_block_n(const affgw_conv_desc* d);    /* tile width the tcgen05 kernel uses for this conv, 0 = n/a */
-int affgw_conv_tc_dgrad_block_n(const affgw_conv_desc* d); /* same for the dgrad of the forward described by d */
+                         int passes, void* stream);
+long long affgw_pack_weight_tc_bytes(int Cout, int Cin, int KH, int KW, int i_pad, int transpose_flip, int passes);
+/* activation tensor [rows][pitch] (fp32 or bf16) -> operand planes [passes == 3 ? 2 : 1][rows][c_store] (bf16), with the
+ * activation_first non-linearity (blocks.py:151-153) applied and channels C..c_store-1 zero-filled */
+long long affgw_operand_planes_bytes(long long rows, int c_store, int passes);
+int affgw_split_planes(const void* x, int x_dtype, void* planes, long long rows, int C, int pitch, int c_store, int passes,
+                       int pre_act, void* stream);
+int affgw_conv_tc_supported(const affgw_conv_desc* d);   /* 1 if the tcgen05 kernel takes this convolution */
 
 int affgw_conv2d_fwd(const void* x, const void* w_packed, const float* bias, const void* addend, void* y,
                      const affgw_conv_desc* d, void* stream);
-/* gradient w.r.t. x of the forward described by d.  dy:[N,Ho,Wo,Cout] (y_dtype), w_packed_t from
- * affgw_pack_weight(..., transpose_flip = 1), x only read when pre_act != NONE.  workspace holds the gradient
- * w.r.t. the padded/upsampled virtual input before it is folded back (reflect halo, x2 nearest). */
+/* gradient w.r.t. x of the forward described by d.  dy:[N,Ho,Wo,Cout] (y_dtype; operand planes on the tcgen05 route),
+ * w_packed_t from affgw_pack_weight[_tc](..., transpose_flip = 1), x only read when pre_act != NONE.  workspace holds
+ * the gradient w.r.t. the padded/upsampled virtual input before it is folded back (reflect halo, x2 nearest).
+ * On the tcgen05 route dx is a dense [N,H,W,Cin] tensor of grad_dtype. */
 long long affgw_conv2d_dgrad_ws_bytes(const affgw_conv_desc* d);
 int affgw_conv2d_dgrad(const void* dy, const void* w_packed_t, const void* x, void* dx, void* workspace,
                        const affgw_conv_desc* d, void* stream);
-/* dw (OIHW fp32) += dY^T * gather(x); caller zeroes dw first.  With algo = TCGEN05 the split-K partials are reduced in
- * `workspace` (affgw_conv2d_wgrad_ws_bytes, 0 = the shape is not tensor-core eligible, use algo = SIMT, no workspace). */
+/* dw (OIHW fp32) += dY^T * gather(x); caller zeroes dw first.  With algo = TCGEN05 x and dy are operand planes and the
+ * split-K partials are reduced in `workspace` (affgw_conv2d_wgrad_ws_bytes; 0 = not eligible, use algo = SIMT). */
 long long affgw_conv2d_wgrad_ws_bytes(const affgw_conv_desc* d);
 int affgw_conv2d_wgrad(const void* x, const void* dy, float* dw_oihw, void* workspace, const affgw_conv_desc* d, void* stream);
 /* out[c] += sum_m a[m][c]  (bias gradient); caller zeroes out */

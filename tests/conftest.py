@@ -39,7 +39,7 @@ def golden():
     return load
 
 
-@pytest.fixture(params=["fp32", "bf16"])
+@pytest.fixture(params=["fp32", "bf16", "bf16x1"])
 def mode(request):
     import affganwriting_b200 as A
     A.set_precision(request.param)

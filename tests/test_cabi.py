@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol():
     assert len(names) >= 45
     for n in names:
         assert hasattr(h, n), n
-    assert h.affgw_version() == 100
+    assert h.affgw_version() == 101
 
 
 def test_python_binding_covers_the_header():
@@ -48,18 +48,25 @@ def test_host_side_argument_validation_needs_no_gpu():
     from affganwriting_b200 import _lib
     h = _lib.lib()
     d = _lib.ConvDesc()
-    assert h.affgw_conv_tc_block_n(ctypes.byref(d)) == 0
+    assert h.affgw_conv_tc_supported(ctypes.byref(d)) == 0
     assert b"non-positive" in h.affgw_last_error()
     d.N, d.H, d.W, d.Cin, d.Cout, d.KH, d.KW = 2, 8, 27, 512, 512, 3, 3
     d.stride, d.pad, d.pad_mode, d.upsample, d.Ho, d.Wo = 1, 1, 1, 1, 8, 27
     d.in_pitch, d.out_pitch, d.x_dtype, d.w_dtype, d.y_dtype = 512, 512, 1, 1, 1
-    assert h.affgw_conv_tc_block_n(ctypes.byref(d)) == 128
-    assert h.affgw_conv2d_dgrad_ws_bytes(ctypes.byref(d)) == 2 * 10 * 29 * 512 * 2     # reflect: folded path
+    d.algo, d.passes, d.grad_dtype = 2, 3, 0
+    assert h.affgw_conv_tc_supported(ctypes.byref(d)) == 1
+    assert h.affgw_conv2d_dgrad_ws_bytes(ctypes.byref(d)) == 2 * 10 * 29 * 512 * 4     # reflect: folded path, fp32 dx
     d.pad_mode = 0
     assert h.affgw_conv2d_dgrad_ws_bytes(ctypes.byref(d)) == 0                          # zero pad: direct
+    d.passes = 2
+    assert h.affgw_conv_tc_supported(ctypes.byref(d)) == 0 and b"passes" in h.affgw_last_error()
+    d.passes = 1
     d.Ho = 9
-    assert h.affgw_conv_tc_block_n(ctypes.byref(d)) == 0 and b"output extent" in h.affgw_last_error()
-    assert h.affgw_pack_weight_tc_bytes(512, 512, 3, 3, 512, 0, 128) == 512 * 512 * 9 * 2
+    assert h.affgw_conv_tc_supported(ctypes.byref(d)) == 0 and b"output extent" in h.affgw_last_error()
+    assert h.affgw_pack_weight_tc_bytes(512, 512, 3, 3, 512, 0, 1) == 512 * 512 * 9 * 2
+    assert h.affgw_pack_weight_tc_bytes(512, 512, 3, 3, 512, 0, 3) == 512 * 512 * 9 * 2 * 2
+    assert h.affgw_pack_weight_tc_bytes(512, 512, 3, 3, 510, 0, 1) < 0                 # c_store must be a multiple of 8
+    assert h.affgw_operand_planes_bytes(100, 56, 3) == 100 * 56 * 2 * 2
 
 
 @pytest.mark.parametrize("key,build", [("gen_c50", "gen"), ("dis", "dis"), ("cla", "cla")])

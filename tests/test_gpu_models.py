@@ -2,12 +2,13 @@
 
 fp32 mode   image <= 1e-4 max-abs against the image the REFERENCE produced (tests/golden/gen_fwd_c15_b4.npz);
             per-parameter gradient cosine >= 0.999 against autograd over the CPU oracle, norms against the reference's.
-bf16 mode   checked against the oracle evaluated under the bf16 storage model (oracle.storage_model("bf16"): the same
-            algorithm with operands / activations rounded to bfloat16 at the points where the product stores them):
-            image <= 2e-2 max-abs, gradient cosine >= 0.999 globally.  The distance of bf16 mode to the fp32 reference
-            is reported and bounded by what that storage model itself costs (measured here on the CPU: a 1e-6 input
-            perturbation moves the image by ~1e-4 on this random-init network, so 2^-9 operand rounding cannot stay
-            within 2e-2 of fp32 for ANY bf16 implementation; see DESIGN.md "precision").
+bf16 mode   (tcgen05 convolutions on split-bf16 operands, three MMAs per product) is held to BASELINE.json's bf16 bars
+            against the same fp32 references: image <= 2e-2 max-abs, gradient cosine >= 0.999.
+bf16x1 mode (one MMA per product) is checked against the oracle evaluated under the bf16 storage model
+            (oracle.storage_model("bf16"): the same algorithm with convolution operands rounded to bfloat16).  Its
+            distance to the fp32 reference is reported and bounded by what that model itself costs (measured on the CPU:
+            a 1e-6 input perturbation moves the image by ~1e-4 on this random-init network, so a single 2^-9 operand
+            rounding cannot stay within 2e-2 of fp32 for ANY implementation; see DESIGN.md "precision").
 """
 import numpy as np
 import pytest
@@ -73,13 +74,19 @@ def test_generator_forward_matches_reference(mode, specs, golden):
             assert abs(float(res[i].float().abs().mean()) - float(gold[f"result{i}.abs_mean"])) <= 1e-4
         assert rel_err(f_xt, torch.from_numpy(gold["f_xt"])) <= 1e-4
         stat_tol = 1e-4
+    elif mode == "bf16":
+        rms = float((xg.detach().cpu() - torch.from_numpy(gold["xg"])).pow(2).mean().sqrt())
+        print(f"\n[bf16] generated image error vs reference: max-abs {err_ref:.3e}, rms {rms:.3e}")
+        assert err_ref <= 2e-2
+        assert rel_err(f_xt, torch.from_numpy(gold["f_xt"])) <= 2e-3
+        stat_tol = 2e-3
     else:
         with torch.no_grad(), O.storage_model("bf16"):
             model = O.gen_forward(cpu["tr_img"], cpu["label_xt"], sd)
         ref = torch.from_numpy(gold["xg"])
         cost, cost_rms = _maxabs(model, ref), float((model - ref).pow(2).mean().sqrt())
         rms = float((xg.detach().cpu() - ref).pow(2).mean().sqrt())
-        print(f"\n[bf16] image error vs fp32 reference: max-abs {err_ref:.3e}, rms {rms:.3e}; the bf16 storage model itself "
+        print(f"\n[bf16x1] image error vs fp32 reference: max-abs {err_ref:.3e}, rms {rms:.3e}; the bf16 storage model itself "
               f"(CPU oracle, same rounding points): max-abs {cost:.3e}, rms {cost_rms:.3e}; ours vs that model: {_maxabs(xg, model):.3e}")
         # bf16 mode must not be worse than what bf16 storage inherently costs on this network (see module docstring)
         assert rms <= 1.5 * cost_rms + 1e-3
@@ -107,12 +114,15 @@ def test_generator_eval_mode_batch_one(mode, specs, golden):
     if mode == "fp32":
         print(f"\n[fp32] eval-mode batch-1 image max-abs error vs reference: {err_ref:.3e}")
         assert err_ref <= 1e-4
+    elif mode == "bf16":
+        print(f"\n[bf16] eval-mode batch-1 image max-abs error vs reference: {err_ref:.3e}")
+        assert err_ref <= 2e-2
     else:
         with torch.no_grad(), O.storage_model("bf16"):
             model = O.gen_forward(cpu["tr_img"][:1], cpu["label_xt"][:1], W.make_state(specs["gen_c15"]), training=False)
         ref = torch.from_numpy(gold["xg_eval_b1"])
         cost = _maxabs(model, ref)
-        print(f"\n[bf16] eval-mode batch-1 image max-abs vs fp32 reference {err_ref:.3e} (bf16 storage model: {cost:.3e})")
+        print(f"\n[bf16x1] eval-mode batch-1 image max-abs vs fp32 reference {err_ref:.3e} (bf16 storage model: {cost:.3e})")
         assert err_ref <= 1.5 * cost + 2e-2
 
 
@@ -125,16 +135,18 @@ def test_dis_cla_forward_and_losses(mode, specs, golden):
     out = dis(xg)
     vals = dict(real=float(dis.calc_dis_real_loss(batch["img_xt"])), fake=float(dis.calc_dis_fake_loss(xg)),
                 gen=float(dis.calc_gen_loss(xg)), cla=float(cla(batch["img_xt"], batch["tr_wid"])))
-    if mode == "fp32":
-        assert rel_err(out, torch.from_numpy(gold["dis.out"])) <= 1e-4
+    if mode in ("fp32", "bf16"):
+        tol = 1e-4 if mode == "fp32" else 2e-3
+        print(f"\n[{mode}] dis logits vs reference: {rel_err(out, torch.from_numpy(gold['dis.out'])):.3e}")
+        assert rel_err(out, torch.from_numpy(gold["dis.out"])) <= tol
         for k, ref in (("real", "dis.real_loss"), ("fake", "dis.fake_loss"), ("gen", "dis.gen_loss"), ("cla", "cla.loss")):
-            assert abs(vals[k] - float(gold[ref])) <= 1e-4 * max(1.0, abs(float(gold[ref]))), k
+            assert abs(vals[k] - float(gold[ref])) <= tol * max(1.0, abs(float(gold[ref]))), k
     else:
         dsd, csd = W.make_state(specs["dis"]), W.make_state(specs["cla"])
         with torch.no_grad(), O.storage_model("bf16"):
             m_out = O.dis_forward(torch.from_numpy(gg["xg"]), dsd)
             m_cla = float(O.cla_loss(cpu["img_xt"], cpu["tr_wid"], csd))
-        print(f"\n[bf16] dis logits: vs bf16-storage oracle {rel_err(out, m_out):.3e}, vs fp32 reference "
+        print(f"\n[bf16x1] dis logits: vs bf16-storage oracle {rel_err(out, m_out):.3e}, vs fp32 reference "
               f"{rel_err(out, torch.from_numpy(gold['dis.out'])):.3e}")
         assert rel_err(out, m_out) <= 2e-2
         assert abs(vals["cla"] - m_cla) <= 2e-2 * max(1.0, abs(m_cla))
@@ -166,7 +178,7 @@ def test_gen_update_gradients(mode, specs, golden):
     """network_tro.py:57-103 without the recogniser term: l_total = l_dis + l_cla, backward into the generator."""
     gd = golden("grads_c15_b4.npz")
     cpu_batch = O.synthetic_batch(4, 15)
-    full, ld_o, lc_o = _oracle_gen_update(specs, cpu_batch, mode)
+    full, ld_o, lc_o = _oracle_gen_update(specs, cpu_batch, "bf16" if mode == "bf16x1" else "fp32")
     gen = _gen(specs).train()
     dis, cla = _dis_cla(specs)
     batch = _cuda(cpu_batch)
@@ -178,7 +190,7 @@ def test_gen_update_gradients(mode, specs, golden):
     l_dis = (dis.calc_gen_loss(outs[0]) + dis.calc_gen_loss(outs[1])) / 2
     l_cla = (cla(outs[0], batch["tr_wid"]) + cla(outs[1], batch["tr_wid"])) / 2
     (l_dis + l_cla).backward()
-    ltol = 1e-4 if mode == "fp32" else 5e-2
+    ltol = {"fp32": 1e-4, "bf16": 5e-3, "bf16x1": 5e-2}[mode]
     assert abs(float(l_dis) - ld_o) <= ltol * max(1.0, abs(ld_o)) and abs(float(l_cla) - lc_o) <= ltol * max(1.0, abs(lc_o))
     if mode == "fp32":
         assert abs(float(l_dis) - float(gd["gen.l_dis"])) <= 1e-4 and abs(float(l_cla) - float(gd["gen.l_cla"])) <= 1e-3
@@ -207,6 +219,9 @@ def test_gen_update_gradients(mode, specs, golden):
     if mode == "fp32":
         assert glob >= 0.999 and rows[0][0] >= 0.999
         assert all(abs(r - 1.0) <= 2e-3 for _, r, _ in rows)
+    elif mode == "bf16":
+        assert glob >= 0.999 and rows[0][0] >= 0.995
+        assert all(abs(r - 1.0) <= 3e-2 for _, r, _ in rows), sorted(rows, key=lambda t: -abs(t[1] - 1))[:3]
     else:
         # two independent bf16 realisations of this network agree to ~0.96 (the storage model against itself with a
         # different summation order behaves the same); kernel-level gradient accuracy is pinned block by block in
@@ -228,10 +243,10 @@ def test_dis_and_cla_update_gradients(mode, specs, golden):
     l_fake.backward()
     l_c = cla(batch["tr_img"][:, 0:1], batch["tr_wid"])
     l_c.backward()
-    ltol = 1e-4 if mode == "fp32" else 5e-2
+    ltol = {"fp32": 1e-4, "bf16": 2e-3, "bf16x1": 5e-2}[mode]
     for val, key in ((l_real, "dis.l_real"), (l_fake, "dis.l_fake"), (l_c, "cla.loss")):
         assert abs(float(val) - float(gd[key])) <= ltol * max(1.0, abs(float(gd[key]))), key
-    lim = 2e-3 if mode == "fp32" else 0.1
+    lim = {"fp32": 2e-3, "bf16": 1e-2, "bf16x1": 0.1}[mode]
     assert abs(float(im1.grad.norm()) - float(gd["dis.dimg_norm"])) <= lim * float(gd["dis.dimg_norm"])
     worst = 0.0
     for net, name in ((dis, "dis"), (cla, "cla")):
