@@ -23,13 +23,13 @@ def start_kernel_timing():
     _profile["records"] = []
 
 
-def stop_kernel_timing():
-    """-> {name: {"launches", "ms", "flops"}} ; synchronises the device once."""
+def stop_kernel_timing(by_shape=False):
+    """-> {name: {"launches", "ms", "flops"}} ; synchronises the device once.  by_shape=True keys on (name, shape tag)."""
     recs, _profile["records"] = _profile["records"] or [], None
     torch.cuda.synchronize()
     out = {}
-    for name, e0, e1, fl in recs:
-        d = out.setdefault(name, {"launches": 0, "ms": 0.0, "flops": 0.0})
+    for name, tag, e0, e1, fl in recs:
+        d = out.setdefault((name, tag) if by_shape else name, {"launches": 0, "ms": 0.0, "flops": 0.0})
         d["launches"] += 1
         d["ms"] += e0.elapsed_time(e1)
         d["flops"] += fl
@@ -37,9 +37,9 @@ def stop_kernel_timing():
 
 
 class _timed:
-    def __init__(self, name, flops):
+    def __init__(self, name, flops, tag=None):
         self.on = _profile["records"] is not None
-        self.name, self.flops = name, flops
+        self.name, self.flops, self.tag = name, flops, tag
 
     def __enter__(self):
         if self.on:
@@ -50,7 +50,7 @@ class _timed:
     def __exit__(self, *a):
         if self.on:
             self.e1.record()
-            _profile["records"].append((self.name, self.e0, self.e1, self.flops))
+            _profile["records"].append((self.name, self.tag, self.e0, self.e1, self.flops))
 
 
 def set_precision(mode):
@@ -334,6 +334,7 @@ class _Conv2d(Function):
             addend = _dense_cl(addend, y_dtype)
         b32 = None if bias is None else bias.detach()
         flops = 2.0 * g["N"] * g["Ho"] * g["Wo"] * g["Cout"] * g["Cin"] * g["KH"] * g["KW"]
+        tag = "%dx%dx%d c%d->%d k%d s%d u%d" % (g["N"], g["H"], g["W"], g["Cin"], g["Cout"], g["KH"], cfg.stride, cfg.upsample)
         planes = None
         if use_tc:
             cs = _up8(g["Cin"])
@@ -342,18 +343,18 @@ class _Conv2d(Function):
                 raise RuntimeError("conv2d: tcgen05 kernel refused the shape: " + L.last_error())
             planes = _split_planes(x, g["N"] * g["H"] * g["W"], g["Cin"], g["pitch"], passes, cfg.pre_act)
             wp = _pack_tc(weight, cs, False, passes)
-            with _timed("conv_fwd_tcgen05", flops):
+            with _timed("conv_fwd_tcgen05", flops, tag):
                 L.call("affgw_conv2d_fwd", planes.data_ptr(), wp.data_ptr(), L.ptr(b32), L.ptr(addend), y.data_ptr(),
                        C.byref(d), L.stream())
         else:
             d = _desc(g, cfg, g["Cin"], L.F32, L.F32, L.F32, L.ALGO_SIMT)
             wp = _pack(weight, torch.float32, g["Cin"], False)
-            with _timed("conv_fwd_simt", flops):
+            with _timed("conv_fwd_simt", flops, tag):
                 L.call("affgw_conv2d_fwd", x.data_ptr(), wp.data_ptr(), L.ptr(b32), L.ptr(addend), y.data_ptr(), C.byref(d),
                        L.stream())
-        ctx.cfg, ctx.g, ctx.use_tc, ctx.passes = cfg, g, use_tc, passes
+        ctx.cfg, ctx.g, ctx.use_tc, ctx.passes, ctx.tag = cfg, g, use_tc, passes, tag
         ctx.has_bias, ctx.has_addend = bias is not None, addend is not None
-        keep_x = (not use_tc) or cfg.pre_act != "none"
+        keep_x = (not use_tc) or cfg.pre_act != "none" or _state["simt_wgrad"]
         ctx.save_for_backward(x if keep_x else None, weight, y if cfg.post_act != "none" else None, planes)
         ctx.x_meta = (x.shape, x.device)
         return y
@@ -391,13 +392,13 @@ class _Conv2d(Function):
                 if ws_bytes <= 0:
                     raise RuntimeError("conv2d_wgrad: tcgen05 kernel refused the shape: " + L.last_error())
                 wsb = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-                with _timed("conv_wgrad_tcgen05", flops):
+                with _timed("conv_wgrad_tcgen05", flops, ctx.tag):
                     L.call("affgw_conv2d_wgrad", planes.data_ptr(), dzp.data_ptr(), dw.data_ptr(), wsb.data_ptr(), C.byref(d), st)
             else:
                 if x is None:
                     raise RuntimeError("conv2d backward: the CUDA-core wgrad needs the saved fp32 input")
                 d = _desc(g, fwd_cfg, cin, L.F32, L.F32, L.F32, L.ALGO_SIMT)
-                with _timed("conv_wgrad_simt", flops):
+                with _timed("conv_wgrad_simt", flops, ctx.tag):
                     L.call("affgw_conv2d_wgrad", x.data_ptr(), dz.data_ptr(), dw.data_ptr(), None, C.byref(d), st)
         if need_x:
             if use_tc:
@@ -427,7 +428,7 @@ class _Conv2d(Function):
                 raise RuntimeError("conv2d_dgrad_ws_bytes: " + L.last_error())
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev) if ws_bytes else None
             src = dzp if use_tc else dz
-            with _timed("conv_dgrad_tcgen05" if use_tc else "conv_dgrad_simt", flops):
+            with _timed("conv_dgrad_tcgen05" if use_tc else "conv_dgrad_simt", flops, ctx.tag):
                 L.call("affgw_conv2d_dgrad", src.data_ptr(), wt.data_ptr(), L.ptr(x), base.data_ptr(), L.ptr(ws),
                        C.byref(d), st)
             if use_tc and g["Cx"] != cin:      # the weight reads only the first `cin` channels of a wider input
