@@ -34,8 +34,10 @@ SIGNATURES = {
     "affgw_launch_count": [],
     "affgw_device_ok": [],
     "affgw_pack_weight": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
-    "affgw_pack_weight_tc": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
-    "affgw_pack_weight_tc_bytes": [_I, _I, _I, _I, _I, _I, _I],
+    "affgw_pack_weight_tc": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
+    "affgw_pack_weight_tc_bytes": [_I, _I, _I, _I, _I, _I, _I, _I],
+    "affgw_conv_tc_layout": [_D, _I],
+    "affgw_conv_tc_prefer_shift": [_I],
     "affgw_operand_planes_bytes": [_L, _I, _I],
     "affgw_split_planes": [_P, _I, _P, _L, _I, _I, _I, _I, _I, _P],
     "affgw_conv_tc_supported": [_D],

@@ -26,6 +26,13 @@ int pack_weight_tc(const float* w, void* out, int Cout, int Cin, int KH, int KW,
 long long pack_weight_tc_bytes(int Cout, int Cin, int KH, int KW, int ipad, int transpose_flip, int passes);
 int split_planes(const void* x, int x_dt, void* planes, long long rows, int C, int pitch, int c_store, int passes, int pre_act,
                  cudaStream_t st);
+// conv_shift.cu
+int conv_shift_ok(const ConvGeom& g, int passes);
+int conv_fwd_shift(const void* x_planes, long long plane_stride, const void* w_packed, const float* bias, const void* addend,
+                   void* y, int y_dt, const ConvGeom& g, int passes, cudaStream_t st);
+int pack_weight_shift(const float* w, void* out, int Cout, int Cin, int K, int ipad, int transpose_flip, int passes,
+                      cudaStream_t st);
+long long pack_weight_shift_bytes(int Cout, int Cin, int K, int ipad, int transpose_flip, int passes);
 // conv_tc_wgrad.cu
 int conv_wgrad_tc_ok(const ConvGeom& g);
 long long conv_wgrad_tc_ws_bytes(const ConvGeom& g);
@@ -141,13 +148,27 @@ int affgw_pack_weight(const float* w, void* out, int out_dtype, int Cout, int Ci
 }
 
 static inline bool passes_ok(int p) { return p == 1 || p == 3; }
+static std::atomic<int> g_prefer_shift{1};
 
-long long affgw_pack_weight_tc_bytes(int Cout, int Cin, int KH, int KW, int i_pad, int transpose_flip, int passes) {
+int affgw_conv_tc_prefer_shift(int enable) {
+    const int prev = g_prefer_shift.load();
+    if (enable >= 0) g_prefer_shift.store(enable ? 1 : 0);
+    return prev;
+}
+
+long long affgw_pack_weight_tc_bytes(int Cout, int Cin, int KH, int KW, int i_pad, int transpose_flip, int passes, int layout) {
+    if (layout == AFFGW_WLAYOUT_SHIFT) return KH == KW ? pack_weight_shift_bytes(Cout, Cin, KH, i_pad, transpose_flip, passes) : -1;
+    if (layout != AFFGW_WLAYOUT_IM2COL) return -1;
     return pack_weight_tc_bytes(Cout, Cin, KH, KW, i_pad, transpose_flip, passes);
 }
 int affgw_pack_weight_tc(const float* w, void* out, int Cout, int Cin, int KH, int KW, int i_pad, int transpose_flip,
-                         int passes, void* stream) {
+                         int passes, int layout, void* stream) {
     AFFGW_CHECK(w && out, "pack_weight_tc: null pointer");
+    AFFGW_CHECK(layout == AFFGW_WLAYOUT_IM2COL || layout == AFFGW_WLAYOUT_SHIFT, "pack_weight_tc: bad layout");
+    if (layout == AFFGW_WLAYOUT_SHIFT) {
+        AFFGW_CHECK(KH == KW, "pack_weight_tc: the shifted kernel takes square filters");
+        return pack_weight_shift(w, out, Cout, Cin, KH, i_pad, transpose_flip, passes, S(stream));
+    }
     return pack_weight_tc(w, out, Cout, Cin, KH, KW, i_pad, transpose_flip, passes, S(stream));
 }
 long long affgw_operand_planes_bytes(long long rows, int c_store, int passes) {
@@ -172,10 +193,23 @@ static int make_tc_geom(const affgw_conv_desc* d, ConvGeom& g) {
     return 0;
 }
 
+// which tcgen05 kernel (= which packed-weight layout) a geometry runs on
+static int tc_layout(const ConvGeom& g, int passes) {
+    if (g_prefer_shift.load() && conv_shift_ok(g, passes)) return AFFGW_WLAYOUT_SHIFT;
+    return conv_tc_ok(g) > 0 ? AFFGW_WLAYOUT_IM2COL : 0;
+}
+static int conv_tc_dispatch(const void* x, long long plane, const void* w, const float* bias, const void* addend, void* y,
+                            int y_dt, const ConvGeom& g, int passes, cudaStream_t st) {
+    const int lay = tc_layout(g, passes);
+    AFFGW_CHECK(lay != 0, "conv (tcgen05): shape not supported (stored Cin %d, pitch %d)", g.Cin, g.in_pitch);
+    if (lay == AFFGW_WLAYOUT_SHIFT) return conv_fwd_shift(x, plane, w, bias, addend, y, y_dt, g, passes, st);
+    return conv_fwd_tc(x, plane, w, bias, addend, y, y_dt, g, passes, st);
+}
+
 int affgw_conv_tc_supported(const affgw_conv_desc* d) {
     ConvGeom g;
     if (!d || make_tc_geom(d, g)) return 0;
-    return conv_tc_ok(g) > 0;
+    return tc_layout(g, d->passes) != 0;
 }
 
 int affgw_conv2d_fwd(const void* x, const void* w, const float* bias, const void* addend, void* y,
@@ -185,9 +219,8 @@ int affgw_conv2d_fwd(const void* x, const void* w, const float* bias, const void
     AFFGW_CHECK(x && w && y, "conv2d_fwd: null pointer");
     if (d->algo == AFFGW_ALGO_TCGEN05) {
         if (int rc = make_tc_geom(d, g)) return rc;
-        AFFGW_CHECK(conv_tc_ok(g) > 0, "conv2d_fwd: shape not supported by the tcgen05 kernel");
         const long long plane = (long long)d->N * d->H * d->W * d->in_pitch;
-        return conv_fwd_tc(x, plane, w, bias, addend, y, d->y_dtype, g, d->passes, S(stream));
+        return conv_tc_dispatch(x, plane, w, bias, addend, y, d->y_dtype, g, d->passes, S(stream));
     }
     return conv_fwd_simt(x, d->x_dtype, w, d->w_dtype, bias, addend, y, d->y_dtype, g, S(stream));
 }
@@ -225,6 +258,21 @@ static void dgrad_geom(const affgw_conv_desc* d, const affgw_conv_desc& dd, Conv
     g.M = (long long)g.N * g.Ho * g.Wo;
 }
 
+int affgw_conv_tc_layout(const affgw_conv_desc* d, int for_dgrad) {
+    ConvGeom g;
+    if (!d || !passes_ok(d->passes)) return 0;
+    if (!for_dgrad) {
+        if (make_tc_geom(d, g)) return 0;
+        return tc_layout(g, d->passes);
+    }
+    affgw_conv_desc dd;
+    bool direct;
+    int Hp, Wp;
+    if (make_geom(d, g) || d->algo != AFFGW_ALGO_TCGEN05 || make_dgrad(d, dd, direct, Hp, Wp)) return 0;
+    dgrad_geom(d, dd, g);
+    return tc_layout(g, d->passes);
+}
+
 long long affgw_conv2d_dgrad_ws_bytes(const affgw_conv_desc* d) {
     affgw_conv_desc dd;
     bool direct;
@@ -251,9 +299,8 @@ int affgw_conv2d_dgrad(const void* dy, const void* wt, const void* x, void* dx, 
     if (tc) {
         AFFGW_CHECK(passes_ok(d->passes) && dt_ok(d->grad_dtype), "conv2d_dgrad: bad passes / grad_dtype");
         AFFGW_CHECK(d->y_dtype == AFFGW_BF16 && d->w_dtype == AFFGW_BF16, "conv2d_dgrad (tcgen05): operands are bf16 planes / tiles");
-        AFFGW_CHECK(conv_tc_ok(g) > 0, "conv2d_dgrad: shape not supported by the tcgen05 kernel");
         const long long plane = (long long)dd.N * dd.H * dd.W * dd.in_pitch;
-        rc = conv_fwd_tc(dy, plane, wt, nullptr, nullptr, out, gdt, g, d->passes, S(stream));
+        rc = conv_tc_dispatch(dy, plane, wt, nullptr, nullptr, out, gdt, g, d->passes, S(stream));
     } else {
         rc = conv_fwd_simt(dy, dd.x_dtype, wt, d->w_dtype, nullptr, nullptr, out, dd.y_dtype, g, S(stream));
     }

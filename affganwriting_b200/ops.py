@@ -252,19 +252,24 @@ def _pack(weight, dtype, ipad, flip):
     return _WeightCache.get(weight, ("plain", dtype, ipad, flip), build)
 
 
-def _pack_tc(weight, ipad, flip, passes):
+def _pack_tc(weight, ipad, flip, passes, layout):
     w4 = _w4(weight.detach())
     co, ci, kh, kw = w4.shape
 
     def build():
-        nbytes = L.lib().affgw_pack_weight_tc_bytes(co, ci, kh, kw, ipad, int(flip), passes)
+        nbytes = L.lib().affgw_pack_weight_tc_bytes(co, ci, kh, kw, ipad, int(flip), passes, layout)
         if nbytes <= 0:
             raise RuntimeError("affgw_pack_weight_tc_bytes: bad configuration")
         out = torch.empty(nbytes // 2, dtype=torch.bfloat16, device=weight.device)
         L.call("affgw_pack_weight_tc", w4.contiguous().data_ptr(), out.data_ptr(), co, ci, kh, kw, ipad, int(flip), passes,
-               L.stream())
+               layout, L.stream())
         return out
-    return _WeightCache.get(weight, ("tc", ipad, flip, passes), build)
+    return _WeightCache.get(weight, ("tc", ipad, flip, passes, layout), build)
+
+
+def prefer_shift_kernel(flag=True):
+    """Route stride-1 convolutions through the shared-memory-window tcgen05 kernel (default) or the im2col one."""
+    return bool(L.lib().affgw_conv_tc_prefer_shift(int(bool(flag))))
 
 
 def _up8(c):
@@ -339,10 +344,11 @@ class _Conv2d(Function):
         if use_tc:
             cs = _up8(g["Cin"])
             d = _desc(g, cfg, g["Cin"], L.BF16, L.BF16, L.F32, L.ALGO_TC, in_pitch=cs, passes=passes, pre_act="none")
-            if not L.lib().affgw_conv_tc_supported(C.byref(d)):
-                raise RuntimeError("conv2d: tcgen05 kernel refused the shape: " + L.last_error())
+            layout = L.lib().affgw_conv_tc_layout(C.byref(d), 0)
+            if not layout:
+                raise RuntimeError("conv2d: tcgen05 kernels refused the shape: " + L.last_error())
             planes = _split_planes(x, g["N"] * g["H"] * g["W"], g["Cin"], g["pitch"], passes, cfg.pre_act)
-            wp = _pack_tc(weight, cs, False, passes)
+            wp = _pack_tc(weight, cs, False, passes, layout)
             with _timed("conv_fwd_tcgen05", flops, tag):
                 L.call("affgw_conv2d_fwd", planes.data_ptr(), wp.data_ptr(), L.ptr(b32), L.ptr(addend), y.data_ptr(),
                        C.byref(d), L.stream())
@@ -408,7 +414,10 @@ class _Conv2d(Function):
                     dx = empty_cl(g["N"], cin, g["H"], g["W"], torch.float32, dev)
                 d = _desc(g, fwd_cfg, cin, L.BF16, L.BF16, L.BF16, L.ALGO_TC, in_pitch=cs, out_pitch=cso, passes=passes,
                           grad_dt=L.F32)
-                wt = _pack_tc(weight, cso, True, passes)
+                layout = L.lib().affgw_conv_tc_layout(C.byref(d), 1)
+                if not layout:
+                    raise RuntimeError("conv2d_dgrad: tcgen05 kernels refused the shape: " + L.last_error())
+                wt = _pack_tc(weight, cso, True, passes, layout)
                 base = dx
             else:
                 if g["Cx"] != cin and not (cfg.pad_mode == "zero" and cfg.upsample == 1 and cfg.pre_act == "none"):

@@ -20,12 +20,14 @@
 extern "C" {
 #endif
 
-#define AFFGW_VERSION 101
+#define AFFGW_VERSION 102
 
 enum { AFFGW_DT_F32 = 0, AFFGW_DT_BF16 = 1 };
 enum { AFFGW_ACT_NONE = 0, AFFGW_ACT_RELU = 1, AFFGW_ACT_LRELU = 2, AFFGW_ACT_TANH = 3 };
 enum { AFFGW_PAD_ZERO = 0, AFFGW_PAD_REFLECT = 1, AFFGW_PAD_REPLICATE = 2 };
 enum { AFFGW_ALGO_AUTO = 0, AFFGW_ALGO_SIMT = 1, AFFGW_ALGO_TCGEN05 = 2 };
+/* packed-weight layouts of the two tcgen05 convolution kernels (affgw_conv_tc_layout tells which one a geometry uses) */
+enum { AFFGW_WLAYOUT_IM2COL = 1, AFFGW_WLAYOUT_SHIFT = 2 };
 
 /* One convolution = pad -> conv -> (+bias) -> (+addend) -> activation, i.e. the conv part of Conv2dBlock.forward
  * (blocks.py:150-163) with the explicit pad module (blocks.py:113-121), nn.Upsample(scale_factor=2)
@@ -67,8 +69,13 @@ int affgw_pack_weight(const float* w_oihw, void* out, int out_dtype, int Cout, i
 /* same, into the 128B-swizzled shared-memory tile images the tcgen05 kernel bulk-copies (bf16; hi and lo tiles when
  * passes = 3).  i_pad = c_store of the operand planes the weight will meet (x planes, or dY planes for transpose_flip). */
 int affgw_pack_weight_tc(const float* w_oihw, void* out, int Cout, int Cin, int KH, int KW, int i_pad, int transpose_flip,
-                         int passes, void* stream);
-long long affgw_pack_weight_tc_bytes(int Cout, int Cin, int KH, int KW, int i_pad, int transpose_flip, int passes);
+                         int passes, int layout, void* stream);
+long long affgw_pack_weight_tc_bytes(int Cout, int Cin, int KH, int KW, int i_pad, int transpose_flip, int passes, int layout);
+/* AFFGW_WLAYOUT_* the forward (for_dgrad = 0) or input-gradient (1) convolution described by d runs on; 0 = not
+ * supported.  Stride-1 convolutions take the shared-memory-window ("shifted") kernel, the rest the im2col kernel. */
+int affgw_conv_tc_layout(const affgw_conv_desc* d, int for_dgrad);
+/* enable (1) / disable (0) the shifted kernel, -1 = query only; returns the previous setting (A/B testing) */
+int affgw_conv_tc_prefer_shift(int enable);
 /* activation tensor [rows][pitch] (fp32 or bf16) -> operand planes [passes == 3 ? 2 : 1][rows][c_store] (bf16), with the
  * activation_first non-linearity (blocks.py:151-153) applied and channels C..c_store-1 zero-filled */
 long long affgw_operand_planes_bytes(long long rows, int c_store, int passes);

@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol():
     assert len(names) >= 45
     for n in names:
         assert hasattr(h, n), n
-    assert h.affgw_version() == 101
+    assert h.affgw_version() == 102
 
 
 def test_python_binding_covers_the_header():
@@ -63,9 +63,18 @@ def test_host_side_argument_validation_needs_no_gpu():
     d.passes = 1
     d.Ho = 9
     assert h.affgw_conv_tc_supported(ctypes.byref(d)) == 0 and b"output extent" in h.affgw_last_error()
-    assert h.affgw_pack_weight_tc_bytes(512, 512, 3, 3, 512, 0, 1) == 512 * 512 * 9 * 2
-    assert h.affgw_pack_weight_tc_bytes(512, 512, 3, 3, 512, 0, 3) == 512 * 512 * 9 * 2 * 2
-    assert h.affgw_pack_weight_tc_bytes(512, 512, 3, 3, 510, 0, 1) < 0                 # c_store must be a multiple of 8
+    for layout in (1, 2):                                                               # im2col tiles / shifted-kernel planes
+        assert h.affgw_pack_weight_tc_bytes(512, 512, 3, 3, 512, 0, 1, layout) == 512 * 512 * 9 * 2
+        assert h.affgw_pack_weight_tc_bytes(512, 512, 3, 3, 512, 0, 3, layout) == 512 * 512 * 9 * 2 * 2
+        assert h.affgw_pack_weight_tc_bytes(512, 512, 3, 3, 510, 0, 1, layout) < 0     # c_store must be a multiple of 8
+    assert h.affgw_pack_weight_tc_bytes(512, 512, 3, 3, 512, 0, 1, 7) < 0
+    d.Ho, d.passes = 8, 3
+    assert h.affgw_conv_tc_layout(ctypes.byref(d), 0) == 2 and h.affgw_conv_tc_layout(ctypes.byref(d), 1) == 2
+    assert h.affgw_conv_tc_prefer_shift(0) == 1
+    assert h.affgw_conv_tc_layout(ctypes.byref(d), 0) == 1
+    assert h.affgw_conv_tc_prefer_shift(1) == 0
+    d.stride, d.Ho, d.Wo = 2, 4, 14                                                      # strided: im2col kernel only
+    assert h.affgw_conv_tc_layout(ctypes.byref(d), 0) == 1
     assert h.affgw_operand_planes_bytes(100, 56, 3) == 100 * 56 * 2 * 2
 
 
