@@ -150,9 +150,13 @@ int affgw_pack_weight(const float* w, void* out, int out_dtype, int Cout, int Ci
 static inline bool passes_ok(int p) { return p == 1 || p == 3; }
 static std::atomic<int> g_prefer_shift{1};
 
+extern int g_wgrad_prefer_shift;
 int affgw_conv_tc_prefer_shift(int enable) {
     const int prev = g_prefer_shift.load();
-    if (enable >= 0) g_prefer_shift.store(enable ? 1 : 0);
+    if (enable >= 0) {
+        g_prefer_shift.store(enable ? 1 : 0);
+        g_wgrad_prefer_shift = enable ? 1 : 0;
+    }
     return prev;
 }
 

@@ -460,3 +460,327 @@ int conv_fwd_shift(const void* x_planes, long long plane_stride, const void* w_p
         default: return launch_shift<64, 1>(a, p.smem_bytes, st);
     }
 }
+
+// =====================================================================================================================
+// Weight gradient in the same position space:
+//
+//   dW[co][ky][kx][ci] = sum_q  V[q + ky*Wp + kx][ci] * dYp[q][co]         (dYp = dY scattered to padded positions)
+//
+// a GEMM whose reduction runs over positions.  Both operands sit in shared memory in the planar layout above, which is
+// UMMA's un-swizzled "MN-major" form (8 positions x 8 channels per core matrix; LBO = 128 B to the next 8 positions,
+// SBO = plane pitch to the next 8 channels).  One CTA owns a (128 input channels) x (BN output channels) x (kernel row ky)
+// block of dW: for every 16 positions it issues one MMA per kx whose A descriptor starts kx positions further into the
+// window - the input window is read once per kernel ROW instead of once per tap, dY once per row.  M is always 128
+// (absent channel groups stay zero in shared memory), so thin layers cost N/2 clocks per MMA, not a 128x128 tile.
+// The position range is split over grid.y; partials are reduced with coalesced fp32 atomics into ws[co][tap][ci].
+// =====================================================================================================================
+namespace {
+
+constexpr int WG_THREADS = 160;              // 4 producer / epilogue warps + 1 MMA warp
+
+struct WsArgs {
+    const bf16* x; long long x_plane;        // planes [NPL][N*H*W][Cs]
+    const bf16* dy; long long dy_plane;      // planes [NPL][N*Ho*Wo][Cys]
+    float* ws;                               // [Cout][taps][Cs] fp32
+    int N, H, W, Cs;
+    int up, pad, pad_mode, K;
+    int Hv, Wv, Hp, Wp, Ho, Wo;
+    int Cout, Cys;
+    int KP, pitchA16, pitchB16;              // positions per stage; plane pitches in 16-byte units
+    int n_co_blocks;
+    int chunks_total, chunks_per_split;
+    int a_bytes, b_bytes, stages;
+    int Q;
+};
+
+__device__ __forceinline__ uint64_t make_mnmajor_nosw_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;     // to the next 8 positions (K)
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;     // to the next 8 channels (M / N)
+    d |= 1ull << 46;
+    return d;
+}
+__host__ __device__ constexpr uint32_t make_idesc_bf16_mnmn(int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+template <int BN, int NPASS>
+__global__ void __launch_bounds__(WG_THREADS, 1)
+conv_wgrad_shift_kernel(const __grid_constant__ WsArgs a) {
+    constexpr int NPL = NPASS == 3 ? 2 : 1;
+    constexpr int GB = BN / 8;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 127u) & ~127u;
+    const int stages = a.stages;
+    const int stage_bytes = a.a_bytes + a.b_bytes;
+    const uint32_t bar_base = smem_base + stages * stage_bytes;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (MAX_STAGES + s); };
+    const uint32_t tmem_full_bar = bar_base + 8u * (2 * MAX_STAGES);
+    const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * MAX_STAGES + 1);
+    auto a_smem = [&](int s) { return smem_base + s * stage_bytes; };
+    auto b_smem = [&](int s) { return smem_base + s * stage_bytes + a.a_bytes; };
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int ky = blockIdx.x % a.K;
+    const int cob = (blockIdx.x / a.K) % a.n_co_blocks;
+    const int cib = blockIdx.x / (a.K * a.n_co_blocks);
+    const int cbeg = blockIdx.y * a.chunks_per_split;
+    const int cend = min(a.chunks_total, cbeg + a.chunks_per_split);
+    const int nst = cend - cbeg;
+    constexpr int TMEM_COLS = 512;
+
+    // absent channel groups must read as zeros for the whole kernel: clear every stage once
+    for (uint32_t o = tid * 16u; o < (uint32_t)(stages * stage_bytes); o += WG_THREADS * 16u)
+        asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(smem_base + o), "r"(0u) : "memory");
+    fence_proxy_async();
+    if (tid == 128) {
+        for (int s = 0; s < stages; ++s) {
+            mbar_init(full_bar(s), 128);
+            mbar_init(empty_bar(s), 1);
+        }
+        mbar_init(tmem_full_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 4) {
+        __syncwarp();
+        tmem_alloc(tmem_ptr_addr, TMEM_COLS);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr));
+    const uint32_t pitchA = (uint32_t)a.pitchA16 * 16u, pitchB = (uint32_t)a.pitchB16 * 16u;
+
+    if (warp < 4) {
+        // ============================== producer ==============================
+        const int g = tid & 15, jj = tid >> 4;            // channel group, position slot (8 positions per pass)
+        const int ca = cib * 128 + g * 8;                 // input channel of this thread's group
+        const int cbn = cob * BN + g * 8;                 // output channel of this thread's group
+        const bool a_on = ca < a.Cs, b_on = g < GB && cbn < a.Cys;
+        const int wlen = a.KP + a.K - 1;
+        for (int st = 0; st < nst; ++st) {
+            const int s = st % stages;
+            const uint32_t ph = (uint32_t)(st / stages) & 1u;
+            mbar_wait(empty_bar(s), ph ^ 1u);
+            const int q0 = (cbeg + st) * a.KP;
+            if (a_on) {
+                const uint32_t dst0 = a_smem(s) + (uint32_t)g * pitchA;
+                // decode the first position with divisions, then walk: 8 positions further per iteration
+                const int qf = q0 + ky * a.Wp + jj;
+                int xp = qf % a.Wp;
+                const int r = qf / a.Wp;
+                int yp = r % a.Hp, n = r / a.Hp;
+                for (int j = jj; j < wlen; j += 8) {
+                    bool ok = n < a.N;
+                    const bf16* src = a.x;
+                    if (ok) {
+                        const int sy = map_coord(yp - a.pad, a.Hv, a.pad_mode, a.up, 1);
+                        const int sx = map_coord(xp - a.pad, a.Wv, a.pad_mode, a.up, 1);
+                        ok = sy >= 0 && sx >= 0;
+                        if (ok) src = a.x + ((size_t)((n * a.H + sy) * a.W + sx) * a.Cs + ca);
+                    }
+                    const uint32_t dst = dst0 + (uint32_t)j * 16u;
+                    cp_async_16(dst, src, ok ? 16u : 0u);
+                    if (NPL == 2) cp_async_16(dst + 16u * pitchA, ok ? src + a.x_plane : src, ok ? 16u : 0u);
+                    xp += 8;
+                    while (xp >= a.Wp) {
+                        xp -= a.Wp;
+                        if (++yp == a.Hp) { yp = 0; ++n; }
+                    }
+                }
+            }
+            if (b_on) {
+                const uint32_t dst0 = b_smem(s) + (uint32_t)g * pitchB;
+                const int qf = q0 + jj;
+                int xp = qf % a.Wp;
+                const int r = qf / a.Wp;
+                int yp = r % a.Hp, n = r / a.Hp;
+                for (int j = jj; j < a.KP; j += 8) {
+                    const bool ok = n < a.N && yp < a.Ho && xp < a.Wo;
+                    const bf16* src = ok ? a.dy + ((size_t)((n * a.Ho + yp) * a.Wo + xp) * a.Cys + cbn) : a.dy;
+                    const uint32_t dst = dst0 + (uint32_t)j * 16u;
+                    cp_async_16(dst, src, ok ? 16u : 0u);
+                    if (NPL == 2) cp_async_16(dst + (uint32_t)GB * pitchB, ok ? src + a.dy_plane : src, ok ? 16u : 0u);
+                    xp += 8;
+                    while (xp >= a.Wp) {
+                        xp -= a.Wp;
+                        if (++yp == a.Hp) { yp = 0; ++n; }
+                    }
+                }
+            }
+            cp_async_commit();
+            if (st >= 1) {
+                cp_async_wait<1>();
+                fence_proxy_async();
+                mbar_arrive(full_bar((st - 1) % stages));
+            }
+        }
+        cp_async_wait<0>();
+        fence_proxy_async();
+        if (nst >= 1) mbar_arrive(full_bar((nst - 1) % stages));
+
+        // ============================== epilogue: fp32 reductions into ws[co][tap][ci] ==============================
+        mbar_wait(tmem_full_bar, 0);
+        tc_fence_after();
+        const int ci = cib * 128 + warp * 32 + lane;
+        const bool rok = ci < a.Cs;
+        const int taps = a.K * a.K;
+        for (int kx = 0; kx < a.K; ++kx) {
+            float* wbase = a.ws + (size_t)(ky * a.K + kx) * a.Cs + ci;
+#pragma unroll 1
+            for (int jb = 0; jb < BN / 16; ++jb) {
+                const int nb = cob * BN + jb * 16;
+                if (nb >= a.Cout) break;
+                uint32_t raw[16];
+                tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(kx * BN + jb * 16), raw);
+                if (rok) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                        if (nb + i < a.Cout) atomicAdd(wbase + (size_t)(nb + i) * taps * a.Cs, __uint_as_float(raw[i]));
+                }
+            }
+        }
+        tc_fence_before();
+    } else if (lane == 0) {
+        // ============================== MMA issuer ==============================
+        constexpr uint32_t idesc = make_idesc_bf16_mnmn(BN);
+        for (int st = 0; st < nst; ++st) {
+            const int s = st % stages;
+            const uint32_t ph = (uint32_t)(st / stages) & 1u;
+            mbar_wait(full_bar(s), ph);
+            tc_fence_after();
+            const uint32_t ab = a_smem(s), bb = b_smem(s);
+            for (int k = 0; k < a.KP / 16; ++k) {
+                const uint64_t b_hi = make_mnmajor_nosw_desc(bb + k * 256u, 128u, pitchB);
+                const uint64_t b_lo = make_mnmajor_nosw_desc(bb + (uint32_t)GB * pitchB + k * 256u, 128u, pitchB);
+                for (int kx = 0; kx < a.K; ++kx) {
+                    const uint32_t astart = ab + (uint32_t)(k * 16 + kx) * 16u;
+                    const uint64_t a_hi = make_mnmajor_nosw_desc(astart, 128u, pitchA);
+                    const uint32_t accum = (uint32_t)((st | k) != 0);
+                    umma_bf16(tmem_base + kx * BN, a_hi, b_hi, idesc, accum);
+                    if (NPASS == 3) {
+                        const uint64_t a_lo = make_mnmajor_nosw_desc(astart + 16u * pitchA, 128u, pitchA);
+                        umma_bf16(tmem_base + kx * BN, a_lo, b_hi, idesc, 1u);
+                        umma_bf16(tmem_base + kx * BN, a_hi, b_lo, idesc, 1u);
+                    }
+                }
+            }
+            umma_commit(empty_bar(s));
+        }
+        umma_commit(tmem_full_bar);
+    }
+    __syncthreads();
+    if (warp == 4) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+struct WsPlan {
+    int bn, KP, pitchA16, pitchB16, a_bytes, b_bytes, stages, smem_bytes;
+};
+
+int make_wg_plan(const ConvGeom& g, int passes, WsPlan& p) {
+    if (g.stride != 1 || g.zi != 1 || g.KH != g.KW || g.KH > 7) return 0;
+    if (g.Cin % 8 != 0 || g.in_pitch != g.Cin || g.out_pitch % 8 != 0 || g.out_pitch < g.Cout) return 0;
+    if (g.pre_act != ACT_NONE) return 0;
+    if (g.Cin < 128 || g.KH == 1) return 0;                     // measured: thin layers and 1x1 filters are faster on the im2col wgrad
+    const int npl = passes == 3 ? 2 : 1;
+    const long long Hp = g.Hv + 2 * g.pad, Wp = g.Wv + 2 * g.pad;
+    if (Hp - g.KH + 1 != g.Ho || Wp - g.KW + 1 != g.Wo) return 0;
+    if (2 * Hp * Wp > 3LL * g.Ho * g.Wo) return 0;              // tiny maps: padding positions dominate, im2col kernel
+    if ((long long)g.N * Hp * Wp + 4096 >= (1LL << 31) / 16) return 0;
+    if ((long long)g.N * g.H * g.W * g.Cin >= (1LL << 31) || g.M * g.out_pitch >= (1LL << 31)) return 0;
+    const int limit = g.KH <= 4 ? 128 : 64;                     // K * BN TMEM columns <= 512
+    p.bn = g.Cout <= 16 ? 16 : g.Cout <= 32 ? 32 : g.Cout <= 64 ? 64 : limit;
+    p.KP = (g.Cin <= 32 && p.bn <= 32) ? 128 : 64;
+    p.pitchA16 = p.KP + 9;
+    p.pitchB16 = p.KP + 1;
+    p.a_bytes = npl * 16 * p.pitchA16 * 16;
+    p.b_bytes = npl * (p.bn / 8) * p.pitchB16 * 16;
+    const int stage = p.a_bytes + p.b_bytes;
+    const int st = (SMEM_LIMIT - 128 - 256) / stage;
+    if (st < 2) return 0;
+    p.stages = st > MAX_STAGES ? MAX_STAGES : st;
+    p.smem_bytes = p.stages * stage + 128 + 256;
+    return 1;
+}
+
+template <int BN, int NPASS>
+int launch_wg_shift(const WsArgs& args, dim3 grid, int smem_bytes, cudaStream_t st) {
+    auto kern = conv_wgrad_shift_kernel<BN, NPASS>;
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) {
+            affgw_set_error("conv_wgrad_shift: cannot reserve %d bytes of shared memory", SMEM_LIMIT);
+            return -2;
+        }
+        configured = true;
+    }
+    kern<<<grid, WG_THREADS, smem_bytes, st>>>(args);
+    AFFGW_LAUNCH_CHECK("conv_wgrad_shift");
+    return 0;
+}
+
+}  // namespace
+
+int conv_wgrad_shift_ok(const ConvGeom& g, int passes) {
+    WsPlan p;
+    return make_wg_plan(g, passes, p);
+}
+
+// ws: [Cout][taps][g.Cin] fp32, zeroed by the caller; g.Cin / g.out_pitch are the stored channel counts of the planes
+int conv_wgrad_shift(const void* x_planes, long long x_plane, const void* dy_planes, long long dy_plane, float* ws,
+                     const ConvGeom& g, int passes, cudaStream_t st) {
+    WsPlan p;
+    if (!make_wg_plan(g, passes, p)) {
+        affgw_set_error("conv_wgrad_shift: unsupported convolution");
+        return -1;
+    }
+    WsArgs a;
+    a.x = (const bf16*)x_planes; a.x_plane = x_plane;
+    a.dy = (const bf16*)dy_planes; a.dy_plane = dy_plane;
+    a.ws = ws;
+    a.N = g.N; a.H = g.H; a.W = g.W; a.Cs = g.Cin;
+    a.up = g.up; a.pad = g.pad; a.pad_mode = g.pad_mode; a.K = g.KH;
+    a.Hv = g.Hv; a.Wv = g.Wv; a.Hp = g.Hv + 2 * g.pad; a.Wp = g.Wv + 2 * g.pad; a.Ho = g.Ho; a.Wo = g.Wo;
+    a.Cout = g.Cout; a.Cys = g.out_pitch;
+    a.KP = p.KP; a.pitchA16 = p.pitchA16; a.pitchB16 = p.pitchB16;
+    a.a_bytes = p.a_bytes; a.b_bytes = p.b_bytes; a.stages = p.stages;
+    a.Q = g.N * a.Hp * a.Wp;
+    const int n_ci = (g.Cin + 127) / 128;
+    a.n_co_blocks = (g.Cout + p.bn - 1) / p.bn;
+    const long long q_last = ((long long)(g.N - 1) * a.Hp + g.Ho - 1) * a.Wp + g.Wo - 1;
+    a.chunks_total = (int)(q_last / p.KP + 1);
+    const int tiles = n_ci * a.n_co_blocks * g.KH;
+    // split the position range so that the CTAs fill whole waves of 148 SMs (each split keeps >= 8 stages of work)
+    int max_splits = (a.chunks_total + 7) / 8;
+    if (max_splits > 320 / tiles + 1) max_splits = 320 / tiles + 1;
+    int splits = 1;
+    double best = 0.0;
+    for (int sp = 1; sp <= max_splits; ++sp) {
+        const int ctas = tiles * sp;
+        const double eff = (double)ctas / (double)((ctas + 147) / 148 * 148);
+        if (eff > best + 0.02) { best = eff; splits = sp; }
+    }
+    a.chunks_per_split = (a.chunks_total + splits - 1) / splits;
+    splits = (a.chunks_total + a.chunks_per_split - 1) / a.chunks_per_split;
+    dim3 grid((unsigned)tiles, (unsigned)splits);
+    if (passes == 3) {
+        switch (p.bn) {
+            case 16: return launch_wg_shift<16, 3>(a, grid, p.smem_bytes, st);
+            case 32: return launch_wg_shift<32, 3>(a, grid, p.smem_bytes, st);
+            case 64: return launch_wg_shift<64, 3>(a, grid, p.smem_bytes, st);
+            default: return launch_wg_shift<128, 3>(a, grid, p.smem_bytes, st);
+        }
+    }
+    switch (p.bn) {
+        case 16: return launch_wg_shift<16, 1>(a, grid, p.smem_bytes, st);
+        case 32: return launch_wg_shift<32, 1>(a, grid, p.smem_bytes, st);
+        case 64: return launch_wg_shift<64, 1>(a, grid, p.smem_bytes, st);
+        default: return launch_wg_shift<128, 1>(a, grid, p.smem_bytes, st);
+    }
+}

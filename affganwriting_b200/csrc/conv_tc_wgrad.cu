@@ -307,6 +307,12 @@ int launch_wg_p(WgArgs& a, int passes, cudaStream_t st) {
 }  // namespace
 
 int conv_tc_block_n(int cout);
+// conv_shift.cu
+int conv_wgrad_shift_ok(const ConvGeom& g, int passes);
+int conv_wgrad_shift(const void* x_planes, long long x_plane, const void* dy_planes, long long dy_plane, float* ws,
+                     const ConvGeom& g, int passes, cudaStream_t st);
+extern int g_wgrad_prefer_shift;
+int g_wgrad_prefer_shift = 1;
 
 // g.Cin must be the STORED channel count of the x planes, g.out_pitch that of the dY planes (multiples of 8)
 int conv_wgrad_tc_ok(const ConvGeom& g) {
@@ -335,6 +341,9 @@ int conv_wgrad_tc(const void* x_planes, long long x_plane, const void* dy_planes
     a.dy = (const bf16*)dy_planes; a.dy_plane = dy_plane;
     a.ws = ws; a.g = g; a.m_per_split = 0;
     int rc;
+    if (g_wgrad_prefer_shift && conv_wgrad_shift_ok(g, passes)) {
+        rc = conv_wgrad_shift(x_planes, x_plane, dy_planes, dy_plane, ws, g, passes, st);
+    } else
     switch (bn) {
         case 16: rc = launch_wg_p<16>(a, passes, st); break;
         case 32: rc = launch_wg_p<32>(a, passes, st); break;

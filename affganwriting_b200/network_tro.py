@@ -50,7 +50,9 @@ class ConTranModel(nn.Module):
         img_xt, label_xt, label_xt_swap = self._to(img_xt), self._to(label_xt), self._to(label_xt_swap)
 
         if mode == "cla_update":                                  # network_tro.py:50-55
-            img = tr_img[:, 0:1, :, :].requires_grad_()
+            # the reference marks this slice requires_grad_ (network_tro.py:51) but never reads its gradient: the input
+            # gradient of the stem convolution is dead work and is not computed here
+            img = tr_img[:, 0:1, :, :]
             l_cla_tr = self.cla(img, tr_wid)
             l_cla_tr.backward()
             return l_cla_tr
@@ -69,8 +71,9 @@ class ConTranModel(nn.Module):
             return l_total, l_dis, l_cla, l_l1, l_rec
 
         if mode == "dis_update":                                  # network_tro.py:105-138
-            s1 = tr_img[:, 0:1, :, :].requires_grad_()
-            s2 = tr_img[:, 1:2, :, :].requires_grad_()
+            # as above: network_tro.py:108-109 sets requires_grad_ on both real samples, nobody reads .grad
+            s1 = tr_img[:, 0:1, :, :]
+            s2 = tr_img[:, 1:2, :, :]
             l_real = (self.dis.calc_dis_real_loss(s1) + self.dis.calc_dis_real_loss(s2)) / 2.
             l_real.backward(retain_graph=True)
             with torch.no_grad():
