@@ -15,6 +15,7 @@ F32, BF16 = 0, 1
 ACT = {"none": 0, "relu": 1, "lrelu": 2, "tanh": 3}
 PAD = {"zero": 0, "reflect": 1, "replicate": 2}
 ALGO_AUTO, ALGO_SIMT, ALGO_TC = 0, 1, 2
+WLAYOUT_IM2COL, WLAYOUT_SHIFT = 1, 2
 
 
 class ConvDesc(C.Structure):
@@ -22,6 +23,12 @@ class ConvDesc(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "N", "H", "W", "Cin", "Cout", "KH", "KW", "stride", "pad", "pad_mode", "upsample", "Ho", "Wo",
         "in_pitch", "out_pitch", "pre_act", "post_act", "x_dtype", "w_dtype", "y_dtype", "algo", "passes", "grad_dtype")]
+
+
+class PosFrame(C.Structure):
+    """Mirror of `affgw_pos_frame` (include/affgw.h)."""
+    _fields_ = [("N", C.c_int32), ("Hp", C.c_int32), ("Wp", C.c_int32), ("G", C.c_int32), ("lead", C.c_int32),
+                ("reserved", C.c_int32), ("QA", C.c_int64)]
 
 
 _P, _I, _L, _F = C.c_void_p, C.c_int, C.c_longlong, C.c_float
@@ -37,6 +44,9 @@ SIGNATURES = {
     "affgw_pack_weight_tc": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     "affgw_pack_weight_tc_bytes": [_I, _I, _I, _I, _I, _I, _I, _I],
     "affgw_conv_tc_layout": [_D, _I],
+    "affgw_conv_pos_frames": [_D, C.POINTER(PosFrame), C.POINTER(PosFrame)],
+    "affgw_position_planes_bytes": [C.POINTER(PosFrame), _I],
+    "affgw_split_positions": [_P, _I, _P, C.POINTER(PosFrame), _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     "affgw_conv_tc_prefer_shift": [_I],
     "affgw_operand_planes_bytes": [_L, _I, _I],
     "affgw_split_planes": [_P, _I, _P, _L, _I, _I, _I, _I, _I, _P],
@@ -80,7 +90,7 @@ SIGNATURES = {
     "affgw_bucket_pack": [_P, _P, _P, _I, _P, _P],
     "affgw_bucket_unpack": [_P, _P, _P, _I, _P, _F, _P],
 }
-_RESTYPE = {"affgw_last_error": C.c_char_p, "affgw_launch_count": _L, "affgw_pack_weight_tc_bytes": _L, "affgw_operand_planes_bytes": _L,
+_RESTYPE = {"affgw_last_error": C.c_char_p, "affgw_launch_count": _L, "affgw_pack_weight_tc_bytes": _L, "affgw_operand_planes_bytes": _L, "affgw_position_planes_bytes": _L,
             "affgw_conv2d_dgrad_ws_bytes": _L, "affgw_conv2d_wgrad_ws_bytes": _L}
 
 _lib = None

@@ -6,6 +6,7 @@
 
 #include "../../include/affgw.h"
 #include "common.cuh"
+#include "pos_frame.cuh"
 
 // ---- implemented in the other translation units -------------------------------------------------------------
 int conv_fwd_simt(const void* x, int x_dt, const void* w, int w_dt, const float* bias, const void* addend, void* y,
@@ -27,9 +28,13 @@ long long pack_weight_tc_bytes(int Cout, int Cin, int KH, int KW, int ipad, int 
 int split_planes(const void* x, int x_dt, void* planes, long long rows, int C, int pitch, int c_store, int passes, int pre_act,
                  cudaStream_t st);
 // conv_shift.cu
-int conv_shift_ok(const ConvGeom& g, int passes);
-int conv_fwd_shift(const void* x_planes, long long plane_stride, const void* w_packed, const float* bias, const void* addend,
-                   void* y, int y_dt, const ConvGeom& g, int passes, cudaStream_t st);
+int conv_shift_ok(const ConvGeom& g);
+void conv_shift_frame(const ConvGeom& g, int channels, PosFrame& f);
+int split_positions(const void* src, int dt, void* planes, const PosFrame& f, int Hs, int Ws, int C, int pitch, int up, int oy0,
+                    int ox0, int pad_mode, int pre_act, int passes, cudaStream_t st);
+int conv_pos_tc(const void* x_planes, const PosFrame& f, const void* w_packed, const float* bias, const void* addend, void* y,
+                int K, int q_shift, int oy0, int ox0, int OH, int OW, int Cout, int out_pitch, int post_act, int passes,
+                cudaStream_t st);
 int pack_weight_shift(const float* w, void* out, int Cout, int Cin, int K, int ipad, int transpose_flip, int passes,
                       cudaStream_t st);
 long long pack_weight_shift_bytes(int Cout, int Cin, int K, int ipad, int transpose_flip, int passes);
@@ -38,6 +43,8 @@ int conv_wgrad_tc_ok(const ConvGeom& g);
 long long conv_wgrad_tc_ws_bytes(const ConvGeom& g);
 int conv_wgrad_tc(const void* x_planes, long long x_plane, const void* dy_planes, long long dy_plane, float* dw, void* workspace,
                   const ConvGeom& g, int cin_w, int passes, cudaStream_t st);
+int conv_wgrad_pos(const void* x_planes, const PosFrame& fx, const void* dy_planes, const PosFrame& fy, float* dw, void* workspace,
+                   const ConvGeom& g, int cin_w, int passes, cudaStream_t st);
 // norm.cu
 int norm_stats(const void* x, int dt, float* ws, float* mean, float* rstd, float* var_unbiased, int G, long long P, int C,
                float eps, int unbiased, cudaStream_t st);
@@ -150,13 +157,9 @@ int affgw_pack_weight(const float* w, void* out, int out_dtype, int Cout, int Ci
 static inline bool passes_ok(int p) { return p == 1 || p == 3; }
 static std::atomic<int> g_prefer_shift{1};
 
-extern int g_wgrad_prefer_shift;
 int affgw_conv_tc_prefer_shift(int enable) {
     const int prev = g_prefer_shift.load();
-    if (enable >= 0) {
-        g_prefer_shift.store(enable ? 1 : 0);
-        g_wgrad_prefer_shift = enable ? 1 : 0;
-    }
+    if (enable >= 0) g_prefer_shift.store(enable ? 1 : 0);
     return prev;
 }
 
@@ -197,23 +200,17 @@ static int make_tc_geom(const affgw_conv_desc* d, ConvGeom& g) {
     return 0;
 }
 
-// which tcgen05 kernel (= which packed-weight layout) a geometry runs on
-static int tc_layout(const ConvGeom& g, int passes) {
-    if (g_prefer_shift.load() && conv_shift_ok(g, passes)) return AFFGW_WLAYOUT_SHIFT;
+// which tcgen05 kernel family (= which operand-plane and packed-weight layout) the FORWARD geometry g selects; forward,
+// dgrad and wgrad of one convolution always use the same family
+static int tc_layout(const ConvGeom& g) {
+    if (g_prefer_shift.load() && conv_shift_ok(g)) return AFFGW_WLAYOUT_SHIFT;
     return conv_tc_ok(g) > 0 ? AFFGW_WLAYOUT_IM2COL : 0;
-}
-static int conv_tc_dispatch(const void* x, long long plane, const void* w, const float* bias, const void* addend, void* y,
-                            int y_dt, const ConvGeom& g, int passes, cudaStream_t st) {
-    const int lay = tc_layout(g, passes);
-    AFFGW_CHECK(lay != 0, "conv (tcgen05): shape not supported (stored Cin %d, pitch %d)", g.Cin, g.in_pitch);
-    if (lay == AFFGW_WLAYOUT_SHIFT) return conv_fwd_shift(x, plane, w, bias, addend, y, y_dt, g, passes, st);
-    return conv_fwd_tc(x, plane, w, bias, addend, y, y_dt, g, passes, st);
 }
 
 int affgw_conv_tc_supported(const affgw_conv_desc* d) {
     ConvGeom g;
     if (!d || make_tc_geom(d, g)) return 0;
-    return tc_layout(g, d->passes) != 0;
+    return tc_layout(g) != 0;
 }
 
 int affgw_conv2d_fwd(const void* x, const void* w, const float* bias, const void* addend, void* y,
@@ -223,8 +220,17 @@ int affgw_conv2d_fwd(const void* x, const void* w, const float* bias, const void
     AFFGW_CHECK(x && w && y, "conv2d_fwd: null pointer");
     if (d->algo == AFFGW_ALGO_TCGEN05) {
         if (int rc = make_tc_geom(d, g)) return rc;
+        const int lay = tc_layout(g);
+        AFFGW_CHECK(lay != 0, "conv2d_fwd: shape not supported by the tcgen05 kernels (stored Cin %d)", g.Cin);
+        if (lay == AFFGW_WLAYOUT_SHIFT) {
+            AFFGW_CHECK(d->y_dtype == AFFGW_F32, "conv2d_fwd: the position-space kernel writes fp32");
+            PosFrame f;
+            conv_shift_frame(g, d->Cin, f);
+            return conv_pos_tc(x, f, w, bias, addend, y, d->KH, 0, 0, 0, d->Ho, d->Wo, d->Cout, d->out_pitch, d->post_act,
+                               d->passes, S(stream));
+        }
         const long long plane = (long long)d->N * d->H * d->W * d->in_pitch;
-        return conv_tc_dispatch(x, plane, w, bias, addend, y, d->y_dtype, g, d->passes, S(stream));
+        return conv_fwd_tc(x, plane, w, bias, addend, y, d->y_dtype, g, d->passes, S(stream));
     }
     return conv_fwd_simt(x, d->x_dtype, w, d->w_dtype, bias, addend, y, d->y_dtype, g, S(stream));
 }
@@ -264,17 +270,65 @@ static void dgrad_geom(const affgw_conv_desc* d, const affgw_conv_desc& dd, Conv
 
 int affgw_conv_tc_layout(const affgw_conv_desc* d, int for_dgrad) {
     ConvGeom g;
-    if (!d || !passes_ok(d->passes)) return 0;
-    if (!for_dgrad) {
-        if (make_tc_geom(d, g)) return 0;
-        return tc_layout(g, d->passes);
-    }
+    if (!d || !passes_ok(d->passes) || d->algo != AFFGW_ALGO_TCGEN05) return 0;
+    affgw_conv_desc f = *d;
+    f.x_dtype = f.w_dtype = AFFGW_BF16;
+    f.pre_act = ACT_NONE;
+    if (make_tc_geom(&f, g)) return 0;
+    const int lay = tc_layout(g);
+    if (lay == AFFGW_WLAYOUT_SHIFT || !for_dgrad) return lay;
     affgw_conv_desc dd;
     bool direct;
     int Hp, Wp;
-    if (make_geom(d, g) || d->algo != AFFGW_ALGO_TCGEN05 || make_dgrad(d, dd, direct, Hp, Wp)) return 0;
+    if (make_dgrad(d, dd, direct, Hp, Wp)) return 0;
     dgrad_geom(d, dd, g);
-    return tc_layout(g, d->passes);
+    return conv_tc_ok(g) > 0 ? AFFGW_WLAYOUT_IM2COL : 0;
+}
+
+// forward frame of a position-space convolution (geometry only; dtypes / pre_act of d are not looked at)
+static int shift_frames(const affgw_conv_desc* d, ConvGeom& g, PosFrame& fx, PosFrame& fy) {
+    affgw_conv_desc f = *d;
+    f.x_dtype = f.w_dtype = AFFGW_BF16;
+    f.pre_act = ACT_NONE;
+    if (int rc = make_tc_geom(&f, g)) return rc;
+    AFFGW_CHECK(conv_shift_ok(g), "not a position-space convolution (stride %d, %dx%d filter)", d->stride, d->KH, d->KW);
+    conv_shift_frame(g, d->Cin, fx);
+    conv_shift_frame(g, d->Cout, fy);
+    return 0;
+}
+static void export_frame(const PosFrame& f, affgw_pos_frame* o) {
+    o->N = f.N; o->Hp = f.Hp; o->Wp = f.Wp; o->G = f.G; o->lead = f.lead; o->reserved = 0; o->QA = f.QA;
+}
+static PosFrame import_frame(const affgw_pos_frame* o) {
+    PosFrame f;
+    f.N = o->N; f.Hp = o->Hp; f.Wp = o->Wp; f.G = o->G; f.lead = o->lead; f.QA = o->QA;
+    return f;
+}
+
+int affgw_conv_pos_frames(const affgw_conv_desc* d, affgw_pos_frame* fx, affgw_pos_frame* fy) {
+    AFFGW_CHECK(d && fx && fy, "conv_pos_frames: null pointer");
+    ConvGeom g;
+    PosFrame a, b;
+    if (int rc = shift_frames(d, g, a, b)) return rc;
+    export_frame(a, fx);
+    export_frame(b, fy);
+    return 0;
+}
+long long affgw_position_planes_bytes(const affgw_pos_frame* f, int passes) {
+    if (!f || !passes_ok(passes) || f->G <= 0 || f->QA <= 0) return -1;
+    return (long long)(passes == 3 ? 2 : 1) * f->G * f->QA * 16;
+}
+int affgw_split_positions(const void* src, int dtype, void* planes, const affgw_pos_frame* f, int Hs, int Ws, int C, int pitch,
+                          int upsample, int oy0, int ox0, int pad_mode, int pre_act, int passes, void* stream) {
+    AFFGW_CHECK(src && planes && f && dt_ok(dtype) && passes_ok(passes), "split_positions: bad argument");
+    AFFGW_CHECK(Hs > 0 && Ws > 0 && C > 0 && pitch >= C && (upsample == 1 || upsample == 2), "split_positions: bad source");
+    AFFGW_CHECK(pad_mode >= 0 && pad_mode <= 2 && pre_act >= 0 && pre_act <= 3, "split_positions: bad mode");
+    AFFGW_CHECK(C <= 8 * f->G, "split_positions: %d channels do not fit %d groups", C, f->G);
+    if (pad_mode == PAD_REFLECT)
+        AFFGW_CHECK(oy0 < Hs * upsample && ox0 < Ws * upsample && f->Hp - oy0 - Hs * upsample < Hs * upsample &&
+                        f->Wp - ox0 - Ws * upsample < Ws * upsample, "split_positions: reflect pad >= input extent");
+    return split_positions(src, dtype, planes, import_frame(f), Hs, Ws, C, pitch, upsample, oy0, ox0, pad_mode, pre_act, passes,
+                           S(stream));
 }
 
 long long affgw_conv2d_dgrad_ws_bytes(const affgw_conv_desc* d) {
@@ -303,8 +357,24 @@ int affgw_conv2d_dgrad(const void* dy, const void* wt, const void* x, void* dx, 
     if (tc) {
         AFFGW_CHECK(passes_ok(d->passes) && dt_ok(d->grad_dtype), "conv2d_dgrad: bad passes / grad_dtype");
         AFFGW_CHECK(d->y_dtype == AFFGW_BF16 && d->w_dtype == AFFGW_BF16, "conv2d_dgrad (tcgen05): operands are bf16 planes / tiles");
-        const long long plane = (long long)dd.N * dd.H * dd.W * dd.in_pitch;
-        rc = conv_tc_dispatch(dy, plane, wt, nullptr, nullptr, out, gdt, g, d->passes, S(stream));
+        if (affgw_conv_tc_layout(d, 1) == AFFGW_WLAYOUT_SHIFT) {
+            // position space of the FORWARD convolution: dV[p] = sum_taps dYp[p - (K-1)(Wp+1) + tap] . Wflip[tap]
+            AFFGW_CHECK(gdt == AFFGW_F32, "conv2d_dgrad: the position-space kernel writes fp32");
+            ConvGeom gf;
+            PosFrame fx, fy;
+            if (int rc2 = shift_frames(d, gf, fx, fy)) return rc2;
+            const int qs = -(d->KH - 1) * (fy.Wp + 1);
+            if (direct)
+                rc = conv_pos_tc(dy, fy, wt, nullptr, nullptr, dx, d->KH, qs, d->pad, d->pad, d->H, d->W, d->Cin, d->Cin, ACT_NONE,
+                                 d->passes, S(stream));
+            else
+                rc = conv_pos_tc(dy, fy, wt, nullptr, nullptr, workspace, d->KH, qs, 0, 0, Hp, Wp, d->Cin, d->Cin, ACT_NONE,
+                                 d->passes, S(stream));
+        } else {
+            AFFGW_CHECK(conv_tc_ok(g) > 0, "conv2d_dgrad: shape not supported by the tcgen05 kernel");
+            const long long plane = (long long)dd.N * dd.H * dd.W * dd.in_pitch;
+            rc = conv_fwd_tc(dy, plane, wt, nullptr, nullptr, out, gdt, g, d->passes, S(stream));
+        }
     } else {
         rc = conv_fwd_simt(dy, dd.x_dtype, wt, d->w_dtype, nullptr, nullptr, out, dd.y_dtype, g, S(stream));
     }
@@ -330,6 +400,7 @@ static int make_wgrad_tc_geom(const affgw_conv_desc* d, ConvGeom& g) {
 long long affgw_conv2d_wgrad_ws_bytes(const affgw_conv_desc* d) {
     ConvGeom g;
     if (!d || d->algo != AFFGW_ALGO_TCGEN05 || make_wgrad_tc_geom(d, g)) return 0;
+    if (affgw_conv_tc_layout(d, 0) == AFFGW_WLAYOUT_SHIFT) return conv_wgrad_tc_ws_bytes(g);
     return conv_wgrad_tc_ok(g) ? conv_wgrad_tc_ws_bytes(g) : 0;
 }
 
@@ -341,8 +412,14 @@ int affgw_conv2d_wgrad(const void* x, const void* dy, float* dw, void* workspace
         if (int rc = make_wgrad_tc_geom(d, g)) return rc;
         AFFGW_CHECK(passes_ok(d->passes), "conv2d_wgrad: passes must be 1 or 3");
         AFFGW_CHECK(d->x_dtype == AFFGW_BF16 && d->y_dtype == AFFGW_BF16, "conv2d_wgrad (tcgen05): operands are bf16 planes");
-        AFFGW_CHECK(conv_wgrad_tc_ok(g), "conv2d_wgrad: shape not supported by the tcgen05 kernel");
         AFFGW_CHECK(workspace != nullptr, "conv2d_wgrad: the tcgen05 kernel needs affgw_conv2d_wgrad_ws_bytes() of workspace");
+        if (affgw_conv_tc_layout(d, 0) == AFFGW_WLAYOUT_SHIFT) {
+            ConvGeom gf;
+            PosFrame fx, fy;
+            if (int rc2 = shift_frames(d, gf, fx, fy)) return rc2;
+            return conv_wgrad_pos(x, fx, dy, fy, dw, workspace, g, d->Cin, d->passes, S(stream));
+        }
+        AFFGW_CHECK(conv_wgrad_tc_ok(g), "conv2d_wgrad: shape not supported by the tcgen05 kernel");
         const long long xpl = (long long)d->N * d->H * d->W * d->in_pitch;
         const long long ypl = g.M * d->out_pitch;
         return conv_wgrad_tc(x, xpl, dy, ypl, dw, workspace, g, d->Cin, d->passes, S(stream));

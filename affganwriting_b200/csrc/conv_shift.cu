@@ -1,80 +1,86 @@
-// Stride-1 convolution as a "shifted" implicit GEMM on the 5th-generation tensor cores (tcgen05.mma, TMEM accumulators).
+// Stride-1 convolutions (forward, input gradient, weight gradient) as "shifted" GEMMs in POSITION SPACE on the
+// 5th-generation tensor cores (tcgen05.mma, fp32 accumulators in TMEM).
 //
 // The im2col kernel in conv_tc.cu re-reads every input element once per filter tap from L2 (9x for 3x3, 25x for 5x5,
-// 49x for 7x7); at ~42 B/clk/SM of L2->SM bandwidth that, not the tensor pipe, bounded it.  Here a CTA stages a window of
-// the PADDED (and, for the decoder, x2-upsampled) input in shared memory ONCE per 16-channel block and every filter tap
-// is just a different start address of the same window:
+// 49x for 7x7); at ~42 B/clk/SM of L2->SM bandwidth that, not the tensor pipe, bounded it.  Here every tensor of one
+// convolution lives in the position space of its PADDED (and, for the decoder, x2-upsampled) input:
 //
-//   virtual input V[n][yp][xp][c], yp < Hp = up*H + 2*pad, xp < Wp; flattened position q = (n*Hp + yp)*Wp + xp
-//   output (n, y, x) lives at q = (n*Hp + y)*Wp + x and reads V[q + ky*Wp + kx]           (stride 1)
+//   frame [N][Hp][Wp], Hp = up*H + 2*pad; flattened position q = (n*Hp + yp)*Wp + xp
+//   V[q][ci]   the padded / upsampled / pre-activated input          ("x position planes")
+//   Yp[q][co]  the output at its top-left-aligned position, zero where yp >= Ho or xp >= Wo ("dY position planes")
 //
-//   shared-memory window, "planar": [hi/lo plane][8-channel group][position] x 16 bytes.  Eight consecutive positions
-//   of one channel group are 128 contiguous bytes = one UMMA core matrix of the un-swizzled K-major operand layout,
-//   so A for tap (ky, kx) and M-tile mt is the descriptor {start = window + (mt*128 + ky*Wp + kx)*16,
-//   LBO = plane pitch (next 8 channels), SBO = 128 (next 8 positions)}.  Padding (zero / reflect / replicate) and
-//   nearest x2 upsampling are resolved once per position when the window is filled (16-byte cp.async with the mapped
-//   source address or zero fill), never per tap.
+//   forward   Y[q]        = sum_{ky,kx} V[q + ky*Wp + kx] . W[ky][kx]
+//   dgrad     dV[p]       = sum_{ky,kx} dYp[p - (K-1)(Wp+1) + ky*Wp + kx] . Wflip[ky][kx]      (any padding mode; the
+//                           reflect / upsample fold or the zero-pad crop happens on dV afterwards / in the epilogue)
+//   wgrad     dW[ky][kx]  = sum_q V[q + ky*Wp + kx]^T . dYp[q]
 //
-// CTA tile: 4 M-tiles x 128 positions against BN <= 64 output channels, so a weight stage (taps x 16 channels x BN,
-// one cp.async.bulk) is reused by 512 output positions; 2 x 4 x BN TMEM columns double-buffer the accumulators so the
-// epilogue of one tile overlaps the main loop of the next.  Positions that fall on padding columns / rows compute junk
-// that the epilogue skips (2/Wp of the work).  The 16/32-channel discriminator blocks, the 1->16 and 64->1 7x7 stems
-// and the 512-channel VGG / decoder layers all run through this kernel; dgrad is the same kernel on flipped weights.
+// Operand planes are stored PLANAR in HBM: [hi|lo plane][8-channel group][position] x 16 bytes, written by
+// split_positions_kernel (padding mode, upsampling, activation-first LeakyReLU and the split-bf16 remainder are all
+// resolved there, once per element).  Eight consecutive positions of one group are 128 contiguous bytes = one UMMA
+// core matrix of the un-swizzled layouts (K-major for forward / dgrad, MN-major for wgrad), so
+//   * a pipeline stage is filled by a handful of cp.async.bulk copies (TMA engine, mbarrier complete_tx) of CONTIGUOUS
+//     runs of positions - no per-thread gather, no index arithmetic in the main loop;
+//   * every filter tap is just a different descriptor start address inside the same shared-memory window.
 //
-// NPASS = 3: split-bf16 product a*w ~= a_hi*w_hi + a_lo*w_hi + a_hi*w_lo (see conv_tc.cu).
+// NPASS = 3: split-bf16 product a*w ~= a_hi*w_hi + a_lo*w_hi + a_hi*w_lo (hi = bf16(v), lo = bf16(v - hi)).
 //
-// Replaces the cuDNN convolutions behind reference blocks.py:148 / vgg_tro_channel3_modi.py:47 / modules_tro.py:594-603.
+// Replaces the cuDNN convolutions (forward and backward) behind reference blocks.py:148 /
+// vgg_tro_channel3_modi.py:47 / modules_tro.py:594-603 and loss.backward() (network_tro.py:55,102,113,129).
 #include "common.cuh"
+#include "pos_frame.cuh"
 #include "tc_ptx.cuh"
 
 namespace {
 
 using namespace tcptx;
 
-constexpr int NUM_PRODUCER_THREADS = 128;
-constexpr int MMA_WARP = 4;
-constexpr int NUM_THREADS = 32 * 9;          // 4 producer warps + 1 MMA warp + 4 epilogue warps
+constexpr int MMA_WARP = 1;
+constexpr int NUM_THREADS = 32 * 6;          // producer warp, MMA warp, 4 epilogue warps
 constexpr int MT = 4;                        // M-tiles (of 128 positions) per CTA tile
 constexpr int TILE_POS = MT * 128;
-constexpr int MAXP = 16;                     // window positions per producer thread pair slot: NP <= 64 * MAXP
 constexpr int MAX_STAGES = 4;
 constexpr int SMEM_LIMIT = 227 * 1024;
 
 struct ShArgs {
-    const bf16* x;             // operand planes [NPL][N*H*W][Cs]
-    long long x_plane;         // elements between the hi and lo plane
+    const bf16* x;             // position planes [NPL][G][QA][8]
     const bf16* w;             // [n_tile][ky][cb][kx][plane][cgroup][BN][8]
     const float* bias;
     const float* addend;
     float* y;
-    int N, H, W, Cs;           // stored input (before upsampling); Cs = stored channels of the planes
-    int up, pad, pad_mode, K;
-    int Hv, Wv, Hp, Wp, Ho, Wo;
+    int N, Hp, Wp, K;
+    int G, lead;
+    long long QA;
+    int q_shift;               // window start relative to the tile's first position (0 forward, -(K-1)(Wp+1) dgrad)
+    int oy0, ox0, OH, OW;      // output pixel of position (n, yp, xp) = (n, yp - oy0, xp - ox0) if inside [OH) x [OW)
     int Cout, out_pitch, post_act;
     int CB;                    // 16-channel blocks
     int KYG;                   // kernel rows per pipeline stage: K (whole filter) or 1
-    int NP, NPa;               // window positions per stage, plane pitch in positions
+    int NP, NPa;               // window positions per stage, shared-memory plane pitch in positions
     int stages;
-    int a_bytes, b_chunk_bytes;   // bytes of one stage's window / of one (ky, cb) weight chunk
+    int a_bytes, b_chunk_bytes;   // shared-memory bytes of one stage's window / bytes of one (ky, cb) weight chunk
     int n_tiles;
     int total_tiles;
-    int Q;                     // N * Hp * Wp
     int vec_ok;
 };
 
-// K-major, un-swizzled shared-memory matrix descriptor (core matrices of 8 rows x 16 bytes)
-__device__ __forceinline__ uint64_t make_kmajor_nosw_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// un-swizzled shared-memory matrix descriptors (core matrices of 8 rows x 16 bytes)
+__device__ __forceinline__ uint64_t make_nosw_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
-    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;     // between the two 8-element K core matrices
-    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;     // between 8-row groups along M / N
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
     d |= 1ull << 46;                                      // descriptor version (sm_100)
     return d;
 }
-__host__ __device__ constexpr uint32_t make_idesc_bf16_kk(int n) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+// kind::f16, D = f32, A = B = bf16, M = 128, N = n; mn_major sets the A and B major bits (wgrad)
+__host__ __device__ constexpr uint32_t make_idesc(int n, bool mn_major) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | (mn_major ? ((1u << 15) | (1u << 16)) : 0u) | ((uint32_t)(n >> 3) << 17) |
+           ((uint32_t)(128 >> 4) << 24);
 }
 
+// ---------------------------------------------------------------------------------------- forward / input gradient
+// CTA tile: 4 M-tiles x 128 positions against BN <= 64 output channels; a stage = the window of one 16-channel block
+// (all kernel rows, or one kernel row when the whole-filter window does not fit twice in shared memory) + its weights.
 template <int BN, int NPASS>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_shift_tcgen05_kernel(const __grid_constant__ ShArgs a) {
@@ -99,7 +105,7 @@ conv_shift_tcgen05_kernel(const __grid_constant__ ShArgs a) {
 
     if (tid == MMA_WARP * 32) {
         for (int s = 0; s < stages; ++s) {
-            mbar_init(full_bar(s), NUM_PRODUCER_THREADS);
+            mbar_init(full_bar(s), 1);
             mbar_init(empty_bar(s), 1);
         }
         for (int i = 0; i < 2; ++i) {
@@ -118,79 +124,41 @@ conv_shift_tcgen05_kernel(const __grid_constant__ ShArgs a) {
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr));
 
-    if (warp < 4) {
-        // ============================== window / weight producer ==============================
-        const int cg = tid & 1;               // 8-channel group of the 16-channel block this thread copies
-        const int p0 = tid >> 1;              // positions p0, p0 + 64, ...
-        const size_t w_tile_elems = (size_t)a.K * a.CB * (a.b_chunk_bytes / 2);
-        uint32_t it = 0;
-        for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
-            const int nt = t % a.n_tiles;
-            const int q0 = (t / a.n_tiles) * TILE_POS;
-            const bf16* wt = a.w + (size_t)nt * w_tile_elems;
-            for (int kg = 0; kg < KG; ++kg) {
-                // source pixel of every window position this thread owns (padding / upsampling resolved here, once)
-                int off[MAXP];
-                const int qb = q0 + kg * a.KYG * a.Wp;
-#pragma unroll
-                for (int i = 0; i < MAXP; ++i) {
-                    const int p = p0 + 64 * i;
-                    int o = -2;                                   // -2: outside the window, nothing to copy
-                    if (p < a.NP) {
-                        const int q = qb + p;
-                        o = -1;                                   // -1: contributes zeros
-                        if (q < a.Q) {
-                            const int xp = q % a.Wp;
-                            const int r = q / a.Wp;
-                            const int yp = r % a.Hp;
-                            const int n = r / a.Hp;
-                            const int sy = map_coord(yp - a.pad, a.Hv, a.pad_mode, a.up, 1);
-                            const int sx = map_coord(xp - a.pad, a.Wv, a.pad_mode, a.up, 1);
-                            if (sy >= 0 && sx >= 0) o = (n * a.H + sy) * a.W + sx;
-                        }
-                    }
-                    off[i] = o;
-                }
-                for (int cb = 0; cb < a.CB; ++cb, ++it) {
-                    const int s = it % stages;
-                    const uint32_t ph = (it / stages) & 1u;
-                    mbar_wait(empty_bar(s), ph ^ 1u);
-                    if (tid == 0) {
-                        mbar_expect_tx(full_bar(s), (uint32_t)b_bytes);
+    if (warp == 0) {
+        // ============================== producer: bulk copies only ==============================
+        if (lane == 0) {
+            const size_t w_tile_elems = (size_t)a.K * a.CB * (a.b_chunk_bytes / 2);
+            const uint32_t win_bytes = (uint32_t)a.NP * 16u;
+            uint32_t it = 0;
+            for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
+                const int nt = t % a.n_tiles;
+                const long long q0 = (long long)(t / a.n_tiles) * TILE_POS + a.q_shift + a.lead;
+                const bf16* wt = a.w + (size_t)nt * w_tile_elems;
+                for (int kg = 0; kg < KG; ++kg) {
+                    const long long qw = q0 + (long long)kg * a.KYG * a.Wp;
+                    for (int cb = 0; cb < a.CB; ++cb, ++it) {
+                        const int s = it % stages;
+                        const uint32_t ph = (it / stages) & 1u;
+                        mbar_wait(empty_bar(s), ph ^ 1u);
+                        mbar_arrive_expect_tx(full_bar(s), (uint32_t)b_bytes + 2u * NPL * win_bytes);
                         for (int r = 0; r < a.KYG; ++r)
                             bulk_copy_g2s(b_smem(s) + r * a.b_chunk_bytes,
                                           wt + ((size_t)(kg * a.KYG + r) * a.CB + cb) * (a.b_chunk_bytes / 2),
                                           (uint32_t)a.b_chunk_bytes, full_bar(s));
-                    }
-                    const int c = cb * 16 + cg * 8;
-                    const bool cok = c < a.Cs;
-                    const uint32_t dst0 = a_smem(s) + (uint32_t)cg * plane_pitch + (uint32_t)p0 * 16u;
 #pragma unroll
-                    for (int i = 0; i < MAXP; ++i) {
-                        if (off[i] != -2) {
-                            const bool ok = cok && off[i] >= 0;
-                            const bf16* src = ok ? a.x + ((size_t)off[i] * a.Cs + c) : a.x;
-                            const uint32_t dst = dst0 + (uint32_t)(64 * i) * 16u;
-                            cp_async_16(dst, src, ok ? 16u : 0u);
-                            if (NPL == 2) cp_async_16(dst + 2u * plane_pitch, ok ? src + a.x_plane : src, ok ? 16u : 0u);
-                        }
-                    }
-                    cp_async_commit();
-                    if (it >= 1u) {
-                        cp_async_wait<1>();
-                        fence_proxy_async();
-                        mbar_arrive(full_bar((it - 1u) % stages));
+                        for (int pl = 0; pl < NPL; ++pl)
+#pragma unroll
+                            for (int cg = 0; cg < 2; ++cg)
+                                bulk_copy_g2s(a_smem(s) + (uint32_t)(pl * 2 + cg) * plane_pitch,
+                                              a.x + (((size_t)pl * a.G + cb * 2 + cg) * a.QA + qw) * 8, win_bytes, full_bar(s));
                     }
                 }
             }
         }
-        cp_async_wait<0>();
-        fence_proxy_async();
-        if (it >= 1u) mbar_arrive(full_bar((it - 1u) % stages));
     } else if (warp == MMA_WARP) {
         // ============================== MMA issuer (one thread) ==============================
         if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_bf16_kk(BN);
+            constexpr uint32_t idesc = make_idesc(BN, false);
             const uint32_t b_plane = 2u * BN * 16u;               // bytes of one [cgroup][BN][8] weight image
             uint32_t it = 0, tl = 0;
             for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x, ++tl) {
@@ -203,23 +171,25 @@ conv_shift_tcgen05_kernel(const __grid_constant__ ShArgs a) {
                     const uint32_t ph = (it / stages) & 1u;
                     mbar_wait(full_bar(s), ph);
                     tc_fence_after();
-                    const uint32_t ab = a_smem(s), bb = b_smem(s);
+                    // descriptors differ only in their start address: add (byte offset >> 4) to the low word
+                    const uint64_t a_base = make_nosw_desc(a_smem(s), plane_pitch, 128u);           // K-major: LBO = next 8
+                    const uint64_t b_base = make_nosw_desc(b_smem(s), BN * 16u, 128u);              // channels, SBO = next 8 rows
+                    const uint32_t a_lo_off = (2u * plane_pitch) >> 4, b_lo_off = b_plane >> 4;
+                    uint32_t tap = 0;
                     for (int r = 0; r < a.KYG; ++r) {
-                        for (int kx = 0; kx < a.K; ++kx) {
-                            const uint32_t tap = (uint32_t)(r * a.K + kx);
-                            const uint64_t b_hi = make_kmajor_nosw_desc(bb + tap * NPL * b_plane, BN * 16u, 128u);
-                            const uint64_t b_lo = make_kmajor_nosw_desc(bb + (tap * NPL + 1u) * b_plane, BN * 16u, 128u);
-                            const uint32_t shift = (uint32_t)(r * a.Wp + kx) * 16u;
-                            const uint32_t first = (uint32_t)((st | (int)tap) != 0);
+                        const uint32_t row = (uint32_t)(r * a.Wp);
+#pragma unroll 1
+                        for (int kx = 0; kx < a.K; ++kx, ++tap) {
+                            const uint64_t b_hi = b_base + (uint64_t)(tap * NPL * (b_plane >> 4));
+                            const uint64_t a_t = a_base + (uint64_t)(row + (uint32_t)kx);
+                            const uint32_t accum = (uint32_t)((st | (int)tap) != 0);
 #pragma unroll
                             for (int mt = 0; mt < MT; ++mt) {
-                                const uint32_t aoff = ab + shift + (uint32_t)mt * 2048u;
-                                const uint64_t a_hi = make_kmajor_nosw_desc(aoff, plane_pitch, 128u);
-                                umma_bf16(d0 + mt * BN, a_hi, b_hi, idesc, first);
+                                const uint64_t a_hi = a_t + (uint64_t)(mt * 128);
+                                umma_bf16(d0 + mt * BN, a_hi, b_hi, idesc, accum);
                                 if (NPASS == 3) {
-                                    const uint64_t a_lo = make_kmajor_nosw_desc(aoff + 2u * plane_pitch, plane_pitch, 128u);
-                                    umma_bf16(d0 + mt * BN, a_lo, b_hi, idesc, 1u);
-                                    umma_bf16(d0 + mt * BN, a_hi, b_lo, idesc, 1u);
+                                    umma_bf16(d0 + mt * BN, a_hi + a_lo_off, b_hi, idesc, 1u);
+                                    umma_bf16(d0 + mt * BN, a_hi, b_hi + b_lo_off, idesc, 1u);
                                 }
                             }
                         }
@@ -242,12 +212,12 @@ conv_shift_tcgen05_kernel(const __grid_constant__ ShArgs a) {
 #pragma unroll 1
             for (int mt = 0; mt < MT; ++mt) {
                 const int q = q0 + mt * 128 + wq * 32 + lane;
-                const int xp = q % a.Wp;
+                const int xp = q % a.Wp - a.ox0;
                 const int r = q / a.Wp;
-                const int yp = r % a.Hp;
+                const int yp = r % a.Hp - a.oy0;
                 const int n = r / a.Hp;
-                const bool valid = n < a.N && yp < a.Ho && xp < a.Wo;
-                const long long m = ((long long)n * a.Ho + yp) * a.Wo + xp;
+                const bool valid = n < a.N && (unsigned)yp < (unsigned)a.OH && (unsigned)xp < (unsigned)a.OW;
+                const long long m = ((long long)n * a.OH + yp) * a.OW + xp;
                 if (__ballot_sync(0xffffffffu, valid) == 0u) continue;      // warp-uniform: a run of padding positions
 #pragma unroll 1
                 for (int j = 0; j < BN / 16; ++j) {
@@ -326,11 +296,81 @@ __global__ void pack_weight_shift_kernel(const float* __restrict__ w, bf16* __re
                 v = w[(((long long)o * Cin + i) * K + ky) * K + kx];
         }
         const bf16 hi = __float2bfloat16_rn(v);
-        // destination: ((((nt*K + ky)*CB + cb)*K + kx)*npl + pl)*2 + cgp)*BN + n)*8 + e
         const long long base = ((((long long)nt * K + ky) * CB + cb) * K + kx) * npl;
         bf16* dst = out + (((base * 2 + cgp) * BN + n) * 8 + e);
         dst[0] = hi;
         if (npl == 2) dst[2LL * BN * 8] = __float2bfloat16_rn(v - __bfloat162float(hi));
+    }
+}
+
+// ---------------------------------------------------------------------------------------- position planes
+// src [N][Hs][Ws][pitch] (fp32 or bf16) -> planes [npl][G][QA][8] bf16.  Frame position (n, yp, xp) takes the source pixel
+// map(yp - oy0), map(xp - ox0) of the (x up) virtual source under pad_mode, or zero; the lead / tail margins are zeros.
+// One block transposes a tile of 32 positions x 32 channel groups through shared memory so that both the NHWC reads and
+// the planar writes are contiguous.
+template <typename T, int TG>
+__global__ void __launch_bounds__(256)
+split_positions_kernel(const T* __restrict__ src, bf16* __restrict__ planes, int N, int Hs, int Ws, int C, int pitch, int up,
+                       int oy0, int ox0, int pad_mode, int pre_act, int Hp, int Wp, int G, int lead, int QA, int npl) {
+    constexpr int TP = 1024 / TG;                     // positions per block: the tile is always 1024 (position, group) items
+    __shared__ uint4 tile[2][TG * (TP + 1)];          // [plane][group][position], +1 column against bank conflicts
+    const int tid = threadIdx.x;
+    const int p0 = blockIdx.x * TP;                   // stored position (lead included)
+    const int g0 = blockIdx.y * TG;
+    const int Q = N * Hp * Wp;
+    const bool vec = (pitch % 8 == 0) && (C % 8 == 0);
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+        const int item = tid + 256 * it;
+        const int gl = item % TG, pi = item / TG;
+        const int g = g0 + gl;
+        const int q = p0 + pi - lead;
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = 0.f;
+        if (g * 8 < C && q >= 0 && q < Q) {
+            const int xp = q % Wp;
+            const int r = q / Wp;
+            const int yp = r % Hp;
+            const int n = r / Hp;
+            const int sy = map_coord(yp - oy0, Hs * up, pad_mode, up, 1);
+            const int sx = map_coord(xp - ox0, Ws * up, pad_mode, up, 1);
+            if (sy >= 0 && sx >= 0) {
+                const T* sp = src + ((size_t)((n * Hs + sy) * Ws + sx) * pitch + g * 8);
+                if (vec) {
+                    ld8(sp, v);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v[i] = (g * 8 + i < C) ? to_f(sp[i]) : 0.f;
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = act_apply(v[i], pre_act);
+            }
+        }
+        uint4 hi, lo;
+        __nv_bfloat162* hh = reinterpret_cast<__nv_bfloat162*>(&hi);
+        __nv_bfloat162* ll = reinterpret_cast<__nv_bfloat162*>(&lo);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            hh[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+            const float2 f = __bfloat1622float2(hh[i]);
+            ll[i] = __floats2bfloat162_rn(v[2 * i] - f.x, v[2 * i + 1] - f.y);
+        }
+        tile[0][gl * (TP + 1) + pi] = hi;
+        tile[1][gl * (TP + 1) + pi] = lo;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+        const int item = tid + 256 * it;
+        const int pi = item % TP, gl = item / TP;
+        const int g = g0 + gl;
+        const int p = p0 + pi;
+        if (g < G && p < QA) {
+            uint4* dst = reinterpret_cast<uint4*>(planes) + ((size_t)g * QA + p);
+            dst[0] = tile[0][gl * (TP + 1) + pi];
+            if (npl == 2) dst[(size_t)G * QA] = tile[1][gl * (TP + 1) + pi];
+        }
     }
 }
 
@@ -340,27 +380,16 @@ struct ShPlan {
 
 int shift_block_n(int cout) { return cout > 32 ? 64 : cout > 16 ? 32 : 16; }
 
-// stage geometry for a convolution; returns 0 if the shifted kernel cannot take it
-int make_plan(const ConvGeom& g, int passes, ShPlan& p) {
-    if (g.stride != 1 || g.zi != 1 || g.KH != g.KW) return 0;
-    if (g.Cin % 8 != 0 || g.in_pitch != g.Cin) return 0;
-    const int npl = passes == 3 ? 2 : 1;
-    const long long Hp = g.Hv + 2 * g.pad, Wp = g.Wv + 2 * g.pad;
-    if (Hp - g.KH + 1 != g.Ho || Wp - g.KW + 1 != g.Wo) return 0;
-    // 1x1 filters have no tap reuse to exploit, and on tiny maps the padding positions (computed, then dropped) cost more
-    // than the window saves: both stay on the im2col kernel
-    if (g.KH == 1 || 2 * Hp * Wp > 3LL * g.Ho * g.Wo) return 0;
-    if ((long long)g.N * Hp * Wp + 2048 >= (1LL << 31) / 16) return 0;           // 32-bit position / byte arithmetic
-    if ((long long)g.N * g.H * g.W * g.Cin >= (1LL << 31)) return 0;
-    p.bn = shift_block_n(g.Cout);
+// pipeline-stage geometry; K x K filter on a frame of pitch Wp, npl planes, BN-wide weight stage
+int make_plan(int K, int Wp, int npl, int bn, ShPlan& p) {
+    p.bn = bn;
     for (int mode = 0; mode < 2; ++mode) {
-        p.KYG = mode == 0 ? g.KH : 1;
-        if (mode == 1 && g.KH == 1) break;
-        p.NP = TILE_POS + (p.KYG - 1) * (int)Wp + g.KW - 1;
-        if (p.NP > 64 * MAXP) continue;
+        p.KYG = mode == 0 ? K : 1;
+        if (mode == 1 && K == 1) break;
+        p.NP = TILE_POS + (p.KYG - 1) * Wp + K - 1;
         p.NPa = (p.NP + 7) / 8 * 8;
         p.a_bytes = npl * 2 * p.NPa * 16;
-        p.b_chunk_bytes = g.KW * npl * 2 * p.bn * 16;
+        p.b_chunk_bytes = K * npl * 2 * p.bn * 16;
         const int stage = p.a_bytes + p.KYG * p.b_chunk_bytes;
         const int st = (SMEM_LIMIT - 128 - 256) / stage;
         if (st < 2) continue;
@@ -374,13 +403,13 @@ int make_plan(const ConvGeom& g, int passes, ShPlan& p) {
 template <int BN, int NPASS>
 int launch_shift(const ShArgs& args, int smem_bytes, cudaStream_t st) {
     auto kern = conv_shift_tcgen05_kernel<BN, NPASS>;
-    static int configured = 0;
-    if (configured < smem_bytes) {
+    static bool configured = false;
+    if (!configured) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) {
             affgw_set_error("conv_shift: cannot reserve %d bytes of shared memory", SMEM_LIMIT);
             return -2;
         }
-        configured = SMEM_LIMIT;
+        configured = true;
     }
     const int grid = args.total_tiles < 148 ? args.total_tiles : 148;
     kern<<<grid, NUM_THREADS, smem_bytes, st>>>(args);
@@ -390,9 +419,62 @@ int launch_shift(const ShArgs& args, int smem_bytes, cudaStream_t st) {
 
 }  // namespace
 
-int conv_shift_ok(const ConvGeom& g, int passes) {
+// Is the forward convolution g a position-space convolution?  One rule for forward, dgrad and wgrad so that the operand
+// planes of a layer are built once.
+int conv_shift_ok(const ConvGeom& g) {
+    if (g.stride != 1 || g.zi != 1 || g.KH != g.KW || g.KH < 2 || g.KH > 7) return 0;
+    const long long Hp = g.Hv + 2 * g.pad, Wp = g.Wv + 2 * g.pad;
+    if (Hp - g.KH + 1 != g.Ho || Wp - g.KW + 1 != g.Wo) return 0;
+    // on tiny maps the padding positions (computed, then dropped) cost more than the window saves; 1x1 filters have no tap
+    // reuse to exploit: both stay on the im2col kernels
+    if (2 * Hp * Wp > 3LL * g.Ho * g.Wo) return 0;
+    if ((long long)g.N * Hp * Wp + 8192 >= (1LL << 31) / 16) return 0;           // 32-bit position arithmetic
     ShPlan p;
-    return make_plan(g, passes, p);
+    if (!make_plan(g.KH, (int)Wp, 2, 64, p)) return 0;
+    return 1;
+}
+
+// frame of the forward convolution g for a tensor with `channels` channels
+void conv_shift_frame(const ConvGeom& g, int channels, PosFrame& f) {
+    f.N = g.N;
+    f.Hp = g.Hv + 2 * g.pad;
+    f.Wp = g.Wv + 2 * g.pad;
+    f.G = 2 * ((channels + 15) / 16);
+    const int span = (g.KH - 1) * (f.Wp + 1);
+    f.lead = (span + 7) / 8 * 8;
+    const long long Q = (long long)f.N * f.Hp * f.Wp;
+    f.QA = f.lead + (Q + TILE_POS - 1) / TILE_POS * TILE_POS + TILE_POS + span + g.KH + 32;
+    f.QA = (f.QA + 31) / 32 * 32;
+}
+
+int split_positions(const void* src, int dt, void* planes, const PosFrame& f, int Hs, int Ws, int C, int pitch, int up, int oy0,
+                    int ox0, int pad_mode, int pre_act, int passes, cudaStream_t st) {
+    const int npl = passes == 3 ? 2 : 1;
+    if (f.QA >= (1LL << 31) || (long long)f.N * Hs * Ws >= (1LL << 31)) {
+        affgw_set_error("split_positions: frame too large for 32-bit position arithmetic");
+        return -1;
+    }
+    const int QA = (int)f.QA;
+#define AFFGW_SPLIT(T, TGV)                                                                                               \
+    split_positions_kernel<T, TGV><<<dim3((unsigned)((QA + 1024 / TGV - 1) / (1024 / TGV)), (unsigned)((f.G + TGV - 1) / TGV)), \
+                                     256, 0, st>>>((const T*)src, (bf16*)planes, f.N, Hs, Ws, C, pitch, up, oy0, ox0, pad_mode, \
+                                                   pre_act, f.Hp, f.Wp, f.G, f.lead, QA, npl)
+    if (dt == AFFGW_F32) {
+        if (f.G <= 2) AFFGW_SPLIT(float, 2);
+        else if (f.G <= 4) AFFGW_SPLIT(float, 4);
+        else if (f.G <= 8) AFFGW_SPLIT(float, 8);
+        else if (f.G <= 16) AFFGW_SPLIT(float, 16);
+        else AFFGW_SPLIT(float, 32);
+    } else {
+        if (f.G <= 2) AFFGW_SPLIT(bf16, 2);
+        else if (f.G <= 4) AFFGW_SPLIT(bf16, 4);
+        else if (f.G <= 8) AFFGW_SPLIT(bf16, 8);
+        else if (f.G <= 16) AFFGW_SPLIT(bf16, 16);
+        else AFFGW_SPLIT(bf16, 32);
+    }
+#undef AFFGW_SPLIT
+    AFFGW_LAUNCH_CHECK("split_positions");
+    return 0;
 }
 
 long long pack_weight_shift_bytes(int Cout, int Cin, int K, int ipad, int transpose_flip, int passes) {
@@ -420,32 +502,37 @@ int pack_weight_shift(const float* w, void* out, int Cout, int Cin, int K, int i
     return 0;
 }
 
-int conv_fwd_shift(const void* x_planes, long long plane_stride, const void* w_packed, const float* bias, const void* addend,
-                   void* y, int y_dt, const ConvGeom& g, int passes, cudaStream_t st) {
+// One position-space convolution over the planes `x` (frame f): out[(n, yp - oy0, xp - ox0)][co] for the positions whose
+// shifted coordinates fall inside [OH) x [OW).
+//   forward : q_shift = 0,               (oy0, ox0, OH, OW) = (0, 0, Ho, Wo)
+//   dgrad   : q_shift = -(K-1)(Wp+1),    (pad, pad, H, W) for the zero-pad crop or (0, 0, Hp, Wp) for the full frame
+int conv_pos_tc(const void* x_planes, const PosFrame& f, const void* w_packed, const float* bias, const void* addend, void* y,
+                int K, int q_shift, int oy0, int ox0, int OH, int OW, int Cout, int out_pitch, int post_act, int passes,
+                cudaStream_t st) {
     ShPlan p;
-    if (y_dt != AFFGW_F32 || !make_plan(g, passes, p)) {
-        affgw_set_error("conv_shift: unsupported convolution (stride %d, stored Cin %d, passes %d)", g.stride, g.Cin, passes);
+    const int npl = passes == 3 ? 2 : 1;
+    if (!make_plan(K, f.Wp, npl, shift_block_n(Cout), p) || -q_shift > f.lead) {
+        affgw_set_error("conv_shift: window of a %dx%d filter on a %d-wide frame does not fit", K, K, f.Wp);
         return -1;
     }
     ShArgs a;
     a.x = (const bf16*)x_planes;
-    a.x_plane = plane_stride;
     a.w = (const bf16*)w_packed;
     a.bias = bias;
     a.addend = (const float*)addend;
     a.y = (float*)y;
-    a.N = g.N; a.H = g.H; a.W = g.W; a.Cs = g.Cin;
-    a.up = g.up; a.pad = g.pad; a.pad_mode = g.pad_mode; a.K = g.KH;
-    a.Hv = g.Hv; a.Wv = g.Wv; a.Hp = g.Hv + 2 * g.pad; a.Wp = g.Wv + 2 * g.pad; a.Ho = g.Ho; a.Wo = g.Wo;
-    a.Cout = g.Cout; a.out_pitch = g.out_pitch; a.post_act = g.post_act;
-    a.CB = (g.Cin + 15) / 16;
+    a.N = f.N; a.Hp = f.Hp; a.Wp = f.Wp; a.K = K;
+    a.G = f.G; a.lead = f.lead; a.QA = f.QA;
+    a.q_shift = q_shift;
+    a.oy0 = oy0; a.ox0 = ox0; a.OH = OH; a.OW = OW;
+    a.Cout = Cout; a.out_pitch = out_pitch; a.post_act = post_act;
+    a.CB = f.G / 2;
     a.KYG = p.KYG; a.NP = p.NP; a.NPa = p.NPa; a.stages = p.stages;
     a.a_bytes = p.a_bytes; a.b_chunk_bytes = p.b_chunk_bytes;
-    a.n_tiles = (g.Cout + p.bn - 1) / p.bn;
-    a.Q = g.N * a.Hp * a.Wp;
-    const long long q_last = ((long long)(g.N - 1) * a.Hp + g.Ho - 1) * a.Wp + g.Wo - 1;
+    a.n_tiles = (Cout + p.bn - 1) / p.bn;
+    const long long q_last = ((long long)(f.N - 1) * f.Hp + oy0 + OH - 1) * f.Wp + ox0 + OW - 1;
     a.total_tiles = (int)((q_last / TILE_POS + 1) * a.n_tiles);
-    a.vec_ok = (g.Cout % 16 == 0) && (g.out_pitch % 4 == 0) && (((uintptr_t)y) % 16 == 0) &&
+    a.vec_ok = (Cout % 16 == 0) && (out_pitch % 4 == 0) && (((uintptr_t)y) % 16 == 0) &&
                (!addend || ((uintptr_t)addend) % 16 == 0);
     if (passes == 3) {
         switch (p.bn) {
@@ -462,48 +549,32 @@ int conv_fwd_shift(const void* x_planes, long long plane_stride, const void* w_p
 }
 
 // =====================================================================================================================
-// Weight gradient in the same position space:
+// Weight gradient:  dW[co][ky][kx][ci] = sum_q V[q + ky*Wp + kx][ci] * dYp[q][co]
 //
-//   dW[co][ky][kx][ci] = sum_q  V[q + ky*Wp + kx][ci] * dYp[q][co]         (dYp = dY scattered to padded positions)
-//
-// a GEMM whose reduction runs over positions.  Both operands sit in shared memory in the planar layout above, which is
-// UMMA's un-swizzled "MN-major" form (8 positions x 8 channels per core matrix; LBO = 128 B to the next 8 positions,
-// SBO = plane pitch to the next 8 channels).  One CTA owns a (128 input channels) x (BN output channels) x (kernel row ky)
-// block of dW: for every 16 positions it issues one MMA per kx whose A descriptor starts kx positions further into the
-// window - the input window is read once per kernel ROW instead of once per tap, dY once per row.  M is always 128
-// (absent channel groups stay zero in shared memory), so thin layers cost N/2 clocks per MMA, not a 128x128 tile.
-// The position range is split over grid.y; partials are reduced with coalesced fp32 atomics into ws[co][tap][ci].
+// A GEMM whose reduction runs over positions.  The planar layout is UMMA's un-swizzled "MN-major" form (8 positions x
+// 8 channels per core matrix; LBO = 128 B to the next 8 positions, SBO = plane pitch to the next 8 channels).  One CTA
+// owns a (128 input channels) x (BN output channels) x (kernel row ky) block of dW: for every 16 positions it issues one
+// MMA per kx whose A descriptor starts kx positions further into the window, so the input is read once per kernel ROW,
+// not once per tap.  M is always 128 (absent channel groups stay zero in shared memory), so thin layers cost N/2 clocks
+// per MMA.  The position range is split over grid.y; partials are reduced with coalesced fp32 atomics into
+// ws[co][tap][ci].
 // =====================================================================================================================
 namespace {
 
-constexpr int WG_THREADS = 160;              // 4 producer / epilogue warps + 1 MMA warp
+constexpr int WG_THREADS = 192;              // producer warp, MMA warp, 4 epilogue warps
 
 struct WsArgs {
-    const bf16* x; long long x_plane;        // planes [NPL][N*H*W][Cs]
-    const bf16* dy; long long dy_plane;      // planes [NPL][N*Ho*Wo][Cys]
-    float* ws;                               // [Cout][taps][Cs] fp32
-    int N, H, W, Cs;
-    int up, pad, pad_mode, K;
-    int Hv, Wv, Hp, Wp, Ho, Wo;
-    int Cout, Cys;
+    const bf16* x; const bf16* dy;           // position planes
+    float* ws;                               // [Cout][taps][cs] fp32
+    int K, Wp;
+    int Gx, Gy, lead;
+    long long QA;
+    int Cs, Cout;                            // row length of ws / real output channels
     int KP, pitchA16, pitchB16;              // positions per stage; plane pitches in 16-byte units
     int n_co_blocks;
     int chunks_total, chunks_per_split;
     int a_bytes, b_bytes, stages;
-    int Q;
 };
-
-__device__ __forceinline__ uint64_t make_mnmajor_nosw_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
-    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;     // to the next 8 positions (K)
-    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;     // to the next 8 channels (M / N)
-    d |= 1ull << 46;
-    return d;
-}
-__host__ __device__ constexpr uint32_t make_idesc_bf16_mnmn(int n) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-}
 
 template <int BN, int NPASS>
 __global__ void __launch_bounds__(WG_THREADS, 1)
@@ -530,20 +601,22 @@ conv_wgrad_shift_kernel(const __grid_constant__ WsArgs a) {
     const int cend = min(a.chunks_total, cbeg + a.chunks_per_split);
     const int nst = cend - cbeg;
     constexpr int TMEM_COLS = 512;
+    const int ga = min(16, a.Gx - cib * 16);                  // input groups this CTA really has
+    const int gb = min(GB, a.Gy - cob * GB);                  // output groups
 
     // absent channel groups must read as zeros for the whole kernel: clear every stage once
     for (uint32_t o = tid * 16u; o < (uint32_t)(stages * stage_bytes); o += WG_THREADS * 16u)
         asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(smem_base + o), "r"(0u) : "memory");
     fence_proxy_async();
-    if (tid == 128) {
+    if (tid == 32) {
         for (int s = 0; s < stages; ++s) {
-            mbar_init(full_bar(s), 128);
+            mbar_init(full_bar(s), 1);
             mbar_init(empty_bar(s), 1);
         }
         mbar_init(tmem_full_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 4) {
+    if (warp == MMA_WARP) {
         __syncwarp();
         tmem_alloc(tmem_ptr_addr, TMEM_COLS);
     }
@@ -554,159 +627,93 @@ conv_wgrad_shift_kernel(const __grid_constant__ WsArgs a) {
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr));
     const uint32_t pitchA = (uint32_t)a.pitchA16 * 16u, pitchB = (uint32_t)a.pitchB16 * 16u;
 
-    if (warp < 4) {
-        // ============================== producer ==============================
-        const int g = tid & 15, jj = tid >> 4;            // channel group, position slot (8 positions per pass)
-        const int ca = cib * 128 + g * 8;                 // input channel of this thread's group
-        const int cbn = cob * BN + g * 8;                 // output channel of this thread's group
-        const bool a_on = ca < a.Cs, b_on = g < GB && cbn < a.Cys;
-        const int wlen = a.KP + a.K - 1;
+    if (warp == 0) {
+        // ============================== producer: one bulk copy per (plane, channel group) ==============================
+        const uint32_t wbytes = (uint32_t)(a.KP + a.K - 1) * 16u, dbytes = (uint32_t)a.KP * 16u;
+        const uint32_t tx = (uint32_t)NPL * ((uint32_t)ga * wbytes + (uint32_t)gb * dbytes);
         for (int st = 0; st < nst; ++st) {
             const int s = st % stages;
             const uint32_t ph = (uint32_t)(st / stages) & 1u;
             mbar_wait(empty_bar(s), ph ^ 1u);
-            const int q0 = (cbeg + st) * a.KP;
-            if (a_on) {
-                const uint32_t dst0 = a_smem(s) + (uint32_t)g * pitchA;
-                // decode the first position with divisions, then walk: 8 positions further per iteration
-                const int qf = q0 + ky * a.Wp + jj;
-                int xp = qf % a.Wp;
-                const int r = qf / a.Wp;
-                int yp = r % a.Hp, n = r / a.Hp;
-                for (int j = jj; j < wlen; j += 8) {
-                    bool ok = n < a.N;
-                    const bf16* src = a.x;
-                    if (ok) {
-                        const int sy = map_coord(yp - a.pad, a.Hv, a.pad_mode, a.up, 1);
-                        const int sx = map_coord(xp - a.pad, a.Wv, a.pad_mode, a.up, 1);
-                        ok = sy >= 0 && sx >= 0;
-                        if (ok) src = a.x + ((size_t)((n * a.H + sy) * a.W + sx) * a.Cs + ca);
-                    }
-                    const uint32_t dst = dst0 + (uint32_t)j * 16u;
-                    cp_async_16(dst, src, ok ? 16u : 0u);
-                    if (NPL == 2) cp_async_16(dst + 16u * pitchA, ok ? src + a.x_plane : src, ok ? 16u : 0u);
-                    xp += 8;
-                    while (xp >= a.Wp) {
-                        xp -= a.Wp;
-                        if (++yp == a.Hp) { yp = 0; ++n; }
-                    }
-                }
+            if (lane == 0) mbar_arrive_expect_tx(full_bar(s), tx);
+            __syncwarp();
+            const long long q0 = (long long)(cbeg + st) * a.KP + a.lead;
+            for (int i = lane; i < NPL * ga; i += 32) {
+                const int pl = i / ga, g = i - pl * ga;
+                bulk_copy_g2s(a_smem(s) + (uint32_t)(pl * 16 + g) * pitchA,
+                              a.x + (((size_t)pl * a.Gx + cib * 16 + g) * a.QA + q0 + (long long)ky * a.Wp) * 8, wbytes,
+                              full_bar(s));
             }
-            if (b_on) {
-                const uint32_t dst0 = b_smem(s) + (uint32_t)g * pitchB;
-                const int qf = q0 + jj;
-                int xp = qf % a.Wp;
-                const int r = qf / a.Wp;
-                int yp = r % a.Hp, n = r / a.Hp;
-                for (int j = jj; j < a.KP; j += 8) {
-                    const bool ok = n < a.N && yp < a.Ho && xp < a.Wo;
-                    const bf16* src = ok ? a.dy + ((size_t)((n * a.Ho + yp) * a.Wo + xp) * a.Cys + cbn) : a.dy;
-                    const uint32_t dst = dst0 + (uint32_t)j * 16u;
-                    cp_async_16(dst, src, ok ? 16u : 0u);
-                    if (NPL == 2) cp_async_16(dst + (uint32_t)GB * pitchB, ok ? src + a.dy_plane : src, ok ? 16u : 0u);
-                    xp += 8;
-                    while (xp >= a.Wp) {
-                        xp -= a.Wp;
-                        if (++yp == a.Hp) { yp = 0; ++n; }
-                    }
-                }
-            }
-            cp_async_commit();
-            if (st >= 1) {
-                cp_async_wait<1>();
-                fence_proxy_async();
-                mbar_arrive(full_bar((st - 1) % stages));
+            for (int i = lane; i < NPL * gb; i += 32) {
+                const int pl = i / gb, g = i - pl * gb;
+                bulk_copy_g2s(b_smem(s) + (uint32_t)(pl * GB + g) * pitchB,
+                              a.dy + (((size_t)pl * a.Gy + cob * GB + g) * a.QA + q0) * 8, dbytes, full_bar(s));
             }
         }
-        cp_async_wait<0>();
-        fence_proxy_async();
-        if (nst >= 1) mbar_arrive(full_bar((nst - 1) % stages));
-
+    } else if (warp == MMA_WARP) {
+        // ============================== MMA issuer ==============================
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(BN, true);
+            for (int st = 0; st < nst; ++st) {
+                const int s = st % stages;
+                const uint32_t ph = (uint32_t)(st / stages) & 1u;
+                mbar_wait(full_bar(s), ph);
+                tc_fence_after();
+                // MN-major: LBO = to the next 8 positions (k), SBO = to the next 8 channels (m / n); descriptors differ only
+                // in their start address: add (byte offset >> 4) to the low word
+                const uint64_t a_base = make_nosw_desc(a_smem(s), 128u, pitchA);
+                const uint64_t b_base = make_nosw_desc(b_smem(s), 128u, pitchB);
+                const uint32_t a_lo_off = (16u * pitchA) >> 4, b_lo_off = ((uint32_t)GB * pitchB) >> 4;
+#pragma unroll 1
+                for (int k = 0; k < a.KP / 16; ++k) {
+                    const uint64_t b_hi = b_base + (uint64_t)(k * 16);
+                    const uint32_t accum = (uint32_t)((st | k) != 0);
+#pragma unroll 1
+                    for (int kx = 0; kx < a.K; ++kx) {
+                        const uint64_t a_hi = a_base + (uint64_t)(k * 16 + kx);
+                        umma_bf16(tmem_base + kx * BN, a_hi, b_hi, idesc, accum);
+                        if (NPASS == 3) {
+                            umma_bf16(tmem_base + kx * BN, a_hi + a_lo_off, b_hi, idesc, 1u);
+                            umma_bf16(tmem_base + kx * BN, a_hi, b_hi + b_lo_off, idesc, 1u);
+                        }
+                    }
+                }
+                umma_commit(empty_bar(s));
+            }
+            umma_commit(tmem_full_bar);
+        }
+    } else {
         // ============================== epilogue: fp32 reductions into ws[co][tap][ci] ==============================
+        const int wq = warp & 3;
         mbar_wait(tmem_full_bar, 0);
         tc_fence_after();
-        const int ci = cib * 128 + warp * 32 + lane;
+        const int ci = cib * 128 + wq * 32 + lane;
         const bool rok = ci < a.Cs;
         const int taps = a.K * a.K;
-        for (int kx = 0; kx < a.K; ++kx) {
-            float* wbase = a.ws + (size_t)(ky * a.K + kx) * a.Cs + ci;
+        if (nst > 0) {
+            for (int kx = 0; kx < a.K; ++kx) {
+                float* wbase = a.ws + (size_t)(ky * a.K + kx) * a.Cs + ci;
 #pragma unroll 1
-            for (int jb = 0; jb < BN / 16; ++jb) {
-                const int nb = cob * BN + jb * 16;
-                if (nb >= a.Cout) break;
-                uint32_t raw[16];
-                tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(kx * BN + jb * 16), raw);
-                if (rok) {
+                for (int jb = 0; jb < BN / 16; ++jb) {
+                    const int nb = cob * BN + jb * 16;
+                    if (nb >= a.Cout) break;
+                    uint32_t raw[16];
+                    tmem_ld16(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(kx * BN + jb * 16), raw);
+                    if (rok) {
 #pragma unroll
-                    for (int i = 0; i < 16; ++i)
-                        if (nb + i < a.Cout) atomicAdd(wbase + (size_t)(nb + i) * taps * a.Cs, __uint_as_float(raw[i]));
+                        for (int i = 0; i < 16; ++i)
+                            if (nb + i < a.Cout) atomicAdd(wbase + (size_t)(nb + i) * taps * a.Cs, __uint_as_float(raw[i]));
+                    }
                 }
             }
         }
         tc_fence_before();
-    } else if (lane == 0) {
-        // ============================== MMA issuer ==============================
-        constexpr uint32_t idesc = make_idesc_bf16_mnmn(BN);
-        for (int st = 0; st < nst; ++st) {
-            const int s = st % stages;
-            const uint32_t ph = (uint32_t)(st / stages) & 1u;
-            mbar_wait(full_bar(s), ph);
-            tc_fence_after();
-            const uint32_t ab = a_smem(s), bb = b_smem(s);
-            for (int k = 0; k < a.KP / 16; ++k) {
-                const uint64_t b_hi = make_mnmajor_nosw_desc(bb + k * 256u, 128u, pitchB);
-                const uint64_t b_lo = make_mnmajor_nosw_desc(bb + (uint32_t)GB * pitchB + k * 256u, 128u, pitchB);
-                for (int kx = 0; kx < a.K; ++kx) {
-                    const uint32_t astart = ab + (uint32_t)(k * 16 + kx) * 16u;
-                    const uint64_t a_hi = make_mnmajor_nosw_desc(astart, 128u, pitchA);
-                    const uint32_t accum = (uint32_t)((st | k) != 0);
-                    umma_bf16(tmem_base + kx * BN, a_hi, b_hi, idesc, accum);
-                    if (NPASS == 3) {
-                        const uint64_t a_lo = make_mnmajor_nosw_desc(astart + 16u * pitchA, 128u, pitchA);
-                        umma_bf16(tmem_base + kx * BN, a_lo, b_hi, idesc, 1u);
-                        umma_bf16(tmem_base + kx * BN, a_hi, b_lo, idesc, 1u);
-                    }
-                }
-            }
-            umma_commit(empty_bar(s));
-        }
-        umma_commit(tmem_full_bar);
     }
     __syncthreads();
-    if (warp == 4) {
+    if (warp == MMA_WARP) {
         tc_fence_after();
         tmem_dealloc(tmem_base, TMEM_COLS);
     }
-}
-
-struct WsPlan {
-    int bn, KP, pitchA16, pitchB16, a_bytes, b_bytes, stages, smem_bytes;
-};
-
-int make_wg_plan(const ConvGeom& g, int passes, WsPlan& p) {
-    if (g.stride != 1 || g.zi != 1 || g.KH != g.KW || g.KH > 7) return 0;
-    if (g.Cin % 8 != 0 || g.in_pitch != g.Cin || g.out_pitch % 8 != 0 || g.out_pitch < g.Cout) return 0;
-    if (g.pre_act != ACT_NONE) return 0;
-    if (g.Cin < 128 || g.KH == 1) return 0;                     // measured: thin layers and 1x1 filters are faster on the im2col wgrad
-    const int npl = passes == 3 ? 2 : 1;
-    const long long Hp = g.Hv + 2 * g.pad, Wp = g.Wv + 2 * g.pad;
-    if (Hp - g.KH + 1 != g.Ho || Wp - g.KW + 1 != g.Wo) return 0;
-    if (2 * Hp * Wp > 3LL * g.Ho * g.Wo) return 0;              // tiny maps: padding positions dominate, im2col kernel
-    if ((long long)g.N * Hp * Wp + 4096 >= (1LL << 31) / 16) return 0;
-    if ((long long)g.N * g.H * g.W * g.Cin >= (1LL << 31) || g.M * g.out_pitch >= (1LL << 31)) return 0;
-    const int limit = g.KH <= 4 ? 128 : 64;                     // K * BN TMEM columns <= 512
-    p.bn = g.Cout <= 16 ? 16 : g.Cout <= 32 ? 32 : g.Cout <= 64 ? 64 : limit;
-    p.KP = (g.Cin <= 32 && p.bn <= 32) ? 128 : 64;
-    p.pitchA16 = p.KP + 9;
-    p.pitchB16 = p.KP + 1;
-    p.a_bytes = npl * 16 * p.pitchA16 * 16;
-    p.b_bytes = npl * (p.bn / 8) * p.pitchB16 * 16;
-    const int stage = p.a_bytes + p.b_bytes;
-    const int st = (SMEM_LIMIT - 128 - 256) / stage;
-    if (st < 2) return 0;
-    p.stages = st > MAX_STAGES ? MAX_STAGES : st;
-    p.smem_bytes = p.stages * stage + 128 + 256;
-    return 1;
 }
 
 template <int BN, int NPASS>
@@ -727,35 +734,35 @@ int launch_wg_shift(const WsArgs& args, dim3 grid, int smem_bytes, cudaStream_t 
 
 }  // namespace
 
-int conv_wgrad_shift_ok(const ConvGeom& g, int passes) {
-    WsPlan p;
-    return make_wg_plan(g, passes, p);
-}
-
-// ws: [Cout][taps][g.Cin] fp32, zeroed by the caller; g.Cin / g.out_pitch are the stored channel counts of the planes
-int conv_wgrad_shift(const void* x_planes, long long x_plane, const void* dy_planes, long long dy_plane, float* ws,
-                     const ConvGeom& g, int passes, cudaStream_t st) {
-    WsPlan p;
-    if (!make_wg_plan(g, passes, p)) {
-        affgw_set_error("conv_wgrad_shift: unsupported convolution");
+// x planes: frame fx; dY planes: same frame positions, fy.G groups.
+// ws: [Cout][K*K][cs] fp32, zeroed by the caller (cs = row length, >= the real input channels).
+int conv_wgrad_pos_tc(const void* x_planes, const PosFrame& fx, const void* dy_planes, const PosFrame& fy, float* ws, int K,
+                      int Cout, int cs, int Ho, int Wo, int passes, cudaStream_t st) {
+    const int npl = passes == 3 ? 2 : 1;
+    const int limit = K <= 4 ? 128 : 64;                        // K * BN TMEM columns <= 512
+    const int bn = Cout <= 16 ? 16 : Cout <= 32 ? 32 : Cout <= 64 ? 64 : limit;
+    WsArgs a;
+    a.KP = 64;
+    a.pitchA16 = a.KP + 9;
+    a.pitchB16 = a.KP + 1;
+    a.a_bytes = npl * 16 * a.pitchA16 * 16;
+    a.b_bytes = npl * (bn / 8) * a.pitchB16 * 16;
+    const int stage = a.a_bytes + a.b_bytes;
+    const int stg = (SMEM_LIMIT - 128 - 256) / stage;
+    if (stg < 2 || K > 7 || fx.QA != fy.QA || fx.lead != fy.lead || fx.Wp != fy.Wp) {
+        affgw_set_error("conv_wgrad_shift: unsupported configuration");
         return -1;
     }
-    WsArgs a;
-    a.x = (const bf16*)x_planes; a.x_plane = x_plane;
-    a.dy = (const bf16*)dy_planes; a.dy_plane = dy_plane;
-    a.ws = ws;
-    a.N = g.N; a.H = g.H; a.W = g.W; a.Cs = g.Cin;
-    a.up = g.up; a.pad = g.pad; a.pad_mode = g.pad_mode; a.K = g.KH;
-    a.Hv = g.Hv; a.Wv = g.Wv; a.Hp = g.Hv + 2 * g.pad; a.Wp = g.Wv + 2 * g.pad; a.Ho = g.Ho; a.Wo = g.Wo;
-    a.Cout = g.Cout; a.Cys = g.out_pitch;
-    a.KP = p.KP; a.pitchA16 = p.pitchA16; a.pitchB16 = p.pitchB16;
-    a.a_bytes = p.a_bytes; a.b_bytes = p.b_bytes; a.stages = p.stages;
-    a.Q = g.N * a.Hp * a.Wp;
-    const int n_ci = (g.Cin + 127) / 128;
-    a.n_co_blocks = (g.Cout + p.bn - 1) / p.bn;
-    const long long q_last = ((long long)(g.N - 1) * a.Hp + g.Ho - 1) * a.Wp + g.Wo - 1;
-    a.chunks_total = (int)(q_last / p.KP + 1);
-    const int tiles = n_ci * a.n_co_blocks * g.KH;
+    a.stages = stg > MAX_STAGES ? MAX_STAGES : stg;
+    const int smem_bytes = a.stages * stage + 128 + 256;
+    a.x = (const bf16*)x_planes; a.dy = (const bf16*)dy_planes; a.ws = ws;
+    a.K = K; a.Wp = fx.Wp; a.Gx = fx.G; a.Gy = fy.G; a.lead = fx.lead; a.QA = fx.QA;
+    a.Cs = cs; a.Cout = Cout;
+    const int n_ci = (fx.G + 15) / 16;
+    a.n_co_blocks = (Cout + bn - 1) / bn;
+    const long long q_last = ((long long)(fx.N - 1) * fx.Hp + Ho - 1) * fx.Wp + Wo - 1;
+    a.chunks_total = (int)(q_last / a.KP + 1);
+    const int tiles = n_ci * a.n_co_blocks * K;
     // split the position range so that the CTAs fill whole waves of 148 SMs (each split keeps >= 8 stages of work)
     int max_splits = (a.chunks_total + 7) / 8;
     if (max_splits > 320 / tiles + 1) max_splits = 320 / tiles + 1;
@@ -770,17 +777,17 @@ int conv_wgrad_shift(const void* x_planes, long long x_plane, const void* dy_pla
     splits = (a.chunks_total + a.chunks_per_split - 1) / a.chunks_per_split;
     dim3 grid((unsigned)tiles, (unsigned)splits);
     if (passes == 3) {
-        switch (p.bn) {
-            case 16: return launch_wg_shift<16, 3>(a, grid, p.smem_bytes, st);
-            case 32: return launch_wg_shift<32, 3>(a, grid, p.smem_bytes, st);
-            case 64: return launch_wg_shift<64, 3>(a, grid, p.smem_bytes, st);
-            default: return launch_wg_shift<128, 3>(a, grid, p.smem_bytes, st);
+        switch (bn) {
+            case 16: return launch_wg_shift<16, 3>(a, grid, smem_bytes, st);
+            case 32: return launch_wg_shift<32, 3>(a, grid, smem_bytes, st);
+            case 64: return launch_wg_shift<64, 3>(a, grid, smem_bytes, st);
+            default: return launch_wg_shift<128, 3>(a, grid, smem_bytes, st);
         }
     }
-    switch (p.bn) {
-        case 16: return launch_wg_shift<16, 1>(a, grid, p.smem_bytes, st);
-        case 32: return launch_wg_shift<32, 1>(a, grid, p.smem_bytes, st);
-        case 64: return launch_wg_shift<64, 1>(a, grid, p.smem_bytes, st);
-        default: return launch_wg_shift<128, 1>(a, grid, p.smem_bytes, st);
+    switch (bn) {
+        case 16: return launch_wg_shift<16, 1>(a, grid, smem_bytes, st);
+        case 32: return launch_wg_shift<32, 1>(a, grid, smem_bytes, st);
+        case 64: return launch_wg_shift<64, 1>(a, grid, smem_bytes, st);
+        default: return launch_wg_shift<128, 1>(a, grid, smem_bytes, st);
     }
 }

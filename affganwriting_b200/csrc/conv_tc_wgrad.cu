@@ -16,6 +16,7 @@
 // Replaces the weight-gradient half of cuDNN's convolution backward behind the reference's loss.backward()
 // (network_tro.py:55,102,113,129).
 #include "common.cuh"
+#include "pos_frame.cuh"
 #include "tc_ptx.cuh"
 
 namespace {
@@ -307,12 +308,6 @@ int launch_wg_p(WgArgs& a, int passes, cudaStream_t st) {
 }  // namespace
 
 int conv_tc_block_n(int cout);
-// conv_shift.cu
-int conv_wgrad_shift_ok(const ConvGeom& g, int passes);
-int conv_wgrad_shift(const void* x_planes, long long x_plane, const void* dy_planes, long long dy_plane, float* ws,
-                     const ConvGeom& g, int passes, cudaStream_t st);
-extern int g_wgrad_prefer_shift;
-int g_wgrad_prefer_shift = 1;
 
 // g.Cin must be the STORED channel count of the x planes, g.out_pitch that of the dY planes (multiples of 8)
 int conv_wgrad_tc_ok(const ConvGeom& g) {
@@ -341,9 +336,6 @@ int conv_wgrad_tc(const void* x_planes, long long x_plane, const void* dy_planes
     a.dy = (const bf16*)dy_planes; a.dy_plane = dy_plane;
     a.ws = ws; a.g = g; a.m_per_split = 0;
     int rc;
-    if (g_wgrad_prefer_shift && conv_wgrad_shift_ok(g, passes)) {
-        rc = conv_wgrad_shift(x_planes, x_plane, dy_planes, dy_plane, ws, g, passes, st);
-    } else
     switch (bn) {
         case 16: rc = launch_wg_p<16>(a, passes, st); break;
         case 32: rc = launch_wg_p<32>(a, passes, st); break;
@@ -351,6 +343,28 @@ int conv_wgrad_tc(const void* x_planes, long long x_plane, const void* dy_planes
         default: rc = launch_wg_p<128>(a, passes, st); break;
     }
     if (rc) return rc;
+    const int taps = g.KH * g.KW;
+    const long long total = (long long)g.Cout * cin_w * taps;
+    const int blocks = (int)min((long long)148 * 8, (total + 255) / 256);
+    wgrad_unpack_kernel<<<blocks, 256, 0, st>>>(ws, dw, g.Cout, cin_w, g.Cin, taps);
+    AFFGW_LAUNCH_CHECK("wgrad_unpack");
+    return 0;
+}
+
+// conv_shift.cu
+int conv_wgrad_pos_tc(const void* x_planes, const PosFrame& fx, const void* dy_planes, const PosFrame& fy, float* ws, int K,
+                      int Cout, int cs, int Ho, int Wo, int passes, cudaStream_t st);
+
+// position-space weight gradient (conv_shift.cu) + the same workspace reduction / unpack as above;
+// g.Cin = stored channel count of the ws rows, cin_w = channels of the parameter
+int conv_wgrad_pos(const void* x_planes, const PosFrame& fx, const void* dy_planes, const PosFrame& fy, float* dw, void* workspace,
+                   const ConvGeom& g, int cin_w, int passes, cudaStream_t st) {
+    float* ws = (float*)workspace;
+    if (cudaMemsetAsync(ws, 0, (size_t)conv_wgrad_tc_ws_bytes(g), st) != cudaSuccess) {
+        affgw_set_error("conv_wgrad_pos: memset failed");
+        return -2;
+    }
+    if (int rc = conv_wgrad_pos_tc(x_planes, fx, dy_planes, fy, ws, g.KH, g.Cout, g.Cin, g.Ho, g.Wo, passes, st)) return rc;
     const int taps = g.KH * g.KW;
     const long long total = (long long)g.Cout * cin_w * taps;
     const int blocks = (int)min((long long)148 * 8, (total + 255) / 256);

@@ -285,6 +285,23 @@ def _split_planes(x, rows, c, pitch, passes, pre_act="none"):
     return planes
 
 
+def _pos_frames(d):
+    fx, fy = L.PosFrame(), L.PosFrame()
+    L.call("affgw_conv_pos_frames", C.byref(d), C.byref(fx), C.byref(fy))
+    return fx, fy
+
+
+def _split_positions(src, frame, hs, ws, c, pitch, up, origin, pad_mode, pre_act, passes):
+    """fp32 NHWC tensor -> planar position planes [1 or 2][G][QA][8] bf16 on the frame of a stride-1 convolution."""
+    nbytes = L.lib().affgw_position_planes_bytes(C.byref(frame), passes)
+    if nbytes <= 0:
+        raise RuntimeError("affgw_position_planes_bytes: bad frame")
+    planes = torch.empty(nbytes // 2, dtype=torch.bfloat16, device=src.device)
+    L.call("affgw_split_positions", src.data_ptr(), L.dt(src), planes.data_ptr(), C.byref(frame), hs, ws, c, pitch, up, origin,
+           origin, L.PAD[pad_mode], L.ACT[pre_act], passes, L.stream())
+    return planes
+
+
 def _conv_geom(x, weight, cfg):
     """-> dict(N,H,W,Cx,pitch,Cout,Cin,KH,KW,Ho,Wo, two_d)"""
     w4 = _w4(weight)
@@ -347,7 +364,12 @@ class _Conv2d(Function):
             layout = L.lib().affgw_conv_tc_layout(C.byref(d), 0)
             if not layout:
                 raise RuntimeError("conv2d: tcgen05 kernels refused the shape: " + L.last_error())
-            planes = _split_planes(x, g["N"] * g["H"] * g["W"], g["Cin"], g["pitch"], passes, cfg.pre_act)
+            if layout == L.WLAYOUT_SHIFT:
+                fx, _ = _pos_frames(d)
+                planes = _split_positions(x, fx, g["H"], g["W"], g["Cin"], g["pitch"], cfg.upsample, cfg.pad, cfg.pad_mode,
+                                          cfg.pre_act, passes)
+            else:
+                planes = _split_planes(x, g["N"] * g["H"] * g["W"], g["Cin"], g["pitch"], passes, cfg.pre_act)
             wp = _pack_tc(weight, cs, False, passes, layout)
             with _timed("conv_fwd_tcgen05", flops, tag):
                 L.call("affgw_conv2d_fwd", planes.data_ptr(), wp.data_ptr(), L.ptr(b32), L.ptr(addend), y.data_ptr(),
@@ -359,6 +381,7 @@ class _Conv2d(Function):
                 L.call("affgw_conv2d_fwd", x.data_ptr(), wp.data_ptr(), L.ptr(b32), L.ptr(addend), y.data_ptr(), C.byref(d),
                        L.stream())
         ctx.cfg, ctx.g, ctx.use_tc, ctx.passes, ctx.tag = cfg, g, use_tc, passes, tag
+        ctx.layout = layout if use_tc else 0
         ctx.has_bias, ctx.has_addend = bias is not None, addend is not None
         keep_x = (not use_tc) or cfg.pre_act != "none" or _state["simt_wgrad"]
         ctx.save_for_backward(x if keep_x else None, weight, y if cfg.post_act != "none" else None, planes)
@@ -389,7 +412,13 @@ class _Conv2d(Function):
         use_tc = ctx.use_tc
         if use_tc and (need_w or need_x):
             cs, cso = _up8(cin), _up8(cout)
-            dzp = _split_planes(dz, M, cout, cout, passes)
+            if ctx.layout == L.WLAYOUT_SHIFT:
+                # dY on the forward convolution's position frame: one split feeds both dgrad and wgrad
+                d0 = _desc(g, fwd_cfg, cin, L.BF16, L.BF16, L.BF16, L.ALGO_TC, in_pitch=cs, out_pitch=cso, passes=passes)
+                _, fy = _pos_frames(d0)
+                dzp = _split_positions(dz, fy, g["Ho"], g["Wo"], cout, cout, 1, 0, "zero", "none", passes)
+            else:
+                dzp = _split_planes(dz, M, cout, cout, passes)
         if need_w:
             dw = torch.zeros(weight.shape, dtype=torch.float32, device=dev)
             if use_tc and not _state["simt_wgrad"]:

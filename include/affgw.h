@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define AFFGW_VERSION 102
+#define AFFGW_VERSION 103
 
 enum { AFFGW_DT_F32 = 0, AFFGW_DT_BF16 = 1 };
 enum { AFFGW_ACT_NONE = 0, AFFGW_ACT_RELU = 1, AFFGW_ACT_LRELU = 2, AFFGW_ACT_TANH = 3 };
@@ -74,6 +74,22 @@ long long affgw_pack_weight_tc_bytes(int Cout, int Cin, int KH, int KW, int i_pa
 /* AFFGW_WLAYOUT_* the forward (for_dgrad = 0) or input-gradient (1) convolution described by d runs on; 0 = not
  * supported.  Stride-1 convolutions take the shared-memory-window ("shifted") kernel, the rest the im2col kernel. */
 int affgw_conv_tc_layout(const affgw_conv_desc* d, int for_dgrad);
+/* Position space of a stride-1 convolution (AFFGW_WLAYOUT_SHIFT): the frame [N][Hp][Wp] of its padded / upsampled input,
+ * q = (n*Hp + yp)*Wp + xp.  Operand planes on it are planar: [hi|lo plane][G channel groups][QA positions][8] bf16, with
+ * `lead` zero positions in front of q = 0.  affgw_conv_pos_frames gives the frame of the x planes (fx) and of the dY
+ * planes (fy: same positions, output channels); affgw_split_positions builds either:
+ *   x planes : src = x [N][H][W][pitch], (Hs, Ws) = (H, W), upsample, (oy0, ox0) = (pad, pad), the conv's pad_mode and
+ *              pre-activation (activation_first blocks, blocks.py:151-153)
+ *   dY planes: src = dY [N][Ho][Wo][Cout], upsample 1, (oy0, ox0) = (0, 0), AFFGW_PAD_ZERO, no activation
+ * and affgw_conv2d_fwd / _dgrad / _wgrad take those planes as their x / dy arguments when affgw_conv_tc_layout says SHIFT. */
+typedef struct affgw_pos_frame {
+    int32_t N, Hp, Wp, G, lead, reserved;
+    int64_t QA;
+} affgw_pos_frame;
+int affgw_conv_pos_frames(const affgw_conv_desc* d, affgw_pos_frame* fx, affgw_pos_frame* fy);
+long long affgw_position_planes_bytes(const affgw_pos_frame* f, int passes);
+int affgw_split_positions(const void* src, int dtype, void* planes, const affgw_pos_frame* f, int Hs, int Ws, int C, int pitch,
+                          int upsample, int oy0, int ox0, int pad_mode, int pre_act, int passes, void* stream);
 /* enable (1) / disable (0) the shifted kernel, -1 = query only; returns the previous setting (A/B testing) */
 int affgw_conv_tc_prefer_shift(int enable);
 /* activation tensor [rows][pitch] (fp32 or bf16) -> operand planes [passes == 3 ? 2 : 1][rows][c_store] (bf16), with the
