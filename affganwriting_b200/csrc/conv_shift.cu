@@ -36,8 +36,12 @@ using namespace tcptx;
 
 constexpr int MMA_WARP = 1;
 constexpr int NUM_THREADS = 32 * 6;          // producer warp, MMA warp, 4 epilogue warps
-constexpr int MT = 4;                        // M-tiles (of 128 positions) per CTA tile
-constexpr int TILE_POS = MT * 128;
+constexpr int MAX_TILE_POS = 512;            // largest CTA tile in positions (frames keep that much tail)
+// CTA tile = MT M-tiles of 128 positions x BN output channels; NBUF TMEM accumulator buffers of MT*BN columns.
+// Wide N amortises the 4 KB A read of a 128-row MMA over more tensor clocks (the shared-memory pipe delivers 128 B/clk):
+// BN = 256 needs 12 KB per 128 clocks, BN = 64 needs 6 KB per 32.
+__host__ __device__ constexpr int tile_mt(int bn) { return bn <= 64 ? 4 : 2; }
+__host__ __device__ constexpr int tile_nbuf(int bn) { return bn <= 128 ? 2 : 1; }
 constexpr int MAX_STAGES = 4;
 constexpr int SMEM_LIMIT = 227 * 1024;
 
@@ -79,12 +83,13 @@ __host__ __device__ constexpr uint32_t make_idesc(int n, bool mn_major) {
 }
 
 // ---------------------------------------------------------------------------------------- forward / input gradient
-// CTA tile: 4 M-tiles x 128 positions against BN <= 64 output channels; a stage = the window of one 16-channel block
-// (all kernel rows, or one kernel row when the whole-filter window does not fit twice in shared memory) + its weights.
+// A stage = the window of one 16-channel block (all kernel rows, or one kernel row when the whole-filter window does not
+// fit twice in shared memory) + its weights.
 template <int BN, int NPASS>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_shift_tcgen05_kernel(const __grid_constant__ ShArgs a) {
     constexpr int NPL = NPASS == 3 ? 2 : 1;
+    constexpr int MT = tile_mt(BN), NBUF = tile_nbuf(BN), TILE_POS = MT * 128;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 127u) & ~127u;
     const int stages = a.stages;
@@ -116,7 +121,7 @@ conv_shift_tcgen05_kernel(const __grid_constant__ ShArgs a) {
     }
     if (warp == MMA_WARP) {
         __syncwarp();
-        tmem_alloc(tmem_ptr_addr, 2 * MT * BN);
+        tmem_alloc(tmem_ptr_addr, NBUF * MT * BN);
     }
     tc_fence_before();
     __syncthreads();
@@ -162,7 +167,7 @@ conv_shift_tcgen05_kernel(const __grid_constant__ ShArgs a) {
             const uint32_t b_plane = 2u * BN * 16u;               // bytes of one [cgroup][BN][8] weight image
             uint32_t it = 0, tl = 0;
             for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x, ++tl) {
-                const uint32_t acc = tl & 1u, acc_ph = (tl >> 1) & 1u;
+                const uint32_t acc = tl % NBUF, acc_ph = (tl / NBUF) & 1u;
                 mbar_wait(tmem_empty_bar(acc), acc_ph ^ 1u);
                 tc_fence_after();
                 const uint32_t d0 = tmem_base + acc * (MT * BN);
@@ -204,7 +209,7 @@ conv_shift_tcgen05_kernel(const __grid_constant__ ShArgs a) {
         const int wq = warp & 3;          // TMEM lane quarter this warp may read
         uint32_t tl = 0;
         for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x, ++tl) {
-            const uint32_t acc = tl & 1u, acc_ph = (tl >> 1) & 1u;
+            const uint32_t acc = tl % NBUF, acc_ph = (tl / NBUF) & 1u;
             const int n0 = (t % a.n_tiles) * BN;
             const int q0 = (t / a.n_tiles) * TILE_POS;
             mbar_wait(tmem_full_bar(acc), acc_ph);
@@ -268,7 +273,7 @@ conv_shift_tcgen05_kernel(const __grid_constant__ ShArgs a) {
     __syncthreads();
     if (warp == MMA_WARP) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, 2 * MT * BN);
+        tmem_dealloc(tmem_base, NBUF * MT * BN);
     }
 }
 
@@ -378,7 +383,7 @@ struct ShPlan {
     int bn, KYG, NP, NPa, stages, a_bytes, b_chunk_bytes, smem_bytes;
 };
 
-int shift_block_n(int cout) { return cout > 32 ? 64 : cout > 16 ? 32 : 16; }
+int shift_block_n(int cout) { return cout > 128 ? 256 : cout > 64 ? 128 : cout > 32 ? 64 : cout > 16 ? 32 : 16; }
 
 // pipeline-stage geometry; K x K filter on a frame of pitch Wp, npl planes, BN-wide weight stage
 int make_plan(int K, int Wp, int npl, int bn, ShPlan& p) {
@@ -386,7 +391,7 @@ int make_plan(int K, int Wp, int npl, int bn, ShPlan& p) {
     for (int mode = 0; mode < 2; ++mode) {
         p.KYG = mode == 0 ? K : 1;
         if (mode == 1 && K == 1) break;
-        p.NP = TILE_POS + (p.KYG - 1) * Wp + K - 1;
+        p.NP = tile_mt(bn) * 128 + (p.KYG - 1) * Wp + K - 1;
         p.NPa = (p.NP + 7) / 8 * 8;
         p.a_bytes = npl * 2 * p.NPa * 16;
         p.b_chunk_bytes = K * npl * 2 * p.bn * 16;
@@ -430,7 +435,8 @@ int conv_shift_ok(const ConvGeom& g) {
     if (2 * Hp * Wp > 3LL * g.Ho * g.Wo) return 0;
     if ((long long)g.N * Hp * Wp + 8192 >= (1LL << 31) / 16) return 0;           // 32-bit position arithmetic
     ShPlan p;
-    if (!make_plan(g.KH, (int)Wp, 2, 64, p)) return 0;
+    for (int bn = 16; bn <= 256; bn *= 2)
+        if (!make_plan(g.KH, (int)Wp, 2, bn, p)) return 0;
     return 1;
 }
 
@@ -443,7 +449,7 @@ void conv_shift_frame(const ConvGeom& g, int channels, PosFrame& f) {
     const int span = (g.KH - 1) * (f.Wp + 1);
     f.lead = (span + 7) / 8 * 8;
     const long long Q = (long long)f.N * f.Hp * f.Wp;
-    f.QA = f.lead + (Q + TILE_POS - 1) / TILE_POS * TILE_POS + TILE_POS + span + g.KH + 32;
+    f.QA = f.lead + (Q + MAX_TILE_POS - 1) / MAX_TILE_POS * MAX_TILE_POS + MAX_TILE_POS + span + g.KH + 32;
     f.QA = (f.QA + 31) / 32 * 32;
 }
 
@@ -531,20 +537,24 @@ int conv_pos_tc(const void* x_planes, const PosFrame& f, const void* w_packed, c
     a.a_bytes = p.a_bytes; a.b_chunk_bytes = p.b_chunk_bytes;
     a.n_tiles = (Cout + p.bn - 1) / p.bn;
     const long long q_last = ((long long)(f.N - 1) * f.Hp + oy0 + OH - 1) * f.Wp + ox0 + OW - 1;
-    a.total_tiles = (int)((q_last / TILE_POS + 1) * a.n_tiles);
+    a.total_tiles = (int)((q_last / (tile_mt(p.bn) * 128) + 1) * a.n_tiles);
     a.vec_ok = (Cout % 16 == 0) && (out_pitch % 4 == 0) && (((uintptr_t)y) % 16 == 0) &&
                (!addend || ((uintptr_t)addend) % 16 == 0);
     if (passes == 3) {
         switch (p.bn) {
             case 16: return launch_shift<16, 3>(a, p.smem_bytes, st);
             case 32: return launch_shift<32, 3>(a, p.smem_bytes, st);
-            default: return launch_shift<64, 3>(a, p.smem_bytes, st);
+            case 64: return launch_shift<64, 3>(a, p.smem_bytes, st);
+            case 128: return launch_shift<128, 3>(a, p.smem_bytes, st);
+            default: return launch_shift<256, 3>(a, p.smem_bytes, st);
         }
     }
     switch (p.bn) {
         case 16: return launch_shift<16, 1>(a, p.smem_bytes, st);
         case 32: return launch_shift<32, 1>(a, p.smem_bytes, st);
-        default: return launch_shift<64, 1>(a, p.smem_bytes, st);
+        case 64: return launch_shift<64, 1>(a, p.smem_bytes, st);
+        case 128: return launch_shift<128, 1>(a, p.smem_bytes, st);
+        default: return launch_shift<256, 1>(a, p.smem_bytes, st);
     }
 }
 
