@@ -26,6 +26,8 @@
 //
 // Replaces the cuDNN convolutions (forward and backward) behind reference blocks.py:148 /
 // vgg_tro_channel3_modi.py:47 / modules_tro.py:594-603 and loss.backward() (network_tro.py:55,102,113,129).
+#include <cuda.h>
+
 #include "common.cuh"
 #include "pos_frame.cuh"
 #include "tc_ptx.cuh"
@@ -434,9 +436,10 @@ int conv_shift_ok(const ConvGeom& g) {
     // reuse to exploit: both stay on the im2col kernels
     if (2 * Hp * Wp > 3LL * g.Ho * g.Wo) return 0;
     if ((long long)g.N * Hp * Wp + 8192 >= (1LL << 31) / 16) return 0;           // 32-bit position arithmetic
+    // the forward tile is as wide as Cout allows, the dgrad tile as wide as Cin allows: both windows must fit
     ShPlan p;
-    for (int bn = 16; bn <= 256; bn *= 2)
-        if (!make_plan(g.KH, (int)Wp, 2, bn, p)) return 0;
+    if (!make_plan(g.KH, (int)Wp, 2, shift_block_n(g.Cout), p)) return 0;
+    if (!make_plan(g.KH, (int)Wp, 2, shift_block_n(g.Cin), p)) return 0;
     return 1;
 }
 
@@ -580,7 +583,9 @@ struct WsArgs {
     int Gx, Gy, lead;
     long long QA;
     int Cs, Cout;                            // row length of ws / real output channels
-    int KP, pitchA16, pitchB16;              // positions per stage; plane pitches in 16-byte units
+    int KP, pitchA16, pitchB16;              // positions per stage; shared-memory plane pitches in 16-byte units
+    int rowsA, rowsB;                        // channel groups per TMA box (<= 16, <= BN / 8)
+    int KXG, n_kxg;                          // filter columns per CTA (KXG * BN <= 512 TMEM columns), column groups per row
     int n_co_blocks;
     int chunks_total, chunks_per_split;
     int a_bytes, b_bytes, stages;
@@ -588,7 +593,8 @@ struct WsArgs {
 
 template <int BN, int NPASS>
 __global__ void __launch_bounds__(WG_THREADS, 1)
-conv_wgrad_shift_kernel(const __grid_constant__ WsArgs a) {
+conv_wgrad_shift_kernel(const __grid_constant__ WsArgs a, const __grid_constant__ CUtensorMap tmx,
+                        const __grid_constant__ CUtensorMap tmdy) {
     constexpr int NPL = NPASS == 3 ? 2 : 1;
     constexpr int GB = BN / 8;
     extern __shared__ uint8_t smem_raw[];
@@ -604,16 +610,16 @@ conv_wgrad_shift_kernel(const __grid_constant__ WsArgs a) {
     auto b_smem = [&](int s) { return smem_base + s * stage_bytes + a.a_bytes; };
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int ky = blockIdx.x % a.K;
-    const int cob = (blockIdx.x / a.K) % a.n_co_blocks;
-    const int cib = blockIdx.x / (a.K * a.n_co_blocks);
+    const int kxg = blockIdx.x % a.n_kxg;
+    const int ky = (blockIdx.x / a.n_kxg) % a.K;
+    const int cob = (blockIdx.x / (a.n_kxg * a.K)) % a.n_co_blocks;
+    const int cib = blockIdx.x / (a.n_kxg * a.K * a.n_co_blocks);
+    const int kx0 = kxg * a.KXG;
+    const int nkx = min(a.KXG, a.K - kx0);
     const int cbeg = blockIdx.y * a.chunks_per_split;
     const int cend = min(a.chunks_total, cbeg + a.chunks_per_split);
     const int nst = cend - cbeg;
     constexpr int TMEM_COLS = 512;
-    const int ga = min(16, a.Gx - cib * 16);                  // input groups this CTA really has
-    const int gb = min(GB, a.Gy - cob * GB);                  // output groups
-
     // absent channel groups must read as zeros for the whole kernel: clear every stage once
     for (uint32_t o = tid * 16u; o < (uint32_t)(stages * stage_bytes); o += WG_THREADS * 16u)
         asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(smem_base + o), "r"(0u) : "memory");
@@ -638,26 +644,25 @@ conv_wgrad_shift_kernel(const __grid_constant__ WsArgs a) {
     const uint32_t pitchA = (uint32_t)a.pitchA16 * 16u, pitchB = (uint32_t)a.pitchB16 * 16u;
 
     if (warp == 0) {
-        // ============================== producer: one bulk copy per (plane, channel group) ==============================
-        const uint32_t wbytes = (uint32_t)(a.KP + a.K - 1) * 16u, dbytes = (uint32_t)a.KP * 16u;
-        const uint32_t tx = (uint32_t)NPL * ((uint32_t)ga * wbytes + (uint32_t)gb * dbytes);
-        for (int st = 0; st < nst; ++st) {
-            const int s = st % stages;
-            const uint32_t ph = (uint32_t)(st / stages) & 1u;
-            mbar_wait(empty_bar(s), ph ^ 1u);
-            if (lane == 0) mbar_arrive_expect_tx(full_bar(s), tx);
-            __syncwarp();
-            const long long q0 = (long long)(cbeg + st) * a.KP + a.lead;
-            for (int i = lane; i < NPL * ga; i += 32) {
-                const int pl = i / ga, g = i - pl * ga;
-                bulk_copy_g2s(a_smem(s) + (uint32_t)(pl * 16 + g) * pitchA,
-                              a.x + (((size_t)pl * a.Gx + cib * 16 + g) * a.QA + q0 + (long long)ky * a.Wp) * 8, wbytes,
-                              full_bar(s));
-            }
-            for (int i = lane; i < NPL * gb; i += 32) {
-                const int pl = i / gb, g = i - pl * gb;
-                bulk_copy_g2s(b_smem(s) + (uint32_t)(pl * GB + g) * pitchB,
-                              a.dy + (((size_t)pl * a.Gy + cob * GB + g) * a.QA + q0) * 8, dbytes, full_bar(s));
+        // ============================== producer: one tiled TMA load per (operand, plane) ==============================
+        // tensor maps view the planes as [plane * G + group][position] rows of 16-byte (two uint64) elements; a box is
+        // (window positions) x (channel groups) and lands densely: [group][position] x 16 B.  Rows past this CTA's real
+        // groups hold other channels' data or TMA zero fill - they only feed accumulator rows / columns nobody reads.
+        if (lane == 0) {
+            tma_prefetch_desc(&tmx);
+            tma_prefetch_desc(&tmdy);
+            const uint32_t tx = (uint32_t)NPL * 16u * ((uint32_t)a.rowsA * (uint32_t)a.pitchA16 + (uint32_t)a.rowsB * (uint32_t)a.pitchB16);
+            for (int st = 0; st < nst; ++st) {
+                const int s = st % stages;
+                const uint32_t ph = (uint32_t)(st / stages) & 1u;
+                mbar_wait(empty_bar(s), ph ^ 1u);
+                mbar_arrive_expect_tx(full_bar(s), tx);
+                const int q0 = (cbeg + st) * a.KP + a.lead;
+#pragma unroll
+                for (int pl = 0; pl < NPL; ++pl) {
+                    tma_load_2d(a_smem(s) + (uint32_t)(pl * 16) * pitchA, &tmx, 2 * (q0 + ky * a.Wp), pl * a.Gx + cib * 16, full_bar(s));
+                    tma_load_2d(b_smem(s) + (uint32_t)(pl * GB) * pitchB, &tmdy, 2 * q0, pl * a.Gy + cob * GB, full_bar(s));
+                }
             }
         }
     } else if (warp == MMA_WARP) {
@@ -679,12 +684,12 @@ conv_wgrad_shift_kernel(const __grid_constant__ WsArgs a) {
                     const uint64_t b_hi = b_base + (uint64_t)(k * 16);
                     const uint32_t accum = (uint32_t)((st | k) != 0);
 #pragma unroll 1
-                    for (int kx = 0; kx < a.K; ++kx) {
-                        const uint64_t a_hi = a_base + (uint64_t)(k * 16 + kx);
-                        umma_bf16(tmem_base + kx * BN, a_hi, b_hi, idesc, accum);
+                    for (int j = 0; j < nkx; ++j) {
+                        const uint64_t a_hi = a_base + (uint64_t)(k * 16 + kx0 + j);
+                        umma_bf16(tmem_base + j * BN, a_hi, b_hi, idesc, accum);
                         if (NPASS == 3) {
-                            umma_bf16(tmem_base + kx * BN, a_hi + a_lo_off, b_hi, idesc, 1u);
-                            umma_bf16(tmem_base + kx * BN, a_hi, b_hi + b_lo_off, idesc, 1u);
+                            umma_bf16(tmem_base + j * BN, a_hi + a_lo_off, b_hi, idesc, 1u);
+                            umma_bf16(tmem_base + j * BN, a_hi, b_hi + b_lo_off, idesc, 1u);
                         }
                     }
                 }
@@ -701,14 +706,15 @@ conv_wgrad_shift_kernel(const __grid_constant__ WsArgs a) {
         const bool rok = ci < a.Cs;
         const int taps = a.K * a.K;
         if (nst > 0) {
-            for (int kx = 0; kx < a.K; ++kx) {
+            for (int j = 0; j < nkx; ++j) {
+                const int kx = kx0 + j;
                 float* wbase = a.ws + (size_t)(ky * a.K + kx) * a.Cs + ci;
 #pragma unroll 1
                 for (int jb = 0; jb < BN / 16; ++jb) {
                     const int nb = cob * BN + jb * 16;
                     if (nb >= a.Cout) break;
                     uint32_t raw[16];
-                    tmem_ld16(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(kx * BN + jb * 16), raw);
+                    tmem_ld16(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(j * BN + jb * 16), raw);
                     if (rok) {
 #pragma unroll
                         for (int i = 0; i < 16; ++i)
@@ -726,8 +732,44 @@ conv_wgrad_shift_kernel(const __grid_constant__ WsArgs a) {
     }
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode_tiled() {
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return (EncodeTiledFn)p;
+    }();
+    return fn;
+}
+// planes [rows = npl * G][QA positions x 16 bytes] as a 2-D tensor of uint64 pairs; box = box_pos positions x box_rows groups
+int make_plane_map(CUtensorMap* tm, const void* planes, long long QA, int rows, int box_pos, int box_rows) {
+    EncodeTiledFn enc = get_encode_tiled();
+    if (!enc) {
+        affgw_set_error("cuTensorMapEncodeTiled is not available from this driver");
+        return -2;
+    }
+    const cuuint64_t gdim[2] = {(cuuint64_t)QA * 2, (cuuint64_t)rows};
+    const cuuint64_t gstride[1] = {(cuuint64_t)QA * 16};
+    const cuuint32_t box[2] = {(cuuint32_t)box_pos * 2, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, const_cast<void*>(planes), gdim, gstride, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        affgw_set_error("cuTensorMapEncodeTiled failed (%d): QA %lld rows %d box %d x %d", (int)r, QA, rows, box_pos, box_rows);
+        return -2;
+    }
+    return 0;
+}
+
 template <int BN, int NPASS>
-int launch_wg_shift(const WsArgs& args, dim3 grid, int smem_bytes, cudaStream_t st) {
+int launch_wg_shift(const WsArgs& args, const CUtensorMap& tmx, const CUtensorMap& tmdy, dim3 grid, int smem_bytes, cudaStream_t st) {
     auto kern = conv_wgrad_shift_kernel<BN, NPASS>;
     static bool configured = false;
     if (!configured) {
@@ -737,7 +779,7 @@ int launch_wg_shift(const WsArgs& args, dim3 grid, int smem_bytes, cudaStream_t 
         }
         configured = true;
     }
-    kern<<<grid, WG_THREADS, smem_bytes, st>>>(args);
+    kern<<<grid, WG_THREADS, smem_bytes, st>>>(args, tmx, tmdy);
     AFFGW_LAUNCH_CHECK("conv_wgrad_shift");
     return 0;
 }
@@ -749,20 +791,24 @@ int launch_wg_shift(const WsArgs& args, dim3 grid, int smem_bytes, cudaStream_t 
 int conv_wgrad_pos_tc(const void* x_planes, const PosFrame& fx, const void* dy_planes, const PosFrame& fy, float* ws, int K,
                       int Cout, int cs, int Ho, int Wo, int passes, cudaStream_t st) {
     const int npl = passes == 3 ? 2 : 1;
-    const int limit = K <= 4 ? 128 : 64;                        // K * BN TMEM columns <= 512
-    const int bn = Cout <= 16 ? 16 : Cout <= 32 ? 32 : Cout <= 64 ? 64 : limit;
+    const int bn = Cout <= 16 ? 16 : Cout <= 32 ? 32 : Cout <= 64 ? 64 : 128;
     WsArgs a;
     a.KP = 64;
-    a.pitchA16 = a.KP + 9;
-    a.pitchB16 = a.KP + 1;
+    a.rowsA = fx.G < 16 ? fx.G : 16;
+    a.rowsB = fy.G < bn / 8 ? fy.G : bn / 8;
+    a.pitchA16 = a.KP + K - 1;                                  // dense TMA boxes: pitch = box width
+    a.pitchB16 = a.KP + (bn >= 64 ? 1 : bn == 32 ? 2 : 4);      // every plane of a stage starts 128-byte aligned (TMA destination)
     a.a_bytes = npl * 16 * a.pitchA16 * 16;
     a.b_bytes = npl * (bn / 8) * a.pitchB16 * 16;
     const int stage = a.a_bytes + a.b_bytes;
     const int stg = (SMEM_LIMIT - 128 - 256) / stage;
-    if (stg < 2 || K > 7 || fx.QA != fy.QA || fx.lead != fy.lead || fx.Wp != fy.Wp) {
+    if (stg < 2 || K > 7 || fx.QA != fy.QA || fx.lead != fy.lead || fx.Wp != fy.Wp || fx.QA >= (1LL << 30)) {
         affgw_set_error("conv_wgrad_shift: unsupported configuration");
         return -1;
     }
+    CUtensorMap tmx, tmdy;
+    if (int rc = make_plane_map(&tmx, x_planes, fx.QA, npl * fx.G, a.pitchA16, a.rowsA)) return rc;
+    if (int rc = make_plane_map(&tmdy, dy_planes, fy.QA, npl * fy.G, a.pitchB16, a.rowsB)) return rc;
     a.stages = stg > MAX_STAGES ? MAX_STAGES : stg;
     const int smem_bytes = a.stages * stage + 128 + 256;
     a.x = (const bf16*)x_planes; a.dy = (const bf16*)dy_planes; a.ws = ws;
@@ -772,7 +818,10 @@ int conv_wgrad_pos_tc(const void* x_planes, const PosFrame& fx, const void* dy_p
     a.n_co_blocks = (Cout + bn - 1) / bn;
     const long long q_last = ((long long)(fx.N - 1) * fx.Hp + Ho - 1) * fx.Wp + Wo - 1;
     a.chunks_total = (int)(q_last / a.KP + 1);
-    const int tiles = n_ci * a.n_co_blocks * K;
+    const int per_cta = 512 / bn;                               // filter columns whose accumulators fit in TMEM
+    a.n_kxg = (K + per_cta - 1) / per_cta;
+    a.KXG = (K + a.n_kxg - 1) / a.n_kxg;
+    const int tiles = n_ci * a.n_co_blocks * K * a.n_kxg;
     // split the position range so that the CTAs fill whole waves of 148 SMs (each split keeps >= 8 stages of work)
     int max_splits = (a.chunks_total + 7) / 8;
     if (max_splits > 320 / tiles + 1) max_splits = 320 / tiles + 1;
@@ -788,16 +837,16 @@ int conv_wgrad_pos_tc(const void* x_planes, const PosFrame& fx, const void* dy_p
     dim3 grid((unsigned)tiles, (unsigned)splits);
     if (passes == 3) {
         switch (bn) {
-            case 16: return launch_wg_shift<16, 3>(a, grid, smem_bytes, st);
-            case 32: return launch_wg_shift<32, 3>(a, grid, smem_bytes, st);
-            case 64: return launch_wg_shift<64, 3>(a, grid, smem_bytes, st);
-            default: return launch_wg_shift<128, 3>(a, grid, smem_bytes, st);
+            case 16: return launch_wg_shift<16, 3>(a, tmx, tmdy, grid, smem_bytes, st);
+            case 32: return launch_wg_shift<32, 3>(a, tmx, tmdy, grid, smem_bytes, st);
+            case 64: return launch_wg_shift<64, 3>(a, tmx, tmdy, grid, smem_bytes, st);
+            default: return launch_wg_shift<128, 3>(a, tmx, tmdy, grid, smem_bytes, st);
         }
     }
     switch (bn) {
-        case 16: return launch_wg_shift<16, 1>(a, grid, smem_bytes, st);
-        case 32: return launch_wg_shift<32, 1>(a, grid, smem_bytes, st);
-        case 64: return launch_wg_shift<64, 1>(a, grid, smem_bytes, st);
-        default: return launch_wg_shift<128, 1>(a, grid, smem_bytes, st);
+        case 16: return launch_wg_shift<16, 1>(a, tmx, tmdy, grid, smem_bytes, st);
+        case 32: return launch_wg_shift<32, 1>(a, tmx, tmdy, grid, smem_bytes, st);
+        case 64: return launch_wg_shift<64, 1>(a, tmx, tmdy, grid, smem_bytes, st);
+        default: return launch_wg_shift<128, 1>(a, tmx, tmdy, grid, smem_bytes, st);
     }
 }
