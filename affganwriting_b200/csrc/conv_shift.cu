@@ -585,7 +585,8 @@ struct WsArgs {
     int Cs, Cout;                            // row length of ws / real output channels
     int KP, pitchA16, pitchB16;              // positions per stage; shared-memory plane pitches in 16-byte units
     int rowsA, rowsB;                        // channel groups per TMA box (<= 16, <= BN / 8)
-    int KXG, n_kxg;                          // filter columns per CTA (KXG * BN <= 512 TMEM columns), column groups per row
+    int KXG, n_kxg;                          // filter columns per CTA (accumulators <= 512 TMEM columns), column groups per row
+    int TPM, slots;                          // filter columns packed into the M rows of one MMA (thin layers); A group slots
     int n_co_blocks;
     int chunks_total, chunks_per_split;
     int a_bytes, b_bytes, stages;
@@ -651,7 +652,8 @@ conv_wgrad_shift_kernel(const __grid_constant__ WsArgs a, const __grid_constant_
         if (lane == 0) {
             tma_prefetch_desc(&tmx);
             tma_prefetch_desc(&tmdy);
-            const uint32_t tx = (uint32_t)NPL * 16u * ((uint32_t)a.rowsA * (uint32_t)a.pitchA16 + (uint32_t)a.rowsB * (uint32_t)a.pitchB16);
+            const uint32_t copies = a.TPM == 1 ? 1u : (uint32_t)nkx;
+            const uint32_t tx = (uint32_t)NPL * 16u * (copies * (uint32_t)a.rowsA * (uint32_t)a.pitchA16 + (uint32_t)a.rowsB * (uint32_t)a.pitchB16);
             for (int st = 0; st < nst; ++st) {
                 const int s = st % stages;
                 const uint32_t ph = (uint32_t)(st / stages) & 1u;
@@ -660,7 +662,14 @@ conv_wgrad_shift_kernel(const __grid_constant__ WsArgs a, const __grid_constant_
                 const int q0 = (cbeg + st) * a.KP + a.lead;
 #pragma unroll
                 for (int pl = 0; pl < NPL; ++pl) {
-                    tma_load_2d(a_smem(s) + (uint32_t)(pl * 16) * pitchA, &tmx, 2 * (q0 + ky * a.Wp), pl * a.Gx + cib * 16, full_bar(s));
+                    if (a.TPM == 1) {
+                        tma_load_2d(a_smem(s) + (uint32_t)(pl * a.slots) * pitchA, &tmx, 2 * (q0 + ky * a.Wp), pl * a.Gx + cib * 16,
+                                    full_bar(s));
+                    } else {            // thin layer: one pre-shifted copy of the window per filter column, stacked along M
+                        for (int j = 0; j < nkx; ++j)
+                            tma_load_2d(a_smem(s) + (uint32_t)(pl * a.slots + j * a.Gx) * pitchA, &tmx,
+                                        2 * (q0 + ky * a.Wp + kx0 + j), pl * a.Gx, full_bar(s));
+                    }
                     tma_load_2d(b_smem(s) + (uint32_t)(pl * GB) * pitchB, &tmdy, 2 * q0, pl * a.Gy + cob * GB, full_bar(s));
                 }
             }
@@ -678,14 +687,19 @@ conv_wgrad_shift_kernel(const __grid_constant__ WsArgs a, const __grid_constant_
                 // in their start address: add (byte offset >> 4) to the low word
                 const uint64_t a_base = make_nosw_desc(a_smem(s), 128u, pitchA);
                 const uint64_t b_base = make_nosw_desc(b_smem(s), 128u, pitchB);
-                const uint32_t a_lo_off = (16u * pitchA) >> 4, b_lo_off = ((uint32_t)GB * pitchB) >> 4;
+                const uint32_t a_lo_off = ((uint32_t)a.slots * pitchA) >> 4, b_lo_off = ((uint32_t)GB * pitchB) >> 4;
+                // shared window: accumulator j = filter column kx0 + j, A starts j positions further;
+                // packed: accumulator j = columns [j*TPM, (j+1)*TPM) stacked along M, A starts at their first copy
+                const int nacc = a.TPM == 1 ? nkx : (nkx + a.TPM - 1) / a.TPM;
+                const uint32_t a_step = a.TPM == 1 ? 1u : (uint32_t)(a.TPM * a.Gx * a.pitchA16);
+                const uint32_t a_first = a.TPM == 1 ? (uint32_t)kx0 : 0u;
 #pragma unroll 1
                 for (int k = 0; k < a.KP / 16; ++k) {
                     const uint64_t b_hi = b_base + (uint64_t)(k * 16);
                     const uint32_t accum = (uint32_t)((st | k) != 0);
 #pragma unroll 1
-                    for (int j = 0; j < nkx; ++j) {
-                        const uint64_t a_hi = a_base + (uint64_t)(k * 16 + kx0 + j);
+                    for (int j = 0; j < nacc; ++j) {
+                        const uint64_t a_hi = a_base + (uint64_t)((uint32_t)(k * 16) + a_first + (uint32_t)j * a_step);
                         umma_bf16(tmem_base + j * BN, a_hi, b_hi, idesc, accum);
                         if (NPASS == 3) {
                             umma_bf16(tmem_base + j * BN, a_hi + a_lo_off, b_hi, idesc, 1u);
@@ -702,13 +716,25 @@ conv_wgrad_shift_kernel(const __grid_constant__ WsArgs a, const __grid_constant_
         const int wq = warp & 3;
         mbar_wait(tmem_full_bar, 0);
         tc_fence_after();
-        const int ci = cib * 128 + wq * 32 + lane;
-        const bool rok = ci < a.Cs;
+        const int m = wq * 32 + lane;                        // accumulator row
         const int taps = a.K * a.K;
+        const int nacc = a.TPM == 1 ? nkx : (nkx + a.TPM - 1) / a.TPM;
         if (nst > 0) {
-            for (int j = 0; j < nkx; ++j) {
-                const int kx = kx0 + j;
-                float* wbase = a.ws + (size_t)(ky * a.K + kx) * a.Cs + ci;
+            for (int j = 0; j < nacc; ++j) {
+                // which (filter column, input channel) this row holds
+                int kx, ci;
+                bool rok;
+                if (a.TPM == 1) {
+                    kx = kx0 + j;
+                    ci = cib * 128 + m;
+                    rok = ci < a.Cs;
+                } else {
+                    const int slot = m >> 3, jj = slot / a.Gx;
+                    kx = kx0 + j * a.TPM + jj;
+                    ci = (slot - jj * a.Gx) * 8 + (m & 7);
+                    rok = jj < a.TPM && kx < kx0 + nkx && ci < a.Cs;
+                }
+                float* wbase = a.ws + (size_t)(ky * a.K + (rok ? kx : 0)) * a.Cs + (rok ? ci : 0);
 #pragma unroll 1
                 for (int jb = 0; jb < BN / 16; ++jb) {
                     const int nb = cob * BN + jb * 16;
@@ -794,11 +820,24 @@ int conv_wgrad_pos_tc(const void* x_planes, const PosFrame& fx, const void* dy_p
     const int bn = Cout <= 16 ? 16 : Cout <= 32 ? 32 : Cout <= 64 ? 64 : 128;
     WsArgs a;
     a.KP = 64;
+    // thin layers (<= 64 stored input channels): stack TPM pre-shifted copies of the window along the 128 M rows, one MMA
+    // then covers TPM filter columns.  Otherwise one shared window, one accumulator per filter column.
+    const bool packed = fx.G <= 8 && K > 1;
+    a.TPM = packed ? (K < 16 / fx.G ? K : 16 / fx.G) : 1;
+    int acc_max = 512 / bn;                                     // accumulators that fit in TMEM ...
+    if (packed) {                                               // ... and whose window copies fit in ~40 group slots
+        const int cap = 24 / (a.TPM * fx.G) > 1 ? 24 / (a.TPM * fx.G) : 1;
+        if (acc_max > cap) acc_max = cap;
+    }
+    const int per_cta = a.TPM * acc_max;                        // filter columns one CTA can own
+    a.n_kxg = (K + per_cta - 1) / per_cta;
+    a.KXG = (K + a.n_kxg - 1) / a.n_kxg;
+    a.slots = packed ? (a.KXG + a.TPM - 1) / a.TPM * a.TPM * fx.G + 16 : 16;
     a.rowsA = fx.G < 16 ? fx.G : 16;
     a.rowsB = fy.G < bn / 8 ? fy.G : bn / 8;
-    a.pitchA16 = a.KP + K - 1;                                  // dense TMA boxes: pitch = box width
+    a.pitchA16 = packed ? a.KP + 4 : a.KP + K - 1;              // dense TMA boxes: pitch = box width
     a.pitchB16 = a.KP + (bn >= 64 ? 1 : bn == 32 ? 2 : 4);      // every plane of a stage starts 128-byte aligned (TMA destination)
-    a.a_bytes = npl * 16 * a.pitchA16 * 16;
+    a.a_bytes = npl * a.slots * a.pitchA16 * 16;
     a.b_bytes = npl * (bn / 8) * a.pitchB16 * 16;
     const int stage = a.a_bytes + a.b_bytes;
     const int stg = (SMEM_LIMIT - 128 - 256) / stage;
@@ -818,9 +857,6 @@ int conv_wgrad_pos_tc(const void* x_planes, const PosFrame& fx, const void* dy_p
     a.n_co_blocks = (Cout + bn - 1) / bn;
     const long long q_last = ((long long)(fx.N - 1) * fx.Hp + Ho - 1) * fx.Wp + Wo - 1;
     a.chunks_total = (int)(q_last / a.KP + 1);
-    const int per_cta = 512 / bn;                               // filter columns whose accumulators fit in TMEM
-    a.n_kxg = (K + per_cta - 1) / per_cta;
-    a.KXG = (K + a.n_kxg - 1) / a.n_kxg;
     const int tiles = n_ci * a.n_co_blocks * K * a.n_kxg;
     // split the position range so that the CTAs fill whole waves of 148 SMs (each split keeps >= 8 stages of work)
     int max_splits = (a.chunks_total + 7) / 8;

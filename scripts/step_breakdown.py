@@ -35,6 +35,9 @@ def main():
     e1.record(); torch.cuda.synchronize()
     step_ms = e0.elapsed_time(e1) / 3
     print(f"step {step_ms:.1f} ms (mode {args.mode}, batch {args.batch})")
+    import time
+    torch.cuda.synchronize(); t0 = time.perf_counter(); tr.train_step(batch); t1 = time.perf_counter(); torch.cuda.synchronize()
+    print(f"host-side issue time of one step (no sync): {1e3 * (t1 - t0):.1f} ms")
     ops.start_kernel_timing()
     tr.train_step(batch)
     rec = ops.stop_kernel_timing(by_shape=True)
