@@ -43,6 +43,11 @@ SIGNATURES = {
     "affgw_pack_weight": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "affgw_pack_weight_tc": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     "affgw_pack_weight_tc_bytes": [_I, _I, _I, _I, _I, _I, _I, _I],
+    "affgw_maxpool3s2_fwd": [_P, _P, _I, _I, _I, _I, _I, _P],
+    "affgw_maxpool3s2_bwd": [_P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "affgw_resize_bilinear_fwd": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
+    "affgw_resize_bilinear_bwd": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
+    "affgw_add_act": [_P, _P, _P, _I, _L, _I, _P],
     "affgw_conv_tc_layout": [_D, _I],
     "affgw_conv_pos_frames": [_D, C.POINTER(PosFrame), C.POINTER(PosFrame)],
     "affgw_position_planes_bytes": [C.POINTER(PosFrame), _I],

@@ -68,6 +68,11 @@ int gate_bwd(const void* dy, const void* x, const void* r, const void* xl, const
 int gap_fwd(const void* x, void* out, int dt, int N, long long P, int C, cudaStream_t st);
 int bcast_add(const void* a, const void* v, void* out, int dt, int N, long long P, int C, float scale, cudaStream_t st);
 int add2(const void* a, const void* b, void* out, int dt, long long n, cudaStream_t st);
+int add_act(const void* a, const void* b, void* out, int dt, long long n, int act, cudaStream_t st);
+int maxpool3s2_fwd(const void* x, void* y, int dt, int N, int H, int W, int C, cudaStream_t st);
+int maxpool3s2_bwd(const void* dy, const void* x, void* dx, int dt, int N, int H, int W, int C, cudaStream_t st);
+int resize_bilinear_fwd(const void* x, void* y, int dt, int N, int H, int W, int C, int Ho, int Wo, cudaStream_t st);
+int resize_bilinear_bwd(const void* dy, float* dx, int dt, int N, int H, int W, int C, int Ho, int Wo, cudaStream_t st);
 int act_bwd(const void* dy, const void* y, void* dz, int dt, long long n, int act, cudaStream_t st);
 int resize_nearest_fwd(const void* x, void* y, int dt, int N, int H, int W, int C, int Ho, int Wo, cudaStream_t st);
 int resize_nearest_bwd(const void* dy, void* dx, int dt, int N, int H, int W, int C, int Ho, int Wo, cudaStream_t st);
@@ -502,6 +507,26 @@ int affgw_gap_fwd(const void* x, void* out, int dt, int N, long long P, int C, v
 int affgw_bcast_add(const void* a, const void* v, void* out, int dt, int N, long long P, int C, float scale, void* s) {
     REQ(v && out && dt_ok(dt) && N > 0 && P > 0 && C > 0, "bcast_add");
     return bcast_add(a, v, out, dt, N, P, C, scale, S(s));
+}
+int affgw_maxpool3s2_fwd(const void* x, void* y, int dt, int N, int H, int W, int C, void* s) {
+    REQ(x && y && dt_ok(dt) && N > 0 && H > 1 && W > 1 && C > 0, "maxpool3s2_fwd");
+    return maxpool3s2_fwd(x, y, dt, N, H, W, C, S(s));
+}
+int affgw_maxpool3s2_bwd(const void* dy, const void* x, void* dx, int dt, int N, int H, int W, int C, void* s) {
+    REQ(dy && x && dx && dt_ok(dt) && N > 0 && H > 1 && W > 1 && C > 0, "maxpool3s2_bwd");
+    return maxpool3s2_bwd(dy, x, dx, dt, N, H, W, C, S(s));
+}
+int affgw_resize_bilinear_fwd(const void* x, void* y, int dt, int N, int H, int W, int C, int Ho, int Wo, void* s) {
+    REQ(x && y && dt_ok(dt) && N > 0 && H > 0 && W > 0 && C > 0 && Ho > 0 && Wo > 0, "resize_bilinear_fwd");
+    return resize_bilinear_fwd(x, y, dt, N, H, W, C, Ho, Wo, S(s));
+}
+int affgw_resize_bilinear_bwd(const void* dy, float* dx, int dt, int N, int H, int W, int C, int Ho, int Wo, void* s) {
+    REQ(dy && dx && dt_ok(dt) && N > 0 && H > 0 && W > 0 && C > 0 && Ho > 0 && Wo > 0, "resize_bilinear_bwd");
+    return resize_bilinear_bwd(dy, dx, dt, N, H, W, C, Ho, Wo, S(s));
+}
+int affgw_add_act(const void* a, const void* b, void* out, int dt, long long n, int act, void* s) {
+    REQ(a && b && out && dt_ok(dt) && n > 0 && act >= 0 && act <= 3, "add_act");
+    return add_act(a, b, out, dt, n, act, S(s));
 }
 int affgw_add2(const void* a, const void* b, void* out, int dt, long long n, void* s) {
     REQ(a && b && out && dt_ok(dt) && n > 0, "add2");

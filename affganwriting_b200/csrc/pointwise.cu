@@ -286,6 +286,163 @@ __global__ void add2_kernel(const T* __restrict__ a, const T* __restrict__ b, T*
     }
 }
 
+
+// ---------------------------------------------------------------- max pool 3x3 stride 2 pad 1 (torchvision ResNet stem)
+template <typename T, int VEC>
+__global__ void maxpool3s2_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int H, int W, int C, int Ho, int Wo) {
+    const int cv = C / VEC;
+    const long long total = (long long)N * Ho * Wo * cv;
+    GRID_STRIDE(idx, total) {
+        const int c = (int)(idx % cv) * VEC;
+        long long t = idx / cv;
+        const int ox = (int)(t % Wo);
+        t /= Wo;
+        const int oy = (int)(t % Ho);
+        const int n = (int)(t / Ho);
+        float m[VEC];
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) m[i] = -INFINITY;
+        for (int ky = 0; ky < 3; ++ky) {
+            const int yy = 2 * oy - 1 + ky;
+            if (yy < 0 || yy >= H) continue;
+            for (int kx = 0; kx < 3; ++kx) {
+                const int xx = 2 * ox - 1 + kx;
+                if (xx < 0 || xx >= W) continue;
+                float v[VEC];
+                ldv<VEC>(x + (((long long)n * H + yy) * W + xx) * C + c, v);
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) m[i] = fmaxf(m[i], v[i]);
+            }
+        }
+        stv<VEC>(y + idx * VEC, m);
+    }
+}
+
+// gather form: input pixel (yy, xx) receives dy of every window whose FIRST maximum in scan order it is (PyTorch tie rule)
+template <typename T, int VEC>
+__global__ void maxpool3s2_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, T* __restrict__ dx, int N, int H, int W,
+                                      int C, int Ho, int Wo) {
+    const int cv = C / VEC;
+    const long long total = (long long)N * H * W * cv;
+    GRID_STRIDE(idx, total) {
+        const int c = (int)(idx % cv) * VEC;
+        long long t = idx / cv;
+        const int xx = (int)(t % W);
+        t /= W;
+        const int yy = (int)(t % H);
+        const int n = (int)(t / H);
+        float mine[VEC], out[VEC];
+        ldv<VEC>(x + idx * VEC, mine);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) out[i] = 0.f;
+        // windows (oy, ox) with 2*oy - 1 <= yy <= 2*oy + 1
+        for (int oy = (yy + 1) / 2 - ((yy + 1) % 2 == 0 ? 1 : 0); oy <= (yy + 1) / 2; ++oy) {
+            if (oy < 0 || oy >= Ho) continue;
+            for (int ox = (xx + 1) / 2 - ((xx + 1) % 2 == 0 ? 1 : 0); ox <= (xx + 1) / 2; ++ox) {
+                if (ox < 0 || ox >= Wo) continue;
+                const int my_pos = (yy - (2 * oy - 1)) * 3 + (xx - (2 * ox - 1));
+                bool win[VEC];
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) win[i] = true;
+                for (int ky = 0; ky < 3; ++ky) {
+                    const int y2 = 2 * oy - 1 + ky;
+                    if (y2 < 0 || y2 >= H) continue;
+                    for (int kx = 0; kx < 3; ++kx) {
+                        const int x2 = 2 * ox - 1 + kx;
+                        if (x2 < 0 || x2 >= W) continue;
+                        const int pos = ky * 3 + kx;
+                        if (pos == my_pos) continue;
+                        float v[VEC];
+                        ldv<VEC>(x + (((long long)n * H + y2) * W + x2) * C + c, v);
+#pragma unroll
+                        for (int i = 0; i < VEC; ++i)      // an earlier element wins ties, a later one must be strictly greater
+                            if (pos < my_pos ? v[i] >= mine[i] : v[i] > mine[i]) win[i] = false;
+                    }
+                }
+                float g[VEC];
+                ldv<VEC>(dy + (((long long)n * Ho + oy) * Wo + ox) * C + c, g);
+#pragma unroll
+                for (int i = 0; i < VEC; ++i)
+                    if (win[i]) out[i] += g[i];
+            }
+        }
+        stv<VEC>(dx + idx * VEC, out);
+    }
+}
+
+// ---------------------------------------------------------------- bilinear resize, align_corners = False (F.interpolate)
+__device__ __forceinline__ void bilinear_src(int dst, int in, int out, int& i0, int& i1, float& w1) {
+    float s = ((float)dst + 0.5f) * ((float)in / (float)out) - 0.5f;
+    if (s < 0.f) s = 0.f;
+    i0 = min((int)s, in - 1);
+    i1 = min(i0 + 1, in - 1);
+    w1 = s - (float)i0;
+}
+template <typename T, int VEC>
+__global__ void resize_bilinear_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int H, int W, int C, int Ho, int Wo) {
+    const int cv = C / VEC;
+    const long long total = (long long)N * Ho * Wo * cv;
+    GRID_STRIDE(idx, total) {
+        const int c = (int)(idx % cv) * VEC;
+        long long t = idx / cv;
+        const int ox = (int)(t % Wo);
+        t /= Wo;
+        const int oy = (int)(t % Ho);
+        const int n = (int)(t / Ho);
+        int y0, y1, x0, x1;
+        float wy, wx;
+        bilinear_src(oy, H, Ho, y0, y1, wy);
+        bilinear_src(ox, W, Wo, x0, x1, wx);
+        const T* base = x + (long long)n * H * W * C + c;
+        float a[VEC], b[VEC], d[VEC], e[VEC], o[VEC];
+        ldv<VEC>(base + ((long long)y0 * W + x0) * C, a);
+        ldv<VEC>(base + ((long long)y0 * W + x1) * C, b);
+        ldv<VEC>(base + ((long long)y1 * W + x0) * C, d);
+        ldv<VEC>(base + ((long long)y1 * W + x1) * C, e);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i)
+            o[i] = (1.f - wy) * ((1.f - wx) * a[i] + wx * b[i]) + wy * ((1.f - wx) * d[i] + wx * e[i]);
+        stv<VEC>(y + idx * VEC, o);
+    }
+}
+// scatter form with fp32 atomics (dx zeroed by the caller; maps are tiny: 2x7 -> 8x27)
+template <typename T>
+__global__ void resize_bilinear_bwd_kernel(const T* __restrict__ dy, float* __restrict__ dx, int N, int H, int W, int C, int Ho,
+                                           int Wo) {
+    const long long total = (long long)N * Ho * Wo * C;
+    GRID_STRIDE(idx, total) {
+        const int c = (int)(idx % C);
+        long long t = idx / C;
+        const int ox = (int)(t % Wo);
+        t /= Wo;
+        const int oy = (int)(t % Ho);
+        const int n = (int)(t / Ho);
+        int y0, y1, x0, x1;
+        float wy, wx;
+        bilinear_src(oy, H, Ho, y0, y1, wy);
+        bilinear_src(ox, W, Wo, x0, x1, wx);
+        const float g = to_f(dy[idx]);
+        float* base = dx + (long long)n * H * W * C + c;
+        atomicAdd(base + ((long long)y0 * W + x0) * C, g * (1.f - wy) * (1.f - wx));
+        atomicAdd(base + ((long long)y0 * W + x1) * C, g * (1.f - wy) * wx);
+        atomicAdd(base + ((long long)y1 * W + x0) * C, g * wy * (1.f - wx));
+        atomicAdd(base + ((long long)y1 * W + x1) * C, g * wy * wx);
+    }
+}
+
+// ---------------------------------------------------------------- out = act(a + b)   (BasicBlock / Bottleneck tail)
+template <typename T, int VEC>
+__global__ void add_act_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ out, long long nvec, int act) {
+    GRID_STRIDE(idx, nvec) {
+        float x[VEC], y[VEC];
+        ldv<VEC>(a + idx * VEC, x);
+        ldv<VEC>(b + idx * VEC, y);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) x[i] = act_apply(x[i] + y[i], act);
+        stv<VEC>(out + idx * VEC, x);
+    }
+}
+
 // ---------------------------------------------------------------- nearest resize (F.interpolate default mode)
 __device__ __forceinline__ int nearest_src(int dst, int in, int out) {
     const float scale = (float)in / (float)out;
@@ -619,6 +776,50 @@ int bcast_add(const void* a, const void* v, void* out, int dt, int N, long long 
     DISPATCH_T_VEC(dt, C, CALL);
 #undef CALL
     AFFGW_LAUNCH_CHECK("bcast_add");
+    return 0;
+}
+
+int maxpool3s2_fwd(const void* x, void* y, int dt, int N, int H, int W, int C, cudaStream_t st) {
+    const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+    const long long total = (long long)N * Ho * Wo * VECN(C);
+#define CALL(T, V) maxpool3s2_fwd_kernel<T, V><<<ew_blocks(total), 256, 0, st>>>((const T*)x, (T*)y, N, H, W, C, Ho, Wo)
+    DISPATCH_T_VEC(dt, C, CALL);
+#undef CALL
+    AFFGW_LAUNCH_CHECK("maxpool3s2_fwd");
+    return 0;
+}
+int maxpool3s2_bwd(const void* dy, const void* x, void* dx, int dt, int N, int H, int W, int C, cudaStream_t st) {
+    const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+    const long long total = (long long)N * H * W * VECN(C);
+#define CALL(T, V) maxpool3s2_bwd_kernel<T, V><<<ew_blocks(total), 256, 0, st>>>((const T*)dy, (const T*)x, (T*)dx, N, H, W, C, Ho, Wo)
+    DISPATCH_T_VEC(dt, C, CALL);
+#undef CALL
+    AFFGW_LAUNCH_CHECK("maxpool3s2_bwd");
+    return 0;
+}
+int resize_bilinear_fwd(const void* x, void* y, int dt, int N, int H, int W, int C, int Ho, int Wo, cudaStream_t st) {
+    const long long total = (long long)N * Ho * Wo * VECN(C);
+#define CALL(T, V) resize_bilinear_fwd_kernel<T, V><<<ew_blocks(total), 256, 0, st>>>((const T*)x, (T*)y, N, H, W, C, Ho, Wo)
+    DISPATCH_T_VEC(dt, C, CALL);
+#undef CALL
+    AFFGW_LAUNCH_CHECK("resize_bilinear_fwd");
+    return 0;
+}
+int resize_bilinear_bwd(const void* dy, float* dx, int dt, int N, int H, int W, int C, int Ho, int Wo, cudaStream_t st) {
+    const long long total = (long long)N * Ho * Wo * C;
+    if (dt == AFFGW_F32)
+        resize_bilinear_bwd_kernel<float><<<ew_blocks(total), 256, 0, st>>>((const float*)dy, dx, N, H, W, C, Ho, Wo);
+    else
+        resize_bilinear_bwd_kernel<bf16><<<ew_blocks(total), 256, 0, st>>>((const bf16*)dy, dx, N, H, W, C, Ho, Wo);
+    AFFGW_LAUNCH_CHECK("resize_bilinear_bwd");
+    return 0;
+}
+int add_act(const void* a, const void* b, void* out, int dt, long long n, int act, cudaStream_t st) {
+    const long long nv = n % 8 == 0 ? n / 8 : n;
+#define CALL(T, V) add_act_kernel<T, V><<<ew_blocks(nv), 256, 0, st>>>((const T*)a, (const T*)b, (T*)out, nv, act)
+    DISPATCH_T_VEC(dt, n, CALL);
+#undef CALL
+    AFFGW_LAUNCH_CHECK("add_act");
     return 0;
 }
 int add2(const void* a, const void* b, void* out, int dt, long long n, cudaStream_t st) {

@@ -12,6 +12,7 @@ import sys
 
 from . import blocks as _blocks
 from . import modules_tro as _modules
+from . import resnet_encoder as _resnet
 
 BLOCK_NAMES = ("Conv2dBlock", "ResBlock", "ResBlocks", "ActFirstResBlock", "LinearBlock", "AdaptiveInstanceNorm2d", "iAFF",
                "get_key", "mean_variance_norm")
@@ -33,4 +34,8 @@ def install(ref_blocks="blocks", ref_modules="modules_tro"):
         if hasattr(rm, n):
             setattr(rm, n, getattr(src, n))
             done.append((ref_modules, n))
+    # the encoder the reference's GenModel_FC constructs by default (modules_tro.py:219)
+    if hasattr(rm, "ImageEncoderResNet50"):
+        rm.ImageEncoderResNet50 = _resnet.ImageEncoderResNet50
+        done.append((ref_modules, "ImageEncoderResNet50"))
     return done

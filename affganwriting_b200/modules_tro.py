@@ -179,9 +179,26 @@ class Decoder(nn.Module):
         return x
 
 
+def make_encoder(name, in_channels=None):
+    """'vgg' (ImageEncoder, the north-star path), 'resnet50' (the encoder active in the reference, modules_tro.py:219) or
+    'resnet18' (modules_tro2.py:447-516)."""
+    from .load_data import NUM_CHANNEL
+    from .resnet_encoder import ImageEncoderResNet18, ImageEncoderResNet50
+    c = NUM_CHANNEL if in_channels is None else in_channels
+    if name == "vgg":
+        return ImageEncoder()
+    if name == "resnet50":
+        return ImageEncoderResNet50(weight_path=None, in_channels=c)
+    if name == "resnet18":
+        return ImageEncoderResNet18(weight_path=None, in_channels=c)
+    raise ValueError(f"unknown style encoder {name!r}")
+
+
 class GenModel_FC(nn.Module):
     def __init__(self, text_max_len=OUTPUT_MAX_LEN, encoder=None):
         super().__init__()
+        if isinstance(encoder, str):
+            encoder = make_encoder(encoder)
         self.enc_image = encoder if encoder is not None else ImageEncoder()
         self.enc_text = TextEncoder_FC(text_max_len)
         self.dec = Decoder()

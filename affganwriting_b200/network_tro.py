@@ -18,10 +18,10 @@ w_rec = 1.
 
 
 class ConTranModel(nn.Module):
-    def __init__(self, num_writers, show_iter_num=500, oov=True, rec=None, device=None):
+    def __init__(self, num_writers, show_iter_num=500, oov=True, rec=None, device=None, encoder=None):
         super().__init__()
         dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
-        self.gen = GenModel_FC(OUTPUT_MAX_LEN).to(dev)
+        self.gen = GenModel_FC(OUTPUT_MAX_LEN, encoder=encoder).to(dev)
         self.cla = WriterClaModel(num_writers).to(dev)
         self.dis = DisModel().to(dev)
         if rec is not None:

@@ -626,6 +626,83 @@ def max_pool2(x):
     return _MaxPool2.apply(x)
 
 
+class _MaxPool3s2(Function):
+    """nn.MaxPool2d(kernel_size=3, stride=2, padding=1) (torchvision ResNet stem)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = _dense_cl(x)
+        n, c, h, w = x.shape
+        y = empty_cl(n, c, (h - 1) // 2 + 1, (w - 1) // 2 + 1, x.dtype, x.device)
+        L.call("affgw_maxpool3s2_fwd", x.data_ptr(), y.data_ptr(), L.dt(x), n, h, w, c, L.stream())
+        ctx.save_for_backward(x)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        n, c, h, w = x.shape
+        dy = _dense_cl(dy, x.dtype)
+        dx = torch.empty_like(x)
+        L.call("affgw_maxpool3s2_bwd", dy.data_ptr(), x.data_ptr(), dx.data_ptr(), L.dt(x), n, h, w, c, L.stream())
+        return dx
+
+
+def max_pool3s2(x):
+    return _MaxPool3s2.apply(x)
+
+
+class _ResizeBilinear(Function):
+    """F.interpolate(size=(ho, wo), mode="bilinear", align_corners=False) (modules_tro.py:527)."""
+
+    @staticmethod
+    def forward(ctx, x, ho, wo):
+        x = _dense_cl(x)
+        n, c, h, w = x.shape
+        y = empty_cl(n, c, ho, wo, x.dtype, x.device)
+        L.call("affgw_resize_bilinear_fwd", x.data_ptr(), y.data_ptr(), L.dt(x), n, h, w, c, ho, wo, L.stream())
+        ctx.shape = (n, c, h, w, ho, wo)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        n, c, h, w, ho, wo = ctx.shape
+        dy = _dense_cl(dy)
+        dx = empty_cl(n, c, h, w, torch.float32, dy.device, zero=True)
+        L.call("affgw_resize_bilinear_bwd", dy.data_ptr(), dx.data_ptr(), L.dt(dy), n, h, w, c, ho, wo, L.stream())
+        return dx, None, None
+
+
+def resize_bilinear(x, ho, wo):
+    return _ResizeBilinear.apply(x, ho, wo)
+
+
+class _AddAct(Function):
+    """act(a + b): `out += residual; out = relu(out)` of the ResNet blocks."""
+
+    @staticmethod
+    def forward(ctx, a, b, act):
+        a = _dense_cl(a)
+        b = _dense_cl(b, a.dtype)
+        y = torch.empty_like(a)
+        L.call("affgw_add_act", a.data_ptr(), b.data_ptr(), y.data_ptr(), L.dt(a), a.numel(), L.ACT[act], L.stream())
+        ctx.act = act
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (y,) = ctx.saved_tensors
+        dy = _dense_cl(dy, y.dtype)
+        dz = torch.empty_like(y)
+        L.call("affgw_act_bwd", dy.data_ptr(), y.data_ptr(), dz.data_ptr(), L.dt(y), y.numel(), L.ACT[ctx.act], L.stream())
+        return dz, dz, None
+
+
+def add_act(a, b, act="relu"):
+    return _AddAct.apply(a, b, act)
+
+
 class _AvgPool3s2Reflect(Function):
     @staticmethod
     def forward(ctx, x):

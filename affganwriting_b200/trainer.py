@@ -12,8 +12,8 @@ from .parallel import GradientReducer, broadcast_module
 
 class Trainer:
     def __init__(self, num_writers=500, lr_gen=1e-4, lr_dis=1e-4, lr_cla=1e-5, device=None, skip_unused_wgrad=True,
-                 bucket_bytes=None):
-        self.model = ConTranModel(num_writers, oov=True, device=device)
+                 bucket_bytes=None, encoder=None):
+        self.model = ConTranModel(num_writers, oov=True, device=device, encoder=encoder)
         m = self.model
         # main_run.py:275-278: Adam over filter(requires_grad, parameters()) with default betas / eps
         self.cla_opt = torch.optim.Adam([p for p in m.cla.parameters() if p.requires_grad], lr=lr_cla)

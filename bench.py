@@ -162,6 +162,8 @@ def main():
     ap.add_argument("--impl", default="affgw", choices=["affgw", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--encoder", default="vgg", choices=["vgg", "resnet18", "resnet50"],
+                    help="style encoder: vgg = configs[1] (default, the headline), resnet18 = configs[2]")
     ap.add_argument("--quick", action="store_true", help="timed steps only (no e2e / generation / CPU legs): the command ncu profiles")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "affgw" else args.warmup
@@ -189,7 +191,7 @@ def main():
 
     A.set_precision("bf16")
     torch.manual_seed(0)
-    trainer = Trainer(num_writers=500, device=dev)
+    trainer = Trainer(num_writers=500, device=dev, encoder=None if args.encoder == "vgg" else args.encoder)
     B = args.batch
     host = synthetic_batch(B, NUM_CHANNEL, seed=1234 + rank)
     host = tuple(t.pin_memory() if torch.is_tensor(t) else t for t in host)
@@ -302,7 +304,9 @@ def main():
         "metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic",
-        "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
+        "config": {"workload": WORKLOAD if args.encoder == "vgg" else WORKLOAD.replace(
+                       "configs[1]", "configs[2] (%s style encoder)" % args.encoder),
+                   "encoder": args.encoder, "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
                    "l2": "inputs larger than L2: 177 MB of style images are re-read every step (L2 is 126 MB)",
                    "samples_per_sec": value * B},
         "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 12,
@@ -311,12 +315,13 @@ def main():
         "clocks": clocks.summary(),
         "roofline": roofline,
         "kernels": kernels,
-        "step_tflops": {"algorithmic_tflop_per_step": STEP_GFLOP_PER_SAMPLE * B / 1e3,
-                        "achieved_tflops": STEP_GFLOP_PER_SAMPLE * B / 1e3 / (ms_step / 1e3),
-                        "frac_of_peak": STEP_GFLOP_PER_SAMPLE * B / 1e3 / (ms_step / 1e3) / tf_peak},
+        "step_tflops": None if args.encoder != "vgg" else {
+            "algorithmic_tflop_per_step": STEP_GFLOP_PER_SAMPLE * B / 1e3,
+            "achieved_tflops_per_gpu": STEP_GFLOP_PER_SAMPLE * B / 1e3 / (ms_step / 1e3),
+            "frac_of_peak": STEP_GFLOP_PER_SAMPLE * B / 1e3 / (ms_step / 1e3) / tf_peak},
         "cpu_baseline": cpu_baseline,
         "extra": {"gen_images_per_sec": gen_img_s, "gen_batch_per_gpu": B, "gen_ms_per_batch": ms_gen,
-                  "gen_frac_of_peak": 62.17e-3 * gen_img_s / tf_peak},
+                  "gen_frac_of_peak": None if args.encoder != "vgg" else 62.17e-3 * gen_img_s / world / tf_peak},
     }
     print(json.dumps(line), flush=True)
     if world > 1:

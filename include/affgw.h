@@ -141,6 +141,14 @@ int affgw_avgpool3s2_fwd(const void* x, void* y, int dtype, int N, int H, int W,
 int affgw_avgpool3s2_bwd(const void* dy, void* dx, int dtype, int N, int H, int W, int C, void* stream);
 int affgw_resize_nearest_fwd(const void* x, void* y, int dtype, int N, int H, int W, int C, int Ho, int Wo, void* stream);
 int affgw_resize_nearest_bwd(const void* dy, void* dx, int dtype, int N, int H, int W, int C, int Ho, int Wo, void* stream);
+/* torchvision ResNet encoders (modules_tro.py:464-533, modules_tro2.py:447-516): nn.MaxPool2d(3, 2, 1) of the stem,
+ * F.interpolate(mode="bilinear", align_corners=False) of the last map (dx fp32, zeroed by the caller),
+ * out = act(a + b) for the residual tails */
+int affgw_maxpool3s2_fwd(const void* x, void* y, int dtype, int N, int H, int W, int C, void* stream);
+int affgw_maxpool3s2_bwd(const void* dy, const void* x, void* dx, int dtype, int N, int H, int W, int C, void* stream);
+int affgw_resize_bilinear_fwd(const void* x, void* y, int dtype, int N, int H, int W, int C, int Ho, int Wo, void* stream);
+int affgw_resize_bilinear_bwd(const void* dy, float* dx, int dtype, int N, int H, int W, int C, int Ho, int Wo, void* stream);
+int affgw_add_act(const void* a, const void* b, void* out, int dtype, long long n, int act, void* stream);
 
 /* ---- iAFF pieces (blocks.py:286-299) ---------------------------------------------------------------------- */
 /* y = x*w + r*(1-w), w = sigmoid(xl + xg[n,c]) */

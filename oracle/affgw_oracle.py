@@ -302,6 +302,48 @@ def image_encoder(x, sd, prefix="enc_image."):
 # ----------------------------------------------------------------------------------------------
 # text encoder, mix, decoder, generator (modules_tro.py:208-317, 586-607)
 # ----------------------------------------------------------------------------------------------
+RESNET_PLAN = {"resnet18": ("basic", (2, 2, 2, 2), (64, 64, 128, 256, 512)),
+               "resnet50": ("bottleneck", (3, 4, 6, 3), (64, 256, 512, 1024, 2048))}
+
+
+def resnet_encoder(x, sd, prefix="enc_image.", arch="resnet50", training=True, stats=None):
+    """modules_tro.py:464-533 (ResNet-50, the encoder active in the reference's GenModel_FC) and modules_tro2.py:447-516
+    (ResNet-18): torchvision ResNet trunk - conv7x7/s2 + BN + ReLU (feat1), MaxPool2d(3, 2, 1), four stages of
+    BasicBlock / Bottleneck (feat2..feat5; stride on conv1 of a BasicBlock, on conv2 of a Bottleneck) - then 1x1
+    `reduce_layers` to 512 channels and a bilinear (align_corners=False) resize of the last map to (8, 27)."""
+    kind, depths, _ = RESNET_PLAN[arch]
+    m = prefix + "model."
+
+    def bn(t, name, relu=False):
+        t = batch_norm(t, sd, name, training, stats)
+        return q(torch.relu(t)) if relu else q(t)
+
+    x = q(x)
+    x = bn(q(_conv(x, sd[m + "conv1.weight"], None, stride=2, padding=3)), m + "bn1.", relu=True)
+    feats = [x]
+    x = F.max_pool2d(x, 3, 2, 1)
+    for li, depth in enumerate(depths, start=1):
+        for bi in range(depth):
+            b = f"{m}layer{li}.{bi}."
+            stride = 2 if (li > 1 and bi == 0) else 1
+            identity = x
+            if kind == "basic":
+                out = bn(q(_conv(x, sd[b + "conv1.weight"], None, stride=stride, padding=1)), b + "bn1.", relu=True)
+                out = bn(q(_conv(out, sd[b + "conv2.weight"], None, padding=1)), b + "bn2.")
+            else:
+                out = bn(q(_conv(x, sd[b + "conv1.weight"], None)), b + "bn1.", relu=True)
+                out = bn(q(_conv(out, sd[b + "conv2.weight"], None, stride=stride, padding=1)), b + "bn2.", relu=True)
+                out = bn(q(_conv(out, sd[b + "conv3.weight"], None)), b + "bn3.")
+            if b + "downsample.0.weight" in sd:
+                identity = bn(q(_conv(x, sd[b + "downsample.0.weight"], None, stride=stride)), b + "downsample.1.")
+            x = q(torch.relu(out + identity))
+        feats.append(x)
+    results = [q(_conv(f, sd[f"{prefix}reduce_layers.{i}.weight"], sd[f"{prefix}reduce_layers.{i}.bias"]))
+               for i, f in enumerate(feats)]
+    results[-1] = F.interpolate(results[-1], size=(8, 27), mode="bilinear", align_corners=False)
+    return results
+
+
 def text_encoder(label, f_xs_shape, sd, prefix="enc_text.", training=True, stats=None):
     """modules_tro.py:285-317 -> (adain params [B,4096], content map [B,512,h,w])."""
     emb = q(sd[prefix + "embed.weight"][label])                        # b, t, 64

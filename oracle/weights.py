@@ -55,3 +55,12 @@ def make_state(spec, seed=0):
 def spec_of(module_or_state):
     sd = module_or_state.state_dict() if hasattr(module_or_state, "state_dict") else module_or_state
     return {k: list(v.shape) for k, v in sd.items()}
+
+
+def alias_extractor(sd):
+    """torchvision-ResNet encoders: `extractor.*` (the fx GraphModule) shares its tensors with `model.*` in the reference
+    (modules_tro.py:503), so a state built key by key must carry identical values under both prefixes."""
+    for k in list(sd):
+        if k.startswith("extractor.") and "model." + k[len("extractor."):] in sd:
+            sd[k] = sd["model." + k[len("extractor."):]]
+    return sd

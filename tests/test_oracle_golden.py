@@ -112,3 +112,26 @@ def test_train_mode_batch_of_one_raises(specs):
     batch = O.synthetic_batch(1, 15)
     with pytest.raises(ValueError):
         O.text_encoder(batch["label_xt"], (1, 512, 8, 27), sd, "enc_text.")
+
+
+@pytest.mark.parametrize("arch", ["resnet18", "resnet50"])
+def test_resnet_encoder_oracle_matches_reference_fixture(arch, golden):
+    """the oracle's torchvision-ResNet encoder against the fp64 run of the reference class
+    (tests/golden/resnet_enc.npz, written by oracle/make_golden_resnet.py)."""
+    g = golden("resnet_enc.npz")
+    spec = json.load(open(os.path.join(GOLDEN, "resnet_spec.json")))[arch]
+    rep = json.load(open(os.path.join(GOLDEN, "oracle_vs_reference_resnet.json")))
+    assert all(r["max_abs"] <= r["tol"] for r in rep) and len(rep) >= 14
+    sd = {k: v.requires_grad_(v.is_floating_point()) for k, v in W.alias_extractor(W.make_state(spec)).items()}
+    x = O.synthetic_batch(2, 50)["tr_img"].requires_grad_()
+    stats = {}
+    res = O.resnet_encoder(x, sd, "", arch, True, stats)
+    sum(r.square().mean() for r in res).backward()
+    noise_f, noise_g = float(g[f"{arch}.noise.fwd"]), float(g[f"{arch}.noise.dx"])
+    for i, r in enumerate(res):
+        assert list(r.shape) == g[f"{arch}.result{i}.shape"].tolist()
+        assert rel_err(r[:, :8], _t(g[f"{arch}.result{i}.head"])) <= 1e-5 + 3 * noise_f
+    assert [int(v) for v in res[-1].shape] == [2, 512, 8, 27]
+    assert abs(float(x.grad.norm()) / float(g[f"{arch}.dx.norm"]) - 1) <= 1e-4 + 3 * noise_g
+    assert int(stats["model.layer3.1.bn1.num_batches_tracked"]) == 1
+    assert rel_err(stats["model.bn1.running_mean"], _t(g[f"{arch}.post.model.bn1.running_mean"])) <= 1e-5
