@@ -235,6 +235,13 @@ class _WeightCache:
         return ent[2]
 
 
+def clear_weight_cache(module):
+    """Drop every packed operand copy of `module`'s parameters.  Trainer calls this before capturing CUDA graphs so that
+    each graph re-packs the weights it reads instead of pointing at a copy an earlier eager iteration made."""
+    for p in module.parameters():
+        p.__dict__.pop("_affgw_packed", None)
+
+
 def _w4(weight):
     return weight if weight.dim() == 4 else weight.view(weight.shape[0], weight.shape[1], 1, 1)
 

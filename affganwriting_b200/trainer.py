@@ -3,6 +3,12 @@ recogniser update: cla_update -> dis_update -> gen_update, each followed by the 
 the sub-network that was just differentiated and by its Adam step.
 
 torch.optim.Adam is used as-is (fused multi-tensor Adam is SURVEY.md §8(f).2, a "next" row).
+
+CUDA graphs.  One iteration is ~5000 small launches issued from Python (~27 us each, ~140 ms per iteration on the host),
+which is of the same order as the GPU time of the kernels themselves.  With `cuda_graph=True` the forward + backward of
+each of the three sub-steps is captured once (after a few eager iterations that run every lazy initialisation) and
+replayed from then on; the gradient exchange (NCCL) and the optimiser steps stay eager between the replays, so nothing
+that talks to another rank is ever inside a graph.  The batch is copied into static device tensors before each replay.
 """
 import torch
 
@@ -11,8 +17,10 @@ from .parallel import GradientReducer, broadcast_module
 
 
 class Trainer:
+    GRAPH_WARMUP = 3      # eager iterations before the capture
+
     def __init__(self, num_writers=500, lr_gen=1e-4, lr_dis=1e-4, lr_cla=1e-5, device=None, skip_unused_wgrad=True,
-                 bucket_bytes=None, encoder=None):
+                 bucket_bytes=None, encoder=None, cuda_graph=False):
         self.model = ConTranModel(num_writers, oov=True, device=device, encoder=encoder)
         m = self.model
         # main_run.py:275-278: Adam over filter(requires_grad, parameters()) with default betas / eps
@@ -22,24 +30,27 @@ class Trainer:
         kw = {} if bucket_bytes is None else {"bucket_bytes": bucket_bytes}
         self.red = {"cla": GradientReducer(m.cla.parameters(), **kw), "dis": GradientReducer(m.dis.parameters(), **kw),
                     "gen": GradientReducer(m.gen.parameters(), **kw)}
+        self.opt = {"cla": self.cla_opt, "dis": self.dis_opt, "gen": self.gen_opt}
         # the reference computes dis / cla weight gradients inside gen_update and throws them away at the next
         # zero_grad (main_run.py:148-163); skipping them changes nothing observable
         self.skip_unused_wgrad = skip_unused_wgrad
+        self.cuda_graph = bool(cuda_graph)
+        self._graphs = None           # {name: (CUDAGraph, static outputs)}
+        self._static_in = None
+        self._eager_steps = 0
+        self._side = None
+        self.graph_launches = 0       # libaffgw launches recorded in the three graphs (= launches per replayed iteration)
         broadcast_module(m)
 
-    def train_step(self, batch, epoch=0):
+    # ------------------------------------------------------------------------------------------------ sub-steps
+    def _fwd_bwd(self, name, batch, epoch):
+        """zero_grad + forward + backward of one sub-step; returns its loss tensors."""
         m = self.model
-        self.cla_opt.zero_grad()
-        l_cla = m(batch, epoch, "cla_update")
-        self.red["cla"].reduce()
-        self.cla_opt.step()
-
-        self.dis_opt.zero_grad()
-        l_dis = m(batch, epoch, "dis_update")
-        self.red["dis"].reduce()
-        self.dis_opt.step()
-
-        self.gen_opt.zero_grad()
+        self.opt[name].zero_grad()
+        if name == "cla":
+            return (m(batch, epoch, "cla_update"),)
+        if name == "dis":
+            return (m(batch, epoch, "dis_update"),)
         frozen = []
         if self.skip_unused_wgrad:
             for p in list(m.dis.parameters()) + list(m.cla.parameters()):
@@ -51,7 +62,79 @@ class Trainer:
         finally:
             for p in frozen:
                 p.requires_grad_(True)
-        self.red["gen"].reduce()
-        self.gen_opt.step()
+        return (l_total, l_dis_g, l_cla_g)
+
+    def _finish(self, name):
+        self.red[name].reduce()
+        self.opt[name].step()
+
+    @staticmethod
+    def _pack(outs):
+        (l_cla,), (l_dis,), (l_total, l_dis_g, l_cla_g) = outs["cla"], outs["dis"], outs["gen"]
         return {"cla": l_cla.detach(), "dis": l_dis.detach(), "gen": l_total.detach(), "gen_dis": l_dis_g.detach(),
                 "gen_cla": l_cla_g.detach()}
+
+    def train_step_eager(self, batch, epoch=0):
+        outs = {}
+        for name in ("cla", "dis", "gen"):
+            outs[name] = self._fwd_bwd(name, batch, epoch)
+            self._finish(name)
+        return self._pack(outs)
+
+    # ------------------------------------------------------------------------------------------------ graph replay
+    def train_step(self, batch, epoch=0):
+        if not self.cuda_graph:
+            return self.train_step_eager(batch, epoch)
+        if self._graphs is None:
+            if self._eager_steps < self.GRAPH_WARMUP:
+                # eager iterations on the stream the graphs will be captured on, so that the autograd nodes that outlive an
+                # iteration (AccumulateGrad) belong to that stream
+                self._eager_steps += 1
+                if self._side is None:
+                    self._side = torch.cuda.Stream(device=self.model.device_)
+                self._side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(self._side):
+                    out = self.train_step_eager(batch, epoch)
+                torch.cuda.current_stream().wait_stream(self._side)
+                return out
+            return self._capture(batch, epoch)      # the capture pass itself runs this iteration
+        for dst, src in zip(self._static_in, batch):
+            if torch.is_tensor(dst) and dst.data_ptr() != src.data_ptr():
+                dst.copy_(src, non_blocking=True)
+        outs = {}
+        for name in ("cla", "dis", "gen"):
+            graph, static_out, grads = self._graphs[name]
+            graph.replay()
+            for p, g in grads:                      # an eager iteration in between may have re-pointed .grad
+                p.grad = g
+            outs[name] = static_out
+            self._finish(name)
+        self.model.iter_num += 1
+        return self._pack(outs)
+
+    def _capture(self, batch, epoch):
+        from . import _lib, ops
+        dev = self.model.device_
+        self._static_in = tuple(t.to(dev).clone() if torch.is_tensor(t) else t for t in batch)
+        torch.cuda.synchronize()
+        ops.clear_weight_cache(self.model)          # every packed weight a graph reads must be packed inside a graph
+        pool = torch.cuda.graph_pool_handle()       # the three graphs always replay in capture order: one shared pool
+        graphs, outs = {}, {}
+        self.graph_launches = 0
+        n0 = _lib.launch_count()
+        for name in ("cla", "dis", "gen"):
+            self.opt[name].zero_grad(set_to_none=True)      # captured backward WRITES fresh .grad tensors (no accumulation)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, pool=pool, stream=self._side):
+                out = self._fwd_bwd(name, self._static_in, epoch)
+            n_captured = _lib.launch_count() - n0
+            g.replay()                              # run the sub-step for real: this call is one full training iteration
+            grads = [(p, p.grad) for grp in self.opt[name].param_groups for p in grp["params"] if p.grad is not None]
+            graphs[name] = (g, out, grads)
+            outs[name] = out
+            self._finish(name)
+            self.graph_launches += n_captured
+            n0 = _lib.launch_count()
+        torch.cuda.synchronize()
+        self._graphs = graphs                       # (iter_num was advanced by the captured gen_update's Python side)
+        return self._pack(outs)

@@ -164,6 +164,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--encoder", default="vgg", choices=["vgg", "resnet18", "resnet50"],
                     help="style encoder: vgg = configs[1] (default, the headline), resnet18 = configs[2]")
+    ap.add_argument("--no-graph", action="store_true", help="issue every launch from Python instead of replaying a CUDA graph")
     ap.add_argument("--quick", action="store_true", help="timed steps only (no e2e / generation / CPU legs): the command ncu profiles")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "affgw" else args.warmup
@@ -191,7 +192,8 @@ def main():
 
     A.set_precision("bf16")
     torch.manual_seed(0)
-    trainer = Trainer(num_writers=500, device=dev, encoder=None if args.encoder == "vgg" else args.encoder)
+    trainer = Trainer(num_writers=500, device=dev, encoder=None if args.encoder == "vgg" else args.encoder,
+                      cuda_graph=not args.no_graph)
     B = args.batch
     host = synthetic_batch(B, NUM_CHANNEL, seed=1234 + rank)
     host = tuple(t.pin_memory() if torch.is_tensor(t) else t for t in host)
@@ -225,6 +227,9 @@ def main():
         losses = trainer.train_step(dev_batch)
         return float(losses["gen"].item()) + float(losses["dis"].item()) + float(losses["cla"].item())
 
+    if not args.no_graph:                                # eager iterations + CUDA-graph capture, before the warm-up steps
+        for _ in range(Trainer.GRAPH_WARMUP + 1):
+            step_resident()
     for _ in range(args.warmup):
         step_resident()
     A.check_device_errors()
@@ -234,6 +239,8 @@ def main():
         n0 = A.launch_count()
         ms_total = timed(step_resident, args.steps)
         launches = A.launch_count() - n0
+    if trainer.graph_launches:                           # replayed launches are not seen by the library's launch counter
+        launches += trainer.graph_launches * args.steps
     ms_step = ms_total / args.steps
     value = world / (ms_step / 1e3)                       # whole-job steps/s: every rank completes one step per step time
 
@@ -246,7 +253,7 @@ def main():
         return
     # ---- instrumented pass: per-launch CUDA events (on the launching stream) around every convolution kernel
     ops.start_kernel_timing()
-    ms_instr = timed(step_resident, 2)
+    ms_instr = timed(lambda: trainer.train_step_eager(resident), 2)      # eager: events cannot sit inside a graph replay
     kern = ops.stop_kernel_timing()
     instr_steps = 2
 
@@ -307,6 +314,7 @@ def main():
         "config": {"workload": WORKLOAD if args.encoder == "vgg" else WORKLOAD.replace(
                        "configs[1]", "configs[2] (%s style encoder)" % args.encoder),
                    "encoder": args.encoder, "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
+                   "cuda_graph": bool(trainer.graph_launches),
                    "l2": "inputs larger than L2: 177 MB of style images are re-read every step (L2 is 126 MB)",
                    "samples_per_sec": value * B},
         "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 12,

@@ -286,3 +286,46 @@ def test_full_size_properties(specs):
         assert float((r_all[2:3].float() - r_one.float()).abs().max()) <= 0.07
     finally:
         A.set_precision("fp32")
+
+
+def test_cuda_graph_replay_matches_eager_iterations(specs):
+    """Trainer(cuda_graph=True) - three captured sub-steps, eager gradient exchange + Adam in between - must walk the
+    same trajectory as the eager trainer (main_run.py:146-167 order).  The trajectory itself is chaotic with respect to the
+    order of the fp32 atomics in the statistics / weight-gradient reductions (two EAGER trainers drift apart in the 4th
+    digit of the generator loss within three iterations), so the bound is the eager-vs-eager drift measured alongside."""
+    from affganwriting_b200.trainer import Trainer
+    import bench
+    A.set_precision("bf16")
+    try:
+        dev = torch.device("cuda", 0)
+        batch = tuple(t.cuda() if torch.is_tensor(t) else t for t in bench.synthetic_batch(4, 50, 7))
+        torch.manual_seed(0)
+        a = Trainer(num_writers=500, device=dev)
+        b = Trainer(num_writers=500, device=dev)
+        g = Trainer(num_writers=500, device=dev, cuda_graph=True)
+        b.model.load_state_dict(a.model.state_dict())
+        g.model.load_state_dict(a.model.state_dict())
+        drift_ee = drift_eg = 0.0
+        for it in range(7):
+            la, lb, lg = a.train_step(batch), b.train_step(batch), g.train_step(batch)
+            for k in la:
+                drift_ee = max(drift_ee, abs(float(la[k]) - float(lb[k])))
+                drift_eg = max(drift_eg, abs(float(la[k]) - float(lg[k])))
+            if it < 2:          # before the divergence has had time to grow, all three agree tightly
+                assert all(abs(float(la[k]) - float(lg[k])) <= 1e-4 * max(1.0, abs(float(la[k]))) for k in la), it
+        assert g.graph_launches > 1000 and g._graphs is not None and g._eager_steps == Trainer.GRAPH_WARMUP
+
+        def weight_drift(x, y):
+            sx, sy = x.model.state_dict(), y.model.state_dict()
+            for k, v in sx.items():
+                if not v.is_floating_point():
+                    assert torch.equal(v, sy[k]), k                      # num_batches_tracked
+            return max(float((v - sy[k]).abs().max()) for k, v in sx.items() if v.is_floating_point())
+        w_ee, w_eg = weight_drift(a, b), weight_drift(a, g)
+        print(f"\nafter 7 iterations: loss drift eager/eager {drift_ee:.2e}, eager/graph {drift_eg:.2e}; "
+              f"weight+buffer drift eager/eager {w_ee:.2e}, eager/graph {w_eg:.2e}")
+        assert drift_eg <= 4 * drift_ee + 1e-4
+        assert w_eg <= 4 * w_ee + 1e-4
+        assert a.model.iter_num == g.model.iter_num
+    finally:
+        A.set_precision("fp32")
