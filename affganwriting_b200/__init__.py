@@ -9,9 +9,9 @@ Public surface mirrors the reference's Python modules for this path:
 All arithmetic runs in csrc/libaffgw.so (C ABI in include/affgw.h); there is no CPU or PyTorch fallback.
 """
 from . import _lib
-from .ops import check_device_errors, force_simt, precision, set_precision  # noqa: F401
+from .ops import check_device_errors, force_simt, precision, set_precision, weights_updated  # noqa: F401
 
-__all__ = ["set_precision", "precision", "force_simt", "check_device_errors", "launch_count", "lib_path"]
+__all__ = ["set_precision", "precision", "force_simt", "check_device_errors", "weights_updated", "launch_count", "lib_path"]
 
 
 def launch_count():

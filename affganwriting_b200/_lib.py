@@ -51,7 +51,7 @@ SIGNATURES = {
     "affgw_conv_tc_layout": [_D, _I],
     "affgw_conv_pos_frames": [_D, C.POINTER(PosFrame), C.POINTER(PosFrame)],
     "affgw_position_planes_bytes": [C.POINTER(PosFrame), _I],
-    "affgw_split_positions": [_P, _I, _P, C.POINTER(PosFrame), _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
+    "affgw_split_positions": [_P, _I, _P, C.POINTER(PosFrame), _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P],
     "affgw_conv_tc_prefer_shift": [_I],
     "affgw_operand_planes_bytes": [_L, _I, _I],
     "affgw_split_planes": [_P, _I, _P, _L, _I, _I, _I, _I, _I, _P],

@@ -31,7 +31,7 @@ int split_planes(const void* x, int x_dt, void* planes, long long rows, int C, i
 int conv_shift_ok(const ConvGeom& g);
 void conv_shift_frame(const ConvGeom& g, int channels, PosFrame& f);
 int split_positions(const void* src, int dt, void* planes, const PosFrame& f, int Hs, int Ws, int C, int pitch, int up, int oy0,
-                    int ox0, int pad_mode, int pre_act, int passes, cudaStream_t st);
+                    int ox0, int pad_mode, int pre_act, int passes, float* colsum, cudaStream_t st);
 int conv_pos_tc(const void* x_planes, const PosFrame& f, const void* w_packed, const float* bias, const void* addend, void* y,
                 int K, int q_shift, int oy0, int ox0, int OH, int OW, int Cout, int out_pitch, int post_act, int passes,
                 cudaStream_t st);
@@ -324,7 +324,7 @@ long long affgw_position_planes_bytes(const affgw_pos_frame* f, int passes) {
     return (long long)(passes == 3 ? 2 : 1) * f->G * f->QA * 16;
 }
 int affgw_split_positions(const void* src, int dtype, void* planes, const affgw_pos_frame* f, int Hs, int Ws, int C, int pitch,
-                          int upsample, int oy0, int ox0, int pad_mode, int pre_act, int passes, void* stream) {
+                          int upsample, int oy0, int ox0, int pad_mode, int pre_act, int passes, float* colsum, void* stream) {
     AFFGW_CHECK(src && planes && f && dt_ok(dtype) && passes_ok(passes), "split_positions: bad argument");
     AFFGW_CHECK(Hs > 0 && Ws > 0 && C > 0 && pitch >= C && (upsample == 1 || upsample == 2), "split_positions: bad source");
     AFFGW_CHECK(pad_mode >= 0 && pad_mode <= 2 && pre_act >= 0 && pre_act <= 3, "split_positions: bad mode");
@@ -332,8 +332,10 @@ int affgw_split_positions(const void* src, int dtype, void* planes, const affgw_
     if (pad_mode == PAD_REFLECT)
         AFFGW_CHECK(oy0 < Hs * upsample && ox0 < Ws * upsample && f->Hp - oy0 - Hs * upsample < Hs * upsample &&
                         f->Wp - ox0 - Ws * upsample < Ws * upsample, "split_positions: reflect pad >= input extent");
+    AFFGW_CHECK(colsum == nullptr || (upsample == 1 && pad_mode == PAD_ZERO && pre_act == ACT_NONE),
+                "split_positions: the fused column sum is for dY planes (no padding copies, no activation)");
     return split_positions(src, dtype, planes, import_frame(f), Hs, Ws, C, pitch, upsample, oy0, ox0, pad_mode, pre_act, passes,
-                           S(stream));
+                           colsum, S(stream));
 }
 
 long long affgw_conv2d_dgrad_ws_bytes(const affgw_conv_desc* d) {

@@ -318,65 +318,99 @@ __global__ void pack_weight_shift_kernel(const float* __restrict__ w, bf16* __re
 template <typename T, int TG>
 __global__ void __launch_bounds__(256)
 split_positions_kernel(const T* __restrict__ src, bf16* __restrict__ planes, int N, int Hs, int Ws, int C, int pitch, int up,
-                       int oy0, int ox0, int pad_mode, int pre_act, int Hp, int Wp, int G, int lead, int QA, int npl) {
-    constexpr int TP = 1024 / TG;                     // positions per block: the tile is always 1024 (position, group) items
+                       int oy0, int ox0, int pad_mode, int pre_act, int Hp, int Wp, int G, int lead, int QA, int npl,
+                       float* __restrict__ colsum) {
+    constexpr int TP = 1024 / TG;                     // positions per tile: a tile is always 1024 (position, group) items
     __shared__ uint4 tile[2][TG * (TP + 1)];          // [plane][group][position], +1 column against bank conflicts
+    __shared__ float red[8][TG * 8];
     const int tid = threadIdx.x;
-    const int p0 = blockIdx.x * TP;                   // stored position (lead included)
     const int g0 = blockIdx.y * TG;
     const int Q = N * Hp * Wp;
     const bool vec = (pitch % 8 == 0) && (C % 8 == 0);
+    const int n_tiles = (QA + TP - 1) / TP;
+    float csum[8];                                    // per-channel sums of this thread's items (bias gradient)
 #pragma unroll
-    for (int it = 0; it < 4; ++it) {
-        const int item = tid + 256 * it;
-        const int gl = item % TG, pi = item / TG;
-        const int g = g0 + gl;
-        const int q = p0 + pi - lead;
-        float v[8];
+    for (int i = 0; i < 8; ++i) csum[i] = 0.f;
+    for (int tx = blockIdx.x; tx < n_tiles; tx += gridDim.x) {
+        const int p0 = tx * TP;                       // stored position (lead included)
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = 0.f;
-        if (g * 8 < C && q >= 0 && q < Q) {
-            const int xp = q % Wp;
-            const int r = q / Wp;
-            const int yp = r % Hp;
-            const int n = r / Hp;
-            const int sy = map_coord(yp - oy0, Hs * up, pad_mode, up, 1);
-            const int sx = map_coord(xp - ox0, Ws * up, pad_mode, up, 1);
-            if (sy >= 0 && sx >= 0) {
-                const T* sp = src + ((size_t)((n * Hs + sy) * Ws + sx) * pitch + g * 8);
-                if (vec) {
-                    ld8(sp, v);
-                } else {
+        for (int it = 0; it < 4; ++it) {
+            const int item = tid + 256 * it;
+            const int gl = item % TG, pi = item / TG;
+            const int g = g0 + gl;
+            const int q = p0 + pi - lead;
+            float v[8];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) v[i] = (g * 8 + i < C) ? to_f(sp[i]) : 0.f;
+            for (int i = 0; i < 8; ++i) v[i] = 0.f;
+            if (g * 8 < C && q >= 0 && q < Q) {
+                const int xp = q % Wp;
+                const int r = q / Wp;
+                const int yp = r % Hp;
+                const int n = r / Hp;
+                const int sy = map_coord(yp - oy0, Hs * up, pad_mode, up, 1);
+                const int sx = map_coord(xp - ox0, Ws * up, pad_mode, up, 1);
+                if (sy >= 0 && sx >= 0) {
+                    const T* sp = src + ((size_t)((n * Hs + sy) * Ws + sx) * pitch + g * 8);
+                    if (vec) {
+                        ld8(sp, v);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) v[i] = (g * 8 + i < C) ? to_f(sp[i]) : 0.f;
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v[i] = act_apply(v[i], pre_act);
                 }
+            }
 #pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] = act_apply(v[i], pre_act);
+            for (int i = 0; i < 8; ++i) csum[i] += v[i];
+            uint4 hi, lo;
+            __nv_bfloat162* hh = reinterpret_cast<__nv_bfloat162*>(&hi);
+            __nv_bfloat162* ll = reinterpret_cast<__nv_bfloat162*>(&lo);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                hh[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+                const float2 f = __bfloat1622float2(hh[i]);
+                ll[i] = __floats2bfloat162_rn(v[2 * i] - f.x, v[2 * i + 1] - f.y);
+            }
+            tile[0][gl * (TP + 1) + pi] = hi;
+            tile[1][gl * (TP + 1) + pi] = lo;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+            const int item = tid + 256 * it;
+            const int pi = item % TP, gl = item / TP;
+            const int g = g0 + gl;
+            const int p = p0 + pi;
+            if (g < G && p < QA) {
+                uint4* dst = reinterpret_cast<uint4*>(planes) + ((size_t)g * QA + p);
+                dst[0] = tile[0][gl * (TP + 1) + pi];
+                if (npl == 2) dst[(size_t)G * QA] = tile[1][gl * (TP + 1) + pi];
             }
         }
-        uint4 hi, lo;
-        __nv_bfloat162* hh = reinterpret_cast<__nv_bfloat162*>(&hi);
-        __nv_bfloat162* ll = reinterpret_cast<__nv_bfloat162*>(&lo);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            hh[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-            const float2 f = __bfloat1622float2(hh[i]);
-            ll[i] = __floats2bfloat162_rn(v[2 * i] - f.x, v[2 * i + 1] - f.y);
-        }
-        tile[0][gl * (TP + 1) + pi] = hi;
-        tile[1][gl * (TP + 1) + pi] = lo;
+        __syncthreads();
     }
-    __syncthreads();
+    if (colsum != nullptr) {
+        // db[c] = sum over positions of dY[., c] (the conv bias gradient, fused here because this kernel reads dY anyway).
+        // Every item of a thread has the same channel group (256 % TG == 0): reduce the lanes of a warp that share it,
+        // then the 8 warps through shared memory, then ONE atomic per (block, channel).
 #pragma unroll
-    for (int it = 0; it < 4; ++it) {
-        const int item = tid + 256 * it;
-        const int pi = item % TP, gl = item / TP;
-        const int g = g0 + gl;
-        const int p = p0 + pi;
-        if (g < G && p < QA) {
-            uint4* dst = reinterpret_cast<uint4*>(planes) + ((size_t)g * QA + p);
-            dst[0] = tile[0][gl * (TP + 1) + pi];
-            if (npl == 2) dst[(size_t)G * QA] = tile[1][gl * (TP + 1) + pi];
+        for (int off = TG; off < 32; off <<= 1)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) csum[i] += __shfl_xor_sync(0xffffffffu, csum[i], off);
+        const int lane = tid & 31, warp = tid >> 5;
+        if (lane < TG) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) red[warp][lane * 8 + i] = csum[i];
+        }
+        __syncthreads();
+        for (int j = tid; j < TG * 8; j += 256) {
+            // with TG == 32 a warp's 32 lanes hold 32 different groups, but lane -> group is tid % TG for every warp
+            float t = 0.f;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) t += red[w][j];
+            const int c = g0 * 8 + j;
+            if (c < C) atomicAdd(colsum + c, t);
         }
     }
 }
@@ -429,11 +463,13 @@ int launch_shift(const ShArgs& args, int smem_bytes, cudaStream_t st) {
 // Is the forward convolution g a position-space convolution?  One rule for forward, dgrad and wgrad so that the operand
 // planes of a layer are built once.
 int conv_shift_ok(const ConvGeom& g) {
-    if (g.stride != 1 || g.zi != 1 || g.KH != g.KW || g.KH < 2 || g.KH > 7) return 0;
+    if (g.stride != 1 || g.zi != 1 || g.KH != g.KW || g.KH > 7) return 0;
+    // 1x1 filters have no tap reuse to exploit; only the thin ones (the 16/32-channel shortcuts of the discriminator at full
+    // resolution) come here, because the bulk-copy pipeline beats the per-thread gather of the im2col kernel for them
+    if (g.KH == 1 && (g.Cin > 64 || g.Cout > 64 || (long long)g.H * g.W < 1024)) return 0;
     const long long Hp = g.Hv + 2 * g.pad, Wp = g.Wv + 2 * g.pad;
     if (Hp - g.KH + 1 != g.Ho || Wp - g.KW + 1 != g.Wo) return 0;
-    // on tiny maps the padding positions (computed, then dropped) cost more than the window saves; 1x1 filters have no tap
-    // reuse to exploit: both stay on the im2col kernels
+    // on tiny maps the padding positions (computed, then dropped) cost more than the window saves: im2col kernels
     if (2 * Hp * Wp > 3LL * g.Ho * g.Wo) return 0;
     if ((long long)g.N * Hp * Wp + 8192 >= (1LL << 31) / 16) return 0;           // 32-bit position arithmetic
     // the forward tile is as wide as Cout allows, the dgrad tile as wide as Cin allows: both windows must fit
@@ -457,7 +493,7 @@ void conv_shift_frame(const ConvGeom& g, int channels, PosFrame& f) {
 }
 
 int split_positions(const void* src, int dt, void* planes, const PosFrame& f, int Hs, int Ws, int C, int pitch, int up, int oy0,
-                    int ox0, int pad_mode, int pre_act, int passes, cudaStream_t st) {
+                    int ox0, int pad_mode, int pre_act, int passes, float* colsum, cudaStream_t st) {
     const int npl = passes == 3 ? 2 : 1;
     if (f.QA >= (1LL << 31) || (long long)f.N * Hs * Ws >= (1LL << 31)) {
         affgw_set_error("split_positions: frame too large for 32-bit position arithmetic");
@@ -465,9 +501,9 @@ int split_positions(const void* src, int dt, void* planes, const PosFrame& f, in
     }
     const int QA = (int)f.QA;
 #define AFFGW_SPLIT(T, TGV)                                                                                               \
-    split_positions_kernel<T, TGV><<<dim3((unsigned)((QA + 1024 / TGV - 1) / (1024 / TGV)), (unsigned)((f.G + TGV - 1) / TGV)), \
+    split_positions_kernel<T, TGV><<<dim3((unsigned)min((QA + 1024 / TGV - 1) / (1024 / TGV), 148 * 8), (unsigned)((f.G + TGV - 1) / TGV)), \
                                      256, 0, st>>>((const T*)src, (bf16*)planes, f.N, Hs, Ws, C, pitch, up, oy0, ox0, pad_mode, \
-                                                   pre_act, f.Hp, f.Wp, f.G, f.lead, QA, npl)
+                                                   pre_act, f.Hp, f.Wp, f.G, f.lead, QA, npl, colsum)
     if (dt == AFFGW_F32) {
         if (f.G <= 2) AFFGW_SPLIT(float, 2);
         else if (f.G <= 4) AFFGW_SPLIT(float, 4);

@@ -76,6 +76,7 @@ struct TcArgs {
     void* y;
     ConvGeom g;                // g.Cin = stored channels of the planes (== pitch), g.Ktot = taps * g.Cin
     int KB, n_tiles;
+    int ksplit, kb_per_split;  // split of the k-block range over CTAs (tiny-M layers); partial sums are reduced with atomics
     long long total_tiles;
     int vec_ok;                // 16-column vector stores allowed (Cout % 16 == 0 and aligned pitch)
 };
@@ -165,8 +166,11 @@ conv_igemm_tcgen05_kernel(const __grid_constant__ TcArgs a) {
         constexpr int LAG = STAGES - 1;
         uint32_t it = 0;                  // k-block counter across tiles: stage = it % STAGES
         for (long long t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
-            const int nt = (int)(t % a.n_tiles);
-            const long long m0 = (t / a.n_tiles) * BM;
+            const int ks = (int)(t % a.ksplit);
+            const long long tmn = t / a.ksplit;
+            const int nt = (int)(tmn % a.n_tiles);
+            const long long m0 = (tmn / a.n_tiles) * BM;
+            const int kb0 = ks * a.kb_per_split, kb1 = min(KB, kb0 + a.kb_per_split);
             int vy0[8], vx0[8], nbase[8];
             bool mvalid[8];
 #pragma unroll
@@ -185,16 +189,20 @@ conv_igemm_tcgen05_kernel(const __grid_constant__ TcArgs a) {
                 nbase[i] = n * g.H * g.W;
             }
             const bf16* wt = a.w_tiles + (size_t)nt * KB * (NPL * BN * BK);
-            int ky = 0, kx = 0, c0 = 0;   // uniform-tap cursor
+            int ky = 0, kx = 0, c0 = 0;   // uniform-tap cursor, positioned at this split's first k-block
             int sy[8], sx[8];
             if (uniform_tap) {
+                const int tap0 = (kb0 * BK) / g.Cin;
+                c0 = kb0 * BK - tap0 * g.Cin;
+                ky = tap0 / g.KW;
+                kx = tap0 - ky * g.KW;
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    sy[i] = map_coord(vy0[i], g.Hv, g.pad_mode, g.up, g.zi);
-                    sx[i] = map_coord(vx0[i], g.Wv, g.pad_mode, g.up, g.zi);
+                    sy[i] = map_coord(vy0[i] + ky, g.Hv, g.pad_mode, g.up, g.zi);
+                    sx[i] = map_coord(vx0[i] + kx, g.Wv, g.pad_mode, g.up, g.zi);
                 }
             }
-            for (int kb = 0; kb < KB; ++kb, ++it) {
+            for (int kb = kb0; kb < kb1; ++kb, ++it) {
                 const int s = it % STAGES;
                 const uint32_t ph = (it / STAGES) & 1u;
                 mbar_wait(empty_bar(s), ph ^ 1u);
@@ -267,7 +275,9 @@ conv_igemm_tcgen05_kernel(const __grid_constant__ TcArgs a) {
                 mbar_wait(tmem_empty_bar(acc), acc_ph ^ 1u);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BN;
-                for (int kb = 0; kb < KB; ++kb, ++it) {
+                const int ks = (int)(t % a.ksplit);
+                const int nkb = min(KB, (ks + 1) * a.kb_per_split) - ks * a.kb_per_split;
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1u;
                     mbar_wait(full_bar(s), ph);
@@ -298,8 +308,11 @@ conv_igemm_tcgen05_kernel(const __grid_constant__ TcArgs a) {
         uint32_t tl = 0;
         for (long long t = blockIdx.x; t < a.total_tiles; t += gridDim.x, ++tl) {
             const uint32_t acc = tl & 1u, acc_ph = (tl >> 1) & 1u;
-            const int n0 = (int)(t % a.n_tiles) * BN;
-            const long long m = (t / a.n_tiles) * BM + q * 32 + lane;
+            const int ks = (int)(t % a.ksplit);
+            const long long tmn = t / a.ksplit;
+            const int n0 = (int)(tmn % a.n_tiles) * BN;
+            const long long m = (tmn / a.n_tiles) * BM + q * 32 + lane;
+            const bool first_split = ks == 0;
             mbar_wait(tmem_full_bar(acc), acc_ph);
             tc_fence_after();
 #pragma unroll 1
@@ -308,7 +321,23 @@ conv_igemm_tcgen05_kernel(const __grid_constant__ TcArgs a) {
                 if (nb >= g.Cout) break;                       // warp-uniform
                 uint32_t raw[16];
                 tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + (uint32_t)(j * 16), raw);
-                if (m < g.M) {
+                if (m < g.M && a.ksplit > 1) {
+                    // split k range: fp32 partial sums into the zeroed output; bias / addend ride with the first split
+                    if constexpr (sizeof(TO) == 4) {
+                        float* yr = reinterpret_cast<float*>(y) + m * g.out_pitch + nb;
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            if (nb + i < g.Cout) {
+                                float r = __uint_as_float(raw[i]);
+                                if (first_split) {
+                                    if (a.bias) r += __ldg(a.bias + nb + i);
+                                    if (addend) r += to_f(addend[m * g.out_pitch + nb + i]);
+                                }
+                                atomicAdd(yr + i, r);
+                            }
+                        }
+                    }
+                } else if (m < g.M) {
                     float v[16];
                     if (a.vec_ok) {
 #pragma unroll
@@ -479,7 +508,24 @@ int conv_fwd_tc(const void* x_planes, long long plane_stride, const void* w_tile
     a.g.Ktot = g.KH * g.KW * g.Cin;
     a.KB = (a.g.Ktot + BK - 1) / BK;
     a.n_tiles = (g.Cout + bn - 1) / bn;
-    a.total_tiles = ((g.M + BM - 1) / BM) * a.n_tiles;
+    const long long mn_tiles = ((g.M + BM - 1) / BM) * a.n_tiles;
+    // tiny-M layers (the 2x7 / 4x14 maps of the discriminator) give a handful of output tiles with a long k loop each:
+    // spread the k-blocks over the idle SMs
+    a.ksplit = 1;
+    a.kb_per_split = a.KB;
+    if (y_dt == AFFGW_F32 && g.post_act == ACT_NONE && mn_tiles <= 74 && a.KB >= 8) {
+        int want = (int)(148 / mn_tiles);
+        if (want > a.KB / 4) want = a.KB / 4;
+        if (want > 1) {
+            a.kb_per_split = (a.KB + want - 1) / want;
+            a.ksplit = (a.KB + a.kb_per_split - 1) / a.kb_per_split;
+        }
+    }
+    a.total_tiles = mn_tiles * a.ksplit;
+    if (a.ksplit > 1 && cudaMemsetAsync(y, 0, (size_t)g.M * g.out_pitch * sizeof(float), st) != cudaSuccess) {
+        affgw_set_error("conv_fwd_tc: memset failed");
+        return -2;
+    }
     const int esz = y_dt == AFFGW_F32 ? 4 : 2;
     a.vec_ok = (g.Cout % 16 == 0) && ((g.out_pitch * esz) % 16 == 0) && (((uintptr_t)y) % 16 == 0) &&
                (!addend || ((uintptr_t)addend) % 16 == 0);

@@ -12,6 +12,8 @@ from torch.autograd import Function
 
 from . import _lib as L  # noqa: N812
 
+import os as _os
+_FUSE_DB = _os.environ.get("AFFGW_FUSE_DB", "1") != "0"
 _state = {"mode": "fp32", "passes": 3, "force_simt": False, "simt_wgrad": False}
 _err_flag = {}
 _profile = {"records": None}
@@ -228,11 +230,22 @@ class _WeightCache:
     def get(weight, kind, builder):
         cache = weight.__dict__.setdefault("_affgw_packed", {})
         ent = cache.get(kind)
-        ver = weight._version
+        # autograd's version counter catches ordinary in-place updates; fused / multi-tensor optimiser kernels do not always
+        # bump it (torch.optim.Adam(fused=True) does not), so an explicit per-parameter epoch (weights_updated) is part of
+        # the key as well
+        ver = (weight._version, weight.__dict__.get("_affgw_epoch", 0))
         if ent is None or ent[0] != ver or ent[1] != weight.data_ptr():
             ent = (ver, weight.data_ptr(), builder())
             cache[kind] = ent
         return ent[2]
+
+
+def weights_updated(module_or_params):
+    """Tell the packed-operand cache that these parameters were modified in place by something autograd's version counter
+    does not see (a fused optimiser step, a raw-pointer copy).  Cheap: one integer per parameter."""
+    params = module_or_params.parameters() if hasattr(module_or_params, "parameters") else module_or_params
+    for p in params:
+        p.__dict__["_affgw_epoch"] = p.__dict__.get("_affgw_epoch", 0) + 1
 
 
 def clear_weight_cache(module):
@@ -298,14 +311,14 @@ def _pos_frames(d):
     return fx, fy
 
 
-def _split_positions(src, frame, hs, ws, c, pitch, up, origin, pad_mode, pre_act, passes):
+def _split_positions(src, frame, hs, ws, c, pitch, up, origin, pad_mode, pre_act, passes, colsum=None):
     """fp32 NHWC tensor -> planar position planes [1 or 2][G][QA][8] bf16 on the frame of a stride-1 convolution."""
     nbytes = L.lib().affgw_position_planes_bytes(C.byref(frame), passes)
     if nbytes <= 0:
         raise RuntimeError("affgw_position_planes_bytes: bad frame")
     planes = torch.empty(nbytes // 2, dtype=torch.bfloat16, device=src.device)
     L.call("affgw_split_positions", src.data_ptr(), L.dt(src), planes.data_ptr(), C.byref(frame), hs, ws, c, pitch, up, origin,
-           origin, L.PAD[pad_mode], L.ACT[pre_act], passes, L.stream())
+           origin, L.PAD[pad_mode], L.ACT[pre_act], passes, L.ptr(colsum), L.stream())
     return planes
 
 
@@ -411,19 +424,23 @@ class _Conv2d(Function):
         M = g["N"] * g["Ho"] * g["Wo"]
         cin, cout = g["Cin"], g["Cout"]
         db = dw = dx = None
+        use_tc = ctx.use_tc
+        # position-space layers: the bias gradient is summed by the kernel that splits dY into operand planes
+        fuse_db = use_tc and ctx.layout == L.WLAYOUT_SHIFT and (need_w or need_x) and _FUSE_DB
         if ctx.has_bias and need_b:
             db = torch.zeros(cout, dtype=torch.float32, device=dev)
-            L.call("affgw_colsum", dz.data_ptr(), L.F32, db.data_ptr(), M, cout, cout, st)
+            if not fuse_db:
+                L.call("affgw_colsum", dz.data_ptr(), L.F32, db.data_ptr(), M, cout, cout, st)
         fwd_cfg = cfg._replace(post_act="none")
         flops = 2.0 * M * cout * cin * g["KH"] * g["KW"]
-        use_tc = ctx.use_tc
         if use_tc and (need_w or need_x):
             cs, cso = _up8(cin), _up8(cout)
             if ctx.layout == L.WLAYOUT_SHIFT:
                 # dY on the forward convolution's position frame: one split feeds both dgrad and wgrad
                 d0 = _desc(g, fwd_cfg, cin, L.BF16, L.BF16, L.BF16, L.ALGO_TC, in_pitch=cs, out_pitch=cso, passes=passes)
                 _, fy = _pos_frames(d0)
-                dzp = _split_positions(dz, fy, g["Ho"], g["Wo"], cout, cout, 1, 0, "zero", "none", passes)
+                dzp = _split_positions(dz, fy, g["Ho"], g["Wo"], cout, cout, 1, 0, "zero", "none", passes,
+                                       colsum=db if fuse_db else None)
             else:
                 dzp = _split_planes(dz, M, cout, cout, passes)
         if need_w:

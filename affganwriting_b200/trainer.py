@@ -12,6 +12,7 @@ that talks to another rank is ever inside a graph.  The batch is copied into sta
 """
 import torch
 
+from . import ops
 from .network_tro import ConTranModel
 from .parallel import GradientReducer, broadcast_module
 
@@ -24,9 +25,12 @@ class Trainer:
         self.model = ConTranModel(num_writers, oov=True, device=device, encoder=encoder)
         m = self.model
         # main_run.py:275-278: Adam over filter(requires_grad, parameters()) with default betas / eps
-        self.cla_opt = torch.optim.Adam([p for p in m.cla.parameters() if p.requires_grad], lr=lr_cla)
-        self.dis_opt = torch.optim.Adam([p for p in m.dis.parameters() if p.requires_grad], lr=lr_dis)
-        self.gen_opt = torch.optim.Adam([p for p in m.gen.parameters() if p.requires_grad], lr=lr_gen)
+        # (fused=True is torch's single-pass multi-tensor implementation of the same update)
+        import os
+        fused = os.environ.get("AFFGW_FUSED_ADAM", "1") != "0"
+        self.cla_opt = torch.optim.Adam([p for p in m.cla.parameters() if p.requires_grad], lr=lr_cla, fused=fused)
+        self.dis_opt = torch.optim.Adam([p for p in m.dis.parameters() if p.requires_grad], lr=lr_dis, fused=fused)
+        self.gen_opt = torch.optim.Adam([p for p in m.gen.parameters() if p.requires_grad], lr=lr_gen, fused=fused)
         kw = {} if bucket_bytes is None else {"bucket_bytes": bucket_bytes}
         self.red = {"cla": GradientReducer(m.cla.parameters(), **kw), "dis": GradientReducer(m.dis.parameters(), **kw),
                     "gen": GradientReducer(m.gen.parameters(), **kw)}
@@ -67,6 +71,7 @@ class Trainer:
     def _finish(self, name):
         self.red[name].reduce()
         self.opt[name].step()
+        ops.weights_updated(p for grp in self.opt[name].param_groups for p in grp["params"])   # fused Adam: see ops._WeightCache
 
     @staticmethod
     def _pack(outs):
@@ -113,7 +118,7 @@ class Trainer:
         return self._pack(outs)
 
     def _capture(self, batch, epoch):
-        from . import _lib, ops
+        from . import _lib
         dev = self.model.device_
         self._static_in = tuple(t.to(dev).clone() if torch.is_tensor(t) else t for t in batch)
         torch.cuda.synchronize()

@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define AFFGW_VERSION 103
+#define AFFGW_VERSION 104
 
 enum { AFFGW_DT_F32 = 0, AFFGW_DT_BF16 = 1 };
 enum { AFFGW_ACT_NONE = 0, AFFGW_ACT_RELU = 1, AFFGW_ACT_LRELU = 2, AFFGW_ACT_TANH = 3 };
@@ -80,7 +80,8 @@ int affgw_conv_tc_layout(const affgw_conv_desc* d, int for_dgrad);
  * planes (fy: same positions, output channels); affgw_split_positions builds either:
  *   x planes : src = x [N][H][W][pitch], (Hs, Ws) = (H, W), upsample, (oy0, ox0) = (pad, pad), the conv's pad_mode and
  *              pre-activation (activation_first blocks, blocks.py:151-153)
- *   dY planes: src = dY [N][Ho][Wo][Cout], upsample 1, (oy0, ox0) = (0, 0), AFFGW_PAD_ZERO, no activation
+ *   dY planes: src = dY [N][Ho][Wo][Cout], upsample 1, (oy0, ox0) = (0, 0), AFFGW_PAD_ZERO, no activation; `colsum`
+ *              (optional, fp32 [Cout], zeroed by the caller) receives sum_m dY[m][c] = the bias gradient
  * and affgw_conv2d_fwd / _dgrad / _wgrad take those planes as their x / dy arguments when affgw_conv_tc_layout says SHIFT. */
 typedef struct affgw_pos_frame {
     int32_t N, Hp, Wp, G, lead, reserved;
@@ -89,7 +90,7 @@ typedef struct affgw_pos_frame {
 int affgw_conv_pos_frames(const affgw_conv_desc* d, affgw_pos_frame* fx, affgw_pos_frame* fy);
 long long affgw_position_planes_bytes(const affgw_pos_frame* f, int passes);
 int affgw_split_positions(const void* src, int dtype, void* planes, const affgw_pos_frame* f, int Hs, int Ws, int C, int pitch,
-                          int upsample, int oy0, int ox0, int pad_mode, int pre_act, int passes, void* stream);
+                          int upsample, int oy0, int ox0, int pad_mode, int pre_act, int passes, float* colsum, void* stream);
 /* enable (1) / disable (0) the shifted kernel, -1 = query only; returns the previous setting (A/B testing) */
 int affgw_conv_tc_prefer_shift(int enable);
 /* activation tensor [rows][pitch] (fp32 or bf16) -> operand planes [passes == 3 ? 2 : 1][rows][c_store] (bf16), with the

@@ -20,5 +20,7 @@ def cmp(x, y, tag):
             rows.append((float((v - sy[k]).abs().max()), k))
     rows.sort(reverse=True)
     print(tag, rows[:6])
+import os
+print("env", {k: v for k, v in os.environ.items() if k.startswith("AFFGW")})
 cmp(a, b, "eager vs eager")
 cmp(a, g, "eager vs graph")

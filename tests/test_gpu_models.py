@@ -306,14 +306,19 @@ def test_cuda_graph_replay_matches_eager_iterations(specs):
         b.model.load_state_dict(a.model.state_dict())
         g.model.load_state_dict(a.model.state_dict())
         drift_ee = drift_eg = 0.0
+        first = None
         for it in range(7):
             la, lb, lg = a.train_step(batch), b.train_step(batch), g.train_step(batch)
+            first = first or {k: float(v) for k, v in la.items()}
             for k in la:
                 drift_ee = max(drift_ee, abs(float(la[k]) - float(lb[k])))
                 drift_eg = max(drift_eg, abs(float(la[k]) - float(lg[k])))
             if it < 2:          # before the divergence has had time to grow, all three agree tightly
                 assert all(abs(float(la[k]) - float(lg[k])) <= 1e-4 * max(1.0, abs(float(la[k]))) for k in la), it
         assert g.graph_launches > 1000 and g._graphs is not None and g._eager_steps == Trainer.GRAPH_WARMUP
+        # the optimiser steps must reach the kernels (packed-weight cache invalidation, ops.weights_updated): the writer
+        # classifier's loss falls by ~0.007 per iteration at lr 1e-5 on a fixed batch
+        assert float(la["cla"]) < first["cla"] - 0.02 and float(lg["cla"]) < first["cla"] - 0.02
 
         def weight_drift(x, y):
             sx, sy = x.model.state_dict(), y.model.state_dict()
