@@ -28,6 +28,8 @@ long long pack_weight_tc_bytes(int Cout, int Cin, int KH, int KW, int ipad, int 
 int split_planes(const void* x, int x_dt, void* planes, long long rows, int C, int pitch, int c_store, int passes, int pre_act,
                  cudaStream_t st);
 // conv_shift.cu
+int shift_block_n(int cout);
+int wgrad_shift_block_n(int cout);
 int conv_shift_ok(const ConvGeom& g);
 void conv_shift_frame(const ConvGeom& g, int channels, PosFrame& f);
 int split_positions(const void* src, int dt, void* planes, const PosFrame& f, int Hs, int Ws, int C, int pitch, int up, int oy0,
@@ -288,6 +290,15 @@ int affgw_conv_tc_layout(const affgw_conv_desc* d, int for_dgrad) {
     if (make_dgrad(d, dd, direct, Hp, Wp)) return 0;
     dgrad_geom(d, dd, g);
     return conv_tc_ok(g) > 0 ? AFFGW_WLAYOUT_IM2COL : 0;
+}
+
+// output-channel tile width (the BN template argument) of the kernel that runs d: which = 0 forward, 1 dgrad, 2 wgrad
+int affgw_conv_tc_tile_n(const affgw_conv_desc* d, int which) {
+    if (!d || which < 0 || which > 2) return 0;
+    const int lay = affgw_conv_tc_layout(d, which == 1);
+    if (!lay) return 0;
+    if (lay == AFFGW_WLAYOUT_SHIFT) return which == 2 ? wgrad_shift_block_n(d->Cout) : shift_block_n(which == 1 ? d->Cin : d->Cout);
+    return conv_tc_block_n(which == 1 ? d->Cin : d->Cout);
 }
 
 // forward frame of a position-space convolution (geometry only; dtypes / pre_act of d are not looked at)

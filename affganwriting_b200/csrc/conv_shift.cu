@@ -418,9 +418,13 @@ split_positions_kernel(const T* __restrict__ src, bf16* __restrict__ planes, int
 struct ShPlan {
     int bn, KYG, NP, NPa, stages, a_bytes, b_chunk_bytes, smem_bytes;
 };
+}  // namespace
 
 int shift_block_n(int cout) { return cout > 128 ? 256 : cout > 64 ? 128 : cout > 32 ? 64 : cout > 16 ? 32 : 16; }
 
+int wgrad_shift_block_n(int cout) { return cout <= 16 ? 16 : cout <= 32 ? 32 : cout <= 64 ? 64 : 128; }
+
+namespace {
 // pipeline-stage geometry; K x K filter on a frame of pitch Wp, npl planes, BN-wide weight stage
 int make_plan(int K, int Wp, int npl, int bn, ShPlan& p) {
     p.bn = bn;
@@ -853,7 +857,7 @@ int launch_wg_shift(const WsArgs& args, const CUtensorMap& tmx, const CUtensorMa
 int conv_wgrad_pos_tc(const void* x_planes, const PosFrame& fx, const void* dy_planes, const PosFrame& fy, float* ws, int K,
                       int Cout, int cs, int Ho, int Wo, int passes, cudaStream_t st) {
     const int npl = passes == 3 ? 2 : 1;
-    const int bn = Cout <= 16 ? 16 : Cout <= 32 ? 32 : Cout <= 64 ? 64 : 128;
+    const int bn = wgrad_shift_block_n(Cout);
     WsArgs a;
     a.KP = 64;
     // thin layers (<= 64 stored input channels): stack TPM pre-shifted copies of the window along the 128 M rows, one MMA

@@ -25,17 +25,31 @@ def start_kernel_timing():
     _profile["records"] = []
 
 
-def stop_kernel_timing(by_shape=False):
-    """-> {name: {"launches", "ms", "flops"}} ; synchronises the device once.  by_shape=True keys on (name, shape tag)."""
+def stop_kernel_timing(by_shape=False, by_kernel=False):
+    """-> {name: {"launches", "ms", "flops"}} ; synchronises the device once.  by_shape=True keys on (name, shape tag),
+    by_kernel=True on the CUDA kernel function the call ran (e.g. conv_shift_tcgen05_kernel<256, 3>)."""
     recs, _profile["records"] = _profile["records"] or [], None
     torch.cuda.synchronize()
     out = {}
     for name, tag, e0, e1, fl in recs:
-        d = out.setdefault((name, tag) if by_shape else name, {"launches": 0, "ms": 0.0, "flops": 0.0})
+        kern = name
+        if isinstance(tag, tuple):
+            tag, kern = tag
+        key = kern if by_kernel else ((name, tag) if by_shape else name)
+        d = out.setdefault(key, {"launches": 0, "ms": 0.0, "flops": 0.0, "kind": name})
         d["launches"] += 1
         d["ms"] += e0.elapsed_time(e1)
         d["flops"] += fl
     return out
+
+
+def _kernel_name(d, which, passes):
+    """CUDA kernel function a tcgen05 convolution call lands on (matches the names in an ncu / CUPTI launch list)."""
+    lay = L.lib().affgw_conv_tc_layout(C.byref(d), int(which == 1))
+    bn = L.lib().affgw_conv_tc_tile_n(C.byref(d), which)
+    if lay == L.WLAYOUT_SHIFT:
+        return ("conv_wgrad_shift_kernel<%d, %d>" if which == 2 else "conv_shift_tcgen05_kernel<%d, %d>") % (bn, passes)
+    return ("conv_wgrad_tcgen05_kernel<%d, %d>" if which == 2 else "conv_igemm_tcgen05_kernel<%d, %d, float>") % (bn, passes)
 
 
 class _timed:
@@ -391,7 +405,7 @@ class _Conv2d(Function):
             else:
                 planes = _split_planes(x, g["N"] * g["H"] * g["W"], g["Cin"], g["pitch"], passes, cfg.pre_act)
             wp = _pack_tc(weight, cs, False, passes, layout)
-            with _timed("conv_fwd_tcgen05", flops, tag):
+            with _timed("conv_fwd_tcgen05", flops, (tag, _kernel_name(d, 0, passes)) if _profile["records"] is not None else tag):
                 L.call("affgw_conv2d_fwd", planes.data_ptr(), wp.data_ptr(), L.ptr(b32), L.ptr(addend), y.data_ptr(),
                        C.byref(d), L.stream())
         else:
@@ -451,7 +465,8 @@ class _Conv2d(Function):
                 if ws_bytes <= 0:
                     raise RuntimeError("conv2d_wgrad: tcgen05 kernel refused the shape: " + L.last_error())
                 wsb = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-                with _timed("conv_wgrad_tcgen05", flops, ctx.tag):
+                with _timed("conv_wgrad_tcgen05", flops,
+                            (ctx.tag, _kernel_name(d, 2, passes)) if _profile["records"] is not None else ctx.tag):
                     L.call("affgw_conv2d_wgrad", planes.data_ptr(), dzp.data_ptr(), dw.data_ptr(), wsb.data_ptr(), C.byref(d), st)
             else:
                 if x is None:
@@ -490,7 +505,8 @@ class _Conv2d(Function):
                 raise RuntimeError("conv2d_dgrad_ws_bytes: " + L.last_error())
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev) if ws_bytes else None
             src = dzp if use_tc else dz
-            with _timed("conv_dgrad_tcgen05" if use_tc else "conv_dgrad_simt", flops, ctx.tag):
+            with _timed("conv_dgrad_tcgen05" if use_tc else "conv_dgrad_simt", flops,
+                        (ctx.tag, _kernel_name(d, 1, passes)) if (use_tc and _profile["records"] is not None) else ctx.tag):
                 L.call("affgw_conv2d_dgrad", src.data_ptr(), wt.data_ptr(), L.ptr(x), base.data_ptr(), L.ptr(ws),
                        C.byref(d), st)
             if use_tc and g["Cx"] != cin:      # the weight reads only the first `cin` channels of a wider input

@@ -140,7 +140,7 @@ def run_reference_arm(args, rank):
         return
     threads = os.cpu_count() or 1
     sample_batch = 4
-    sec = cpu_reference_steps(sample_batch, max(1, args.steps), min(args.warmup, 1), threads)
+    sec = cpu_reference_steps(sample_batch, max(1, min(args.steps, 10)), min(args.warmup, 1), threads)
     value = (sample_batch / sec) / BATCH_PER_GPU
     sample = (f"{max(1, args.steps)} timed iterations of the CPU oracle port at batch {sample_batch} (fp32, {threads} threads); "
               f"steps/s = samples/s / {BATCH_PER_GPU}")
@@ -254,7 +254,7 @@ def main():
     # ---- instrumented pass: per-launch CUDA events (on the launching stream) around every convolution kernel
     ops.start_kernel_timing()
     ms_instr = timed(lambda: trainer.train_step_eager(resident), 2)      # eager: events cannot sit inside a graph replay
-    kern = ops.stop_kernel_timing()
+    kern = ops.stop_kernel_timing(by_kernel=True)
     instr_steps = 2
 
     step_e2e()
@@ -281,11 +281,16 @@ def main():
         pass
     tf_peak = peaks.get("bf16_tflops_sustained", 1400.0)
     peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if peaks else "fallback 1.4 PF sustained"
-    kernels = {}
+    kernels, kinds = {}, {}
     for name, d in kern.items():
         tf = d["flops"] / (d["ms"] * 1e-3) / 1e12 if d["ms"] > 0 else 0.0
         kernels[name] = {"launches_per_step": d["launches"] / instr_steps, "ms_per_step": d["ms"] / instr_steps,
                          "share_of_step": d["ms"] / ms_instr, "tflops": tf, "frac_of_peak": tf / tf_peak}
+        k = kinds.setdefault(d["kind"], {"launches": 0, "ms": 0.0, "flops": 0.0})
+        k["launches"] += d["launches"]; k["ms"] += d["ms"]; k["flops"] += d["flops"]
+    by_kind = {n: {"launches_per_step": k["launches"] / instr_steps, "ms_per_step": k["ms"] / instr_steps,
+                   "share_of_step": k["ms"] / ms_instr, "tflops": k["flops"] / (k["ms"] * 1e-3) / 1e12 if k["ms"] > 0 else 0.0}
+               for n, k in kinds.items()}
     dominant = max(kernels, key=lambda k: kernels[k]["ms_per_step"]) if kernels else None
     roofline = None
     if dominant:
@@ -293,18 +298,31 @@ def main():
         roofline = {"kernel": dominant, "bound": "tensor", "achieved": k["tflops"], "peak": tf_peak, "unit": "TFLOP/s",
                     "frac": k["frac_of_peak"], "traffic": None, "peak_source": peak_src,
                     "avg_launch_ms": k["ms_per_step"] / max(k["launches_per_step"], 1e-9),
-                    "note": "algorithmic FLOPs (direct-convolution MAC x 2) of all launches of this kernel family in one step / "
-                            "their summed CUDA-event time; the bf16 mode issues 3 tensor-core MMAs per product (split-bf16, "
-                            "DESIGN.md section 3), so executed tensor FLOPs are 3x this and frac is capped at 1/3"}
+                    "share_of_step": k["share_of_step"],
+                    "executed_tflops": 3.0 * k["tflops"], "executed_frac": 3.0 * k["frac_of_peak"],
+                    "note": "achieved = algorithmic FLOPs (direct-convolution MAC x 2) of every launch of this kernel function in "
+                            "one eager step / their summed CUDA-event time on the launching stream.  The bf16 mode issues 3 "
+                            "tensor-core MMAs per product (split-bf16, DESIGN.md section 3): executed_* count those, so frac "
+                            "is capped at 1/3 and executed_frac is the tensor-pipe utilisation against the measured cuBLAS "
+                            "peak.  traffic: profiles/ holds the ncu DRAM bytes of this kernel on one layer"}
+
+    try:        # DRAM bytes of the dominant kernel from the committed ncu --set full capture (one layer, see profiles/README.md)
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get(dominant)
+        if tr and roofline:
+            roofline["traffic"] = tr["dram_bytes_per_launch"]
+            roofline["traffic_note"] = ("ncu dram__bytes_read.sum + dram__bytes_write.sum per launch on " + tr["layer"] +
+                                        "; algorithmic bytes of that launch: %d" % sum(tr["algorithmic_bytes_per_launch"].values()))
+    except Exception:
+        pass
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        sec = cpu_reference_steps(2, 1, 0, threads)
-        v = (2 / sec) / BATCH_PER_GPU
+        sec = cpu_reference_steps(4, 3, 1, threads)
+        v = (4 / sec) / BATCH_PER_GPU
         cpu_baseline = {"value": v, "unit": "steps/s", "cores": threads, "kind": "port",
-                        "sample": f"1 iteration of the CPU oracle port at batch 2 ({sec:.1f} s, fp32, {threads} threads); "
-                                  f"steps/s = samples/s / {BATCH_PER_GPU}"}
+                        "sample": f"3 timed iterations (after 1 warm-up) of the CPU oracle port at batch 4 ({sec:.2f} s each, fp32, "
+                                  f"{threads} threads); steps/s = samples/s / {BATCH_PER_GPU}"}
 
     h2d = batch_bytes(host)
     line = {

@@ -91,6 +91,9 @@ int affgw_conv_pos_frames(const affgw_conv_desc* d, affgw_pos_frame* fx, affgw_p
 long long affgw_position_planes_bytes(const affgw_pos_frame* f, int passes);
 int affgw_split_positions(const void* src, int dtype, void* planes, const affgw_pos_frame* f, int Hs, int Ws, int C, int pitch,
                           int upsample, int oy0, int ox0, int pad_mode, int pre_act, int passes, float* colsum, void* stream);
+/* output-channel tile width (the BN template argument) of the kernel that runs the forward (which = 0), input-gradient (1)
+ * or weight-gradient (2) convolution of d - lets a profiler name the kernel a call lands on */
+int affgw_conv_tc_tile_n(const affgw_conv_desc* d, int which);
 /* enable (1) / disable (0) the shifted kernel, -1 = query only; returns the previous setting (A/B testing) */
 int affgw_conv_tc_prefer_shift(int enable);
 /* activation tensor [rows][pitch] (fp32 or bf16) -> operand planes [passes == 3 ? 2 : 1][rows][c_store] (bf16), with the
