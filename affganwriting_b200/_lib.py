@@ -48,6 +48,11 @@ SIGNATURES = {
     "affgw_resize_bilinear_fwd": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "affgw_resize_bilinear_bwd": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "affgw_add_act": [_P, _P, _P, _I, _L, _I, _P],
+    "affgw_conv_thin_supported": [_D],
+    "affgw_conv_thin_ws_bytes": [_D, _I],
+    "affgw_conv_thin_fwd": [_P, _P, _P, _P, _P, _D, _P],
+    "affgw_conv_thin_dgrad": [_P, _P, _P, _P, _D, _P],
+    "affgw_conv_thin_wgrad": [_P, _P, _P, _D, _P],
     "affgw_conv_tc_layout": [_D, _I],
     "affgw_conv_tc_tile_n": [_D, _I],
     "affgw_conv_pos_frames": [_D, C.POINTER(PosFrame), C.POINTER(PosFrame)],
@@ -96,7 +101,7 @@ SIGNATURES = {
     "affgw_bucket_pack": [_P, _P, _P, _I, _P, _P],
     "affgw_bucket_unpack": [_P, _P, _P, _I, _P, _F, _P],
 }
-_RESTYPE = {"affgw_last_error": C.c_char_p, "affgw_launch_count": _L, "affgw_pack_weight_tc_bytes": _L, "affgw_operand_planes_bytes": _L, "affgw_position_planes_bytes": _L,
+_RESTYPE = {"affgw_last_error": C.c_char_p, "affgw_launch_count": _L, "affgw_pack_weight_tc_bytes": _L, "affgw_operand_planes_bytes": _L, "affgw_position_planes_bytes": _L, "affgw_conv_thin_ws_bytes": _L,
             "affgw_conv2d_dgrad_ws_bytes": _L, "affgw_conv2d_wgrad_ws_bytes": _L}
 
 _lib = None

@@ -40,6 +40,11 @@ int conv_pos_tc(const void* x_planes, const PosFrame& f, const void* w_packed, c
 int pack_weight_shift(const float* w, void* out, int Cout, int Cin, int K, int ipad, int transpose_flip, int passes,
                       cudaStream_t st);
 long long pack_weight_shift_bytes(int Cout, int Cin, int K, int ipad, int transpose_flip, int passes);
+// conv_thin.cu
+int conv_thin_ok(int Cin, int Cout, int K, int stride, int up);
+int conv_thin_fwd(const float* x, const float* w, const float* bias, float* y, float* scratch, const ConvGeom& g, cudaStream_t st);
+int conv_thin_dgrad_frame(const float* dy, const float* w, float* dframe, float* scratch, const ConvGeom& g, cudaStream_t st);
+int conv_thin_wgrad(const float* x, const float* dy, float* dw, const ConvGeom& g, cudaStream_t st);
 // conv_tc_wgrad.cu
 int conv_wgrad_tc_ok(const ConvGeom& g);
 long long conv_wgrad_tc_ws_bytes(const ConvGeom& g);
@@ -443,6 +448,56 @@ int affgw_conv2d_wgrad(const void* x, const void* dy, float* dw, void* workspace
         return conv_wgrad_tc(x, xpl, dy, ypl, dw, workspace, g, d->Cin, d->passes, S(stream));
     }
     return conv_wgrad_simt(x, d->x_dtype, dy, d->y_dtype, dw, g, S(stream));
+}
+
+// ---- single-channel-sided stencils on the CUDA cores (conv_thin.cu): fp32 NHWC tensors and the OIHW parameter directly
+static int thin_geom(const affgw_conv_desc* d, ConvGeom& g) {
+    if (int rc = make_geom(d, g)) return rc;
+    AFFGW_CHECK(d->x_dtype == AFFGW_F32 && d->y_dtype == AFFGW_F32, "conv_thin: fp32 tensors only");
+    AFFGW_CHECK(d->KH == d->KW && d->in_pitch == d->Cin && d->out_pitch == d->Cout, "conv_thin: dense square-filter convolution expected");
+    AFFGW_CHECK(d->pre_act == ACT_NONE, "conv_thin: no activation-first variant");
+    AFFGW_CHECK(conv_thin_ok(d->Cin, d->Cout, d->KH, d->stride, d->upsample) != 0,
+                "conv_thin: %d -> %d channels, %dx%d, stride %d is not a single-channel-sided stencil", d->Cin, d->Cout, d->KH,
+                d->KW, d->stride);
+    return 0;
+}
+int affgw_conv_thin_supported(const affgw_conv_desc* d) {
+    ConvGeom g;
+    if (!d || d->x_dtype != AFFGW_F32 || d->y_dtype != AFFGW_F32 || d->KH != d->KW || d->in_pitch != d->Cin ||
+        d->out_pitch != d->Cout || d->pre_act != ACT_NONE || make_geom(d, g))
+        return 0;
+    return conv_thin_ok(d->Cin, d->Cout, d->KH, d->stride, d->upsample);
+}
+static long long thin_scratch_bytes(const affgw_conv_desc* d) {
+    return (long long)d->KH * d->KW * (d->Cin > d->Cout ? d->Cin : d->Cout) * 4;
+}
+long long affgw_conv_thin_ws_bytes(const affgw_conv_desc* d, int for_dgrad) {
+    if (!affgw_conv_thin_supported(d)) return -1;
+    const long long frame = (long long)d->N * (d->H + 2 * d->pad) * (d->W + 2 * d->pad) * d->Cin * 4;
+    return thin_scratch_bytes(d) + (for_dgrad ? (frame + 255) / 256 * 256 : 0);
+}
+int affgw_conv_thin_fwd(const float* x, const float* w_oihw, const float* bias, float* y, void* workspace,
+                        const affgw_conv_desc* d, void* stream) {
+    ConvGeom g;
+    if (int rc = thin_geom(d, g)) return rc;
+    AFFGW_CHECK(x && w_oihw && y && workspace, "conv_thin_fwd: null pointer");
+    return conv_thin_fwd(x, w_oihw, bias, y, (float*)workspace, g, S(stream));
+}
+int affgw_conv_thin_dgrad(const float* dy, const float* w_oihw, float* dx, void* workspace, const affgw_conv_desc* d, void* stream) {
+    ConvGeom g;
+    if (int rc = thin_geom(d, g)) return rc;
+    AFFGW_CHECK(dy && w_oihw && dx && workspace, "conv_thin_dgrad: null pointer");
+    const long long frame = (long long)d->N * (d->H + 2 * d->pad) * (d->W + 2 * d->pad) * d->Cin * 4;
+    float* dframe = (float*)workspace;
+    float* scratch = (float*)((char*)workspace + (frame + 255) / 256 * 256);
+    if (int rc = conv_thin_dgrad_frame(dy, w_oihw, dframe, scratch, g, S(stream))) return rc;
+    return conv_fold(dframe, nullptr, dx, AFFGW_F32, d->N, d->H, d->W, d->Cin, d->pad, d->pad_mode, 1, ACT_NONE, S(stream));
+}
+int affgw_conv_thin_wgrad(const float* x, const float* dy, float* dw_oihw, const affgw_conv_desc* d, void* stream) {
+    ConvGeom g;
+    if (int rc = thin_geom(d, g)) return rc;
+    AFFGW_CHECK(x && dy && dw_oihw, "conv_thin_wgrad: null pointer");
+    return conv_thin_wgrad(x, dy, dw_oihw, g, S(stream));
 }
 
 int affgw_colsum(const void* a, int dtype, float* out, long long M, int C, int pitch, void* stream) {

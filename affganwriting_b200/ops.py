@@ -14,6 +14,7 @@ from . import _lib as L  # noqa: N812
 
 import os as _os
 _FUSE_DB = _os.environ.get("AFFGW_FUSE_DB", "1") != "0"
+_THIN = _os.environ.get("AFFGW_THIN", "1") != "0"
 _state = {"mode": "fp32", "passes": 3, "force_simt": False, "simt_wgrad": False}
 _err_flag = {}
 _profile = {"records": None}
@@ -104,6 +105,14 @@ class conv_passes:
 
 def act_dtype():
     return torch.float32
+
+
+def use_thin_kernels(flag=True):
+    """Route single-channel-sided stencils (7x7 stems, decoder output conv) to the fp32 CUDA-core kernels (default) or,
+    when off, through the tensor-core kernels like every other convolution (tests)."""
+    global _THIN
+    prev, _THIN = _THIN, bool(flag)
+    return prev
 
 
 def force_simt(flag=True):
@@ -392,7 +401,19 @@ class _Conv2d(Function):
         flops = 2.0 * g["N"] * g["Ho"] * g["Wo"] * g["Cout"] * g["Cin"] * g["KH"] * g["KW"]
         tag = "%dx%dx%d c%d->%d k%d s%d u%d" % (g["N"], g["H"], g["W"], g["Cin"], g["Cout"], g["KH"], cfg.stride, cfg.upsample)
         planes = None
-        if use_tc:
+        thin = False
+        if use_tc and addend is None and cfg.pre_act == "none" and not g["two_d"] and g["pitch"] == g["Cin"] \
+                and (g["Cin"] == 1 or g["Cout"] == 1) and _THIN:
+            dthin = _desc(g, cfg, g["Cin"], L.F32, L.F32, L.F32, L.ALGO_SIMT)
+            thin = bool(L.lib().affgw_conv_thin_supported(C.byref(dthin)))
+        if thin:
+            # single-channel-sided stencil (7x7 stems, decoder output conv): fp32 CUDA-core kernels, no operand planes
+            ws = torch.empty(L.lib().affgw_conv_thin_ws_bytes(C.byref(dthin), 0), dtype=torch.uint8, device=x.device)
+            with _timed("conv_fwd_thin", flops, (tag, "conv_thin fwd") if _profile["records"] is not None else tag):
+                L.call("affgw_conv_thin_fwd", x.data_ptr(), _w4(weight.detach()).contiguous().data_ptr(), L.ptr(b32),
+                       y.data_ptr(), ws.data_ptr(), C.byref(dthin), L.stream())
+            layout = 0
+        elif use_tc:
             cs = _up8(g["Cin"])
             d = _desc(g, cfg, g["Cin"], L.BF16, L.BF16, L.F32, L.ALGO_TC, in_pitch=cs, passes=passes, pre_act="none")
             layout = L.lib().affgw_conv_tc_layout(C.byref(d), 0)
@@ -414,10 +435,11 @@ class _Conv2d(Function):
             with _timed("conv_fwd_simt", flops, tag):
                 L.call("affgw_conv2d_fwd", x.data_ptr(), wp.data_ptr(), L.ptr(b32), L.ptr(addend), y.data_ptr(), C.byref(d),
                        L.stream())
-        ctx.cfg, ctx.g, ctx.use_tc, ctx.passes, ctx.tag = cfg, g, use_tc, passes, tag
+        ctx.cfg, ctx.g, ctx.use_tc, ctx.passes, ctx.tag = cfg, g, use_tc and not thin, passes, tag
         ctx.layout = layout if use_tc else 0
+        ctx.thin = thin
         ctx.has_bias, ctx.has_addend = bias is not None, addend is not None
-        keep_x = (not use_tc) or cfg.pre_act != "none" or _state["simt_wgrad"]
+        keep_x = (not use_tc) or thin or cfg.pre_act != "none" or _state["simt_wgrad"]
         ctx.save_for_backward(x if keep_x else None, weight, y if cfg.post_act != "none" else None, planes)
         ctx.x_meta = (x.shape, x.device)
         return y
@@ -457,6 +479,20 @@ class _Conv2d(Function):
                                        colsum=db if fuse_db else None)
             else:
                 dzp = _split_planes(dz, M, cout, cout, passes)
+        if ctx.thin:
+            dthin = _desc(g, fwd_cfg, cin, L.F32, L.F32, L.F32, L.ALGO_SIMT)
+            if need_w:
+                dw = torch.zeros(weight.shape, dtype=torch.float32, device=dev)
+                with _timed("conv_wgrad_thin", flops, (ctx.tag, "conv_thin wgrad") if _profile["records"] is not None else ctx.tag):
+                    L.call("affgw_conv_thin_wgrad", x.data_ptr(), dz.data_ptr(), dw.data_ptr(), C.byref(dthin), st)
+            if need_x:
+                dx = empty_cl(g["N"], cin, g["H"], g["W"], torch.float32, dev)
+                ws = torch.empty(L.lib().affgw_conv_thin_ws_bytes(C.byref(dthin), 1), dtype=torch.uint8, device=dev)
+                with _timed("conv_dgrad_thin", flops, (ctx.tag, "conv_thin dgrad") if _profile["records"] is not None else ctx.tag):
+                    L.call("affgw_conv_thin_dgrad", dz.data_ptr(), _w4(weight.detach()).contiguous().data_ptr(), dx.data_ptr(),
+                           ws.data_ptr(), C.byref(dthin), st)
+            da = dz if (ctx.has_addend and need_a) else None
+            return dx, dw, db, da, None
         if need_w:
             dw = torch.zeros(weight.shape, dtype=torch.float32, device=dev)
             if use_tc and not _state["simt_wgrad"]:

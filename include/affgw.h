@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define AFFGW_VERSION 104
+#define AFFGW_VERSION 105
 
 enum { AFFGW_DT_F32 = 0, AFFGW_DT_BF16 = 1 };
 enum { AFFGW_ACT_NONE = 0, AFFGW_ACT_RELU = 1, AFFGW_ACT_LRELU = 2, AFFGW_ACT_TANH = 3 };
@@ -116,6 +116,17 @@ int affgw_conv2d_dgrad(const void* dy, const void* w_packed_t, const void* x, vo
  * split-K partials are reduced in `workspace` (affgw_conv2d_wgrad_ws_bytes; 0 = not eligible, use algo = SIMT). */
 long long affgw_conv2d_wgrad_ws_bytes(const affgw_conv_desc* d);
 int affgw_conv2d_wgrad(const void* x, const void* dy, float* dw_oihw, void* workspace, const affgw_conv_desc* d, void* stream);
+/* Single-channel-sided stride-1 stencils on the CUDA cores, fp32 in and out: the 1 -> 16 7x7 stems of DisModel /
+ * WriterClaModel (modules_tro.py:125-128,175-178) and the 64 -> 1 7x7 + tanh output convolution of the Decoder
+ * (modules_tro.py:600-603).  x [N,H,W,Cin] and y / dy [N,Ho,Wo,Cout] dense NHWC fp32, w the OIHW parameter itself (no
+ * packing), pre_act must be NONE.  _supported: 0 = no, 1 = one input channel, 2 = one output channel.  workspace:
+ * affgw_conv_thin_ws_bytes(d, for_dgrad) bytes.  wgrad ADDS into dw (caller zeroes it). */
+int affgw_conv_thin_supported(const affgw_conv_desc* d);
+long long affgw_conv_thin_ws_bytes(const affgw_conv_desc* d, int for_dgrad);
+int affgw_conv_thin_fwd(const float* x, const float* w_oihw, const float* bias, float* y, void* workspace,
+                        const affgw_conv_desc* d, void* stream);
+int affgw_conv_thin_dgrad(const float* dy, const float* w_oihw, float* dx, void* workspace, const affgw_conv_desc* d, void* stream);
+int affgw_conv_thin_wgrad(const float* x, const float* dy, float* dw_oihw, const affgw_conv_desc* d, void* stream);
 /* out[c] += sum_m a[m][c]  (bias gradient); caller zeroes out */
 int affgw_colsum(const void* a, int dtype, float* out, long long M, int C, int pitch, void* stream);
 

@@ -65,6 +65,42 @@ def tc_mode(request):
     A.set_precision("fp32")
 
 
+@pytest.fixture(params=[True, False], ids=["thin", "tensorcore"])
+def thin_route(request):
+    """Single-channel-sided stencils have their own fp32 CUDA-core kernels; both routes are checked."""
+    prev = ops.use_thin_kernels(request.param)
+    yield request.param
+    ops.use_thin_kernels(prev)
+
+
+@pytest.mark.parametrize("case", [CASES[9], CASES[13], (3, 20, 45, 1, 64, 5, 1, 2, "zero", 1, "none"),
+                                  (3, 20, 45, 16, 1, 3, 1, 1, "replicate", 1, "none")])
+def test_single_channel_stencils(case, thin_route, tc_mode):
+    """conv_thin.cu (1 -> N and N -> 1 stencils, forward / dgrad / wgrad) and the tensor-core route for the same layers."""
+    if not thin_route and case[5] != 7:
+        pytest.skip("covered by the generic cases")
+    n, h, w_, ci, co, k, s, p, pm, up, pre = case
+    # (one bf16 rounding per operand through a tanh on a 64-channel 7x7 sum: looser than the linear cases)
+    tol = TOL[tc_mode] if (thin_route or tc_mode == "bf16") else 6e-2
+    g = torch.Generator(device="cuda").manual_seed(4)
+    x = torch.randn(n, ci, h, w_, device="cuda", generator=g)
+    wgt = torch.randn(co, ci, k, k, device="cuda", generator=g) * (2.0 / (ci * k * k)) ** 0.5
+    b = torch.randn(co, device="cuda", generator=g)
+    xi = ops.to_internal(x).detach().clone().requires_grad_()
+    wi, bi = wgt.clone().requires_grad_(), b.clone().requires_grad_()
+    ops.start_kernel_timing()
+    y = ops.conv2d(xi, wi, bi, stride=s, pad=p, pad_mode=pm, upsample=up, pre_act=pre, post_act="tanh")
+    xr, wr, br = x.double().requires_grad_(), wgt.double().requires_grad_(), b.double().requires_grad_()
+    yr = torch.tanh(ref_conv(xr, wr, br, s, p, pm, up, pre))
+    gy = torch.randn(yr.shape, device="cuda", generator=g)
+    y.backward(gy)
+    names = set(ops.stop_kernel_timing())
+    assert any("thin" in nm for nm in names) == thin_route, names
+    yr.backward(gy.double())
+    e = dict(y=rel(y, yr), dx=rel(xi.grad, xr.grad), dw=rel(wi.grad, wr.grad), db=rel(bi.grad, br.grad))
+    assert all(v <= tol for v in e.values()), e
+
+
 @pytest.mark.parametrize("case", CASES)
 def test_tc_conv_matches_float64_torch(case, tc_mode):
     n, h, w_, ci, co, k, s, p, pm, up, pre = case
