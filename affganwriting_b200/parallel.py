@@ -39,27 +39,34 @@ class CudaPacker:
     """Gather / scatter a list of fp32 gradient tensors into one contiguous bucket with one kernel launch each."""
 
     def pack(self, grads, bucket):
-        ptrs, sizes, offs = self._tables(grads, bucket.device)
+        ptrs, sizes, offs = self._tables(grads, bucket.device)[:3]
         L.call("affgw_bucket_pack", ptrs.data_ptr(), sizes.data_ptr(), offs.data_ptr(), len(grads), bucket.data_ptr(),
                L.stream())
-        self._keep = (ptrs, sizes, offs)
 
     def unpack(self, grads, bucket, scale):
-        ptrs, sizes, offs = self._tables(grads, bucket.device)
+        ptrs, sizes, offs = self._tables(grads, bucket.device)[:3]
         L.call("affgw_bucket_unpack", ptrs.data_ptr(), sizes.data_ptr(), offs.data_ptr(), len(grads), bucket.data_ptr(),
                float(scale), L.stream())
-        self._keep = (ptrs, sizes, offs)
 
-    @staticmethod
-    def _tables(grads, device):
+    def _tables(self, grads, device):
+        # pointer / size / offset tables on the device; cached by the pointer tuple, which is constant from one iteration
+        # to the next when the backward passes are replayed as CUDA graphs (static gradient buffers)
+        ptrs = tuple(g.data_ptr() for g in grads)
+        cache = self.__dict__.setdefault("_table_cache", {})
+        hit = cache.get(ptrs)
+        if hit is not None:
+            return hit
         n = [g.numel() for g in grads]
         off, acc = [], 0
         for k in n:
             off.append(acc)
             acc += k
-        host = torch.tensor([[g.data_ptr() for g in grads], n, off], dtype=torch.int64).pin_memory()
+        host = torch.tensor([list(ptrs), n, off], dtype=torch.int64).pin_memory()
         dev = host.to(device, non_blocking=True)
-        return dev[0], dev[1], dev[2]
+        if len(cache) > 256:
+            cache.clear()
+        cache[ptrs] = (dev[0], dev[1], dev[2], host)          # keep the pinned source alive until the copy has run
+        return cache[ptrs]
 
 
 class GradientReducer:

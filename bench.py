@@ -252,8 +252,9 @@ def main():
             dist.destroy_process_group()
         return
     # ---- instrumented pass: per-launch CUDA events (on the launching stream) around every convolution kernel
+    trainer.train_step_eager(resident)                   # eager: events cannot sit inside a graph replay
     ops.start_kernel_timing()
-    ms_instr = timed(lambda: trainer.train_step_eager(resident), 2)      # eager: events cannot sit inside a graph replay
+    timed(lambda: trainer.train_step_eager(resident), 2)
     kern = ops.stop_kernel_timing(by_kernel=True)
     instr_steps = 2
 
@@ -281,16 +282,11 @@ def main():
         pass
     tf_peak = peaks.get("bf16_tflops_sustained", 1400.0)
     peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if peaks else "fallback 1.4 PF sustained"
-    kernels, kinds = {}, {}
+    kernels = {}
     for name, d in kern.items():
         tf = d["flops"] / (d["ms"] * 1e-3) / 1e12 if d["ms"] > 0 else 0.0
         kernels[name] = {"launches_per_step": d["launches"] / instr_steps, "ms_per_step": d["ms"] / instr_steps,
-                         "share_of_step": d["ms"] / ms_instr, "tflops": tf, "frac_of_peak": tf / tf_peak}
-        k = kinds.setdefault(d["kind"], {"launches": 0, "ms": 0.0, "flops": 0.0})
-        k["launches"] += d["launches"]; k["ms"] += d["ms"]; k["flops"] += d["flops"]
-    by_kind = {n: {"launches_per_step": k["launches"] / instr_steps, "ms_per_step": k["ms"] / instr_steps,
-                   "share_of_step": k["ms"] / ms_instr, "tflops": k["flops"] / (k["ms"] * 1e-3) / 1e12 if k["ms"] > 0 else 0.0}
-               for n, k in kinds.items()}
+                         "share_of_step": d["ms"] / instr_steps / ms_step, "tflops": tf, "frac_of_peak": tf / tf_peak}
     dominant = max(kernels, key=lambda k: kernels[k]["ms_per_step"]) if kernels else None
     roofline = None
     if dominant:
