@@ -1,0 +1,48 @@
+"""Generation (the reference's tt.test_single_writer.* / helpers.generate_from_batch loops: enc_image -> enc_text -> mix ->
+decode under no_grad, tt.test_single_writer.4_scenarios.py:150-158) replayed as a CUDA graph.
+
+A generator forward is ~400 small kernels; issued from Python it is host-bound at batch 64.  GraphedGenerator captures
+one forward for a fixed (batch, style planes) shape and replays it: inputs are copied into static tensors, the image
+comes back in a static tensor (clone it if it has to outlive the next call).  Weights are read at replay time, so a
+load_state_dict / optimiser step between calls is picked up as long as ops.weights_updated(gen) is called - the packed
+operand copies are rebuilt inside the graph on every replay.
+"""
+import torch
+
+from . import ops
+
+
+class GraphedGenerator:
+    def __init__(self, gen, warmup=2):
+        self.gen = gen
+        self.warmup = int(warmup)
+        self._graph = None
+        self._shape = None
+        self._calls = 0
+        self._side = None
+
+    @torch.no_grad()
+    def __call__(self, tr_img, label):
+        key = (tuple(tr_img.shape), tuple(label.shape), self.gen.training)
+        if self._graph is None or key != self._shape:
+            if self._shape != key:
+                self._graph, self._calls, self._shape = None, 0, key
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=tr_img.device)
+            if self._calls < self.warmup:                 # eager calls on the capture stream: lazy initialisation, allocator
+                self._calls += 1
+                self._side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(self._side):
+                    out = self.gen(tr_img, label)
+                torch.cuda.current_stream().wait_stream(self._side)
+                return out
+            self._img, self._lab = tr_img.clone(), label.clone()
+            torch.cuda.synchronize()
+            ops.clear_weight_cache(self.gen)              # every packed weight the graph reads is packed inside it
+            self._graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._graph, stream=self._side):
+                self._out = self.gen(self._img, self._lab)
+        self._img.copy_(tr_img, non_blocking=True)
+        self._lab.copy_(label, non_blocking=True)
+        self._graph.replay()
+        return self._out

@@ -264,10 +264,12 @@ def main():
 
     # ---- generation throughput (secondary number of BASELINE.json's metric): style encode + decode per image
     gen = trainer.model.gen
+    from affganwriting_b200.inference import GraphedGenerator
+    gen_fn = gen if args.no_graph else GraphedGenerator(gen)
     with torch.no_grad():
-        for _ in range(2):
-            gen(resident[3], resident[7])
-        ms_gen = timed(lambda: gen(resident[3], resident[7]), 5) / 5
+        for _ in range(4):
+            gen_fn(resident[3], resident[7])
+        ms_gen = timed(lambda: gen_fn(resident[3], resident[7]), 10) / 10
     gen_img_s = world * B / (ms_gen / 1e3)
 
     if rank != 0:

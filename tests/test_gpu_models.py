@@ -336,3 +336,30 @@ def test_cuda_graph_replay_matches_eager_iterations(specs):
         assert a.model.iter_num == g.model.iter_num
     finally:
         A.set_precision("fp32")
+
+
+def test_graphed_generator_matches_eager(specs):
+    """inference.GraphedGenerator: the captured forward returns what the eager forward returns, and follows a weight update."""
+    from affganwriting_b200.inference import GraphedGenerator
+    from affganwriting_b200 import ops
+    A.set_precision("bf16")
+    try:
+        gen = _gen(specs).eval()
+        batch = _cuda(O.synthetic_batch(4, 15))
+        fast = GraphedGenerator(gen)
+        with torch.no_grad():
+            ref = gen(batch["tr_img"], batch["label_xt"]).clone()
+            for _ in range(4):
+                out = fast(batch["tr_img"], batch["label_xt"])
+            assert fast._graph is not None
+            assert float((out - ref).abs().max()) <= 2e-3           # run-to-run noise of the fp32 atomics is ~3e-4
+            other = gen(batch["tr_img"].flip(0), batch["label_xt_swap"]).clone()
+            out2 = fast(batch["tr_img"].flip(0), batch["label_xt_swap"])
+            assert float((out2 - other).abs().max()) <= 2e-3
+            gen.dec.model[7].conv.weight.mul_(1.5)           # a weight update between calls must be seen by the replay
+            ops.weights_updated(gen)
+            moved = gen(batch["tr_img"], batch["label_xt"]).clone()
+            out3 = fast(batch["tr_img"], batch["label_xt"])
+            assert float((out3 - moved).abs().max()) <= 2e-3 and float((out3 - ref).abs().max()) > 1e-2
+    finally:
+        A.set_precision("fp32")
