@@ -363,3 +363,56 @@ def test_graphed_generator_matches_eager(specs):
             assert float((out3 - moved).abs().max()) <= 2e-3 and float((out3 - ref).abs().max()) > 1e-2
     finally:
         A.set_precision("fp32")
+
+
+def test_contran_model_modes_match_oracle(specs):
+    """ConTranModel.forward (network_tro.py:39-138): cla_update / dis_update / gen_update compose the same losses and
+    gradients as the oracle's per-pair formulation - including the batching of the paired discriminator / classifier
+    evaluations into one 2B pass (an identity, see network_tro.ConTranModel._pair)."""
+    from affganwriting_b200.network_tro import ConTranModel
+    A.set_precision("fp32")
+    cpu = O.synthetic_batch(2, 50)
+    full = {}
+    for pre, key in (("gen.", "gen_c50"), ("dis.", "dis"), ("cla.", "cla")):
+        for k, v in W.make_state(specs[key]).items():
+            full[pre + k] = v.clone().requires_grad_(v.is_floating_point())
+    lt, ld, lc, _, _ = O.gen_update(cpu, full)
+    lt.backward()
+    gen_grads = {k[4:]: v.grad.clone() for k, v in full.items() if k.startswith("gen.") and v.grad is not None}
+    for v in full.values():
+        v.grad = None
+    l_real, l_fake = O.dis_update(cpu, full)
+    (l_real + l_fake).backward()
+    dis_grads = {k[4:]: v.grad.clone() for k, v in full.items() if k.startswith("dis.") and v.grad is not None}
+    l_c = O.cla_update(cpu, full)
+
+    model = ConTranModel(O.NUM_WRITERS, device=torch.device("cuda", 0))
+    model.load_state_dict({k: v.detach() for k, v in full.items()})
+    model.train()
+    batch = (None, cpu["tr_wid"], None, cpu["tr_img"], None, None, cpu["img_xt"], cpu["label_xt"], cpu["label_xt_swap"])
+    got_c = model(batch, 0, "cla_update")
+    assert abs(float(got_c) - float(l_c)) <= 1e-4 * max(1.0, abs(float(l_c)))
+    model.zero_grad()
+    model.load_state_dict({k: v.detach() for k, v in full.items()})         # BatchNorm buffers back to the start
+    got_d = model(batch, 0, "dis_update")
+    assert abs(float(got_d) - float(l_real + l_fake)) <= 2e-4 * max(1.0, abs(float(l_real + l_fake)))
+    dots = na = nb = 0.0
+    for k, p in model.dis.named_parameters():
+        a, b = p.grad.double().cpu().reshape(-1), dis_grads[k].double().reshape(-1)
+        dots += float(a @ b); na += float(a @ a); nb += float(b @ b)
+    assert dots / (na ** 0.5 * nb ** 0.5) >= 0.9999
+    model.zero_grad()
+    model.load_state_dict({k: v.detach() for k, v in full.items()})
+    got_t, got_ld, got_lc, _, _ = model(batch, 0, "gen_update")
+    assert abs(float(got_ld) - float(ld)) <= 2e-4 * max(1.0, abs(float(ld)))
+    assert abs(float(got_lc) - float(lc)) <= 2e-4 * max(1.0, abs(float(lc)))
+    assert abs(float(got_t) - float(lt)) <= 2e-4 * max(1.0, abs(float(lt)))
+    dots = na = nb = 0.0
+    for k, p in model.gen.named_parameters():
+        if p.grad is None or k not in gen_grads:
+            continue
+        a, b = p.grad.double().cpu().reshape(-1), gen_grads[k].double().reshape(-1)
+        dots += float(a @ b); na += float(a @ a); nb += float(b @ b)
+    cos = dots / (na ** 0.5 * nb ** 0.5)
+    print(f"\nConTranModel gen_update vs oracle: l_total {float(got_t):.6f} / {float(lt):.6f}, gradient cosine {cos:.6f}")
+    assert cos >= 0.999
