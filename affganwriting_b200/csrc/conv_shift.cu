@@ -872,11 +872,15 @@ int conv_wgrad_pos_tc(const void* x_planes, const PosFrame& fx, const void* dy_p
     const int per_cta = a.TPM * acc_max;                        // filter columns one CTA can own
     a.n_kxg = (K + per_cta - 1) / per_cta;
     a.KXG = (K + a.n_kxg - 1) / a.n_kxg;
-    a.slots = packed ? (a.KXG + a.TPM - 1) / a.TPM * a.TPM * fx.G + 16 : 16;
+    // group slots of one plane: the last accumulator's MMA reads 16 slots from its first copy
+    a.slots = packed ? ((a.KXG + a.TPM - 1) / a.TPM - 1) * a.TPM * fx.G + 16 : 16;
     a.rowsA = fx.G < 16 ? fx.G : 16;
     a.rowsB = fy.G < bn / 8 ? fy.G : bn / 8;
-    a.pitchA16 = packed ? a.KP + 4 : a.KP + K - 1;              // dense TMA boxes: pitch = box width
-    a.pitchB16 = a.KP + (bn >= 64 ? 1 : bn == 32 ? 2 : 4);      // every plane of a stage starts 128-byte aligned (TMA destination)
+    // thin layers are bound by the per-stage hand-shake, not by bytes: 128 positions per stage (the TMA box limit of 256
+    // uint64 elements) when three such stages fit
+    if (packed && npl * (a.slots + bn / 8) * 128 * 16 * 3 <= SMEM_LIMIT - 1024) a.KP = 128;
+    a.pitchA16 = a.KP == 128 ? 128 : (packed ? a.KP + 4 : a.KP + K - 1);     // dense TMA boxes: pitch = box width
+    a.pitchB16 = a.KP == 128 ? 128 : a.KP + (bn >= 64 ? 1 : bn == 32 ? 2 : 4);  // planes start 128-byte aligned (TMA destination)
     a.a_bytes = npl * a.slots * a.pitchA16 * 16;
     a.b_bytes = npl * (bn / 8) * a.pitchB16 * 16;
     const int stage = a.a_bytes + a.b_bytes;
