@@ -22,7 +22,7 @@ class ConvDesc(C.Structure):
     """Mirror of `affgw_conv_desc` (include/affgw.h)."""
     _fields_ = [(n, C.c_int32) for n in (
         "N", "H", "W", "Cin", "Cout", "KH", "KW", "stride", "pad", "pad_mode", "upsample", "Ho", "Wo",
-        "in_pitch", "out_pitch", "pre_act", "post_act", "x_dtype", "w_dtype", "y_dtype", "algo", "passes", "grad_dtype")]
+        "in_pitch", "out_pitch", "pre_act", "post_act", "x_dtype", "w_dtype", "y_dtype", "algo", "passes", "grad_dtype", "stride_w")]
 
 
 class PosFrame(C.Structure):
@@ -45,6 +45,8 @@ SIGNATURES = {
     "affgw_pack_weight_tc_bytes": [_I, _I, _I, _I, _I, _I, _I, _I],
     "affgw_maxpool3s2_fwd": [_P, _P, _I, _I, _I, _I, _I, _P],
     "affgw_maxpool3s2_bwd": [_P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "affgw_maxpool3_fwd": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
+    "affgw_maxpool3_bwd": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "affgw_resize_bilinear_fwd": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "affgw_resize_bilinear_bwd": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "affgw_add_act": [_P, _P, _P, _I, _L, _I, _P],

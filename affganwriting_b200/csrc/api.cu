@@ -76,8 +76,8 @@ int gap_fwd(const void* x, void* out, int dt, int N, long long P, int C, cudaStr
 int bcast_add(const void* a, const void* v, void* out, int dt, int N, long long P, int C, float scale, cudaStream_t st);
 int add2(const void* a, const void* b, void* out, int dt, long long n, cudaStream_t st);
 int add_act(const void* a, const void* b, void* out, int dt, long long n, int act, cudaStream_t st);
-int maxpool3s2_fwd(const void* x, void* y, int dt, int N, int H, int W, int C, cudaStream_t st);
-int maxpool3s2_bwd(const void* dy, const void* x, void* dx, int dt, int N, int H, int W, int C, cudaStream_t st);
+int maxpool3_fwd(const void* x, void* y, int dt, int N, int H, int W, int C, int SY, int SX, cudaStream_t st);
+int maxpool3_bwd(const void* dy, const void* x, void* dx, int dt, int N, int H, int W, int C, int SY, int SX, cudaStream_t st);
 int resize_bilinear_fwd(const void* x, void* y, int dt, int N, int H, int W, int C, int Ho, int Wo, cudaStream_t st);
 int resize_bilinear_bwd(const void* dy, float* dx, int dt, int N, int H, int W, int C, int Ho, int Wo, cudaStream_t st);
 int act_bwd(const void* dy, const void* y, void* dz, int dt, long long n, int act, cudaStream_t st);
@@ -118,7 +118,8 @@ static int make_geom(const affgw_conv_desc* d, ConvGeom& g, int zero_insert = 1)
     AFFGW_CHECK(d != nullptr, "conv: null descriptor");
     AFFGW_CHECK(d->N > 0 && d->H > 0 && d->W > 0 && d->Cin > 0 && d->Cout > 0 && d->KH > 0 && d->KW > 0,
                 "conv: non-positive extent");
-    AFFGW_CHECK(d->stride >= 1 && d->pad >= 0, "conv: bad stride/pad");
+    AFFGW_CHECK(d->stride >= 1 && d->stride_w >= 0 && d->pad >= 0, "conv: bad stride/pad");
+    const int sw = d->stride_w ? d->stride_w : d->stride;
     AFFGW_CHECK(d->upsample == 1 || d->upsample == 2, "conv: upsample must be 1 or 2");
     AFFGW_CHECK(d->pad_mode >= 0 && d->pad_mode <= 2, "conv: bad pad_mode");
     AFFGW_CHECK(dt_ok(d->x_dtype) && dt_ok(d->w_dtype) && dt_ok(d->y_dtype), "conv: bad dtype");
@@ -126,13 +127,14 @@ static int make_geom(const affgw_conv_desc* d, ConvGeom& g, int zero_insert = 1)
     g.N = d->N; g.H = d->H; g.W = d->W; g.Cin = d->Cin;
     g.Cout = d->Cout; g.KH = d->KH; g.KW = d->KW;
     g.stride = d->stride; g.pad = d->pad; g.pad_mode = d->pad_mode; g.up = d->upsample; g.zi = zero_insert;
+    g.stride_w = sw; g.zi_w = zero_insert;
     g.Ho = d->Ho; g.Wo = d->Wo;
     g.in_pitch = d->in_pitch; g.out_pitch = d->out_pitch;
     g.pre_act = d->pre_act; g.post_act = d->post_act;
     g.Hv = d->H * d->upsample; g.Wv = d->W * d->upsample;
     g.Ktot = d->KH * d->KW * d->Cin;
     g.M = (long long)d->N * d->Ho * d->Wo;
-    const int eh = (g.Hv + 2 * d->pad - d->KH) / d->stride + 1, ew = (g.Wv + 2 * d->pad - d->KW) / d->stride + 1;
+    const int eh = (g.Hv + 2 * d->pad - d->KH) / d->stride + 1, ew = (g.Wv + 2 * d->pad - d->KW) / sw + 1;
     AFFGW_CHECK(eh == d->Ho && ew == d->Wo, "conv: output extent %dx%d does not match the geometry (%dx%d)", d->Ho, d->Wo,
                 eh, ew);
     if (d->pad_mode == PAD_REFLECT) AFFGW_CHECK(d->pad < g.Hv && d->pad < g.Wv, "conv: reflect pad >= input extent");
@@ -257,7 +259,7 @@ static int make_dgrad(const affgw_conv_desc* d, affgw_conv_desc& dd, bool& direc
     Wp = d->W * d->upsample + 2 * d->pad;
     dd = *d;
     dd.N = d->N; dd.H = d->Ho; dd.W = d->Wo; dd.Cin = d->Cout; dd.Cout = d->Cin;
-    dd.stride = 1; dd.pad_mode = PAD_ZERO; dd.upsample = 1;
+    dd.stride = 1; dd.stride_w = 0; dd.pad_mode = PAD_ZERO; dd.upsample = 1;
     dd.pad = direct ? d->KH - 1 - d->pad : d->KH - 1;
     dd.Ho = direct ? d->H : Hp;
     dd.Wo = direct ? d->W : Wp;
@@ -271,10 +273,11 @@ static int make_dgrad(const affgw_conv_desc* d, affgw_conv_desc& dd, bool& direc
 static void dgrad_geom(const affgw_conv_desc* d, const affgw_conv_desc& dd, ConvGeom& g) {
     // built by hand: the virtual input is dY zero-inserted by the forward stride
     g.N = dd.N; g.H = dd.H; g.W = dd.W; g.Cin = dd.Cin; g.Cout = dd.Cout; g.KH = dd.KH; g.KW = dd.KW;
-    g.stride = 1; g.pad = dd.pad; g.pad_mode = PAD_ZERO; g.up = 1; g.zi = d->stride;
+    const int sw = d->stride_w ? d->stride_w : d->stride;
+    g.stride = g.stride_w = 1; g.pad = dd.pad; g.pad_mode = PAD_ZERO; g.up = 1; g.zi = d->stride; g.zi_w = sw;
     g.Ho = dd.Ho; g.Wo = dd.Wo; g.in_pitch = dd.in_pitch; g.out_pitch = dd.out_pitch;
     g.pre_act = ACT_NONE; g.post_act = ACT_NONE;
-    g.Hv = (dd.H - 1) * d->stride + 1; g.Wv = (dd.W - 1) * d->stride + 1;
+    g.Hv = (dd.H - 1) * d->stride + 1; g.Wv = (dd.W - 1) * sw + 1;
     if (d->algo == AFFGW_ALGO_TCGEN05) g.Cin = dd.in_pitch;       // stored channels of the dY planes
     g.Ktot = g.KH * g.KW * g.Cin;
     g.M = (long long)g.N * g.Ho * g.Wo;
@@ -456,7 +459,7 @@ static int thin_geom(const affgw_conv_desc* d, ConvGeom& g) {
     AFFGW_CHECK(d->x_dtype == AFFGW_F32 && d->y_dtype == AFFGW_F32, "conv_thin: fp32 tensors only");
     AFFGW_CHECK(d->KH == d->KW && d->in_pitch == d->Cin && d->out_pitch == d->Cout, "conv_thin: dense square-filter convolution expected");
     AFFGW_CHECK(d->pre_act == ACT_NONE, "conv_thin: no activation-first variant");
-    AFFGW_CHECK(conv_thin_ok(d->Cin, d->Cout, d->KH, d->stride, d->upsample) != 0,
+    AFFGW_CHECK(conv_thin_ok(d->Cin, d->Cout, d->KH, d->stride_w > d->stride ? d->stride_w : d->stride, d->upsample) != 0,
                 "conv_thin: %d -> %d channels, %dx%d, stride %d is not a single-channel-sided stencil", d->Cin, d->Cout, d->KH,
                 d->KW, d->stride);
     return 0;
@@ -466,7 +469,7 @@ int affgw_conv_thin_supported(const affgw_conv_desc* d) {
     if (!d || d->x_dtype != AFFGW_F32 || d->y_dtype != AFFGW_F32 || d->KH != d->KW || d->in_pitch != d->Cin ||
         d->out_pitch != d->Cout || d->pre_act != ACT_NONE || make_geom(d, g))
         return 0;
-    return conv_thin_ok(d->Cin, d->Cout, d->KH, d->stride, d->upsample);
+    return conv_thin_ok(d->Cin, d->Cout, d->KH, d->stride_w > d->stride ? d->stride_w : d->stride, d->upsample);
 }
 static long long thin_scratch_bytes(const affgw_conv_desc* d) {
     return (long long)d->KH * d->KW * (d->Cin > d->Cout ? d->Cin : d->Cout) * 4;
@@ -578,11 +581,19 @@ int affgw_bcast_add(const void* a, const void* v, void* out, int dt, int N, long
 }
 int affgw_maxpool3s2_fwd(const void* x, void* y, int dt, int N, int H, int W, int C, void* s) {
     REQ(x && y && dt_ok(dt) && N > 0 && H > 1 && W > 1 && C > 0, "maxpool3s2_fwd");
-    return maxpool3s2_fwd(x, y, dt, N, H, W, C, S(s));
+    return maxpool3_fwd(x, y, dt, N, H, W, C, 2, 2, S(s));
 }
 int affgw_maxpool3s2_bwd(const void* dy, const void* x, void* dx, int dt, int N, int H, int W, int C, void* s) {
     REQ(dy && x && dx && dt_ok(dt) && N > 0 && H > 1 && W > 1 && C > 0, "maxpool3s2_bwd");
-    return maxpool3s2_bwd(dy, x, dx, dt, N, H, W, C, S(s));
+    return maxpool3_bwd(dy, x, dx, dt, N, H, W, C, 2, 2, S(s));
+}
+int affgw_maxpool3_fwd(const void* x, void* y, int dt, int N, int H, int W, int C, int sy, int sx, void* s) {
+    REQ(x && y && dt_ok(dt) && N > 0 && H > 1 && W > 1 && C > 0 && (sy == 1 || sy == 2) && (sx == 1 || sx == 2), "maxpool3_fwd");
+    return maxpool3_fwd(x, y, dt, N, H, W, C, sy, sx, S(s));
+}
+int affgw_maxpool3_bwd(const void* dy, const void* x, void* dx, int dt, int N, int H, int W, int C, int sy, int sx, void* s) {
+    REQ(dy && x && dx && dt_ok(dt) && N > 0 && H > 1 && W > 1 && C > 0 && (sy == 1 || sy == 2) && (sx == 1 || sx == 2), "maxpool3_bwd");
+    return maxpool3_bwd(dy, x, dx, dt, N, H, W, C, sy, sx, S(s));
 }
 int affgw_resize_bilinear_fwd(const void* x, void* y, int dt, int N, int H, int W, int C, int Ho, int Wo, void* s) {
     REQ(x && y && dt_ok(dt) && N > 0 && H > 0 && W > 0 && C > 0 && Ho > 0 && Wo > 0, "resize_bilinear_fwd");

@@ -108,7 +108,8 @@ __device__ __forceinline__ int map_coord(int v, int V, int pad_mode, int up, int
 struct ConvGeom {
     int N, H, W, Cin;        // stored input
     int Cout, KH, KW;
-    int stride, pad, pad_mode, up, zi;
+    int stride, pad, pad_mode, up, zi;   // stride / zi: rows
+    int stride_w, zi_w;                  // columns (differ from the row values only for Resnet18.py's (2,1) stem)
     int Ho, Wo;              // output extent
     int in_pitch, out_pitch; // elements between consecutive pixels (>= Cin / Cout)
     int pre_act, post_act;

@@ -467,7 +467,7 @@ int launch_shift(const ShArgs& args, int smem_bytes, cudaStream_t st) {
 // Is the forward convolution g a position-space convolution?  One rule for forward, dgrad and wgrad so that the operand
 // planes of a layer are built once.
 int conv_shift_ok(const ConvGeom& g) {
-    if (g.stride != 1 || g.zi != 1 || g.KH != g.KW || g.KH > 7) return 0;
+    if (g.stride != 1 || g.stride_w != 1 || g.zi != 1 || g.zi_w != 1 || g.KH != g.KW || g.KH > 7) return 0;
     // 1x1 filters have no tap reuse to exploit; only the thin ones (the 16/32-channel shortcuts of the discriminator at full
     // resolution) come here, because the bulk-copy pipeline beats the per-thread gather of the im2col kernel for them
     if (g.KH == 1 && (g.Cin > 64 || g.Cout > 64 || (long long)g.H * g.W < 1024)) return 0;

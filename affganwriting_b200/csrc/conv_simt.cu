@@ -36,7 +36,7 @@ conv_fwd_simt_kernel(const TI* __restrict__ x, const TW* __restrict__ w, const f
         oy = (int)(t % g.Ho);
         n_img = (int)(t / g.Ho);
     }
-    const int vy0 = oy * g.stride - g.pad, vx0 = ox * g.stride - g.pad;
+    const int vy0 = oy * g.stride - g.pad, vx0 = ox * g.stride_w - g.pad;
     const TI* xn = x + (long long)n_img * g.H * g.W * g.in_pitch;
     const int wn = n0 + lr;
     const bool nvalid = wn < g.Cout;
@@ -59,7 +59,7 @@ conv_fwd_simt_kernel(const TI* __restrict__ x, const TW* __restrict__ w, const f
                 if (mvalid) {
                     const int ky = tap / g.KW, kx = tap - ky * g.KW;
                     const int sy = map_coord(vy0 + ky, g.Hv, g.pad_mode, g.up, g.zi);
-                    const int sx = map_coord(vx0 + kx, g.Wv, g.pad_mode, g.up, g.zi);
+                    const int sx = map_coord(vx0 + kx, g.Wv, g.pad_mode, g.up, g.zi_w);
                     if (sy >= 0 && sx >= 0)
                         av = act_apply(to_f(xn[((long long)sy * g.W + sx) * g.in_pitch + ci]), g.pre_act);
                 }
@@ -157,7 +157,7 @@ conv_wgrad_simt_kernel(const TI* __restrict__ x, const TG* __restrict__ dy, floa
             n_img = (int)(t / g.Ho);
         }
         const TI* xn = x + (long long)n_img * g.H * g.W * g.in_pitch;
-        const int vy0 = oy * g.stride - g.pad, vx0 = ox * g.stride - g.pad;
+        const int vy0 = oy * g.stride - g.pad, vx0 = ox * g.stride_w - g.pad;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             float dv = 0.f, xv = 0.f;
@@ -166,7 +166,7 @@ conv_wgrad_simt_kernel(const TI* __restrict__ x, const TG* __restrict__ dy, floa
                 if (co < g.Cout) dv = to_f(dy[m * g.out_pitch + co]);
                 if (kval[j]) {
                     const int sy = map_coord(vy0 + ky[j], g.Hv, g.pad_mode, g.up, g.zi);
-                    const int sx = map_coord(vx0 + kx[j], g.Wv, g.pad_mode, g.up, g.zi);
+                    const int sx = map_coord(vx0 + kx[j], g.Wv, g.pad_mode, g.up, g.zi_w);
                     if (sy >= 0 && sx >= 0)
                         xv = act_apply(to_f(xn[((long long)sy * g.W + sx) * g.in_pitch + ci[j]]), g.pre_act);
                 }

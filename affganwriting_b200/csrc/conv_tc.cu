@@ -185,7 +185,7 @@ conv_igemm_tcgen05_kernel(const __grid_constant__ TcArgs a) {
                     n = (int)(q / g.Ho);
                 }
                 vy0[i] = oy * g.stride - g.pad;
-                vx0[i] = ox * g.stride - g.pad;
+                vx0[i] = ox * g.stride_w - g.pad;
                 nbase[i] = n * g.H * g.W;
             }
             const bf16* wt = a.w_tiles + (size_t)nt * KB * (NPL * BN * BK);
@@ -199,7 +199,7 @@ conv_igemm_tcgen05_kernel(const __grid_constant__ TcArgs a) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     sy[i] = map_coord(vy0[i] + ky, g.Hv, g.pad_mode, g.up, g.zi);
-                    sx[i] = map_coord(vx0[i] + kx, g.Wv, g.pad_mode, g.up, g.zi);
+                    sx[i] = map_coord(vx0[i] + kx, g.Wv, g.pad_mode, g.up, g.zi_w);
                 }
             }
             for (int kb = kb0; kb < kb1; ++kb, ++it) {
@@ -231,7 +231,7 @@ conv_igemm_tcgen05_kernel(const __grid_constant__ TcArgs a) {
                         yy = sy[i]; xx = sx[i];
                     } else {
                         yy = map_coord(vy0[i] + ky, g.Hv, g.pad_mode, g.up, g.zi);
-                        xx = map_coord(vx0[i] + kx, g.Wv, g.pad_mode, g.up, g.zi);
+                        xx = map_coord(vx0[i] + kx, g.Wv, g.pad_mode, g.up, g.zi_w);
                     }
                     const bool ok = mvalid[i] && kvalid && yy >= 0 && xx >= 0;
                     const bf16* src = ok ? a.x + ((size_t)(nbase[i] + yy * g.W + xx) * g.Cin + coff) : a.x;
@@ -256,7 +256,7 @@ conv_igemm_tcgen05_kernel(const __grid_constant__ TcArgs a) {
                             for (int i = 0; i < 8; ++i) sy[i] = map_coord(vy0[i] + ky, g.Hv, g.pad_mode, g.up, g.zi);
                         }
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) sx[i] = map_coord(vx0[i] + kx, g.Wv, g.pad_mode, g.up, g.zi);
+                        for (int i = 0; i < 8; ++i) sx[i] = map_coord(vx0[i] + kx, g.Wv, g.pad_mode, g.up, g.zi_w);
                     }
                 }
             }

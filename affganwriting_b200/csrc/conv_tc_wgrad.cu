@@ -171,7 +171,7 @@ conv_wgrad_tcgen05_kernel(const __grid_constant__ WgArgs a) {
                     int sy = 0, sx = 0;
                     if (ok) {
                         sy = map_fast(oy[j] * g.stride + dyo[i], g.Hv, g.pad_mode, g.up);
-                        sx = map_fast(ox[j] * g.stride + dxo[i], g.Wv, g.pad_mode, g.up);
+                        sx = map_fast(ox[j] * g.stride_w + dxo[i], g.Wv, g.pad_mode, g.up);
                         ok = sy >= 0 && sx >= 0;
                     }
                     const bf16* src = ok ? a.x + ((size_t)((size_t)nimg[j] * g.H * g.W + (size_t)sy * g.W + sx) * g.Cin + coff[i])
@@ -312,7 +312,7 @@ int conv_tc_block_n(int cout);
 // g.Cin must be the STORED channel count of the x planes, g.out_pitch that of the dY planes (multiples of 8)
 int conv_wgrad_tc_ok(const ConvGeom& g) {
     if (g.Cin % 8 != 0 || g.in_pitch != g.Cin || g.out_pitch % 8 != 0 || g.out_pitch < g.Cout) return 0;
-    if (g.pre_act != ACT_NONE || g.zi != 1) return 0;
+    if (g.pre_act != ACT_NONE || g.zi != 1 || g.zi_w != 1) return 0;
     if ((long long)g.N * g.H * g.W >= (1LL << 31)) return 0;
     return conv_tc_block_n(g.Cout);
 }

@@ -322,7 +322,7 @@ static int launch_corr(const float* many, const float* one, float* dw, int N, in
 
 // y = act(conv(pad(x)) + bias).  scratch: K*K*max(Cin,Cout) floats (re-laid filter for the 1 -> N kernel)
 int conv_thin_fwd(const float* x, const float* w, const float* bias, float* y, float* scratch, const ConvGeom& g, cudaStream_t st) {
-    const int kind = conv_thin_ok(g.Cin, g.Cout, g.KH, g.stride, g.up);
+    const int kind = conv_thin_ok(g.Cin, g.Cout, g.KH, max(g.stride, g.stride_w), g.up);
     if (!kind || g.KH != g.KW || g.pre_act != ACT_NONE) {
         affgw_set_error("conv_thin: not a single-channel-sided stride-1 convolution");
         return -1;
@@ -337,7 +337,7 @@ int conv_thin_fwd(const float* x, const float* w, const float* bias, float* y, f
 
 // gradient w.r.t. the PADDED input frame [N][H + 2 pad][W + 2 pad][Cin] (zero-padded correlation of dY with the flipped filter)
 int conv_thin_dgrad_frame(const float* dy, const float* w, float* dframe, float* scratch, const ConvGeom& g, cudaStream_t st) {
-    const int kind = conv_thin_ok(g.Cin, g.Cout, g.KH, g.stride, g.up);
+    const int kind = conv_thin_ok(g.Cin, g.Cout, g.KH, max(g.stride, g.stride_w), g.up);
     const int K = g.KH, Hp = g.H + 2 * g.pad, Wp = g.W + 2 * g.pad;
     if (!kind) {
         affgw_set_error("conv_thin: not a single-channel-sided stride-1 convolution");
@@ -356,7 +356,7 @@ int conv_thin_dgrad_frame(const float* dy, const float* w, float* dframe, float*
 
 // dw (OIHW, one of O / I is 1) += correlation; the caller zeroes dw
 int conv_thin_wgrad(const float* x, const float* dy, float* dw, const ConvGeom& g, cudaStream_t st) {
-    const int kind = conv_thin_ok(g.Cin, g.Cout, g.KH, g.stride, g.up);
+    const int kind = conv_thin_ok(g.Cin, g.Cout, g.KH, max(g.stride, g.stride_w), g.up);
     if (!kind) {
         affgw_set_error("conv_thin: not a single-channel-sided stride-1 convolution");
         return -1;

@@ -287,9 +287,11 @@ __global__ void add2_kernel(const T* __restrict__ a, const T* __restrict__ b, T*
 }
 
 
-// ---------------------------------------------------------------- max pool 3x3 stride 2 pad 1 (torchvision ResNet stem)
+// ---------------------------------------------------------------- max pool 3x3 pad 1, strides (SY, SX) in {1, 2}
+// (2,2): torchvision ResNet stem; (2,1) and (1,1): Resnet18.py:45-46
 template <typename T, int VEC>
-__global__ void maxpool3s2_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int H, int W, int C, int Ho, int Wo) {
+__global__ void maxpool3s2_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int H, int W, int C, int Ho, int Wo,
+                                      int SY, int SX) {
     const int cv = C / VEC;
     const long long total = (long long)N * Ho * Wo * cv;
     GRID_STRIDE(idx, total) {
@@ -303,10 +305,10 @@ __global__ void maxpool3s2_fwd_kernel(const T* __restrict__ x, T* __restrict__ y
 #pragma unroll
         for (int i = 0; i < VEC; ++i) m[i] = -INFINITY;
         for (int ky = 0; ky < 3; ++ky) {
-            const int yy = 2 * oy - 1 + ky;
+            const int yy = SY * oy - 1 + ky;
             if (yy < 0 || yy >= H) continue;
             for (int kx = 0; kx < 3; ++kx) {
-                const int xx = 2 * ox - 1 + kx;
+                const int xx = SX * ox - 1 + kx;
                 if (xx < 0 || xx >= W) continue;
                 float v[VEC];
                 ldv<VEC>(x + (((long long)n * H + yy) * W + xx) * C + c, v);
@@ -321,7 +323,7 @@ __global__ void maxpool3s2_fwd_kernel(const T* __restrict__ x, T* __restrict__ y
 // gather form: input pixel (yy, xx) receives dy of every window whose FIRST maximum in scan order it is (PyTorch tie rule)
 template <typename T, int VEC>
 __global__ void maxpool3s2_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, T* __restrict__ dx, int N, int H, int W,
-                                      int C, int Ho, int Wo) {
+                                      int C, int Ho, int Wo, int SY, int SX) {
     const int cv = C / VEC;
     const long long total = (long long)N * H * W * cv;
     GRID_STRIDE(idx, total) {
@@ -335,20 +337,20 @@ __global__ void maxpool3s2_bwd_kernel(const T* __restrict__ dy, const T* __restr
         ldv<VEC>(x + idx * VEC, mine);
 #pragma unroll
         for (int i = 0; i < VEC; ++i) out[i] = 0.f;
-        // windows (oy, ox) with 2*oy - 1 <= yy <= 2*oy + 1
-        for (int oy = (yy + 1) / 2 - ((yy + 1) % 2 == 0 ? 1 : 0); oy <= (yy + 1) / 2; ++oy) {
-            if (oy < 0 || oy >= Ho) continue;
-            for (int ox = (xx + 1) / 2 - ((xx + 1) % 2 == 0 ? 1 : 0); ox <= (xx + 1) / 2; ++ox) {
-                if (ox < 0 || ox >= Wo) continue;
-                const int my_pos = (yy - (2 * oy - 1)) * 3 + (xx - (2 * ox - 1));
+        // windows (oy, ox) with S*o - 1 <= coordinate <= S*o + 1, i.e. ceil((c - 1) / S) <= o <= floor((c + 1) / S)
+        const int oy_lo = yy <= 1 ? 0 : (yy - 1 + SY - 1) / SY, oy_hi = min((yy + 1) / SY, Ho - 1);
+        const int ox_lo = xx <= 1 ? 0 : (xx - 1 + SX - 1) / SX, ox_hi = min((xx + 1) / SX, Wo - 1);
+        for (int oy = oy_lo; oy <= oy_hi; ++oy) {
+            for (int ox = ox_lo; ox <= ox_hi; ++ox) {
+                const int my_pos = (yy - (SY * oy - 1)) * 3 + (xx - (SX * ox - 1));
                 bool win[VEC];
 #pragma unroll
                 for (int i = 0; i < VEC; ++i) win[i] = true;
                 for (int ky = 0; ky < 3; ++ky) {
-                    const int y2 = 2 * oy - 1 + ky;
+                    const int y2 = SY * oy - 1 + ky;
                     if (y2 < 0 || y2 >= H) continue;
                     for (int kx = 0; kx < 3; ++kx) {
-                        const int x2 = 2 * ox - 1 + kx;
+                        const int x2 = SX * ox - 1 + kx;
                         if (x2 < 0 || x2 >= W) continue;
                         const int pos = ky * 3 + kx;
                         if (pos == my_pos) continue;
@@ -779,19 +781,19 @@ int bcast_add(const void* a, const void* v, void* out, int dt, int N, long long 
     return 0;
 }
 
-int maxpool3s2_fwd(const void* x, void* y, int dt, int N, int H, int W, int C, cudaStream_t st) {
-    const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+int maxpool3_fwd(const void* x, void* y, int dt, int N, int H, int W, int C, int SY, int SX, cudaStream_t st) {
+    const int Ho = (H - 1) / SY + 1, Wo = (W - 1) / SX + 1;
     const long long total = (long long)N * Ho * Wo * VECN(C);
-#define CALL(T, V) maxpool3s2_fwd_kernel<T, V><<<ew_blocks(total), 256, 0, st>>>((const T*)x, (T*)y, N, H, W, C, Ho, Wo)
+#define CALL(T, V) maxpool3s2_fwd_kernel<T, V><<<ew_blocks(total), 256, 0, st>>>((const T*)x, (T*)y, N, H, W, C, Ho, Wo, SY, SX)
     DISPATCH_T_VEC(dt, C, CALL);
 #undef CALL
     AFFGW_LAUNCH_CHECK("maxpool3s2_fwd");
     return 0;
 }
-int maxpool3s2_bwd(const void* dy, const void* x, void* dx, int dt, int N, int H, int W, int C, cudaStream_t st) {
-    const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+int maxpool3_bwd(const void* dy, const void* x, void* dx, int dt, int N, int H, int W, int C, int SY, int SX, cudaStream_t st) {
+    const int Ho = (H - 1) / SY + 1, Wo = (W - 1) / SX + 1;
     const long long total = (long long)N * H * W * VECN(C);
-#define CALL(T, V) maxpool3s2_bwd_kernel<T, V><<<ew_blocks(total), 256, 0, st>>>((const T*)dy, (const T*)x, (T*)dx, N, H, W, C, Ho, Wo)
+#define CALL(T, V) maxpool3s2_bwd_kernel<T, V><<<ew_blocks(total), 256, 0, st>>>((const T*)dy, (const T*)x, (T*)dx, N, H, W, C, Ho, Wo, SY, SX)
     DISPATCH_T_VEC(dt, C, CALL);
 #undef CALL
     AFFGW_LAUNCH_CHECK("maxpool3s2_bwd");

@@ -38,4 +38,11 @@ def install(ref_blocks="blocks", ref_modules="modules_tro"):
     if hasattr(rm, "ImageEncoderResNet50"):
         rm.ImageEncoderResNet50 = _resnet.ImageEncoderResNet50
         done.append((ref_modules, "ImageEncoderResNet50"))
+    # the stand-alone ResNet-18 (Resnet18.py), when the caller has imported it
+    r18 = sys.modules.get("Resnet18")
+    if r18 is not None:
+        from . import Resnet18 as _r18
+        for n in ("conv3x3", "BasicBlock", "ResNet18"):
+            setattr(r18, n, getattr(_r18, n))
+            done.append(("Resnet18", n))
     return done

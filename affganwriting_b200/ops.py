@@ -243,7 +243,7 @@ def input_to_internal(x, c_pad=None, dtype=None):
 
 
 # ------------------------------------------------------------------------------------------------ convolution
-ConvCfg = collections.namedtuple("ConvCfg", "stride pad pad_mode upsample pre_act post_act out_dtype")
+ConvCfg = collections.namedtuple("ConvCfg", "stride pad pad_mode upsample pre_act post_act out_dtype stride_w")
 
 
 class _WeightCache:
@@ -364,7 +364,7 @@ def _conv_geom(x, weight, cfg):
         raise RuntimeError(f"conv2d: input has {cx} channels, weight expects {ci}")
     hv, wv = h * cfg.upsample, w * cfg.upsample
     ho = (hv + 2 * cfg.pad - kh) // cfg.stride + 1
-    wo = (wv + 2 * cfg.pad - kw) // cfg.stride + 1
+    wo = (wv + 2 * cfg.pad - kw) // cfg.stride_w + 1
     return dict(N=n, H=h, W=w, Cx=cx, pitch=pitch, Cout=co, Cin=ci, KH=kh, KW=kw, Ho=ho, Wo=wo, two_d=x.dim() == 2)
 
 
@@ -378,6 +378,7 @@ def _desc(g, cfg, cin, x_dt, w_dt, y_dt, algo, in_pitch=None, out_pitch=None, pa
     d.pre_act, d.post_act = L.ACT[cfg.pre_act if pre_act is None else pre_act], L.ACT[cfg.post_act]
     d.x_dtype, d.w_dtype, d.y_dtype = x_dt, w_dt, y_dt
     d.algo, d.passes, d.grad_dtype = algo, passes, grad_dt
+    d.stride_w = cfg.stride_w
     return d
 
 
@@ -399,7 +400,7 @@ class _Conv2d(Function):
             addend = _dense_cl(addend, y_dtype)
         b32 = None if bias is None else bias.detach()
         flops = 2.0 * g["N"] * g["Ho"] * g["Wo"] * g["Cout"] * g["Cin"] * g["KH"] * g["KW"]
-        tag = "%dx%dx%d c%d->%d k%d s%d u%d" % (g["N"], g["H"], g["W"], g["Cin"], g["Cout"], g["KH"], cfg.stride, cfg.upsample)
+        tag = "%dx%dx%d c%d->%d k%d s%d u%d" % (g["N"], g["H"], g["W"], g["Cin"], g["Cout"], g["KH"], cfg.stride if cfg.stride == cfg.stride_w else cfg.stride * 10 + cfg.stride_w, cfg.upsample)
         planes = None
         thin = False
         if use_tc and addend is None and cfg.pre_act == "none" and not g["two_d"] and g["pitch"] == g["Cin"] \
@@ -557,7 +558,8 @@ class _Conv2d(Function):
 def conv2d(x, weight, bias=None, stride=1, pad=0, pad_mode="zero", upsample=1, pre_act="none", post_act="none",
            addend=None, out_dtype=None):
     """pad -> [nearest x2] -> conv -> +bias -> +addend -> activation   (blocks.py:150-163, modules_tro.py:594-598)"""
-    cfg = ConvCfg(int(stride), int(pad), pad_mode, int(upsample), pre_act, post_act, out_dtype)
+    sh, sw = (stride if isinstance(stride, (tuple, list)) else (stride, stride))     # (rows, columns), nn.Conv2d order
+    cfg = ConvCfg(int(sh), int(pad), pad_mode, int(upsample), pre_act, post_act, out_dtype, int(sw))
     return _Conv2d.apply(x, weight, bias, addend, cfg)
 
 
@@ -702,16 +704,18 @@ def max_pool2(x):
     return _MaxPool2.apply(x)
 
 
-class _MaxPool3s2(Function):
-    """nn.MaxPool2d(kernel_size=3, stride=2, padding=1) (torchvision ResNet stem)."""
+class _MaxPool3(Function):
+    """nn.MaxPool2d(kernel_size=3, stride=(sy, sx), padding=1): (2, 2) is the torchvision ResNet stem, (2, 1) and (1, 1) are
+    Resnet18.py:45-46."""
 
     @staticmethod
-    def forward(ctx, x):
+    def forward(ctx, x, sy, sx):
         x = _dense_cl(x)
         n, c, h, w = x.shape
-        y = empty_cl(n, c, (h - 1) // 2 + 1, (w - 1) // 2 + 1, x.dtype, x.device)
-        L.call("affgw_maxpool3s2_fwd", x.data_ptr(), y.data_ptr(), L.dt(x), n, h, w, c, L.stream())
+        y = empty_cl(n, c, (h - 1) // sy + 1, (w - 1) // sx + 1, x.dtype, x.device)
+        L.call("affgw_maxpool3_fwd", x.data_ptr(), y.data_ptr(), L.dt(x), n, h, w, c, sy, sx, L.stream())
         ctx.save_for_backward(x)
+        ctx.strides = (sy, sx)
         return y
 
     @staticmethod
@@ -720,12 +724,17 @@ class _MaxPool3s2(Function):
         n, c, h, w = x.shape
         dy = _dense_cl(dy, x.dtype)
         dx = torch.empty_like(x)
-        L.call("affgw_maxpool3s2_bwd", dy.data_ptr(), x.data_ptr(), dx.data_ptr(), L.dt(x), n, h, w, c, L.stream())
-        return dx
+        L.call("affgw_maxpool3_bwd", dy.data_ptr(), x.data_ptr(), dx.data_ptr(), L.dt(x), n, h, w, c, *ctx.strides, L.stream())
+        return dx, None, None
+
+
+def max_pool3(x, stride=2):
+    sy, sx = stride if isinstance(stride, (tuple, list)) else (stride, stride)
+    return _MaxPool3.apply(x, int(sy), int(sx))
 
 
 def max_pool3s2(x):
-    return _MaxPool3s2.apply(x)
+    return _MaxPool3.apply(x, 2, 2)
 
 
 class _ResizeBilinear(Function):

@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define AFFGW_VERSION 105
+#define AFFGW_VERSION 106
 
 enum { AFFGW_DT_F32 = 0, AFFGW_DT_BF16 = 1 };
 enum { AFFGW_ACT_NONE = 0, AFFGW_ACT_RELU = 1, AFFGW_ACT_LRELU = 2, AFFGW_ACT_TANH = 3 };
@@ -51,6 +51,8 @@ typedef struct affgw_conv_desc {
      * out_pitch = pitch of y (forward) or c_store of the dY planes (dgrad / wgrad).                              */
     int32_t passes;              /* 1: a_hi*w_hi; 3: split-bf16 a_hi*w_hi + a_lo*w_hi + a_hi*w_lo                */
     int32_t grad_dtype;          /* dtype of dx (and of x when the fold needs the pre-activation derivative)   */
+    int32_t stride_w;            /* column stride when it differs from `stride` (rows): Resnet18.py:43 uses
+                                    stride=(2, 1); 0 = same as stride                                          */
 } affgw_conv_desc;
 
 int affgw_version(void);
@@ -161,6 +163,10 @@ int affgw_resize_nearest_bwd(const void* dy, void* dx, int dtype, int N, int H, 
  * out = act(a + b) for the residual tails */
 int affgw_maxpool3s2_fwd(const void* x, void* y, int dtype, int N, int H, int W, int C, void* stream);
 int affgw_maxpool3s2_bwd(const void* dy, const void* x, void* dx, int dtype, int N, int H, int W, int C, void* stream);
+/* nn.MaxPool2d(3, stride=(sy, sx), padding=1), sy, sx in {1, 2}: the (2,1) and (1,1) pools of Resnet18.py:45-46;
+ * y is [N, (H-1)/sy+1, (W-1)/sx+1, C] */
+int affgw_maxpool3_fwd(const void* x, void* y, int dtype, int N, int H, int W, int C, int sy, int sx, void* stream);
+int affgw_maxpool3_bwd(const void* dy, const void* x, void* dx, int dtype, int N, int H, int W, int C, int sy, int sx, void* stream);
 int affgw_resize_bilinear_fwd(const void* x, void* y, int dtype, int N, int H, int W, int C, int Ho, int Wo, void* stream);
 int affgw_resize_bilinear_bwd(const void* dy, float* dx, int dtype, int N, int H, int W, int C, int Ho, int Wo, void* stream);
 int affgw_add_act(const void* a, const void* b, void* out, int dtype, long long n, int act, void* stream);

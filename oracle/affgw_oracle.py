@@ -344,6 +344,33 @@ def resnet_encoder(x, sd, prefix="enc_image.", arch="resnet50", training=True, s
     return results
 
 
+def resnet18_standalone(x, sd, prefix="", training=True, stats=None):
+    """Resnet18.py:38-88 (`ResNet18`, `BasicBlock` :9-36): conv3x3 stride (2, 1) + BN + ReLU, MaxPool2d(3, (2, 1), 1) -> map 0;
+    three stages of two BasicBlocks (first block of each stage: stride 2 on conv1 and a conv1x1/s2 + BN shortcut) -> maps
+    1..3; MaxPool2d(3, 1, 1) of the last -> map 4.  No biases, BatchNorm eps 1e-5, widths nb/4, nb/4, nb/2, nb."""
+    def bn(t, name, relu=False):
+        t = batch_norm(t, sd, name, training, stats)
+        return q(torch.relu(t)) if relu else q(t)
+
+    x = q(x)
+    x = bn(q(_conv(x, sd[prefix + "conv1.weight"], None, stride=(2, 1), padding=1)), prefix + "bn1.", relu=True)
+    x = F.max_pool2d(x, 3, (2, 1), 1)
+    results = [x]
+    for li in (1, 2, 3):
+        for bi in range(2):
+            b = f"{prefix}layer{li}.{bi}."
+            stride = 2 if bi == 0 else 1
+            out = bn(q(_conv(x, sd[b + "conv1.weight"], None, stride=stride, padding=1)), b + "bn1.", relu=True)
+            out = bn(q(_conv(out, sd[b + "conv2.weight"], None, padding=1)), b + "bn2.")
+            identity = x
+            if b + "downsample.0.weight" in sd:
+                identity = bn(q(_conv(x, sd[b + "downsample.0.weight"], None, stride=stride)), b + "downsample.1.")
+            x = q(torch.relu(out + identity))
+        results.append(x)
+    results.append(F.max_pool2d(x, 3, 1, 1))
+    return results
+
+
 def text_encoder(label, f_xs_shape, sd, prefix="enc_text.", training=True, stats=None):
     """modules_tro.py:285-317 -> (adain params [B,4096], content map [B,512,h,w])."""
     emb = q(sd[prefix + "embed.weight"][label])                        # b, t, 64

@@ -108,3 +108,93 @@ def test_generator_with_resnet50_encoder_matches_oracle(specs):
             gen.zero_grad()
         finally:
             A.set_precision("fp32")
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Resnet18.py:4-88 - the stand-alone ResNet18 / BasicBlock classes (row stride 2, column stride 1 in the stem and first pool)
+S18_CASES = {"nb384_c50": (384, 50, 2), "nb512_c3": (512, 3, 3)}
+
+
+def _s18_spec(case):
+    return json.load(open(os.path.join(GOLDEN, "resnet18_standalone_spec.json")))[case]
+
+
+@pytest.mark.parametrize("case", list(S18_CASES))
+def test_resnet18_standalone_keys_match_reference(case):
+    from affganwriting_b200.Resnet18 import ResNet18
+    nb, cin, _ = S18_CASES[case]
+    mine = {k: list(v.shape) for k, v in ResNet18(nb_feat=nb, in_channels=cin).state_dict().items()}
+    assert mine == _s18_spec(case) and list(mine) == list(_s18_spec(case))
+
+
+@pytest.mark.parametrize("case", list(S18_CASES))
+def test_resnet18_standalone_forward_backward(case, mode, golden):
+    from affganwriting_b200.Resnet18 import ResNet18
+    g = golden("resnet18_standalone.npz")
+    nb, cin, batch = S18_CASES[case]
+    net = ResNet18(nb_feat=nb, in_channels=cin)
+    net.load_state_dict(W.make_state(_s18_spec(case)))
+    net = net.cuda().train()
+    x = O.synthetic_batch(batch, cin)["tr_img"].cuda().requires_grad_()
+    res = net(x)
+    loss = sum(r.float().square().mean() for r in res)
+    loss.backward()
+    noise_f, noise_g = float(g[f"{case}.noise.fwd"]), float(g[f"{case}.noise.dx"])
+    ftol = {"fp32": 1e-4, "bf16": 5e-3, "bf16x1": 6e-2}[mode] + 3 * noise_f
+    worst = 0.0
+    for i, r in enumerate(res):
+        assert list(r.shape) == g[f"{case}.result{i}.shape"].tolist()
+        worst = max(worst, rel_err(r[:, :8], _t(g[f"{case}.result{i}.head"])))
+    print(f"\n[{mode}] Resnet18.py {case}: worst map error vs reference {worst:.3e} (tolerance {ftol:.1e})")
+    assert worst <= ftol
+    assert abs(float(loss) - float(g[f"{case}.loss"])) <= 10 * ftol * float(g[f"{case}.loss"])
+    if mode == "bf16x1":
+        return
+    gtol = {"fp32": 2e-3, "bf16": 2e-2}[mode] + 4 * noise_g
+    dx = x.grad.cpu()
+    assert abs(float(dx.norm()) / float(g[f"{case}.dx.norm"]) - 1) <= gtol
+    assert cosine(dx[:, :3, ::4, ::4], _t(g[f"{case}.dx.head"])) >= 1 - gtol
+    assert cosine(net.conv1.weight.grad[:8].cpu(), _t(g[f"{case}.grad.conv1"])) >= 1 - gtol
+    ref_norm = dict(zip(g[f"{case}.grad.keys"].tolist(), g[f"{case}.grad.norms"].tolist()))
+    bad = [(k, float(p.grad.norm()) / ref_norm[k]) for k, p in net.named_parameters()
+           if ref_norm[k] > 1e-6 and abs(float(p.grad.norm()) / ref_norm[k] - 1) > 5 * gtol]
+    assert len(bad) <= len(ref_norm) // 20, bad[:5]
+    post = net.state_dict()
+    assert int(post["layer2.0.bn1.num_batches_tracked"]) == 1
+    for k in ("bn1.running_mean", "layer1.0.downsample.1.running_var", "layer3.1.bn2.running_mean"):
+        assert rel_err(post[k], _t(g[f"{case}.post.{k}"])) <= {"fp32": 1e-4, "bf16": 5e-3}[mode] + 3 * noise_f, k
+
+
+@pytest.mark.parametrize("strides", [(2, 1), (1, 1), (2, 2), (1, 2)])
+def test_max_pool3_strides_match_torch(strides):
+    """nn.MaxPool2d(3, stride, 1) forward and the first-maximum gradient rule, including ties (Resnet18.py:45-46)."""
+    import torch.nn.functional as F
+    from affganwriting_b200 import ops
+    torch.manual_seed(3)
+    x = torch.randint(-3, 4, (2, 16, 9, 14)).float().cuda().requires_grad_()      # small integers -> many ties
+    y = ops.max_pool3(ops.input_to_internal(x), strides)
+    yr = F.max_pool2d(x, 3, strides, 1)
+    assert y.shape == yr.shape and torch.equal(y.contiguous(), yr)
+    w = torch.randn_like(yr)
+    (gx,) = torch.autograd.grad((y * w).sum(), x)
+    (gr,) = torch.autograd.grad((yr * w).sum(), x)
+    assert torch.allclose(gx, gr, atol=1e-6)
+
+
+@pytest.mark.parametrize("stride", [(2, 1), (1, 2), (3, 1)])
+def test_conv_anisotropic_stride(stride, mode):
+    """affgw_conv_desc.stride_w: nn.Conv2d(..., stride=(rows, columns)) forward, input gradient and weight gradient."""
+    import torch.nn.functional as F
+    from affganwriting_b200 import ops
+    torch.manual_seed(5)
+    x = torch.randn(3, 24, 17, 29).cuda().requires_grad_()
+    w = (torch.randn(40, 24, 3, 3) * 0.1).cuda().requires_grad_()
+    y = ops.conv2d(ops.input_to_internal(x), w, None, stride=stride, pad=1)
+    yr = F.conv2d(x.double(), w.double(), None, stride=stride, padding=1)
+    assert y.shape == yr.shape
+    tol = {"fp32": 1e-5, "bf16": 1e-4, "bf16x1": 2e-2}[mode]
+    assert rel_err(y, yr.float()) <= tol
+    gy = torch.randn_like(yr)
+    gx, gw = torch.autograd.grad((y.double() * gy).sum(), (x, w))
+    gxr, gwr = torch.autograd.grad((yr * gy).sum(), (x, w))
+    assert rel_err(gx, gxr.float()) <= tol and rel_err(gw, gwr.float()) <= tol

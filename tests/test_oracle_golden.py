@@ -135,3 +135,28 @@ def test_resnet_encoder_oracle_matches_reference_fixture(arch, golden):
     assert abs(float(x.grad.norm()) / float(g[f"{arch}.dx.norm"]) - 1) <= 1e-4 + 3 * noise_g
     assert int(stats["model.layer3.1.bn1.num_batches_tracked"]) == 1
     assert rel_err(stats["model.bn1.running_mean"], _t(g[f"{arch}.post.model.bn1.running_mean"])) <= 1e-5
+
+
+@pytest.mark.parametrize("case", ["nb384_c50", "nb512_c3"])
+def test_resnet18_standalone_oracle_matches_reference_fixture(case, golden):
+    """SURVEY.md §8 row a9, `Resnet18.py:9-88` (row stride 2 / column stride 1 stem and pool): the oracle against the fp64 run
+    of the reference module (tests/golden/resnet18_standalone.npz, oracle/make_golden_resnet18_standalone.py)."""
+    g = golden("resnet18_standalone.npz")
+    spec = json.load(open(os.path.join(GOLDEN, "resnet18_standalone_spec.json")))[case]
+    rep = json.load(open(os.path.join(GOLDEN, "oracle_vs_reference_resnet18_standalone.json")))
+    assert all(r["max_abs"] <= r["tol"] for r in rep) and len(rep) >= 14
+    batch, cin = (2, 50) if case == "nb384_c50" else (3, 3)
+    sd = {k: v.requires_grad_(v.is_floating_point()) for k, v in W.make_state(spec).items()}
+    x = O.synthetic_batch(batch, cin)["tr_img"].requires_grad_()
+    stats = {}
+    res = O.resnet18_standalone(x, sd, "", True, stats)
+    sum(r.square().mean() for r in res).backward()
+    noise_f, noise_g = float(g[f"{case}.noise.fwd"]), float(g[f"{case}.noise.dx"])
+    for i, r in enumerate(res):
+        assert list(r.shape) == g[f"{case}.result{i}.shape"].tolist()
+        assert rel_err(r[:, :8], _t(g[f"{case}.result{i}.head"])) <= 1e-5 + 3 * noise_f
+    assert list(res[0].shape[2:]) == [16, 216] and list(res[4].shape[2:]) == [2, 27]      # rows / 4, columns kept
+    assert abs(float(x.grad.norm()) / float(g[f"{case}.dx.norm"]) - 1) <= 1e-4 + 3 * noise_g
+    assert rel_err(sd["conv1.weight"].grad[:8], _t(g[f"{case}.grad.conv1"])) <= 1e-4 + 3 * noise_g
+    assert int(stats["layer2.0.bn1.num_batches_tracked"]) == 1
+    assert rel_err(stats["bn1.running_mean"], _t(g[f"{case}.post.bn1.running_mean"])) <= 1e-5
