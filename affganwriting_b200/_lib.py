@@ -45,6 +45,7 @@ SIGNATURES = {
     "affgw_pack_weight_tc_bytes": [_I, _I, _I, _I, _I, _I, _I, _I],
     "affgw_maxpool3s2_fwd": [_P, _P, _I, _I, _I, _I, _I, _P],
     "affgw_maxpool3s2_bwd": [_P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "affgw_u8_to_image": [_P, _P, _L, _P],
     "affgw_maxpool3_fwd": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "affgw_maxpool3_bwd": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "affgw_resize_bilinear_fwd": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P],

@@ -94,6 +94,7 @@ int bce_logits_bwd(const void* x, int dt, float target, const float* gout, void*
 int softmax_ce_fwd(const void* x, int dt, const long long* y, float* loss, int B, int C, int* err, cudaStream_t st);
 int softmax_ce_bwd(const void* x, int dt, const long long* y, const float* gout, void* dx, int B, int C, cudaStream_t st);
 int nchw_to_nhwc(const float* x, void* y, int dt, int N, int C, long long HW, int cpad, cudaStream_t st);
+int u8_to_image(const unsigned char* src, float* dst, long long n, cudaStream_t st);
 int nhwc_to_nchw(const void* x, float* y, int dt, int N, int C, long long HW, int cpad, cudaStream_t st);
 int cast_dtype(const void* x, int in_dt, void* y, int out_dt, long long n, cudaStream_t st);
 int concat2(void* a, void* b, void* out, int dt, long long rows, int ca, int cb, int to_out, cudaStream_t st);
@@ -647,6 +648,11 @@ int affgw_softmax_ce_fwd(const void* x, int dt, const long long* y, float* loss,
 int affgw_softmax_ce_bwd(const void* x, int dt, const long long* y, const float* gout, void* dx, int B, int C, void* s) {
     REQ(x && y && gout && dx && dt_ok(dt) && B > 0 && C > 0, "softmax_ce_bwd");
     return softmax_ce_bwd(x, dt, y, gout, dx, B, C, S(s));
+}
+int affgw_u8_to_image(const unsigned char* src, float* dst, long long n, void* s) {
+    REQ(src && dst && n > 0, "u8_to_image");
+    REQ(((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 15) == 0, "u8_to_image: buffers must be 16-byte aligned");
+    return u8_to_image(src, dst, n, S(s));
 }
 int affgw_nchw_to_nhwc(const float* x, void* y, int dt, int N, int C, long long HW, int c_pad, void* s) {
     REQ(x && y && dt_ok(dt) && N > 0 && C > 0 && HW > 0 && c_pad >= C, "nchw_to_nhwc");

@@ -627,6 +627,36 @@ __global__ void softmax_ce_bwd_kernel(const T* __restrict__ x, const long long* 
         dx[(long long)row * C + c] = from_f<T>((expf(to_f(xr[c]) - mx) * inv - (c == t ? 1.f : 0.f)) * g);
 }
 
+// ---------------------------------------------------------------- uint8 wire format -> normalised image
+// load_data.py:147-166 after the resize: img/255. and 1. - img in float64 (numpy promotes uint8 / float), stored into a
+// float32 canvas, then (canvas - 0.5) / 0.5 in float32.  256 possible results: a per-block table built with exactly those
+// operations, then one table look-up per byte (16 bytes in, 64 bytes out per thread and iteration).
+__global__ void u8_to_image_kernel(const unsigned char* __restrict__ src, float* __restrict__ dst, long long n) {
+    __shared__ float lut[256];
+    {
+        const double ink = 1.0 - (double)threadIdx.x / 255.0;
+        const float canvas = (float)ink;
+        lut[threadIdx.x] = (canvas - 0.5f) / 0.5f;
+    }
+    __syncthreads();
+    const long long vecs = n / 16;
+    GRID_STRIDE(i, vecs) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(src) + i);
+        const unsigned w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float4 o;
+            o.x = lut[w[k] & 255u];
+            o.y = lut[(w[k] >> 8) & 255u];
+            o.z = lut[(w[k] >> 16) & 255u];
+            o.w = lut[w[k] >> 24];
+            reinterpret_cast<float4*>(dst)[i * 4 + k] = o;
+        }
+    }
+    if (blockIdx.x == 0)
+        for (long long i = vecs * 16 + threadIdx.x; i < n; i += blockDim.x) dst[i] = lut[src[i]];
+}
+
 // ---------------------------------------------------------------- layout / dtype conversion
 // NCHW fp32 -> NHWC T with the channel dimension zero-padded to cpad (tile-transposed through shared memory)
 template <typename T>
@@ -911,6 +941,12 @@ int softmax_ce_bwd(const void* x, int dt, const long long* y, const float* gout,
     if (dt == AFFGW_F32) softmax_ce_bwd_kernel<float><<<cdiv(B, 8), 256, 0, st>>>((const float*)x, y, gout, (float*)dx, B, C);
     else softmax_ce_bwd_kernel<bf16><<<cdiv(B, 8), 256, 0, st>>>((const bf16*)x, y, gout, (bf16*)dx, B, C);
     AFFGW_LAUNCH_CHECK("softmax_ce_bwd");
+    return 0;
+}
+int u8_to_image(const unsigned char* src, float* dst, long long n, cudaStream_t st) {
+    const long long vecs = (n + 15) / 16;
+    u8_to_image_kernel<<<ew_blocks(vecs), 256, 0, st>>>(src, dst, n);
+    AFFGW_LAUNCH_CHECK("u8_to_image");
     return 0;
 }
 int nchw_to_nhwc(const float* x, void* y, int dt, int N, int C, long long HW, int cpad, cudaStream_t st) {

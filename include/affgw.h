@@ -202,6 +202,10 @@ int affgw_softmax_ce_bwd(const void* x, int dtype, const long long* y, const flo
                          void* stream);
 
 /* ---- layout / dtype (the boundary: callers hand NCHW fp32 tensors, network_tro.py:30-36) ------------------- */
+/* Wire format of the style / target images: grey-level uint8 pixels as cv2 leaves them after the
+ * resize (load_data.py:151), right padding = 255.  dst[i] = the reference's normalisation of src[i], bit for bit:
+ * float32((float32(1. - src/255.) - 0.5) / 0.5) (load_data.py:152-166).  Both buffers 16-byte aligned, n elements. */
+int affgw_u8_to_image(const unsigned char* src, float* dst, long long n, void* stream);
 int affgw_nchw_to_nhwc(const float* x, void* y, int dtype, int N, int C, long long HW, int c_pad, void* stream);
 int affgw_nhwc_to_nchw(const void* x, float* y, int dtype, int N, int C, long long HW, int c_pad, void* stream);
 int affgw_cast(const void* x, int in_dtype, void* y, int out_dtype, long long n, void* stream);

@@ -525,3 +525,41 @@ def synthetic_batch(batch, num_channel=50, seed=1234):
         label_xt_swap=torch.tensor([label_padding(w) for w in w2], dtype=torch.int64),
         words=w1, words_swap=w2,
     )
+
+
+# ----------------------------------------------------------------------------------------------
+# uint8 wire format of the images
+# ----------------------------------------------------------------------------------------------
+def normalize_resized_u8(img_u8, height=64, width=216):
+    """load_data.py:152-166, the arithmetic of `read_image_single` AFTER cv2.resize (:151): `img/255.` and `1. - img` in
+    float64, crop to `width` columns or paste into a float32 zero canvas, `(canvas - 0.5) / 0.5` in float32.
+    img_u8: numpy uint8 [height, w].  Returns (float32 [height, width], img_width)."""
+    import numpy as np
+    img = img_u8 / 255.
+    img = 1. - img
+    img_width = img.shape[-1]
+    if img_width > width:
+        out = img[:, :width]
+        img_width = width
+    else:
+        out = np.zeros((height, width), dtype="float32")
+        out[:, :img_width] = img
+    out = out.astype("float32")
+    return (out - 0.5) / 0.5, img_width
+
+
+def pad_resized_u8(img_u8, height=64, width=216):
+    """The same image as ONE uint8 canvas (the wire format): crop to `width` columns or right-pad with 255, the grey level
+    whose normalisation is the canvas background (1 - 255/255 = 0 -> -1)."""
+    import numpy as np
+    out = np.full((height, width), 255, dtype=np.uint8)
+    w = min(width, img_u8.shape[-1])
+    out[:, :w] = img_u8[:, :w]
+    return out
+
+
+def decode_u8(u8):
+    """Wire format -> normalised float32 (numpy, any shape): element-wise restatement of load_data.py:152-166."""
+    import numpy as np
+    canvas = (1. - u8 / 255.).astype("float32")
+    return (canvas - np.float32(0.5)) / np.float32(0.5)

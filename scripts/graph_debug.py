@@ -3,8 +3,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.ins
 import affganwriting_b200 as A
 from affganwriting_b200.trainer import Trainer
 import bench
+from affganwriting_b200 import load_data as LD
 A.set_precision("bf16")
-batch = tuple(t.cuda() if torch.is_tensor(t) else t for t in bench.synthetic_batch(4, 50, 7))
+batch = LD.batch_to_device(bench.synthetic_batch(4, 50, 7), torch.device('cuda'))
 dev = torch.device("cuda", 0)
 torch.manual_seed(0); a = Trainer(device=dev)
 b = Trainer(device=dev); b.model.load_state_dict(a.model.state_dict())

@@ -10,6 +10,7 @@ import affganwriting_b200 as A
 from affganwriting_b200 import ops
 from affganwriting_b200.trainer import Trainer
 import bench
+from affganwriting_b200 import load_data as LD
 
 
 def main():
@@ -24,7 +25,7 @@ def main():
     A.set_precision(args.mode)
     torch.manual_seed(0)
     tr = Trainer(num_writers=500, device=dev)
-    batch = tuple(t.to(dev) if torch.is_tensor(t) else t for t in bench.synthetic_batch(args.batch, 50, 1234))
+    batch = LD.batch_to_device(bench.synthetic_batch(args.batch, 50, 1234), dev)
     for _ in range(3):
         tr.train_step(batch)
     torch.cuda.synchronize()

@@ -295,10 +295,11 @@ def test_cuda_graph_replay_matches_eager_iterations(specs):
     digit of the generator loss within three iterations), so the bound is the eager-vs-eager drift measured alongside."""
     from affganwriting_b200.trainer import Trainer
     import bench
+    from affganwriting_b200 import load_data as LD
     A.set_precision("bf16")
     try:
         dev = torch.device("cuda", 0)
-        batch = tuple(t.cuda() if torch.is_tensor(t) else t for t in bench.synthetic_batch(4, 50, 7))
+        batch = LD.batch_to_device(bench.synthetic_batch(4, 50, 7), torch.device('cuda'))
         torch.manual_seed(0)
         a = Trainer(num_writers=500, device=dev)
         b = Trainer(num_writers=500, device=dev)

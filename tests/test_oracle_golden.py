@@ -160,3 +160,19 @@ def test_resnet18_standalone_oracle_matches_reference_fixture(case, golden):
     assert rel_err(sd["conv1.weight"].grad[:8], _t(g[f"{case}.grad.conv1"])) <= 1e-4 + 3 * noise_g
     assert int(stats["layer2.0.bn1.num_batches_tracked"]) == 1
     assert rel_err(stats["bn1.running_mean"], _t(g[f"{case}.post.bn1.running_mean"])) <= 1e-5
+
+
+def test_u8_wire_format_oracle_matches_reference_loader(golden):
+    """the oracle's restatement of load_data.py:152-166 against float32 canvases returned by the
+    reference's own `read_image_single` (tests/golden/u8_wire.npz, oracle/make_golden_u8.py) - bit for bit."""
+    g = golden("u8_wire.npz")
+    levels = set()
+    for i in range(int(g["count"])):
+        u8, ref = g[f"u8.{i}"], g[f"ref.{i}"]
+        mine, width = O.normalize_resized_u8(u8)
+        assert width == int(g[f"width.{i}"]) and mine.dtype == np.float32 and np.array_equal(mine, ref)
+        wire = O.pad_resized_u8(u8)
+        assert wire.dtype == np.uint8 and wire.shape == (64, 216) and np.array_equal(O.decode_u8(wire), ref)
+        levels |= set(np.unique(u8).tolist())
+    assert len(levels) == 256                                    # every grey level went through the reference
+    assert O.decode_u8(np.array([255, 0], dtype=np.uint8)).tolist() == [-1.0, 1.0]
