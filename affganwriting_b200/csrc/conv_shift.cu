@@ -474,7 +474,8 @@ int conv_shift_ok(const ConvGeom& g) {
     const long long Hp = g.Hv + 2 * g.pad, Wp = g.Wv + 2 * g.pad;
     if (Hp - g.KH + 1 != g.Ho || Wp - g.KW + 1 != g.Wo) return 0;
     // on tiny maps the padding positions (computed, then dropped) cost more than the window saves: im2col kernels
-    if (2 * Hp * Wp > 3LL * g.Ho * g.Wo) return 0;
+    static const int waste_x10 = [] { const char* e = getenv("AFFGW_SHIFT_WASTE_X10"); return e ? atoi(e) : 15; }();
+    if (10 * Hp * Wp > (long long)waste_x10 * g.Ho * g.Wo) return 0;
     if ((long long)g.N * Hp * Wp + 8192 >= (1LL << 31) / 16) return 0;           // 32-bit position arithmetic
     // the forward tile is as wide as Cout allows, the dgrad tile as wide as Cin allows: both windows must fit
     ShPlan p;

@@ -191,6 +191,12 @@ conv_igemm_tcgen05_kernel(const __grid_constant__ TcArgs a) {
             const bf16* wt = a.w_tiles + (size_t)nt * KB * (NPL * BN * BK);
             int ky = 0, kx = 0, c0 = 0;   // uniform-tap cursor, positioned at this split's first k-block
             int sy[8], sx[8];
+            int off[8];                   // uniform tap: element offset of row i's source pixel (channel 0), -1 = zero row
+            auto refresh = [&]() {
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    off[i] = (mvalid[i] && sy[i] >= 0 && sx[i] >= 0) ? (nbase[i] + sy[i] * g.W + sx[i]) * g.Cin : -1;
+            };
             if (uniform_tap) {
                 const int tap0 = (kb0 * BK) / g.Cin;
                 c0 = kb0 * BK - tap0 * g.Cin;
@@ -201,7 +207,9 @@ conv_igemm_tcgen05_kernel(const __grid_constant__ TcArgs a) {
                     sy[i] = map_coord(vy0[i] + ky, g.Hv, g.pad_mode, g.up, g.zi);
                     sx[i] = map_coord(vx0[i] + kx, g.Wv, g.pad_mode, g.up, g.zi_w);
                 }
+                refresh();
             }
+            const uint32_t dst_off = rg * 128 + ((chunk ^ (rg & 7)) << 4);     // rows rg + 16 i keep (r & 7)
             for (int kb = kb0; kb < kb1; ++kb, ++it) {
                 const int s = it % STAGES;
                 const uint32_t ph = (it / STAGES) & 1u;
@@ -210,34 +218,34 @@ conv_igemm_tcgen05_kernel(const __grid_constant__ TcArgs a) {
                     mbar_expect_tx(full_bar(s), Cfg::B_BYTES);
                     bulk_copy_g2s(b_smem(s), wt + (size_t)kb * (NPL * BN * BK), Cfg::B_BYTES, full_bar(s));
                 }
-                const uint32_t a_base = a_smem(s);
-                int coff;
-                bool kvalid = true;
+                const uint32_t a_base = a_smem(s) + dst_off;
                 if (uniform_tap) {
-                    coff = c0 + chunk * 8;
+                    const bf16* const xc = a.x + c0 + chunk * 8;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const bool ok = off[i] >= 0;
+                        const bf16* src = xc + (ok ? off[i] : 0);
+                        const uint32_t dst = a_base + i * 2048;
+                        cp_async_16(dst, src, ok ? 16u : 0u);
+                        if (NPL == 2) cp_async_16(dst + A_PLANE_BYTES, src + a.x_plane, ok ? 16u : 0u);
+                    }
                 } else {
                     const int kidx = kb * BK + chunk * 8;
-                    kvalid = kidx < g.Ktot;
+                    const bool kvalid = kidx < g.Ktot;
                     const int tap = kidx / g.Cin;
-                    coff = kidx - tap * g.Cin;
+                    const int coff = kidx - tap * g.Cin;
                     ky = tap / g.KW;
                     kx = tap - ky * g.KW;
-                }
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int r = rg + 16 * i;
-                    int yy, xx;
-                    if (uniform_tap) {
-                        yy = sy[i]; xx = sx[i];
-                    } else {
-                        yy = map_coord(vy0[i] + ky, g.Hv, g.pad_mode, g.up, g.zi);
-                        xx = map_coord(vx0[i] + kx, g.Wv, g.pad_mode, g.up, g.zi_w);
+                    for (int i = 0; i < 8; ++i) {
+                        const int yy = map_coord(vy0[i] + ky, g.Hv, g.pad_mode, g.up, g.zi);
+                        const int xx = map_coord(vx0[i] + kx, g.Wv, g.pad_mode, g.up, g.zi_w);
+                        const bool ok = mvalid[i] && kvalid && yy >= 0 && xx >= 0;
+                        const bf16* src = ok ? a.x + ((size_t)(nbase[i] + yy * g.W + xx) * g.Cin + coff) : a.x;
+                        const uint32_t dst = a_base + i * 2048;
+                        cp_async_16(dst, src, ok ? 16u : 0u);
+                        if (NPL == 2) cp_async_16(dst + A_PLANE_BYTES, ok ? src + a.x_plane : src, ok ? 16u : 0u);
                     }
-                    const bool ok = mvalid[i] && kvalid && yy >= 0 && xx >= 0;
-                    const bf16* src = ok ? a.x + ((size_t)(nbase[i] + yy * g.W + xx) * g.Cin + coff) : a.x;
-                    const uint32_t dst = a_base + r * 128 + ((chunk ^ (r & 7)) << 4);
-                    cp_async_16(dst, src, ok ? 16u : 0u);
-                    if (NPL == 2) cp_async_16(dst + A_PLANE_BYTES, ok ? src + a.x_plane : src, ok ? 16u : 0u);
                 }
                 cp_async_commit();
                 if (it >= (uint32_t)LAG) {
@@ -245,7 +253,7 @@ conv_igemm_tcgen05_kernel(const __grid_constant__ TcArgs a) {
                     fence_proxy_async();
                     mbar_arrive(full_bar((it - LAG) % STAGES));
                 }
-                if (uniform_tap) {      // advance (c0, kx, ky) and refresh the source coordinates that changed
+                if (uniform_tap) {      // advance (c0, kx, ky); the source pixels change only when the tap does
                     c0 += BK;
                     if (c0 == g.Cin) {
                         c0 = 0;
@@ -257,6 +265,7 @@ conv_igemm_tcgen05_kernel(const __grid_constant__ TcArgs a) {
                         }
 #pragma unroll
                         for (int i = 0; i < 8; ++i) sx[i] = map_coord(vx0[i] + kx, g.Wv, g.pad_mode, g.up, g.zi_w);
+                        refresh();
                     }
                 }
             }
@@ -485,7 +494,7 @@ int conv_tc_block_n(int cout) { return cout > 64 ? 128 : cout > 32 ? 64 : cout >
 // g.Cin is the STORED channel count of the operand planes
 int conv_tc_ok(const ConvGeom& g) {
     if (g.Cin % 8 != 0 || g.in_pitch != g.Cin) return 0;
-    if ((long long)g.N * g.H * g.W * g.Cin >= (1LL << 40)) return 0;
+    if ((long long)g.N * g.H * g.W * g.Cin >= (1LL << 31)) return 0;      // 32-bit element offsets in the gather
     if ((long long)g.N * g.H * g.W >= (1LL << 31)) return 0;
     return conv_tc_block_n(g.Cout);
 }

@@ -72,6 +72,21 @@ __device__ __forceinline__ int map_fast(int v, int V, int pad_mode, int up) {
     return up == 2 ? (v >> 1) : v;
 }
 
+// q = n / d for 0 <= n < 2^31 with one 32 x 32 -> 64 bit multiply: mul = ceil(2^k / d), k = 31 + ceil(log2 d)
+struct FastDiv {
+    uint32_t mul, k, d;
+};
+inline FastDiv make_fastdiv(int d) {
+    FastDiv f;
+    int s = 0;
+    while ((1LL << s) < d) ++s;
+    f.k = 31 + s;
+    f.mul = (uint32_t)(((1ULL << f.k) + (uint64_t)d - 1) / (uint64_t)d);
+    f.d = (uint32_t)d;
+    return f;
+}
+__device__ __forceinline__ uint32_t fast_div(uint32_t n, const FastDiv& f) { return (uint32_t)(((uint64_t)n * f.mul) >> f.k); }
+
 struct WgArgs {
     const bf16* x;      // operand planes [NPL][N*H*W][Cin]   (g.Cin = stored channels)
     long long x_plane;
@@ -80,6 +95,7 @@ struct WgArgs {
     float* ws;          // [Cout][taps * Cin] fp32 partial sums
     ConvGeom g;
     long long m_per_split;
+    FastDiv div_wo, div_ho;
 };
 
 template <int BN, int NPASS>
@@ -143,17 +159,15 @@ conv_wgrad_tcgen05_kernel(const __grid_constant__ WgArgs a) {
         bool nvalid[BNI];
 #pragma unroll
         for (int i = 0; i < BNI; ++i) nvalid[i] = (chunk * 8 < BN) && (n0 + i * 64 + chunk * 8 < g.out_pitch);
-        int oy[4], ox[4], nimg[4];
-        long long mrow[4];
+        // 32-bit pixel / element arithmetic throughout (conv_wgrad_tc_ok bounds the tensors below 2^31 elements)
+        uint32_t mrow[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            mrow[j] = mbeg + slot + 16 * j;
-            const long long mm = min(mrow[j], g.M - 1);
-            ox[j] = (int)(mm % g.Wo);
-            const long long t = mm / g.Wo;
-            oy[j] = (int)(t % g.Ho);
-            nimg[j] = (int)(t / g.Ho);
-        }
+        for (int j = 0; j < 4; ++j) mrow[j] = (uint32_t)mbeg + slot + 16 * j;
+        const uint32_t m_end = (uint32_t)mend, m_last = (uint32_t)(g.M - 1);
+        int ncol[BNI];
+#pragma unroll
+        for (int i = 0; i < BNI; ++i) ncol[i] = n0 + i * 64 + chunk * 8;
+        const int HW = g.H * g.W;
         constexpr int LAG = STAGES - 1;
         for (int st = 0; st < nstages; ++st) {
             const int s = st % STAGES;
@@ -163,36 +177,34 @@ conv_wgrad_tcgen05_kernel(const __grid_constant__ WgArgs a) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const int r = slot + 16 * j;
-                const bool mok = mrow[j] < mend;
+                const bool mok = mrow[j] < m_end;
                 const uint32_t soff = r * 128 + ((chunk ^ (r & 7)) << 4);
+                // pixel index -> (image, oy, ox): two multiply-shift divisions (the maps are as small as 2 x 7, so stepping
+                // the coordinates by 64 pixels with carries costs far more than recomputing them)
+                const uint32_t mm = min(mrow[j], m_last);
+                const uint32_t t = fast_div(mm, a.div_wo);
+                const int ox = (int)(mm - t * (uint32_t)g.Wo);
+                const uint32_t nimg = fast_div(t, a.div_ho);
+                const int oy = (int)(t - nimg * (uint32_t)g.Ho);
+                const int ybase = oy * g.stride, xbase = ox * g.stride_w;
+                const int pix0 = (int)nimg * HW;
 #pragma unroll
                 for (int i = 0; i < 2; ++i) {
-                    bool ok = mok && kvalid[i];
-                    int sy = 0, sx = 0;
-                    if (ok) {
-                        sy = map_fast(oy[j] * g.stride + dyo[i], g.Hv, g.pad_mode, g.up);
-                        sx = map_fast(ox[j] * g.stride_w + dxo[i], g.Wv, g.pad_mode, g.up);
-                        ok = sy >= 0 && sx >= 0;
-                    }
-                    const bf16* src = ok ? a.x + ((size_t)((size_t)nimg[j] * g.H * g.W + (size_t)sy * g.W + sx) * g.Cin + coff[i])
-                                         : a.x;
+                    const int sy = map_fast(ybase + dyo[i], g.Hv, g.pad_mode, g.up);
+                    const int sx = map_fast(xbase + dxo[i], g.Wv, g.pad_mode, g.up);
+                    const bool ok = mok && kvalid[i] && sy >= 0 && sx >= 0;
+                    const bf16* src = a.x + (ok ? (pix0 + sy * g.W + sx) * g.Cin + coff[i] : 0);
                     cp_async_16(a_base + i * IMG_BYTES + soff, src, ok ? 16u : 0u);
-                    if (NPL == 2) cp_async_16(a_base + Cfg::A_PLANE + i * IMG_BYTES + soff, ok ? src + a.x_plane : src, ok ? 16u : 0u);
+                    if (NPL == 2) cp_async_16(a_base + Cfg::A_PLANE + i * IMG_BYTES + soff, src + a.x_plane, ok ? 16u : 0u);
                 }
 #pragma unroll
                 for (int i = 0; i < BNI; ++i) {
                     const bool ok = mok && nvalid[i];
-                    const bf16* src = ok ? a.dy + (size_t)mrow[j] * g.out_pitch + n0 + i * 64 + chunk * 8 : a.dy;
+                    const bf16* src = a.dy + (ok ? (int)mm * g.out_pitch + ncol[i] : 0);
                     cp_async_16(b_base + i * IMG_BYTES + soff, src, ok ? 16u : 0u);
-                    if (NPL == 2) cp_async_16(b_base + Cfg::B_PLANE + i * IMG_BYTES + soff, ok ? src + a.dy_plane : src, ok ? 16u : 0u);
+                    if (NPL == 2) cp_async_16(b_base + Cfg::B_PLANE + i * IMG_BYTES + soff, src + a.dy_plane, ok ? 16u : 0u);
                 }
-                // advance this row slot by one stage (64 pixels)
-                mrow[j] += BP;
-                ox[j] += BP;
-                while (ox[j] >= g.Wo) {
-                    ox[j] -= g.Wo;
-                    if (++oy[j] == g.Ho) { oy[j] = 0; ++nimg[j]; }
-                }
+                mrow[j] += BP;          // next stage: 64 pixels on
             }
             cp_async_commit();
             if (st >= LAG) {
@@ -284,12 +296,22 @@ int launch_wg(WgArgs& a, cudaStream_t st) {
     const ConvGeom& g = a.g;
     const int ktot = g.KH * g.KW * g.Cin;
     const int gx = (ktot + 127) / 128, gy = (g.Cout + BN - 1) / BN;
+    // split of the pixel range over CTAs.  One round of CTAs costs a fixed part (launch, pipeline fill, and above all the fp32
+    // reductions of its 128 x BN tile into the workspace, which contend with the other splits of the same tile) plus its
+    // stages; measured on B200: ~20 us fixed, ~1.2 us per 64-pixel stage.  Pick the split count with the lowest modelled time.
     const long long per_wave = 148LL * (NPASS == 3 ? 1 : 2);
-    long long splits = (2 * per_wave + (long long)gx * gy - 1) / ((long long)gx * gy);
-    const long long max_splits = (g.M + 511) / 512;
-    if (splits > max_splits) splits = max_splits;
-    if (splits < 1) splits = 1;
-    if (splits > 65535) splits = 65535;
+    const long long tiles = (long long)gx * gy;
+    const long long total_stages = (g.M + BP - 1) / BP;
+    long long max_splits = (g.M + 511) / 512;
+    if (max_splits > 65535) max_splits = 65535;
+    if (max_splits < 1) max_splits = 1;
+    long long splits = 1, best = -1;
+    for (long long sp = 1; sp <= max_splits; ++sp) {
+        const long long rounds = (tiles * sp + per_wave - 1) / per_wave;
+        const long long cost = rounds * (100 + 6 * ((total_stages + sp - 1) / sp));
+        if (best < 0 || cost < best) { best = cost; splits = sp; }
+        if (tiles * sp >= 4 * per_wave) break;
+    }
     long long mps = (g.M + splits - 1) / splits;
     mps = (mps + BP - 1) / BP * BP;
     splits = (g.M + mps - 1) / mps;
@@ -313,7 +335,7 @@ int conv_tc_block_n(int cout);
 int conv_wgrad_tc_ok(const ConvGeom& g) {
     if (g.Cin % 8 != 0 || g.in_pitch != g.Cin || g.out_pitch % 8 != 0 || g.out_pitch < g.Cout) return 0;
     if (g.pre_act != ACT_NONE || g.zi != 1 || g.zi_w != 1) return 0;
-    if ((long long)g.N * g.H * g.W >= (1LL << 31)) return 0;
+    if ((long long)g.N * g.H * g.W * g.Cin >= (1LL << 31) || g.M * g.out_pitch >= (1LL << 31)) return 0;   // 32-bit offsets
     return conv_tc_block_n(g.Cout);
 }
 
@@ -335,6 +357,8 @@ int conv_wgrad_tc(const void* x_planes, long long x_plane, const void* dy_planes
     a.x = (const bf16*)x_planes; a.x_plane = x_plane;
     a.dy = (const bf16*)dy_planes; a.dy_plane = dy_plane;
     a.ws = ws; a.g = g; a.m_per_split = 0;
+    a.div_wo = make_fastdiv(g.Wo);
+    a.div_ho = make_fastdiv(g.Ho);
     int rc;
     switch (bn) {
         case 16: rc = launch_wg_p<16>(a, passes, st); break;

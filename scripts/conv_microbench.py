@@ -30,6 +30,10 @@ SHAPES = [
     ("dis_128_128@8x27", 8, 27, 128, 128, 3, 1, "reflect", 1),
     ("dis_256_256@4x14", 4, 14, 256, 256, 3, 1, "reflect", 1),
     ("dis_512_512@2x7", 2, 7, 512, 512, 3, 1, "reflect", 1),
+    ("dis_256_512@4x14", 4, 14, 256, 512, 3, 1, "reflect", 1),
+    ("dis_512_1024@2x7", 2, 7, 512, 1024, 3, 1, "reflect", 1),
+    ("iaff_512_128@8x27", 8, 27, 512, 128, 1, 0, "zero", 1),
+    ("iaff_128_512@8x27", 8, 27, 128, 512, 1, 0, "zero", 1),
 ]
 
 
