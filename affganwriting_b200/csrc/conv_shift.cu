@@ -163,8 +163,8 @@ conv_shift_tcgen05_kernel(const __grid_constant__ ShArgs a) {
             }
         }
     } else if (warp == MMA_WARP) {
-        // ============================== MMA issuer (one thread) ==============================
-        if (lane == 0) {
+        // ============================== MMA issuer ==============================
+        {   // every lane runs the loops (warp-uniform), one elected lane issues: see umma_bf16_elect
             constexpr uint32_t idesc = make_idesc(BN, false);
             const uint32_t b_plane = 2u * BN * 16u;               // bytes of one [cgroup][BN][8] weight image
             uint32_t it = 0, tl = 0;
@@ -193,17 +193,17 @@ conv_shift_tcgen05_kernel(const __grid_constant__ ShArgs a) {
 #pragma unroll
                             for (int mt = 0; mt < MT; ++mt) {
                                 const uint64_t a_hi = a_t + (uint64_t)(mt * 128);
-                                umma_bf16(d0 + mt * BN, a_hi, b_hi, idesc, accum);
+                                umma_bf16_elect(d0 + mt * BN, a_hi, b_hi, idesc, accum);
                                 if (NPASS == 3) {
-                                    umma_bf16(d0 + mt * BN, a_hi + a_lo_off, b_hi, idesc, 1u);
-                                    umma_bf16(d0 + mt * BN, a_hi, b_hi + b_lo_off, idesc, 1u);
+                                    umma_bf16_elect(d0 + mt * BN, a_hi + a_lo_off, b_hi, idesc, 1u);
+                                    umma_bf16_elect(d0 + mt * BN, a_hi, b_hi + b_lo_off, idesc, 1u);
                                 }
                             }
                         }
                     }
-                    umma_commit(empty_bar(s));
+                    umma_commit_elect(empty_bar(s));
                 }
-                umma_commit(tmem_full_bar(acc));
+                umma_commit_elect(tmem_full_bar(acc));
             }
         }
     } else {
@@ -717,7 +717,7 @@ conv_wgrad_shift_kernel(const __grid_constant__ WsArgs a, const __grid_constant_
         }
     } else if (warp == MMA_WARP) {
         // ============================== MMA issuer ==============================
-        if (lane == 0) {
+        {   // every lane runs the loops (warp-uniform), one elected lane issues: see umma_bf16_elect
             constexpr uint32_t idesc = make_idesc(BN, true);
             for (int st = 0; st < nst; ++st) {
                 const int s = st % stages;
@@ -741,16 +741,16 @@ conv_wgrad_shift_kernel(const __grid_constant__ WsArgs a, const __grid_constant_
 #pragma unroll 1
                     for (int j = 0; j < nacc; ++j) {
                         const uint64_t a_hi = a_base + (uint64_t)((uint32_t)(k * 16) + a_first + (uint32_t)j * a_step);
-                        umma_bf16(tmem_base + j * BN, a_hi, b_hi, idesc, accum);
+                        umma_bf16_elect(tmem_base + j * BN, a_hi, b_hi, idesc, accum);
                         if (NPASS == 3) {
-                            umma_bf16(tmem_base + j * BN, a_hi + a_lo_off, b_hi, idesc, 1u);
-                            umma_bf16(tmem_base + j * BN, a_hi, b_hi + b_lo_off, idesc, 1u);
+                            umma_bf16_elect(tmem_base + j * BN, a_hi + a_lo_off, b_hi, idesc, 1u);
+                            umma_bf16_elect(tmem_base + j * BN, a_hi, b_hi + b_lo_off, idesc, 1u);
                         }
                     }
                 }
-                umma_commit(empty_bar(s));
+                umma_commit_elect(empty_bar(s));
             }
-            umma_commit(tmem_full_bar);
+            umma_commit_elect(tmem_full_bar);
         }
     } else {
         // ============================== epilogue: fp32 reductions into ws[co][tap][ci] ==============================

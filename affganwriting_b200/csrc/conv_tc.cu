@@ -275,8 +275,8 @@ conv_igemm_tcgen05_kernel(const __grid_constant__ TcArgs a) {
         fence_proxy_async();
         for (uint32_t j = (it > (uint32_t)LAG ? it - LAG : 0u); j < it; ++j) mbar_arrive(full_bar(j % STAGES));
     } else if (warp == MMA_WARP) {
-        // ============================== MMA issuer (one thread) ==============================
-        if (lane == 0) {
+        // ============================== MMA issuer ==============================
+        {   // every lane runs the loops (warp-uniform), one elected lane issues: see umma_bf16_elect
             constexpr uint32_t idesc = make_idesc_bf16(BN);
             uint32_t it = 0, tl = 0;
             for (long long t = blockIdx.x; t < a.total_tiles; t += gridDim.x, ++tl) {
@@ -295,18 +295,18 @@ conv_igemm_tcgen05_kernel(const __grid_constant__ TcArgs a) {
                     const uint64_t b_hi = make_kmajor_sw128_desc(b_smem(s));
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k)   // +32 bytes (encoded >>4) per 16-element K step inside the swizzle atom
-                        umma_bf16(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, (uint32_t)((kb | k) != 0));
+                        umma_bf16_elect(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, (uint32_t)((kb | k) != 0));
                     if (NPASS == 3) {
                         const uint64_t a_lo = make_kmajor_sw128_desc(a_smem(s) + A_PLANE_BYTES);
                         const uint64_t b_lo = make_kmajor_sw128_desc(b_smem(s) + Cfg::B_PLANE_BYTES);
 #pragma unroll
-                        for (int k = 0; k < BK / 16; ++k) umma_bf16(d_tmem, a_lo + 2 * k, b_hi + 2 * k, idesc, 1u);
+                        for (int k = 0; k < BK / 16; ++k) umma_bf16_elect(d_tmem, a_lo + 2 * k, b_hi + 2 * k, idesc, 1u);
 #pragma unroll
-                        for (int k = 0; k < BK / 16; ++k) umma_bf16(d_tmem, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
+                        for (int k = 0; k < BK / 16; ++k) umma_bf16_elect(d_tmem, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
                     }
-                    umma_commit(empty_bar(s));
+                    umma_commit_elect(empty_bar(s));
                 }
-                umma_commit(tmem_full_bar(acc));
+                umma_commit_elect(tmem_full_bar(acc));
             }
         }
     } else {

@@ -237,8 +237,9 @@ conv_wgrad_tcgen05_kernel(const __grid_constant__ WgArgs a) {
             }
         }
         tc_fence_before();
-    } else if (lane == 0) {
+    } else {
         // ============================== MMA issuer ==============================
+        // every lane of warp 4 runs the loops (warp-uniform), one elected lane issues: see umma_bf16_elect
         constexpr uint32_t idesc = make_idesc_bf16_mn(BN);
         constexpr uint32_t lbo = (uint32_t)IMG_BYTES, sbo = 1024u;
         for (int st = 0; st < nstages; ++st) {
@@ -250,17 +251,17 @@ conv_wgrad_tcgen05_kernel(const __grid_constant__ WgArgs a) {
             for (int k = 0; k < BP / 16; ++k) {      // 16 pixels = two 8-row swizzle atoms = 2048 bytes per K step
                 const uint64_t a_hi = make_mnmajor_sw128_desc(a_smem(s) + k * 2048, lbo, sbo);
                 const uint64_t b_hi = make_mnmajor_sw128_desc(b_smem(s) + k * 2048, lbo, sbo);
-                umma_bf16(tmem_base, a_hi, b_hi, idesc, (uint32_t)((st | k) != 0));
+                umma_bf16_elect(tmem_base, a_hi, b_hi, idesc, (uint32_t)((st | k) != 0));
                 if (NPASS == 3) {
                     const uint64_t a_lo = make_mnmajor_sw128_desc(a_smem(s) + Cfg::A_PLANE + k * 2048, lbo, sbo);
                     const uint64_t b_lo = make_mnmajor_sw128_desc(b_smem(s) + Cfg::B_PLANE + k * 2048, lbo, sbo);
-                    umma_bf16(tmem_base, a_lo, b_hi, idesc, 1u);
-                    umma_bf16(tmem_base, a_hi, b_lo, idesc, 1u);
+                    umma_bf16_elect(tmem_base, a_lo, b_hi, idesc, 1u);
+                    umma_bf16_elect(tmem_base, a_hi, b_lo, idesc, 1u);
                 }
             }
-            umma_commit(empty_bar(s));
+            umma_commit_elect(empty_bar(s));
         }
-        umma_commit(tmem_full_bar);
+        umma_commit_elect(tmem_full_bar);
     }
     __syncthreads();
     if (warp == 4) {

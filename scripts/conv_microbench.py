@@ -26,6 +26,10 @@ SHAPES = [
     ("dec_up_256_128@16x54", 16, 54, 256, 128, 5, 2, "reflect", 2),
     ("dec_up_128_64@32x108", 32, 108, 128, 64, 5, 2, "reflect", 2),
     ("mix_1024_512@8x27", 8, 27, 1024, 512, 1, 0, "zero", 1),
+    ("thin_16_16@64x216", 64, 216, 16, 16, 3, 1, "reflect", 1),
+    ("thin_16_32@64x216", 64, 216, 16, 32, 3, 1, "reflect", 1),
+    ("thin_32_32@32x108", 32, 108, 32, 32, 3, 1, "reflect", 1),
+    ("thin_32_64@32x108", 32, 108, 32, 64, 3, 1, "reflect", 1),
     ("dis_64_64@16x54", 16, 54, 64, 64, 3, 1, "reflect", 1),
     ("dis_128_128@8x27", 8, 27, 128, 128, 3, 1, "reflect", 1),
     ("dis_256_256@4x14", 4, 14, 256, 256, 3, 1, "reflect", 1),
