@@ -42,14 +42,19 @@ constexpr int MAX_TILE_POS = 512;            // largest CTA tile in positions (f
 // CTA tile = MT M-tiles of 128 positions x BN output channels; NBUF TMEM accumulator buffers of MT*BN columns.
 // Wide N amortises the 4 KB A read of a 128-row MMA over more tensor clocks (the shared-memory pipe delivers 128 B/clk):
 // BN = 256 needs 12 KB per 128 clocks, BN = 64 needs 6 KB per 32.
-__host__ __device__ constexpr int tile_mt(int bn) { return bn <= 64 ? 4 : 2; }
+// Split-bf16 mode with BN <= 64 packs [w_hi | w_lo] along N: a_hi x [w_hi | w_lo] is ONE MMA of width 2 BN (two accumulator
+// column blocks, summed in the epilogue), a_lo x w_hi a second one - two reads of the A tile per tap instead of three, which
+// is what bounds these thin layers (4 KB of A per MMA at 128 B/clk against N/2 tensor clocks).
+__host__ __device__ constexpr bool tile_packed(int bn, int npl) { return npl == 2 && bn <= 64; }
+__host__ __device__ constexpr int tile_acc_w(int bn, int npl) { return tile_packed(bn, npl) ? 2 * bn : bn; }
+__host__ __device__ constexpr int tile_mt(int bn, int npl) { return bn <= 32 ? 4 : (bn == 64 ? (npl == 2 ? 2 : 4) : 2); }
 __host__ __device__ constexpr int tile_nbuf(int bn) { return bn <= 128 ? 2 : 1; }
 constexpr int MAX_STAGES = 4;
 constexpr int SMEM_LIMIT = 227 * 1024;
 
 struct ShArgs {
     const bf16* x;             // position planes [NPL][G][QA][8]
-    const bf16* w;             // [n_tile][ky][cb][kx][plane][cgroup][BN][8]
+    const bf16* w;             // [n_tile][ky][cb][kx][cgroup][plane][BN][8]
     const float* bias;
     const float* addend;
     float* y;
@@ -91,7 +96,9 @@ template <int BN, int NPASS>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_shift_tcgen05_kernel(const __grid_constant__ ShArgs a) {
     constexpr int NPL = NPASS == 3 ? 2 : 1;
-    constexpr int MT = tile_mt(BN), NBUF = tile_nbuf(BN), TILE_POS = MT * 128;
+    constexpr int MT = tile_mt(BN, NPL), NBUF = tile_nbuf(BN), TILE_POS = MT * 128;
+    constexpr bool PK = tile_packed(BN, NPL);
+    constexpr int ACC_W = tile_acc_w(BN, NPL);      // accumulator columns per M-tile
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 127u) & ~127u;
     const int stages = a.stages;
@@ -123,7 +130,7 @@ conv_shift_tcgen05_kernel(const __grid_constant__ ShArgs a) {
     }
     if (warp == MMA_WARP) {
         __syncwarp();
-        tmem_alloc(tmem_ptr_addr, NBUF * MT * BN);
+        tmem_alloc(tmem_ptr_addr, NBUF * MT * ACC_W);
     }
     tc_fence_before();
     __syncthreads();
@@ -166,13 +173,14 @@ conv_shift_tcgen05_kernel(const __grid_constant__ ShArgs a) {
         // ============================== MMA issuer ==============================
         {   // every lane runs the loops (warp-uniform), one elected lane issues: see umma_bf16_elect
             constexpr uint32_t idesc = make_idesc(BN, false);
-            const uint32_t b_plane = 2u * BN * 16u;               // bytes of one [cgroup][BN][8] weight image
+            constexpr uint32_t idesc2 = make_idesc(PK ? 2 * BN : BN, false);
+            const uint32_t b_tap = (uint32_t)NPL * 2u * BN * 16u;   // bytes of one tap's [cgroup][plane][BN][8] weight image
             uint32_t it = 0, tl = 0;
             for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x, ++tl) {
                 const uint32_t acc = tl % NBUF, acc_ph = (tl / NBUF) & 1u;
                 mbar_wait(tmem_empty_bar(acc), acc_ph ^ 1u);
                 tc_fence_after();
-                const uint32_t d0 = tmem_base + acc * (MT * BN);
+                const uint32_t d0 = tmem_base + acc * (MT * ACC_W);
                 for (int st = 0; st < KG * a.CB; ++st, ++it) {
                     const int s = it % stages;
                     const uint32_t ph = (it / stages) & 1u;
@@ -180,23 +188,28 @@ conv_shift_tcgen05_kernel(const __grid_constant__ ShArgs a) {
                     tc_fence_after();
                     // descriptors differ only in their start address: add (byte offset >> 4) to the low word
                     const uint64_t a_base = make_nosw_desc(a_smem(s), plane_pitch, 128u);           // K-major: LBO = next 8
-                    const uint64_t b_base = make_nosw_desc(b_smem(s), BN * 16u, 128u);              // channels, SBO = next 8 rows
-                    const uint32_t a_lo_off = (2u * plane_pitch) >> 4, b_lo_off = b_plane >> 4;
+                    const uint64_t b_base = make_nosw_desc(b_smem(s), NPL * BN * 16u, 128u);        // channels, SBO = next 8 rows
+                    const uint32_t a_lo_off = (2u * plane_pitch) >> 4, b_lo_off = (BN * 16u) >> 4;   // lo rows follow the hi rows
                     uint32_t tap = 0;
                     for (int r = 0; r < a.KYG; ++r) {
                         const uint32_t row = (uint32_t)(r * a.Wp);
 #pragma unroll 1
                         for (int kx = 0; kx < a.K; ++kx, ++tap) {
-                            const uint64_t b_hi = b_base + (uint64_t)(tap * NPL * (b_plane >> 4));
+                            const uint64_t b_hi = b_base + (uint64_t)(tap * (b_tap >> 4));
                             const uint64_t a_t = a_base + (uint64_t)(row + (uint32_t)kx);
                             const uint32_t accum = (uint32_t)((st | (int)tap) != 0);
 #pragma unroll
                             for (int mt = 0; mt < MT; ++mt) {
                                 const uint64_t a_hi = a_t + (uint64_t)(mt * 128);
-                                umma_bf16_elect(d0 + mt * BN, a_hi, b_hi, idesc, accum);
-                                if (NPASS == 3) {
-                                    umma_bf16_elect(d0 + mt * BN, a_hi + a_lo_off, b_hi, idesc, 1u);
-                                    umma_bf16_elect(d0 + mt * BN, a_hi, b_hi + b_lo_off, idesc, 1u);
+                                if (PK) {       // columns [0, BN): a_hi w_hi + a_lo w_hi, columns [BN, 2 BN): a_hi w_lo
+                                    umma_bf16_elect(d0 + mt * ACC_W, a_hi, b_hi, idesc2, accum);
+                                    umma_bf16_elect(d0 + mt * ACC_W, a_hi + a_lo_off, b_hi, idesc, 1u);
+                                } else {
+                                    umma_bf16_elect(d0 + mt * ACC_W, a_hi, b_hi, idesc, accum);
+                                    if (NPASS == 3) {
+                                        umma_bf16_elect(d0 + mt * ACC_W, a_hi + a_lo_off, b_hi, idesc, 1u);
+                                        umma_bf16_elect(d0 + mt * ACC_W, a_hi, b_hi + b_lo_off, idesc, 1u);
+                                    }
                                 }
                             }
                         }
@@ -231,7 +244,14 @@ conv_shift_tcgen05_kernel(const __grid_constant__ ShArgs a) {
                     const int nb = n0 + j * 16;
                     if (nb >= a.Cout) break;                                // warp-uniform
                     uint32_t raw[16];
-                    tmem_ld16(tmem_base + ((uint32_t)(wq * 32) << 16) + acc * (MT * BN) + (uint32_t)(mt * BN + j * 16), raw);
+                    const uint32_t tcol = tmem_base + ((uint32_t)(wq * 32) << 16) + acc * (MT * ACC_W) + (uint32_t)(mt * ACC_W + j * 16);
+                    tmem_ld16(tcol, raw);
+                    if (PK) {
+                        uint32_t raw2[16];
+                        tmem_ld16(tcol + BN, raw2);
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) raw[i] = __float_as_uint(__uint_as_float(raw[i]) + __uint_as_float(raw2[i]));
+                    }
                     if (valid) {
                         float* yrow = a.y + m * a.out_pitch + nb;
                         if (a.vec_ok) {
@@ -275,11 +295,12 @@ conv_shift_tcgen05_kernel(const __grid_constant__ ShArgs a) {
     __syncthreads();
     if (warp == MMA_WARP) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, NBUF * MT * BN);
+        tmem_dealloc(tmem_base, NBUF * MT * ACC_W);
     }
 }
 
-// weights: OIHW fp32 -> [n_tile][ky][cb][kx][plane][cgroup][BN][8] bf16 (plane 1 = bf16 remainder, when npl == 2)
+// weights: OIHW fp32 -> [n_tile][ky][cb][kx][cgroup][plane][BN][8] bf16 (plane 1 = bf16 remainder, when npl == 2): inside a
+// channel group the BN remainder rows follow the BN leading rows, so one K-major descriptor covers [w_hi | w_lo] as 2 BN rows
 __global__ void pack_weight_shift_kernel(const float* __restrict__ w, bf16* __restrict__ out, int Cout, int Cin, int K,
                                          int transpose_flip, int BN, int ntiles, int CB, int npl) {
     const int Od = transpose_flip ? Cin : Cout, Id = transpose_flip ? Cout : Cin;
@@ -303,10 +324,10 @@ __global__ void pack_weight_shift_kernel(const float* __restrict__ w, bf16* __re
                 v = w[(((long long)o * Cin + i) * K + ky) * K + kx];
         }
         const bf16 hi = __float2bfloat16_rn(v);
-        const long long base = ((((long long)nt * K + ky) * CB + cb) * K + kx) * npl;
-        bf16* dst = out + (((base * 2 + cgp) * BN + n) * 8 + e);
+        const long long tap = (((long long)nt * K + ky) * CB + cb) * K + kx;
+        bf16* dst = out + ((((tap * 2 + cgp) * npl) * BN + n) * 8 + e);
         dst[0] = hi;
-        if (npl == 2) dst[2LL * BN * 8] = __float2bfloat16_rn(v - __bfloat162float(hi));
+        if (npl == 2) dst[(long long)BN * 8] = __float2bfloat16_rn(v - __bfloat162float(hi));
     }
 }
 
@@ -319,7 +340,7 @@ template <typename T, int TG>
 __global__ void __launch_bounds__(256)
 split_positions_kernel(const T* __restrict__ src, bf16* __restrict__ planes, int N, int Hs, int Ws, int C, int pitch, int up,
                        int oy0, int ox0, int pad_mode, int pre_act, int Hp, int Wp, int G, int lead, int QA, int npl,
-                       float* __restrict__ colsum) {
+                       float* __restrict__ colsum, const FastDiv div_wp, const FastDiv div_hp) {
     constexpr int TP = 1024 / TG;                     // positions per tile: a tile is always 1024 (position, group) items
     __shared__ uint4 tile[2][TG * (TP + 1)];          // [plane][group][position], +1 column against bank conflicts
     __shared__ float red[8][TG * 8];
@@ -343,13 +364,24 @@ split_positions_kernel(const T* __restrict__ src, bf16* __restrict__ planes, int
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[i] = 0.f;
             if (g * 8 < C && q >= 0 && q < Q) {
-                const int xp = q % Wp;
-                const int r = q / Wp;
-                const int yp = r % Hp;
-                const int n = r / Hp;
-                const int sy = map_coord(yp - oy0, Hs * up, pad_mode, up, 1);
-                const int sx = map_coord(xp - ox0, Ws * up, pad_mode, up, 1);
-                if (sy >= 0 && sx >= 0) {
+                // position -> (image, row, column) with multiply-shift divisions; the generic coordinate map only for
+                // replicate padding (nearest x2 upsampling is a shift)
+                const int r = (int)fast_div((uint32_t)q, div_wp);
+                const int xp = q - r * Wp;
+                const int n = (int)fast_div((uint32_t)r, div_hp);
+                const int yp = r - n * Hp;
+                int sy = yp - oy0, sx = xp - ox0;
+                const int Hv = Hs * up, Wv = Ws * up;
+                if (pad_mode == PAD_REPLICATE) {
+                    sy = max(0, min(sy, Hv - 1));
+                    sx = max(0, min(sx, Wv - 1));
+                } else if (pad_mode == PAD_REFLECT) {
+                    sy = sy < 0 ? -sy : (sy >= Hv ? 2 * (Hv - 1) - sy : sy);
+                    sx = sx < 0 ? -sx : (sx >= Wv ? 2 * (Wv - 1) - sx : sx);
+                }
+                const bool inside = (unsigned)sy < (unsigned)Hv && (unsigned)sx < (unsigned)Wv;
+                if (up == 2) { sy >>= 1; sx >>= 1; }
+                if (inside) {
                     const T* sp = src + ((size_t)((n * Hs + sy) * Ws + sx) * pitch + g * 8);
                     if (vec) {
                         ld8(sp, v);
@@ -357,12 +389,16 @@ split_positions_kernel(const T* __restrict__ src, bf16* __restrict__ planes, int
 #pragma unroll
                         for (int i = 0; i < 8; ++i) v[i] = (g * 8 + i < C) ? to_f(sp[i]) : 0.f;
                     }
+                    if (pre_act != ACT_NONE) {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) v[i] = act_apply(v[i], pre_act);
+                        for (int i = 0; i < 8; ++i) v[i] = act_apply(v[i], pre_act);
+                    }
                 }
             }
+            if (colsum != nullptr) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) csum[i] += v[i];
+                for (int i = 0; i < 8; ++i) csum[i] += v[i];
+            }
             uint4 hi, lo;
             __nv_bfloat162* hh = reinterpret_cast<__nv_bfloat162*>(&hi);
             __nv_bfloat162* ll = reinterpret_cast<__nv_bfloat162*>(&lo);
@@ -431,7 +467,7 @@ int make_plan(int K, int Wp, int npl, int bn, ShPlan& p) {
     for (int mode = 0; mode < 2; ++mode) {
         p.KYG = mode == 0 ? K : 1;
         if (mode == 1 && K == 1) break;
-        p.NP = tile_mt(bn) * 128 + (p.KYG - 1) * Wp + K - 1;
+        p.NP = tile_mt(bn, npl) * 128 + (p.KYG - 1) * Wp + K - 1;
         p.NPa = (p.NP + 7) / 8 * 8;
         p.a_bytes = npl * 2 * p.NPa * 16;
         p.b_chunk_bytes = K * npl * 2 * p.bn * 16;
@@ -508,7 +544,7 @@ int split_positions(const void* src, int dt, void* planes, const PosFrame& f, in
 #define AFFGW_SPLIT(T, TGV)                                                                                               \
     split_positions_kernel<T, TGV><<<dim3((unsigned)min((QA + 1024 / TGV - 1) / (1024 / TGV), 148 * 8), (unsigned)((f.G + TGV - 1) / TGV)), \
                                      256, 0, st>>>((const T*)src, (bf16*)planes, f.N, Hs, Ws, C, pitch, up, oy0, ox0, pad_mode, \
-                                                   pre_act, f.Hp, f.Wp, f.G, f.lead, QA, npl, colsum)
+                                                   pre_act, f.Hp, f.Wp, f.G, f.lead, QA, npl, colsum, make_fastdiv(f.Wp), make_fastdiv(f.Hp))
     if (dt == AFFGW_F32) {
         if (f.G <= 2) AFFGW_SPLIT(float, 2);
         else if (f.G <= 4) AFFGW_SPLIT(float, 4);
@@ -581,7 +617,7 @@ int conv_pos_tc(const void* x_planes, const PosFrame& f, const void* w_packed, c
     a.a_bytes = p.a_bytes; a.b_chunk_bytes = p.b_chunk_bytes;
     a.n_tiles = (Cout + p.bn - 1) / p.bn;
     const long long q_last = ((long long)(f.N - 1) * f.Hp + oy0 + OH - 1) * f.Wp + ox0 + OW - 1;
-    a.total_tiles = (int)((q_last / (tile_mt(p.bn) * 128) + 1) * a.n_tiles);
+    a.total_tiles = (int)((q_last / (tile_mt(p.bn, npl) * 128) + 1) * a.n_tiles);
     a.vec_ok = (Cout % 16 == 0) && (out_pitch % 4 == 0) && (((uintptr_t)y) % 16 == 0) &&
                (!addend || ((uintptr_t)addend) % 16 == 0);
     if (passes == 3) {
@@ -639,6 +675,10 @@ conv_wgrad_shift_kernel(const __grid_constant__ WsArgs a, const __grid_constant_
                         const __grid_constant__ CUtensorMap tmdy) {
     constexpr int NPL = NPASS == 3 ? 2 : 1;
     constexpr int GB = BN / 8;
+    // thin tiles in split-bf16 mode: x_hi x [dY_hi | dY_lo] is one MMA of width 2 BN (the remainder plane's channel groups follow
+    // the leading plane's in shared memory), x_lo x dY_hi a second one; the epilogue adds the two column blocks (see tile_packed)
+    constexpr bool PK = tile_packed(BN, NPL);
+    constexpr int ACC_W = tile_acc_w(BN, NPL);
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 127u) & ~127u;
     const int stages = a.stages;
@@ -719,6 +759,7 @@ conv_wgrad_shift_kernel(const __grid_constant__ WsArgs a, const __grid_constant_
         // ============================== MMA issuer ==============================
         {   // every lane runs the loops (warp-uniform), one elected lane issues: see umma_bf16_elect
             constexpr uint32_t idesc = make_idesc(BN, true);
+            constexpr uint32_t idesc2 = make_idesc(PK ? 2 * BN : BN, true);
             for (int st = 0; st < nst; ++st) {
                 const int s = st % stages;
                 const uint32_t ph = (uint32_t)(st / stages) & 1u;
@@ -741,10 +782,15 @@ conv_wgrad_shift_kernel(const __grid_constant__ WsArgs a, const __grid_constant_
 #pragma unroll 1
                     for (int j = 0; j < nacc; ++j) {
                         const uint64_t a_hi = a_base + (uint64_t)((uint32_t)(k * 16) + a_first + (uint32_t)j * a_step);
-                        umma_bf16_elect(tmem_base + j * BN, a_hi, b_hi, idesc, accum);
-                        if (NPASS == 3) {
-                            umma_bf16_elect(tmem_base + j * BN, a_hi + a_lo_off, b_hi, idesc, 1u);
-                            umma_bf16_elect(tmem_base + j * BN, a_hi, b_hi + b_lo_off, idesc, 1u);
+                        if (PK) {
+                            umma_bf16_elect(tmem_base + j * ACC_W, a_hi, b_hi, idesc2, accum);
+                            umma_bf16_elect(tmem_base + j * ACC_W, a_hi + a_lo_off, b_hi, idesc, 1u);
+                        } else {
+                            umma_bf16_elect(tmem_base + j * ACC_W, a_hi, b_hi, idesc, accum);
+                            if (NPASS == 3) {
+                                umma_bf16_elect(tmem_base + j * ACC_W, a_hi + a_lo_off, b_hi, idesc, 1u);
+                                umma_bf16_elect(tmem_base + j * ACC_W, a_hi, b_hi + b_lo_off, idesc, 1u);
+                            }
                         }
                     }
                 }
@@ -781,7 +827,14 @@ conv_wgrad_shift_kernel(const __grid_constant__ WsArgs a, const __grid_constant_
                     const int nb = cob * BN + jb * 16;
                     if (nb >= a.Cout) break;
                     uint32_t raw[16];
-                    tmem_ld16(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(j * BN + jb * 16), raw);
+                    const uint32_t tcol = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(j * ACC_W + jb * 16);
+                    tmem_ld16(tcol, raw);
+                    if (PK) {
+                        uint32_t raw2[16];
+                        tmem_ld16(tcol + BN, raw2);
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) raw[i] = __float_as_uint(__uint_as_float(raw[i]) + __uint_as_float(raw2[i]));
+                    }
                     if (rok) {
 #pragma unroll
                         for (int i = 0; i < 16; ++i)
@@ -865,7 +918,7 @@ int conv_wgrad_pos_tc(const void* x_planes, const PosFrame& fx, const void* dy_p
     // then covers TPM filter columns.  Otherwise one shared window, one accumulator per filter column.
     const bool packed = fx.G <= 8 && K > 1;
     a.TPM = packed ? (K < 16 / fx.G ? K : 16 / fx.G) : 1;
-    int acc_max = 512 / bn;                                     // accumulators that fit in TMEM ...
+    int acc_max = 512 / tile_acc_w(bn, npl);                    // accumulators that fit in TMEM ...
     if (packed) {                                               // ... and whose window copies fit in ~40 group slots
         const int cap = 24 / (a.TPM * fx.G) > 1 ? 24 / (a.TPM * fx.G) : 1;
         if (acc_max > cap) acc_max = cap;

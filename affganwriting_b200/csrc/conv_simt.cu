@@ -260,6 +260,69 @@ __global__ void conv_fold_kernel(const T* __restrict__ dxp, const T* __restrict_
     }
 }
 
+// Fast form for zero / reflect padding with up in {1, 2} (every layer of the path): one grid row per stored image row, so the
+// row candidates are block-uniform; the UP x UP interior taps are unconditional and the reflected ones (border pixels only)
+// predicated.  Reflection: padded coordinate p < pad maps to v = pad - p, p >= V + pad to v = 2 (V - 1) - (p - pad).
+template <typename T, int VEC, int UP>
+__global__ void __launch_bounds__(256)
+conv_fold_fast_kernel(const T* __restrict__ dxp, const T* __restrict__ xin, T* __restrict__ dx, int H, int W, int C, int pad,
+                      int reflect, int pre_act) {
+    const int Hv = H * UP, Wv = W * UP, Hp = Hv + 2 * pad, Wp = Wv + 2 * pad;
+    const int cv = C / VEC;
+    const int row = blockIdx.y, n = row / H, yy = row - n * H;
+    int ys[3 * UP];
+    bool yok[3 * UP];
+#pragma unroll
+    for (int u = 0; u < UP; ++u) {
+        const int v = yy * UP + u;
+        ys[3 * u] = pad + v;
+        yok[3 * u] = true;
+        ys[3 * u + 1] = pad - v;
+        yok[3 * u + 1] = reflect && v >= 1 && v <= pad;
+        ys[3 * u + 2] = pad + 2 * (Hv - 1) - v;
+        yok[3 * u + 2] = reflect && v <= Hv - 2 && v >= Hv - 1 - pad;
+    }
+    const T* const img = dxp + (long long)n * Hp * Wp * C;
+    const int items = W * cv;
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < items; i += gridDim.x * 256) {
+        const int xx = i / cv, c = (i - xx * cv) * VEC;
+        float acc[VEC];
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) acc[k] = 0.f;
+#pragma unroll
+        for (int a = 0; a < 3 * UP; ++a) {
+            if (!yok[a]) continue;                                      // block-uniform
+            const T* const rp = img + (long long)ys[a] * Wp * C + c;
+#pragma unroll
+            for (int u = 0; u < UP; ++u) {
+                const int v = xx * UP + u;
+                float t[VEC];
+                ldv<VEC>(rp + (pad + v) * C, t);
+#pragma unroll
+                for (int k = 0; k < VEC; ++k) acc[k] += t[k];
+                if (reflect && v >= 1 && v <= pad) {
+                    ldv<VEC>(rp + (pad - v) * C, t);
+#pragma unroll
+                    for (int k = 0; k < VEC; ++k) acc[k] += t[k];
+                }
+                if (reflect && v <= Wv - 2 && v >= Wv - 1 - pad) {
+                    ldv<VEC>(rp + (pad + 2 * (Wv - 1) - v) * C, t);
+#pragma unroll
+                    for (int k = 0; k < VEC; ++k) acc[k] += t[k];
+                }
+            }
+        }
+        const long long o = ((long long)row * W + xx) * C + c;
+        if (pre_act != ACT_NONE) {
+            float xv[VEC];
+            ldv<VEC>(xin + o, xv);
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) acc[k] *= act_grad(xv[k], pre_act);
+        }
+        stv<VEC>(dx + o, acc);
+    }
+}
+
 // column sums of a [M][pitch] matrix (bias gradient): out[c] += sum_m a[m][c]
 template <typename T>
 __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ a, float* __restrict__ out, long long M, int C,
@@ -364,6 +427,16 @@ int conv_fold(const void* dxp, const void* xin, void* dx, int dt, int N, int H, 
               int up, int pre_act, cudaStream_t st) {
     const bool v8 = (C % 8 == 0);
     const long long total = (long long)N * H * W * (v8 ? C / 8 : C);
+    if (v8 && dt == AFFGW_F32 && (up == 1 || up == 2) && pad_mode != PAD_REPLICATE && (long long)N * H <= 65535 &&
+        (long long)(W * up + 2 * pad) * C < (1LL << 30)) {
+        const int items = W * (C / 8);
+        dim3 grid((unsigned)min(8, (items + 255) / 256), (unsigned)(N * H));
+        const int reflect = pad_mode == PAD_REFLECT;
+        if (up == 1) conv_fold_fast_kernel<float, 8, 1><<<grid, 256, 0, st>>>((const float*)dxp, (const float*)xin, (float*)dx, H, W, C, pad, reflect, pre_act);
+        else conv_fold_fast_kernel<float, 8, 2><<<grid, 256, 0, st>>>((const float*)dxp, (const float*)xin, (float*)dx, H, W, C, pad, reflect, pre_act);
+        AFFGW_LAUNCH_CHECK("conv_fold");
+        return 0;
+    }
     const int blocks = (int)min((long long)148 * 8, (total + 255) / 256);
     if (dt == AFFGW_F32) {
         if (v8) conv_fold_kernel<float, 8><<<blocks, 256, 0, st>>>((const float*)dxp, (const float*)xin, (float*)dx, N, H, W, C, pad, pad_mode, up, pre_act);

@@ -72,21 +72,6 @@ __device__ __forceinline__ int map_fast(int v, int V, int pad_mode, int up) {
     return up == 2 ? (v >> 1) : v;
 }
 
-// q = n / d for 0 <= n < 2^31 with one 32 x 32 -> 64 bit multiply: mul = ceil(2^k / d), k = 31 + ceil(log2 d)
-struct FastDiv {
-    uint32_t mul, k, d;
-};
-inline FastDiv make_fastdiv(int d) {
-    FastDiv f;
-    int s = 0;
-    while ((1LL << s) < d) ++s;
-    f.k = 31 + s;
-    f.mul = (uint32_t)(((1ULL << f.k) + (uint64_t)d - 1) / (uint64_t)d);
-    f.d = (uint32_t)d;
-    return f;
-}
-__device__ __forceinline__ uint32_t fast_div(uint32_t n, const FastDiv& f) { return (uint32_t)(((uint64_t)n * f.mul) >> f.k); }
-
 struct WgArgs {
     const bf16* x;      // operand planes [NPL][N*H*W][Cin]   (g.Cin = stored channels)
     long long x_plane;

@@ -32,7 +32,21 @@ norm_stats_partial_kernel(const T* __restrict__ x, float* __restrict__ ws, long 
     for (int i = 0; i < VEC; ++i) s1[i] = s2[i] = 0.f;
     if (c < C) {
         ldv<VEC>(xg + c, K);
-        for (long long p = pbeg + tp; p < pend; p += S::TP) {
+        long long p = pbeg + tp;
+        for (; p + S::TP < pend; p += 2 * S::TP) {          // two positions in flight per thread
+            float v[VEC], w[VEC];
+            ldv<VEC>(xg + p * C + c, v);
+            ldv<VEC>(xg + (p + S::TP) * C + c, w);
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) {
+                const float d = v[i] - K[i], e = w[i] - K[i];
+                s1[i] += d;
+                s2[i] = fmaf(d, d, s2[i]);
+                s1[i] += e;
+                s2[i] = fmaf(e, e, s2[i]);
+            }
+        }
+        if (p < pend) {
             float v[VEC];
             ldv<VEC>(xg + p * C + c, v);
 #pragma unroll
@@ -78,30 +92,62 @@ __global__ void norm_stats_finalize_kernel(const T* __restrict__ x, const float*
 }
 
 // y = act( (x - mean) * rstd * gamma + beta ) + residual        gamma/beta indexed [g_or_0][c]
+// Same thread tile as the statistics kernels: a thread keeps the statistics of its VEC channels in registers and walks
+// positions (no index arithmetic per element); two positions are in flight per thread and the grid is sized for ~8 blocks per SM
+// so that enough bytes are outstanding to cover the HBM latency.
 template <typename T, int VEC>
-__global__ void norm_apply_kernel(const T* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ rstd,
-                                  const float* __restrict__ gamma, const float* __restrict__ beta,
-                                  const T* __restrict__ residual, T* __restrict__ y, int G, long long P, int C, int act,
-                                  int affine_per_group) {
-    const int cv = C / VEC;
-    const long long total = (long long)G * P * cv;
-    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-         idx += (long long)gridDim.x * blockDim.x) {
-        const int c = (int)(idx % cv) * VEC;
-        const int g = (int)(idx / cv / P);
-        const long long o = (idx / cv) * C + c;
-        float v[VEC], r[VEC];
-        ldv<VEC>(x + o, v);
-        if (residual) ldv<VEC>(residual + o, r);
-        const int sc = g * C + c, ac = (affine_per_group ? g * C : 0) + c;
+__global__ void __launch_bounds__(256)
+norm_apply_kernel(const T* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ rstd,
+                  const float* __restrict__ gamma, const float* __restrict__ beta, const T* __restrict__ residual,
+                  T* __restrict__ y, long long P, int C, int act, int affine_per_group, long long p_per_split) {
+    using S = StatTile<VEC>;
+    const int tc = threadIdx.x % S::TC, tp = threadIdx.x / S::TC;
+    const int c = blockIdx.x * S::CB + tc * VEC;
+    const int g = blockIdx.y;
+    if (c >= C) return;
+    const long long pbeg = blockIdx.z * p_per_split, pend = min(P, pbeg + p_per_split);
+    const long long base = (long long)g * P * C + c;
+    float mu[VEC], rs[VEC], ga[VEC], be[VEC];
+    const int sc = g * C + c, ac = (affine_per_group ? g * C : 0) + c;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+        mu[i] = mean[sc + i];
+        rs[i] = rstd[sc + i];
+        ga[i] = gamma ? gamma[ac + i] : 1.f;
+        be[i] = gamma ? beta[ac + i] : 0.f;
+    }
+    const bool affine = gamma != nullptr;
+    auto one = [&](float (&v)[VEC], const float (&r)[VEC]) {
 #pragma unroll
         for (int i = 0; i < VEC; ++i) {
-            float t = (v[i] - mean[sc + i]) * rstd[sc + i];
-            if (gamma) t = fmaf(t, gamma[ac + i], beta[ac + i]);
+            float t = (v[i] - mu[i]) * rs[i];
+            if (affine) t = fmaf(t, ga[i], be[i]);
             t = act_apply(t, act);
             v[i] = residual ? t + r[i] : t;
         }
-        stv<VEC>(y + o, v);
+    };
+    long long p = pbeg + tp;
+    for (; p + S::TP < pend; p += 2 * S::TP) {
+        float v0[VEC], v1[VEC], r0[VEC], r1[VEC];
+        const long long o0 = base + p * C, o1 = o0 + (long long)S::TP * C;
+        ldv<VEC>(x + o0, v0);
+        ldv<VEC>(x + o1, v1);
+        if (residual) {
+            ldv<VEC>(residual + o0, r0);
+            ldv<VEC>(residual + o1, r1);
+        }
+        one(v0, r0);
+        one(v1, r1);
+        stv<VEC>(y + o0, v0);
+        stv<VEC>(y + o1, v1);
+    }
+    if (p < pend) {
+        float v0[VEC], r0[VEC];
+        const long long o0 = base + p * C;
+        ldv<VEC>(x + o0, v0);
+        if (residual) ldv<VEC>(residual + o0, r0);
+        one(v0, r0);
+        stv<VEC>(y + o0, v0);
     }
 }
 
@@ -163,33 +209,60 @@ norm_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x, const 
 
 // dx = rstd * gamma * ( dy' - [batch_stats] (s1 + xhat * s2) / P )
 template <typename T, int VEC>
-__global__ void norm_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __restrict__ mean,
-                                      const float* __restrict__ rstd, const float* __restrict__ gamma,
-                                      const float* __restrict__ beta, const float* __restrict__ s1,
-                                      const float* __restrict__ s2, T* __restrict__ dx, int G, long long P, int C, int act,
-                                      int affine_per_group, int batch_stats, int unbiased) {
-    const int cv = C / VEC;
-    const long long total = (long long)G * P * cv;
+__global__ void __launch_bounds__(256)
+norm_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __restrict__ mean,
+                      const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ beta,
+                      const float* __restrict__ s1, const float* __restrict__ s2, T* __restrict__ dx, long long P, int C, int act,
+                      int affine_per_group, int batch_stats, int unbiased, long long p_per_split) {
+    using S = StatTile<VEC>;
+    const int tc = threadIdx.x % S::TC, tp = threadIdx.x / S::TC;
+    const int c = blockIdx.x * S::CB + tc * VEC;
+    const int g = blockIdx.y;
+    if (c >= C) return;
+    const long long pbeg = blockIdx.z * p_per_split, pend = min(P, pbeg + p_per_split);
+    const long long base = (long long)g * P * C + c;
     const float invP = 1.f / (float)P;
     const float invP2 = (unbiased && P > 1) ? 1.f / (float)(P - 1) : invP;
-    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-         idx += (long long)gridDim.x * blockDim.x) {
-        const int c = (int)(idx % cv) * VEC;
-        const int g = (int)(idx / cv / P);
-        const long long o = (idx / cv) * C + c;
-        float v[VEC], d[VEC];
-        ldv<VEC>(x + o, v);
-        ldv<VEC>(dy + o, d);
-        const int sc = g * C + c, ac = (affine_per_group ? g * C : 0) + c;
+    float mu[VEC], rs[VEC], ga[VEC], be[VEC], t1[VEC], t2[VEC];
+    const int sc = g * C + c, ac = (affine_per_group ? g * C : 0) + c;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+        mu[i] = mean[sc + i];
+        rs[i] = rstd[sc + i];
+        ga[i] = gamma ? gamma[ac + i] : 1.f;
+        be[i] = gamma ? beta[ac + i] : 0.f;
+        t1[i] = batch_stats ? s1[sc + i] * invP : 0.f;
+        t2[i] = batch_stats ? s2[sc + i] * invP2 : 0.f;
+    }
+    auto one = [&](float (&v)[VEC], const float (&d)[VEC]) {
 #pragma unroll
         for (int i = 0; i < VEC; ++i) {
-            const float rs = rstd[sc + i], xh = (v[i] - mean[sc + i]) * rs;
-            const float ga = gamma ? gamma[ac + i] : 1.f, be = gamma ? beta[ac + i] : 0.f;
-            float dd = d[i] * act_grad(fmaf(xh, ga, be), act);
-            if (batch_stats) dd -= s1[sc + i] * invP + xh * s2[sc + i] * invP2;
-            v[i] = rs * ga * dd;
+            const float xh = (v[i] - mu[i]) * rs[i];
+            float dd = d[i] * act_grad(fmaf(xh, ga[i], be[i]), act);
+            if (batch_stats) dd -= t1[i] + xh * t2[i];
+            v[i] = rs[i] * ga[i] * dd;
         }
-        stv<VEC>(dx + o, v);
+    };
+    long long p = pbeg + tp;
+    for (; p + S::TP < pend; p += 2 * S::TP) {
+        float v0[VEC], v1[VEC], d0[VEC], d1[VEC];
+        const long long o0 = base + p * C, o1 = o0 + (long long)S::TP * C;
+        ldv<VEC>(x + o0, v0);
+        ldv<VEC>(x + o1, v1);
+        ldv<VEC>(dy + o0, d0);
+        ldv<VEC>(dy + o1, d1);
+        one(v0, d0);
+        one(v1, d1);
+        stv<VEC>(dx + o0, v0);
+        stv<VEC>(dx + o1, v1);
+    }
+    if (p < pend) {
+        float v0[VEC], d0[VEC];
+        const long long o0 = base + p * C;
+        ldv<VEC>(x + o0, v0);
+        ldv<VEC>(dy + o0, d0);
+        one(v0, d0);
+        stv<VEC>(dx + o0, v0);
     }
 }
 
@@ -217,8 +290,10 @@ __global__ void bn_eval_stats_kernel(const float* __restrict__ running_mean, con
 
 inline int ew_blocks(long long total) { return (int)min((long long)148 * 8, (total + 255) / 256); }
 
-inline long long pick_split(int gx, int G, long long P, int& splits) {
-    long long s = (2LL * 148 + (long long)gx * G - 1) / ((long long)gx * G);
+// split the position range so that the grid has about `target` blocks (reductions: a few waves; streaming kernels: ~8 resident
+// blocks per SM so that enough loads are in flight)
+inline long long pick_split(int gx, int G, long long P, int& splits, long long target = 4LL * 148) {
+    long long s = (target + (long long)gx * G - 1) / ((long long)gx * G);
     const long long maxs = (P + 127) / 128;
     if (s > maxs) s = maxs;
     if (s < 1) s = 1;
@@ -263,8 +338,11 @@ int norm_stats(const void* x, int dt, float* ws, float* mean, float* rstd, float
 
 int norm_apply(const void* x, int dt, const float* mean, const float* rstd, const float* gamma, const float* beta,
                const void* residual, void* y, int G, long long P, int C, int act, int affine_per_group, cudaStream_t st) {
-    const long long total = (long long)G * P * (C % 8 == 0 ? C / 8 : C);
-#define CALL(T, V) norm_apply_kernel<T, V><<<ew_blocks(total), 256, 0, st>>>((const T*)x, mean, rstd, gamma, beta, (const T*)residual, (T*)y, G, P, C, act, affine_per_group)
+    const int cb = (C % 8 == 0) ? 64 : 32;
+    int splits;
+    const long long pps = pick_split(cdiv(C, cb), G, P, splits, 8LL * 148);
+    dim3 grid(cdiv(C, cb), G, splits);
+#define CALL(T, V) norm_apply_kernel<T, V><<<grid, 256, 0, st>>>((const T*)x, mean, rstd, gamma, beta, (const T*)residual, (T*)y, P, C, act, affine_per_group, pps)
     DISPATCH_T_VEC(dt, C, CALL);
 #undef CALL
     AFFGW_LAUNCH_CHECK("norm_apply");
@@ -288,8 +366,10 @@ int norm_bwd(const void* dy, const void* x, int dt, const float* mean, const flo
     DISPATCH_T_VEC(dt, C, CALL);
 #undef CALL
     AFFGW_LAUNCH_CHECK("norm_bwd_reduce");
-    const long long total = (long long)G * P * (C % 8 == 0 ? C / 8 : C);
-#define CALL(T, V) norm_bwd_apply_kernel<T, V><<<ew_blocks(total), 256, 0, st>>>((const T*)dy, (const T*)x, mean, rstd, gamma, beta, s1, s2, (T*)dx, G, P, C, act, affine_per_group, batch_stats, unbiased)
+    int asplits;
+    const long long apps = pick_split(cdiv(C, cb), G, P, asplits, 8LL * 148);
+    dim3 agrid(cdiv(C, cb), G, asplits);
+#define CALL(T, V) norm_bwd_apply_kernel<T, V><<<agrid, 256, 0, st>>>((const T*)dy, (const T*)x, mean, rstd, gamma, beta, s1, s2, (T*)dx, P, C, act, affine_per_group, batch_stats, unbiased, apps)
     DISPATCH_T_VEC(dt, C, CALL);
 #undef CALL
     AFFGW_LAUNCH_CHECK("norm_bwd_apply");

@@ -158,6 +158,60 @@ __global__ void avgpool3s2_bwd_kernel(const T* __restrict__ dy, T* __restrict__ 
     }
 }
 
+// Row-per-block form of the kernel above (fp32, 8-channel vectors): the candidate output rows of an input row and their
+// multiplicities are block-uniform; no 64-bit index arithmetic per element.
+template <int VEC>
+__global__ void __launch_bounds__(256)
+avgpool3s2_bwd_rows_kernel(const float* __restrict__ dy, float* __restrict__ dx, int H, int W, int C, int Ho, int Wo) {
+    const int cv = C / VEC;
+    const int row = blockIdx.y, n = row / H, yy = row - n * H;
+    const int oyb = max(0, (yy - 1) / 2 - 1);
+    int cy[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int oy = oyb + j;
+        cy[j] = 0;
+        if (oy < Ho) {
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky) cy[j] += (refl(2 * oy + ky - 1, H) == yy);
+        }
+    }
+    const float* const img = dy + (long long)n * Ho * Wo * C;
+    const int items = W * cv;
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < items; i += gridDim.x * 256) {
+        const int xx = i / cv, c = (i - xx * cv) * VEC;
+        const int oxb = max(0, (xx - 1) / 2 - 1);
+        int cx[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int ox = oxb + k;
+            cx[k] = 0;
+            if (ox < Wo) {
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) cx[k] += (refl(2 * ox + kx - 1, W) == xx);
+            }
+        }
+        float acc[VEC];
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) acc[e] = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (!cy[j]) continue;                                   // block-uniform
+            const float* const rp = img + (long long)(oyb + j) * Wo * C + c;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (!cx[k]) continue;
+                float g[VEC];
+                ldv<VEC>(rp + (oxb + k) * C, g);
+                const float wgt = (float)(cy[j] * cx[k]) * (1.f / 9.f);
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) acc[e] = fmaf(g[e], wgt, acc[e]);
+            }
+        }
+        stv<VEC>(dx + ((long long)row * W + xx) * C + c, acc);
+    }
+}
+
 // ---------------------------------------------------------------- iAFF gate
 __device__ __forceinline__ float sigmoidf_(float v) { return 1.f / (1.f + __expf(-v)); }
 
@@ -770,6 +824,13 @@ int avgpool3s2_fwd(const void* x, void* y, int dt, int N, int H, int W, int C, c
 int avgpool3s2_bwd(const void* dy, void* dx, int dt, int N, int H, int W, int C, cudaStream_t st) {
     const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
     const long long total = (long long)N * H * W * VECN(C);
+    if (dt == AFFGW_F32 && C % 8 == 0 && (long long)N * H <= 65535) {
+        const int items = W * (C / 8);
+        dim3 grid((unsigned)min(8, (items + 255) / 256), (unsigned)(N * H));
+        avgpool3s2_bwd_rows_kernel<8><<<grid, 256, 0, st>>>((const float*)dy, (float*)dx, H, W, C, Ho, Wo);
+        AFFGW_LAUNCH_CHECK("avgpool3s2_bwd");
+        return 0;
+    }
 #define CALL(T, V) avgpool3s2_bwd_kernel<T, V><<<ew_blocks(total), 256, 0, st>>>((const T*)dy, (T*)dx, N, H, W, C, Ho, Wo)
     DISPATCH_T_VEC(dt, C, CALL);
 #undef CALL
