@@ -678,36 +678,54 @@ int affgw_cast(const void* x, int in_dt, void* y, int out_dt, long long n, void*
 
 }  // extern "C"
 
-// ---- gradient bucket pack / unpack (one block column per tensor) ---------------------------------------------
+// ---- gradient bucket pack / unpack -------------------------------------------------------------------------------
+// The bucket is cut into spans of 4096 elements; a block finds the tensor that covers the start of its span by binary search in
+// the (dense, increasing) offset table and walks on from there, so the copy is coalesced on both sides and the grid is sized by
+// bytes, not by tensor count (one 9 MB weight gradient used to be copied by 32 blocks).
 namespace {
-__global__ void bucket_pack_kernel(const float* const* ptrs, const long long* sizes, const long long* offsets, float* bucket) {
-    const float* src = ptrs[blockIdx.y];
-    float* dst = bucket + offsets[blockIdx.y];
-    const long long n = sizes[blockIdx.y];
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-        dst[i] = src[i];
-}
-__global__ void bucket_unpack_kernel(float* const* ptrs, const long long* sizes, const long long* offsets,
-                                     const float* bucket, float scale) {
-    float* dst = ptrs[blockIdx.y];
-    const float* src = bucket + offsets[blockIdx.y];
-    const long long n = sizes[blockIdx.y];
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-        dst[i] = src[i] * scale;
+template <bool UNPACK>
+__global__ void __launch_bounds__(256)
+bucket_copy_kernel(float* const* __restrict__ ptrs, const long long* __restrict__ sizes, const long long* __restrict__ offsets, int n,
+                   float* __restrict__ bucket, float scale) {
+    constexpr int SPAN = 256 * 16;
+    const long long total = offsets[n - 1] + sizes[n - 1];
+    for (long long s0 = blockIdx.x * (long long)SPAN; s0 < total; s0 += (long long)gridDim.x * SPAN) {
+        int lo = 0, hi = n - 1;
+        while (lo < hi) {                               // last tensor whose offset is <= s0
+            const int mid = (lo + hi + 1) >> 1;
+            if (offsets[mid] <= s0) lo = mid; else hi = mid - 1;
+        }
+        int t = lo;
+        long long toff = offsets[t], tend = toff + sizes[t];
+        float* p = ptrs[t];
+#pragma unroll 4
+        for (int k = 0; k < 16; ++k) {
+            const long long i = s0 + k * 256 + threadIdx.x;
+            if (i >= total) break;
+            while (i >= tend) {
+                ++t;
+                toff = offsets[t];
+                tend = toff + sizes[t];
+                p = ptrs[t];
+            }
+            if (UNPACK) p[i - toff] = bucket[i] * scale;
+            else bucket[i] = p[i - toff];
+        }
+    }
 }
 }  // namespace
 
 extern "C" int affgw_bucket_pack(const float* const* ptrs, const long long* sizes, const long long* offsets, int n,
                                  float* bucket, void* stream) {
     AFFGW_CHECK(ptrs && sizes && offsets && bucket && n > 0 && n <= 65535, "bucket_pack: bad argument");
-    bucket_pack_kernel<<<dim3(32, n), 256, 0, S(stream)>>>(ptrs, sizes, offsets, bucket);
+    bucket_copy_kernel<false><<<148 * 8, 256, 0, S(stream)>>>(const_cast<float* const*>(ptrs), sizes, offsets, n, bucket, 1.f);
     AFFGW_LAUNCH_CHECK("bucket_pack");
     return 0;
 }
 extern "C" int affgw_bucket_unpack(float* const* ptrs, const long long* sizes, const long long* offsets, int n,
                                    const float* bucket, float scale, void* stream) {
     AFFGW_CHECK(ptrs && sizes && offsets && bucket && n > 0 && n <= 65535, "bucket_unpack: bad argument");
-    bucket_unpack_kernel<<<dim3(32, n), 256, 0, S(stream)>>>(ptrs, sizes, offsets, bucket, scale);
+    bucket_copy_kernel<true><<<148 * 8, 256, 0, S(stream)>>>(ptrs, sizes, offsets, n, const_cast<float*>(bucket), scale);
     AFFGW_LAUNCH_CHECK("bucket_unpack");
     return 0;
 }
