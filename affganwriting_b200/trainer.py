@@ -9,6 +9,18 @@ which is of the same order as the GPU time of the kernels themselves.  With `cud
 each of the three sub-steps is captured once (after a few eager iterations that run every lazy initialisation) and
 replayed from then on; the gradient exchange (NCCL) and the optimiser steps stay eager between the replays, so nothing
 that talks to another rank is ever inside a graph.  The batch is copied into static device tensors before each replay.
+
+Overlapped exchange (`overlap_exchange=True`, graph mode only).  The three sub-networks have separate parameters and
+cla_update touches only the classifier, dis_update only generator (forward) + discriminator, gen_update all three.  So the
+gradient exchange + Adam of the GENERATOR (the largest: ~160 MB of gradients) can run on a side stream while the next
+iteration's cla_update graph replays, and the classifier's while dis_update replays; the discriminator's cannot (gen_update
+needs its new weights at once).  Stream order: the side stream waits for the graph that produced the gradients; the main
+stream waits for the step's event before the first graph that reads the updated weights (dis_update after the generator's
+step, gen_update after the classifier's) - the same points where the next replay would overwrite the gradient buffers.
+Each graph then has its OWN memory pool: with a shared pool the classifier graph's scratch buffers alias the generator
+graph's gradient buffers, which the side stream is still reading.  `join()` makes the main stream wait for everything
+pending; train_step() leaves the generator's step in flight, so call join() before reading weights, evaluating,
+checkpointing or switching to another path.
 """
 import torch
 
@@ -21,7 +33,7 @@ class Trainer:
     GRAPH_WARMUP = 3      # eager iterations before the capture
 
     def __init__(self, num_writers=500, lr_gen=1e-4, lr_dis=1e-4, lr_cla=1e-5, device=None, skip_unused_wgrad=True,
-                 bucket_bytes=None, encoder=None, cuda_graph=False):
+                 bucket_bytes=None, encoder=None, cuda_graph=False, overlap_exchange=False):
         self.model = ConTranModel(num_writers, oov=True, device=device, encoder=encoder)
         m = self.model
         # main_run.py:275-278: Adam over filter(requires_grad, parameters()) with default betas / eps
@@ -44,6 +56,9 @@ class Trainer:
         self._eager_steps = 0
         self._side = None
         self.graph_launches = 0       # libaffgw launches recorded in the three graphs (= launches per replayed iteration)
+        self.overlap_exchange = bool(overlap_exchange) and self.cuda_graph
+        self._comm = None             # side stream of the overlapped exchange
+        self._pending = {}            # sub-network -> event of its exchange + Adam queued on the side stream
         broadcast_module(m)
 
     # ------------------------------------------------------------------------------------------------ sub-steps
@@ -79,7 +94,27 @@ class Trainer:
         return {"cla": l_cla.detach(), "dis": l_dis.detach(), "gen": l_total.detach(), "gen_dis": l_dis_g.detach(),
                 "gen_cla": l_cla_g.detach()}
 
+    # ------------------------------------------------------------------------------------------------ overlapped exchange
+    def join(self, *names):
+        """Main stream waits for the exchange + optimiser step of the named sub-networks (all pending ones when none is
+        named) queued on the side stream; no host synchronisation."""
+        for name in (names or tuple(self._pending)):
+            ev = self._pending.pop(name, None)
+            if ev is not None:
+                torch.cuda.current_stream().wait_event(ev)
+
+    def _finish_on_side_stream(self, name):
+        if self._comm is None:
+            self._comm = torch.cuda.Stream(device=self.model.device_)
+        self._comm.wait_stream(torch.cuda.current_stream())     # the graph that produced these gradients
+        with torch.cuda.stream(self._comm):
+            self._finish(name)
+            ev = torch.cuda.Event()
+            ev.record(self._comm)
+        self._pending[name] = ev
+
     def train_step_eager(self, batch, epoch=0):
+        self.join()
         outs = {}
         for name in ("cla", "dis", "gen"):
             outs[name] = self._fwd_bwd(name, batch, epoch)
@@ -91,6 +126,7 @@ class Trainer:
         if not self.cuda_graph:
             return self.train_step_eager(batch, epoch)
         if self._graphs is None:
+            self.join()
             if self._eager_steps < self.GRAPH_WARMUP:
                 # eager iterations on the stream the graphs will be captured on, so that the autograd nodes that outlive an
                 # iteration (AccumulateGrad) belong to that stream
@@ -109,11 +145,20 @@ class Trainer:
         outs = {}
         for name in ("cla", "dis", "gen"):
             graph, static_out, grads = self._graphs[name]
+            # dis_update reads the generator stepped by the previous iteration, gen_update also the classifier stepped by this
+            # one; cla_update reads neither, so the generator's exchange + Adam overlap it (and the classifier's dis_update)
+            if name == "dis":
+                self.join("gen")
+            elif name == "gen":
+                self.join()
             graph.replay()
             for p, g in grads:                      # an eager iteration in between may have re-pointed .grad
                 p.grad = g
             outs[name] = static_out
-            self._finish(name)
+            if self.overlap_exchange and name != "dis":
+                self._finish_on_side_stream(name)
+            else:
+                self._finish(name)
         self.model.iter_num += 1
         return self._pack(outs)
 
@@ -123,7 +168,8 @@ class Trainer:
         self._static_in = tuple(t.to(dev).clone() if torch.is_tensor(t) else t for t in batch)
         torch.cuda.synchronize()
         ops.clear_weight_cache(self.model)          # every packed weight a graph reads must be packed inside a graph
-        pool = torch.cuda.graph_pool_handle()       # the three graphs always replay in capture order: one shared pool
+        # the three graphs always replay in capture order: one shared pool - unless the exchange overlaps the next replay
+        pool = None if self.overlap_exchange else torch.cuda.graph_pool_handle()
         graphs, outs = {}, {}
         self.graph_launches = 0
         n0 = _lib.launch_count()

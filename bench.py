@@ -168,6 +168,7 @@ def main():
     ap.add_argument("--encoder", default="vgg", choices=["vgg", "resnet18", "resnet50"],
                     help="style encoder: vgg = configs[1] (default, the headline), resnet18 = configs[2]")
     ap.add_argument("--no-graph", action="store_true", help="issue every launch from Python instead of replaying a CUDA graph")
+    ap.add_argument("--no-overlap", action="store_true", help="gradient exchange + Adam on the main stream (no side-stream overlap)")
     ap.add_argument("--quick", action="store_true", help="timed steps only (no e2e / generation / CPU legs): the command ncu profiles")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "affgw" else args.warmup
@@ -197,7 +198,7 @@ def main():
     A.set_precision("bf16")
     torch.manual_seed(0)
     trainer = Trainer(num_writers=500, device=dev, encoder=None if args.encoder == "vgg" else args.encoder,
-                      cuda_graph=not args.no_graph)
+                      cuda_graph=not args.no_graph, overlap_exchange=not args.no_overlap)
     B = args.batch
     host = synthetic_batch(B, NUM_CHANNEL, seed=1234 + rank)
     host = tuple(t.pin_memory() if torch.is_tensor(t) else t for t in host)
@@ -274,6 +275,7 @@ def main():
     e2e_value = world / (ms_e2e / 1e3)
 
     # ---- generation throughput (secondary number of BASELINE.json's metric): style encode + decode per image
+    trainer.join()                                       # the last generator step may still be on the side stream
     gen = trainer.model.gen
     from affganwriting_b200.inference import GraphedGenerator
     gen_fn = gen if args.no_graph else GraphedGenerator(gen)
@@ -341,7 +343,7 @@ def main():
         "config": {"workload": WORKLOAD if args.encoder == "vgg" else WORKLOAD.replace(
                        "configs[1]", "configs[2] (%s style encoder)" % args.encoder),
                    "encoder": args.encoder, "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
-                   "cuda_graph": bool(trainer.graph_launches),
+                   "cuda_graph": bool(trainer.graph_launches), "overlap_exchange": bool(trainer.overlap_exchange),
                    "l2": "inputs larger than L2: 177 MB of style images are re-read every step (L2 is 126 MB)",
                    "samples_per_sec": value * B},
         "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 12,

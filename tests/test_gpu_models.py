@@ -305,19 +305,25 @@ def test_cuda_graph_replay_matches_eager_iterations(specs):
         b = Trainer(num_writers=500, device=dev)
         g = Trainer(num_writers=500, device=dev, cuda_graph=True)
         g.GRAPH_WARMUP = 1                     # capture at iteration 1, pure replays from iteration 2 on
+        # same, with the generator's / classifier's exchange + Adam on a side stream under the next graph replay
+        o = Trainer(num_writers=500, device=dev, cuda_graph=True, overlap_exchange=True)
+        o.GRAPH_WARMUP = 1
         b.model.load_state_dict(a.model.state_dict())
         g.model.load_state_dict(a.model.state_dict())
-        drift_ee = drift_eg = 0.0
+        o.model.load_state_dict(a.model.state_dict())
+        drift_ee = drift_eg = drift_eo = 0.0
         first = None
         for it in range(7):
-            la, lb, lg = a.train_step(batch), b.train_step(batch), g.train_step(batch)
+            la, lb, lg, lo = a.train_step(batch), b.train_step(batch), g.train_step(batch), o.train_step(batch)
             first = first or {k: float(v) for k, v in la.items()}
             for k in la:
                 drift_ee = max(drift_ee, abs(float(la[k]) - float(lb[k])))
                 drift_eg = max(drift_eg, abs(float(la[k]) - float(lg[k])))
+                drift_eo = max(drift_eo, abs(float(la[k]) - float(lo[k])))
             if it < 3:          # eager, capture pass, first pure replay: before the divergence has had time to grow
-                assert all(abs(float(la[k]) - float(lg[k])) <= 2e-4 * max(1.0, abs(float(la[k]))) for k in la), \
-                    (it, {k: (float(la[k]), float(lg[k])) for k in la})
+                for lx in (lg, lo):
+                    assert all(abs(float(la[k]) - float(lx[k])) <= 2e-4 * max(1.0, abs(float(la[k]))) for k in la), \
+                        (it, {k: (float(la[k]), float(lx[k])) for k in la})
         assert g.graph_launches > 1000 and g._graphs is not None and g._eager_steps == 1
         # the optimiser steps must reach the kernels (packed-weight cache invalidation, ops.weights_updated): the writer
         # classifier's loss falls by ~0.007 per iteration at lr 1e-5 on a fixed batch
@@ -329,12 +335,16 @@ def test_cuda_graph_replay_matches_eager_iterations(specs):
                 if not v.is_floating_point():
                     assert torch.equal(v, sy[k]), k                      # num_batches_tracked
             return max(float((v - sy[k]).abs().max()) for k, v in sx.items() if v.is_floating_point())
-        w_ee, w_eg = weight_drift(a, b), weight_drift(a, g)
-        print(f"\nafter 7 iterations: loss drift eager/eager {drift_ee:.2e}, eager/graph {drift_eg:.2e}; "
-              f"weight+buffer drift eager/eager {w_ee:.2e}, eager/graph {w_eg:.2e}")
-        assert drift_eg <= 10 * drift_ee + 2e-2
-        assert w_eg <= 10 * w_ee + 0.3
-        assert a.model.iter_num == g.model.iter_num
+        assert o._pending and o.overlap_exchange      # the generator's step of the last iteration is still on the side stream
+        o.join()
+        assert not o._pending
+        w_ee, w_eg, w_eo = weight_drift(a, b), weight_drift(a, g), weight_drift(a, o)
+        print(f"\nafter 7 iterations: loss drift eager/eager {drift_ee:.2e}, eager/graph {drift_eg:.2e}, eager/overlapped "
+              f"{drift_eo:.2e}; weight+buffer drift eager/eager {w_ee:.2e}, eager/graph {w_eg:.2e}, eager/overlapped {w_eo:.2e}")
+        assert drift_eg <= 10 * drift_ee + 2e-2 and drift_eo <= 10 * drift_ee + 2e-2
+        assert w_eg <= 10 * w_ee + 0.3 and w_eo <= 10 * w_ee + 0.3
+        assert a.model.iter_num == g.model.iter_num == o.model.iter_num
+        assert float(lo["cla"]) < first["cla"] - 0.02
     finally:
         A.set_precision("fp32")
 
