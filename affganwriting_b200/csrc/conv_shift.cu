@@ -48,7 +48,7 @@ constexpr int MAX_TILE_POS = 512;            // largest CTA tile in positions (f
 __host__ __device__ constexpr bool tile_packed(int bn, int npl) { return npl == 2 && bn <= 64; }
 __host__ __device__ constexpr int tile_acc_w(int bn, int npl) { return tile_packed(bn, npl) ? 2 * bn : bn; }
 __host__ __device__ constexpr int tile_mt(int bn, int npl) { return bn <= 32 ? 4 : (bn == 64 ? (npl == 2 ? 2 : 4) : 2); }
-__host__ __device__ constexpr int tile_nbuf(int bn) { return bn <= 128 ? 2 : 1; }
+__host__ __device__ constexpr int tile_nbuf(int acc_cols) { return 2 * acc_cols <= 512 ? 2 : 1; }   // accumulator buffers in TMEM
 constexpr int MAX_STAGES = 4;
 constexpr int SMEM_LIMIT = 227 * 1024;
 
@@ -92,13 +92,13 @@ __host__ __device__ constexpr uint32_t make_idesc(int n, bool mn_major) {
 // ---------------------------------------------------------------------------------------- forward / input gradient
 // A stage = the window of one 16-channel block (all kernel rows, or one kernel row when the whole-filter window does not
 // fit twice in shared memory) + its weights.
-template <int BN, int NPASS>
+template <int BN, int NPASS, int MT>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_shift_tcgen05_kernel(const __grid_constant__ ShArgs a) {
     constexpr int NPL = NPASS == 3 ? 2 : 1;
-    constexpr int MT = tile_mt(BN, NPL), NBUF = tile_nbuf(BN), TILE_POS = MT * 128;
     constexpr bool PK = tile_packed(BN, NPL);
     constexpr int ACC_W = tile_acc_w(BN, NPL);      // accumulator columns per M-tile
+    constexpr int NBUF = tile_nbuf(MT * ACC_W), TILE_POS = MT * 128;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 127u) & ~127u;
     const int stages = a.stages;
@@ -462,12 +462,13 @@ int wgrad_shift_block_n(int cout) { return cout <= 16 ? 16 : cout <= 32 ? 32 : c
 
 namespace {
 // pipeline-stage geometry; K x K filter on a frame of pitch Wp, npl planes, BN-wide weight stage
-int make_plan(int K, int Wp, int npl, int bn, ShPlan& p) {
+int make_plan(int K, int Wp, int npl, int bn, ShPlan& p, int mt = 0) {
     p.bn = bn;
+    if (mt == 0) mt = tile_mt(bn, npl);
     for (int mode = 0; mode < 2; ++mode) {
         p.KYG = mode == 0 ? K : 1;
         if (mode == 1 && K == 1) break;
-        p.NP = tile_mt(bn, npl) * 128 + (p.KYG - 1) * Wp + K - 1;
+        p.NP = mt * 128 + (p.KYG - 1) * Wp + K - 1;
         p.NPa = (p.NP + 7) / 8 * 8;
         p.a_bytes = npl * 2 * p.NPa * 16;
         p.b_chunk_bytes = K * npl * 2 * p.bn * 16;
@@ -481,9 +482,9 @@ int make_plan(int K, int Wp, int npl, int bn, ShPlan& p) {
     return 0;
 }
 
-template <int BN, int NPASS>
+template <int BN, int NPASS, int MT = tile_mt(BN, NPASS == 3 ? 2 : 1)>
 int launch_shift(const ShArgs& args, int smem_bytes, cudaStream_t st) {
-    auto kern = conv_shift_tcgen05_kernel<BN, NPASS>;
+    auto kern = conv_shift_tcgen05_kernel<BN, NPASS, MT>;
     static bool configured = false;
     if (!configured) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) {
@@ -510,7 +511,11 @@ int conv_shift_ok(const ConvGeom& g) {
     const long long Hp = g.Hv + 2 * g.pad, Wp = g.Wv + 2 * g.pad;
     if (Hp - g.KH + 1 != g.Ho || Wp - g.KW + 1 != g.Wo) return 0;
     // on tiny maps the padding positions (computed, then dropped) cost more than the window saves: im2col kernels
-    static const int waste_x10 = [] { const char* e = getenv("AFFGW_SHIFT_WASTE_X10"); return e ? atoi(e) : 15; }();
+    // ... unless the layer is wide: there the im2col kernel is bound by the L2 -> SM path (its operands are re-read per tap and per
+    // output-channel tile) and computing up to 2x the positions on the tensor pipe is still the faster way (4 x 14 maps: 1.7x;
+    // measured break-even is between that and the 2.6x of 2 x 7 maps)
+    static const int waste_env = [] { const char* e = getenv("AFFGW_SHIFT_WASTE_X10"); return e ? atoi(e) : 0; }();
+    const int waste_x10 = waste_env ? waste_env : ((g.Cin >= 128 && g.Cout >= 128) ? 20 : 15);
     if (10 * Hp * Wp > (long long)waste_x10 * g.Ho * g.Wo) return 0;
     if ((long long)g.N * Hp * Wp + 8192 >= (1LL << 31) / 16) return 0;           // 32-bit position arithmetic
     // the forward tile is as wide as Cout allows, the dgrad tile as wide as Cin allows: both windows must fit
@@ -597,7 +602,13 @@ int conv_pos_tc(const void* x_planes, const PosFrame& f, const void* w_packed, c
                 cudaStream_t st) {
     ShPlan p;
     const int npl = passes == 3 ? 2 : 1;
-    if (!make_plan(K, f.Wp, npl, shift_block_n(Cout), p) || -q_shift > f.lead) {
+    const int bn0 = shift_block_n(Cout);
+    const long long q_last = ((long long)(f.N - 1) * f.Hp + oy0 + OH - 1) * f.Wp + ox0 + OW - 1;
+    // tiny maps with wide layers (the 4 x 14 / 2 x 7 blocks of the discriminator): 256-position tiles leave most SMs idle;
+    // 128-position tiles double the tile count and double-buffer the 256-column accumulator
+    int mt = tile_mt(bn0, npl);
+    if (bn0 == 256 && (q_last / (mt * 128) + 1) * ((Cout + 255) / 256) < 148) mt = 1;
+    if (!make_plan(K, f.Wp, npl, bn0, p, mt) || -q_shift > f.lead) {
         affgw_set_error("conv_shift: window of a %dx%d filter on a %d-wide frame does not fit", K, K, f.Wp);
         return -1;
     }
@@ -616,8 +627,7 @@ int conv_pos_tc(const void* x_planes, const PosFrame& f, const void* w_packed, c
     a.KYG = p.KYG; a.NP = p.NP; a.NPa = p.NPa; a.stages = p.stages;
     a.a_bytes = p.a_bytes; a.b_chunk_bytes = p.b_chunk_bytes;
     a.n_tiles = (Cout + p.bn - 1) / p.bn;
-    const long long q_last = ((long long)(f.N - 1) * f.Hp + oy0 + OH - 1) * f.Wp + ox0 + OW - 1;
-    a.total_tiles = (int)((q_last / (tile_mt(p.bn, npl) * 128) + 1) * a.n_tiles);
+    a.total_tiles = (int)((q_last / (mt * 128) + 1) * a.n_tiles);
     a.vec_ok = (Cout % 16 == 0) && (out_pitch % 4 == 0) && (((uintptr_t)y) % 16 == 0) &&
                (!addend || ((uintptr_t)addend) % 16 == 0);
     if (passes == 3) {
@@ -626,7 +636,7 @@ int conv_pos_tc(const void* x_planes, const PosFrame& f, const void* w_packed, c
             case 32: return launch_shift<32, 3>(a, p.smem_bytes, st);
             case 64: return launch_shift<64, 3>(a, p.smem_bytes, st);
             case 128: return launch_shift<128, 3>(a, p.smem_bytes, st);
-            default: return launch_shift<256, 3>(a, p.smem_bytes, st);
+            default: return mt == 1 ? launch_shift<256, 3, 1>(a, p.smem_bytes, st) : launch_shift<256, 3>(a, p.smem_bytes, st);
         }
     }
     switch (p.bn) {
@@ -634,7 +644,7 @@ int conv_pos_tc(const void* x_planes, const PosFrame& f, const void* w_packed, c
         case 32: return launch_shift<32, 1>(a, p.smem_bytes, st);
         case 64: return launch_shift<64, 1>(a, p.smem_bytes, st);
         case 128: return launch_shift<128, 1>(a, p.smem_bytes, st);
-        default: return launch_shift<256, 1>(a, p.smem_bytes, st);
+        default: return mt == 1 ? launch_shift<256, 1, 1>(a, p.smem_bytes, st) : launch_shift<256, 1>(a, p.smem_bytes, st);
     }
 }
 

@@ -33,6 +33,8 @@ CASES = [
     (2, 64, 216, 64, 1, 7, 1, 3, "reflect", 1, "none"),           # decoder output conv (Cout = 1)
     (4, 2, 7, 1024, 500, 2, 7, 0, "zero", 1, "lrelu"),            # head: kernel 2, stride 7 (zero-insertion dgrad)
     (4, 2, 7, 512, 1024, 3, 1, 1, "reflect", 1, "lrelu"),
+    (6, 4, 14, 256, 256, 3, 1, 1, "reflect", 1, "lrelu"),         # tiny map, wide layer: 128-position tiles (MT = 1)
+    (3, 4, 14, 256, 512, 3, 1, 1, "zero", 1, "none"),             # same for a zero-padded layer (ResNet stage 3/4 shapes)
     (5, 7, 9, 192, 72, 3, 1, 1, "replicate", 1, "none"),          # ragged everything
     (1, 64, 216, 64, 64, 3, 1, 1, "zero", 1, "none"),             # many pixel splits in wgrad
 ]
