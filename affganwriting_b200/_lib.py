@@ -58,6 +58,7 @@ SIGNATURES = {
     "affgw_conv_thin_wgrad": [_P, _P, _P, _D, _P],
     "affgw_conv_tc_layout": [_D, _I],
     "affgw_conv_tc_tile_n": [_D, _I],
+    "affgw_conv_tc_tile_m": [_D, _I],
     "affgw_conv_pos_frames": [_D, C.POINTER(PosFrame), C.POINTER(PosFrame)],
     "affgw_position_planes_bytes": [C.POINTER(PosFrame), _I],
     "affgw_split_positions": [_P, _I, _P, C.POINTER(PosFrame), _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P],

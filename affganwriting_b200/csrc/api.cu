@@ -42,6 +42,7 @@ int pack_weight_shift(const float* w, void* out, int Cout, int Cin, int K, int i
 long long pack_weight_shift_bytes(int Cout, int Cin, int K, int ipad, int transpose_flip, int passes);
 // conv_thin.cu
 int conv_thin_ok(int Cin, int Cout, int K, int stride, int up);
+int shift_tile_mt(int cout, int npl, long long q_last);
 int conv_thin_fwd(const float* x, const float* w, const float* bias, float* y, float* scratch, const ConvGeom& g, cudaStream_t st);
 int conv_thin_dgrad_frame(const float* dy, const float* w, float* dframe, float* scratch, const ConvGeom& g, cudaStream_t st);
 int conv_thin_wgrad(const float* x, const float* dy, float* dw, const ConvGeom& g, cudaStream_t st);
@@ -302,6 +303,20 @@ int affgw_conv_tc_layout(const affgw_conv_desc* d, int for_dgrad) {
 }
 
 // output-channel tile width (the BN template argument) of the kernel that runs d: which = 0 forward, 1 dgrad, 2 wgrad
+// positions per CTA tile of the kernel that runs d (which = 0 forward, 1 dgrad; profiling labels: matches the third
+// template argument x 128 of conv_shift_tcgen05_kernel), 128 for every other kernel
+int affgw_conv_tc_tile_m(const affgw_conv_desc* d, int which) {
+    if (!d || which < 0 || which > 1 || affgw_conv_tc_layout(d, which) != AFFGW_WLAYOUT_SHIFT) return 128;
+    const long long Hp = (long long)d->H * d->upsample + 2 * d->pad, Wp = (long long)d->W * d->upsample + 2 * d->pad;
+    long long q_last;
+    if (which == 0) {
+        q_last = ((long long)(d->N - 1) * Hp + d->Ho - 1) * Wp + d->Wo - 1;
+    } else {
+        const bool direct = d->pad_mode == PAD_ZERO && d->upsample == 1 && d->pre_act == ACT_NONE;
+        q_last = direct ? ((long long)(d->N - 1) * Hp + d->pad + d->H - 1) * Wp + d->pad + d->W - 1 : (long long)d->N * Hp * Wp - 1;
+    }
+    return 128 * shift_tile_mt(which == 1 ? d->Cin : d->Cout, d->passes == 3 ? 2 : 1, q_last);
+}
 int affgw_conv_tc_tile_n(const affgw_conv_desc* d, int which) {
     if (!d || which < 0 || which > 2) return 0;
     const int lay = affgw_conv_tc_layout(d, which == 1);

@@ -460,6 +460,15 @@ int shift_block_n(int cout) { return cout > 128 ? 256 : cout > 64 ? 128 : cout >
 
 int wgrad_shift_block_n(int cout) { return cout <= 16 ? 16 : cout <= 32 ? 32 : cout <= 64 ? 64 : 128; }
 
+// M-tiles (of 128 positions) per CTA tile of the forward / dgrad kernel for `cout` output channels when the last computed
+// position is q_last
+int shift_tile_mt(int cout, int npl, long long q_last) {
+    const int bn = shift_block_n(cout);
+    int mt = tile_mt(bn, npl);
+    if (bn == 256 && (q_last / (mt * 128) + 1) * ((cout + 255) / 256) < 148) mt = 1;
+    return mt;
+}
+
 namespace {
 // pipeline-stage geometry; K x K filter on a frame of pitch Wp, npl planes, BN-wide weight stage
 int make_plan(int K, int Wp, int npl, int bn, ShPlan& p, int mt = 0) {
@@ -606,8 +615,7 @@ int conv_pos_tc(const void* x_planes, const PosFrame& f, const void* w_packed, c
     const long long q_last = ((long long)(f.N - 1) * f.Hp + oy0 + OH - 1) * f.Wp + ox0 + OW - 1;
     // tiny maps with wide layers (the 4 x 14 / 2 x 7 blocks of the discriminator): 256-position tiles leave most SMs idle;
     // 128-position tiles double the tile count and double-buffer the 256-column accumulator
-    int mt = tile_mt(bn0, npl);
-    if (bn0 == 256 && (q_last / (mt * 128) + 1) * ((Cout + 255) / 256) < 148) mt = 1;
+    const int mt = shift_tile_mt(Cout, npl, q_last);
     if (!make_plan(K, f.Wp, npl, bn0, p, mt) || -q_shift > f.lead) {
         affgw_set_error("conv_shift: window of a %dx%d filter on a %d-wide frame does not fit", K, K, f.Wp);
         return -1;

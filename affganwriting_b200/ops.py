@@ -49,7 +49,9 @@ def _kernel_name(d, which, passes):
     lay = L.lib().affgw_conv_tc_layout(C.byref(d), int(which == 1))
     bn = L.lib().affgw_conv_tc_tile_n(C.byref(d), which)
     if lay == L.WLAYOUT_SHIFT:
-        return ("conv_wgrad_shift_kernel<%d, %d>" if which == 2 else "conv_shift_tcgen05_kernel<%d, %d>") % (bn, passes)
+        if which == 2:
+            return "conv_wgrad_shift_kernel<%d, %d>" % (bn, passes)
+        return "conv_shift_tcgen05_kernel<%d, %d, %d>" % (bn, passes, L.lib().affgw_conv_tc_tile_m(C.byref(d), which) // 128)
     return ("conv_wgrad_tcgen05_kernel<%d, %d>" if which == 2 else "conv_igemm_tcgen05_kernel<%d, %d, float>") % (bn, passes)
 
 

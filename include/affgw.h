@@ -96,6 +96,9 @@ int affgw_split_positions(const void* src, int dtype, void* planes, const affgw_
 /* output-channel tile width (the BN template argument) of the kernel that runs the forward (which = 0), input-gradient (1)
  * or weight-gradient (2) convolution of d - lets a profiler name the kernel a call lands on */
 int affgw_conv_tc_tile_n(const affgw_conv_desc* d, int which);
+/* positions per CTA tile of the position-space forward (which = 0) / dgrad (which = 1) kernel that runs d: 128 x the third
+ * template argument of conv_shift_tcgen05_kernel (profiling labels); 128 for every other kernel */
+int affgw_conv_tc_tile_m(const affgw_conv_desc* d, int which);
 /* enable (1) / disable (0) the shifted kernel, -1 = query only; returns the previous setting (A/B testing) */
 int affgw_conv_tc_prefer_shift(int enable);
 /* activation tensor [rows][pitch] (fp32 or bf16) -> operand planes [passes == 3 ? 2 : 1][rows][c_store] (bf16), with the
