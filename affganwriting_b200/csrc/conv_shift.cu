@@ -465,7 +465,8 @@ int wgrad_shift_block_n(int cout) { return cout <= 16 ? 16 : cout <= 32 ? 32 : c
 int shift_tile_mt(int cout, int npl, long long q_last) {
     const int bn = shift_block_n(cout);
     int mt = tile_mt(bn, npl);
-    if (bn == 256 && (q_last / (mt * 128) + 1) * ((cout + 255) / 256) < 148) mt = 1;
+    // (only when 256-position tiles leave a third of the SMs idle: at ~146 tiles the larger tile's weight reuse wins)
+    if (bn == 256 && (q_last / (mt * 128) + 1) * ((cout + 255) / 256) < 100) mt = 1;
     return mt;
 }
 

@@ -9,7 +9,6 @@ print({k: d[k] for k in ("value", "ms_per_step", "gpu_launches", "clocks")})
 print("e2e", d["e2e"]); r = d["roofline"]; print("roofline", {k: r[k] for k in ("kernel", "achieved", "frac", "executed_frac", "share_of_step", "avg_launch_ms")})
 print("extra", d["extra"]); print("cpu", d["cpu_baseline"])
 for k, v in sorted(d["kernels"].items(), key=lambda kv: -kv[1]["ms_per_step"])[:14]: print("  %-46s" % k, {a: round(b, 3) for a, b in v.items()})
-for k, v in d["kernel_kinds"].items(): print("  kind", k, {a: round(b, 3) for a, b in v.items()})
 PY
 timeout 600 python bench.py --quick --no-graph --steps 1 --warmup 3 > gpurun_out/quick.json 2> gpurun_out/quick.err; rc=$?; echo "quick rc=$rc"; cat gpurun_out/quick.json
 if [ $rc -eq 0 ]; then
