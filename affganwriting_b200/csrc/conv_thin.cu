@@ -64,20 +64,22 @@ conv_1toN_kernel(const float* __restrict__ in, const float* __restrict__ wt /* [
 }
 
 // ------------------------------------------------------------------------------------------------ C -> 1 channel
-// tile = 8 rows x 128 columns, 4 consecutive pixels per thread; 8 channels of the halo tile in shared memory at a time
-constexpr int N1_CC = 8, N1_TW = 128, N1_PITCH = N1_TW + 8;     // pitch: >= 128 + K - 1, multiple of 4 floats
+// tile = 16 rows x 128 columns; a thread owns 2 rows x 4 consecutive pixels, so every input row it reads from shared memory
+// feeds both output rows, and the K x K filter of the current channel sits in registers (the kernel is bound by shared-memory
+// reads, not FMAs: 3 128-bit loads per 28 FMAs with one row per thread).  8 channels of the halo tile in shared memory at a time.
+constexpr int N1_CC = 8, N1_TW = 128, N1_ROWS = 16, N1_PITCH = N1_TW + 8;     // pitch: >= 128 + K - 1, multiple of 4 floats
 template <int K>
 __global__ void __launch_bounds__(256)
 conv_Nto1_kernel(const float* __restrict__ in, const float* __restrict__ w /* [C][K][K] */, const float* __restrict__ bias,
                  float* __restrict__ out, int H, int W, int C, int Ho, int Wo, int pad, int pad_mode, int post_act) {
     extern __shared__ __align__(16) float smem[];
-    constexpr int TH = 8 + K - 1;
+    constexpr int TH = N1_ROWS + K - 1;
     float* tile = smem;                                    // [N1_CC][TH][N1_PITCH]
     float* ws = smem + N1_CC * TH * N1_PITCH;              // [N1_CC][K][K]
     const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
-    const int x0 = blockIdx.x * N1_TW, y0 = blockIdx.y * 8, n = blockIdx.z;
+    const int x0 = blockIdx.x * N1_TW, y0 = blockIdx.y * N1_ROWS, n = blockIdx.z;
     constexpr int TWL = N1_TW + K - 1;
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
     for (int c0 = 0; c0 < C; c0 += N1_CC) {
         __syncthreads();
         for (int p = tid; p < TH * TWL; p += 256) {            // one pixel (8 contiguous channels = 2 x 16 bytes) per thread
@@ -97,9 +99,14 @@ conv_Nto1_kernel(const float* __restrict__ in, const float* __restrict__ w /* [C
         __syncthreads();
 #pragma unroll 1
         for (int c = 0; c < N1_CC; ++c) {
+            float wr[K][K];
 #pragma unroll
-            for (int ky = 0; ky < K; ++ky) {
-                const float* row = tile + (c * TH + ty + ky) * N1_PITCH + 4 * tx;
+            for (int ky = 0; ky < K; ++ky)
+#pragma unroll
+                for (int kx = 0; kx < K; ++kx) wr[ky][kx] = ws[(c * K + ky) * K + kx];
+#pragma unroll
+            for (int r = 0; r < K + 1; ++r) {                  // input row 2 ty + r feeds output row j with filter row r - j
+                const float* row = tile + (c * TH + 2 * ty + r) * N1_PITCH + 4 * tx;
                 float v[K + 3];
 #pragma unroll
                 for (int j = 0; j < (K + 3 + 3) / 4; ++j) {
@@ -109,23 +116,29 @@ conv_Nto1_kernel(const float* __restrict__ in, const float* __restrict__ w /* [C
                     if (4 * j + 2 < K + 3) v[4 * j + 2] = f.z;
                     if (4 * j + 3 < K + 3) v[4 * j + 3] = f.w;
                 }
-                const float* wr = ws + (c * K + ky) * K;
 #pragma unroll
-                for (int kx = 0; kx < K; ++kx) {
-                    const float wv = wr[kx];
+                for (int j = 0; j < 2; ++j) {
+                    const int ky = r - j;
+                    if (ky < 0 || ky >= K) continue;           // resolved at compile time
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) acc[j] = fmaf(v[j + kx], wv, acc[j]);
+                    for (int kx = 0; kx < K; ++kx)
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) acc[j][i] = fmaf(v[i + kx], wr[ky][kx], acc[j][i]);
                 }
             }
         }
     }
-    const int y = y0 + ty, x = x0 + 4 * tx;
-    if (y < Ho) {
-        const float b = bias ? __ldg(bias) : 0.f;
-        float* o = out + ((size_t)n * Ho + y) * Wo + x;
+    const float b = bias ? __ldg(bias) : 0.f;
+    const int x = x0 + 4 * tx;
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-            if (x + j < Wo) o[j] = act_apply(acc[j] + b, post_act);
+    for (int j = 0; j < 2; ++j) {
+        const int y = y0 + 2 * ty + j;
+        if (y < Ho) {
+            float* o = out + ((size_t)n * Ho + y) * Wo + x;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (x + i < Wo) o[i] = act_apply(acc[j][i] + b, post_act);
+        }
     }
 }
 
@@ -270,13 +283,13 @@ static int launch_1toN(const float* in, const float* wt, const float* bias, floa
 template <int K>
 static int launch_Nto1_k(const float* in, const float* w, const float* bias, float* out, int N, int H, int W, int C, int Ho, int Wo,
                          int pad, int pad_mode, int post_act, cudaStream_t st) {
-    const int smem = (N1_CC * (8 + K - 1) * N1_PITCH + N1_CC * K * K) * 4;
+    const int smem = (N1_CC * (N1_ROWS + K - 1) * N1_PITCH + N1_CC * K * K) * 4;
     static bool configured = false;
     if (!configured) {
         cudaFuncSetAttribute(conv_Nto1_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         configured = true;
     }
-    dim3 grid((Wo + N1_TW - 1) / N1_TW, (Ho + 7) / 8, N);
+    dim3 grid((Wo + N1_TW - 1) / N1_TW, (Ho + N1_ROWS - 1) / N1_ROWS, N);
     conv_Nto1_kernel<K><<<grid, 256, smem, st>>>(in, w, bias, out, H, W, C, Ho, Wo, pad, pad_mode, post_act);
     AFFGW_LAUNCH_CHECK("conv_Nto1");
     return 0;
