@@ -104,6 +104,7 @@ SIGNATURES = {
     "affgw_split_channels": [_P, _P, _P, _I, _L, _I, _I, _P],
     "affgw_bucket_pack": [_P, _P, _P, _I, _P, _P],
     "affgw_bucket_unpack": [_P, _P, _P, _I, _P, _F, _P],
+    "affgw_adam_step": [_P, _P, _P, _P, _P, _P, _I, _F, _F, _F, _F, _L, _F, _P],
 }
 _RESTYPE = {"affgw_last_error": C.c_char_p, "affgw_launch_count": _L, "affgw_pack_weight_tc_bytes": _L, "affgw_operand_planes_bytes": _L, "affgw_position_planes_bytes": _L, "affgw_conv_thin_ws_bytes": _L,
             "affgw_conv2d_dgrad_ws_bytes": _L, "affgw_conv2d_wgrad_ws_bytes": _L}

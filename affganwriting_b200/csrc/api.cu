@@ -744,3 +744,59 @@ extern "C" int affgw_bucket_unpack(float* const* ptrs, const long long* sizes, c
     AFFGW_LAUNCH_CHECK("bucket_unpack");
     return 0;
 }
+
+
+// ---- multi-tensor Adam (torch.optim.Adam, main_run.py:275-278: default betas / eps, no weight decay, no amsgrad) ----------
+// One launch steps every tensor of a table: the element range is cut into 4096-element spans like the gradient buckets; the
+// bias corrections of this step come from the host (all tensors of a call share the step count).
+//   m = m + (g - m)(1 - b1);  v = b2 v + (1 - b2) g^2;  p -= (lr / bc1) * m / (sqrt(v) / sqrt(bc2) + eps)
+namespace {
+__global__ void __launch_bounds__(256)
+adam_step_kernel(float* const* __restrict__ params, const float* const* __restrict__ grads, float* const* __restrict__ exp_avg,
+                 float* const* __restrict__ exp_avg_sq, const long long* __restrict__ sizes, const long long* __restrict__ offsets,
+                 int n, float step_size, float beta1, float beta2, float eps, float inv_bc2_sqrt, float grad_scale) {
+    constexpr int SPAN = 256 * 16;
+    const long long total = offsets[n - 1] + sizes[n - 1];
+    for (long long s0 = blockIdx.x * (long long)SPAN; s0 < total; s0 += (long long)gridDim.x * SPAN) {
+        int lo = 0, hi = n - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (offsets[mid] <= s0) lo = mid; else hi = mid - 1;
+        }
+        int t = lo;
+        long long toff = offsets[t], tend = toff + sizes[t];
+#pragma unroll 4
+        for (int k = 0; k < 16; ++k) {
+            const long long i = s0 + k * 256 + threadIdx.x;
+            if (i >= total) break;
+            while (i >= tend) {
+                ++t;
+                toff = offsets[t];
+                tend = toff + sizes[t];
+            }
+            const long long j = i - toff;
+            const float g = grads[t][j] * grad_scale;
+            float m = exp_avg[t][j], v = exp_avg_sq[t][j];
+            m = fmaf(g - m, 1.f - beta1, m);
+            v = fmaf(v, beta2, (1.f - beta2) * g * g);
+            exp_avg[t][j] = m;
+            exp_avg_sq[t][j] = v;
+            const float denom = sqrtf(v) * inv_bc2_sqrt + eps;
+            params[t][j] -= step_size * (m / denom);
+        }
+    }
+}
+}  // namespace
+
+extern "C" int affgw_adam_step(float* const* params, const float* const* grads, float* const* exp_avg, float* const* exp_avg_sq,
+                               const long long* sizes, const long long* offsets, int n, float lr, float beta1, float beta2,
+                               float eps, long long step, float grad_scale, void* stream) {
+    AFFGW_CHECK(params && grads && exp_avg && exp_avg_sq && sizes && offsets && n > 0 && n <= 65535, "adam_step: bad argument");
+    AFFGW_CHECK(step >= 1 && lr >= 0.f && beta1 >= 0.f && beta1 < 1.f && beta2 >= 0.f && beta2 < 1.f && eps >= 0.f,
+                "adam_step: bad hyper-parameter");
+    const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
+    adam_step_kernel<<<148 * 8, 256, 0, S(stream)>>>(params, grads, exp_avg, exp_avg_sq, sizes, offsets, n, (float)(lr / bc1), beta1,
+                                                      beta2, eps, (float)(1.0 / sqrt(bc2)), grad_scale);
+    AFFGW_LAUNCH_CHECK("adam_step");
+    return 0;
+}

@@ -2,7 +2,8 @@
 recogniser update: cla_update -> dis_update -> gen_update, each followed by the data-parallel gradient exchange of
 the sub-network that was just differentiated and by its Adam step.
 
-torch.optim.Adam is used as-is (fused multi-tensor Adam is SURVEY.md §8(f).2, a "next" row).
+The optimiser is `optim.Adam`: torch.optim.Adam's update for the reference's configuration as ONE libaffgw launch per
+sub-network; AFFGW_ADAM=torch selects torch.optim.Adam(fused=True) instead.
 
 CUDA graphs.  One iteration is ~5000 small launches issued from Python (~27 us each, ~140 ms per iteration on the host),
 which is of the same order as the GPU time of the kernels themselves.  With `cuda_graph=True` the forward + backward of
@@ -26,6 +27,7 @@ import torch
 
 from . import ops
 from .network_tro import ConTranModel
+from .optim import Adam
 from .parallel import GradientReducer, broadcast_module
 
 
@@ -39,10 +41,14 @@ class Trainer:
         # main_run.py:275-278: Adam over filter(requires_grad, parameters()) with default betas / eps
         # (fused=True is torch's single-pass multi-tensor implementation of the same update)
         import os
-        fused = os.environ.get("AFFGW_FUSED_ADAM", "1") != "0"
-        self.cla_opt = torch.optim.Adam([p for p in m.cla.parameters() if p.requires_grad], lr=lr_cla, fused=fused)
-        self.dis_opt = torch.optim.Adam([p for p in m.dis.parameters() if p.requires_grad], lr=lr_dis, fused=fused)
-        self.gen_opt = torch.optim.Adam([p for p in m.gen.parameters() if p.requires_grad], lr=lr_gen, fused=fused)
+        if os.environ.get("AFFGW_ADAM", "affgw") == "torch":
+            fused = os.environ.get("AFFGW_FUSED_ADAM", "1") != "0"
+            make = lambda ps, lr: torch.optim.Adam(ps, lr=lr, fused=fused)      # noqa: E731
+        else:
+            make = lambda ps, lr: Adam(ps, lr=lr)                               # noqa: E731
+        self.cla_opt = make([p for p in m.cla.parameters() if p.requires_grad], lr_cla)
+        self.dis_opt = make([p for p in m.dis.parameters() if p.requires_grad], lr_dis)
+        self.gen_opt = make([p for p in m.gen.parameters() if p.requires_grad], lr_gen)
         kw = {} if bucket_bytes is None else {"bucket_bytes": bucket_bytes}
         self.red = {"cla": GradientReducer(m.cla.parameters(), **kw), "dis": GradientReducer(m.dis.parameters(), **kw),
                     "gen": GradientReducer(m.gen.parameters(), **kw)}

@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define AFFGW_VERSION 106
+#define AFFGW_VERSION 107
 
 enum { AFFGW_DT_F32 = 0, AFFGW_DT_BF16 = 1 };
 enum { AFFGW_ACT_NONE = 0, AFFGW_ACT_RELU = 1, AFFGW_ACT_LRELU = 2, AFFGW_ACT_TANH = 3 };
@@ -223,6 +223,14 @@ int affgw_bucket_pack(const float* const* ptrs, const long long* sizes, const lo
                       void* stream);
 int affgw_bucket_unpack(float* const* ptrs, const long long* sizes, const long long* offsets, int n, const float* bucket,
                         float scale, void* stream);
+/* torch.optim.Adam step (main_run.py:275-278: betas (0.9, 0.999), eps 1e-8, no weight decay, no amsgrad) over a table of n
+ * fp32 tensors in ONE launch.  Device tables: params / grads / exp_avg / exp_avg_sq pointers, sizes and
+ * dense increasing offsets (offsets[i+1] = offsets[i] + sizes[i]) as for the buckets.  `step` >= 1 is the step count AFTER
+ * this call (bias corrections 1 - beta^step are formed on the host in double); grads are multiplied by grad_scale first.
+ *   m += (g - m)(1 - beta1);  v = beta2 v + (1 - beta2) g^2;  p -= lr / bc1 * m / (sqrt(v) / sqrt(bc2) + eps)              */
+int affgw_adam_step(float* const* params, const float* const* grads, float* const* exp_avg, float* const* exp_avg_sq,
+                    const long long* sizes, const long long* offsets, int n, float lr, float beta1, float beta2, float eps,
+                    long long step, float grad_scale, void* stream);
 
 #ifdef __cplusplus
 }
