@@ -116,3 +116,79 @@ def test_missing_library_fails_loudly(monkeypatch):
     monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libaffgw.so")
     with pytest.raises(RuntimeError, match="no CPU or PyTorch fallback"):
         _lib.lib()
+
+
+def _conv_desc(n, h, w, cin, cout, k, pad, pad_mode=1, stride=1, stride_w=0, passes=3, upsample=1):
+    from affganwriting_b200 import _lib
+    d = _lib.ConvDesc()
+    d.N, d.H, d.W, d.Cin, d.Cout, d.KH, d.KW = n, h, w, cin, cout, k, k
+    sw = stride_w or stride
+    d.stride, d.stride_w, d.pad, d.pad_mode, d.upsample = stride, stride_w, pad, pad_mode, upsample
+    d.Ho, d.Wo = (h * upsample + 2 * pad - k) // stride + 1, (w * upsample + 2 * pad - k) // sw + 1
+    c8 = lambda c: (c + 7) // 8 * 8                                               # noqa: E731
+    d.in_pitch, d.out_pitch, d.x_dtype, d.w_dtype, d.y_dtype = c8(cin), c8(cout), 1, 1, 1
+    d.algo, d.passes, d.grad_dtype = 2, passes, 0
+    return d
+
+
+def test_kernel_routing_of_the_step_shapes_needs_no_gpu():
+    """Which tcgen05 kernel a layer lands on: position-space kernels for stride-1 filters unless the padding
+    overhead is too large, 128-position tiles only where 256-position tiles would leave SMs idle, wide-N tiles by channel
+    count; the descriptor's column stride (Resnet18.py's (2, 1) stem) is honoured by the geometry check."""
+    from affganwriting_b200 import _lib
+    h = _lib.lib()
+    SHIFT, IM2COL = _lib.WLAYOUT_SHIFT, _lib.WLAYOUT_IM2COL
+    lay = lambda d, dg=0: h.affgw_conv_tc_layout(ctypes.byref(d), dg)             # noqa: E731
+    tn = lambda d, which: h.affgw_conv_tc_tile_n(ctypes.byref(d), which)          # noqa: E731
+    tm = lambda d, which: h.affgw_conv_tc_tile_m(ctypes.byref(d), which)          # noqa: E731
+    vgg = _conv_desc(64, 32, 108, 256, 256, 3, 1, pad_mode=0)
+    assert lay(vgg) == SHIFT and tn(vgg, 0) == 256 and tn(vgg, 1) == 256 and tn(vgg, 2) == 128 and tm(vgg, 0) == 256
+    res = _conv_desc(64, 8, 27, 512, 512, 3, 1)                                   # ~146 tiles of 256 positions: keep them
+    assert lay(res) == SHIFT and tm(res, 0) == 256 and tm(res, 1) == 256
+    d414 = _conv_desc(128, 4, 14, 256, 256, 3, 1)                                 # wide layer on a tiny map: 1.7x padding accepted,
+    assert lay(d414) == SHIFT and tn(d414, 0) == 256 and tm(d414, 0) == 128       # 128-position tiles
+    d27 = _conv_desc(128, 2, 7, 512, 512, 3, 1)                                   # 2.6x padding: im2col kernels
+    assert lay(d27) == IM2COL and tn(d27, 0) == 128 and tm(d27, 0) == 128
+    thin = _conv_desc(128, 64, 216, 16, 16, 3, 1)
+    assert lay(thin) == SHIFT and tn(thin, 0) == 16 and tn(thin, 2) == 16 and tm(thin, 0) == 512
+    c64 = _conv_desc(64, 64, 216, 64, 64, 3, 1, pad_mode=0)
+    assert tn(c64, 0) == 64 and tm(c64, 0) == 256                                 # N-packed hi/lo weights: 2 M-tiles
+    assert tm(_conv_desc(64, 64, 216, 64, 64, 3, 1, pad_mode=0, passes=1), 0) == 512
+    mix = _conv_desc(64, 8, 27, 1024, 512, 1, 0, pad_mode=0)
+    assert lay(mix) == IM2COL
+    shortcut = _conv_desc(128, 64, 216, 16, 32, 1, 0, pad_mode=0)                 # thin full-resolution 1x1: bulk-copy pipeline
+    assert lay(shortcut) == SHIFT
+    up = _conv_desc(64, 8, 27, 512, 256, 5, 2, upsample=2)
+    assert lay(up) == SHIFT and up.Ho == 16 and up.Wo == 54
+    stem = _conv_desc(2, 64, 216, 56, 96, 3, 1, pad_mode=0, stride=2, stride_w=1)  # rows / 2, columns kept
+    assert (stem.Ho, stem.Wo) == (32, 216) and h.affgw_conv_tc_supported(ctypes.byref(stem)) == 1 and lay(stem) == IM2COL
+    stem.Wo = 108                                                                  # the extent a (2, 2) stride would give
+    assert h.affgw_conv_tc_supported(ctypes.byref(stem)) == 0 and b"output extent" in h.affgw_last_error()
+
+
+def test_host_side_validation_of_optimiser_and_wire_format_needs_no_gpu():
+    import torch
+    from affganwriting_b200 import load_data as LD
+    from affganwriting_b200.optim import Adam
+    with pytest.raises(ValueError):
+        Adam([])
+    p = torch.zeros(3, requires_grad=True)
+    for bad in (dict(lr=-1.0), dict(eps=-1e-8), dict(betas=(1.0, 0.999)), dict(betas=(0.9, -0.1))):
+        with pytest.raises(ValueError):
+            Adam([p], **bad)
+    opt = Adam([p], lr=2e-4)
+    assert opt.param_groups[0]["lr"] == 2e-4 and opt.param_groups[0]["betas"] == (0.9, 0.999) and opt.param_groups[0]["eps"] == 1e-8
+    opt.step()                                                   # no gradient anywhere: nothing to do, no CUDA needed
+    assert opt.state == {} and opt.state_dict() == {"state": {}, "param_groups": [dict(
+        lr=2e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0, amsgrad=False, params=[0])]}
+    p.grad = torch.ones(3)
+    with pytest.raises(RuntimeError):
+        opt.step()                                               # CPU tensors: the product has no CPU path
+    opt.zero_grad()
+    assert p.grad is None
+    ref = torch.optim.Adam([torch.zeros(3, requires_grad=True), torch.zeros(2, requires_grad=True)])
+    with pytest.raises(ValueError):
+        opt.load_state_dict(ref.state_dict())                    # parameter group of another size
+    with pytest.raises(RuntimeError):
+        LD.decode_u8(torch.zeros(16, dtype=torch.uint8))         # CPU tensor
+    assert LD.batch_to_device(("src", 3), "cpu") == ("src", 3)   # non-tensor members pass through untouched
