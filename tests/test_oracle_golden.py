@@ -176,3 +176,38 @@ def test_u8_wire_format_oracle_matches_reference_loader(golden):
         levels |= set(np.unique(u8).tolist())
     assert len(levels) == 256                                    # every grey level went through the reference
     assert O.decode_u8(np.array([255, 0], dtype=np.uint8)).tolist() == [-1.0, 1.0]
+
+
+@pytest.mark.parametrize("case,batch", [("b3", 3), ("b2", 2)])
+def test_recogniser_oracle_matches_reference_fixture(case, batch, golden):
+    """SURVEY.md §8(f).1 (next row, oracle only so far): oracle.rec_oracle against logits the reference's RecModel produced
+    under the same torch seed (tests/golden/rec.npz, oracle/make_golden_rec.py).  Dropout is active on this path, so the pin
+    also checks that the restatement draws its random numbers in the reference's order."""
+    from oracle import rec_oracle as R
+    g = golden("rec.npz")
+    rep = json.load(open(os.path.join(GOLDEN, "oracle_vs_reference_rec.json")))
+    assert all(r["max_abs"] <= r["tol"] for r in rep) and len(rep) >= 6
+    sd = W.make_state(json.load(open(os.path.join(GOLDEN, "rec_spec.json"))))
+    b = O.synthetic_batch(batch, 15)
+    ref = _t(g[f"{case}.logits"])
+    stats = {}
+    torch.manual_seed(int(g[f"{case}.seed"]))
+    with torch.no_grad():
+        out = R.rec_forward(b["img_xt"], b["label_xt"], sd, [216] * batch, True, stats)
+    assert out.shape == ref.shape == (batch, 11, 55)
+    ok = ~torch.isnan(ref)
+    assert torch.equal(torch.isnan(out), ~ok)
+    assert float((out - ref)[ok].abs().max()) <= 1e-4 * max(1.0, float(ref[ok].abs().max()))
+    assert torch.equal(out.argmax(-1), _t(g[f"{case}.tokens"]))
+    target = b["label_xt"][:, 1:]
+    assert bool(torch.isnan(R.label_smoothing_loss(out, target))) == bool(g[f"{case}.loss_is_nan"])
+    loss = float(R.label_smoothing_loss(torch.nan_to_num(out, nan=0.0), target))
+    assert abs(loss - float(g[f"{case}.loss_nan_zeroed"])) <= 1e-4 * max(1.0, abs(loss))
+    k = "seq2seq.encoder.layer.features.1."
+    assert int(stats[k + "num_batches_tracked"]) == 1
+    assert rel_err(stats[k + "running_mean"], _t(g[f"{case}.post.features1.running_mean"])) <= 1e-5
+    # the path consumes random numbers (Dropout2d + GRU dropout under the forced train()): another seed, other logits
+    torch.manual_seed(int(g[f"{case}.seed"]) + 100)
+    with torch.no_grad():
+        other = R.rec_forward(b["img_xt"], b["label_xt"], sd, [216] * batch, True, None)
+    assert float((other - out)[~torch.isnan(other) & ok].abs().max()) > 1e-3
