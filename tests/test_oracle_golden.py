@@ -206,6 +206,20 @@ def test_recogniser_oracle_matches_reference_fixture(case, batch, golden):
     k = "seq2seq.encoder.layer.features.1."
     assert int(stats[k + "num_batches_tracked"]) == 1
     assert rel_err(stats[k + "running_mean"], _t(g[f"{case}.post.features1.running_mean"])) <= 1e-5
+    # backward of rec_update (network_tro.py:39-48) against the reference's gradients: per-tensor norms and the image gradient
+    sdo = {k: (v.clone().requires_grad_() if v.is_floating_point() else v) for k, v in sd.items()}
+    x = b["img_xt"].clone().requires_grad_()
+    torch.manual_seed(int(g[f"{case}.seed"]))
+    R.label_smoothing_loss(R.rec_forward(x, b["label_xt"], sdo, [216] * batch, True, None), target).backward()
+    ref_norm = dict(zip(g[f"{case}.grad.keys"].tolist(), g[f"{case}.grad.norms"].tolist()))
+    big = max(ref_norm.values())
+    for key, n in ref_norm.items():
+        mine = float(sdo[key].grad.norm())
+        assert abs(mine - n) <= 1e-2 * n + 1e-4 * big, (key, mine, n)      # structurally zero gradients: absolute bound only
+    dx_head = x.grad[:, :, ::8, ::8]
+    assert abs(float(x.grad.norm()) / float(g[f"{case}.dx.norm"]) - 1) <= 1e-2
+    assert float((dx_head.flatten() @ _t(g[f"{case}.dx.head"]).flatten()) /
+                 (dx_head.norm() * _t(g[f"{case}.dx.head"]).norm())) >= 0.999
     # the path consumes random numbers (Dropout2d + GRU dropout under the forced train()): another seed, other logits
     torch.manual_seed(int(g[f"{case}.seed"]) + 100)
     with torch.no_grad():
