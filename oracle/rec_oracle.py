@@ -160,3 +160,100 @@ def label_smoothing_loss(pred, target, vocab_size=55, padding_idx=2, smoothing=0
     dist[:, padding_idx] = 0
     dist[t == padding_idx] = 0.0
     return F.kl_div(x, dist, reduction="sum")
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Mask-injectable form (what a device implementation can be compared with): the same network with the recurrent layers
+# written out and every random draw exposed.  `masks` maps a draw's name to the KEEP-mask already divided by (1 - p)
+#   "enc.drop2d"            [B, 512, 1, 1]     Dropout2d after the VGG features (one value per (sample, channel))
+#   "enc.gru"               [T, B, 1024]       dropout on the encoder GRU's layer-0 output (both directions), before layer 1
+#   "dec.gru.{b}.{t}.{h}"   [1, 1, 512]        same for the decoder GRU, beam-search visit (sample b, step t, hypothesis h)
+# With masks=None the draws are made with torch's generator in exactly this order, which reproduces `_VF.gru` / F.dropout2d bit for
+# bit under the same seed (checked in tests/test_oracle_golden.py), and the masks drawn are returned in `record` if given.
+# ----------------------------------------------------------------------------------------------------------------------
+def _gru_cell(x, h, w_ih, w_hh, b_ih, b_hh):
+    gi, gh = F.linear(x, w_ih, b_ih), F.linear(h, w_hh, b_hh)
+    i_r, i_z, i_n = gi.chunk(3, -1)
+    h_r, h_z, h_n = gh.chunk(3, -1)
+    r, z = torch.sigmoid(i_r + h_r), torch.sigmoid(i_z + h_z)
+    n = torch.tanh(i_n + r * h_n)
+    return (1 - z) * n + z * h          # written as torch does: n + z * (h - n) differs in the last bit only
+
+
+def _draw(name, shape, dtype, masks, record):
+    if masks is not None:
+        m = masks[name]
+        assert tuple(m.shape) == tuple(shape), (name, tuple(m.shape), tuple(shape))
+    else:
+        m = torch.empty(shape, dtype=dtype).bernoulli_(1 - P_DROP).div_(1 - P_DROP)
+    if record is not None:
+        record[name] = m
+    return m
+
+
+def gru_layers(x, h0, weights, bidirectional, training, name, masks=None, record=None):
+    """nn.GRU with 2 layers on a [T, B, F] input of full-length sequences: returns (output [T, B, H * dirs], h_n [2 * dirs, B, H]);
+    inter-layer dropout (p = 0.5) multiplies the layer-0 output by the draw `name`."""
+    dirs = 2 if bidirectional else 1
+    T = x.shape[0]
+    finals = []
+    for layer in range(LAYERS):
+        outs = []
+        for d in range(dirs):
+            w = weights[4 * (layer * dirs + d): 4 * (layer * dirs + d) + 4]
+            h = h0[layer * dirs + d]
+            steps = range(T - 1, -1, -1) if d == 1 else range(T)
+            seq = [None] * T
+            for t in steps:
+                h = _gru_cell(x[t], h, *w)
+                seq[t] = h
+            outs.append(torch.stack(seq, 0))
+            finals.append(h)
+        x = torch.cat(outs, -1)
+        if layer == 0 and training:
+            x = x * _draw(name, x.shape, x.dtype, masks, record)
+    return x, torch.stack(finals, 0)
+
+
+def rec_forward_explicit(img, label, sd, masks=None, record=None, training=True, stats=None, beam_size=3, vocab_size=55,
+                         output_max_len=12):
+    """rec_forward with every random draw exposed (see above); all images must span the full width (the GAN step passes
+    img_width = IMG_WIDTH for every sample, network_tro.py:43,88-89)."""
+    x = torch.cat([img, img, img], dim=1)
+    B = x.shape[0]
+    ep, dp = "seq2seq.encoder.", "seq2seq.decoder."
+    f = vgg19_bn_features(x, sd, ep + "layer.features.", training, stats)
+    if training:
+        f = f * _draw("enc.drop2d", (B, f.shape[1], 1, 1), f.dtype, masks, record)
+    f = f.permute(3, 0, 2, 1).reshape(-1, B, f.shape[2] * f.shape[1])
+    enc_T = f.shape[0]
+    out, hid = gru_layers(f, torch.zeros(2 * LAYERS, B, HIDDEN, dtype=f.dtype), _gru_weights(sd, ep + "rnn.", True), True,
+                          training, "enc.gru", masks, record)
+    enc_out, enc_hidden = out[:, :, :HIDDEN] + out[:, :, HIDDEN:], hid[[1, 3]]
+    steps = output_max_len - 1
+    eye = torch.eye(vocab_size, dtype=f.dtype)
+    best = torch.zeros(steps, B, vocab_size, dtype=f.dtype)
+    dec_w = _gru_weights(sd, dp + "gru.", False)
+    for b in range(B):
+        enc_b = enc_out[:, b:b + 1, :]
+        beams = [dict(logp=0.0, tokens=[int(label[b, 0])], hidden=enc_hidden[:, b:b + 1, :].contiguous(),
+                      attn=torch.zeros(1, enc_T, dtype=f.dtype), dists=[])]
+        for t in range(steps):
+            new = []
+            for hyp, beam in enumerate(beams):
+                attn = attention(beam["hidden"], enc_b, [enc_T], beam["attn"], sd, dp + "attention.")
+                context = torch.bmm(enc_b.permute(1, 2, 0), attn).squeeze(2)
+                emb = sd[dp + "embedding.weight"][beam["tokens"][-1]].unsqueeze(0)
+                o, hnew = gru_layers(torch.cat((emb, context), 1).unsqueeze(0), beam["hidden"], dec_w, False, training,
+                                     f"dec.gru.{b}.{t}.{hyp}", masks, record)
+                logits = F.linear(o.squeeze(0), sd[dp + "out.weight"], sd[dp + "out.bias"])
+                logp = torch.log(logits + 1e-12).squeeze(0)
+                top_lp, top_id = torch.topk(logp, k=beam_size, dim=-1)
+                for k in range(beam_size):
+                    new.append(dict(logp=beam["logp"] + float(top_lp[k]), tokens=beam["tokens"] + [int(top_id[k])], hidden=hnew,
+                                    attn=attn.squeeze(2), dists=beam["dists"] + [logits.squeeze(0)]))
+            new.sort(key=lambda z: z["logp"], reverse=True)
+            beams = new[:beam_size]
+        top = max(beams, key=lambda z: z["logp"])
+        best[:len(top["dists"]), b, :] = torch.stack(top["dists"], dim=0)
+    return best.permute(1, 0, 2)

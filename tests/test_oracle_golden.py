@@ -225,3 +225,27 @@ def test_recogniser_oracle_matches_reference_fixture(case, batch, golden):
     with torch.no_grad():
         other = R.rec_forward(b["img_xt"], b["label_xt"], sd, [216] * batch, True, None)
     assert float((other - out)[~torch.isnan(other) & ok].abs().max()) > 1e-3
+
+
+def test_recogniser_oracle_with_explicit_dropout_masks(golden):
+    """The mask-injectable form of the recogniser oracle (the comparison target for a device implementation, which cannot
+    reproduce torch's CPU generator): drawing the masks with torch's generator in the documented order reproduces the
+    `_VF.gru` / F.dropout2d form - and so the reference - bit for bit up to rounding; feeding the recorded masks back in gives the
+    same logits again."""
+    from oracle import rec_oracle as R
+    g = golden("rec.npz")
+    sd = W.make_state(json.load(open(os.path.join(GOLDEN, "rec_spec.json"))))
+    b = O.synthetic_batch(2, 15)
+    ref = _t(g["b2.logits"])
+    with torch.no_grad():
+        rec = {}
+        torch.manual_seed(int(g["b2.seed"]))
+        drawn = R.rec_forward_explicit(b["img_xt"], b["label_xt"], sd, record=rec)
+        assert float((drawn - ref).abs().max()) <= 1e-4 * max(1.0, float(ref.abs().max()))
+        assert tuple(rec["enc.drop2d"].shape) == (2, 512, 1, 1) and tuple(rec["enc.gru"].shape) == (13, 2, 1024)
+        assert len(rec) == 2 + 2 * (1 + 10 * 3) and set(rec["enc.gru"].unique().tolist()) == {0.0, 2.0}
+        again = R.rec_forward_explicit(b["img_xt"], b["label_xt"], sd, masks=rec)
+        assert torch.equal(again, drawn)
+        # other masks, other logits; no masks at all (eval-style call) is yet another function
+        flipped = {k: (2.0 - v) for k, v in rec.items()}
+        assert float((R.rec_forward_explicit(b["img_xt"], b["label_xt"], sd, masks=flipped) - drawn).abs().max()) > 1e-3
