@@ -19,7 +19,11 @@ Two properties of the reference that any replacement has to reproduce, and that 
     torch.manual_seed the restatement consumes the generator identically (it calls the same ATen dropout / GRU entry points),
     which is what makes a bit-exact pin possible; a CUDA implementation has to take these masks as INPUTS.
   * The beam search scores hypotheses with log(step_out + 1e-12) where step_out are the decoder's raw LOGITS, not
-    probabilities (seq2seqnew2.py:126): negative logits give NaN scores, and torch.topk ranks NaN above every number.
+    probabilities (seq2seqnew2.py:126): negative logits give NaN scores, and torch.topk ranks NaN above every number.  On
+    random-init weights 46 % of the logits are negative, i.e. EVERY step has more than beam_size NaN scores and the hypotheses
+    kept are decided by the order in which ATen's CPU topk returns NaNs (e.g. topk([.3, nan, 1, nan, -2, nan, nan], 3) ->
+    indices [3, 6, 5]) and by how list.sort treats NaN keys.  The tokens chosen feed the next step, so the returned logits
+    depend on it: a device implementation either emulates that order or does the 3 x 55 selection with the same CPU calls.
 """
 import numpy as np
 import torch
