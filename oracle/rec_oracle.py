@@ -261,3 +261,52 @@ def rec_forward_explicit(img, label, sd, masks=None, record=None, training=True,
         top = max(beams, key=lambda z: z["logp"])
         best[:len(top["dists"]), b, :] = torch.stack(top["dists"], dim=0)
     return best.permute(1, 0, 2)
+
+
+def rec_forward_batched(img, label, sd, masks, stats=None, beam_size=3, vocab_size=55, output_max_len=12):
+    """The shape a device implementation takes (prototype, test infrastructure): per decoding step ONE batched decoder call
+    over every live hypothesis of every sample (B rows at step 0, 3 B afterwards) - attention, context, embedding, 2-layer GRU
+    step with the per-visit masks gathered row by row, logits - and then, per sample, the reference's own selection calls
+    (torch.topk / list.sort / max on 3 x 55 scores) on the host.  Same results as rec_forward_explicit with the same masks
+    (tests/test_oracle_golden.py), so only the arithmetic has to move to the device."""
+    x = torch.cat([img, img, img], dim=1)
+    B = x.shape[0]
+    ep, dp = "seq2seq.encoder.", "seq2seq.decoder."
+    f = vgg19_bn_features(x, sd, ep + "layer.features.", True, stats) * masks["enc.drop2d"]
+    f = f.permute(3, 0, 2, 1).reshape(-1, B, f.shape[2] * f.shape[1])
+    T = f.shape[0]
+    out, hid = gru_layers(f, torch.zeros(2 * LAYERS, B, HIDDEN, dtype=f.dtype), _gru_weights(sd, ep + "rnn.", True), True, True,
+                          "enc.gru", masks)
+    enc_out, enc_hidden = out[:, :, :HIDDEN] + out[:, :, HIDDEN:], hid[[1, 3]]
+    steps = output_max_len - 1
+    dec_w = _gru_weights(sd, dp + "gru.", False)
+    beams = [[dict(logp=0.0, tokens=[int(label[b, 0])], hidden=enc_hidden[:, b, :], attn=torch.zeros(T, dtype=f.dtype), dists=[])]
+             for b in range(B)]
+    for t in range(steps):
+        rows = [(b, h) for b in range(B) for h in range(len(beams[b]))]
+        hidden = torch.stack([beams[b][h]["hidden"] for b, h in rows], 1)                    # 2, N, 512
+        prev = torch.stack([beams[b][h]["attn"] for b, h in rows], 0)                         # N, T
+        enc = enc_out[:, [b for b, _ in rows], :]                                             # T, N, 512
+        tok = torch.tensor([beams[b][h]["tokens"][-1] for b, h in rows])
+        attn = attention(hidden, enc, [T] * len(rows), prev, sd, dp + "attention.")           # N, T, 1
+        context = torch.bmm(enc.permute(1, 2, 0), attn).squeeze(2)
+        xin = torch.cat((sd[dp + "embedding.weight"][tok], context), 1)
+        drop = torch.cat([masks[f"dec.gru.{b}.{t}.{h}"] for b, h in rows], 1)                 # 1, N, 512
+        h0 = _gru_cell(xin, hidden[0], *dec_w[0:4])
+        h1 = _gru_cell(h0 * drop[0], hidden[1], *dec_w[4:8])
+        logits = F.linear(h1, sd[dp + "out.weight"], sd[dp + "out.bias"])                     # N, V
+        new = [[] for _ in range(B)]
+        for r, (b, h) in enumerate(rows):                                                     # host side: the reference's own calls
+            beam = beams[b][h]
+            top_lp, top_id = torch.topk(torch.log(logits[r] + 1e-12), k=beam_size, dim=-1)
+            for k in range(beam_size):
+                new[b].append(dict(logp=beam["logp"] + float(top_lp[k]), tokens=beam["tokens"] + [int(top_id[k])],
+                                   hidden=torch.stack((h0[r], h1[r]), 0), attn=attn[r, :, 0], dists=beam["dists"] + [logits[r]]))
+        for b in range(B):
+            new[b].sort(key=lambda z: z["logp"], reverse=True)
+            beams[b] = new[b][:beam_size]
+    best = torch.zeros(steps, B, vocab_size, dtype=f.dtype)
+    for b in range(B):
+        top = max(beams[b], key=lambda z: z["logp"])
+        best[:, b, :] = torch.stack(top["dists"], dim=0)
+    return best.permute(1, 0, 2)

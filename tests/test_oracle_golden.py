@@ -246,6 +246,9 @@ def test_recogniser_oracle_with_explicit_dropout_masks(golden):
         assert len(rec) == 2 + 2 * (1 + 10 * 3) and set(rec["enc.gru"].unique().tolist()) == {0.0, 2.0}
         again = R.rec_forward_explicit(b["img_xt"], b["label_xt"], sd, masks=rec)
         assert torch.equal(again, drawn)
+        # the device-shaped prototype: one batched decoder call per step over all live hypotheses, selection on the host
+        batched = R.rec_forward_batched(b["img_xt"], b["label_xt"], sd, rec)
+        assert float((batched - drawn).abs().max()) <= 1e-5 and torch.equal(batched.argmax(-1), drawn.argmax(-1))
         # other masks, other logits; no masks at all (eval-style call) is yet another function
         flipped = {k: (2.0 - v) for k, v in rec.items()}
         assert float((R.rec_forward_explicit(b["img_xt"], b["label_xt"], sd, masks=flipped) - drawn).abs().max()) > 1e-3
