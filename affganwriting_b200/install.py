@@ -20,29 +20,48 @@ MODULE_NAMES = ("GenModel_FC", "DisModel", "WriterClaModel", "TextEncoder_FC", "
                 "get_num_adain_params")
 
 
-def install(ref_blocks="blocks", ref_modules="modules_tro"):
-    """Patch the reference modules in place. Returns the list of (module, attribute) pairs that were replaced."""
+_saved = []      # (module object, attribute, original) of everything install() replaced
+
+
+def _swap(mod, mod_name, attr, new, done):
+    _saved.append((mod, attr, getattr(mod, attr)))
+    setattr(mod, attr, new)
+    done.append((mod_name, attr))
+
+
+def install(ref_blocks="blocks", ref_modules="modules_tro", ref_network="network_tro"):
+    """Patch the reference modules in place. Returns the list of (module, attribute) pairs that were replaced.
+    `network_tro` binds the model classes by name at import (network_tro.py:4): when it is already imported its bindings are
+    replaced too, so install() works before or after `import network_tro`."""
     done = []
     rb = sys.modules.get(ref_blocks) or importlib.import_module(ref_blocks)
     for n in BLOCK_NAMES:
         if hasattr(rb, n):
-            setattr(rb, n, getattr(_blocks, n))
-            done.append((ref_blocks, n))
+            _swap(rb, ref_blocks, n, getattr(_blocks, n), done)
     rm = sys.modules.get(ref_modules) or importlib.import_module(ref_modules)
     for n in MODULE_NAMES + BLOCK_NAMES:
         src = _modules if n in MODULE_NAMES else _blocks
         if hasattr(rm, n):
-            setattr(rm, n, getattr(src, n))
-            done.append((ref_modules, n))
+            _swap(rm, ref_modules, n, getattr(src, n), done)
     # the encoder the reference's GenModel_FC constructs by default (modules_tro.py:219)
     if hasattr(rm, "ImageEncoderResNet50"):
-        rm.ImageEncoderResNet50 = _resnet.ImageEncoderResNet50
-        done.append((ref_modules, "ImageEncoderResNet50"))
+        _swap(rm, ref_modules, "ImageEncoderResNet50", _resnet.ImageEncoderResNet50, done)
+    nt = sys.modules.get(ref_network)
+    if nt is not None:
+        for n in ("GenModel_FC", "DisModel", "WriterClaModel"):
+            if hasattr(nt, n):
+                _swap(nt, ref_network, n, getattr(_modules, n), done)
     # the stand-alone ResNet-18 (Resnet18.py), when the caller has imported it
     r18 = sys.modules.get("Resnet18")
     if r18 is not None:
         from . import Resnet18 as _r18
         for n in ("conv3x3", "BasicBlock", "ResNet18"):
-            setattr(r18, n, getattr(_r18, n))
-            done.append(("Resnet18", n))
+            _swap(r18, "Resnet18", n, getattr(_r18, n), done)
     return done
+
+
+def uninstall():
+    """Undo every install() of this process (tests share one interpreter with the oracle generators)."""
+    while _saved:
+        mod, attr, orig = _saved.pop()
+        setattr(mod, attr, orig)

@@ -46,6 +46,13 @@ def _dis_cla_trunk(n_layers, final_dim):
 
 
 def _run_trunk(cnn_f, cnn_c, x):
+    # weight gradients of these trunks keep split operands (ops.wgrad_passes): they sum B*H*W strongly cancelling terms of
+    # a mean-reduced loss, where one bf16 rounding of dY costs ~3e-4 of per-tensor cosine (scripts/precision_sweep.py)
+    with ops.wgrad_passes(3):
+        return _run_trunk_inner(cnn_f, cnn_c, x)
+
+
+def _run_trunk_inner(cnn_f, cnn_c, x):
     x = ops.input_to_internal(x)
     i, n = 0, len(cnn_f)
     while i < n:

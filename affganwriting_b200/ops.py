@@ -15,7 +15,9 @@ from . import _lib as L  # noqa: N812
 import os as _os
 _FUSE_DB = _os.environ.get("AFFGW_FUSE_DB", "1") != "0"
 _THIN = _os.environ.get("AFFGW_THIN", "1") != "0"
-_state = {"mode": "fp32", "passes": 3, "force_simt": False, "simt_wgrad": False}
+# "passes": tensor-core MMAs per product of (forward, input-gradient, weight-gradient) GEMMs: 3 = split operands, 1 = single
+_state = {"mode": "fp32", "passes": (3, 3, 3), "force_simt": False, "simt_wgrad": False}
+_MODES = {"fp32": (3, 3, 3), "bf16": (3, 1, 1), "bf16x3": (3, 3, 3), "bf16x1": (1, 1, 1)}
 _err_flag = {}
 _profile = {"records": None}
 
@@ -75,14 +77,18 @@ class _timed:
 def set_precision(mode):
     """Activations, statistics and gradients are stored in fp32 in every mode; the mode selects the convolution engine:
        'fp32'   : CUDA-core FFMA convolutions (<= 1e-4 against the CPU reference)
-       'bf16'   : tcgen05 tensor-core convolutions on split-bf16 operands, three MMAs per product
-                  (a_hi*w_hi + a_lo*w_hi + a_hi*w_lo, fp32 TMEM accumulation) - the mode that meets the 2e-2 image bar
-       'bf16x1' : tcgen05 with one bf16 MMA per product (fastest; on this network the 2^-9 operand rounding is amplified
-                  to ~2e-1 on the image at random init, see DESIGN.md "precision")."""
-    if mode not in ("fp32", "bf16", "bf16x1"):
-        raise ValueError("precision must be 'fp32', 'bf16' or 'bf16x1'")
+       'bf16'   : tcgen05 tensor-core convolutions.  FORWARD GEMMs run on split-bf16 operands, three MMAs per product
+                  (a_hi*w_hi + a_lo*w_hi + a_hi*w_lo, fp32 TMEM accumulation): forward rounding is amplified layer by layer
+                  and only the split meets the 2e-2 image bar.  BACKWARD GEMMs (input and weight gradients) are linear in
+                  dY, their rounding is not amplified, and run one MMA per product: gradient cosine stays >= 0.9997 per
+                  tensor against the fp32 reference (scripts/precision_sweep.py, DESIGN.md "precision").
+       'bf16x3' : three MMAs per product in all three GEMMs (the round-1 'bf16' mode).
+       'bf16x1' : one bf16 MMA per product everywhere (fastest; on this network the 2^-9 forward operand rounding is
+                  amplified to ~2e-1 on the image at random init)."""
+    if mode not in _MODES:
+        raise ValueError("precision must be one of " + ", ".join(repr(m) for m in _MODES))
     _state["mode"] = mode
-    _state["passes"] = 1 if mode == "bf16x1" else 3
+    _state["passes"] = _MODES[mode]
 
 
 def precision():
@@ -90,19 +96,31 @@ def precision():
 
 
 class conv_passes:
-    """Context manager: run the tensor-core convolutions issued inside with `n` (1 or 3) MMAs per product."""
+    """Context manager: the tensor-core convolutions whose FORWARD is issued inside run with the given MMAs per product
+    (1 or 3) in their forward / input-gradient / weight-gradient GEMMs; None keeps the mode's value.  The backward GEMMs of
+    a layer use what was in force at its forward.  conv_passes(n) sets all three."""
 
-    def __init__(self, n):
-        assert n in (1, 3)
-        self.n = n
+    def __init__(self, fwd=None, dgrad=None, wgrad=None):
+        if dgrad is None and wgrad is None and fwd is not None:
+            dgrad = wgrad = fwd
+        assert all(v in (None, 1, 3) for v in (fwd, dgrad, wgrad))
+        self.req = (fwd, dgrad, wgrad)
 
     def __enter__(self):
         self.prev = _state["passes"]
         if _state["mode"] != "fp32":
-            _state["passes"] = self.n
+            _state["passes"] = tuple(p if r is None else r for p, r in zip(self.prev, self.req))
 
     def __exit__(self, *a):
         _state["passes"] = self.prev
+
+
+class wgrad_passes(conv_passes):
+    """conv_passes(wgrad=n): used around the discriminator / classifier trunks, whose weight gradients sum many
+    cancelling terms (mean-reduced losses over all logits) and keep the split operands."""
+
+    def __init__(self, n):
+        super().__init__(None, None, n)
 
 
 def act_dtype():
@@ -393,7 +411,11 @@ class _Conv2d(Function):
         g = _conv_geom(x, weight, cfg)
         y_dtype = torch.float32
         use_tc = _state["mode"] != "fp32" and not _state["force_simt"]
-        passes = _state["passes"]
+        passes, pd, pw = _state["passes"]
+        need_wgrad = weight.requires_grad and torch.is_grad_enabled()
+        # the x operand planes are shared by the forward and the weight-gradient GEMM: written with a remainder plane when
+        # either needs it (a single-pass kernel reads the leading plane of a two-plane tensor)
+        px = 3 if (passes == 3 or (need_wgrad and pw == 3)) else 1
         if g["two_d"]:
             y = torch.empty((g["N"], g["Cout"]), dtype=y_dtype, device=x.device)
         else:
@@ -425,9 +447,9 @@ class _Conv2d(Function):
             if layout == L.WLAYOUT_SHIFT:
                 fx, _ = _pos_frames(d)
                 planes = _split_positions(x, fx, g["H"], g["W"], g["Cin"], g["pitch"], cfg.upsample, cfg.pad, cfg.pad_mode,
-                                          cfg.pre_act, passes)
+                                          cfg.pre_act, px)
             else:
-                planes = _split_planes(x, g["N"] * g["H"] * g["W"], g["Cin"], g["pitch"], passes, cfg.pre_act)
+                planes = _split_planes(x, g["N"] * g["H"] * g["W"], g["Cin"], g["pitch"], px, cfg.pre_act)
             wp = _pack_tc(weight, cs, False, passes, layout)
             with _timed("conv_fwd_tcgen05", flops, (tag, _kernel_name(d, 0, passes)) if _profile["records"] is not None else tag):
                 L.call("affgw_conv2d_fwd", planes.data_ptr(), wp.data_ptr(), L.ptr(b32), L.ptr(addend), y.data_ptr(),
@@ -438,7 +460,7 @@ class _Conv2d(Function):
             with _timed("conv_fwd_simt", flops, tag):
                 L.call("affgw_conv2d_fwd", x.data_ptr(), wp.data_ptr(), L.ptr(b32), L.ptr(addend), y.data_ptr(), C.byref(d),
                        L.stream())
-        ctx.cfg, ctx.g, ctx.use_tc, ctx.passes, ctx.tag = cfg, g, use_tc and not thin, passes, tag
+        ctx.cfg, ctx.g, ctx.use_tc, ctx.passes, ctx.tag = cfg, g, use_tc and not thin, (pd, pw, px), tag
         ctx.layout = layout if use_tc else 0
         ctx.thin = thin
         ctx.has_bias, ctx.has_addend = bias is not None, addend is not None
@@ -450,8 +472,12 @@ class _Conv2d(Function):
     @staticmethod
     def backward(ctx, dy):
         x, weight, y, planes = ctx.saved_tensors
-        cfg, g, passes = ctx.cfg, ctx.g, ctx.passes
+        cfg, g, (pd, pw, px) = ctx.cfg, ctx.g, ctx.passes
         need_x, need_w, need_b, need_a = ctx.needs_input_grad[:4]
+        if px != 3:
+            pw = 1                      # the saved x planes have no remainder plane
+        # dY planes feed both backward GEMMs: remainder plane when either runs split operands
+        pdy = 3 if ((need_x and pd == 3) or (need_w and pw == 3)) else 1
         dev = ctx.x_meta[1]
         dz = _dense_cl(dy, torch.float32)
         if cfg.post_act != "none":
@@ -476,12 +502,12 @@ class _Conv2d(Function):
             cs, cso = _up8(cin), _up8(cout)
             if ctx.layout == L.WLAYOUT_SHIFT:
                 # dY on the forward convolution's position frame: one split feeds both dgrad and wgrad
-                d0 = _desc(g, fwd_cfg, cin, L.BF16, L.BF16, L.BF16, L.ALGO_TC, in_pitch=cs, out_pitch=cso, passes=passes)
+                d0 = _desc(g, fwd_cfg, cin, L.BF16, L.BF16, L.BF16, L.ALGO_TC, in_pitch=cs, out_pitch=cso, passes=pdy)
                 _, fy = _pos_frames(d0)
-                dzp = _split_positions(dz, fy, g["Ho"], g["Wo"], cout, cout, 1, 0, "zero", "none", passes,
+                dzp = _split_positions(dz, fy, g["Ho"], g["Wo"], cout, cout, 1, 0, "zero", "none", pdy,
                                        colsum=db if fuse_db else None)
             else:
-                dzp = _split_planes(dz, M, cout, cout, passes)
+                dzp = _split_planes(dz, M, cout, cout, pdy)
         if ctx.thin:
             dthin = _desc(g, fwd_cfg, cin, L.F32, L.F32, L.F32, L.ALGO_SIMT)
             if need_w:
@@ -499,13 +525,13 @@ class _Conv2d(Function):
         if need_w:
             dw = torch.zeros(weight.shape, dtype=torch.float32, device=dev)
             if use_tc and not _state["simt_wgrad"]:
-                d = _desc(g, fwd_cfg, cin, L.BF16, L.BF16, L.BF16, L.ALGO_TC, in_pitch=cs, out_pitch=cso, passes=passes)
+                d = _desc(g, fwd_cfg, cin, L.BF16, L.BF16, L.BF16, L.ALGO_TC, in_pitch=cs, out_pitch=cso, passes=pw)
                 ws_bytes = L.lib().affgw_conv2d_wgrad_ws_bytes(C.byref(d))
                 if ws_bytes <= 0:
                     raise RuntimeError("conv2d_wgrad: tcgen05 kernel refused the shape: " + L.last_error())
                 wsb = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
                 with _timed("conv_wgrad_tcgen05", flops,
-                            (ctx.tag, _kernel_name(d, 2, passes)) if _profile["records"] is not None else ctx.tag):
+                            (ctx.tag, _kernel_name(d, 2, pw)) if _profile["records"] is not None else ctx.tag):
                     L.call("affgw_conv2d_wgrad", planes.data_ptr(), dzp.data_ptr(), dw.data_ptr(), wsb.data_ptr(), C.byref(d), st)
             else:
                 if x is None:
@@ -519,12 +545,12 @@ class _Conv2d(Function):
                     dx = torch.empty((g["N"], cin), dtype=torch.float32, device=dev)
                 else:
                     dx = empty_cl(g["N"], cin, g["H"], g["W"], torch.float32, dev)
-                d = _desc(g, fwd_cfg, cin, L.BF16, L.BF16, L.BF16, L.ALGO_TC, in_pitch=cs, out_pitch=cso, passes=passes,
+                d = _desc(g, fwd_cfg, cin, L.BF16, L.BF16, L.BF16, L.ALGO_TC, in_pitch=cs, out_pitch=cso, passes=pd,
                           grad_dt=L.F32)
                 layout = L.lib().affgw_conv_tc_layout(C.byref(d), 1)
                 if not layout:
                     raise RuntimeError("conv2d_dgrad: tcgen05 kernels refused the shape: " + L.last_error())
-                wt = _pack_tc(weight, cso, True, passes, layout)
+                wt = _pack_tc(weight, cso, True, pd, layout)
                 base = dx
             else:
                 if g["Cx"] != cin and not (cfg.pad_mode == "zero" and cfg.upsample == 1 and cfg.pre_act == "none"):
@@ -545,7 +571,7 @@ class _Conv2d(Function):
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev) if ws_bytes else None
             src = dzp if use_tc else dz
             with _timed("conv_dgrad_tcgen05" if use_tc else "conv_dgrad_simt", flops,
-                        (ctx.tag, _kernel_name(d, 1, passes)) if (use_tc and _profile["records"] is not None) else ctx.tag):
+                        (ctx.tag, _kernel_name(d, 1, pd)) if (use_tc and _profile["records"] is not None) else ctx.tag):
                 L.call("affgw_conv2d_dgrad", src.data_ptr(), wt.data_ptr(), L.ptr(x), base.data_ptr(), L.ptr(ws),
                        C.byref(d), st)
             if use_tc and g["Cx"] != cin:      # the weight reads only the first `cin` channels of a wider input

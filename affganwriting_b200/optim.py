@@ -9,6 +9,7 @@ is created lazily; `state_dict()` / `load_state_dict()` use torch's layout, so o
 import torch
 
 from . import _lib as L  # noqa: N812
+from .ops import weights_updated
 
 
 class Adam:
@@ -59,6 +60,9 @@ class Adam:
                 L.call("affgw_adam_step", t[0].data_ptr(), t[1].data_ptr(), t[2].data_ptr(), t[3].data_ptr(), t[4].data_ptr(),
                        t[5].data_ptr(), len(ps), grp["lr"], grp["betas"][0], grp["betas"][1], grp["eps"], int(step),
                        float(grad_scale), L.stream())
+                # the kernel writes through raw pointers, so autograd's version counters do not move: tell the packed
+                # operand cache of the convolutions (ops._WeightCache) that these parameters changed
+                weights_updated(ps)
 
     def _table(self, ps):
         key = tuple((p.data_ptr(), p.grad.data_ptr()) for p in ps)
@@ -75,6 +79,7 @@ class Adam:
                              [self.state[p]["exp_avg_sq"].data_ptr() for p in ps], sizes, offs], dtype=torch.int64).pin_memory()
         dev = host.to(ps[0].device, non_blocking=True)
         if len(self._tables) > 64:
+            torch.cuda.synchronize()        # a side stream may still be reading the tables about to be freed
             self._tables.clear()
         self._tables[key] = tuple(dev[i] for i in range(6)) + (host,)       # keep the pinned source alive until the copy has run
         return self._tables[key]

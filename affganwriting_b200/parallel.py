@@ -64,6 +64,7 @@ class CudaPacker:
         host = torch.tensor([list(ptrs), n, off], dtype=torch.int64).pin_memory()
         dev = host.to(device, non_blocking=True)
         if len(cache) > 256:
+            torch.cuda.synchronize()        # a side stream may still be reading the tables about to be freed
             cache.clear()
         cache[ptrs] = (dev[0], dev[1], dev[2], host)          # keep the pinned source alive until the copy has run
         return cache[ptrs]

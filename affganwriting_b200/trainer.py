@@ -91,8 +91,9 @@ class Trainer:
 
     def _finish(self, name):
         self.red[name].reduce()
-        self.opt[name].step()
-        ops.weights_updated(p for grp in self.opt[name].param_groups for p in grp["params"])   # fused Adam: see ops._WeightCache
+        self.opt[name].step()           # optim.Adam invalidates the packed-weight cache itself (ops.weights_updated)
+        if not isinstance(self.opt[name], Adam):
+            ops.weights_updated(p for grp in self.opt[name].param_groups for p in grp["params"])   # torch fused Adam
 
     @staticmethod
     def _pack(outs):
@@ -145,6 +146,11 @@ class Trainer:
                 torch.cuda.current_stream().wait_stream(self._side)
                 return out
             return self._capture(batch, epoch)      # the capture pass itself runs this iteration
+        # a replay computes on the captured shapes only: a batch of another shape (the reference's loaders keep the last,
+        # shorter batch of an epoch, main_run.py:123-130) runs eagerly instead - copy_ would raise, or silently broadcast a
+        # single sample over the captured batch
+        if not self._matches_capture(batch):
+            return self.train_step_eager(batch, epoch)
         for dst, src in zip(self._static_in, batch):
             if torch.is_tensor(dst) and dst.data_ptr() != src.data_ptr():
                 dst.copy_(src, non_blocking=True)
@@ -166,7 +172,29 @@ class Trainer:
             else:
                 self._finish(name)
         self.model.iter_num += 1
-        return self._pack(outs)
+        # the static loss tensors are overwritten by the next replay: hand out copies
+        return {k: v.clone() for k, v in self._pack(outs).items()}
+
+    def _matches_capture(self, batch):
+        if len(batch) != len(self._static_in):
+            return False
+        for dst, src in zip(self._static_in, batch):
+            if torch.is_tensor(dst) != torch.is_tensor(src):
+                return False
+            if torch.is_tensor(dst) and (dst.shape != src.shape or dst.dtype != src.dtype):
+                return False
+        return True
+
+    # ------------------------------------------------------------------------------------------------ safe reads
+    def state_dict(self):
+        """model.state_dict() after every queued exchange / optimiser step has been ordered before the current stream."""
+        self.join()
+        return self.model.state_dict()
+
+    def eval_step(self, batch, epoch=0):
+        """network_tro.py:140-177 (`eval` mode) on the stepped weights."""
+        self.join()
+        return self.model(batch, epoch, "eval")
 
     def _capture(self, batch, epoch):
         from . import _lib

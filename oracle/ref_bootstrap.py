@@ -3,8 +3,8 @@
 TEST INFRASTRUCTURE, NOT PRODUCT.  Nothing under affganwriting_b200/ may import this.
 It exists to (a) validate oracle/affgw_oracle.py against the real reference and
 (b) generate the golden vectors under tests/golden/ (see oracle/make_golden.py).
-/root/reference does not exist on the GPU box, so nothing on the `-m gpu` path,
-smoke() or bench.py may call into this file.
+/root/reference does not exist on the GPU box; there the staged copy under oracle/_ref/ (oracle/stage_reference.py) is
+used by `bench.py --impl reference` and by the install() test that drives the reference's ConTranModel.
 
 Shims follow SURVEY.md Appendix D; no reference file is modified or copied:
   1. builtins.open redirect of the hard-coded corpus path      (GAN_word/load_data.py:22-29)
@@ -18,7 +18,10 @@ import os
 import sys
 import types
 
-REF_ROOT = "/root/reference"
+# the reference tree where it lies (build container), else the byte-for-byte staged copy of the files this path needs
+# (oracle/stage_reference.py -> oracle/_ref/, git-ignored; it travels to the GPU box with the snapshot)
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+REF_ROOT = "/root/reference" if os.path.isdir("/root/reference/GAN_word") else _STAGED
 REF_WORD = os.path.join(REF_ROOT, "GAN_word")
 _HOME_PREFIX = "/home/woody/iwi5/iwi5333h/AFFGanWriting/"
 
@@ -77,9 +80,11 @@ def load(num_channel=50):
     finally:
         builtins.open = real_open
 
-    modules_tro.gpu = torch.device("cpu")
-    if not torch.cuda.is_available():
+    if not torch.cuda.is_available() or os.environ.get("AFFGW_REF_CPU", "0") == "1":
+        modules_tro.gpu = torch.device("cpu")
         torch.Tensor.cuda = lambda self, *a, **k: self  # modules_tro.py:308
+        import recognizer.models.encoder_vgg as _ev
+        _ev.cuda = torch.device("cpu")                   # encoder_vgg.py:25
 
     class Gen(modules_tro.GenModel_FC):
         """GenModel_FC with the VGG ImageEncoder (modules_tro.py:211 commented line)."""
@@ -95,6 +100,22 @@ def load(num_channel=50):
     ns = types.SimpleNamespace(load_data=load_data, vgg=vgg, blocks=blocks,
                                modules_tro=modules_tro, Gen=Gen)
     _state["ns"] = ns
+    return ns
+
+
+def load_network(num_channel=50):
+    """The reference's network_tro module (ConTranModel) on top of load(); RecModel is built without its pre-trained
+    VGG download (encoder_vgg.py:30, SURVEY.md §8(c) shim 6)."""
+    import importlib
+
+    import torch
+    ns = load(num_channel)
+    import recognizer.models.encoder_vgg as ev
+    ev.PRE_TRAIN_VGG = False
+    nt = sys.modules.get("network_tro") or importlib.import_module("network_tro")
+    if not torch.cuda.is_available() or os.environ.get("AFFGW_REF_CPU", "0") == "1":
+        nt.gpu = torch.device("cpu")
+    ns.network_tro = nt
     return ns
 
 

@@ -3,8 +3,9 @@ entry points, against (a) a plain torch float64 convolution of the same op on th
 kernels of this library.  This is the check that pins the UMMA shared-memory / instruction descriptors, the software
 128B swizzle, the in-gather padding / upsampling / zero-insertion index maps and the split-bf16 operand planes.
 
-Tolerances (relative to the largest reference magnitude): 3 passes (mode 'bf16') 2e-4 - the split keeps ~16 mantissa
-bits per operand; 1 pass (mode 'bf16x1') 2e-2 - one bf16 rounding per operand."""
+Tolerances (relative to the largest reference magnitude): 3 passes (mode 'bf16x3') 2e-4 - the split keeps ~16 mantissa
+bits per operand; 1 pass (mode 'bf16x1') 2e-2 - one bf16 rounding per operand; the shipping mode 'bf16' runs the forward
+GEMM with 3 passes and both backward GEMMs with 1, so y is held to the first bar and dx / dw to the second."""
 import pytest
 import torch
 import torch.nn.functional as F
@@ -38,7 +39,8 @@ CASES = [
     (5, 7, 9, 192, 72, 3, 1, 1, "replicate", 1, "none"),          # ragged everything
     (1, 64, 216, 64, 64, 3, 1, 1, "zero", 1, "none"),             # many pixel splits in wgrad
 ]
-TOL = {"bf16": 2e-4, "bf16x1": 2e-2}
+TOL = {"bf16x3": 2e-4, "bf16x1": 2e-2, "bf16": 2e-4}
+TOL_BWD = {"bf16x3": 2e-4, "bf16x1": 2e-2, "bf16": 2e-2}
 
 
 def ref_conv(x, w, b, s, p, pm, up, pre):
@@ -56,7 +58,7 @@ def rel(a, b):
     return float((a - b).abs().max() / (b.abs().max() + 1e-30))
 
 
-@pytest.fixture(params=["bf16", "bf16x1"])
+@pytest.fixture(params=["bf16x3", "bf16x1", "bf16"])
 def tc_mode(request):
     A.set_precision(request.param)
     A.force_simt(False)
@@ -83,7 +85,7 @@ def test_single_channel_stencils(case, thin_route, tc_mode):
         pytest.skip("covered by the generic cases")
     n, h, w_, ci, co, k, s, p, pm, up, pre = case
     # (one bf16 rounding per operand through a tanh on a 64-channel 7x7 sum: looser than the linear cases)
-    tol = TOL[tc_mode] if (thin_route or tc_mode == "bf16") else 6e-2
+    tol = TOL[tc_mode] if (thin_route or tc_mode == "bf16x3") else 6e-2
     g = torch.Generator(device="cuda").manual_seed(4)
     x = torch.randn(n, ci, h, w_, device="cuda", generator=g)
     wgt = torch.randn(co, ci, k, k, device="cuda", generator=g) * (2.0 / (ci * k * k)) ** 0.5
@@ -123,8 +125,8 @@ def test_tc_conv_matches_float64_torch(case, tc_mode):
     y.backward(gy)
     yr.backward(gy.double())
     e = dict(y=rel(y, yr), dx=rel(xi.grad, xr.grad), dw=rel(wi.grad, wr.grad), db=rel(bi.grad, br.grad))
-    assert all(v <= tol for v in e.values()), e
-    assert cosine(wi.grad, wr.grad) >= (0.9999999 if tc_mode == "bf16" else 0.9999)
+    assert e["y"] <= tol and e["db"] <= tol and e["dx"] <= TOL_BWD[tc_mode] and e["dw"] <= TOL_BWD[tc_mode], e
+    assert cosine(wi.grad, wr.grad) >= (0.9999999 if tc_mode == "bf16x3" else 0.9999)
 
 
 def test_tc_linear_matches_float64_torch(tc_mode):
@@ -139,17 +141,16 @@ def test_tc_linear_matches_float64_torch(tc_mode):
     gy = torch.randn(y.shape, device="cuda", generator=g)
     y.backward(gy)
     gz = gy.double() * (y > 0)          # the mask of OUR forward: a sign flip of a near-zero pre-activation is not a dgrad error
-    tol = TOL[tc_mode]
-    assert rel(y, yr) <= tol
-    assert rel(xi.grad, gz @ wgt.double()) <= tol
-    assert rel(wi.grad, gz.t() @ x.double()) <= tol
+    assert rel(y, yr) <= TOL[tc_mode]
+    assert rel(xi.grad, gz @ wgt.double()) <= TOL_BWD[tc_mode]
+    assert rel(wi.grad, gz.t() @ x.double()) <= TOL_BWD[tc_mode]
 
 
 @pytest.mark.parametrize("case", [CASES[1], CASES[4], CASES[8], CASES[14], CASES[16]])
 def test_tc_matches_cuda_core_kernels(case):
     """Same convolution through the fp32 CUDA-core kernels and through the 3-pass tcgen05 kernels of this library."""
     n, h, w_, ci, co, k, s, p, pm, up, pre = case
-    A.set_precision("bf16")
+    A.set_precision("bf16x3")
     try:
         g = torch.Generator(device="cuda").manual_seed(3)
         x = ops.to_internal(torch.randn(n, ci, h, w_, device="cuda", generator=g))
@@ -171,7 +172,7 @@ def test_tc_matches_cuda_core_kernels(case):
 
 def test_tc_wgrad_matches_cuda_core_wgrad():
     """MN-major tcgen05 weight-gradient kernel vs the CUDA-core wgrad with forward / dgrad kept on tensor cores."""
-    A.set_precision("bf16")
+    A.set_precision("bf16x3")
     try:
         for (n, h, w_, ci, co, k, s, p, pm, up, pre) in (CASES[0], CASES[4], CASES[17]):
             g = torch.Generator(device="cuda").manual_seed(11)
@@ -196,7 +197,7 @@ def test_fp32_mode_never_uses_tensor_cores_and_bf16_always_does():
     from affganwriting_b200 import ops as O_
     x = ops.to_internal(torch.randn(2, 64, 8, 27, device="cuda")).requires_grad_()
     w = torch.randn(64, 64, 3, 3, device="cuda", requires_grad=True)
-    for mode, want in (("fp32", "simt"), ("bf16", "tcgen05"), ("bf16x1", "tcgen05")):
+    for mode, want in (("fp32", "simt"), ("bf16", "tcgen05"), ("bf16x3", "tcgen05"), ("bf16x1", "tcgen05")):
         A.set_precision(mode)
         O_.start_kernel_timing()
         ops.conv2d(x, w, None, pad=1).sum().backward()
