@@ -61,7 +61,7 @@ def install(ref_blocks="blocks", ref_modules="modules_tro", ref_network="network
 
 
 def uninstall():
-    """Undo every install() of this process (tests share one interpreter with the oracle generators)."""
+    """Undo every install() of this process (tests share one interpreter with the golden-vector generators)."""
     while _saved:
         mod, attr, orig = _saved.pop()
         setattr(mod, attr, orig)
