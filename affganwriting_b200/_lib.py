@@ -164,5 +164,17 @@ def require_cuda(*tensors):
             raise RuntimeError("affganwriting_b200 runs on CUDA tensors only (there is no CPU fallback)")
 
 
-def call(name, *args):
+PROFILE = None      # list of (entry point, start event, end event, algorithmic bytes) while bench.py's instrumented pass runs
+
+
+def call(name, *args, nbytes=0):
+    """Invoke an entry point; raises on a non-zero return.  `nbytes` = the ALGORITHMIC HBM traffic of the call (every tensor
+    read once + written once), recorded together with CUDA events on the launching stream when profiling is switched on."""
+    if PROFILE is not None and nbytes:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        check(getattr(lib(), name)(*args), name)
+        e1.record()
+        PROFILE.append((name, e0, e1, int(nbytes)))
+        return
     check(getattr(lib(), name)(*args), name)

@@ -23,15 +23,33 @@ _profile = {"records": None}
 
 
 def start_kernel_timing():
-    """Begin recording (name, start_event, end_event, algorithmic_flops) for every convolution launch; the events sit
-    on the launching (current) stream.  Used by bench.py for the roofline numbers; off by default."""
+    """Begin recording (name, start_event, end_event, algorithmic_flops) for every convolution launch and (entry point, events,
+    algorithmic bytes) for every streaming kernel; the events sit on the launching (current) stream.  Used by bench.py for the
+    roofline numbers; off by default."""
     _profile["records"] = []
+    L.PROFILE = []
+
+
+def stop_stream_timing():
+    """-> {entry point: {"launches", "ms", "bytes"}} of the streaming (HBM-bound) kernels since start_kernel_timing();
+    call before stop_kernel_timing() (which synchronises) or after - it synchronises itself."""
+    recs, L.PROFILE = L.PROFILE or [], None
+    torch.cuda.synchronize()
+    out = {}
+    for name, e0, e1, nb in recs:
+        d = out.setdefault(name, {"launches": 0, "ms": 0.0, "bytes": 0})
+        d["launches"] += 1
+        d["ms"] += e0.elapsed_time(e1)
+        d["bytes"] += nb
+    return out
 
 
 def stop_kernel_timing(by_shape=False, by_kernel=False):
     """-> {name: {"launches", "ms", "flops"}} ; synchronises the device once.  by_shape=True keys on (name, shape tag),
     by_kernel=True on the CUDA kernel function the call ran (e.g. conv_shift_tcgen05_kernel<256, 3>)."""
     recs, _profile["records"] = _profile["records"] or [], None
+    if L.PROFILE is not None and not L.PROFILE:
+        L.PROFILE = None
     torch.cuda.synchronize()
     out = {}
     for name, tag, e0, e1, fl in recs:
@@ -143,6 +161,10 @@ def force_simt(flag=True):
 def force_simt_wgrad(flag=True):
     """Keep forward / dgrad on tcgen05 but compute weight gradients on CUDA cores (cross-check of the MN-major path)."""
     _state["simt_wgrad"] = bool(flag)
+
+
+def _nb(t):
+    return 0 if t is None else t.numel() * t.element_size()
 
 
 def _err_tensor(device):
@@ -344,7 +366,7 @@ def _split_planes(x, rows, c, pitch, passes, pre_act="none"):
     cs = _up8(c)
     planes = torch.empty((2 if passes == 3 else 1, rows, cs), dtype=torch.bfloat16, device=x.device)
     L.call("affgw_split_planes", x.data_ptr(), L.dt(x), planes.data_ptr(), rows, c, pitch, cs, passes, L.ACT[pre_act],
-           L.stream())
+           L.stream(), nbytes=rows * c * x.element_size() + _nb(planes))
     return planes
 
 
@@ -361,7 +383,8 @@ def _split_positions(src, frame, hs, ws, c, pitch, up, origin, pad_mode, pre_act
         raise RuntimeError("affgw_position_planes_bytes: bad frame")
     planes = torch.empty(nbytes // 2, dtype=torch.bfloat16, device=src.device)
     L.call("affgw_split_positions", src.data_ptr(), L.dt(src), planes.data_ptr(), C.byref(frame), hs, ws, c, pitch, up, origin,
-           origin, L.PAD[pad_mode], L.ACT[pre_act], passes, L.ptr(colsum), L.stream())
+           origin, L.PAD[pad_mode], L.ACT[pre_act], passes, L.ptr(colsum), L.stream(),
+           nbytes=frame.N * hs * ws * c * src.element_size() + _nb(planes))
     return planes
 
 
@@ -483,7 +506,7 @@ class _Conv2d(Function):
         if cfg.post_act != "none":
             t = torch.empty_like(dz)
             L.call("affgw_act_bwd", dz.data_ptr(), y.data_ptr(), t.data_ptr(), L.dt(dz), dz.numel(), L.ACT[cfg.post_act],
-                   L.stream())
+                   L.stream(), nbytes=3 * _nb(dz))
             dz = t
         st = L.stream()
         M = g["N"] * g["Ho"] * g["Wo"]
@@ -607,7 +630,7 @@ def _stats(x, G, P, Cc, eps, unbiased, want_var=False):
     rstd = torch.empty(G * Cc, dtype=torch.float32, device=dev)
     var = torch.empty(G * Cc, dtype=torch.float32, device=dev) if want_var else None
     L.call("affgw_norm_stats", x.data_ptr(), L.dt(x), ws.data_ptr(), mean.data_ptr(), rstd.data_ptr(), L.ptr(var), G, P, Cc,
-           float(eps), int(unbiased), L.stream())
+           float(eps), int(unbiased), L.stream(), nbytes=_nb(x))
     return mean, rstd, var
 
 
@@ -634,7 +657,7 @@ class _InstanceNorm(Function):
             residual = _dense_cl(residual, x.dtype)
         y = torch.empty_like(x)
         L.call("affgw_norm_apply", x.data_ptr(), L.dt(x), mean.data_ptr(), rstd.data_ptr(), L.ptr(gamma), L.ptr(beta),
-               L.ptr(residual), y.data_ptr(), G, P, Cc, L.ACT[act], 1, L.stream())
+               L.ptr(residual), y.data_ptr(), G, P, Cc, L.ACT[act], 1, L.stream(), nbytes=_nb(x) + _nb(y) + _nb(residual))
         ctx.act, ctx.unbiased, ctx.affine, ctx.has_res = act, unbiased, gamma is not None, residual is not None
         ctx.save_for_backward(x, mean, rstd, gamma, beta)
         return y
@@ -649,7 +672,7 @@ class _InstanceNorm(Function):
         dx = torch.empty_like(x)
         L.call("affgw_norm_bwd", dy.data_ptr(), x.data_ptr(), L.dt(x), mean.data_ptr(), rstd.data_ptr(), L.ptr(gamma),
                L.ptr(beta), s1.data_ptr(), s2.data_ptr(), dx.data_ptr(), G, P, Cc, L.ACT[ctx.act], 1, 1, int(ctx.unbiased),
-               L.stream())
+               L.stream(), nbytes=_nb(dy) + _nb(x) + _nb(dx))
         return dx, (s2 if ctx.affine else None), (s1 if ctx.affine else None), (dy if ctx.has_res else None), None, None, None
 
 
@@ -681,7 +704,7 @@ class _BatchNorm(Function):
         w32, b32 = weight.detach(), bias.detach()
         y = torch.empty_like(x)
         L.call("affgw_norm_apply", x.data_ptr(), L.dt(x), mean.data_ptr(), rstd.data_ptr(), w32.data_ptr(), b32.data_ptr(),
-               None, y.data_ptr(), G, P, Cc, L.ACT[act], 0, L.stream())
+               None, y.data_ptr(), G, P, Cc, L.ACT[act], 0, L.stream(), nbytes=_nb(x) + _nb(y))
         ctx.act, ctx.training = act, training
         ctx.save_for_backward(x, mean, rstd, weight, bias)
         return y
@@ -696,7 +719,7 @@ class _BatchNorm(Function):
         dx = torch.empty_like(x)
         L.call("affgw_norm_bwd", dy.data_ptr(), x.data_ptr(), L.dt(x), mean.data_ptr(), rstd.data_ptr(),
                weight.detach().data_ptr(), bias.detach().data_ptr(), s1.data_ptr(), s2.data_ptr(), dx.data_ptr(), G, P, Cc,
-               L.ACT[ctx.act], 0, int(ctx.training), 0, L.stream())
+               L.ACT[ctx.act], 0, int(ctx.training), 0, L.stream(), nbytes=_nb(dy) + _nb(x) + _nb(dx))
         return dx, s2, s1, None, None, None, None, None
 
 
@@ -714,7 +737,7 @@ class _MaxPool2(Function):
         x = _dense_cl(x)
         n, c, h, w = x.shape
         y = empty_cl(n, c, h // 2, w // 2, x.dtype, x.device)
-        L.call("affgw_maxpool2_fwd", x.data_ptr(), y.data_ptr(), L.dt(x), n, h, w, c, L.stream())
+        L.call("affgw_maxpool2_fwd", x.data_ptr(), y.data_ptr(), L.dt(x), n, h, w, c, L.stream(), nbytes=_nb(x) + _nb(y))
         ctx.save_for_backward(x)
         return y
 
@@ -724,7 +747,8 @@ class _MaxPool2(Function):
         n, c, h, w = x.shape
         dy = _dense_cl(dy, x.dtype)
         dx = torch.empty_like(x)
-        L.call("affgw_maxpool2_bwd", dy.data_ptr(), x.data_ptr(), dx.data_ptr(), L.dt(x), n, h, w, c, L.stream())
+        L.call("affgw_maxpool2_bwd", dy.data_ptr(), x.data_ptr(), dx.data_ptr(), L.dt(x), n, h, w, c, L.stream(),
+               nbytes=_nb(dy) + _nb(x) + _nb(dx))
         return dx
 
 
@@ -822,7 +846,7 @@ class _AvgPool3s2Reflect(Function):
         x = _dense_cl(x)
         n, c, h, w = x.shape
         y = empty_cl(n, c, (h - 1) // 2 + 1, (w - 1) // 2 + 1, x.dtype, x.device)
-        L.call("affgw_avgpool3s2_fwd", x.data_ptr(), y.data_ptr(), L.dt(x), n, h, w, c, L.stream())
+        L.call("affgw_avgpool3s2_fwd", x.data_ptr(), y.data_ptr(), L.dt(x), n, h, w, c, L.stream(), nbytes=_nb(x) + _nb(y))
         ctx.shape = (n, c, h, w)
         return y
 
@@ -831,7 +855,7 @@ class _AvgPool3s2Reflect(Function):
         n, c, h, w = ctx.shape
         dy = _dense_cl(dy)
         dx = empty_cl(n, c, h, w, dy.dtype, dy.device)
-        L.call("affgw_avgpool3s2_bwd", dy.data_ptr(), dx.data_ptr(), L.dt(dy), n, h, w, c, L.stream())
+        L.call("affgw_avgpool3s2_bwd", dy.data_ptr(), dx.data_ptr(), L.dt(dy), n, h, w, c, L.stream(), nbytes=_nb(dy) + _nb(dx))
         return dx
 
 

@@ -59,7 +59,7 @@ class Adam:
                 t = self._table(ps)
                 L.call("affgw_adam_step", t[0].data_ptr(), t[1].data_ptr(), t[2].data_ptr(), t[3].data_ptr(), t[4].data_ptr(),
                        t[5].data_ptr(), len(ps), grp["lr"], grp["betas"][0], grp["betas"][1], grp["eps"], int(step),
-                       float(grad_scale), L.stream())
+                       float(grad_scale), L.stream(), nbytes=28 * sum(p.numel() for p in ps))
                 # the kernel writes through raw pointers, so autograd's version counters do not move: tell the packed
                 # operand cache of the convolutions (ops._WeightCache) that these parameters changed
                 weights_updated(ps)

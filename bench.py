@@ -16,6 +16,11 @@ import sys
 import threading
 import time
 
+if "reference" in sys.argv[1:] and "--impl" in sys.argv[1:]:
+    # the reference arm is a CPU measurement: hide the GPUs before torch initialises CUDA, so that nothing in the reference
+    # (nn.DataParallel around the VGG slices, modules_tro.py:341-346; `.cuda()` at :308) reaches for a device
+    os.environ["CUDA_VISIBLE_DEVICES"] = ""
+
 import numpy as np
 import torch
 
@@ -341,6 +346,7 @@ def main():
     trainer.train_step_eager(resident)                   # eager: events cannot sit inside a graph replay
     ops.start_kernel_timing()
     timed(lambda: trainer.train_step_eager(resident), 2)
+    streams = ops.stop_stream_timing()
     kern = ops.stop_kernel_timing(by_kernel=True)
     instr_steps = 2
 
@@ -353,11 +359,13 @@ def main():
     trainer.join()                                       # the last generator step may still be on the side stream
     gen = trainer.model.gen
     from affganwriting_b200.inference import GraphedGenerator
+    gen.eval()                                           # the reference generates under model.eval() (tt.test_single_writer.4_scenarios.py:146)
     gen_fn = gen if args.no_graph else GraphedGenerator(gen)
     with torch.no_grad():
         for _ in range(4):
             gen_fn(resident[3], resident[7])
         ms_gen = timed(lambda: gen_fn(resident[3], resident[7]), 10) / 10
+    gen.train()
     gen_img_s = world * B / (ms_gen / 1e3)
 
     if rank != 0:
@@ -372,25 +380,46 @@ def main():
         pass
     tf_peak = peaks.get("bf16_tflops_sustained", 1400.0)
     peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if peaks else "fallback 1.4 PF sustained"
+    hbm_peak = peaks.get("hbm_gbs", 6500.0)
     kernels = {}
+
+    def mma_passes(name):                                # conv_*_kernel<BN, NPASS, ...>: tensor-core MMAs issued per product
+        try:
+            return int(name.split("<")[1].split(",")[1].strip(" >"))
+        except Exception:
+            return 1
     for name, d in kern.items():
         tf = d["flops"] / (d["ms"] * 1e-3) / 1e12 if d["ms"] > 0 else 0.0
         kernels[name] = {"launches_per_step": d["launches"] / instr_steps, "ms_per_step": d["ms"] / instr_steps,
-                         "share_of_step": d["ms"] / instr_steps / ms_step, "tflops": tf, "frac_of_peak": tf / tf_peak}
-    dominant = max(kernels, key=lambda k: kernels[k]["ms_per_step"]) if kernels else None
+                         "share_of_step": d["ms"] / instr_steps / ms_step, "bound": "tensor", "tflops": tf,
+                         "frac_of_peak": tf / tf_peak, "mma_passes": mma_passes(name)}
+    # streaming kernels (normalisation, operand split, pools, optimiser): algorithmic bytes (each tensor read once + written
+    # once) over their CUDA-event time, against the measured HBM copy bandwidth
+    for name, d in streams.items():
+        gbs = d["bytes"] / (d["ms"] * 1e-3) / 1e9 if d["ms"] > 0 else 0.0
+        kernels[name] = {"launches_per_step": d["launches"] / instr_steps, "ms_per_step": d["ms"] / instr_steps,
+                         "share_of_step": d["ms"] / instr_steps / ms_step, "bound": "hbm", "gbs": gbs,
+                         "frac_of_peak": gbs / hbm_peak, "algorithmic_bytes_per_step": d["bytes"] / instr_steps}
+    tensor_kernels = {k: v for k, v in kernels.items() if v["bound"] == "tensor"}
+    dominant = max(tensor_kernels, key=lambda k: tensor_kernels[k]["ms_per_step"]) if tensor_kernels else None
     roofline = None
     if dominant:
         k = kernels[dominant]
         roofline = {"kernel": dominant, "bound": "tensor", "achieved": k["tflops"], "peak": tf_peak, "unit": "TFLOP/s",
                     "frac": k["frac_of_peak"], "traffic": None, "peak_source": peak_src,
                     "avg_launch_ms": k["ms_per_step"] / max(k["launches_per_step"], 1e-9),
-                    "share_of_step": k["share_of_step"],
-                    "executed_tflops": 3.0 * k["tflops"], "executed_frac": 3.0 * k["frac_of_peak"],
+                    "share_of_step": k["share_of_step"], "mma_passes": k["mma_passes"],
+                    "executed_tflops": k["mma_passes"] * k["tflops"], "executed_frac": k["mma_passes"] * k["frac_of_peak"],
                     "note": "achieved = algorithmic FLOPs (direct-convolution MAC x 2) of every launch of this kernel function in "
-                            "one eager step / their summed CUDA-event time on the launching stream.  The bf16 mode issues 3 "
-                            "tensor-core MMAs per product (split-bf16, DESIGN.md section 3): executed_* count those, so frac "
-                            "is capped at 1/3 and executed_frac is the tensor-pipe utilisation against the measured cuBLAS "
-                            "peak.  traffic: profiles/ holds the ncu DRAM bytes of this kernel on one layer"}
+                            "one eager step / their summed CUDA-event time on the launching stream.  Forward GEMMs issue 3 "
+                            "tensor-core MMAs per product (split-bf16 operands, DESIGN.md section 3), backward GEMMs 1: "
+                            "executed_* = mma_passes x the algorithmic figure = tensor-pipe work against the measured cuBLAS "
+                            "peak (a 3-pass kernel's frac is capped at 1/3).  traffic: ncu DRAM bytes of this kernel on one layer"}
+    hbm_ms = sum(v["ms_per_step"] for v in kernels.values() if v["bound"] == "hbm")
+    hbm_bytes = sum(v["algorithmic_bytes_per_step"] for v in kernels.values() if v["bound"] == "hbm")
+    hbm_summary = {"ms_per_step": hbm_ms, "share_of_step": hbm_ms / ms_step, "algorithmic_gb_per_step": hbm_bytes / 1e9,
+                   "achieved_gbs": hbm_bytes / max(hbm_ms, 1e-9) / 1e6, "peak_gbs": hbm_peak,
+                   "frac": hbm_bytes / max(hbm_ms, 1e-9) / 1e6 / hbm_peak}
 
     try:        # DRAM bytes of the dominant kernel from the committed ncu --set full capture (one layer, see profiles/README.md)
         tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get(dominant)
@@ -403,23 +432,20 @@ def main():
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
-        threads = os.cpu_count() or 1
-        from oracle import ref_bootstrap as rb
-        sb = REFERENCE_SAMPLE_BATCH
-        if rb.available():
-            kind, ts = "reference", reference_modules_steps(sb, 3, 1, threads)
-            sec = sum(ts) / len(ts)
-        else:
-            kind, sec = "port", cpu_reference_steps(sb, 3, 1, threads)
-        cpu_baseline = {"value": (sb / sec) / BATCH_PER_GPU, "unit": "steps/s", "cores": threads, "kind": kind,
-                        "sample": f"3 timed iterations (after 1 warm-up) of the {'reference modules' if kind == 'reference' else 'CPU oracle port'} "
-                                  f"on {sb} of the {BATCH_PER_GPU} samples ({sec:.2f} s each, fp32, {threads} threads); "
-                                  f"steps/s = ({sb}/{BATCH_PER_GPU}) / seconds"}
+        # the reference arm of this same file in a child process with the GPUs hidden (3 timed sample steps after 1 warm-up)
+        try:
+            out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "3", "--warmup", "1"],
+                                 capture_output=True, text=True, timeout=900, cwd=ROOT).stdout
+            cpu_baseline = json.loads([ln for ln in out.splitlines() if ln.startswith("{")][-1])["cpu_baseline"]
+        except Exception as e:                      # reported, never fatal for the GPU measurement
+            cpu_baseline = {"value": None, "unit": "steps/s", "cores": os.cpu_count(), "kind": "unavailable", "sample": repr(e)[:200]}
 
     h2d = batch_bytes(host)
     line = {
         "metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "dtype_detail": "bf16 tcgen05 MMAs with fp32 TMEM accumulation (forward: split-bf16 operands, 3 MMAs per product; backward: 1); "
+                        "activations, statistics, gradients and parameters are stored in fp32",
         "data": "synthetic (seeded uint8 grey-level canvases normalised on the GPU like load_data.py:152-166; random-init weights)",
         "config": {"workload": WORKLOAD if args.encoder == "vgg" else WORKLOAD.replace(
                        "configs[1]", "configs[2] (%s style encoder)" % args.encoder),
@@ -435,6 +461,7 @@ def main():
         "gpu_launches": launches,
         "clocks": clocks.summary(),
         "roofline": roofline,
+        "hbm_kernels": hbm_summary,
         "kernels": kernels,
         "step_tflops": None if args.encoder != "vgg" else {
             "algorithmic_tflop_per_step": STEP_GFLOP_PER_SAMPLE * B / 1e3,

@@ -197,4 +197,5 @@ def test_conv_anisotropic_stride(stride, mode):
     gy = torch.randn_like(yr)
     gx, gw = torch.autograd.grad((y.double() * gy).sum(), (x, w))
     gxr, gwr = torch.autograd.grad((yr * gy).sum(), (x, w))
-    assert rel_err(gx, gxr.float()) <= tol and rel_err(gw, gwr.float()) <= tol
+    btol = 2e-2 if mode == "bf16" else tol          # 'bf16': backward GEMMs run one MMA per product
+    assert rel_err(gx, gxr.float()) <= btol and rel_err(gw, gwr.float()) <= btol
