@@ -109,7 +109,12 @@ class LinearBlock(nn.Module):
                 out = ops.batch_norm(out, self.norm)
                 return _standalone_act(out, act)
             return ops.batch_norm(out, self.norm, act=act)
-        raise NotImplementedError("LinearBlock(norm='in') is unused by the reference (blocks.py:78) and not accelerated")
+        # nn.InstanceNorm1d on a 2-D [B, F] input (blocks.py:78-79,99-100): torch reads it as ONE unbatched (C = B, L = F)
+        # sample, i.e. every row is normalised over its F features (biased variance, eps 1e-5, no affine, no running stats)
+        b, f = out.shape
+        y = ops.instance_norm(out.reshape(b, 1, f, 1), act="none" if act == "tanh" else act, eps=self.norm.eps)
+        y = y.reshape(b, f)
+        return _standalone_act(y, act) if act == "tanh" else y
 
 
 def _standalone_act(x, act):

@@ -94,6 +94,10 @@ int bce_logits_fwd(const void* x, int dt, float target, float* loss, long long n
 int bce_logits_bwd(const void* x, int dt, float target, const float* gout, void* dx, long long n, cudaStream_t st);
 int softmax_ce_fwd(const void* x, int dt, const long long* y, float* loss, int B, int C, int* err, cudaStream_t st);
 int softmax_ce_bwd(const void* x, int dt, const long long* y, const float* gout, void* dx, int B, int C, cudaStream_t st);
+int label_smooth_kl_fwd(const float* x, const long long* y, float* loss, int rows, int V, int pad, float smoothing, int* err,
+                        cudaStream_t st);
+int label_smooth_kl_bwd(const float* x, const long long* y, const float* gout, float* dx, int rows, int V, int pad, float smoothing,
+                        cudaStream_t st);
 int nchw_to_nhwc(const float* x, void* y, int dt, int N, int C, long long HW, int cpad, cudaStream_t st);
 int u8_to_image(const unsigned char* src, float* dst, long long n, cudaStream_t st);
 int nhwc_to_nchw(const void* x, float* y, int dt, int N, int C, long long HW, int cpad, cudaStream_t st);
@@ -663,6 +667,17 @@ int affgw_softmax_ce_fwd(const void* x, int dt, const long long* y, float* loss,
 int affgw_softmax_ce_bwd(const void* x, int dt, const long long* y, const float* gout, void* dx, int B, int C, void* s) {
     REQ(x && y && gout && dx && dt_ok(dt) && B > 0 && C > 0, "softmax_ce_bwd");
     return softmax_ce_bwd(x, dt, y, gout, dx, B, C, S(s));
+}
+int affgw_label_smooth_kl_fwd(const float* x, const long long* y, float* loss, int rows, int V, int pad_idx, float smoothing,
+                              int* err, void* s) {
+    REQ(x && y && loss && err && rows > 0 && V > 2 && pad_idx >= 0 && pad_idx < V && smoothing >= 0.f && smoothing < 1.f,
+        "label_smooth_kl_fwd");
+    return label_smooth_kl_fwd(x, y, loss, rows, V, pad_idx, smoothing, err, S(s));
+}
+int affgw_label_smooth_kl_bwd(const float* x, const long long* y, const float* gout, float* dx, int rows, int V, int pad_idx,
+                              float smoothing, void* s) {
+    REQ(x && y && gout && dx && rows > 0 && V > 2 && pad_idx >= 0 && pad_idx < V, "label_smooth_kl_bwd");
+    return label_smooth_kl_bwd(x, y, gout, dx, rows, V, pad_idx, smoothing, S(s));
 }
 int affgw_u8_to_image(const unsigned char* src, float* dst, long long n, void* s) {
     REQ(src && dst && n > 0, "u8_to_image");

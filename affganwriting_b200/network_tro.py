@@ -1,14 +1,22 @@
-"""Training / evaluation step composition (reference GAN_word/network_tro.py:17-177) for the sub-networks on the
-accelerated path: generator, discriminator, writer classifier.  The recogniser (`rec_update`, the l_rec term) is a
-GRU seq2seq with host-side beam search and is out of scope; an optional `rec` module supplied
-by the caller is used unchanged.
+"""Training / evaluation step composition (reference GAN_word/network_tro.py:17-177): all four update modes and `eval`.
+
+Generator, discriminator and writer classifier are this package's classes.  The recogniser is a constructor argument
+(`rec=`): any module with the reference RecModel's call shape `rec(img [B,1,H,W], label [B,T], img_width=...) -> logits
+[B, T-1, vocab]` (modules_tro.py:631-636) - the reference's own RecModel drops in unchanged (tests/test_gpu_rec_step.py).  With
+a recogniser the step is the reference's complete objective: `rec_update` (network_tro.py:39-48) and
+l_total = w_dis l_dis + w_cla l_cla + w_l1 l_l1 + w_rec l_rec in `gen_update` (:57-103).  With rec=None the l_rec term is
+absent (BASELINE.json configs[1] names the three convolutional models only) and a warning says so once.
 
 Loss weights follow network_tro.py:10-13 (w_dis = w_cla = w_rec = 1, w_l1 = 0).
 """
+import warnings
+
+import numpy as np
 import torch
 import torch.nn as nn
 
-from .load_data import OUTPUT_MAX_LEN
+from .load_data import IMG_WIDTH, OUTPUT_MAX_LEN, vocab_size
+from .loss_tro import crit, log_softmax, recon_criterion
 from .modules_tro import DisModel, GenModel_FC, WriterClaModel
 
 w_dis = 1.
@@ -24,8 +32,11 @@ class ConTranModel(nn.Module):
         self.gen = GenModel_FC(OUTPUT_MAX_LEN, encoder=encoder).to(dev)
         self.cla = WriterClaModel(num_writers).to(dev)
         self.dis = DisModel().to(dev)
-        if rec is not None:
-            self.rec = rec
+        self.rec = rec.to(dev) if rec is not None else None
+        if rec is None:
+            warnings.warn("ConTranModel built without a recogniser: gen_update optimises w_dis*l_dis + w_cla*l_cla only and "
+                          "rec_update is unavailable (pass rec=<RecModel> for the reference's full objective, network_tro.py:88-101)",
+                          stacklevel=2)
         self.iter_num = 0
         self.show_iter_num = show_iter_num
         self.oov = oov
@@ -52,10 +63,32 @@ class ConTranModel(nn.Module):
     def _pair(a, b):
         return torch.cat([a, b], dim=0)
 
+    def _recognise(self, img, label):
+        """RecModel call of network_tro.py:43,88-89: every image spans the full width."""
+        widths = torch.from_numpy(np.array([IMG_WIDTH] * img.shape[0]))
+        return self.rec(img, label, img_width=widths)
+
+    @staticmethod
+    def _rec_loss(pred, label):
+        target = label[:, 1:]                                     # remove <GO>  (network_tro.py:44,90-91)
+        return crit(log_softmax(pred.reshape(-1, vocab_size)), target.reshape(-1)), target
+
     def forward(self, train_data_list, epoch, mode, cer_func=None):
         tr_domain, tr_wid, tr_idx, tr_img, tr_img_width, tr_label, img_xt, label_xt, label_xt_swap = train_data_list
         tr_wid, tr_img = self._to(tr_wid), self._to(tr_img)
         img_xt, label_xt, label_xt_swap = self._to(img_xt), self._to(label_xt), self._to(label_xt_swap)
+
+        if mode == "rec_update":                                  # network_tro.py:39-48
+            if self.rec is None:
+                raise ValueError("rec_update needs a recogniser: ConTranModel(..., rec=<RecModel>)")
+            img = tr_img[:, 0:1, :, :]
+            lab = self._to(tr_label)[:, 0, :]
+            pred = self._recognise(img, lab)
+            l_rec_tr, target = self._rec_loss(pred, lab)
+            if cer_func is not None:
+                cer_func.add(pred, target)
+            l_rec_tr.backward()
+            return l_rec_tr
 
         if mode == "cla_update":                                  # network_tro.py:50-55
             # the reference marks this slice requires_grad_ (network_tro.py:51) but never reads its gradient: the input
@@ -71,11 +104,20 @@ class ConTranModel(nn.Module):
             both, wid2 = self._pair(xg, xg_swap), self._pair(tr_wid, tr_wid)
             l_dis = self.dis.calc_gen_loss(both)
             l_cla = self.cla(both, wid2)
-            l_l1 = torch.zeros((), device=xg.device)
-            l_rec = torch.zeros((), device=xg.device)
-            if getattr(self, "rec", None) is not None and cer_func is not None:
-                raise NotImplementedError("recogniser term: pass rec=None (SURVEY.md §8(f).1)")
-            l_total = w_dis * l_dis + w_cla * l_cla
+            l_l1 = torch.zeros((), device=xg.device) if self.oov else recon_criterion(xg, img_xt)   # network_tro.py:82-85
+            if self.rec is not None:                              # network_tro.py:87-97
+                pred_xt = self._recognise(xg, label_xt)
+                pred_xt_swap = self._recognise(xg_swap, label_xt_swap)
+                l_rec_ori, tgt = self._rec_loss(pred_xt, label_xt)
+                l_rec_swap, tgt_swap = self._rec_loss(pred_xt_swap, label_xt_swap)
+                if cer_func is not None:
+                    cer_func[0].add(pred_xt, tgt)
+                    cer_func[1].add(pred_xt_swap, tgt_swap)
+                l_rec = (l_rec_ori + l_rec_swap) / 2.
+                l_total = w_dis * l_dis + w_cla * l_cla + w_l1 * l_l1 + w_rec * l_rec
+            else:
+                l_rec = torch.zeros((), device=xg.device)
+                l_total = w_dis * l_dis + w_cla * l_cla + w_l1 * l_l1
             l_total.backward()
             return l_total, l_dis, l_cla, l_l1, l_rec
 
@@ -91,13 +133,23 @@ class ConTranModel(nn.Module):
             l_fake.backward()
             return l_real + l_fake
 
-        if mode == "eval":                                        # network_tro.py:140-177 without rec / image dump
+        if mode == "eval":                                        # network_tro.py:140-177 (the PNG dump of :151 is the caller's)
             with torch.no_grad():
                 xg, xg_swap = self._generate_pair(tr_img, label_xt, label_xt_swap)
                 self.iter_num += 1
                 both = self._pair(xg, xg_swap)
                 l_dis = self.dis.calc_gen_loss(both)
+                l_rec = torch.zeros((), device=xg.device)
+                if self.rec is not None:
+                    pred_xt = self._recognise(xg, label_xt)
+                    pred_xt_swap = self._recognise(xg_swap, label_xt_swap)
+                    l_a, tgt = self._rec_loss(pred_xt, label_xt)
+                    l_b, tgt_swap = self._rec_loss(pred_xt_swap, label_xt_swap)
+                    if cer_func is not None:
+                        cer_func[0].add(pred_xt, tgt)
+                        cer_func[1].add(pred_xt_swap, tgt_swap)
+                    l_rec = (l_a + l_b) / 2.
                 l_cla = self.cla(both, self._pair(tr_wid, tr_wid))
-            return l_dis, l_cla, torch.zeros((), device=xg.device)
+            return l_dis, l_cla, l_rec
 
-        raise ValueError(f"unsupported mode {mode!r} (rec_update needs the out-of-scope recogniser)")
+        raise ValueError(f"unsupported mode {mode!r}")

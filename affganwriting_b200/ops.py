@@ -1064,3 +1064,36 @@ class _SoftmaxCe(Function):
 
 def cross_entropy(x, y):
     return _SoftmaxCe.apply(x, y)
+
+
+class _LabelSmoothKl(Function):
+    @staticmethod
+    def forward(ctx, x, y, pad_idx, smoothing):
+        L.require_cuda(x, y)
+        x = x.float().contiguous()
+        if y.dtype != torch.int64:
+            raise RuntimeError("label_smoothing_kl: targets must be int64")
+        y = y.contiguous()
+        rows, v = x.shape
+        loss = torch.empty((), dtype=torch.float32, device=x.device)
+        L.call("affgw_label_smooth_kl_fwd", x.data_ptr(), y.data_ptr(), loss.data_ptr(), rows, v, int(pad_idx), float(smoothing),
+               _err_tensor(x.device).data_ptr(), L.stream())
+        ctx.save_for_backward(x, y)
+        ctx.cfg = (int(pad_idx), float(smoothing))
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        x, y = ctx.saved_tensors
+        rows, v = x.shape
+        g = g.float().contiguous()
+        dx = torch.empty_like(x)
+        L.call("affgw_label_smooth_kl_bwd", x.data_ptr(), y.data_ptr(), g.data_ptr(), dx.data_ptr(), rows, v, ctx.cfg[0],
+               ctx.cfg[1], L.stream())
+        return dx, None, None, None
+
+
+def label_smoothing_kl(x, y, pad_idx, smoothing):
+    """crit(log_softmax(x), y) of the reference (loss_tro.py:8-35, network_tro.py:44-45): KL(sum) against the smoothed
+    one-hot; x [rows, V] logits, y [rows] int64."""
+    return _LabelSmoothKl.apply(x, y, pad_idx, smoothing)

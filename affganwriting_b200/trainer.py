@@ -1,6 +1,9 @@
-"""One training iteration as the reference's driver runs it (GAN_word/main_run.py:146-167, 275-278), minus the
-recogniser update: cla_update -> dis_update -> gen_update, each followed by the data-parallel gradient exchange of
-the sub-network that was just differentiated and by its Adam step.
+"""One training iteration as the reference's driver runs it (GAN_word/main_run.py:146-167, 275-278):
+[rec_update ->] cla_update -> dis_update -> gen_update, each followed by the data-parallel gradient exchange of
+the sub-network that was just differentiated and by its Adam step.  The recogniser sub-step (and the l_rec term of
+gen_update) runs when a recogniser module is supplied (`rec=`, see network_tro.ConTranModel); it is stepped by
+torch.optim.Adam at lr 1e-5 like main_run.py:277.  A recogniser decodes with a host-side beam search, so the sub-steps that
+call it (rec_update, gen_update) are issued eagerly even in CUDA-graph mode; cla_update and dis_update are still replayed.
 
 The optimiser is `optim.Adam`: torch.optim.Adam's update for the reference's configuration as ONE libaffgw launch per
 sub-network; AFFGW_ADAM=torch selects torch.optim.Adam(fused=True) instead.
@@ -35,8 +38,12 @@ class Trainer:
     GRAPH_WARMUP = 3      # eager iterations before the capture
 
     def __init__(self, num_writers=500, lr_gen=1e-4, lr_dis=1e-4, lr_cla=1e-5, device=None, skip_unused_wgrad=True,
-                 bucket_bytes=None, encoder=None, cuda_graph=False, overlap_exchange=False):
-        self.model = ConTranModel(num_writers, oov=True, device=device, encoder=encoder)
+                 bucket_bytes=None, encoder=None, cuda_graph=False, overlap_exchange=False, rec=None, lr_rec=1e-5):
+        import warnings
+        with warnings.catch_warnings():
+            if rec is None:
+                warnings.simplefilter("ignore")     # configs[1] of BASELINE.json: the three convolutional models, by design
+            self.model = ConTranModel(num_writers, oov=True, device=device, encoder=encoder, rec=rec)
         m = self.model
         # main_run.py:275-278: Adam over filter(requires_grad, parameters()) with default betas / eps
         # (fused=True is torch's single-pass multi-tensor implementation of the same update)
@@ -53,6 +60,16 @@ class Trainer:
         self.red = {"cla": GradientReducer(m.cla.parameters(), **kw), "dis": GradientReducer(m.dis.parameters(), **kw),
                     "gen": GradientReducer(m.gen.parameters(), **kw)}
         self.opt = {"cla": self.cla_opt, "dis": self.dis_opt, "gen": self.gen_opt}
+        self.names = ("cla", "dis", "gen")
+        self.graphable = ("cla", "dis", "gen")
+        if rec is not None:
+            # the recogniser is a foreign torch module: torch's own Adam steps it (main_run.py:277, lr 1e-5)
+            self.rec_opt = torch.optim.Adam([p for p in m.rec.parameters() if p.requires_grad], lr=lr_rec)
+            self.opt["rec"] = self.rec_opt
+            self.red["rec"] = GradientReducer(m.rec.parameters(), **kw)
+            self.names = ("rec", "cla", "dis", "gen")       # main_run.py:148-167 order
+            self.graphable = ("cla", "dis")                 # rec_update / gen_update decode on the host (beam search)
+        self.cer = None                                     # optional (CER(), CER(), CER()) accumulators: rec, gen, gen-swap
         # the reference computes dis / cla weight gradients inside gen_update and throws them away at the next
         # zero_grad (main_run.py:148-163); skipping them changes nothing observable
         self.skip_unused_wgrad = skip_unused_wgrad
@@ -72,22 +89,25 @@ class Trainer:
         """zero_grad + forward + backward of one sub-step; returns its loss tensors."""
         m = self.model
         self.opt[name].zero_grad()
+        if name == "rec":
+            return (m(batch, epoch, "rec_update", self.cer[0] if self.cer else None),)
         if name == "cla":
             return (m(batch, epoch, "cla_update"),)
         if name == "dis":
             return (m(batch, epoch, "dis_update"),)
         frozen = []
         if self.skip_unused_wgrad:
-            for p in list(m.dis.parameters()) + list(m.cla.parameters()):
+            others = list(m.dis.parameters()) + list(m.cla.parameters()) + (list(m.rec.parameters()) if m.rec is not None else [])
+            for p in others:
                 if p.requires_grad:
                     p.requires_grad_(False)
                     frozen.append(p)
         try:
-            l_total, l_dis_g, l_cla_g, _, _ = m(batch, epoch, "gen_update")
+            l_total, l_dis_g, l_cla_g, _, l_rec_g = m(batch, epoch, "gen_update", self.cer[1:] if self.cer else None)
         finally:
             for p in frozen:
                 p.requires_grad_(True)
-        return (l_total, l_dis_g, l_cla_g)
+        return (l_total, l_dis_g, l_cla_g, l_rec_g)
 
     def _finish(self, name):
         self.red[name].reduce()
@@ -97,9 +117,13 @@ class Trainer:
 
     @staticmethod
     def _pack(outs):
-        (l_cla,), (l_dis,), (l_total, l_dis_g, l_cla_g) = outs["cla"], outs["dis"], outs["gen"]
-        return {"cla": l_cla.detach(), "dis": l_dis.detach(), "gen": l_total.detach(), "gen_dis": l_dis_g.detach(),
-                "gen_cla": l_cla_g.detach()}
+        (l_cla,), (l_dis,), (l_total, l_dis_g, l_cla_g, l_rec_g) = outs["cla"], outs["dis"], outs["gen"]
+        res = {"cla": l_cla.detach(), "dis": l_dis.detach(), "gen": l_total.detach(), "gen_dis": l_dis_g.detach(),
+               "gen_cla": l_cla_g.detach()}
+        if "rec" in outs:
+            res["rec"] = outs["rec"][0].detach()
+            res["gen_rec"] = l_rec_g.detach()
+        return res
 
     # ------------------------------------------------------------------------------------------------ overlapped exchange
     def join(self, *names):
@@ -123,7 +147,7 @@ class Trainer:
     def train_step_eager(self, batch, epoch=0):
         self.join()
         outs = {}
-        for name in ("cla", "dis", "gen"):
+        for name in self.names:
             outs[name] = self._fwd_bwd(name, batch, epoch)
             self._finish(name)
         return self._pack(outs)
@@ -155,14 +179,20 @@ class Trainer:
             if torch.is_tensor(dst) and dst.data_ptr() != src.data_ptr():
                 dst.copy_(src, non_blocking=True)
         outs = {}
-        for name in ("cla", "dis", "gen"):
-            graph, static_out, grads = self._graphs[name]
+        for name in self.names:
             # dis_update reads the generator stepped by the previous iteration, gen_update also the classifier stepped by this
             # one; cla_update reads neither, so the generator's exchange + Adam overlap it (and the classifier's dis_update)
             if name == "dis":
                 self.join("gen")
             elif name == "gen":
                 self.join()
+            if name not in self._graphs:                 # sub-steps that call the recogniser: issued eagerly
+                if name == "rec":
+                    self.join("gen")                     # (nothing of the generator is read, but .grad buffers are shared state)
+                outs[name] = self._fwd_bwd(name, self._static_in, epoch)
+                self._finish(name)
+                continue
+            graph, static_out, grads = self._graphs[name]
             graph.replay()
             for p, g in grads:                      # an eager iteration in between may have re-pointed .grad
                 p.grad = g
@@ -171,7 +201,8 @@ class Trainer:
                 self._finish_on_side_stream(name)
             else:
                 self._finish(name)
-        self.model.iter_num += 1
+        if "gen" in self._graphs:
+            self.model.iter_num += 1                # the captured gen_update's Python side does not run in a replay
         # the static loss tensors are overwritten by the next replay: hand out copies
         return {k: v.clone() for k, v in self._pack(outs).items()}
 
@@ -207,7 +238,12 @@ class Trainer:
         graphs, outs = {}, {}
         self.graph_launches = 0
         n0 = _lib.launch_count()
-        for name in ("cla", "dis", "gen"):
+        for name in self.names:
+            if name not in self.graphable:
+                outs[name] = self._fwd_bwd(name, self._static_in, epoch)
+                self._finish(name)
+                n0 = _lib.launch_count()
+                continue
             self.opt[name].zero_grad(set_to_none=True)      # captured backward WRITES fresh .grad tensors (no accumulation)
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, pool=pool, stream=self._side):

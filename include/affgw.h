@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define AFFGW_VERSION 107
+#define AFFGW_VERSION 108
 
 enum { AFFGW_DT_F32 = 0, AFFGW_DT_BF16 = 1 };
 enum { AFFGW_ACT_NONE = 0, AFFGW_ACT_RELU = 1, AFFGW_ACT_LRELU = 2, AFFGW_ACT_TANH = 3 };
@@ -203,6 +203,14 @@ int affgw_bce_logits_bwd(const void* x, int dtype, float target, const float* gr
 int affgw_softmax_ce_fwd(const void* x, int dtype, const long long* y, float* loss, int B, int C, int* err, void* stream);
 int affgw_softmax_ce_bwd(const void* x, int dtype, const long long* y, const float* grad_out, void* dx, int B, int C,
                          void* stream);
+
+/* Recogniser loss of the GAN step: crit(log_softmax(x), y) = LabelSmoothing(vocab, PAD, 0.4) over KLDivLoss(reduction='sum')
+ * (reference loss_tro.py:8-35 as called at network_tro.py:44-45,92-93).  x [rows][V] fp32 logits, y [rows] int64 targets;
+ * rows whose target is pad_idx and the pad_idx column carry no mass; NaN logits give a NaN loss like torch does. */
+int affgw_label_smooth_kl_fwd(const float* x, const long long* y, float* loss, int rows, int V, int pad_idx, float smoothing,
+                              int* err, void* stream);
+int affgw_label_smooth_kl_bwd(const float* x, const long long* y, const float* grad_out, float* dx, int rows, int V, int pad_idx,
+                              float smoothing, void* stream);
 
 /* ---- layout / dtype (the boundary: callers hand NCHW fp32 tensors, network_tro.py:30-36) ------------------- */
 /* Wire format of the style / target images: grey-level uint8 pixels as cv2 leaves them after the

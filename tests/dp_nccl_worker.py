@@ -58,7 +58,8 @@ def main():
         got = torch.cat([p.grad.reshape(-1) for p in live]).double()
         err = float((got - expect).abs().max() / expect.abs().max())
         differ = float((gathered[0].double() - gathered[1].double()).abs().max() / expect.abs().max())
-        none_kept = all(p.grad is None for p in params if p not in live)
+        live_ids = {id(p) for p in live}
+        none_kept = all(p.grad is None for p in params if id(p) not in live_ids)
         tr.opt[sub].step()
         from affganwriting_b200 import ops
         ops.weights_updated(params)

@@ -1,0 +1,150 @@
+"""The recogniser side of the training step: the fused label-smoothed KL loss against
+torch's own composition (loss_tro.py:8-35), and this package's ConTranModel with a recogniser attached - rec_update and the
+w_rec * l_rec term of gen_update - against the REFERENCE's network_tro.ConTranModel.forward on the same weights, the same
+batch and the same random-number stream (the recogniser draws dropout masks on every call, modules_tro.py:633)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import affganwriting_b200 as A
+from affganwriting_b200 import ops
+from affgw_testutil import cosine
+from oracle import affgw_oracle as O
+from oracle import ref_bootstrap as rb
+
+pytestmark = pytest.mark.gpu
+
+
+def _torch_crit(x, t, V=55, pad=2, smoothing=0.4):
+    lp = torch.log_softmax(x, dim=-1)
+    dist = torch.full_like(lp, smoothing / (V - 2))
+    dist.scatter_(1, t.unsqueeze(1), 1.0 - smoothing)
+    dist[:, pad] = 0
+    dist[t == pad] = 0.0
+    return F.kl_div(lp, dist, reduction="sum")
+
+
+def test_label_smoothing_kl_matches_torch():
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = (torch.randn(88, 55, device="cuda", generator=g) * 3).requires_grad_()
+    t = torch.randint(0, 55, (88,), device="cuda", generator=g)
+    t[::5] = 2                                                    # PAD rows carry no mass
+    loss = ops.label_smoothing_kl(x, t, 2, 0.4)
+    xr = x.detach().double().requires_grad_()
+    ref = _torch_crit(xr, t)
+    assert abs(float(loss) - float(ref)) <= 1e-4 * abs(float(ref))
+    (loss * 0.37).backward()
+    (ref * 0.37).backward()
+    assert float((x.grad.double() - xr.grad).abs().max()) <= 1e-5
+    # the reference's call shape crit(log_softmax(x), y) with real log-probabilities gives the same number (idempotence)
+    from affganwriting_b200 import loss_tro
+    a = loss_tro.crit(loss_tro.log_softmax(x.detach()), t)
+    b = loss_tro.crit(torch.log_softmax(x.detach(), dim=-1), t)
+    assert abs(float(a) - float(ref)) <= 1e-4 * abs(float(ref)) and abs(float(b) - float(ref)) <= 1e-4 * abs(float(ref))
+    # NaN logits (the beam search's raw-logit scoring produces them on random weights) propagate like torch
+    xn = x.detach().clone()
+    xn[7, 3] = float("nan")
+    assert torch.isnan(ops.label_smoothing_kl(xn, t, 2, 0.4)) and torch.isnan(_torch_crit(xn, t))
+    with pytest.raises(RuntimeError):
+        ops.label_smoothing_kl(x.detach(), torch.full((88,), 55, device="cuda"), 2, 0.4)
+        A.check_device_errors()
+
+
+@pytest.mark.skipif(not rb.available(), reason="reference tree neither at /root/reference nor staged in oracle/_ref")
+def test_contran_with_recogniser_matches_reference_forward(specs):
+    """rec_update and gen_update (with l_rec) of affganwriting_b200.network_tro.ConTranModel == the reference's
+    network_tro.ConTranModel.forward, both on libaffgw generator / discriminator / classifier and the reference's RecModel."""
+    import affganwriting_b200.install as inst
+    from affganwriting_b200.network_tro import ConTranModel
+    from affganwriting_b200 import loss_tro as our_loss
+    from oracle import weights as W
+    ns = rb.load_network(50)
+    inst.install()
+    A.set_precision("fp32")
+    try:
+        import loss_tro as ref_loss
+        torch.manual_seed(5)
+        ref_model = ns.network_tro.ConTranModel(500, 500, True)
+        ref_model.gen.load_state_dict(W.make_state(specs["gen_c50"]))
+        ref_model.dis.load_state_dict(W.make_state(specs["dis"]))
+        ref_model.cla.load_state_dict(W.make_state(specs["cla"]))
+        ours = ConTranModel(500, oov=True, rec=ns.modules_tro.RecModel(pretrain=False), device=torch.device("cuda", 0))
+        assert list(ours.state_dict().keys()) == list(ref_model.state_dict().keys())
+        ours.load_state_dict(ref_model.state_dict())
+        ref_model.train(); ours.train()
+        cpu = O.synthetic_batch(3, 50)
+        tr_label = torch.stack([cpu["label_xt"], cpu["label_xt_swap"]], 1).repeat(1, 25, 1)
+        batch = (np.zeros(3, dtype=np.int64), cpu["tr_wid"], np.arange(3), cpu["tr_img"], torch.full((3, 50), 216), tr_label,
+                 cpu["img_xt"], cpu["label_xt"], cpu["label_xt_swap"])
+
+        def grads(model, sub):
+            return {k: p.grad.clone() for k, p in getattr(model, sub).named_parameters() if p.grad is not None}
+
+        # ---- rec_update
+        out = {}
+        for name, model, cer in (("ref", ref_model, ref_loss.CER()), ("ours", ours, our_loss.CER())):
+            model.zero_grad()
+            torch.manual_seed(11)
+            loss = model(batch, 0, "rec_update", cer)
+            out[name] = (float(loss), grads(model, "rec"), (cer.ed, cer.len))
+        assert out["ref"][2] == out["ours"][2]                                      # same CER bookkeeping
+        lr_, lo_ = out["ref"][0], out["ours"][0]
+        assert (np.isnan(lr_) and np.isnan(lo_)) or abs(lr_ - lo_) <= 1e-4 * max(1.0, abs(lr_)), (lr_, lo_)
+        if not np.isnan(lr_):
+            for k, g in out["ref"][1].items():
+                assert cosine(out["ours"][1][k], g) >= 0.9999, k
+        # ---- gen_update with the recogniser term
+        res = {}
+        for name, model, cers in (("ref", ref_model, [ref_loss.CER(), ref_loss.CER()]), ("ours", ours, [our_loss.CER(), our_loss.CER()])):
+            model.zero_grad()
+            model.load_state_dict(ref_model.state_dict() if name == "ours" else model.state_dict())
+            torch.manual_seed(13)
+            l_total, l_dis, l_cla, l_l1, l_rec = model(batch, 0, "gen_update", cers)
+            res[name] = (float(l_total), float(l_dis), float(l_cla), float(l_rec), grads(model, "gen"))
+        print(f"\ngen_update with recogniser: reference composition l_total {res['ref'][0]:.5f} (l_rec {res['ref'][3]:.5f}), "
+              f"this package {res['ours'][0]:.5f} (l_rec {res['ours'][3]:.5f})")
+        for i in (1, 2):
+            assert abs(res["ref"][i] - res["ours"][i]) <= 2e-4 * max(1.0, abs(res["ref"][i]))
+        if not np.isnan(res["ref"][3]):
+            assert abs(res["ref"][3] - res["ours"][3]) <= 2e-3 * max(1.0, abs(res["ref"][3]))
+            assert res["ours"][3] != 0.0
+            dots = na = nb = 0.0
+            for k, g in res["ref"][4].items():
+                a, b = res["ours"][4][k].double().reshape(-1), g.double().reshape(-1)
+                dots += float(a @ b); na += float(a @ a); nb += float(b @ b)
+            assert dots / (na ** 0.5 * nb ** 0.5) >= 0.999
+        else:
+            assert np.isnan(res["ours"][3])
+    finally:
+        inst.uninstall()
+        A.set_precision("fp32")
+
+
+@pytest.mark.skipif(not rb.available(), reason="reference tree neither at /root/reference nor staged in oracle/_ref")
+def test_trainer_runs_the_four_substeps_with_a_recogniser():
+    """main_run.py:146-167 order rec -> cla -> dis -> gen; graph mode replays cla / dis and issues the recogniser steps eagerly."""
+    from affganwriting_b200.trainer import Trainer
+    from affganwriting_b200 import load_data as LD
+    import bench
+    ns = rb.load_network(50)
+    A.set_precision("bf16")
+    try:
+        dev = torch.device("cuda", 0)
+        host = list(bench.synthetic_batch(4, 50, 7))
+        host[5] = host[5].contiguous()
+        batch = LD.batch_to_device(tuple(host), dev)
+        torch.manual_seed(0)
+        t = Trainer(num_writers=500, device=dev, rec=ns.modules_tro.RecModel(pretrain=False), cuda_graph=True)
+        t.GRAPH_WARMUP = 1
+        w0 = next(t.model.rec.parameters()).detach().clone()
+        for _ in range(3):
+            losses = t.train_step(batch)
+        assert set(losses) >= {"rec", "cla", "dis", "gen", "gen_rec"}
+        assert set(t._graphs) == {"cla", "dis"}
+        assert t.model.iter_num == 3
+        assert all(torch.isfinite(losses[k]) for k in ("cla", "dis", "gen_dis", "gen_cla"))
+        if torch.isfinite(losses["rec"]):
+            assert not torch.equal(w0, next(t.model.rec.parameters()).detach())      # the recogniser is being trained
+    finally:
+        A.set_precision("fp32")
