@@ -97,6 +97,15 @@ SIGNATURES = {
     "affgw_bce_logits_bwd": [_P, _I, _F, _P, _P, _L, _P],
     "affgw_softmax_ce_fwd": [_P, _I, _P, _P, _I, _I, _P, _P],
     "affgw_softmax_ce_bwd": [_P, _I, _P, _P, _P, _I, _I, _P],
+    "affgw_gru_cell_fwd": [_P, _L, _P, _P, _P, _I, _I, _P],
+    "affgw_gru_cell_bwd": [_P, _P, _L, _P, _P, _P, _P, _P, _I, _I, _P],
+    "affgw_scale_nc": [_P, _P, _P, _I, _L, _I, _P],
+    "affgw_mul2": [_P, _P, _P, _L, _P],
+    "affgw_map_seq": [_P, _P, _I, _I, _I, _I, _I, _P],
+    "affgw_attn_energy_fwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
+    "affgw_attn_energy_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
+    "affgw_attn_ctx_fwd": [_P, _P, _P, _P, _P, _I, _I, _I, _P],
+    "affgw_attn_ctx_bwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
     "affgw_label_smooth_kl_fwd": [_P, _P, _P, _I, _I, _I, _F, _P, _P],
     "affgw_label_smooth_kl_bwd": [_P, _P, _P, _P, _I, _I, _I, _F, _P],
     "affgw_nchw_to_nhwc": [_P, _P, _I, _I, _I, _L, _I, _P],

@@ -94,6 +94,20 @@ int bce_logits_fwd(const void* x, int dt, float target, float* loss, long long n
 int bce_logits_bwd(const void* x, int dt, float target, const float* gout, void* dx, long long n, cudaStream_t st);
 int softmax_ce_fwd(const void* x, int dt, const long long* y, float* loss, int B, int C, int* err, cudaStream_t st);
 int softmax_ce_bwd(const void* x, int dt, const long long* y, const float* gout, void* dx, int B, int C, cudaStream_t st);
+int gru_cell_fwd(const float* gi, long long gi_pitch, const float* gh, const float* h, float* hout, int N, int H, cudaStream_t st);
+int gru_cell_bwd(const float* dhout, const float* gi, long long gi_pitch, const float* gh, const float* h, float* dgi, float* dgh,
+                 float* dh, int N, int H, cudaStream_t st);
+int scale_nc(const float* x, const float* m, float* y, int N, long long P, int C, cudaStream_t st);
+int mul2(const float* a, const float* b, float* y, long long n, cudaStream_t st);
+int map_seq(const float* src, float* dst, int B, int H, int W, int C, int to_seq, cudaStream_t st);
+int attn_energy_fwd(const float* e, const long long* sidx, const float* hp, const float* loc, const float* v, const float* vb,
+                    float* energy, int N, int T, int F, cudaStream_t st);
+int attn_energy_bwd(const float* denergy, const float* e, const long long* sidx, const float* hp, const float* loc, const float* v,
+                    float* de, float* dhp, float* dloc, float* dv, float* dvb, int N, int T, int F, cudaStream_t st);
+int attn_ctx_fwd(const float* energy, const float* enc, const long long* sidx, float* attn, float* ctx, int N, int T, int F,
+                 cudaStream_t st);
+int attn_ctx_bwd(const float* dattn, const float* dctx, const float* attn, const float* enc, const long long* sidx, float* denergy,
+                 float* denc, int N, int T, int F, cudaStream_t st);
 int label_smooth_kl_fwd(const float* x, const long long* y, float* loss, int rows, int V, int pad, float smoothing, int* err,
                         cudaStream_t st);
 int label_smooth_kl_bwd(const float* x, const long long* y, const float* gout, float* dx, int rows, int V, int pad, float smoothing,
@@ -667,6 +681,47 @@ int affgw_softmax_ce_fwd(const void* x, int dt, const long long* y, float* loss,
 int affgw_softmax_ce_bwd(const void* x, int dt, const long long* y, const float* gout, void* dx, int B, int C, void* s) {
     REQ(x && y && gout && dx && dt_ok(dt) && B > 0 && C > 0, "softmax_ce_bwd");
     return softmax_ce_bwd(x, dt, y, gout, dx, B, C, S(s));
+}
+int affgw_gru_cell_fwd(const float* gi, long long gi_pitch, const float* gh, const float* h, float* h_out, int N, int H, void* s) {
+    REQ(gi && gh && h && h_out && N > 0 && H > 0 && gi_pitch >= 3LL * H, "gru_cell_fwd");
+    return gru_cell_fwd(gi, gi_pitch, gh, h, h_out, N, H, S(s));
+}
+int affgw_gru_cell_bwd(const float* dh_out, const float* gi, long long gi_pitch, const float* gh, const float* h, float* dgi,
+                       float* dgh, float* dh, int N, int H, void* s) {
+    REQ(dh_out && gi && gh && h && dgi && dgh && dh && N > 0 && H > 0 && gi_pitch >= 3LL * H, "gru_cell_bwd");
+    return gru_cell_bwd(dh_out, gi, gi_pitch, gh, h, dgi, dgh, dh, N, H, S(s));
+}
+int affgw_scale_nc(const float* x, const float* m, float* y, int N, long long P, int C, void* s) {
+    REQ(x && m && y && N > 0 && P > 0 && C > 0, "scale_nc");
+    return scale_nc(x, m, y, N, P, C, S(s));
+}
+int affgw_mul2(const float* a, const float* b, float* y, long long n, void* s) {
+    REQ(a && b && y && n > 0, "mul2");
+    return mul2(a, b, y, n, S(s));
+}
+int affgw_map_seq(const float* src, float* dst, int B, int H, int W, int C, int to_seq, void* s) {
+    REQ(src && dst && B > 0 && H > 0 && W > 0 && C > 0, "map_seq");
+    return map_seq(src, dst, B, H, W, C, to_seq, S(s));
+}
+int affgw_attn_energy_fwd(const float* e, const long long* sample, const float* hp, const float* loc, const float* v, const float* vb,
+                          float* energy, int N, int T, int F, void* s) {
+    REQ(e && sample && hp && loc && v && vb && energy && N > 0 && T > 0 && F > 0, "attn_energy_fwd");
+    return attn_energy_fwd(e, sample, hp, loc, v, vb, energy, N, T, F, S(s));
+}
+int affgw_attn_energy_bwd(const float* denergy, const float* e, const long long* sample, const float* hp, const float* loc,
+                          const float* v, float* de, float* dhp, float* dloc, float* dv, float* dvb, int N, int T, int F, void* s) {
+    REQ(denergy && e && sample && hp && loc && v && de && dhp && dloc && dv && dvb && N > 0 && T > 0 && F > 0, "attn_energy_bwd");
+    return attn_energy_bwd(denergy, e, sample, hp, loc, v, de, dhp, dloc, dv, dvb, N, T, F, S(s));
+}
+int affgw_attn_ctx_fwd(const float* energy, const float* enc, const long long* sample, float* attn, float* ctx, int N, int T, int F,
+                       void* s) {
+    REQ(energy && enc && sample && attn && ctx && N > 0 && T > 0 && F > 0, "attn_ctx_fwd");
+    return attn_ctx_fwd(energy, enc, sample, attn, ctx, N, T, F, S(s));
+}
+int affgw_attn_ctx_bwd(const float* dattn, const float* dctx, const float* attn, const float* enc, const long long* sample,
+                       float* denergy, float* denc, int N, int T, int F, void* s) {
+    REQ(dctx && attn && enc && sample && denergy && denc && N > 0 && T > 0 && F > 0, "attn_ctx_bwd");
+    return attn_ctx_bwd(dattn, dctx, attn, enc, sample, denergy, denc, N, T, F, S(s));
 }
 int affgw_label_smooth_kl_fwd(const float* x, const long long* y, float* loss, int rows, int V, int pad_idx, float smoothing,
                               int* err, void* s) {

@@ -29,8 +29,9 @@ def _swap(mod, mod_name, attr, new, done):
     done.append((mod_name, attr))
 
 
-def install(ref_blocks="blocks", ref_modules="modules_tro", ref_network="network_tro"):
+def install(ref_blocks="blocks", ref_modules="modules_tro", ref_network="network_tro", recogniser=True):
     """Patch the reference modules in place. Returns the list of (module, attribute) pairs that were replaced.
+    recogniser=False keeps the reference's own RecModel (plain PyTorch) behind the native generator / discriminator / classifier.
     `network_tro` binds the model classes by name at import (network_tro.py:4): when it is already imported its bindings are
     replaced too, so install() works before or after `import network_tro`."""
     done = []
@@ -43,12 +44,14 @@ def install(ref_blocks="blocks", ref_modules="modules_tro", ref_network="network
         src = _modules if n in MODULE_NAMES else _blocks
         if hasattr(rm, n):
             _swap(rm, ref_modules, n, getattr(src, n), done)
+    if recogniser and hasattr(rm, "RecModel"):
+        _swap(rm, ref_modules, "RecModel", _modules.RecModel, done)
     # the encoder the reference's GenModel_FC constructs by default (modules_tro.py:219)
     if hasattr(rm, "ImageEncoderResNet50"):
         _swap(rm, ref_modules, "ImageEncoderResNet50", _resnet.ImageEncoderResNet50, done)
     nt = sys.modules.get(ref_network)
     if nt is not None:
-        for n in ("GenModel_FC", "DisModel", "WriterClaModel"):
+        for n in ("GenModel_FC", "DisModel", "WriterClaModel") + (("RecModel",) if recogniser else ()):
             if hasattr(nt, n):
                 _swap(nt, ref_network, n, getattr(_modules, n), done)
     # the stand-alone ResNet-18 (Resnet18.py), when the caller has imported it

@@ -2,6 +2,7 @@
 
   DisModel :119-168   WriterClaModel :170-201   GenModel_FC :208-259   TextEncoder_FC :268-317
   ImageEncoder (VGG) :331-375   Decoder :586-607   MLP :684-697   get_num_adain_params :110-116
+  RecModel :610-638 (affganwriting_b200.recognizer)
 
 Same constructor signatures, attribute names, method names and state_dict keys; forwards run libaffgw kernels.
 GenModel_FC takes the style encoder the reference selects by editing source (modules_tro.py:211-219) as an
@@ -14,6 +15,7 @@ from torch import nn
 from . import ops
 from .blocks import ActFirstResBlock, Conv2dBlock, LinearBlock, ResBlocks
 from .load_data import IMG_HEIGHT, IMG_WIDTH, OUTPUT_MAX_LEN, tokens, vocab_size
+from .recognizer import RecModel  # noqa: F401  (modules_tro.py:610-638)
 from .vgg_tro_channel3_modi import _pad64, vgg19_bn
 
 

@@ -204,6 +204,32 @@ int affgw_softmax_ce_fwd(const void* x, int dtype, const long long* y, float* lo
 int affgw_softmax_ce_bwd(const void* x, int dtype, const long long* y, const float* grad_out, void* dx, int B, int C,
                          void* stream);
 
+/* ---- recogniser (RecModel, reference modules_tro.py:610-638) ---------------------------------------------
+ * Only the pieces that are not convolutions / GEMMs; the projections run through affgw_conv2d_*.  All tensors fp32, dense.
+ * GRU cell (torch.nn.GRU semantics; encoder_vgg.py:700, decoder.py:27): gi [N][>= 3H, row pitch gi_pitch] = W_ih x + b_ih,
+ * gh [N][3H] = W_hh h + b_hh, gate order (r, z, n); h_out = (1 - z) n + z h.  The backward call recomputes the gates. */
+int affgw_gru_cell_fwd(const float* gi, long long gi_pitch, const float* gh, const float* h, float* h_out, int N, int H, void* stream);
+int affgw_gru_cell_bwd(const float* dh_out, const float* gi, long long gi_pitch, const float* gh, const float* h, float* dgi,
+                       float* dgh, float* dh, int N, int H, void* stream);
+/* y[n][p][c] = x[n][p][c] * m[n][c]: nn.Dropout2d with the caller's keep-mask / (1 - p) (encoder_vgg.py:709); its own backward */
+int affgw_scale_nc(const float* x, const float* m, float* y, int N, long long P, int C, void* stream);
+int affgw_mul2(const float* a, const float* b, float* y, long long n, void* stream);
+/* NHWC feature map [B][H][W][C] <-> sequence [W][B][H*C] (out.permute(3,0,2,1).reshape(-1, B, H*C), encoder_vgg.py:711-713) */
+int affgw_map_seq(const float* src, float* dst, int B, int H, int W, int C, int to_seq, void* stream);
+/* location attention (attention.py:132-158): energy[n][t] = v . tanh(e[sample[n]][t] + hp[n] + loc[n][t]) + vb.
+ * e [B][T][F] is the projected encoder output shared by the hypotheses of a sample (sample[n] = row -> sample index);
+ * the backward call ACCUMULATES into de / dhp / dv / dvb (zero them first) and writes dloc. */
+int affgw_attn_energy_fwd(const float* e, const long long* sample, const float* hp, const float* loc, const float* v, const float* vb,
+                          float* energy, int N, int T, int F, void* stream);
+int affgw_attn_energy_bwd(const float* denergy, const float* e, const long long* sample, const float* hp, const float* loc,
+                          const float* v, float* de, float* dhp, float* dloc, float* dv, float* dvb, int N, int T, int F, void* stream);
+/* attn[n] = softmax_t(energy[n]); ctx[n] = sum_t attn[n][t] enc[sample[n]][t]  (attention.py:139-141, decoder.py:38-40);
+ * backward: dattn may be NULL, denc is ACCUMULATED (zero it first).  T <= 64. */
+int affgw_attn_ctx_fwd(const float* energy, const float* enc, const long long* sample, float* attn, float* ctx, int N, int T, int F,
+                       void* stream);
+int affgw_attn_ctx_bwd(const float* dattn, const float* dctx, const float* attn, const float* enc, const long long* sample,
+                       float* denergy, float* denc, int N, int T, int F, void* stream);
+
 /* Recogniser loss of the GAN step: crit(log_softmax(x), y) = LabelSmoothing(vocab, PAD, 0.4) over KLDivLoss(reduction='sum')
  * (reference loss_tro.py:8-35 as called at network_tro.py:44-45,92-93).  x [rows][V] fp32 logits, y [rows] int64 targets;
  * rows whose target is pad_idx and the pad_idx column carry no mass; NaN logits give a NaN loss like torch does. */

@@ -60,7 +60,7 @@ def test_contran_with_recogniser_matches_reference_forward(specs):
     from affganwriting_b200 import loss_tro as our_loss
     from oracle import weights as W
     ns = rb.load_network(50)
-    inst.install()
+    inst.install(recogniser=False)
     A.set_precision("fp32")
     try:
         import loss_tro as ref_loss

@@ -16,7 +16,7 @@ needs_ref = pytest.mark.skipif(not rb.available(), reason="reference tree neithe
 def installed():
     import affganwriting_b200.install as inst
     ns = rb.load_network(50)
-    inst.install()
+    inst.install(recogniser=False)
     try:
         yield ns, inst
     finally:
@@ -40,7 +40,7 @@ def test_reference_contran_model_is_built_from_dropin_classes():
     ns = rb.load_network(50)
     ref_sd = _reference_state(ns)          # before install(): the reference's own classes
     import affganwriting_b200.install as inst
-    done = inst.install()
+    done = inst.install(recogniser=False)
     try:
         assert ("network_tro", "GenModel_FC") in done and ("modules_tro", "Conv2dBlock") in done and ("blocks", "iAFF") in done
         nt = ns.network_tro
