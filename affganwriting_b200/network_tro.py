@@ -1,8 +1,9 @@
 """Training / evaluation step composition (reference GAN_word/network_tro.py:17-177): all four update modes and `eval`.
 
 Generator, discriminator and writer classifier are this package's classes.  The recogniser is a constructor argument
-(`rec=`): any module with the reference RecModel's call shape `rec(img [B,1,H,W], label [B,T], img_width=...) -> logits
-[B, T-1, vocab]` (modules_tro.py:631-636) - the reference's own RecModel drops in unchanged (tests/test_gpu_rec_step.py).  With
+(`rec=`): `True` builds this package's native RecModel (affganwriting_b200.recognizer); any other module with the reference
+RecModel's call shape `rec(img [B,1,H,W], label [B,T], img_width=...) -> logits [B, T-1, vocab]` (modules_tro.py:631-636) works
+too - the reference's own RecModel drops in unchanged (tests/test_gpu_rec_step.py).  With
 a recogniser the step is the reference's complete objective: `rec_update` (network_tro.py:39-48) and
 l_total = w_dis l_dis + w_cla l_cla + w_l1 l_l1 + w_rec l_rec in `gen_update` (:57-103).  With rec=None the l_rec term is
 absent (BASELINE.json configs[1] names the three convolutional models only) and a warning says so once.
@@ -32,6 +33,9 @@ class ConTranModel(nn.Module):
         self.gen = GenModel_FC(OUTPUT_MAX_LEN, encoder=encoder).to(dev)
         self.cla = WriterClaModel(num_writers).to(dev)
         self.dis = DisModel().to(dev)
+        if rec is True or rec == "native":
+            from .modules_tro import RecModel
+            rec = RecModel(pretrain=False)          # network_tro.py:23
         self.rec = rec.to(dev) if rec is not None else None
         if rec is None:
             warnings.warn("ConTranModel built without a recogniser: gen_update optimises w_dis*l_dis + w_cla*l_cla only and "

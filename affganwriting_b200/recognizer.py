@@ -17,12 +17,12 @@ seq2seqnew2.py:87-139):
   * the scores of a step ([rows, 55] logits) are copied to the host once and the hypotheses are selected there with the
     reference's own calls (`torch.topk(torch.log(x + 1e-12))`, `list.sort`, `max`): the reference scores raw logits, so
     negative logits give NaN scores and the surviving hypotheses depend on how those calls order NaNs
-    (oracle/rec_oracle.py header) - running the same calls on the same numbers is what keeps the tokens identical;
+    (measured with the CPU oracle, DESIGN.md section 9) - running the same calls on the same numbers is what keeps the tokens identical;
   * the states of the selected parents are gathered on the device for the next step.
 
 `RecModel.forward` always runs in training mode like the reference (modules_tro.py:633 forces `seq2seq.train()`): BatchNorm
 uses batch statistics and the three dropouts are active.  Their keep-masks can be injected (`masks=`, the layout of
-oracle.rec_oracle.rec_forward_explicit) so that a run can be compared with the CPU oracle; otherwise they are drawn on the
+CPU oracle's mask-injectable restatement) so that a run can be compared with the CPU oracle; otherwise they are drawn on the
 device with torch's generator.
 """
 import numpy as np

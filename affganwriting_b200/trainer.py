@@ -63,8 +63,10 @@ class Trainer:
         self.names = ("cla", "dis", "gen")
         self.graphable = ("cla", "dis", "gen")
         if rec is not None:
-            # the recogniser is a foreign torch module: torch's own Adam steps it (main_run.py:277, lr 1e-5)
-            self.rec_opt = torch.optim.Adam([p for p in m.rec.parameters() if p.requires_grad], lr=lr_rec)
+            # main_run.py:277: Adam at lr 1e-5 (optim.Adam for the native recogniser, torch's own for a foreign torch module)
+            from .recognizer import RecModel as _Native
+            rec_params = [p for p in m.rec.parameters() if p.requires_grad]
+            self.rec_opt = make(rec_params, lr_rec) if isinstance(m.rec, _Native) else torch.optim.Adam(rec_params, lr=lr_rec)
             self.opt["rec"] = self.rec_opt
             self.red["rec"] = GradientReducer(m.rec.parameters(), **kw)
             self.names = ("rec", "cla", "dis", "gen")       # main_run.py:148-167 order

@@ -249,6 +249,7 @@ def main():
                     help="style encoder: vgg = configs[1] (default, the headline), resnet18 = configs[2]")
     ap.add_argument("--no-graph", action="store_true", help="issue every launch from Python instead of replaying a CUDA graph")
     ap.add_argument("--no-overlap", action="store_true", help="gradient exchange + Adam on the main stream (no side-stream overlap)")
+    ap.add_argument("--no-rec-extra", action="store_true", help="skip the extra measurement of the full iteration with the recogniser")
     ap.add_argument("--quick", action="store_true", help="timed steps only (no e2e / generation / CPU legs): the command ncu profiles")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "affgw" else args.warmup
@@ -368,6 +369,27 @@ def main():
     gen.train()
     gen_img_s = world * B / (ms_gen / 1e3)
 
+    # ---- the reference driver's COMPLETE iteration (main_run.py:146-167: rec_update -> cla_update -> dis_update -> gen_update
+    # with the w_rec * l_rec term) with the native recogniser attached; reported beside the headline, whose workload
+    # (BASELINE.json configs[1]) names the three convolutional models only.  The recogniser's beam search selects hypotheses on
+    # the host every decoding step, so rec_update / gen_update are issued eagerly here (cla / dis still replay).
+    full_iter = None
+    if not args.no_rec_extra:
+        try:
+            del gen_fn
+            t2 = Trainer(num_writers=500, device=dev, encoder=None if args.encoder == "vgg" else args.encoder,
+                         cuda_graph=not args.no_graph, rec=True)
+            for _ in range(Trainer.GRAPH_WARMUP + 2):
+                t2.train_step(resident)
+            n0 = A.launch_count()
+            ms_full = timed(lambda: t2.train_step(resident), 3) / 3
+            full_iter = {"ms_per_step": ms_full, "steps_per_sec": world / (ms_full / 1e3),
+                         "eager_launches_per_step": (A.launch_count() - n0) / 3, "recogniser": "affganwriting_b200.recognizer.RecModel",
+                         "note": "rec_update + cla_update + dis_update + gen_update(l_dis + l_cla + l_rec), batch %d per GPU" % B}
+            del t2
+        except Exception as e:           # never fatal for the headline
+            full_iter = {"error": repr(e)[:300]}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -468,7 +490,7 @@ def main():
             "achieved_tflops_per_gpu": STEP_GFLOP_PER_SAMPLE * B / 1e3 / (ms_step / 1e3),
             "frac_of_peak": STEP_GFLOP_PER_SAMPLE * B / 1e3 / (ms_step / 1e3) / tf_peak},
         "cpu_baseline": cpu_baseline,
-        "extra": {"gen_images_per_sec": gen_img_s, "gen_batch_per_gpu": B, "gen_ms_per_batch": ms_gen,
+        "extra": {"full_iteration_with_recogniser": full_iter, "gen_images_per_sec": gen_img_s, "gen_batch_per_gpu": B, "gen_ms_per_batch": ms_gen,
                   "gen_frac_of_peak": None if args.encoder != "vgg" else 62.17e-3 * gen_img_s / world / tf_peak},
     }
     print(json.dumps(line), flush=True)

@@ -99,9 +99,11 @@ def test_contran_with_recogniser_matches_reference_forward(specs):
                 assert cosine(out["ours"][1][k], g) >= 0.9999, k
         # ---- gen_update with the recogniser term
         res = {}
-        for name, model, cers in (("ref", ref_model, [ref_loss.CER(), ref_loss.CER()]), ("ours", ours, [our_loss.CER(), our_loss.CER()])):
+        start = {k: v.clone() for k, v in ref_model.state_dict().items()}
+        for name, model, cers in (("ref", ref_model, [ref_loss.CER(), ref_loss.CER()]), ("ref2", ref_model, [ref_loss.CER(), ref_loss.CER()]),
+                                  ("ours", ours, [our_loss.CER(), our_loss.CER()])):
             model.zero_grad()
-            model.load_state_dict(ref_model.state_dict() if name == "ours" else model.state_dict())
+            model.load_state_dict(start)
             torch.manual_seed(13)
             l_total, l_dis, l_cla, l_l1, l_rec = model(batch, 0, "gen_update", cers)
             res[name] = (float(l_total), float(l_dis), float(l_cla), float(l_rec), grads(model, "gen"))
@@ -112,11 +114,19 @@ def test_contran_with_recogniser_matches_reference_forward(specs):
         if not np.isnan(res["ref"][3]):
             assert abs(res["ref"][3] - res["ours"][3]) <= 2e-3 * max(1.0, abs(res["ref"][3]))
             assert res["ours"][3] != 0.0
-            dots = na = nb = 0.0
-            for k, g in res["ref"][4].items():
-                a, b = res["ours"][4][k].double().reshape(-1), g.double().reshape(-1)
-                dots += float(a @ b); na += float(a @ a); nb += float(b @ b)
-            assert dots / (na ** 0.5 * nb ** 0.5) >= 0.999
+
+            def gcos(x, y):
+                dots = na = nb = 0.0
+                for k, g in res[y][4].items():
+                    a, b = res[x][4][k].double().reshape(-1), g.double().reshape(-1)
+                    dots += float(a @ b); na += float(a @ a); nb += float(b @ b)
+                return dots / (na ** 0.5 * nb ** 0.5)
+            c_ours, c_noise = gcos("ours", "ref"), gcos("ref2", "ref")
+            print(f"generator gradient cosine: this package vs reference composition {c_ours:.6f}; reference composition run twice "
+                  f"{c_noise:.6f} (the beam search's NaN-ordered selection flips on 1e-6 logit differences)")
+            # the step is chaotic through the recogniser's beam selection (rec_oracle.py header): hold our composition to the
+            # reference composition's own run-to-run agreement
+            assert c_ours >= min(0.999, c_noise - 5e-3)
         else:
             assert np.isnan(res["ours"][3])
     finally:
@@ -124,13 +134,15 @@ def test_contran_with_recogniser_matches_reference_forward(specs):
         A.set_precision("fp32")
 
 
-@pytest.mark.skipif(not rb.available(), reason="reference tree neither at /root/reference nor staged in oracle/_ref")
-def test_trainer_runs_the_four_substeps_with_a_recogniser():
-    """main_run.py:146-167 order rec -> cla -> dis -> gen; graph mode replays cla / dis and issues the recogniser steps eagerly."""
+@pytest.mark.parametrize("which", ["native", "reference"])
+def test_trainer_runs_the_four_substeps_with_a_recogniser(which):
+    """main_run.py:146-167 order rec -> cla -> dis -> gen; graph mode replays cla / dis and issues the recogniser steps eagerly.
+    Both with this package's native RecModel and with the reference's own (plain PyTorch) RecModel in the same slot."""
     from affganwriting_b200.trainer import Trainer
     from affganwriting_b200 import load_data as LD
     import bench
-    ns = rb.load_network(50)
+    if which == "reference" and not rb.available():
+        pytest.skip("reference tree neither at /root/reference nor staged in oracle/_ref")
     A.set_precision("bf16")
     try:
         dev = torch.device("cuda", 0)
@@ -138,7 +150,9 @@ def test_trainer_runs_the_four_substeps_with_a_recogniser():
         host[5] = host[5].contiguous()
         batch = LD.batch_to_device(tuple(host), dev)
         torch.manual_seed(0)
-        t = Trainer(num_writers=500, device=dev, rec=ns.modules_tro.RecModel(pretrain=False), cuda_graph=True)
+        rec = True if which == "native" else rb.load_network(50).modules_tro.RecModel(pretrain=False)
+        t = Trainer(num_writers=500, device=dev, rec=rec, cuda_graph=True)
+        assert type(t.model.rec).__module__ == ("affganwriting_b200.recognizer" if which == "native" else "modules_tro")
         t.GRAPH_WARMUP = 1
         w0 = next(t.model.rec.parameters()).detach().clone()
         for _ in range(3):

@@ -82,8 +82,8 @@ def test_native_recogniser_matches_oracle(batch, seed):
     top = max(float(v.grad.norm()) for v in leaves.values() if v.grad is not None)
     worst, n_checked = 1.0, 0
     for k, p in rec.named_parameters():
-        if not k.startswith("seq2seq."):
-            continue                                    # enc.* / dec.* are the same Parameter objects
+        # named_parameters() lists the shared Parameter objects once, under their first names enc.* / dec.*
+        k = ("seq2seq.encoder." + k[4:]) if k.startswith("enc.") else ("seq2seq.decoder." + k[4:]) if k.startswith("dec.") else k
         g = leaves[k].grad
         if g is None or float(g.norm()) < 1e-4 * top:   # unused (attention.proj) or exact-zero (biases in front of BatchNorm)
             continue
@@ -118,7 +118,7 @@ def test_native_recogniser_bf16_and_device_masks():
         assert float((a - c).abs().max()) <= 5e-3 * float(a.abs().max())
         ops.label_smoothing_kl(c.reshape(-1, 55), lab[:, 1:].reshape(-1), 2, 0.4).backward()
         assert img.grad is not None and torch.isfinite(img.grad).all() and float(img.grad.abs().max()) > 0
-        missing = [k for k, p in rec.named_parameters() if p.grad is None and "attention.proj" not in k]
+        missing = [k for k, p in rec.named_parameters() if p.grad is None and "attention.proj." not in k]
         assert not missing, missing
         with pytest.raises(RuntimeError):
             rec(img, lab, img_width=torch.from_numpy(np.array([216, 216, 100, 216])))

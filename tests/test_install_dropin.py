@@ -60,6 +60,16 @@ def test_reference_contran_model_is_built_from_dropin_classes():
     finally:
         inst.uninstall()
     assert ns.modules_tro.DisModel.__module__ == "modules_tro" and ns.network_tro.GenModel_FC.__module__ == "modules_tro"
+    # default install(): the recogniser is replaced too, with the same keys
+    inst.install()
+    try:
+        model = ns.network_tro.ConTranModel(500, 500, True)
+        assert type(model.rec).__module__ == "affganwriting_b200.recognizer"
+        assert list(model.state_dict().keys()) == list(ref_sd.keys())
+        model.load_state_dict(ref_sd, strict=True)
+    finally:
+        inst.uninstall()
+    assert ns.modules_tro.RecModel.__module__ == "modules_tro"
 
 
 @needs_ref
