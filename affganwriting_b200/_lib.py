@@ -16,13 +16,14 @@ ACT = {"none": 0, "relu": 1, "lrelu": 2, "tanh": 3}
 PAD = {"zero": 0, "reflect": 1, "replicate": 2}
 ALGO_AUTO, ALGO_SIMT, ALGO_TC = 0, 1, 2
 WLAYOUT_IM2COL, WLAYOUT_SHIFT = 1, 2
+FMT_BF16, FMT_F16 = 0, 1
 
 
 class ConvDesc(C.Structure):
     """Mirror of `affgw_conv_desc` (include/affgw.h)."""
     _fields_ = [(n, C.c_int32) for n in (
         "N", "H", "W", "Cin", "Cout", "KH", "KW", "stride", "pad", "pad_mode", "upsample", "Ho", "Wo",
-        "in_pitch", "out_pitch", "pre_act", "post_act", "x_dtype", "w_dtype", "y_dtype", "algo", "passes", "grad_dtype", "stride_w")]
+        "in_pitch", "out_pitch", "pre_act", "post_act", "x_dtype", "w_dtype", "y_dtype", "algo", "passes", "grad_dtype", "stride_w", "operand_fmt")]
 
 
 class PosFrame(C.Structure):
@@ -62,6 +63,11 @@ SIGNATURES = {
     "affgw_conv_pos_frames": [_D, C.POINTER(PosFrame), C.POINTER(PosFrame)],
     "affgw_position_planes_bytes": [C.POINTER(PosFrame), _I],
     "affgw_split_positions": [_P, _I, _P, C.POINTER(PosFrame), _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P],
+    "affgw_amax_scale": [_P, _L, _P, _P, _P],
+    "affgw_split_positions_fmt": [_P, _I, _P, C.POINTER(PosFrame), _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _I, _P, _P],
+    "affgw_pack_weight_tc_fmt": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
+    "affgw_conv2d_dgrad_scaled": [_P, _P, _P, _P, _P, _D, _P, _P],
+    "affgw_conv2d_wgrad_scaled": [_P, _P, _P, _P, _D, _P, _P],
     "affgw_conv_tc_prefer_shift": [_I],
     "affgw_operand_planes_bytes": [_L, _I, _I],
     "affgw_split_planes": [_P, _I, _P, _L, _I, _I, _I, _I, _I, _P],

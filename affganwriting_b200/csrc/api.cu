@@ -33,11 +33,12 @@ int wgrad_shift_block_n(int cout);
 int conv_shift_ok(const ConvGeom& g);
 void conv_shift_frame(const ConvGeom& g, int channels, PosFrame& f);
 int split_positions(const void* src, int dt, void* planes, const PosFrame& f, int Hs, int Ws, int C, int pitch, int up, int oy0,
-                    int ox0, int pad_mode, int pre_act, int passes, float* colsum, cudaStream_t st);
+                    int ox0, int pad_mode, int pre_act, int passes, float* colsum, int fmt, const float* scale_dev, cudaStream_t st);
+int amax_scale(const float* x, long long n, float* out2, unsigned* ws, cudaStream_t st);
 int conv_pos_tc(const void* x_planes, const PosFrame& f, const void* w_packed, const float* bias, const void* addend, void* y,
                 int K, int q_shift, int oy0, int ox0, int OH, int OW, int Cout, int out_pitch, int post_act, int passes,
-                cudaStream_t st);
-int pack_weight_shift(const float* w, void* out, int Cout, int Cin, int K, int ipad, int transpose_flip, int passes,
+                int fmt, const float* alpha_dev, cudaStream_t st);
+int pack_weight_shift(const float* w, void* out, int Cout, int Cin, int K, int ipad, int transpose_flip, int passes, int fmt,
                       cudaStream_t st);
 long long pack_weight_shift_bytes(int Cout, int Cin, int K, int ipad, int transpose_flip, int passes);
 // conv_thin.cu
@@ -52,7 +53,7 @@ long long conv_wgrad_tc_ws_bytes(const ConvGeom& g);
 int conv_wgrad_tc(const void* x_planes, long long x_plane, const void* dy_planes, long long dy_plane, float* dw, void* workspace,
                   const ConvGeom& g, int cin_w, int passes, cudaStream_t st);
 int conv_wgrad_pos(const void* x_planes, const PosFrame& fx, const void* dy_planes, const PosFrame& fy, float* dw, void* workspace,
-                   const ConvGeom& g, int cin_w, int passes, cudaStream_t st);
+                   const ConvGeom& g, int cin_w, int passes, int fmt, const float* alpha_dev, cudaStream_t st);
 // norm.cu
 int norm_stats(const void* x, int dt, float* ws, float* mean, float* rstd, float* var_unbiased, int G, long long P, int C,
                float eps, int unbiased, cudaStream_t st);
@@ -202,15 +203,21 @@ long long affgw_pack_weight_tc_bytes(int Cout, int Cin, int KH, int KW, int i_pa
     if (layout != AFFGW_WLAYOUT_IM2COL) return -1;
     return pack_weight_tc_bytes(Cout, Cin, KH, KW, i_pad, transpose_flip, passes);
 }
-int affgw_pack_weight_tc(const float* w, void* out, int Cout, int Cin, int KH, int KW, int i_pad, int transpose_flip,
-                         int passes, int layout, void* stream) {
+int affgw_pack_weight_tc_fmt(const float* w, void* out, int Cout, int Cin, int KH, int KW, int i_pad, int transpose_flip,
+                             int passes, int layout, int operand_fmt, void* stream) {
     AFFGW_CHECK(w && out, "pack_weight_tc: null pointer");
     AFFGW_CHECK(layout == AFFGW_WLAYOUT_IM2COL || layout == AFFGW_WLAYOUT_SHIFT, "pack_weight_tc: bad layout");
+    AFFGW_CHECK(operand_fmt == AFFGW_FMT_BF16 || (operand_fmt == AFFGW_FMT_F16 && layout == AFFGW_WLAYOUT_SHIFT),
+                "pack_weight_tc: fp16 operands are implemented by the position-space kernels only");
     if (layout == AFFGW_WLAYOUT_SHIFT) {
         AFFGW_CHECK(KH == KW, "pack_weight_tc: the shifted kernel takes square filters");
-        return pack_weight_shift(w, out, Cout, Cin, KH, i_pad, transpose_flip, passes, S(stream));
+        return pack_weight_shift(w, out, Cout, Cin, KH, i_pad, transpose_flip, passes, operand_fmt, S(stream));
     }
     return pack_weight_tc(w, out, Cout, Cin, KH, KW, i_pad, transpose_flip, passes, S(stream));
+}
+int affgw_pack_weight_tc(const float* w, void* out, int Cout, int Cin, int KH, int KW, int i_pad, int transpose_flip,
+                         int passes, int layout, void* stream) {
+    return affgw_pack_weight_tc_fmt(w, out, Cout, Cin, KH, KW, i_pad, transpose_flip, passes, layout, AFFGW_FMT_BF16, stream);
 }
 long long affgw_operand_planes_bytes(long long rows, int c_store, int passes) {
     if (rows <= 0 || c_store <= 0 || c_store % 8 != 0 || !passes_ok(passes)) return -1;
@@ -227,7 +234,8 @@ int affgw_split_planes(const void* x, int x_dtype, void* planes, long long rows,
 static int make_tc_geom(const affgw_conv_desc* d, ConvGeom& g) {
     if (int rc = make_geom(d, g)) return rc;
     AFFGW_CHECK(passes_ok(d->passes), "conv (tcgen05): passes must be 1 or 3");
-    AFFGW_CHECK(d->x_dtype == AFFGW_BF16 && d->w_dtype == AFFGW_BF16, "conv (tcgen05): operands are bf16 planes / tiles");
+    AFFGW_CHECK(d->operand_fmt == AFFGW_FMT_BF16 || d->operand_fmt == AFFGW_FMT_F16, "conv (tcgen05): operand_fmt must be 0 (bf16) or 1 (fp16)");
+    AFFGW_CHECK(d->x_dtype == AFFGW_BF16 && d->w_dtype == AFFGW_BF16, "conv (tcgen05): operands are 16-bit planes / tiles");
     AFFGW_CHECK(d->pre_act == ACT_NONE, "conv (tcgen05): the pre-activation is applied by affgw_split_planes");
     g.Cin = d->in_pitch;
     g.Ktot = g.KH * g.KW * g.Cin;
@@ -261,8 +269,9 @@ int affgw_conv2d_fwd(const void* x, const void* w, const float* bias, const void
             PosFrame f;
             conv_shift_frame(g, d->Cin, f);
             return conv_pos_tc(x, f, w, bias, addend, y, d->KH, 0, 0, 0, d->Ho, d->Wo, d->Cout, d->out_pitch, d->post_act,
-                               d->passes, S(stream));
+                               d->passes, d->operand_fmt, nullptr, S(stream));
         }
+        AFFGW_CHECK(d->operand_fmt == AFFGW_FMT_BF16, "conv2d_fwd: fp16 operands are implemented by the position-space kernels only");
         const long long plane = (long long)d->N * d->H * d->W * d->in_pitch;
         return conv_fwd_tc(x, plane, w, bias, addend, y, d->y_dtype, g, d->passes, S(stream));
     }
@@ -376,8 +385,21 @@ long long affgw_position_planes_bytes(const affgw_pos_frame* f, int passes) {
     if (!f || !passes_ok(passes) || f->G <= 0 || f->QA <= 0) return -1;
     return (long long)(passes == 3 ? 2 : 1) * f->G * f->QA * 16;
 }
+int affgw_amax_scale(const float* x, long long n, float* scale2, void* workspace4, void* stream) {
+    AFFGW_CHECK(x && scale2 && workspace4 && n > 0, "amax_scale: bad argument");
+    AFFGW_CHECK(((uintptr_t)x & 15) == 0, "amax_scale: the tensor must be 16-byte aligned");
+    return amax_scale(x, n, scale2, (unsigned*)workspace4, S(stream));
+}
 int affgw_split_positions(const void* src, int dtype, void* planes, const affgw_pos_frame* f, int Hs, int Ws, int C, int pitch,
                           int upsample, int oy0, int ox0, int pad_mode, int pre_act, int passes, float* colsum, void* stream) {
+    return affgw_split_positions_fmt(src, dtype, planes, f, Hs, Ws, C, pitch, upsample, oy0, ox0, pad_mode, pre_act, passes, colsum,
+                                     AFFGW_FMT_BF16, nullptr, stream);
+}
+int affgw_split_positions_fmt(const void* src, int dtype, void* planes, const affgw_pos_frame* f, int Hs, int Ws, int C, int pitch,
+                              int upsample, int oy0, int ox0, int pad_mode, int pre_act, int passes, float* colsum,
+                              int operand_fmt, const float* scale_dev, void* stream) {
+    AFFGW_CHECK(operand_fmt == AFFGW_FMT_BF16 || operand_fmt == AFFGW_FMT_F16, "split_positions: bad operand format");
+    AFFGW_CHECK(scale_dev == nullptr || operand_fmt == AFFGW_FMT_F16, "split_positions: a scale is for fp16 planes");
     AFFGW_CHECK(src && planes && f && dt_ok(dtype) && passes_ok(passes), "split_positions: bad argument");
     AFFGW_CHECK(Hs > 0 && Ws > 0 && C > 0 && pitch >= C && (upsample == 1 || upsample == 2), "split_positions: bad source");
     AFFGW_CHECK(pad_mode >= 0 && pad_mode <= 2 && pre_act >= 0 && pre_act <= 3, "split_positions: bad mode");
@@ -388,7 +410,7 @@ int affgw_split_positions(const void* src, int dtype, void* planes, const affgw_
     AFFGW_CHECK(colsum == nullptr || (upsample == 1 && pad_mode == PAD_ZERO && pre_act == ACT_NONE),
                 "split_positions: the fused column sum is for dY planes (no padding copies, no activation)");
     return split_positions(src, dtype, planes, import_frame(f), Hs, Ws, C, pitch, upsample, oy0, ox0, pad_mode, pre_act, passes,
-                           colsum, S(stream));
+                           colsum, operand_fmt, scale_dev, S(stream));
 }
 
 long long affgw_conv2d_dgrad_ws_bytes(const affgw_conv_desc* d) {
@@ -402,6 +424,10 @@ long long affgw_conv2d_dgrad_ws_bytes(const affgw_conv_desc* d) {
 
 int affgw_conv2d_dgrad(const void* dy, const void* wt, const void* x, void* dx, void* workspace,
                        const affgw_conv_desc* d, void* stream) {
+    return affgw_conv2d_dgrad_scaled(dy, wt, x, dx, workspace, d, nullptr, stream);
+}
+int affgw_conv2d_dgrad_scaled(const void* dy, const void* wt, const void* x, void* dx, void* workspace,
+                              const affgw_conv_desc* d, const float* inv_scale_dev, void* stream) {
     AFFGW_CHECK(d && dy && wt && dx, "conv2d_dgrad: null pointer");
     affgw_conv_desc dd;
     bool direct;
@@ -426,11 +452,12 @@ int affgw_conv2d_dgrad(const void* dy, const void* wt, const void* x, void* dx, 
             const int qs = -(d->KH - 1) * (fy.Wp + 1);
             if (direct)
                 rc = conv_pos_tc(dy, fy, wt, nullptr, nullptr, dx, d->KH, qs, d->pad, d->pad, d->H, d->W, d->Cin, d->Cin, ACT_NONE,
-                                 d->passes, S(stream));
+                                 d->passes, d->operand_fmt, inv_scale_dev, S(stream));
             else
                 rc = conv_pos_tc(dy, fy, wt, nullptr, nullptr, workspace, d->KH, qs, 0, 0, Hp, Wp, d->Cin, d->Cin, ACT_NONE,
-                                 d->passes, S(stream));
+                                 d->passes, d->operand_fmt, inv_scale_dev, S(stream));
         } else {
+            AFFGW_CHECK(d->operand_fmt == AFFGW_FMT_BF16 && !inv_scale_dev, "conv2d_dgrad: fp16 operands are implemented by the position-space kernels only");
             AFFGW_CHECK(conv_tc_ok(g) > 0, "conv2d_dgrad: shape not supported by the tcgen05 kernel");
             const long long plane = (long long)dd.N * dd.H * dd.W * dd.in_pitch;
             rc = conv_fwd_tc(dy, plane, wt, nullptr, nullptr, out, gdt, g, d->passes, S(stream));
@@ -465,6 +492,10 @@ long long affgw_conv2d_wgrad_ws_bytes(const affgw_conv_desc* d) {
 }
 
 int affgw_conv2d_wgrad(const void* x, const void* dy, float* dw, void* workspace, const affgw_conv_desc* d, void* stream) {
+    return affgw_conv2d_wgrad_scaled(x, dy, dw, workspace, d, nullptr, stream);
+}
+int affgw_conv2d_wgrad_scaled(const void* x, const void* dy, float* dw, void* workspace, const affgw_conv_desc* d,
+                              const float* inv_scale_dev, void* stream) {
     ConvGeom g;
     if (int rc = make_geom(d, g)) return rc;
     AFFGW_CHECK(x && dy && dw, "conv2d_wgrad: null pointer");
@@ -477,8 +508,9 @@ int affgw_conv2d_wgrad(const void* x, const void* dy, float* dw, void* workspace
             ConvGeom gf;
             PosFrame fx, fy;
             if (int rc2 = shift_frames(d, gf, fx, fy)) return rc2;
-            return conv_wgrad_pos(x, fx, dy, fy, dw, workspace, g, d->Cin, d->passes, S(stream));
+            return conv_wgrad_pos(x, fx, dy, fy, dw, workspace, g, d->Cin, d->passes, d->operand_fmt, inv_scale_dev, S(stream));
         }
+        AFFGW_CHECK(d->operand_fmt == AFFGW_FMT_BF16 && !inv_scale_dev, "conv2d_wgrad: fp16 operands are implemented by the position-space kernels only");
         AFFGW_CHECK(conv_wgrad_tc_ok(g), "conv2d_wgrad: shape not supported by the tcgen05 kernel");
         const long long xpl = (long long)d->N * d->H * d->W * d->in_pitch;
         const long long ypl = g.M * d->out_pitch;

@@ -27,6 +27,7 @@
 // Replaces the cuDNN convolutions (forward and backward) behind reference blocks.py:148 /
 // vgg_tro_channel3_modi.py:47 / modules_tro.py:594-603 and loss.backward() (network_tro.py:55,102,113,129).
 #include <cuda.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 #include "pos_frame.cuh"
@@ -72,6 +73,9 @@ struct ShArgs {
     int n_tiles;
     int total_tiles;
     int vec_ok;
+    int fmt;                   // operand format of the planes / packed weights: 0 = bf16, 1 = fp16
+    float alpha;               // result = accumulator * alpha * (alpha_dev ? *alpha_dev : 1): undoes the power-of-two operand
+    const float* alpha_dev;    // scales of the fp16 planes (weights x 2^8, dY x a per-tensor scale kept in device memory)
 };
 
 // un-swizzled shared-memory matrix descriptors (core matrices of 8 rows x 16 bytes)
@@ -83,10 +87,11 @@ __device__ __forceinline__ uint64_t make_nosw_desc(uint32_t smem_addr, uint32_t 
     d |= 1ull << 46;                                      // descriptor version (sm_100)
     return d;
 }
-// kind::f16, D = f32, A = B = bf16, M = 128, N = n; mn_major sets the A and B major bits (wgrad)
-__host__ __device__ constexpr uint32_t make_idesc(int n, bool mn_major) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | (mn_major ? ((1u << 15) | (1u << 16)) : 0u) | ((uint32_t)(n >> 3) << 17) |
-           ((uint32_t)(128 >> 4) << 24);
+// kind::f16, D = f32, A and B both bf16 (fmt 0) or both fp16 (fmt 1: the two formats cannot be mixed in one instruction -
+// measured: illegal instruction, scripts/probes/mixed_mma_probe.cu), M = 128, N = n; mn_major sets the A and B major bits (wgrad)
+__host__ __device__ constexpr uint32_t make_idesc(int n, bool mn_major, int fmt = 0) {
+    return (1u << 4) | (fmt ? 0u : ((1u << 7) | (1u << 10))) | (mn_major ? ((1u << 15) | (1u << 16)) : 0u) |
+           ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 
 // ---------------------------------------------------------------------------------------- forward / input gradient
@@ -172,8 +177,8 @@ conv_shift_tcgen05_kernel(const __grid_constant__ ShArgs a) {
     } else if (warp == MMA_WARP) {
         // ============================== MMA issuer ==============================
         {   // every lane runs the loops (warp-uniform), one elected lane issues: see umma_bf16_elect
-            constexpr uint32_t idesc = make_idesc(BN, false);
-            constexpr uint32_t idesc2 = make_idesc(PK ? 2 * BN : BN, false);
+            const uint32_t idesc = make_idesc(BN, false, a.fmt);
+            const uint32_t idesc2 = make_idesc(PK ? 2 * BN : BN, false, a.fmt);
             const uint32_t b_tap = (uint32_t)NPL * 2u * BN * 16u;   // bytes of one tap's [cgroup][plane][BN][8] weight image
             uint32_t it = 0, tl = 0;
             for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x, ++tl) {
@@ -222,6 +227,7 @@ conv_shift_tcgen05_kernel(const __grid_constant__ ShArgs a) {
     } else {
         // ============================== epilogue ==============================
         const int wq = warp & 3;          // TMEM lane quarter this warp may read
+        const float alpha = a.alpha * (a.alpha_dev ? __ldg(a.alpha_dev) : 1.f);
         uint32_t tl = 0;
         for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x, ++tl) {
             const uint32_t acc = tl % NBUF, acc_ph = (tl / NBUF) & 1u;
@@ -257,7 +263,7 @@ conv_shift_tcgen05_kernel(const __grid_constant__ ShArgs a) {
                         if (a.vec_ok) {
                             float v[16];
 #pragma unroll
-                            for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(raw[i]) + (a.bias ? __ldg(a.bias + nb + i) : 0.f);
+                            for (int i = 0; i < 16; ++i) v[i] = fmaf(__uint_as_float(raw[i]), alpha, a.bias ? __ldg(a.bias + nb + i) : 0.f);
                             if (a.addend) {
                                 const float4* ad = reinterpret_cast<const float4*>(a.addend + m * a.out_pitch + nb);
 #pragma unroll
@@ -277,7 +283,7 @@ conv_shift_tcgen05_kernel(const __grid_constant__ ShArgs a) {
 #pragma unroll
                             for (int i = 0; i < 16; ++i) {
                                 if (nb + i < a.Cout) {
-                                    float rr = __uint_as_float(raw[i]) + (a.bias ? __ldg(a.bias + nb + i) : 0.f);
+                                    float rr = fmaf(__uint_as_float(raw[i]), alpha, a.bias ? __ldg(a.bias + nb + i) : 0.f);
                                     if (a.addend) rr += a.addend[m * a.out_pitch + nb + i];
                                     yrow[i] = act_apply(rr, a.post_act);
                                 }
@@ -301,8 +307,17 @@ conv_shift_tcgen05_kernel(const __grid_constant__ ShArgs a) {
 
 // weights: OIHW fp32 -> [n_tile][ky][cb][kx][cgroup][plane][BN][8] bf16 (plane 1 = bf16 remainder, when npl == 2): inside a
 // channel group the BN remainder rows follow the BN leading rows, so one K-major descriptor covers [w_hi | w_lo] as 2 BN rows
+// fmt 1: fp16 planes of w * 2^8 (typical weights ~1e-2 would leave the remainder plane in fp16's subnormal range; the kernels
+// multiply the accumulator by 2^-8, exactly)
+constexpr float F16_W_SCALE = 256.f;
+__device__ __forceinline__ uint16_t f16_bits(float v) {
+    const __half h = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
+    return __half_as_ushort(h);
+}
+__device__ __forceinline__ float f16_val(uint16_t b) { return __half2float(__ushort_as_half(b)); }
+
 __global__ void pack_weight_shift_kernel(const float* __restrict__ w, bf16* __restrict__ out, int Cout, int Cin, int K,
-                                         int transpose_flip, int BN, int ntiles, int CB, int npl) {
+                                         int transpose_flip, int BN, int ntiles, int CB, int npl, int fmt) {
     const int Od = transpose_flip ? Cin : Cout, Id = transpose_flip ? Cout : Cin;
     const long long total = (long long)ntiles * K * CB * K * 2 * BN * 8;      // one plane
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
@@ -323,11 +338,18 @@ __global__ void pack_weight_shift_kernel(const float* __restrict__ w, bf16* __re
             else
                 v = w[(((long long)o * Cin + i) * K + ky) * K + kx];
         }
-        const bf16 hi = __float2bfloat16_rn(v);
         const long long tap = (((long long)nt * K + ky) * CB + cb) * K + kx;
         bf16* dst = out + ((((tap * 2 + cgp) * npl) * BN + n) * 8 + e);
-        dst[0] = hi;
-        if (npl == 2) dst[(long long)BN * 8] = __float2bfloat16_rn(v - __bfloat162float(hi));
+        if (fmt) {
+            const float sv = v * F16_W_SCALE;
+            const uint16_t hb = f16_bits(sv);
+            reinterpret_cast<uint16_t*>(dst)[0] = hb;
+            if (npl == 2) reinterpret_cast<uint16_t*>(dst)[(long long)BN * 8] = f16_bits(sv - f16_val(hb));
+        } else {
+            const bf16 hi = __float2bfloat16_rn(v);
+            dst[0] = hi;
+            if (npl == 2) dst[(long long)BN * 8] = __float2bfloat16_rn(v - __bfloat162float(hi));
+        }
     }
 }
 
@@ -340,7 +362,8 @@ template <typename T, int TG>
 __global__ void __launch_bounds__(256)
 split_positions_kernel(const T* __restrict__ src, bf16* __restrict__ planes, int N, int Hs, int Ws, int C, int pitch, int up,
                        int oy0, int ox0, int pad_mode, int pre_act, int Hp, int Wp, int G, int lead, int QA, int npl,
-                       float* __restrict__ colsum, const FastDiv div_wp, const FastDiv div_hp) {
+                       float* __restrict__ colsum, const FastDiv div_wp, const FastDiv div_hp, int fmt,
+                       const float* __restrict__ scale_dev) {
     constexpr int TP = 1024 / TG;                     // positions per tile: a tile is always 1024 (position, group) items
     __shared__ uint4 tile[2][TG * (TP + 1)];          // [plane][group][position], +1 column against bank conflicts
     __shared__ float red[8][TG * 8];
@@ -352,6 +375,7 @@ split_positions_kernel(const T* __restrict__ src, bf16* __restrict__ planes, int
     float csum[8];                                    // per-channel sums of this thread's items (bias gradient)
 #pragma unroll
     for (int i = 0; i < 8; ++i) csum[i] = 0.f;
+    const float scale = scale_dev ? __ldg(scale_dev) : 1.f;       // fp16 dY planes: per-tensor power-of-two scale
     for (int tx = blockIdx.x; tx < n_tiles; tx += gridDim.x) {
         const int p0 = tx * TP;                       // stored position (lead included)
 #pragma unroll
@@ -400,13 +424,26 @@ split_positions_kernel(const T* __restrict__ src, bf16* __restrict__ planes, int
                 for (int i = 0; i < 8; ++i) csum[i] += v[i];
             }
             uint4 hi, lo;
-            __nv_bfloat162* hh = reinterpret_cast<__nv_bfloat162*>(&hi);
-            __nv_bfloat162* ll = reinterpret_cast<__nv_bfloat162*>(&lo);
+            if (fmt) {
+                __half2* hh = reinterpret_cast<__half2*>(&hi);
+                __half2* ll = reinterpret_cast<__half2*>(&lo);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                hh[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-                const float2 f = __bfloat1622float2(hh[i]);
-                ll[i] = __floats2bfloat162_rn(v[2 * i] - f.x, v[2 * i + 1] - f.y);
+                for (int i = 0; i < 4; ++i) {
+                    const float a0 = fminf(fmaxf(v[2 * i] * scale, -65504.f), 65504.f);
+                    const float a1 = fminf(fmaxf(v[2 * i + 1] * scale, -65504.f), 65504.f);
+                    hh[i] = __floats2half2_rn(a0, a1);
+                    const float2 f = __half22float2(hh[i]);
+                    ll[i] = __floats2half2_rn(a0 - f.x, a1 - f.y);
+                }
+            } else {
+                __nv_bfloat162* hh = reinterpret_cast<__nv_bfloat162*>(&hi);
+                __nv_bfloat162* ll = reinterpret_cast<__nv_bfloat162*>(&lo);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    hh[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+                    const float2 f = __bfloat1622float2(hh[i]);
+                    ll[i] = __floats2bfloat162_rn(v[2 * i] - f.x, v[2 * i + 1] - f.y);
+                }
             }
             tile[0][gl * (TP + 1) + pi] = hi;
             tile[1][gl * (TP + 1) + pi] = lo;
@@ -549,7 +586,7 @@ void conv_shift_frame(const ConvGeom& g, int channels, PosFrame& f) {
 }
 
 int split_positions(const void* src, int dt, void* planes, const PosFrame& f, int Hs, int Ws, int C, int pitch, int up, int oy0,
-                    int ox0, int pad_mode, int pre_act, int passes, float* colsum, cudaStream_t st) {
+                    int ox0, int pad_mode, int pre_act, int passes, float* colsum, int fmt, const float* scale_dev, cudaStream_t st) {
     const int npl = passes == 3 ? 2 : 1;
     if (f.QA >= (1LL << 31) || (long long)f.N * Hs * Ws >= (1LL << 31)) {
         affgw_set_error("split_positions: frame too large for 32-bit position arithmetic");
@@ -559,7 +596,8 @@ int split_positions(const void* src, int dt, void* planes, const PosFrame& f, in
 #define AFFGW_SPLIT(T, TGV)                                                                                               \
     split_positions_kernel<T, TGV><<<dim3((unsigned)min((QA + 1024 / TGV - 1) / (1024 / TGV), 148 * 8), (unsigned)((f.G + TGV - 1) / TGV)), \
                                      256, 0, st>>>((const T*)src, (bf16*)planes, f.N, Hs, Ws, C, pitch, up, oy0, ox0, pad_mode, \
-                                                   pre_act, f.Hp, f.Wp, f.G, f.lead, QA, npl, colsum, make_fastdiv(f.Wp), make_fastdiv(f.Hp))
+                                                   pre_act, f.Hp, f.Wp, f.G, f.lead, QA, npl, colsum, make_fastdiv(f.Wp), make_fastdiv(f.Hp), \
+                                                   fmt, scale_dev)
     if (dt == AFFGW_F32) {
         if (f.G <= 2) AFFGW_SPLIT(float, 2);
         else if (f.G <= 4) AFFGW_SPLIT(float, 4);
@@ -586,7 +624,7 @@ long long pack_weight_shift_bytes(int Cout, int Cin, int K, int ipad, int transp
     return ntiles * K * CB * K * (passes == 3 ? 2 : 1) * 2 * bn * 8 * 2;
 }
 
-int pack_weight_shift(const float* w, void* out, int Cout, int Cin, int K, int ipad, int transpose_flip, int passes,
+int pack_weight_shift(const float* w, void* out, int Cout, int Cin, int K, int ipad, int transpose_flip, int passes, int fmt,
                       cudaStream_t st) {
     if (pack_weight_shift_bytes(Cout, Cin, K, ipad, transpose_flip, passes) <= 0) {
         affgw_set_error("pack_weight_shift: bad configuration (i_pad %d, passes %d)", ipad, passes);
@@ -598,7 +636,7 @@ int pack_weight_shift(const float* w, void* out, int Cout, int Cin, int K, int i
     const long long total = (long long)ntiles * K * CB * K * 2 * bn * 8;
     const int blocks = (int)min((long long)148 * 8, (total + 255) / 256);
     pack_weight_shift_kernel<<<blocks, 256, 0, st>>>(w, (bf16*)out, Cout, Cin, K, transpose_flip, bn, ntiles, CB,
-                                                     passes == 3 ? 2 : 1);
+                                                     passes == 3 ? 2 : 1, fmt);
     AFFGW_LAUNCH_CHECK("pack_weight_shift");
     return 0;
 }
@@ -609,7 +647,7 @@ int pack_weight_shift(const float* w, void* out, int Cout, int Cin, int K, int i
 //   dgrad   : q_shift = -(K-1)(Wp+1),    (pad, pad, H, W) for the zero-pad crop or (0, 0, Hp, Wp) for the full frame
 int conv_pos_tc(const void* x_planes, const PosFrame& f, const void* w_packed, const float* bias, const void* addend, void* y,
                 int K, int q_shift, int oy0, int ox0, int OH, int OW, int Cout, int out_pitch, int post_act, int passes,
-                cudaStream_t st) {
+                int fmt, const float* alpha_dev, cudaStream_t st) {
     ShPlan p;
     const int npl = passes == 3 ? 2 : 1;
     const int bn0 = shift_block_n(Cout);
@@ -639,6 +677,9 @@ int conv_pos_tc(const void* x_planes, const PosFrame& f, const void* w_packed, c
     a.total_tiles = (int)((q_last / (mt * 128) + 1) * a.n_tiles);
     a.vec_ok = (Cout % 16 == 0) && (out_pitch % 4 == 0) && (((uintptr_t)y) % 16 == 0) &&
                (!addend || ((uintptr_t)addend) % 16 == 0);
+    a.fmt = fmt;
+    a.alpha = fmt ? 1.f / F16_W_SCALE : 1.f;        // the packed fp16 weights carry 2^8
+    a.alpha_dev = alpha_dev;
     if (passes == 3) {
         switch (p.bn) {
             case 16: return launch_shift<16, 3>(a, p.smem_bytes, st);
@@ -686,6 +727,8 @@ struct WsArgs {
     int n_co_blocks;
     int chunks_total, chunks_per_split;
     int a_bytes, b_bytes, stages;
+    int fmt;                                 // 0 = bf16 planes, 1 = fp16 planes
+    const float* alpha_dev;                  // 1 / (scale of the fp16 dY planes), device memory; nullptr = 1
 };
 
 template <int BN, int NPASS>
@@ -777,8 +820,8 @@ conv_wgrad_shift_kernel(const __grid_constant__ WsArgs a, const __grid_constant_
     } else if (warp == MMA_WARP) {
         // ============================== MMA issuer ==============================
         {   // every lane runs the loops (warp-uniform), one elected lane issues: see umma_bf16_elect
-            constexpr uint32_t idesc = make_idesc(BN, true);
-            constexpr uint32_t idesc2 = make_idesc(PK ? 2 * BN : BN, true);
+            const uint32_t idesc = make_idesc(BN, true, a.fmt);
+            const uint32_t idesc2 = make_idesc(PK ? 2 * BN : BN, true, a.fmt);
             for (int st = 0; st < nst; ++st) {
                 const int s = st % stages;
                 const uint32_t ph = (uint32_t)(st / stages) & 1u;
@@ -824,6 +867,7 @@ conv_wgrad_shift_kernel(const __grid_constant__ WsArgs a, const __grid_constant_
         tc_fence_after();
         const int m = wq * 32 + lane;                        // accumulator row
         const int taps = a.K * a.K;
+        const float alpha = a.alpha_dev ? __ldg(a.alpha_dev) : 1.f;
         const int nacc = a.TPM == 1 ? nkx : (nkx + a.TPM - 1) / a.TPM;
         if (nst > 0) {
             for (int j = 0; j < nacc; ++j) {
@@ -857,7 +901,7 @@ conv_wgrad_shift_kernel(const __grid_constant__ WsArgs a, const __grid_constant_
                     if (rok) {
 #pragma unroll
                         for (int i = 0; i < 16; ++i)
-                            if (nb + i < a.Cout) atomicAdd(wbase + (size_t)(nb + i) * taps * a.Cs, __uint_as_float(raw[i]));
+                            if (nb + i < a.Cout) atomicAdd(wbase + (size_t)(nb + i) * taps * a.Cs, __uint_as_float(raw[i]) * alpha);
                     }
                 }
             }
@@ -928,7 +972,7 @@ int launch_wg_shift(const WsArgs& args, const CUtensorMap& tmx, const CUtensorMa
 // x planes: frame fx; dY planes: same frame positions, fy.G groups.
 // ws: [Cout][K*K][cs] fp32, zeroed by the caller (cs = row length, >= the real input channels).
 int conv_wgrad_pos_tc(const void* x_planes, const PosFrame& fx, const void* dy_planes, const PosFrame& fy, float* ws, int K,
-                      int Cout, int cs, int Ho, int Wo, int passes, cudaStream_t st) {
+                      int Cout, int cs, int Ho, int Wo, int passes, int fmt, const float* alpha_dev, cudaStream_t st) {
     const int npl = passes == 3 ? 2 : 1;
     const int bn = wgrad_shift_block_n(Cout);
     WsArgs a;
@@ -970,6 +1014,7 @@ int conv_wgrad_pos_tc(const void* x_planes, const PosFrame& fx, const void* dy_p
     a.x = (const bf16*)x_planes; a.dy = (const bf16*)dy_planes; a.ws = ws;
     a.K = K; a.Wp = fx.Wp; a.Gx = fx.G; a.Gy = fy.G; a.lead = fx.lead; a.QA = fx.QA;
     a.Cs = cs; a.Cout = Cout;
+    a.fmt = fmt; a.alpha_dev = alpha_dev;
     const int n_ci = (fx.G + 15) / 16;
     a.n_co_blocks = (Cout + bn - 1) / bn;
     const long long q_last = ((long long)(fx.N - 1) * fx.Hp + Ho - 1) * fx.Wp + Wo - 1;
@@ -1002,4 +1047,47 @@ int conv_wgrad_pos_tc(const void* x_planes, const PosFrame& fx, const void* dy_p
         case 64: return launch_wg_shift<64, 1>(a, tmx, tmdy, grid, smem_bytes, st);
         default: return launch_wg_shift<128, 1>(a, tmx, tmdy, grid, smem_bytes, st);
     }
+}
+
+// =====================================================================================================================
+// Per-tensor power-of-two scale of an fp16 dY operand (gradients span many orders of magnitude below fp16's range):
+// scale = 2^floor(log2(2^14 / amax)), so amax * scale lies in [2^13, 2^14); out[0] = scale, out[1] = 1 / scale.
+// =====================================================================================================================
+namespace {
+__global__ void amax_kernel(const float* __restrict__ x, long long n, unsigned* __restrict__ amax_bits) {
+    float m = 0.f;
+    const long long n4 = n / 4;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const float4 v = reinterpret_cast<const float4*>(x)[i];
+        m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+    }
+    if (blockIdx.x == 0) for (long long i = n4 * 4 + threadIdx.x; i < n; i += blockDim.x) m = fmaxf(m, fabsf(x[i]));
+    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0.f && m == m && m < INFINITY) atomicMax(amax_bits, __float_as_uint(m));   // ordered like floats (>= 0)
+}
+__global__ void amax_finalize_kernel(const unsigned* __restrict__ amax_bits, float* __restrict__ out) {
+    const float amax = __uint_as_float(*amax_bits);
+    float s = 1.f;
+    if (amax > 0.f) {
+        int e;
+        frexpf(amax, &e);                       // amax = f * 2^e, f in [0.5, 1)  ->  amax * 2^(14 - e) in [2^13, 2^14)
+        const int k = max(-120, min(120, 14 - e));
+        s = ldexpf(1.f, k);
+    }
+    out[0] = s;
+    out[1] = 1.f / s;
+}
+}  // namespace
+
+int amax_scale(const float* x, long long n, float* out2, unsigned* ws, cudaStream_t st) {
+    if (cudaMemsetAsync(ws, 0, sizeof(unsigned), st) != cudaSuccess) {
+        affgw_set_error("amax_scale: memset failed");
+        return -2;
+    }
+    const int blocks = (int)min((long long)148 * 8, (n / 4 + 255) / 256 + 1);
+    amax_kernel<<<blocks, 256, 0, st>>>(x, n, ws);
+    AFFGW_LAUNCH_CHECK("amax");
+    amax_finalize_kernel<<<1, 1, 0, st>>>(ws, out2);
+    AFFGW_LAUNCH_CHECK("amax_finalize");
+    return 0;
 }

@@ -363,18 +363,18 @@ int conv_wgrad_tc(const void* x_planes, long long x_plane, const void* dy_planes
 
 // conv_shift.cu
 int conv_wgrad_pos_tc(const void* x_planes, const PosFrame& fx, const void* dy_planes, const PosFrame& fy, float* ws, int K,
-                      int Cout, int cs, int Ho, int Wo, int passes, cudaStream_t st);
+                      int Cout, int cs, int Ho, int Wo, int passes, int fmt, const float* alpha_dev, cudaStream_t st);
 
 // position-space weight gradient (conv_shift.cu) + the same workspace reduction / unpack as above;
 // g.Cin = stored channel count of the ws rows, cin_w = channels of the parameter
 int conv_wgrad_pos(const void* x_planes, const PosFrame& fx, const void* dy_planes, const PosFrame& fy, float* dw, void* workspace,
-                   const ConvGeom& g, int cin_w, int passes, cudaStream_t st) {
+                   const ConvGeom& g, int cin_w, int passes, int fmt, const float* alpha_dev, cudaStream_t st) {
     float* ws = (float*)workspace;
     if (cudaMemsetAsync(ws, 0, (size_t)conv_wgrad_tc_ws_bytes(g), st) != cudaSuccess) {
         affgw_set_error("conv_wgrad_pos: memset failed");
         return -2;
     }
-    if (int rc = conv_wgrad_pos_tc(x_planes, fx, dy_planes, fy, ws, g.KH, g.Cout, g.Cin, g.Ho, g.Wo, passes, st)) return rc;
+    if (int rc = conv_wgrad_pos_tc(x_planes, fx, dy_planes, fy, ws, g.KH, g.Cout, g.Cin, g.Ho, g.Wo, passes, fmt, alpha_dev, st)) return rc;
     const int taps = g.KH * g.KW;
     const long long total = (long long)g.Cout * cin_w * taps;
     const int blocks = (int)min((long long)148 * 8, (total + 255) / 256);

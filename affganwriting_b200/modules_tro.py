@@ -48,6 +48,7 @@ def _dis_cla_trunk(n_layers, final_dim):
 
 
 import os as _os
+_DECODER_F16 = _os.environ.get("AFFGW_DECODER_F16", "1") != "0"
 _TRUNK_WGRAD_PASSES = int(_os.environ.get("AFFGW_TRUNK_WGRAD_PASSES", "1"))
 
 
@@ -175,6 +176,13 @@ class Decoder(nn.Module):
         self.model = nn.Sequential(*model)
 
     def forward(self, x):
+        # The decoder's 3x3 / 5x5 convolutions are the last layers in front of the image: forward rounding is amplified least
+        # there, and they run on fp16 operand planes with ONE tensor-core pass per GEMM (ops.operand_format) instead of the
+        # three of the split-bf16 forward; AFFGW_DECODER_F16=0 keeps the bf16 route.
+        with ops.operand_format("f16" if _DECODER_F16 else None):
+            return self._forward(x)
+
+    def _forward(self, x):
         x = ops.input_to_internal(x)
         mods = list(self.model)
         i = 0

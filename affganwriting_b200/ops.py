@@ -16,7 +16,7 @@ import os as _os
 _FUSE_DB = _os.environ.get("AFFGW_FUSE_DB", "1") != "0"
 _THIN = _os.environ.get("AFFGW_THIN", "1") != "0"
 # "passes": tensor-core MMAs per product of (forward, input-gradient, weight-gradient) GEMMs: 3 = split operands, 1 = single
-_state = {"mode": "fp32", "passes": (3, 3, 3), "force_simt": False, "simt_wgrad": False}
+_state = {"mode": "fp32", "passes": (3, 3, 3), "force_simt": False, "simt_wgrad": False, "fmt": None}
 _MODES = {"fp32": (3, 3, 3), "bf16": (3, 1, 1), "bf16x3": (3, 3, 3), "bf16x1": (1, 1, 1)}
 _err_flag = {}
 _profile = {"records": None}
@@ -65,13 +65,15 @@ def stop_kernel_timing(by_shape=False, by_kernel=False):
 
 
 def _kernel_name(d, which, passes):
-    """CUDA kernel function a tcgen05 convolution call lands on (matches the names in an ncu / CUPTI launch list)."""
+    """CUDA kernel function a tcgen05 convolution call lands on (matches the names in an ncu / CUPTI launch list; calls on
+    fp16 operand planes run the same functions and are listed separately with an " f16" suffix)."""
     lay = L.lib().affgw_conv_tc_layout(C.byref(d), int(which == 1))
     bn = L.lib().affgw_conv_tc_tile_n(C.byref(d), which)
     if lay == L.WLAYOUT_SHIFT:
+        sfx = " f16" if d.operand_fmt == L.FMT_F16 else ""
         if which == 2:
-            return "conv_wgrad_shift_kernel<%d, %d>" % (bn, passes)
-        return "conv_shift_tcgen05_kernel<%d, %d, %d>" % (bn, passes, L.lib().affgw_conv_tc_tile_m(C.byref(d), which) // 128)
+            return "conv_wgrad_shift_kernel<%d, %d>%s" % (bn, passes, sfx)
+        return "conv_shift_tcgen05_kernel<%d, %d, %d>%s" % (bn, passes, L.lib().affgw_conv_tc_tile_m(C.byref(d), which) // 128, sfx)
     return ("conv_wgrad_tcgen05_kernel<%d, %d>" if which == 2 else "conv_igemm_tcgen05_kernel<%d, %d, float>") % (bn, passes)
 
 
@@ -131,6 +133,27 @@ class conv_passes:
 
     def __exit__(self, *a):
         _state["passes"] = self.prev
+
+
+class operand_format:
+    """Context manager: the position-space convolutions whose forward is issued inside run on FP16 operand planes, one MMA per
+    product in all three GEMMs (fmt = "f16"), instead of the mode's bf16 planes.  fp16 carries 11 significant bits per plane
+    against bf16's 8, which is what lets the decoder's convolutions - the last layers in front of the image, where forward rounding
+    is amplified least - drop from three tensor-core passes to one inside the accuracy bars (scripts/precision_sweep.py:
+    image 1.8e-3, worst per-tensor gradient cosine 0.99956 at 50 planes, batch 8).  fp16's range is handled by power-of-two
+    scales that the kernels undo exactly: weights x 2^8, dY x a per-tensor 2^k from its max-abs (affgw_amax_scale).
+    Only active in mode 'bf16'; layers the position-space kernels do not take keep the mode's bf16 route."""
+
+    def __init__(self, fmt):
+        assert fmt in (None, "bf16", "f16")
+        self.fmt = None if fmt == "bf16" else fmt
+
+    def __enter__(self):
+        self.prev = _state["fmt"]
+        _state["fmt"] = self.fmt
+
+    def __exit__(self, *a):
+        _state["fmt"] = self.prev
 
 
 class wgrad_passes(conv_passes):
@@ -337,7 +360,7 @@ def _pack(weight, dtype, ipad, flip):
     return _WeightCache.get(weight, ("plain", dtype, ipad, flip), build)
 
 
-def _pack_tc(weight, ipad, flip, passes, layout):
+def _pack_tc(weight, ipad, flip, passes, layout, fmt=0):
     w4 = _w4(weight.detach())
     co, ci, kh, kw = w4.shape
 
@@ -345,11 +368,11 @@ def _pack_tc(weight, ipad, flip, passes, layout):
         nbytes = L.lib().affgw_pack_weight_tc_bytes(co, ci, kh, kw, ipad, int(flip), passes, layout)
         if nbytes <= 0:
             raise RuntimeError("affgw_pack_weight_tc_bytes: bad configuration")
-        out = torch.empty(nbytes // 2, dtype=torch.bfloat16, device=weight.device)
-        L.call("affgw_pack_weight_tc", w4.contiguous().data_ptr(), out.data_ptr(), co, ci, kh, kw, ipad, int(flip), passes,
-               layout, L.stream())
+        out = torch.empty(nbytes // 2, dtype=torch.bfloat16, device=weight.device)      # 16-bit storage (bf16 or fp16 bits)
+        L.call("affgw_pack_weight_tc_fmt", w4.contiguous().data_ptr(), out.data_ptr(), co, ci, kh, kw, ipad, int(flip), passes,
+               layout, fmt, L.stream())
         return out
-    return _WeightCache.get(weight, ("tc", ipad, flip, passes, layout), build)
+    return _WeightCache.get(weight, ("tc", ipad, flip, passes, layout, fmt), build)
 
 
 def prefer_shift_kernel(flag=True):
@@ -376,16 +399,25 @@ def _pos_frames(d):
     return fx, fy
 
 
-def _split_positions(src, frame, hs, ws, c, pitch, up, origin, pad_mode, pre_act, passes, colsum=None):
-    """fp32 NHWC tensor -> planar position planes [1 or 2][G][QA][8] bf16 on the frame of a stride-1 convolution."""
+def _split_positions(src, frame, hs, ws, c, pitch, up, origin, pad_mode, pre_act, passes, colsum=None, fmt=0, scale=None):
+    """fp32 NHWC tensor -> planar position planes [1 or 2][G][QA][8] (bf16, or fp16 of src * scale[0]) on the frame of a
+    stride-1 convolution."""
     nbytes = L.lib().affgw_position_planes_bytes(C.byref(frame), passes)
     if nbytes <= 0:
         raise RuntimeError("affgw_position_planes_bytes: bad frame")
     planes = torch.empty(nbytes // 2, dtype=torch.bfloat16, device=src.device)
-    L.call("affgw_split_positions", src.data_ptr(), L.dt(src), planes.data_ptr(), C.byref(frame), hs, ws, c, pitch, up, origin,
-           origin, L.PAD[pad_mode], L.ACT[pre_act], passes, L.ptr(colsum), L.stream(),
+    L.call("affgw_split_positions_fmt", src.data_ptr(), L.dt(src), planes.data_ptr(), C.byref(frame), hs, ws, c, pitch, up, origin,
+           origin, L.PAD[pad_mode], L.ACT[pre_act], passes, L.ptr(colsum), fmt, L.ptr(scale), L.stream(),
            nbytes=frame.N * hs * ws * c * src.element_size() + _nb(planes))
     return planes
+
+
+def _amax_scale(t):
+    """Device-side per-tensor power-of-two scale of an fp16 operand: -> float32 [2] = (2^k, 2^-k), no host synchronisation."""
+    out = torch.empty(2, dtype=torch.float32, device=t.device)
+    ws = torch.empty(1, dtype=torch.int32, device=t.device)
+    L.call("affgw_amax_scale", t.data_ptr(), t.numel(), out.data_ptr(), ws.data_ptr(), L.stream(), nbytes=_nb(t))
+    return out
 
 
 def _conv_geom(x, weight, cfg):
@@ -411,7 +443,7 @@ def _conv_geom(x, weight, cfg):
     return dict(N=n, H=h, W=w, Cx=cx, pitch=pitch, Cout=co, Cin=ci, KH=kh, KW=kw, Ho=ho, Wo=wo, two_d=x.dim() == 2)
 
 
-def _desc(g, cfg, cin, x_dt, w_dt, y_dt, algo, in_pitch=None, out_pitch=None, passes=1, grad_dt=0, pre_act=None):
+def _desc(g, cfg, cin, x_dt, w_dt, y_dt, algo, in_pitch=None, out_pitch=None, passes=1, grad_dt=0, pre_act=None, fmt=0):
     d = L.ConvDesc()
     d.N, d.H, d.W, d.Cin = g["N"], g["H"], g["W"], cin
     d.Cout, d.KH, d.KW = g["Cout"], g["KH"], g["KW"]
@@ -422,6 +454,7 @@ def _desc(g, cfg, cin, x_dt, w_dt, y_dt, algo, in_pitch=None, out_pitch=None, pa
     d.x_dtype, d.w_dtype, d.y_dtype = x_dt, w_dt, y_dt
     d.algo, d.passes, d.grad_dtype = algo, passes, grad_dt
     d.stride_w = cfg.stride_w
+    d.operand_fmt = fmt
     return d
 
 
@@ -450,6 +483,7 @@ class _Conv2d(Function):
         tag = "%dx%dx%d c%d->%d k%d s%d u%d" % (g["N"], g["H"], g["W"], g["Cin"], g["Cout"], g["KH"], cfg.stride if cfg.stride == cfg.stride_w else cfg.stride * 10 + cfg.stride_w, cfg.upsample)
         planes = None
         thin = False
+        fmt = L.FMT_BF16
         if use_tc and addend is None and cfg.pre_act == "none" and not g["two_d"] and g["pitch"] == g["Cin"] \
                 and (g["Cin"] == 1 or g["Cout"] == 1) and _THIN:
             dthin = _desc(g, cfg, g["Cin"], L.F32, L.F32, L.F32, L.ALGO_SIMT)
@@ -467,13 +501,18 @@ class _Conv2d(Function):
             layout = L.lib().affgw_conv_tc_layout(C.byref(d), 0)
             if not layout:
                 raise RuntimeError("conv2d: tcgen05 kernels refused the shape: " + L.last_error())
+            # fp16 operand planes (ops.operand_format): position-space layers in mode 'bf16' only, single pass in all three GEMMs
+            if _state["fmt"] == "f16" and _state["mode"] == "bf16" and layout == L.WLAYOUT_SHIFT:
+                fmt = L.FMT_F16
+                passes = pd = pw = px = 1
+                d = _desc(g, cfg, g["Cin"], L.BF16, L.BF16, L.F32, L.ALGO_TC, in_pitch=cs, passes=1, pre_act="none", fmt=fmt)
             if layout == L.WLAYOUT_SHIFT:
                 fx, _ = _pos_frames(d)
                 planes = _split_positions(x, fx, g["H"], g["W"], g["Cin"], g["pitch"], cfg.upsample, cfg.pad, cfg.pad_mode,
-                                          cfg.pre_act, px)
+                                          cfg.pre_act, px, fmt=fmt)
             else:
                 planes = _split_planes(x, g["N"] * g["H"] * g["W"], g["Cin"], g["pitch"], px, cfg.pre_act)
-            wp = _pack_tc(weight, cs, False, passes, layout)
+            wp = _pack_tc(weight, cs, False, passes, layout, fmt)
             with _timed("conv_fwd_tcgen05", flops, (tag, _kernel_name(d, 0, passes)) if _profile["records"] is not None else tag):
                 L.call("affgw_conv2d_fwd", planes.data_ptr(), wp.data_ptr(), L.ptr(b32), L.ptr(addend), y.data_ptr(),
                        C.byref(d), L.stream())
@@ -484,6 +523,7 @@ class _Conv2d(Function):
                 L.call("affgw_conv2d_fwd", x.data_ptr(), wp.data_ptr(), L.ptr(b32), L.ptr(addend), y.data_ptr(), C.byref(d),
                        L.stream())
         ctx.cfg, ctx.g, ctx.use_tc, ctx.passes, ctx.tag = cfg, g, use_tc and not thin, (pd, pw, px), tag
+        ctx.fmt = fmt
         ctx.layout = layout if use_tc else 0
         ctx.thin = thin
         ctx.has_bias, ctx.has_addend = bias is not None, addend is not None
@@ -501,6 +541,8 @@ class _Conv2d(Function):
             pw = 1                      # the saved x planes have no remainder plane
         # dY planes feed both backward GEMMs: remainder plane when either runs split operands
         pdy = 3 if ((need_x and pd == 3) or (need_w and pw == 3)) else 1
+        fmt = ctx.fmt
+        dy_scale = None
         dev = ctx.x_meta[1]
         dz = _dense_cl(dy, torch.float32)
         if cfg.post_act != "none":
@@ -527,8 +569,10 @@ class _Conv2d(Function):
                 # dY on the forward convolution's position frame: one split feeds both dgrad and wgrad
                 d0 = _desc(g, fwd_cfg, cin, L.BF16, L.BF16, L.BF16, L.ALGO_TC, in_pitch=cs, out_pitch=cso, passes=pdy)
                 _, fy = _pos_frames(d0)
+                if fmt == L.FMT_F16:
+                    dy_scale = _amax_scale(dz)       # (2^k, 2^-k) in device memory: gradients need a per-tensor scale in fp16
                 dzp = _split_positions(dz, fy, g["Ho"], g["Wo"], cout, cout, 1, 0, "zero", "none", pdy,
-                                       colsum=db if fuse_db else None)
+                                       colsum=db if fuse_db else None, fmt=fmt, scale=dy_scale)
             else:
                 dzp = _split_planes(dz, M, cout, cout, pdy)
         if ctx.thin:
@@ -548,14 +592,15 @@ class _Conv2d(Function):
         if need_w:
             dw = torch.zeros(weight.shape, dtype=torch.float32, device=dev)
             if use_tc and not _state["simt_wgrad"]:
-                d = _desc(g, fwd_cfg, cin, L.BF16, L.BF16, L.BF16, L.ALGO_TC, in_pitch=cs, out_pitch=cso, passes=pw)
+                d = _desc(g, fwd_cfg, cin, L.BF16, L.BF16, L.BF16, L.ALGO_TC, in_pitch=cs, out_pitch=cso, passes=pw, fmt=fmt)
                 ws_bytes = L.lib().affgw_conv2d_wgrad_ws_bytes(C.byref(d))
                 if ws_bytes <= 0:
                     raise RuntimeError("conv2d_wgrad: tcgen05 kernel refused the shape: " + L.last_error())
                 wsb = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
                 with _timed("conv_wgrad_tcgen05", flops,
                             (ctx.tag, _kernel_name(d, 2, pw)) if _profile["records"] is not None else ctx.tag):
-                    L.call("affgw_conv2d_wgrad", planes.data_ptr(), dzp.data_ptr(), dw.data_ptr(), wsb.data_ptr(), C.byref(d), st)
+                    L.call("affgw_conv2d_wgrad_scaled", planes.data_ptr(), dzp.data_ptr(), dw.data_ptr(), wsb.data_ptr(), C.byref(d),
+                           None if dy_scale is None else dy_scale.data_ptr() + 4, st)
             else:
                 if x is None:
                     raise RuntimeError("conv2d backward: the CUDA-core wgrad needs the saved fp32 input")
@@ -569,11 +614,11 @@ class _Conv2d(Function):
                 else:
                     dx = empty_cl(g["N"], cin, g["H"], g["W"], torch.float32, dev)
                 d = _desc(g, fwd_cfg, cin, L.BF16, L.BF16, L.BF16, L.ALGO_TC, in_pitch=cs, out_pitch=cso, passes=pd,
-                          grad_dt=L.F32)
+                          grad_dt=L.F32, fmt=fmt)
                 layout = L.lib().affgw_conv_tc_layout(C.byref(d), 1)
                 if not layout:
                     raise RuntimeError("conv2d_dgrad: tcgen05 kernels refused the shape: " + L.last_error())
-                wt = _pack_tc(weight, cso, True, pd, layout)
+                wt = _pack_tc(weight, cso, True, pd, layout, fmt)
                 base = dx
             else:
                 if g["Cx"] != cin and not (cfg.pad_mode == "zero" and cfg.upsample == 1 and cfg.pre_act == "none"):
@@ -595,8 +640,8 @@ class _Conv2d(Function):
             src = dzp if use_tc else dz
             with _timed("conv_dgrad_tcgen05" if use_tc else "conv_dgrad_simt", flops,
                         (ctx.tag, _kernel_name(d, 1, pd)) if (use_tc and _profile["records"] is not None) else ctx.tag):
-                L.call("affgw_conv2d_dgrad", src.data_ptr(), wt.data_ptr(), L.ptr(x), base.data_ptr(), L.ptr(ws),
-                       C.byref(d), st)
+                L.call("affgw_conv2d_dgrad_scaled", src.data_ptr(), wt.data_ptr(), L.ptr(x), base.data_ptr(), L.ptr(ws),
+                       C.byref(d), None if dy_scale is None else dy_scale.data_ptr() + 4, st)
             if use_tc and g["Cx"] != cin:      # the weight reads only the first `cin` channels of a wider input
                 full = torch.zeros(ctx.x_meta[0], dtype=torch.float32, device=dev).contiguous(memory_format=torch.channels_last) \
                     if len(ctx.x_meta[0]) == 4 else torch.zeros(ctx.x_meta[0], dtype=torch.float32, device=dev)

@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define AFFGW_VERSION 108
+#define AFFGW_VERSION 109
 
 enum { AFFGW_DT_F32 = 0, AFFGW_DT_BF16 = 1 };
 enum { AFFGW_ACT_NONE = 0, AFFGW_ACT_RELU = 1, AFFGW_ACT_LRELU = 2, AFFGW_ACT_TANH = 3 };
@@ -28,6 +28,8 @@ enum { AFFGW_PAD_ZERO = 0, AFFGW_PAD_REFLECT = 1, AFFGW_PAD_REPLICATE = 2 };
 enum { AFFGW_ALGO_AUTO = 0, AFFGW_ALGO_SIMT = 1, AFFGW_ALGO_TCGEN05 = 2 };
 /* packed-weight layouts of the two tcgen05 convolution kernels (affgw_conv_tc_layout tells which one a geometry uses) */
 enum { AFFGW_WLAYOUT_IM2COL = 1, AFFGW_WLAYOUT_SHIFT = 2 };
+/* 16-bit format of the tensor-core operand planes / packed weights of one convolution (both operands of an MMA share it) */
+enum { AFFGW_FMT_BF16 = 0, AFFGW_FMT_F16 = 1 };
 
 /* One convolution = pad -> conv -> (+bias) -> (+addend) -> activation, i.e. the conv part of Conv2dBlock.forward
  * (blocks.py:150-163) with the explicit pad module (blocks.py:113-121), nn.Upsample(scale_factor=2)
@@ -53,6 +55,9 @@ typedef struct affgw_conv_desc {
     int32_t grad_dtype;          /* dtype of dx (and of x when the fold needs the pre-activation derivative)   */
     int32_t stride_w;            /* column stride when it differs from `stride` (rows): Resnet18.py:43 uses
                                     stride=(2, 1); 0 = same as stride                                          */
+    int32_t operand_fmt;         /* AFFGW_FMT_*: bf16 planes (8 significant bits per plane, fp32's range) or fp16 planes
+                                    (11 bits per plane; position-space kernels only).  fp16 weights are packed x 2^8 and fp16
+                                    dY planes x a per-tensor power of two (affgw_amax_scale); the kernels undo both exactly */
 } affgw_conv_desc;
 
 int affgw_version(void);
@@ -89,6 +94,22 @@ typedef struct affgw_pos_frame {
     int32_t N, Hp, Wp, G, lead, reserved;
     int64_t QA;
 } affgw_pos_frame;
+/* fp16 operand route (decoder convolutions, DESIGN.md "precision"): same calls with an operand format.
+ *   affgw_amax_scale          scale2[0] = 2^k with max|x| * 2^k in [2^13, 2^14), scale2[1] = 2^-k (device memory, no host sync);
+ *                             workspace4 = 4 bytes of device scratch
+ *   affgw_split_positions_fmt planes = fp16(v * *scale_dev) (scale_dev may be NULL = 1); the column sum stays unscaled
+ *   affgw_pack_weight_tc_fmt  fp16 tiles of w * 2^8
+ *   affgw_conv2d_*_scaled     result multiplied by *inv_scale_dev (the dY planes' 2^-k) and, for fp16 weights, by 2^-8 */
+int affgw_amax_scale(const float* x, long long n, float* scale2, void* workspace4, void* stream);
+int affgw_split_positions_fmt(const void* src, int dtype, void* planes, const affgw_pos_frame* f, int Hs, int Ws, int C, int pitch,
+                              int upsample, int oy0, int ox0, int pad_mode, int pre_act, int passes, float* colsum,
+                              int operand_fmt, const float* scale_dev, void* stream);
+int affgw_pack_weight_tc_fmt(const float* w_oihw, void* out, int Cout, int Cin, int KH, int KW, int i_pad, int transpose_flip,
+                             int passes, int layout, int operand_fmt, void* stream);
+int affgw_conv2d_dgrad_scaled(const void* dy, const void* wt, const void* x, void* dx, void* workspace,
+                              const affgw_conv_desc* d, const float* inv_scale_dev, void* stream);
+int affgw_conv2d_wgrad_scaled(const void* x, const void* dy, float* dw, void* workspace, const affgw_conv_desc* d,
+                              const float* inv_scale_dev, void* stream);
 int affgw_conv_pos_frames(const affgw_conv_desc* d, affgw_pos_frame* fx, affgw_pos_frame* fy);
 long long affgw_position_planes_bytes(const affgw_pos_frame* f, int passes);
 int affgw_split_positions(const void* src, int dtype, void* planes, const affgw_pos_frame* f, int Hs, int Ws, int C, int pitch,

@@ -30,6 +30,9 @@ W_SCALE = 256.0     # power-of-two scale applied to fp16 weight planes (undone e
 def rnd(t, fmt, passes, scale=1.0):
     if passes == 0:
         return t
+    if scale == "amax":         # dynamic power-of-two scale: amax * s in [2^13, 2^14)  (dY planes in fp16)
+        amax = float(t.abs().max())
+        scale = 2.0 ** int(torch.floor(torch.log2(torch.tensor(16384.0 / max(amax, 1e-30)))))
     cast = (lambda v: v.bfloat16().float()) if fmt == "bf16" else (lambda v: v.clamp(-65504, 65504).half().float())
     s = t * scale
     hi = cast(s)
@@ -52,10 +55,10 @@ class SimConv(torch.autograd.Function):
         stride, padding, (fx, fw, fg, pf, pd, pw), has_b = ctx.cfg
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
-            dx = torch.nn.grad.conv2d_input(x.shape, rnd(w, fw, pd, W_SCALE if fw == "f16" else 1.0), rnd(dy, fg, pd),
+            dx = torch.nn.grad.conv2d_input(x.shape, rnd(w, fw, pd, W_SCALE if fw == "f16" else 1.0), rnd(dy, fg, pd, "amax" if fg == "f16" else 1.0),
                                             stride=stride, padding=padding)
         if ctx.needs_input_grad[1]:
-            dw = torch.nn.grad.conv2d_weight(rnd(x, fx, pw), w.shape, rnd(dy, fg, pw), stride=stride, padding=padding)
+            dw = torch.nn.grad.conv2d_weight(rnd(x, fx, pw), w.shape, rnd(dy, fg, pw, "amax" if fg == "f16" else 1.0), stride=stride, padding=padding)
         if has_b and ctx.needs_input_grad[2]:
             db = dy.sum(dim=(0, 2, 3))
         return dx, dw, db, None, None, None
@@ -214,6 +217,15 @@ def main():
         show("A + dis/cla wgrad 3", Policy(hi, ov))
         ov = {n: ("bf16", "bf16", "bf16", 1, 1, 1) for n in dec_up}
         show("bf16 all: ups fwd1, rest 3; bwd 1", Policy(("bf16", "bf16", "bf16", 3, 1, 1), ov))
+    elif exp == "plans3":
+        dec_res = ["gen.dec.model.0.model.%d.model.%d.conv." % (i, j) for i in (0, 1) for j in (0, 1)]
+        dec_up = ["gen.dec.model.%d.conv." % i for i in (2, 4, 6)]
+        b3, f1 = ("bf16", "bf16", "bf16", 3, 1, 1), ("f16", "f16", "f16", 1, 1, 1)
+        show("bf16 3/1/1 everywhere (shipping)", Policy(b3))
+        show("ups f16 1/1/1 (dy f16), rest bf16 3/1/1", Policy(b3, {n: f1 for n in dec_up}))
+        show("ups+res f16 1/1/1, rest bf16 3/1/1", Policy(b3, {n: f1 for n in dec_up + dec_res}))
+        show("last 2 ups f16 1/1/1, rest bf16 3/1/1", Policy(b3, {n: f1 for n in dec_up[1:]}))
+        show("ups f16 fwd 1, bwd 3 ; rest bf16 3/1/1", Policy(b3, {n: ("f16", "f16", "f16", 1, 3, 3) for n in dec_up}))
 
 
 if __name__ == "__main__":

@@ -204,3 +204,36 @@ def test_fp32_mode_never_uses_tensor_cores_and_bf16_always_does():
         names = set(O_.stop_kernel_timing())
         assert names and all(want in n for n in names), (mode, names)
     A.set_precision("fp32")
+
+
+@pytest.mark.parametrize("case", [CASES[3], CASES[4], CASES[5], CASES[1], CASES[18]])
+@pytest.mark.parametrize("grad_scale", [1.0, 3e-7])
+def test_fp16_operand_planes(case, grad_scale):
+    """ops.operand_format("f16"): fp16 operand planes, one MMA per product in forward, dgrad and wgrad (the decoder's route).
+    11 significant bits per operand -> 2e-3 of the largest reference magnitude; tiny incoming gradients (3e-7: far below
+    fp16's normal range) exercise the per-tensor power-of-two scale of the dY planes."""
+    n, h, w_, ci, co, k, s, p, pm, up, pre = case
+    A.set_precision("bf16")
+    try:
+        g = torch.Generator(device="cuda").manual_seed(21)
+        x = torch.randn(n, ci, h, w_, device="cuda", generator=g)
+        wgt = torch.randn(co, ci, k, k, device="cuda", generator=g) * (2.0 / (ci * k * k)) ** 0.5
+        b = torch.randn(co, device="cuda", generator=g)
+        xi = ops.to_internal(x).detach().clone().requires_grad_()
+        wi, bi = wgt.clone().requires_grad_(), b.clone().requires_grad_()
+        ops.start_kernel_timing()
+        with ops.operand_format("f16"):
+            y = ops.conv2d(xi, wi, bi, stride=s, pad=p, pad_mode=pm, upsample=up, pre_act=pre)
+        xr, wr, br = x.double().requires_grad_(), wgt.double().requires_grad_(), b.double().requires_grad_()
+        yr = ref_conv(xr, wr, br, s, p, pm, up, pre)
+        gy = torch.randn(yr.shape, device="cuda", generator=g) * grad_scale
+        y.backward(gy)
+        names = set(ops.stop_kernel_timing(by_kernel=True))
+        ops.stop_stream_timing()
+        assert names and all(nm.endswith(" f16") and ", 1" in nm for nm in names), names
+        yr.backward(gy.double())
+        e = dict(y=rel(y, yr), dx=rel(xi.grad, xr.grad), dw=rel(wi.grad, wr.grad), db=rel(bi.grad, br.grad))
+        assert e["y"] <= 2e-3 and e["dx"] <= 2e-3 and e["dw"] <= 2e-3 and e["db"] <= 2e-4, e
+        assert cosine(wi.grad, wr.grad) >= 0.999999 and cosine(xi.grad, xr.grad) >= 0.999999
+    finally:
+        A.set_precision("fp32")
