@@ -65,6 +65,7 @@ SIGNATURES = {
     "affgw_split_positions": [_P, _I, _P, C.POINTER(PosFrame), _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P],
     "affgw_amax_scale": [_P, _L, _P, _P, _P],
     "affgw_split_positions_fmt": [_P, _I, _P, C.POINTER(PosFrame), _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _I, _P, _P],
+    "affgw_split_planes_fmt": [_P, _I, _P, _L, _I, _I, _I, _I, _I, _I, _P, _P],
     "affgw_pack_weight_tc_fmt": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     "affgw_conv2d_dgrad_scaled": [_P, _P, _P, _P, _P, _D, _P, _P],
     "affgw_conv2d_wgrad_scaled": [_P, _P, _P, _P, _D, _P, _P],

@@ -21,12 +21,12 @@ int pack_weight(const float* w, void* out, int out_dt, int Cout, int Cin, int KH
 int conv_tc_block_n(int cout);
 int conv_tc_ok(const ConvGeom& g);
 int conv_fwd_tc(const void* x_planes, long long plane_stride, const void* w_tiles, const float* bias, const void* addend,
-                void* y, int y_dt, const ConvGeom& g, int passes, cudaStream_t st);
-int pack_weight_tc(const float* w, void* out, int Cout, int Cin, int KH, int KW, int ipad, int transpose_flip, int passes,
+                void* y, int y_dt, const ConvGeom& g, int passes, int fmt, const float* alpha_dev, cudaStream_t st);
+int pack_weight_tc(const float* w, void* out, int Cout, int Cin, int KH, int KW, int ipad, int transpose_flip, int passes, int fmt,
                    cudaStream_t st);
 long long pack_weight_tc_bytes(int Cout, int Cin, int KH, int KW, int ipad, int transpose_flip, int passes);
 int split_planes(const void* x, int x_dt, void* planes, long long rows, int C, int pitch, int c_store, int passes, int pre_act,
-                 cudaStream_t st);
+                 int fmt, const float* scale_dev, cudaStream_t st);
 // conv_shift.cu
 int shift_block_n(int cout);
 int wgrad_shift_block_n(int cout);
@@ -51,7 +51,7 @@ int conv_thin_wgrad(const float* x, const float* dy, float* dw, const ConvGeom& 
 int conv_wgrad_tc_ok(const ConvGeom& g);
 long long conv_wgrad_tc_ws_bytes(const ConvGeom& g);
 int conv_wgrad_tc(const void* x_planes, long long x_plane, const void* dy_planes, long long dy_plane, float* dw, void* workspace,
-                  const ConvGeom& g, int cin_w, int passes, cudaStream_t st);
+                  const ConvGeom& g, int cin_w, int passes, int fmt, const float* alpha_dev, cudaStream_t st);
 int conv_wgrad_pos(const void* x_planes, const PosFrame& fx, const void* dy_planes, const PosFrame& fy, float* dw, void* workspace,
                    const ConvGeom& g, int cin_w, int passes, int fmt, const float* alpha_dev, cudaStream_t st);
 // norm.cu
@@ -207,13 +207,12 @@ int affgw_pack_weight_tc_fmt(const float* w, void* out, int Cout, int Cin, int K
                              int passes, int layout, int operand_fmt, void* stream) {
     AFFGW_CHECK(w && out, "pack_weight_tc: null pointer");
     AFFGW_CHECK(layout == AFFGW_WLAYOUT_IM2COL || layout == AFFGW_WLAYOUT_SHIFT, "pack_weight_tc: bad layout");
-    AFFGW_CHECK(operand_fmt == AFFGW_FMT_BF16 || (operand_fmt == AFFGW_FMT_F16 && layout == AFFGW_WLAYOUT_SHIFT),
-                "pack_weight_tc: fp16 operands are implemented by the position-space kernels only");
+    AFFGW_CHECK(operand_fmt == AFFGW_FMT_BF16 || operand_fmt == AFFGW_FMT_F16, "pack_weight_tc: bad operand format");
     if (layout == AFFGW_WLAYOUT_SHIFT) {
         AFFGW_CHECK(KH == KW, "pack_weight_tc: the shifted kernel takes square filters");
         return pack_weight_shift(w, out, Cout, Cin, KH, i_pad, transpose_flip, passes, operand_fmt, S(stream));
     }
-    return pack_weight_tc(w, out, Cout, Cin, KH, KW, i_pad, transpose_flip, passes, S(stream));
+    return pack_weight_tc(w, out, Cout, Cin, KH, KW, i_pad, transpose_flip, passes, operand_fmt, S(stream));
 }
 int affgw_pack_weight_tc(const float* w, void* out, int Cout, int Cin, int KH, int KW, int i_pad, int transpose_flip,
                          int passes, int layout, void* stream) {
@@ -223,11 +222,17 @@ long long affgw_operand_planes_bytes(long long rows, int c_store, int passes) {
     if (rows <= 0 || c_store <= 0 || c_store % 8 != 0 || !passes_ok(passes)) return -1;
     return rows * c_store * 2LL * (passes == 3 ? 2 : 1);
 }
-int affgw_split_planes(const void* x, int x_dtype, void* planes, long long rows, int C, int pitch, int c_store, int passes,
-                       int pre_act, void* stream) {
+int affgw_split_planes_fmt(const void* x, int x_dtype, void* planes, long long rows, int C, int pitch, int c_store, int passes,
+                           int pre_act, int operand_fmt, const float* scale_dev, void* stream) {
     AFFGW_CHECK(x && planes && dt_ok(x_dtype) && rows > 0 && C > 0 && pitch >= C, "split_planes: bad argument");
     AFFGW_CHECK(pre_act >= 0 && pre_act <= 3, "split_planes: bad activation");
-    return split_planes(x, x_dtype, planes, rows, C, pitch, c_store, passes, pre_act, S(stream));
+    AFFGW_CHECK(operand_fmt == AFFGW_FMT_BF16 || operand_fmt == AFFGW_FMT_F16, "split_planes: bad operand format");
+    AFFGW_CHECK(scale_dev == nullptr || operand_fmt == AFFGW_FMT_F16, "split_planes: a scale is for fp16 planes");
+    return split_planes(x, x_dtype, planes, rows, C, pitch, c_store, passes, pre_act, operand_fmt, scale_dev, S(stream));
+}
+int affgw_split_planes(const void* x, int x_dtype, void* planes, long long rows, int C, int pitch, int c_store, int passes,
+                       int pre_act, void* stream) {
+    return affgw_split_planes_fmt(x, x_dtype, planes, rows, C, pitch, c_store, passes, pre_act, AFFGW_FMT_BF16, nullptr, stream);
 }
 
 // geometry seen by the tcgen05 kernels: channels = the STORED channel count of the operand planes
@@ -271,9 +276,8 @@ int affgw_conv2d_fwd(const void* x, const void* w, const float* bias, const void
             return conv_pos_tc(x, f, w, bias, addend, y, d->KH, 0, 0, 0, d->Ho, d->Wo, d->Cout, d->out_pitch, d->post_act,
                                d->passes, d->operand_fmt, nullptr, S(stream));
         }
-        AFFGW_CHECK(d->operand_fmt == AFFGW_FMT_BF16, "conv2d_fwd: fp16 operands are implemented by the position-space kernels only");
         const long long plane = (long long)d->N * d->H * d->W * d->in_pitch;
-        return conv_fwd_tc(x, plane, w, bias, addend, y, d->y_dtype, g, d->passes, S(stream));
+        return conv_fwd_tc(x, plane, w, bias, addend, y, d->y_dtype, g, d->passes, d->operand_fmt, nullptr, S(stream));
     }
     return conv_fwd_simt(x, d->x_dtype, w, d->w_dtype, bias, addend, y, d->y_dtype, g, S(stream));
 }
@@ -457,10 +461,9 @@ int affgw_conv2d_dgrad_scaled(const void* dy, const void* wt, const void* x, voi
                 rc = conv_pos_tc(dy, fy, wt, nullptr, nullptr, workspace, d->KH, qs, 0, 0, Hp, Wp, d->Cin, d->Cin, ACT_NONE,
                                  d->passes, d->operand_fmt, inv_scale_dev, S(stream));
         } else {
-            AFFGW_CHECK(d->operand_fmt == AFFGW_FMT_BF16 && !inv_scale_dev, "conv2d_dgrad: fp16 operands are implemented by the position-space kernels only");
             AFFGW_CHECK(conv_tc_ok(g) > 0, "conv2d_dgrad: shape not supported by the tcgen05 kernel");
             const long long plane = (long long)dd.N * dd.H * dd.W * dd.in_pitch;
-            rc = conv_fwd_tc(dy, plane, wt, nullptr, nullptr, out, gdt, g, d->passes, S(stream));
+            rc = conv_fwd_tc(dy, plane, wt, nullptr, nullptr, out, gdt, g, d->passes, d->operand_fmt, inv_scale_dev, S(stream));
         }
     } else {
         rc = conv_fwd_simt(dy, dd.x_dtype, wt, d->w_dtype, nullptr, nullptr, out, dd.y_dtype, g, S(stream));
@@ -510,11 +513,10 @@ int affgw_conv2d_wgrad_scaled(const void* x, const void* dy, float* dw, void* wo
             if (int rc2 = shift_frames(d, gf, fx, fy)) return rc2;
             return conv_wgrad_pos(x, fx, dy, fy, dw, workspace, g, d->Cin, d->passes, d->operand_fmt, inv_scale_dev, S(stream));
         }
-        AFFGW_CHECK(d->operand_fmt == AFFGW_FMT_BF16 && !inv_scale_dev, "conv2d_wgrad: fp16 operands are implemented by the position-space kernels only");
         AFFGW_CHECK(conv_wgrad_tc_ok(g), "conv2d_wgrad: shape not supported by the tcgen05 kernel");
         const long long xpl = (long long)d->N * d->H * d->W * d->in_pitch;
         const long long ypl = g.M * d->out_pitch;
-        return conv_wgrad_tc(x, xpl, dy, ypl, dw, workspace, g, d->Cin, d->passes, S(stream));
+        return conv_wgrad_tc(x, xpl, dy, ypl, dw, workspace, g, d->Cin, d->passes, d->operand_fmt, inv_scale_dev, S(stream));
     }
     return conv_wgrad_simt(x, d->x_dtype, dy, d->y_dtype, dw, g, S(stream));
 }

@@ -24,12 +24,20 @@
 //
 // Replaces the cuDNN convolutions behind reference blocks.py:148 / vgg_tro_channel3_modi.py:47 /
 // modules_tro.py:252-259; the same kernel computes dgrad.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
 namespace {
 
 using namespace tcptx;
+
+constexpr float F16_W_SCALE = 256.f;         // fp16 weight tiles hold w * 2^8 (see conv_shift.cu)
+__device__ __forceinline__ uint16_t f16_bits(float v) {
+    return __half_as_ushort(__float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f)));
+}
+__device__ __forceinline__ float f16_val(uint16_t b) { return __half2float(__ushort_as_half(b)); }
 
 constexpr int BM = 128, BK = 64;
 constexpr int A_PLANE_BYTES = BM * BK * 2;  // 16 KB
@@ -62,9 +70,9 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
     d |= 2ull << 61;                                    // SWIZZLE_128B
     return d;
 }
-// kind::f16 instruction descriptor: D = f32, A = B = bf16, both K-major, M = 128, N = n
-__host__ __device__ constexpr uint32_t make_idesc_bf16(int n) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+// kind::f16 instruction descriptor: D = f32, A and B both bf16 (fmt 0) or both fp16 (fmt 1), both K-major, M = 128, N = n
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int n, int fmt = 0) {
+    return (1u << 4) | (fmt ? 0u : ((1u << 7) | (1u << 10))) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 
 struct TcArgs {
@@ -79,6 +87,9 @@ struct TcArgs {
     int ksplit, kb_per_split;  // split of the k-block range over CTAs (tiny-M layers); partial sums are reduced with atomics
     long long total_tiles;
     int vec_ok;                // 16-column vector stores allowed (Cout % 16 == 0 and aligned pitch)
+    int fmt;                   // 0 = bf16 operands, 1 = fp16 operands
+    float alpha;               // result = accumulator * alpha * (alpha_dev ? *alpha_dev : 1): undoes the fp16 operand scales
+    const float* alpha_dev;
 };
 
 template <typename TO> __device__ __forceinline__ void store16(TO* dst, const float (&v)[16]);
@@ -277,7 +288,7 @@ conv_igemm_tcgen05_kernel(const __grid_constant__ TcArgs a) {
     } else if (warp == MMA_WARP) {
         // ============================== MMA issuer ==============================
         {   // every lane runs the loops (warp-uniform), one elected lane issues: see umma_bf16_elect
-            constexpr uint32_t idesc = make_idesc_bf16(BN);
+            const uint32_t idesc = make_idesc_bf16(BN, a.fmt);
             uint32_t it = 0, tl = 0;
             for (long long t = blockIdx.x; t < a.total_tiles; t += gridDim.x, ++tl) {
                 const uint32_t acc = tl & 1u, acc_ph = (tl >> 1) & 1u;
@@ -312,6 +323,7 @@ conv_igemm_tcgen05_kernel(const __grid_constant__ TcArgs a) {
     } else {
         // ============================== epilogue ==============================
         const int q = warp & 3;           // TMEM lane quarter this warp may read
+        const float alpha = a.alpha * (a.alpha_dev ? __ldg(a.alpha_dev) : 1.f);
         TO* const y = reinterpret_cast<TO*>(a.y);
         const TO* const addend = reinterpret_cast<const TO*>(a.addend);
         uint32_t tl = 0;
@@ -337,7 +349,7 @@ conv_igemm_tcgen05_kernel(const __grid_constant__ TcArgs a) {
 #pragma unroll
                         for (int i = 0; i < 16; ++i) {
                             if (nb + i < g.Cout) {
-                                float r = __uint_as_float(raw[i]);
+                                float r = __uint_as_float(raw[i]) * alpha;
                                 if (first_split) {
                                     if (a.bias) r += __ldg(a.bias + nb + i);
                                     if (addend) r += to_f(addend[m * g.out_pitch + nb + i]);
@@ -350,7 +362,7 @@ conv_igemm_tcgen05_kernel(const __grid_constant__ TcArgs a) {
                     float v[16];
                     if (a.vec_ok) {
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(raw[i]) + (a.bias ? __ldg(a.bias + nb + i) : 0.f);
+                        for (int i = 0; i < 16; ++i) v[i] = fmaf(__uint_as_float(raw[i]), alpha, a.bias ? __ldg(a.bias + nb + i) : 0.f);
                         if (addend) {
                             float ad[16];
                             load16<TO>(addend + m * g.out_pitch + nb, ad);
@@ -366,7 +378,7 @@ conv_igemm_tcgen05_kernel(const __grid_constant__ TcArgs a) {
 #pragma unroll
                         for (int i = 0; i < 16; ++i) {
                             if (nb + i < g.Cout) {
-                                float r = __uint_as_float(raw[i]) + (a.bias ? __ldg(a.bias + nb + i) : 0.f);
+                                float r = fmaf(__uint_as_float(raw[i]), alpha, a.bias ? __ldg(a.bias + nb + i) : 0.f);
                                 if (addend) r += to_f(addend[m * g.out_pitch + nb + i]);
                                 y[m * g.out_pitch + nb + i] = from_f<TO>(act_apply(r, g.post_act));
                             }
@@ -390,7 +402,7 @@ conv_igemm_tcgen05_kernel(const __grid_constant__ TcArgs a) {
 // weights: logical [O'][taps * I'pad] -> per (n-tile, k-block, plane) [BN][64] tiles with the 128B swizzle already applied;
 // plane 0 = bf16(w), plane 1 = bf16(w - plane0) (written when passes == 3)
 __global__ void pack_weight_tc_kernel(const float* __restrict__ w, bf16* __restrict__ out, int Cout, int Cin, int KH, int KW,
-                                      int ipad, int transpose_flip, int BN, int ntiles, int KB, int npl) {
+                                      int ipad, int transpose_flip, int BN, int ntiles, int KB, int npl, int fmt) {
     const int Od = transpose_flip ? Cin : Cout, Id = transpose_flip ? Cout : Cin;
     const int taps = KH * KW;
     const long long total = (long long)ntiles * KB * BN * BK;
@@ -414,10 +426,17 @@ __global__ void pack_weight_tc_kernel(const float* __restrict__ w, bf16* __restr
             else
                 v = w[(((long long)o * Cin + i) * KH + ky) * KW + kx];
         }
-        const bf16 hi = __float2bfloat16_rn(v);
         bf16* dst = out + (tile * npl) * (BN * BK) + within;
-        dst[0] = hi;
-        if (npl == 2) dst[BN * BK] = __float2bfloat16_rn(v - __bfloat162float(hi));
+        if (fmt) {
+            const float sv = v * F16_W_SCALE;
+            const uint16_t hb = f16_bits(sv);
+            reinterpret_cast<uint16_t*>(dst)[0] = hb;
+            if (npl == 2) reinterpret_cast<uint16_t*>(dst)[BN * BK] = f16_bits(sv - f16_val(hb));
+        } else {
+            const bf16 hi = __float2bfloat16_rn(v);
+            dst[0] = hi;
+            if (npl == 2) dst[BN * BK] = __float2bfloat16_rn(v - __bfloat162float(hi));
+        }
     }
 }
 
@@ -425,7 +444,8 @@ __global__ void pack_weight_tc_kernel(const float* __restrict__ w, bf16* __restr
 // zero-filled, plane 1 = bf16 remainder.
 template <typename T>
 __global__ void split_planes_kernel(const T* __restrict__ x, bf16* __restrict__ planes, long long rows, int C, int pitch,
-                                    int c_store, int npl, int pre_act) {
+                                    int c_store, int npl, int pre_act, int fmt, const float* __restrict__ scale_dev) {
+    const float scale = scale_dev ? __ldg(scale_dev) : 1.f;
     const int groups = c_store / 8;
     const long long total = rows * groups;
     const long long plane = rows * (long long)c_store;
@@ -440,6 +460,22 @@ __global__ void split_planes_kernel(const T* __restrict__ x, bf16* __restrict__ 
         } else {
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[i] = (c + i < C) ? to_f(x[r * pitch + c + i]) : 0.f;
+        }
+        if (fmt) {
+            uint4 hi, lo;
+            __half2* hh = reinterpret_cast<__half2*>(&hi);
+            __half2* ll = reinterpret_cast<__half2*>(&lo);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float a0 = fminf(fmaxf(act_apply(v[2 * i], pre_act) * scale, -65504.f), 65504.f);
+                const float a1 = fminf(fmaxf(act_apply(v[2 * i + 1], pre_act) * scale, -65504.f), 65504.f);
+                hh[i] = __floats2half2_rn(a0, a1);
+                const float2 f = __half22float2(hh[i]);
+                ll[i] = __floats2half2_rn(a0 - f.x, a1 - f.y);
+            }
+            *reinterpret_cast<uint4*>(planes + r * c_store + c) = hi;
+            if (npl == 2) *reinterpret_cast<uint4*>(planes + plane + r * c_store + c) = lo;
+            continue;
         }
         float lo[8];
 #pragma unroll
@@ -500,7 +536,7 @@ int conv_tc_ok(const ConvGeom& g) {
 }
 
 int conv_fwd_tc(const void* x_planes, long long plane_stride, const void* w_tiles, const float* bias, const void* addend,
-                void* y, int y_dt, const ConvGeom& g, int passes, cudaStream_t st) {
+                void* y, int y_dt, const ConvGeom& g, int passes, int fmt, const float* alpha_dev, cudaStream_t st) {
     const int bn = conv_tc_ok(g);
     if (!bn || (passes != 1 && passes != 3)) {
         affgw_set_error("conv_fwd_tc: unsupported shape (stored Cin %d, pitch %d, passes %d)", g.Cin, g.in_pitch, passes);
@@ -538,6 +574,9 @@ int conv_fwd_tc(const void* x_planes, long long plane_stride, const void* w_tile
     const int esz = y_dt == AFFGW_F32 ? 4 : 2;
     a.vec_ok = (g.Cout % 16 == 0) && ((g.out_pitch * esz) % 16 == 0) && (((uintptr_t)y) % 16 == 0) &&
                (!addend || ((uintptr_t)addend) % 16 == 0);
+    a.fmt = fmt;
+    a.alpha = fmt ? 1.f / F16_W_SCALE : 1.f;
+    a.alpha_dev = alpha_dev;
     return y_dt == AFFGW_F32 ? launch_tc_n<float>(a, bn, passes, st) : launch_tc_n<bf16>(a, bn, passes, st);
 }
 
@@ -550,7 +589,7 @@ long long pack_weight_tc_bytes(int Cout, int Cin, int KH, int KW, int ipad, int 
     return ntiles * KB * (passes == 3 ? 2 : 1) * bn * BK * 2;
 }
 
-int pack_weight_tc(const float* w, void* out, int Cout, int Cin, int KH, int KW, int ipad, int transpose_flip, int passes,
+int pack_weight_tc(const float* w, void* out, int Cout, int Cin, int KH, int KW, int ipad, int transpose_flip, int passes, int fmt,
                    cudaStream_t st) {
     if (pack_weight_tc_bytes(Cout, Cin, KH, KW, ipad, transpose_flip, passes) <= 0) {
         affgw_set_error("pack_weight_tc: bad configuration (i_pad %d, passes %d)", ipad, passes);
@@ -563,13 +602,13 @@ int pack_weight_tc(const float* w, void* out, int Cout, int Cin, int KH, int KW,
     const long long total = (long long)ntiles * KB * bn * BK;
     const int blocks = (int)min((long long)148 * 8, (total + 255) / 256);
     pack_weight_tc_kernel<<<blocks, 256, 0, st>>>(w, (bf16*)out, Cout, Cin, KH, KW, ipad, transpose_flip, bn, ntiles, KB,
-                                                  passes == 3 ? 2 : 1);
+                                                  passes == 3 ? 2 : 1, fmt);
     AFFGW_LAUNCH_CHECK("pack_weight_tc");
     return 0;
 }
 
 int split_planes(const void* x, int x_dt, void* planes, long long rows, int C, int pitch, int c_store, int passes, int pre_act,
-                 cudaStream_t st) {
+                 int fmt, const float* scale_dev, cudaStream_t st) {
     if (c_store % 8 != 0 || c_store < C || (passes != 1 && passes != 3)) {
         affgw_set_error("split_planes: bad configuration (C %d, c_store %d, passes %d)", C, c_store, passes);
         return -1;
@@ -578,9 +617,9 @@ int split_planes(const void* x, int x_dt, void* planes, long long rows, int C, i
     const int blocks = (int)min((long long)148 * 16, (total + 255) / 256);
     const int npl = passes == 3 ? 2 : 1;
     if (x_dt == AFFGW_F32)
-        split_planes_kernel<float><<<blocks, 256, 0, st>>>((const float*)x, (bf16*)planes, rows, C, pitch, c_store, npl, pre_act);
+        split_planes_kernel<float><<<blocks, 256, 0, st>>>((const float*)x, (bf16*)planes, rows, C, pitch, c_store, npl, pre_act, fmt, scale_dev);
     else
-        split_planes_kernel<bf16><<<blocks, 256, 0, st>>>((const bf16*)x, (bf16*)planes, rows, C, pitch, c_store, npl, pre_act);
+        split_planes_kernel<bf16><<<blocks, 256, 0, st>>>((const bf16*)x, (bf16*)planes, rows, C, pitch, c_store, npl, pre_act, fmt, scale_dev);
     AFFGW_LAUNCH_CHECK("split_planes");
     return 0;
 }

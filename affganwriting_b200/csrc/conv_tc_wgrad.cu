@@ -56,8 +56,9 @@ __device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr, 
     return d;
 }
 // kind::f16, D = f32, A = B = bf16, both MN-major, M = 128, N = n
-__host__ __device__ constexpr uint32_t make_idesc_bf16_mn(int n) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+__host__ __device__ constexpr uint32_t make_idesc_bf16_mn(int n, int fmt = 0) {       // fmt 0: bf16 operands, 1: fp16 operands
+    return (1u << 4) | (fmt ? 0u : ((1u << 7) | (1u << 10))) | (1u << 15) | (1u << 16) | ((uint32_t)(n >> 3) << 17) |
+           ((uint32_t)(128 >> 4) << 24);
 }
 
 __device__ __forceinline__ int map_fast(int v, int V, int pad_mode, int up) {
@@ -81,6 +82,8 @@ struct WgArgs {
     ConvGeom g;
     long long m_per_split;
     FastDiv div_wo, div_ho;
+    int fmt;                    // 0 = bf16 planes, 1 = fp16 planes
+    const float* alpha_dev;     // 1 / (scale of the fp16 dY planes), device memory; nullptr = 1
 };
 
 template <int BN, int NPASS>
@@ -206,6 +209,7 @@ conv_wgrad_tcgen05_kernel(const __grid_constant__ WgArgs a) {
         mbar_wait(tmem_full_bar, 0);
         tc_fence_after();
         const int row = warp * 32 + lane;
+        const float alpha = a.alpha_dev ? __ldg(a.alpha_dev) : 1.f;
         const int kf = (2 * blockIdx.x) * 64 + row;
         const bool rok = kf < ktot;
         float* wrow = a.ws + kf;
@@ -218,14 +222,14 @@ conv_wgrad_tcgen05_kernel(const __grid_constant__ WgArgs a) {
             if (rok) {
 #pragma unroll
                 for (int i = 0; i < 16; ++i)
-                    if (nb + i < g.Cout) atomicAdd(wrow + (size_t)(nb + i) * ktot, __uint_as_float(raw[i]));
+                    if (nb + i < g.Cout) atomicAdd(wrow + (size_t)(nb + i) * ktot, __uint_as_float(raw[i]) * alpha);
             }
         }
         tc_fence_before();
     } else {
         // ============================== MMA issuer ==============================
         // every lane of warp 4 runs the loops (warp-uniform), one elected lane issues: see umma_bf16_elect
-        constexpr uint32_t idesc = make_idesc_bf16_mn(BN);
+        const uint32_t idesc = make_idesc_bf16_mn(BN, a.fmt);
         constexpr uint32_t lbo = (uint32_t)IMG_BYTES, sbo = 1024u;
         for (int st = 0; st < nstages; ++st) {
             const int s = st % STAGES;
@@ -328,7 +332,7 @@ int conv_wgrad_tc_ok(const ConvGeom& g) {
 long long conv_wgrad_tc_ws_bytes(const ConvGeom& g) { return (long long)g.Cout * g.KH * g.KW * g.Cin * 4; }
 
 int conv_wgrad_tc(const void* x_planes, long long x_plane, const void* dy_planes, long long dy_plane, float* dw, void* workspace,
-                  const ConvGeom& g, int cin_w, int passes, cudaStream_t st) {
+                  const ConvGeom& g, int cin_w, int passes, int fmt, const float* alpha_dev, cudaStream_t st) {
     const int bn = conv_wgrad_tc_ok(g);
     if (!bn || !workspace || (passes != 1 && passes != 3)) {
         affgw_set_error("conv_wgrad_tc: unsupported shape or missing workspace");
@@ -343,6 +347,7 @@ int conv_wgrad_tc(const void* x_planes, long long x_plane, const void* dy_planes
     a.x = (const bf16*)x_planes; a.x_plane = x_plane;
     a.dy = (const bf16*)dy_planes; a.dy_plane = dy_plane;
     a.ws = ws; a.g = g; a.m_per_split = 0;
+    a.fmt = fmt; a.alpha_dev = alpha_dev;
     a.div_wo = make_fastdiv(g.Wo);
     a.div_ho = make_fastdiv(g.Ho);
     int rc;

@@ -48,7 +48,8 @@ def _dis_cla_trunk(n_layers, final_dim):
 
 
 import os as _os
-_DECODER_F16 = _os.environ.get("AFFGW_DECODER_F16", "1") != "0"
+_DECODER_F16 = _os.environ.get("AFFGW_DECODER_F16", "0") != "0"
+_UPCONV_PASSES = int(_os.environ.get("AFFGW_UPCONV_PASSES", "1"))
 _TRUNK_WGRAD_PASSES = int(_os.environ.get("AFFGW_TRUNK_WGRAD_PASSES", "1"))
 
 
@@ -176,9 +177,8 @@ class Decoder(nn.Module):
         self.model = nn.Sequential(*model)
 
     def forward(self, x):
-        # The decoder's 3x3 / 5x5 convolutions are the last layers in front of the image: forward rounding is amplified least
-        # there, and they run on fp16 operand planes with ONE tensor-core pass per GEMM (ops.operand_format) instead of the
-        # three of the split-bf16 forward; AFFGW_DECODER_F16=0 keeps the bf16 route.
+        # AFFGW_DECODER_F16=1: in mode 'bf16', run the decoder's 3x3 / 5x5 convolutions on fp16 operand planes with one pass
+        # per GEMM (ops.operand_format) - superseded by mode 'f16', kept for A/B measurements
         with ops.operand_format("f16" if _DECODER_F16 else None):
             return self._forward(x)
 
@@ -191,7 +191,12 @@ class Decoder(nn.Module):
             if isinstance(m, nn.Upsample):
                 blk = mods[i + 1]
                 blk.upsample = 2                      # nearest x2 folded into the conv's operand gather
-                x = blk(x)
+                # the three 5x5 up-convolutions are the last dense layers in front of the image, where forward rounding is
+                # amplified least: in mode 'f16' their FORWARD GEMM runs one fp16 pass instead of three (image 1.5e-3, worst
+                # per-tensor gradient cosine ~0.9998 in scripts/precision_sweep.py "plans4"; AFFGW_UPCONV_PASSES=3 disables)
+                n_fwd = _UPCONV_PASSES if ops.precision() == "f16" else None
+                with ops.conv_passes(fwd=n_fwd, dgrad=1 if n_fwd else None, wgrad=1 if n_fwd else None):
+                    x = blk(x)
                 i += 2
             elif i == len(mods) - 1:
                 x = m(x, out_dtype=torch.float32)     # tanh image in fp32

@@ -17,7 +17,7 @@ _FUSE_DB = _os.environ.get("AFFGW_FUSE_DB", "1") != "0"
 _THIN = _os.environ.get("AFFGW_THIN", "1") != "0"
 # "passes": tensor-core MMAs per product of (forward, input-gradient, weight-gradient) GEMMs: 3 = split operands, 1 = single
 _state = {"mode": "fp32", "passes": (3, 3, 3), "force_simt": False, "simt_wgrad": False, "fmt": None}
-_MODES = {"fp32": (3, 3, 3), "bf16": (3, 1, 1), "bf16x3": (3, 3, 3), "bf16x1": (1, 1, 1)}
+_MODES = {"fp32": (3, 3, 3), "f16": (3, 1, 1), "bf16": (3, 1, 1), "bf16x3": (3, 3, 3), "bf16x1": (1, 1, 1)}
 _err_flag = {}
 _profile = {"records": None}
 
@@ -74,7 +74,8 @@ def _kernel_name(d, which, passes):
         if which == 2:
             return "conv_wgrad_shift_kernel<%d, %d>%s" % (bn, passes, sfx)
         return "conv_shift_tcgen05_kernel<%d, %d, %d>%s" % (bn, passes, L.lib().affgw_conv_tc_tile_m(C.byref(d), which) // 128, sfx)
-    return ("conv_wgrad_tcgen05_kernel<%d, %d>" if which == 2 else "conv_igemm_tcgen05_kernel<%d, %d, float>") % (bn, passes)
+    sfx = " f16" if d.operand_fmt == L.FMT_F16 else ""
+    return (("conv_wgrad_tcgen05_kernel<%d, %d>" if which == 2 else "conv_igemm_tcgen05_kernel<%d, %d, float>") % (bn, passes)) + sfx
 
 
 class _timed:
@@ -97,7 +98,14 @@ class _timed:
 def set_precision(mode):
     """Activations, statistics and gradients are stored in fp32 in every mode; the mode selects the convolution engine:
        'fp32'   : CUDA-core FFMA convolutions (<= 1e-4 against the CPU reference)
-       'bf16'   : tcgen05 tensor-core convolutions.  FORWARD GEMMs run on split-bf16 operands, three MMAs per product
+       'f16'    : tcgen05 tensor-core convolutions on FP16 operand planes (11 significant bits per plane against bf16's 8, same
+                  tensor throughput, fp32 TMEM accumulation).  Forward GEMMs on split operands (hi + remainder plane, three
+                  MMAs per product), backward GEMMs one MMA per product.  fp16's range is handled by power-of-two scales the
+                  kernels undo exactly: weights x 2^8, every dY tensor x 2^k from its max-abs (device side, no host sync).
+                  Image 2.5e-5 and gradient cosine 0.99998 per tensor against fp32 in the operand-rounding model
+                  (scripts/precision_sweep.py): this is the mode bench.py measures; the decoder's up-convolutions spend part of
+                  that margin on a single forward pass (modules_tro.Decoder).
+       'bf16'   : the same on BF16 operand planes (no scales needed: fp32's range).  FORWARD GEMMs three MMAs per product
                   (a_hi*w_hi + a_lo*w_hi + a_hi*w_lo, fp32 TMEM accumulation): forward rounding is amplified layer by layer
                   and only the split meets the 2e-2 image bar.  BACKWARD GEMMs (input and weight gradients) are linear in
                   dY, their rounding is not amplified, and run one MMA per product: gradient cosine stays >= 0.9997 per
@@ -384,12 +392,13 @@ def _up8(c):
     return (c + 7) // 8 * 8
 
 
-def _split_planes(x, rows, c, pitch, passes, pre_act="none"):
-    """fp32 activations [rows][pitch] -> bf16 operand planes [1 or 2][rows][c_store] of the tcgen05 kernels."""
+def _split_planes(x, rows, c, pitch, passes, pre_act="none", fmt=0, scale=None):
+    """fp32 activations [rows][pitch] -> 16-bit operand planes [1 or 2][rows][c_store] of the tcgen05 kernels (bf16, or fp16
+    of x * scale[0])."""
     cs = _up8(c)
     planes = torch.empty((2 if passes == 3 else 1, rows, cs), dtype=torch.bfloat16, device=x.device)
-    L.call("affgw_split_planes", x.data_ptr(), L.dt(x), planes.data_ptr(), rows, c, pitch, cs, passes, L.ACT[pre_act],
-           L.stream(), nbytes=rows * c * x.element_size() + _nb(planes))
+    L.call("affgw_split_planes_fmt", x.data_ptr(), L.dt(x), planes.data_ptr(), rows, c, pitch, cs, passes, L.ACT[pre_act],
+           fmt, L.ptr(scale), L.stream(), nbytes=rows * c * x.element_size() + _nb(planes))
     return planes
 
 
@@ -501,17 +510,20 @@ class _Conv2d(Function):
             layout = L.lib().affgw_conv_tc_layout(C.byref(d), 0)
             if not layout:
                 raise RuntimeError("conv2d: tcgen05 kernels refused the shape: " + L.last_error())
-            # fp16 operand planes (ops.operand_format): position-space layers in mode 'bf16' only, single pass in all three GEMMs
-            if _state["fmt"] == "f16" and _state["mode"] == "bf16" and layout == L.WLAYOUT_SHIFT:
+            if _state["mode"] == "f16":
+                fmt = L.FMT_F16
+            elif _state["fmt"] == "f16" and _state["mode"] == "bf16" and layout == L.WLAYOUT_SHIFT:
+                # ops.operand_format inside the bf16 mode: fp16 planes for this layer, single pass in all three GEMMs
                 fmt = L.FMT_F16
                 passes = pd = pw = px = 1
-                d = _desc(g, cfg, g["Cin"], L.BF16, L.BF16, L.F32, L.ALGO_TC, in_pitch=cs, passes=1, pre_act="none", fmt=fmt)
+            if fmt:
+                d = _desc(g, cfg, g["Cin"], L.BF16, L.BF16, L.F32, L.ALGO_TC, in_pitch=cs, passes=passes, pre_act="none", fmt=fmt)
             if layout == L.WLAYOUT_SHIFT:
                 fx, _ = _pos_frames(d)
                 planes = _split_positions(x, fx, g["H"], g["W"], g["Cin"], g["pitch"], cfg.upsample, cfg.pad, cfg.pad_mode,
                                           cfg.pre_act, px, fmt=fmt)
             else:
-                planes = _split_planes(x, g["N"] * g["H"] * g["W"], g["Cin"], g["pitch"], px, cfg.pre_act)
+                planes = _split_planes(x, g["N"] * g["H"] * g["W"], g["Cin"], g["pitch"], px, cfg.pre_act, fmt=fmt)
             wp = _pack_tc(weight, cs, False, passes, layout, fmt)
             with _timed("conv_fwd_tcgen05", flops, (tag, _kernel_name(d, 0, passes)) if _profile["records"] is not None else tag):
                 L.call("affgw_conv2d_fwd", planes.data_ptr(), wp.data_ptr(), L.ptr(b32), L.ptr(addend), y.data_ptr(),
@@ -574,7 +586,9 @@ class _Conv2d(Function):
                 dzp = _split_positions(dz, fy, g["Ho"], g["Wo"], cout, cout, 1, 0, "zero", "none", pdy,
                                        colsum=db if fuse_db else None, fmt=fmt, scale=dy_scale)
             else:
-                dzp = _split_planes(dz, M, cout, cout, pdy)
+                if fmt == L.FMT_F16:
+                    dy_scale = _amax_scale(dz)
+                dzp = _split_planes(dz, M, cout, cout, pdy, fmt=fmt, scale=dy_scale)
         if ctx.thin:
             dthin = _desc(g, fwd_cfg, cin, L.F32, L.F32, L.F32, L.ALGO_SIMT)
             if need_w:

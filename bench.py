@@ -249,6 +249,8 @@ def main():
                     help="style encoder: vgg = configs[1] (default, the headline), resnet18 = configs[2]")
     ap.add_argument("--no-graph", action="store_true", help="issue every launch from Python instead of replaying a CUDA graph")
     ap.add_argument("--no-overlap", action="store_true", help="gradient exchange + Adam on the main stream (no side-stream overlap)")
+    ap.add_argument("--precision", default="f16", choices=["f16", "bf16", "bf16x3"],
+                    help="16-bit tensor-core mode: f16 (default; fp16 operand planes) or the same kernels on bf16 planes")
     ap.add_argument("--no-rec-extra", action="store_true", help="skip the extra measurement of the full iteration with the recogniser")
     ap.add_argument("--quick", action="store_true", help="timed steps only (no e2e / generation / CPU legs): the command ncu profiles")
     args = ap.parse_args()
@@ -276,7 +278,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     assert _lib.lib().affgw_device_ok(), _lib.last_error()
 
-    A.set_precision("bf16")
+    A.set_precision(args.precision)
     torch.manual_seed(0)
     trainer = Trainer(num_writers=500, device=dev, encoder=None if args.encoder == "vgg" else args.encoder,
                       cuda_graph=not args.no_graph, overlap_exchange=not args.no_overlap)
@@ -465,13 +467,16 @@ def main():
     h2d = batch_bytes(host)
     line = {
         "metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
-        "dtype_detail": "bf16 tcgen05 MMAs with fp32 TMEM accumulation (forward: split-bf16 operands, 3 MMAs per product; backward: 1); "
-                        "activations, statistics, gradients and parameters are stored in fp32",
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16" if args.precision == "f16" else "bf16",
+        "dtype_detail": ("tcgen05 kind::f16 MMAs on %s operand planes with fp32 TMEM accumulation (forward: split operands, 3 MMAs per "
+                         "product - 1 in the decoder's up-convolutions in mode f16; backward: 1 MMA per product); activations, "
+                         "statistics, gradients and parameters are stored in fp32.  fp16 planes carry 11 significant bits against "
+                         "bf16's 8 at the same tensor throughput; their range is handled by exact power-of-two scales "
+                         "(DESIGN.md section 3)" % ("fp16" if args.precision == "f16" else "bf16")),
         "data": "synthetic (seeded uint8 grey-level canvases normalised on the GPU like load_data.py:152-166; random-init weights)",
         "config": {"workload": WORKLOAD if args.encoder == "vgg" else WORKLOAD.replace(
                        "configs[1]", "configs[2] (%s style encoder)" % args.encoder),
-                   "encoder": args.encoder, "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
+                   "encoder": args.encoder, "precision_mode": args.precision, "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
                    "cuda_graph": bool(trainer.graph_launches), "overlap_exchange": bool(trainer.overlap_exchange),
                    "l2": "inputs larger than L2: 177 MB of style images are re-read every step (L2 is 126 MB)",
                    "samples_per_sec": value * B},

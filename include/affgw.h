@@ -56,7 +56,7 @@ typedef struct affgw_conv_desc {
     int32_t stride_w;            /* column stride when it differs from `stride` (rows): Resnet18.py:43 uses
                                     stride=(2, 1); 0 = same as stride                                          */
     int32_t operand_fmt;         /* AFFGW_FMT_*: bf16 planes (8 significant bits per plane, fp32's range) or fp16 planes
-                                    (11 bits per plane; position-space kernels only).  fp16 weights are packed x 2^8 and fp16
+                                    (11 bits per plane).  fp16 weights are packed x 2^8 and fp16
                                     dY planes x a per-tensor power of two (affgw_amax_scale); the kernels undo both exactly */
 } affgw_conv_desc;
 
@@ -104,6 +104,8 @@ int affgw_amax_scale(const float* x, long long n, float* scale2, void* workspace
 int affgw_split_positions_fmt(const void* src, int dtype, void* planes, const affgw_pos_frame* f, int Hs, int Ws, int C, int pitch,
                               int upsample, int oy0, int ox0, int pad_mode, int pre_act, int passes, float* colsum,
                               int operand_fmt, const float* scale_dev, void* stream);
+int affgw_split_planes_fmt(const void* x, int x_dtype, void* planes, long long rows, int C, int pitch, int c_store, int passes,
+                           int pre_act, int operand_fmt, const float* scale_dev, void* stream);
 int affgw_pack_weight_tc_fmt(const float* w_oihw, void* out, int Cout, int Cin, int KH, int KW, int i_pad, int transpose_flip,
                              int passes, int layout, int operand_fmt, void* stream);
 int affgw_conv2d_dgrad_scaled(const void* dy, const void* wt, const void* x, void* dx, void* workspace,

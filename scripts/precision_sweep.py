@@ -226,6 +226,16 @@ def main():
         show("ups+res f16 1/1/1, rest bf16 3/1/1", Policy(b3, {n: f1 for n in dec_up + dec_res}))
         show("last 2 ups f16 1/1/1, rest bf16 3/1/1", Policy(b3, {n: f1 for n in dec_up[1:]}))
         show("ups f16 fwd 1, bwd 3 ; rest bf16 3/1/1", Policy(b3, {n: ("f16", "f16", "f16", 1, 3, 3) for n in dec_up}))
+    elif exp == "plans4":
+        dec_res = ["gen.dec.model.0.model.%d.model.%d.conv." % (i, j) for i in (0, 1) for j in (0, 1)]
+        dec_up = ["gen.dec.model.%d.conv." % i for i in (2, 4, 6)]
+        vgg = ["gen.enc_image.model.features.%d." % i for i in (0, 3, 6, 9, 13, 16, 19, 22, 26, 29, 32, 35, 39, 42, 45, 48)]
+        f3, f1 = ("f16", "f16", "f16", 3, 1, 1), ("f16", "f16", "f16", 1, 1, 1)
+        show("all f16 (dY f16 scaled) 3/1/1", Policy(f3))
+        show("all f16 3/1/1, decoder res+ups 1/1/1", Policy(f3, {n: f1 for n in dec_up + dec_res}))
+        show("  + dis/cla fwd 1", Policy(f3, {**{n: f1 for n in dec_up + dec_res}, "dis.": f1, "cla.": f1}))
+        show("  + last 4 VGG fwd 1", Policy(f3, {n: f1 for n in dec_up + dec_res + vgg[12:]}))
+        show("  + last 8 VGG fwd 1", Policy(f3, {n: f1 for n in dec_up + dec_res + vgg[8:]}))
 
 
 if __name__ == "__main__":

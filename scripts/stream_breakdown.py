@@ -10,7 +10,7 @@ from affganwriting_b200.trainer import Trainer
 import bench
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
-A.set_precision("bf16")
+A.set_precision("f16")
 dev = torch.device("cuda", 0)
 t = Trainer(num_writers=500, device=dev)
 batch = LD.batch_to_device(bench.synthetic_batch(B, 50, 1234), dev)

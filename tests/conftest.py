@@ -39,10 +39,31 @@ def golden():
     return load
 
 
-@pytest.fixture(params=["fp32", "bf16", "bf16x1"])
+class _Mode(str):
+    """Precision mode handed to the tests.  'f16' (fp16 operand planes, the mode bench.py measures) is held to exactly the bars
+    written for 'bf16' (BASELINE.json's 16-bit tensor-core bars: image 2e-2, cosine 0.999, and the tighter per-block ones), so
+    it compares and hashes like "bf16" - every `{"bf16": tol}[mode]` / `mode == "bf16"` in the test modules applies to it -
+    while printing as itself."""
+
+    def __new__(cls, name, bars_of):
+        obj = super().__new__(cls, name)
+        obj.bars_of = bars_of
+        return obj
+
+    def __eq__(self, other):
+        return str.__eq__(self.bars_of, other)
+
+    def __ne__(self, other):
+        return not self.__eq__(other)
+
+    def __hash__(self):
+        return hash(self.bars_of)
+
+
+@pytest.fixture(params=["fp32", "f16", "bf16", "bf16x1"])
 def mode(request):
     import affganwriting_b200 as A
     A.set_precision(request.param)
     A.force_simt(False)
-    yield request.param
+    yield _Mode(request.param, "bf16" if request.param == "f16" else request.param)
     A.set_precision("fp32")

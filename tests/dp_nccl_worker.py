@@ -33,7 +33,7 @@ def main():
     from affganwriting_b200.trainer import Trainer
     import bench
 
-    A.set_precision("bf16")
+    A.set_precision("f16")
     torch.manual_seed(100 + rank)                     # different initial weights per rank: broadcast_module must fix that
     tr = Trainer(num_writers=500, device=dev, encoder=None if encoder == "vgg" else encoder, bucket_bytes=8 << 20)
     batch = LD.batch_to_device(bench.synthetic_batch(4, 50, seed=7 + rank), dev)      # a different shard per rank

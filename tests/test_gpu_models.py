@@ -275,7 +275,7 @@ def test_cuda_graph_replay_matches_eager_iterations(specs):
     from affganwriting_b200.trainer import Trainer
     import bench
     from affganwriting_b200 import load_data as LD
-    A.set_precision("bf16")
+    A.set_precision("f16")
     try:
         dev = torch.device("cuda", 0)
         batch = LD.batch_to_device(bench.synthetic_batch(4, 50, 7), torch.device('cuda'))
@@ -335,7 +335,7 @@ def test_short_final_batch_after_capture_runs_eagerly(specs):
     from affganwriting_b200.trainer import Trainer
     import bench
     from affganwriting_b200 import load_data as LD
-    A.set_precision("bf16")
+    A.set_precision("f16")
     try:
         dev = torch.device("cuda", 0)
         full = LD.batch_to_device(bench.synthetic_batch(4, 50, 7), dev)
@@ -372,7 +372,7 @@ def test_adam_step_invalidates_packed_weight_cache():
     packed bf16 operand copies the convolutions cache per parameter."""
     from affganwriting_b200 import ops
     from affganwriting_b200.optim import Adam
-    A.set_precision("bf16")
+    A.set_precision("f16")
     try:
         x = ops.to_internal(torch.randn(2, 64, 8, 27, device="cuda"))
         w = torch.nn.Parameter(torch.randn(64, 64, 3, 3, device="cuda") * 0.05)
@@ -392,7 +392,7 @@ def test_graphed_generator_matches_eager(specs):
     """inference.GraphedGenerator: the captured forward returns what the eager forward returns, and follows a weight update."""
     from affganwriting_b200.inference import GraphedGenerator
     from affganwriting_b200 import ops
-    A.set_precision("bf16")
+    A.set_precision("f16")
     try:
         gen = _gen(specs).eval()
         batch = _cuda(O.synthetic_batch(4, 15))

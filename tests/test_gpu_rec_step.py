@@ -143,7 +143,7 @@ def test_trainer_runs_the_four_substeps_with_a_recogniser(which):
     import bench
     if which == "reference" and not rb.available():
         pytest.skip("reference tree neither at /root/reference nor staged in oracle/_ref")
-    A.set_precision("bf16")
+    A.set_precision("f16")
     try:
         dev = torch.device("cuda", 0)
         host = list(bench.synthetic_batch(4, 50, 7))
