@@ -1054,40 +1054,45 @@ int conv_wgrad_pos_tc(const void* x_planes, const PosFrame& fx, const void* dy_p
 // scale = 2^floor(log2(2^14 / amax)), so amax * scale lies in [2^13, 2^14); out[0] = scale, out[1] = 1 / scale.
 // =====================================================================================================================
 namespace {
-__global__ void amax_kernel(const float* __restrict__ x, long long n, unsigned* __restrict__ amax_bits) {
+// ws[0] = running max of |x| as float bits (non-negative floats order like unsigned ints), ws[1] = blocks finished.  Both are zero
+// on entry and are left zero by the last block, which also writes the scale: ONE launch per tensor, no memset.
+__global__ void __launch_bounds__(256) amax_scale_kernel(const float* __restrict__ x, long long n, unsigned* __restrict__ ws,
+                                                         float* __restrict__ out) {
     float m = 0.f;
     const long long n4 = n / 4;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
-        const float4 v = reinterpret_cast<const float4*>(x)[i];
+        const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
         m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
     }
     if (blockIdx.x == 0) for (long long i = n4 * 4 + threadIdx.x; i < n; i += blockDim.x) m = fmaxf(m, fabsf(x[i]));
     for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if ((threadIdx.x & 31) == 0 && m > 0.f && m == m && m < INFINITY) atomicMax(amax_bits, __float_as_uint(m));   // ordered like floats (>= 0)
-}
-__global__ void amax_finalize_kernel(const unsigned* __restrict__ amax_bits, float* __restrict__ out) {
-    const float amax = __uint_as_float(*amax_bits);
-    float s = 1.f;
-    if (amax > 0.f) {
-        int e;
-        frexpf(amax, &e);                       // amax = f * 2^e, f in [0.5, 1)  ->  amax * 2^(14 - e) in [2^13, 2^14)
-        const int k = max(-120, min(120, 14 - e));
-        s = ldexpf(1.f, k);
+    if ((threadIdx.x & 31) == 0 && m > 0.f && m < INFINITY) atomicMax(ws, __float_as_uint(m));     // NaN / inf never enter
+    __shared__ bool last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        last = atomicAdd(ws + 1, 1u) == gridDim.x - 1;
     }
-    out[0] = s;
-    out[1] = 1.f / s;
+    __syncthreads();
+    if (last && threadIdx.x == 0) {
+        __threadfence();
+        const float amax = __uint_as_float(atomicExch(ws, 0u));
+        ws[1] = 0u;
+        float s = 1.f;
+        if (amax > 0.f) {
+            int e;
+            frexpf(amax, &e);                   // amax = f * 2^e, f in [0.5, 1)  ->  amax * 2^(14 - e) in [2^13, 2^14)
+            s = ldexpf(1.f, max(-120, min(120, 14 - e)));
+        }
+        out[0] = s;
+        out[1] = 1.f / s;
+    }
 }
 }  // namespace
 
 int amax_scale(const float* x, long long n, float* out2, unsigned* ws, cudaStream_t st) {
-    if (cudaMemsetAsync(ws, 0, sizeof(unsigned), st) != cudaSuccess) {
-        affgw_set_error("amax_scale: memset failed");
-        return -2;
-    }
-    const int blocks = (int)min((long long)148 * 8, (n / 4 + 255) / 256 + 1);
-    amax_kernel<<<blocks, 256, 0, st>>>(x, n, ws);
-    AFFGW_LAUNCH_CHECK("amax");
-    amax_finalize_kernel<<<1, 1, 0, st>>>(ws, out2);
-    AFFGW_LAUNCH_CHECK("amax_finalize");
+    const int blocks = (int)min((long long)148 * 4, (n / 4 + 255) / 256 + 1);
+    amax_scale_kernel<<<blocks, 256, 0, st>>>(x, n, ws, out2);
+    AFFGW_LAUNCH_CHECK("amax_scale");
     return 0;
 }

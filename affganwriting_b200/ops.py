@@ -424,9 +424,15 @@ def _split_positions(src, frame, hs, ws, c, pitch, up, origin, pad_mode, pre_act
 def _amax_scale(t):
     """Device-side per-tensor power-of-two scale of an fp16 operand: -> float32 [2] = (2^k, 2^-k), no host synchronisation."""
     out = torch.empty(2, dtype=torch.float32, device=t.device)
-    ws = torch.empty(1, dtype=torch.int32, device=t.device)
+    key = (t.device.index, torch.cuda.current_stream().cuda_stream)
+    ws = _amax_ws.get(key)
+    if ws is None:                      # 8 bytes of scratch per (device, stream): zero on entry, left zero by the kernel
+        ws = _amax_ws[key] = torch.zeros(2, dtype=torch.int32, device=t.device)
     L.call("affgw_amax_scale", t.data_ptr(), t.numel(), out.data_ptr(), ws.data_ptr(), L.stream(), nbytes=_nb(t))
     return out
+
+
+_amax_ws = {}
 
 
 def _conv_geom(x, weight, cfg):

@@ -96,11 +96,12 @@ typedef struct affgw_pos_frame {
 } affgw_pos_frame;
 /* fp16 operand route (decoder convolutions, DESIGN.md "precision"): same calls with an operand format.
  *   affgw_amax_scale          scale2[0] = 2^k with max|x| * 2^k in [2^13, 2^14), scale2[1] = 2^-k (device memory, no host sync);
- *                             workspace4 = 4 bytes of device scratch
+ *                             workspace8 = 8 bytes of device scratch that must be ZERO on entry and is left zero (one
+ *                             buffer per stream serves every call)
  *   affgw_split_positions_fmt planes = fp16(v * *scale_dev) (scale_dev may be NULL = 1); the column sum stays unscaled
  *   affgw_pack_weight_tc_fmt  fp16 tiles of w * 2^8
  *   affgw_conv2d_*_scaled     result multiplied by *inv_scale_dev (the dY planes' 2^-k) and, for fp16 weights, by 2^-8 */
-int affgw_amax_scale(const float* x, long long n, float* scale2, void* workspace4, void* stream);
+int affgw_amax_scale(const float* x, long long n, float* scale2, void* workspace8, void* stream);
 int affgw_split_positions_fmt(const void* src, int dtype, void* planes, const affgw_pos_frame* f, int Hs, int Ws, int C, int pitch,
                               int upsample, int oy0, int ox0, int pad_mode, int pre_act, int passes, float* colsum,
                               int operand_fmt, const float* scale_dev, void* stream);

@@ -47,7 +47,8 @@ class SimConv(torch.autograd.Function):
         fx, fw, fg, pf, pd, pw = spec
         ctx.save_for_backward(x, w)
         ctx.cfg = (stride, padding, spec, b is not None)
-        return F.conv2d(rnd(x, fx, pf), rnd(w, fw, pf, W_SCALE if fw == "f16" else 1.0), b, stride=stride, padding=padding)
+        pfx, pfw = pf if isinstance(pf, tuple) else (pf, pf)      # (planes of x, planes of w): (3, 1) = two MMAs, x split only
+        return F.conv2d(rnd(x, fx, pfx), rnd(w, fw, pfw, W_SCALE if fw == "f16" else 1.0), b, stride=stride, padding=padding)
 
     @staticmethod
     def backward(ctx, dy):
@@ -236,6 +237,20 @@ def main():
         show("  + dis/cla fwd 1", Policy(f3, {**{n: f1 for n in dec_up + dec_res}, "dis.": f1, "cla.": f1}))
         show("  + last 4 VGG fwd 1", Policy(f3, {n: f1 for n in dec_up + dec_res + vgg[12:]}))
         show("  + last 8 VGG fwd 1", Policy(f3, {n: f1 for n in dec_up + dec_res + vgg[8:]}))
+    elif exp == "plans5":
+        dec_up = ["gen.dec.model.%d.conv." % i for i in (2, 4, 6)]
+        dec_res = ["gen.dec.model.0.model.%d.model.%d.conv." % (i, j) for i in (0, 1) for j in (0, 1)]
+        vgg = ["gen.enc_image.model.features.%d." % i for i in (0, 3, 6, 9, 13, 16, 19, 22, 26, 29, 32, 35, 39, 42, 45, 48)]
+        f3, f1 = ("f16", "f16", "f16", 3, 1, 1), ("f16", "f16", "f16", 1, 1, 1)
+        xw = ("f16", "f16", "f16", (3, 1), 1, 1)      # x split, w single plane: 2 MMAs
+        wx = ("f16", "f16", "f16", (1, 3), 1, 1)      # w split, x single plane: 2 MMAs
+        base = {n: f1 for n in dec_up}
+        show("shipping f16: 3/1/1, ups 1", Policy(f3, base))
+        show("  + all VGG fwd 2 MMAs (x split)", Policy(f3, {**base, **{n: xw for n in vgg}}))
+        show("  + all VGG fwd 2 MMAs (w split)", Policy(f3, {**base, **{n: wx for n in vgg}}))
+        show("  + VGG[8:] fwd 2 MMAs (x split)", Policy(f3, {**base, **{n: xw for n in vgg[8:]}}))
+        show("  + dec res fwd 2 MMAs (x split)", Policy(f3, {**base, **{n: xw for n in dec_res}}))
+        show("  + everything but ups fwd 2 MMAs (x split)", Policy(xw, base))
 
 
 if __name__ == "__main__":

@@ -86,7 +86,7 @@ def test_single_channel_stencils(case, thin_route, tc_mode):
         pytest.skip("covered by the generic cases")
     n, h, w_, ci, co, k, s, p, pm, up, pre = case
     # (one bf16 rounding per operand through a tanh on a 64-channel 7x7 sum: looser than the linear cases)
-    tol = TOL[tc_mode] if (thin_route or tc_mode in ("bf16x3", "f16")) else 6e-2
+    tol = TOL[tc_mode] if (thin_route or tc_mode == "bf16x3") else (3e-3 if tc_mode == "f16" else 6e-2)
     g = torch.Generator(device="cuda").manual_seed(4)
     x = torch.randn(n, ci, h, w_, device="cuda", generator=g)
     wgt = torch.randn(co, ci, k, k, device="cuda", generator=g) * (2.0 / (ci * k * k)) ** 0.5
