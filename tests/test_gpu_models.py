@@ -301,7 +301,8 @@ def test_cuda_graph_replay_matches_eager_iterations(specs):
                 drift_eo = max(drift_eo, abs(float(la[k]) - float(lo[k])))
             if it < 3:          # eager, capture pass, first pure replay: before the divergence has had time to grow
                 for lx in (lg, lo):
-                    assert all(abs(float(la[k]) - float(lx[k])) <= 2e-4 * max(1.0, abs(float(la[k]))) for k in la), \
+                    # (1e-3: the run-to-run noise of one forward in this mode is 8e-4 on the image, tests/test_gpu_parity_c50.py)
+                    assert all(abs(float(la[k]) - float(lx[k])) <= 1e-3 * max(1.0, abs(float(la[k]))) for k in la), \
                         (it, {k: (float(la[k]), float(lx[k])) for k in la})
         assert g.graph_launches > 1000 and g._graphs is not None and g._eager_steps == 1
         # the optimiser steps must reach the kernels (packed-weight cache invalidation, ops.weights_updated): the writer
