@@ -1059,12 +1059,23 @@ namespace {
 __global__ void __launch_bounds__(256) amax_scale_kernel(const float* __restrict__ x, long long n, unsigned* __restrict__ ws,
                                                          float* __restrict__ out) {
     float m = 0.f;
-    const long long n4 = n / 4;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const long long n4 = n / 4, stride = (long long)gridDim.x * blockDim.x;
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < n4; i += 4 * stride) {          // four 16-byte loads in flight per thread
+        const float4 a = __ldg(reinterpret_cast<const float4*>(x) + i);
+        const float4 b = __ldg(reinterpret_cast<const float4*>(x) + i + stride);
+        const float4 c = __ldg(reinterpret_cast<const float4*>(x) + i + 2 * stride);
+        const float4 d = __ldg(reinterpret_cast<const float4*>(x) + i + 3 * stride);
+        m = fmaxf(m, fmaxf(fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w))),
+                           fmaxf(fmaxf(fabsf(b.x), fabsf(b.y)), fmaxf(fabsf(b.z), fabsf(b.w)))));
+        m = fmaxf(m, fmaxf(fmaxf(fmaxf(fabsf(c.x), fabsf(c.y)), fmaxf(fabsf(c.z), fabsf(c.w))),
+                           fmaxf(fmaxf(fabsf(d.x), fabsf(d.y)), fmaxf(fabsf(d.z), fabsf(d.w)))));
+    }
+    for (; i < n4; i += stride) {
         const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
         m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
     }
-    if (blockIdx.x == 0) for (long long i = n4 * 4 + threadIdx.x; i < n; i += blockDim.x) m = fmaxf(m, fabsf(x[i]));
+    if (blockIdx.x == 0) for (long long j = n4 * 4 + threadIdx.x; j < n; j += blockDim.x) m = fmaxf(m, fabsf(x[j]));
     for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
     if ((threadIdx.x & 31) == 0 && m > 0.f && m < INFINITY) atomicMax(ws, __float_as_uint(m));     // NaN / inf never enter
     __shared__ bool last;
@@ -1091,7 +1102,8 @@ __global__ void __launch_bounds__(256) amax_scale_kernel(const float* __restrict
 }  // namespace
 
 int amax_scale(const float* x, long long n, float* out2, unsigned* ws, cudaStream_t st) {
-    const int blocks = (int)min((long long)148 * 4, (n / 4 + 255) / 256 + 1);
+    // ~4 float4 per thread; at most 8 blocks per SM (2048 threads): enough bytes in flight for the HBM latency
+    const int blocks = (int)max(1LL, min((long long)148 * 8, (n / 16 + 255) / 256));
     amax_scale_kernel<<<blocks, 256, 0, st>>>(x, n, ws, out2);
     AFFGW_LAUNCH_CHECK("amax_scale");
     return 0;
