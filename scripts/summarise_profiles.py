@@ -6,6 +6,12 @@ Runs in the build container (needs `ncu` for the report import only)."""
 import collections, csv, json, os, re, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 G, P = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
+# round tag and the artifact names of scripts/gpu_profile_pass_r02.sh (round 1 used launches_r01b.csv / prof_shift_r01b / bench.json)
+R = sys.argv[1] if len(sys.argv) > 1 else "r02"
+LAUNCHES = {"r01": "launches_r01b.csv"}.get(R, f"launches_{R}.csv")
+REPORT = {"r01": "prof_shift_r01b.ncu-rep"}.get(R, f"prof_shift_{R}.ncu-rep")
+BENCH = {"r01": "bench.json"}.get(R, f"bench_{R}.json")
+MODE = {"r01": "bf16 mode (3 MMAs per product)"}.get(R, "f16 mode (forward 3 MMAs per product, backward 1)")
 
 
 def short(name):
@@ -14,7 +20,7 @@ def short(name):
 
 
 def launch_list():
-    rows = [r for r in csv.reader(open(os.path.join(G, "launches_r01b.csv"))) if len(r) > 8]
+    rows = [r for r in csv.reader(open(os.path.join(G, LAUNCHES))) if len(r) > 8]
     hdr = rows[0]
     ki, vi = hdr.index("Kernel Name"), hdr.index("Metric Value")
     agg = collections.defaultdict(lambda: [0.0, 0])
@@ -24,8 +30,8 @@ def launch_list():
         a[1] += 1
     total = sum(a[0] for a in agg.values())
     n = sum(a[1] for a in agg.values())
-    with open(os.path.join(P, "r01_launch_list_step.csv"), "w") as f:
-        f.write("# ncu launch list of one eager training step (bench.py --quick --no-graph --steps 1 --warmup 3), r01 final kernels\n")
+    with open(os.path.join(P, f"{R}_launch_list_step.csv"), "w") as f:
+        f.write(f"# ncu launch list of one eager training step (bench.py --quick --no-graph --steps 1 --warmup 3), {R} kernels, {MODE}\n")
         f.write("# command: ncu --metrics gpu__time_duration.sum --clock-control none -s <3 warm-up steps> -c <1 step + margin> --csv python bench.py --quick --no-graph --steps 1 --warmup 3\n")
         f.write("# per-launch times under ncu are cold-cache and serialised: compare SHARES with bench.py \"kernels[*].share_of_step\", not absolutes\n")
         f.write(f"# launches in window {n}, summed kernel time {total:.1f} ms\n")
@@ -37,7 +43,7 @@ def launch_list():
 
 
 def full_capture():
-    rep = os.path.join(G, "prof_shift_r01b.ncu-rep")
+    rep = os.path.join(G, REPORT)
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units = rows[0], rows[1]
@@ -48,9 +54,9 @@ def full_capture():
             "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
             "smsp__cycles_active.avg", "sm__cycles_elapsed.avg.per_second"]
     idx = [hdr.index(k) for k in keep if k in hdr]
-    with open(os.path.join(P, "r01_ncu_full_position_kernels_vgg256.csv"), "w") as f:
-        f.write("# ncu --set full --clock-control none --import-source on -k regex:shift -c 6 python scripts/conv_microbench.py --only vgg_256_256 --reps 1   (r01, final kernels)\n")
-        f.write("# layer: VGG conv3x3 256->256 @ 32x108, batch 64, bf16 mode (3 MMAs per product): 260.9 algorithmic GFLOP per launch, 782.8 executed\n")
+    with open(os.path.join(P, f"{R}_ncu_full_position_kernels_vgg256.csv"), "w") as f:
+        f.write(f"# ncu --set full --clock-control none --import-source on -k regex:shift -c 6 python scripts/conv_microbench.py --only vgg_256_256 --reps 1   ({R} kernels)\n")
+        f.write(f"# layer: VGG conv3x3 256->256 @ 32x108, batch 64, {MODE}: 260.9 algorithmic GFLOP per launch\n")
         w = csv.writer(f)
         w.writerow([f"{hdr[i]} [{units[i]}]" for i in idx])
         for r in rows[2:]:
@@ -83,13 +89,13 @@ def full_capture():
                      "us_per_launch_under_ncu": d["us"] / n, "tensor_pipe_active_pct": d["tensor"] / n,
                      "l1tex_throughput_pct": d["l1"] / n}
         print(name, {k: (round(v, 1) if isinstance(v, float) else v) for k, v in res[name].items() if k != "layer"})
-    json.dump(res, open(os.path.join(P, "r01_traffic.json"), "w"), indent=1)
+    json.dump(res, open(os.path.join(P, f"{R}_traffic.json"), "w"), indent=1)
 
 
 def bench():
-    line = open(os.path.join(G, "bench.json")).read().strip().splitlines()[-1]
+    line = open(os.path.join(G, BENCH)).read().strip().splitlines()[-1]
     d = json.loads(line)
-    json.dump(d, open(os.path.join(P, "r01_bench_n1.json"), "w"), indent=1)
+    json.dump(d, open(os.path.join(P, f"{R}_bench_n1.json"), "w"), indent=1)
     print("bench:", d["value"], "steps/s,", d["ms_per_step"], "ms; e2e", d["e2e"]["value"])
 
 
