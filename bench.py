@@ -446,7 +446,7 @@ def main():
                    "frac": hbm_bytes / max(hbm_ms, 1e-9) / 1e6 / hbm_peak}
 
     try:        # DRAM bytes of the dominant kernel from the committed ncu --set full capture (one layer, see profiles/README.md)
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get(dominant)
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json"))).get(dominant.replace(" f16", ""))
         if tr and roofline:
             roofline["traffic"] = tr["dram_bytes_per_launch"]
             roofline["traffic_note"] = ("ncu dram__bytes_read.sum + dram__bytes_write.sum per launch on " + tr["layer"] +
