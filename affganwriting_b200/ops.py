@@ -16,7 +16,7 @@ import os as _os
 _FUSE_DB = _os.environ.get("AFFGW_FUSE_DB", "1") != "0"
 _THIN = _os.environ.get("AFFGW_THIN", "1") != "0"
 # "passes": tensor-core MMAs per product of (forward, input-gradient, weight-gradient) GEMMs: 3 = split operands, 1 = single
-_state = {"mode": "fp32", "passes": (3, 3, 3), "force_simt": False, "simt_wgrad": False, "fmt": None}
+_state = {"mode": "fp32", "passes": (3, 3, 3), "force_simt": False, "simt_wgrad": False, "fmt": None, "grad_accum": False}
 _MODES = {"fp32": (3, 3, 3), "f16": (3, 1, 1), "bf16": (3, 1, 1), "bf16x3": (3, 3, 3), "bf16x1": (1, 1, 1)}
 _err_flag = {}
 _profile = {"records": None}
@@ -162,6 +162,35 @@ class operand_format:
 
     def __exit__(self, *a):
         _state["fmt"] = self.prev
+
+
+class accumulate_into_grad:
+    """Context manager (opt-in, used by trainer.Trainer around forward + backward): a tensor-core weight / bias gradient whose
+    parameter already HAS a `.grad` is added into that buffer by the weight-gradient kernel's own reduction (it accumulates
+    anyway) and `None` is returned to autograd, instead of materialising a fresh gradient that autograd then adds with an ATen
+    kernel (one extra launch and three tensor passes per shared parameter: the two decodes of gen_update, the two backward
+    calls of dis_update).  Same numbers, same `.grad` afterwards.  NOT for `torch.autograd.grad(...)` users: the functional
+    API expects returned gradients - hence opt-in."""
+
+    def __init__(self, flag=True):
+        self.flag = bool(flag)
+
+    def __enter__(self):
+        self.prev = _state["grad_accum"]
+        _state["grad_accum"] = self.flag
+
+    def __exit__(self, *a):
+        _state["grad_accum"] = self.prev
+
+
+def _grad_slot(p):
+    """The parameter's existing gradient buffer when it can take an in-place accumulation, else None."""
+    if not _state["grad_accum"] or p is None or not p.is_leaf:
+        return None
+    g = p.grad
+    if g is None or g.dtype != torch.float32 or g.shape != p.shape or not g.is_contiguous() or g.device != p.device:
+        return None
+    return g
 
 
 class wgrad_passes(conv_passes):
@@ -545,6 +574,7 @@ class _Conv2d(Function):
         ctx.layout = layout if use_tc else 0
         ctx.thin = thin
         ctx.has_bias, ctx.has_addend = bias is not None, addend is not None
+        ctx.bias_ref = bias
         keep_x = (not use_tc) or thin or cfg.pre_act != "none" or _state["simt_wgrad"]
         ctx.save_for_backward(x if keep_x else None, weight, y if cfg.post_act != "none" else None, planes)
         ctx.x_meta = (x.shape, x.device)
@@ -575,8 +605,13 @@ class _Conv2d(Function):
         use_tc = ctx.use_tc
         # position-space layers: the bias gradient is summed by the kernel that splits dY into operand planes
         fuse_db = use_tc and ctx.layout == L.WLAYOUT_SHIFT and (need_w or need_x) and _FUSE_DB
+        db_ret = True
         if ctx.has_bias and need_b:
-            db = torch.zeros(cout, dtype=torch.float32, device=dev)
+            bias_p = ctx.bias_ref
+            db = _grad_slot(bias_p) if (use_tc and not ctx.thin) else None      # atomics add into the existing .grad
+            db_ret = db is None
+            if db is None:
+                db = torch.zeros(cout, dtype=torch.float32, device=dev)
             if not fuse_db:
                 L.call("affgw_colsum", dz.data_ptr(), L.F32, db.data_ptr(), M, cout, cout, st)
         fwd_cfg = cfg._replace(post_act="none")
@@ -609,8 +644,12 @@ class _Conv2d(Function):
                            ws.data_ptr(), C.byref(dthin), st)
             da = dz if (ctx.has_addend and need_a) else None
             return dx, dw, db, da, None
+        dw_ret = True
         if need_w:
-            dw = torch.zeros(weight.shape, dtype=torch.float32, device=dev)
+            dw = _grad_slot(weight) if (use_tc and not _state["simt_wgrad"]) else None   # the unpack kernel accumulates: dw += partials
+            dw_ret = dw is None
+            if dw is None:
+                dw = torch.zeros(weight.shape, dtype=torch.float32, device=dev)
             if use_tc and not _state["simt_wgrad"]:
                 d = _desc(g, fwd_cfg, cin, L.BF16, L.BF16, L.BF16, L.ALGO_TC, in_pitch=cs, out_pitch=cso, passes=pw, fmt=fmt)
                 ws_bytes = L.lib().affgw_conv2d_wgrad_ws_bytes(C.byref(d))
@@ -668,7 +707,7 @@ class _Conv2d(Function):
                 full[:, :cin] = dx
                 dx = full
         da = dz if (ctx.has_addend and need_a) else None
-        return dx, dw, db, da, None
+        return dx, (dw if dw_ret else None), (db if db_ret else None), da, None
 
 
 def conv2d(x, weight, bias=None, stride=1, pad=0, pad_mode="zero", upsample=1, pre_act="none", post_act="none",

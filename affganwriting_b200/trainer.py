@@ -89,6 +89,10 @@ class Trainer:
     # ------------------------------------------------------------------------------------------------ sub-steps
     def _fwd_bwd(self, name, batch, epoch):
         """zero_grad + forward + backward of one sub-step; returns its loss tensors."""
+        with ops.accumulate_into_grad(True):
+            return self._fwd_bwd_inner(name, batch, epoch)
+
+    def _fwd_bwd_inner(self, name, batch, epoch):
         m = self.model
         self.opt[name].zero_grad()
         if name == "rec":

@@ -368,6 +368,32 @@ def test_short_final_batch_after_capture_runs_eagerly(specs):
         A.set_precision("fp32")
 
 
+def test_accumulate_into_grad_matches_autograd_accumulation():
+    """ops.accumulate_into_grad: a second use of a parameter adds into its existing .grad inside the weight-gradient kernel
+    instead of through autograd's ATen add - same gradients (dis_update's two backward calls, gen_update's two decodes)."""
+    from affganwriting_b200 import ops
+    A.set_precision("f16")
+    try:
+        g = torch.Generator(device="cuda").manual_seed(9)
+        x1 = ops.to_internal(torch.randn(2, 64, 8, 27, device="cuda", generator=g))
+        x2 = ops.to_internal(torch.randn(2, 64, 8, 27, device="cuda", generator=g))
+        out = {}
+        for flag in (False, True):
+            w = torch.nn.Parameter(torch.randn(96, 64, 3, 3, device="cuda", generator=torch.Generator(device="cuda").manual_seed(1)) * 0.05)
+            b = torch.nn.Parameter(torch.zeros(96, device="cuda"))
+            with ops.accumulate_into_grad(flag):
+                ops.conv2d(x1, w, b, pad=1, pad_mode="reflect").square().mean().backward()
+                first = w.grad.data_ptr()
+                (ops.conv2d(x2, w, b, pad=1, pad_mode="reflect").square().mean() * 3).backward()     # second use: accumulates
+                ops.linear(x1.reshape(-1, 64)[:, :64], w[:, :, 0, 0].detach().clone().requires_grad_(), None).sum().backward()
+            out[flag] = (w.grad.clone(), b.grad.clone(), w.grad.data_ptr() == first)
+        assert out[True][2]                                       # accumulated in place
+        assert float((out[True][0] - out[False][0]).abs().max()) <= 1e-6 * float(out[False][0].abs().max())
+        assert float((out[True][1] - out[False][1]).abs().max()) <= 1e-5 * float(out[False][1].abs().max())
+    finally:
+        A.set_precision("fp32")
+
+
 def test_adam_step_invalidates_packed_weight_cache():
     """optim.Adam updates parameters through raw pointers (no autograd version bump): the step itself must invalidate the
     packed bf16 operand copies the convolutions cache per parameter."""
