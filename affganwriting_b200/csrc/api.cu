@@ -109,6 +109,8 @@ int attn_ctx_fwd(const float* energy, const float* enc, const long long* sidx, f
                  cudaStream_t st);
 int attn_ctx_bwd(const float* dattn, const float* dctx, const float* attn, const float* enc, const long long* sidx, float* denergy,
                  float* denc, int N, int T, int F, cudaStream_t st);
+int blur3(const float* x, float* y, int N, int H, int W, int C, cudaStream_t st);
+int pixelnorm(const float* x, float* y, int rows, int C, float eps, cudaStream_t st);
 int label_smooth_kl_fwd(const float* x, const long long* y, float* loss, int rows, int V, int pad, float smoothing, int* err,
                         cudaStream_t st);
 int label_smooth_kl_bwd(const float* x, const long long* y, const float* gout, float* dx, int rows, int V, int pad, float smoothing,
@@ -756,6 +758,14 @@ int affgw_attn_ctx_bwd(const float* dattn, const float* dctx, const float* attn,
                        float* denergy, float* denc, int N, int T, int F, void* s) {
     REQ(dctx && attn && enc && sample && denergy && denc && N > 0 && T > 0 && F > 0, "attn_ctx_bwd");
     return attn_ctx_bwd(dattn, dctx, attn, enc, sample, denergy, denc, N, T, F, S(s));
+}
+int affgw_blur3(const float* x, float* y, int N, int H, int W, int C, void* s) {
+    REQ(x && y && x != y && N > 0 && H > 0 && W > 0 && C > 0, "blur3");
+    return blur3(x, y, N, H, W, C, S(s));
+}
+int affgw_pixelnorm(const float* x, float* y, int rows, int C, float eps, void* s) {
+    REQ(x && y && rows > 0 && C > 0 && eps >= 0.f, "pixelnorm");
+    return pixelnorm(x, y, rows, C, eps, S(s));
 }
 int affgw_label_smooth_kl_fwd(const float* x, const long long* y, float* loss, int rows, int V, int pad_idx, float smoothing,
                               int* err, void* s) {

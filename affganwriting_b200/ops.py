@@ -1201,3 +1201,85 @@ def label_smoothing_kl(x, y, pad_idx, smoothing):
     """crit(log_softmax(x), y) of the reference (loss_tro.py:8-35, network_tro.py:44-45): KL(sum) against the smoothed
     one-hot; x [rows, V] logits, y [rows] int64."""
     return _LabelSmoothKl.apply(x, y, pad_idx, smoothing)
+
+
+# ------------------------------------------------------------------------------------------------ line-level generator pieces
+def conv_transpose2d(x, weight, bias=None, stride=2, pad=1):
+    """F.conv_transpose2d(x, weight [Cin, Cout, K, K], bias, stride, padding) - FusedUpsample of the line-level generator
+    (line_generation/model/pure_gen.py:268-279) - computed as what it is: the input gradient of the stride-`stride` convolution
+    with the same weight, on the dgrad kernels (zero-insertion gather).  Forward only (generation); x [N, Cin, H, W] internal."""
+    if torch.is_grad_enabled() and (x.requires_grad or weight.requires_grad):
+        raise RuntimeError("conv_transpose2d is a generation-only operator (call it under torch.no_grad())")
+    x = _dense_cl(input_to_internal(x))
+    n, cv, h, w = x.shape
+    cv_w, cu, kh, kw = weight.shape
+    if cv_w != cv or kh != kw:
+        raise RuntimeError("conv_transpose2d: weight must be [Cin, Cout, K, K] with Cin matching the input")
+    hu, wu = (h - 1) * stride - 2 * pad + kh, (w - 1) * stride - 2 * pad + kw
+    # the forward convolution whose input gradient this is: U [n, cu, hu, wu] -> V [n, cv, h, w]
+    g = dict(N=n, H=hu, W=wu, Cx=cu, pitch=cu, Cout=cv, Cin=cu, KH=kh, KW=kw, Ho=h, Wo=w, two_d=False)
+    cfg = ConvCfg(int(stride), int(pad), "zero", 1, "none", "none", None, int(stride))
+    st = L.stream()
+    out = empty_cl(n, cu, hu, wu, torch.float32, x.device)
+    use_tc = _state["mode"] != "fp32" and not _state["force_simt"]
+    if use_tc:
+        passes = _state["passes"][0]                      # this is a FORWARD computation: the mode's forward pass count
+        fmt = L.FMT_F16 if _state["mode"] == "f16" else L.FMT_BF16
+        cs, cso = _up8(cu), _up8(cv)
+        d = _desc(g, cfg, cu, L.BF16, L.BF16, L.BF16, L.ALGO_TC, in_pitch=cs, out_pitch=cso, passes=passes, grad_dt=L.F32, fmt=fmt)
+        layout = L.lib().affgw_conv_tc_layout(C.byref(d), 1)
+        if not layout:
+            raise RuntimeError("conv_transpose2d: tcgen05 kernels refused the shape: " + L.last_error())
+        if layout == L.WLAYOUT_SHIFT:
+            raise RuntimeError("conv_transpose2d: unexpected position-space layout for a strided convolution")
+        planes = _split_planes(x, n * h * w, cv, cv, passes, fmt=fmt)
+        wt = _pack_tc(weight, cso, True, passes, layout, fmt)
+        src = planes
+    else:
+        d = _desc(g, cfg, cu, L.F32, L.F32, L.F32, L.ALGO_SIMT)
+        wt = _pack(weight, torch.float32, cv, True)
+        src = x
+    ws_bytes = L.lib().affgw_conv2d_dgrad_ws_bytes(C.byref(d))
+    if ws_bytes < 0:
+        raise RuntimeError("conv_transpose2d: " + L.last_error())
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device) if ws_bytes else None
+    L.call("affgw_conv2d_dgrad_scaled", src.data_ptr(), wt.data_ptr(), None, out.data_ptr(), L.ptr(ws), C.byref(d), None, st)
+    if bias is not None:
+        b = bias.detach().float().reshape(1, cu).expand(n, cu).contiguous()
+        res = torch.empty_like(out)
+        L.call("affgw_bcast_add", out.data_ptr(), b.data_ptr(), res.data_ptr(), L.dt(out), n, hu * wu, cu, 1.0, st)
+        out = res
+    return out
+
+
+class _Blur3(Function):
+    """Depthwise 3x3 binomial blur, zero padding (Blur, pure_gen.py:123-136); symmetric kernel: backward = the same blur."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = _dense_cl(x)
+        n, c, h, w = x.shape
+        y = torch.empty_like(x)
+        L.call("affgw_blur3", x.data_ptr(), y.data_ptr(), n, h, w, c, L.stream(), nbytes=2 * _nb(x))
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = _dense_cl(dy, torch.float32)
+        n, c, h, w = dy.shape
+        dx = torch.empty_like(dy)
+        L.call("affgw_blur3", dy.data_ptr(), dx.data_ptr(), n, h, w, c, L.stream(), nbytes=2 * _nb(dy))
+        return dx
+
+
+def blur3(x):
+    return _Blur3.apply(input_to_internal(x))
+
+
+def pixel_norm(x, eps=1e-8):
+    """x / sqrt(mean(x^2, dim=1) + eps) for a [rows, C] tensor (PixelNorm, pure_gen.py:306-311).  Forward only."""
+    L.require_cuda(x)
+    x = x.detach().float().contiguous()
+    y = torch.empty_like(x)
+    L.call("affgw_pixelnorm", x.data_ptr(), y.data_ptr(), x.shape[0], x.shape[1], float(eps), L.stream())
+    return y

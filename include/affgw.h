@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define AFFGW_VERSION 109
+#define AFFGW_VERSION 110
 
 enum { AFFGW_DT_F32 = 0, AFFGW_DT_BF16 = 1 };
 enum { AFFGW_ACT_NONE = 0, AFFGW_ACT_RELU = 1, AFFGW_ACT_LRELU = 2, AFFGW_ACT_TANH = 3 };
@@ -253,6 +253,12 @@ int affgw_attn_ctx_fwd(const float* energy, const float* enc, const long long* s
                        void* stream);
 int affgw_attn_ctx_bwd(const float* dattn, const float* dctx, const float* attn, const float* enc, const long long* sample,
                        float* denergy, float* denc, int N, int T, int F, void* stream);
+
+/* ---- line-level generator (line_generation/model/pure_gen.py) ------------------------------------------
+ * depthwise 3x3 binomial blur (1,2,1)x(1,2,1)/16, zero padding, fp32 NHWC (Blur, pure_gen.py:123-136); symmetric, so the same
+ * call is its own backward.  PixelNorm over the last dimension (pure_gen.py:306-311). */
+int affgw_blur3(const float* x, float* y, int N, int H, int W, int C, void* stream);
+int affgw_pixelnorm(const float* x, float* y, int rows, int C, float eps, void* stream);
 
 /* Recogniser loss of the GAN step: crit(log_softmax(x), y) = LabelSmoothing(vocab, PAD, 0.4) over KLDivLoss(reduction='sum')
  * (reference loss_tro.py:8-35 as called at network_tro.py:44-45,92-93).  x [rows][V] fp32 logits, y [rows] int64 targets;
