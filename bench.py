@@ -392,6 +392,24 @@ def main():
         except Exception as e:           # never fatal for the headline
             full_iter = {"error": repr(e)[:300]}
 
+    # ---- BASELINE.json configs[4]: line-level generator, 64 x 1024 lines (T = 256 spaced characters), batch 32 per GPU
+    line_gen = None
+    try:
+        from affganwriting_b200.linegen import SpacedGenerator
+        lg = SpacedGenerator(80, 128, 256, n_style_trans=6, emb_dropout=False, append_style=True).to(dev).eval()
+        gl = torch.Generator(device=dev).manual_seed(5)
+        idx = torch.randint(0, 80, (256, 32), device=dev, generator=gl)
+        content = torch.zeros(256, 32, 80, device=dev).scatter_(2, idx.unsqueeze(2), 1.0)
+        style = torch.randn(32, 128, device=dev, generator=gl)
+        for _ in range(3):
+            lg(content, style)
+        ms_line = timed(lambda: lg(content, style), 10) / 10
+        line_gen = {"images_per_sec": world * 32 / (ms_line / 1e3), "ms_per_batch": ms_line, "batch_per_gpu": 32,
+                    "image": "64x1024", "note": "SpacedGenerator forward (line_generation/model/pure_gen.py:42-50), eager launches, noise drawn on the device"}
+        del lg
+    except Exception as e:
+        line_gen = {"error": repr(e)[:300]}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -495,7 +513,7 @@ def main():
             "achieved_tflops_per_gpu": STEP_GFLOP_PER_SAMPLE * B / 1e3 / (ms_step / 1e3),
             "frac_of_peak": STEP_GFLOP_PER_SAMPLE * B / 1e3 / (ms_step / 1e3) / tf_peak},
         "cpu_baseline": cpu_baseline,
-        "extra": {"full_iteration_with_recogniser": full_iter, "gen_images_per_sec": gen_img_s, "gen_batch_per_gpu": B, "gen_ms_per_batch": ms_gen,
+        "extra": {"full_iteration_with_recogniser": full_iter, "line_generator": line_gen, "gen_images_per_sec": gen_img_s, "gen_batch_per_gpu": B, "gen_ms_per_batch": ms_gen,
                   "gen_frac_of_peak": None if args.encoder != "vgg" else 62.17e-3 * gen_img_s / world / tf_peak},
     }
     print(json.dumps(line), flush=True)

@@ -72,7 +72,7 @@ def test_linegen_forward_matches_reference_image(mode):
             assert y.shape == ref.shape
             err = float((y.float().cpu() - ref).abs().max() / ref.abs().max())
             print(f"\n[{mode}] line generator {case}: max error relative to max|image| {err:.2e}, {A.launch_count() - n0} launches")
-            assert err <= {"fp32": 1e-4, "f16": 5e-3, "bf16": 2e-2}[mode]
+            assert err <= {"fp32": 1e-5, "f16": 1e-4, "bf16": 1e-3}[mode]      # measured on B200: 4e-7 / 7e-7 / 1e-5
         with pytest.raises(RuntimeError):                    # generation only: no silent autograd through the transposed convolutions
             with torch.enable_grad():
                 g.conv[3].conv1[0](torch.randn(1, 64, 4, 8, device="cuda", requires_grad=True))
