@@ -113,6 +113,10 @@ SIGNATURES = {
     "affgw_attn_energy_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
     "affgw_attn_ctx_fwd": [_P, _P, _P, _P, _P, _I, _I, _I, _P],
     "affgw_attn_ctx_bwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
+    "affgw_layernorm_fwd": [_P, _P, _P, _P, _L, _I, _F, _P],
+    "affgw_gelu_fwd": [_P, _P, _L, _P],
+    "affgw_scale_residual": [_P, _P, _P, _P, _L, _I, _P],
+    "affgw_attention_fwd": [_P, _P, _I, _I, _I, _I, _F, _P],
     "affgw_blur3": [_P, _P, _I, _I, _I, _I, _P],
     "affgw_pixelnorm": [_P, _P, _I, _I, _F, _P],
     "affgw_label_smooth_kl_fwd": [_P, _P, _P, _I, _I, _I, _F, _P, _P],

@@ -109,6 +109,10 @@ int attn_ctx_fwd(const float* energy, const float* enc, const long long* sidx, f
                  cudaStream_t st);
 int attn_ctx_bwd(const float* dattn, const float* dctx, const float* attn, const float* enc, const long long* sidx, float* denergy,
                  float* denc, int N, int T, int F, cudaStream_t st);
+int layernorm_fwd(const float* x, const float* w, const float* b, float* y, long long rows, int D, float eps, cudaStream_t st);
+int gelu_fwd(const float* x, float* y, long long n, cudaStream_t st);
+int scale_residual(const float* x, const float* t, const float* gamma, float* y, long long n, int D, cudaStream_t st);
+int attention_fwd(const float* qkv, float* out, int B, int N, int H, int hd, float scale, cudaStream_t st);
 int blur3(const float* x, float* y, int N, int H, int W, int C, cudaStream_t st);
 int pixelnorm(const float* x, float* y, int rows, int C, float eps, cudaStream_t st);
 int label_smooth_kl_fwd(const float* x, const long long* y, float* loss, int rows, int V, int pad, float smoothing, int* err,
@@ -758,6 +762,22 @@ int affgw_attn_ctx_bwd(const float* dattn, const float* dctx, const float* attn,
                        float* denergy, float* denc, int N, int T, int F, void* s) {
     REQ(dctx && attn && enc && sample && denergy && denc && N > 0 && T > 0 && F > 0, "attn_ctx_bwd");
     return attn_ctx_bwd(dattn, dctx, attn, enc, sample, denergy, denc, N, T, F, S(s));
+}
+int affgw_layernorm_fwd(const float* x, const float* w, const float* b, float* y, long long rows, int D, float eps, void* s) {
+    REQ(x && w && b && y && rows > 0 && D > 0 && eps >= 0.f, "layernorm_fwd");
+    return layernorm_fwd(x, w, b, y, rows, D, eps, S(s));
+}
+int affgw_gelu_fwd(const float* x, float* y, long long n, void* s) {
+    REQ(x && y && n > 0, "gelu_fwd");
+    return gelu_fwd(x, y, n, S(s));
+}
+int affgw_scale_residual(const float* x, const float* t, const float* gamma, float* y, long long n, int D, void* s) {
+    REQ(x && t && y && n > 0 && D > 0 && n % D == 0, "scale_residual");
+    return scale_residual(x, t, gamma, y, n, D, S(s));
+}
+int affgw_attention_fwd(const float* qkv, float* out, int B, int N, int H, int hd, float scale, void* s) {
+    REQ(qkv && out && B > 0 && N > 0 && H > 0 && hd > 0, "attention_fwd");
+    return attention_fwd(qkv, out, B, N, H, hd, scale, S(s));
 }
 int affgw_blur3(const float* x, float* y, int N, int H, int W, int C, void* s) {
     REQ(x && y && x != y && N > 0 && H > 0 && W > 0 && C > 0, "blur3");

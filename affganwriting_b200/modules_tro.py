@@ -208,8 +208,8 @@ class Decoder(nn.Module):
 
 
 def make_encoder(name, in_channels=None):
-    """'vgg' (ImageEncoder, the north-star path), 'resnet50' (the encoder active in the reference, modules_tro.py:219) or
-    'resnet18' (modules_tro2.py:447-516)."""
+    """'vgg' (ImageEncoder, the north-star path), 'resnet50' (the encoder active in the reference, modules_tro.py:219),
+    'resnet18' (modules_tro2.py:447-516) or 'dino' (dinomodel.py: DINOv2 ViT-L/14, generation only)."""
     from .load_data import NUM_CHANNEL
     from .resnet_encoder import ImageEncoderResNet18, ImageEncoderResNet50
     c = NUM_CHANNEL if in_channels is None else in_channels
@@ -219,6 +219,9 @@ def make_encoder(name, in_channels=None):
         return ImageEncoderResNet50(weight_path=None, in_channels=c)
     if name == "resnet18":
         return ImageEncoderResNet18(weight_path=None, in_channels=c)
+    if name in ("dino", "dinov2"):                    # modules_tro.py:214 (commented line): generation only
+        from .dinomodel import ImageEncoderDINOv2
+        return ImageEncoderDINOv2(None, arch="vitl14", ckpt_path=None, in_channels=c, final_size=(8, 27), tap_blocks=[4, 8, 16, 23])
     raise ValueError(f"unknown style encoder {name!r}")
 
 

@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define AFFGW_VERSION 110
+#define AFFGW_VERSION 111
 
 enum { AFFGW_DT_F32 = 0, AFFGW_DT_BF16 = 1 };
 enum { AFFGW_ACT_NONE = 0, AFFGW_ACT_RELU = 1, AFFGW_ACT_LRELU = 2, AFFGW_ACT_TANH = 3 };
@@ -253,6 +253,14 @@ int affgw_attn_ctx_fwd(const float* energy, const float* enc, const long long* s
                        void* stream);
 int affgw_attn_ctx_bwd(const float* dattn, const float* dctx, const float* attn, const float* enc, const long long* sample,
                        float* denergy, float* denc, int N, int T, int F, void* stream);
+
+/* ---- DINOv2 ViT style encoder (BASELINE.json configs[3]: GAN_word/dinomodel.py around a ViT backbone), forward only --------
+ * LayerNorm over the last dimension; exact (erf) GELU; y = x + gamma[c] * t (LayerScale + residual; gamma may be NULL = 1);
+ * multi-head self-attention of qkv [B][N][3][H][hd] (Linear(D, 3D) output) -> [B][N][H*hd], N <= 128 tokens. */
+int affgw_layernorm_fwd(const float* x, const float* w, const float* b, float* y, long long rows, int D, float eps, void* stream);
+int affgw_gelu_fwd(const float* x, float* y, long long n, void* stream);
+int affgw_scale_residual(const float* x, const float* t, const float* gamma, float* y, long long n, int D, void* stream);
+int affgw_attention_fwd(const float* qkv, float* out, int B, int N, int H, int hd, float scale, void* stream);
 
 /* ---- line-level generator (line_generation/model/pure_gen.py) ------------------------------------------
  * depthwise 3x3 binomial blur (1,2,1)x(1,2,1)/16, zero padding, fp32 NHWC (Blur, pure_gen.py:123-136); symmetric, so the same

@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol():
     assert len(names) >= 45
     for n in names:
         assert hasattr(h, n), n
-    assert h.affgw_version() == 110
+    assert h.affgw_version() == 111
 
 
 def test_python_binding_covers_the_header():

@@ -1,0 +1,98 @@
+"""DINOv2 style encoder (BASELINE.json configs[3]).  The reference ships the wrapper only (GAN_word/dinomodel.py); its backbone is
+an absent torch.hub dependency, so: the WRAPPER is pinned against the unmodified reference run around a small stand-in ViT
+(tests/golden/dino.npz, oracle/make_golden_dino.py); the backbone follows the public DINOv2 definition and its parity with the
+real hub module is UNPINNED (oracle/dino_oracle.py header)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import affgw_oracle as O
+from oracle import dino_oracle as DO
+from oracle import weights as W
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _state():
+    meta = json.load(open(os.path.join(GOLDEN, "dino_spec.json")))
+    sd = W.make_state(meta["spec"])
+    for k in meta["spec"]:
+        if k.endswith(("norm1.weight", "norm2.weight", "norm.weight", ".gamma")):
+            sd[k] = sd[k] + 1.0
+    return meta, sd
+
+
+def test_dino_oracle_matches_reference_wrapper():
+    meta, sd = _state()
+    assert all(r["max_abs"] <= r["tol"] for r in meta["report"])
+    gold = np.load(os.path.join(GOLDEN, "dino.npz"))
+    x = O.synthetic_batch(2, 50)["tr_img"]
+    with torch.no_grad():
+        res = DO.dino_encoder(x, sd, meta["arch"]["num_heads"], meta["taps"])
+    assert [tuple(r.shape) for r in res] == [tuple(gold[f"result{i}.shape"]) for i in range(5)]
+    for i in (1, 4):
+        ref = torch.from_numpy(gold[f"result{i}"])
+        assert float((res[i] - ref).abs().max() / ref.abs().max()) <= 1e-5
+
+
+def test_dino_dropin_state_dict_layout():
+    from affganwriting_b200.dinomodel import ImageEncoderDINOv2
+    meta, sd = _state()
+    enc = ImageEncoderDINOv2("/ignored", arch=meta["arch"], in_channels=50, final_size=(8, 27), tap_blocks=meta["taps"])
+    assert list(enc.state_dict().keys()) == list(meta["spec"].keys())
+    assert all(list(v.shape) == meta["spec"][k] for k, v in enc.state_dict().items())
+    enc.load_state_dict(sd, strict=True)
+    big = ImageEncoderDINOv2(None, arch="vitl14")
+    assert big.tap_blocks == [0, 8, 15, 23] and len(big.model.blocks) == 24 and big.embed_dim == 1024     # dinomodel.py:80-86 default taps
+    assert tuple(big.model.patch_embed.proj.weight.shape) == (1024, 50, 14, 14)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["fp32", "f16"])
+def test_dino_encoder_matches_reference_wrapper(mode):
+    import affganwriting_b200 as A
+    from affganwriting_b200.dinomodel import ImageEncoderDINOv2
+    meta, sd = _state()
+    gold = np.load(os.path.join(GOLDEN, "dino.npz"))
+    A.set_precision(mode)
+    try:
+        enc = ImageEncoderDINOv2(None, arch=meta["arch"], in_channels=50, final_size=(8, 27), tap_blocks=meta["taps"])
+        enc.load_state_dict(sd)
+        enc = enc.cuda().eval()
+        x = O.synthetic_batch(2, 50)["tr_img"].cuda()
+        n0 = A.launch_count()
+        res = enc(x)
+        tol = {"fp32": 1e-4, "f16": 2e-3}[mode]
+        for i in range(5):
+            assert tuple(res[i].shape) == tuple(gold[f"result{i}.shape"])
+            assert abs(float(res[i].float().abs().mean()) - float(gold[f"result{i}.abs_mean"])) <= tol * float(gold[f"result{i}.abs_mean"]) * 10
+        errs = {}
+        for i in (1, 4):
+            ref = torch.from_numpy(gold[f"result{i}"])
+            errs[i] = float((res[i].float().cpu() - ref).abs().max() / ref.abs().max())
+        print(f"\n[{mode}] DINO wrapper vs reference (stand-in backbone): relative max error {errs}, {A.launch_count() - n0} launches")
+        assert all(e <= tol for e in errs.values()), errs
+    finally:
+        A.set_precision("fp32")
+
+
+@pytest.mark.gpu
+def test_generator_with_vitl14_encoder_generates():
+    """configs[3] wiring: GenModel_FC with the ViT-L/14 encoder (random weights), eval-mode generation at batch 4."""
+    import affganwriting_b200 as A
+    from affganwriting_b200 import modules_tro as M
+    A.set_precision("f16")
+    try:
+        torch.manual_seed(0)
+        gen = M.GenModel_FC(12, encoder="dino").cuda().eval()
+        b = O.synthetic_batch(4, 50)
+        with torch.no_grad():
+            res = gen.enc_image(b["tr_img"].cuda())
+            assert [tuple(r.shape) for r in res] == [(4, 512, 5, 16)] * 4 + [(4, 512, 8, 27)]
+            img = gen(b["tr_img"].cuda(), b["label_xt"].cuda())
+        assert img.shape == (4, 1, 64, 216) and torch.isfinite(img).all() and float(img.abs().max()) <= 1.0
+    finally:
+        A.set_precision("fp32")
