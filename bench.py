@@ -410,6 +410,23 @@ def main():
     except Exception as e:
         line_gen = {"error": repr(e)[:300]}
 
+    # ---- BASELINE.json configs[3]: DINOv2 ViT-L/14 style encoder + AdaIN decoder, generation at batch 256 per GPU
+    dino_gen = None
+    try:
+        from affganwriting_b200 import modules_tro as M
+        torch.manual_seed(1)
+        dg = M.GenModel_FC(12, encoder="dino").to(dev).eval()
+        big = LD.batch_to_device(synthetic_batch(256, NUM_CHANNEL, seed=99 + rank), dev)
+        with torch.no_grad():
+            for _ in range(2):
+                dg(big[3], big[7])
+            ms_dino = timed(lambda: dg(big[3], big[7]), 3) / 3
+        dino_gen = {"images_per_sec": world * 256 / (ms_dino / 1e3), "ms_per_batch": ms_dino, "batch_per_gpu": 256,
+                    "note": "GenModel_FC(encoder=ImageEncoderDINOv2 vitl14, taps [4, 8, 16, 23]) forward under eval(), random weights, eager launches"}
+        del dg, big
+    except Exception as e:
+        dino_gen = {"error": repr(e)[:300]}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -513,7 +530,7 @@ def main():
             "achieved_tflops_per_gpu": STEP_GFLOP_PER_SAMPLE * B / 1e3 / (ms_step / 1e3),
             "frac_of_peak": STEP_GFLOP_PER_SAMPLE * B / 1e3 / (ms_step / 1e3) / tf_peak},
         "cpu_baseline": cpu_baseline,
-        "extra": {"full_iteration_with_recogniser": full_iter, "line_generator": line_gen, "gen_images_per_sec": gen_img_s, "gen_batch_per_gpu": B, "gen_ms_per_batch": ms_gen,
+        "extra": {"full_iteration_with_recogniser": full_iter, "line_generator": line_gen, "dino_generation": dino_gen, "gen_images_per_sec": gen_img_s, "gen_batch_per_gpu": B, "gen_ms_per_batch": ms_gen,
                   "gen_frac_of_peak": None if args.encoder != "vgg" else 62.17e-3 * gen_img_s / world / tf_peak},
     }
     print(json.dumps(line), flush=True)

@@ -65,7 +65,7 @@ def test_dino_encoder_matches_reference_wrapper(mode):
         x = O.synthetic_batch(2, 50)["tr_img"].cuda()
         n0 = A.launch_count()
         res = enc(x)
-        tol = {"fp32": 1e-4, "f16": 2e-3}[mode]
+        tol = {"fp32": 1e-5, "f16": 1e-4}[mode]        # measured on B200: 1.3e-6 / 2.7e-6
         for i in range(5):
             assert tuple(res[i].shape) == tuple(gold[f"result{i}.shape"])
             assert abs(float(res[i].float().abs().mean()) - float(gold[f"result{i}.abs_mean"])) <= tol * float(gold[f"result{i}.abs_mean"]) * 10
