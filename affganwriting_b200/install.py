@@ -49,6 +49,13 @@ def install(ref_blocks="blocks", ref_modules="modules_tro", ref_network="network
     # the encoder the reference's GenModel_FC constructs by default (modules_tro.py:219)
     if hasattr(rm, "ImageEncoderResNet50"):
         _swap(rm, ref_modules, "ImageEncoderResNet50", _resnet.ImageEncoderResNet50, done)
+    # the DINOv2 wrapper (dinomodel.py; modules_tro.py:29 imports the class by name) - generation only
+    from . import dinomodel as _dino
+    if hasattr(rm, "ImageEncoderDINOv2"):
+        _swap(rm, ref_modules, "ImageEncoderDINOv2", _dino.ImageEncoderDINOv2, done)
+    dm = sys.modules.get("dinomodel")
+    if dm is not None and hasattr(dm, "ImageEncoderDINOv2"):
+        _swap(dm, "dinomodel", "ImageEncoderDINOv2", _dino.ImageEncoderDINOv2, done)
     nt = sys.modules.get(ref_network)
     if nt is not None:
         for n in ("GenModel_FC", "DisModel", "WriterClaModel") + (("RecModel",) if recogniser else ()):
@@ -60,6 +67,22 @@ def install(ref_blocks="blocks", ref_modules="modules_tro", ref_network="network
         from . import Resnet18 as _r18
         for n in ("conv3x3", "BasicBlock", "ResNet18"):
             _swap(r18, "Resnet18", n, getattr(_r18, n), done)
+    return done
+
+
+def install_line_generation(ref_module="model.pure_gen"):
+    """Same for the line-level generator of `line_generation/` (generation only): replaces SpacedGenerator and its building
+    blocks inside the reference's `model.pure_gen`, so `HWWithStyle` (hw_with_style.py:204) builds the libaffgw generator."""
+    from . import linegen as _lg
+    done = []
+    mod = sys.modules.get(ref_module) or importlib.import_module(ref_module)
+    for n in ("SpacedGenerator", "StyledConvBlock", "AdaptiveInstanceNorm", "NoiseInjection", "Blur", "FusedUpsample",
+              "EqualConv2d", "PixelNorm"):
+        if hasattr(mod, n):
+            _swap(mod, ref_module, n, getattr(_lg, n), done)
+    hw = sys.modules.get("model.hw_with_style")
+    if hw is not None and hasattr(hw, "SpacedGenerator"):
+        _swap(hw, "model.hw_with_style", "SpacedGenerator", _lg.SpacedGenerator, done)
     return done
 
 
