@@ -16,7 +16,8 @@ import os as _os
 _FUSE_DB = _os.environ.get("AFFGW_FUSE_DB", "1") != "0"
 _THIN = _os.environ.get("AFFGW_THIN", "1") != "0"
 # "passes": tensor-core MMAs per product of (forward, input-gradient, weight-gradient) GEMMs: 3 = split operands, 1 = single
-_state = {"mode": "fp32", "passes": (3, 3, 3), "force_simt": False, "simt_wgrad": False, "fmt": None, "grad_accum": False}
+_state = {"mode": "fp32", "passes": (3, 3, 3), "force_simt": False, "simt_wgrad": False, "fmt": None, "grad_accum": False,
+          "wgrad_side": None}
 _MODES = {"fp32": (3, 3, 3), "f16": (3, 1, 1), "bf16": (3, 1, 1), "bf16x3": (3, 3, 3), "bf16x1": (1, 1, 1)}
 _err_flag = {}
 _profile = {"records": None}
@@ -181,6 +182,70 @@ class accumulate_into_grad:
 
     def __exit__(self, *a):
         _state["grad_accum"] = self.prev
+
+
+class wgrad_side_stream:
+    """Context manager (opt-in, used by trainer.Trainer around forward + backward): the tensor-core WEIGHT-gradient GEMMs of the
+    backward passes issued inside are launched on a second CUDA stream, forked from the launching stream after the layer's dY
+    operand planes are written and joined when the context exits.  Nothing in a backward pass reads a weight gradient, so this
+    takes ~15 ms of tensor-bound kernels off the dependency chain dY -> dgrad -> norm backward -> next layer's dY: they run
+    beside the HBM-bound kernels of the following layers and fill the SMs a kernel's last wave leaves idle.  Inside a CUDA-graph
+    capture the fork / join become graph edges (two branches of one graph).
+
+    Each weight gradient is written straight into the parameter's `.grad` (created here when it is None; accumulated inside
+    the kernel's own reduction when it exists) and `None` is returned to autograd, so no autograd kernel ever touches a buffer
+    the side stream is still writing.  The operand planes the side stream reads are kept alive until the join (they are
+    allocated on, and returned to, the launching stream).  Same numbers, same `.grad` afterwards - once the context has exited;
+    not for `torch.autograd.grad(...)`.  Implies accumulate_into_grad."""
+
+    _streams = {}
+
+    def __init__(self, flag=True):
+        self.flag = bool(flag)
+
+    def __enter__(self):
+        self.prev = (_state["wgrad_side"], _state["grad_accum"])
+        if self.flag:
+            dev = torch.cuda.current_device()
+            st = wgrad_side_stream._streams.get(dev)
+            if st is None:
+                st = wgrad_side_stream._streams[dev] = torch.cuda.Stream(device=dev)
+            _state["wgrad_side"] = {"stream": st, "keep": [], "forked": False}
+            _state["grad_accum"] = True
+        return self
+
+    def join(self):
+        side = _state["wgrad_side"]
+        if side is not None and side["forked"]:
+            torch.cuda.current_stream().wait_stream(side["stream"])
+            side["forked"] = False
+        if side is not None:
+            side["keep"].clear()
+
+    def __exit__(self, *a):
+        if self.flag:
+            self.join()
+        _state["wgrad_side"], _state["grad_accum"] = self.prev
+
+
+class _on_wgrad_stream:
+    """Fork the side stream from the launching stream and make it current; `keep` = tensors it reads (alive until the join)."""
+
+    def __init__(self, side, keep):
+        self.side = side
+        if side is not None:
+            side["keep"].append(keep)
+
+    def __enter__(self):
+        if self.side is not None:
+            self.side["stream"].wait_stream(torch.cuda.current_stream())
+            self.side["forked"] = True
+            self.ctx = torch.cuda.stream(self.side["stream"])
+            self.ctx.__enter__()
+
+    def __exit__(self, *a):
+        if self.side is not None:
+            self.ctx.__exit__(*a)
 
 
 def _grad_slot(p):
@@ -646,20 +711,28 @@ class _Conv2d(Function):
             return dx, dw, db, da, None
         dw_ret = True
         if need_w:
-            dw = _grad_slot(weight) if (use_tc and not _state["simt_wgrad"]) else None   # the unpack kernel accumulates: dw += partials
+            tc_w = use_tc and not _state["simt_wgrad"]
+            dw = _grad_slot(weight) if tc_w else None   # the unpack kernel accumulates: dw += partials
             dw_ret = dw is None
+            side = _state["wgrad_side"] if tc_w else None
             if dw is None:
                 dw = torch.zeros(weight.shape, dtype=torch.float32, device=dev)
-            if use_tc and not _state["simt_wgrad"]:
+                if side is not None and weight.is_leaf and weight.grad is None:
+                    weight.grad = dw            # ops.wgrad_side_stream: autograd never handles a buffer the side stream writes
+                    dw_ret = False
+                else:
+                    side = None
+            if tc_w:
                 d = _desc(g, fwd_cfg, cin, L.BF16, L.BF16, L.BF16, L.ALGO_TC, in_pitch=cs, out_pitch=cso, passes=pw, fmt=fmt)
                 ws_bytes = L.lib().affgw_conv2d_wgrad_ws_bytes(C.byref(d))
                 if ws_bytes <= 0:
                     raise RuntimeError("conv2d_wgrad: tcgen05 kernel refused the shape: " + L.last_error())
                 wsb = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-                with _timed("conv_wgrad_tcgen05", flops,
-                            (ctx.tag, _kernel_name(d, 2, pw)) if _profile["records"] is not None else ctx.tag):
-                    L.call("affgw_conv2d_wgrad_scaled", planes.data_ptr(), dzp.data_ptr(), dw.data_ptr(), wsb.data_ptr(), C.byref(d),
-                           None if dy_scale is None else dy_scale.data_ptr() + 4, st)
+                with _on_wgrad_stream(side, (planes, dzp, dy_scale, wsb)):
+                    with _timed("conv_wgrad_tcgen05", flops,
+                                (ctx.tag, _kernel_name(d, 2, pw)) if _profile["records"] is not None else ctx.tag):
+                        L.call("affgw_conv2d_wgrad_scaled", planes.data_ptr(), dzp.data_ptr(), dw.data_ptr(), wsb.data_ptr(),
+                               C.byref(d), None if dy_scale is None else dy_scale.data_ptr() + 4, L.stream())
             else:
                 if x is None:
                     raise RuntimeError("conv2d backward: the CUDA-core wgrad needs the saved fp32 input")

@@ -38,7 +38,8 @@ class Trainer:
     GRAPH_WARMUP = 3      # eager iterations before the capture
 
     def __init__(self, num_writers=500, lr_gen=1e-4, lr_dis=1e-4, lr_cla=1e-5, device=None, skip_unused_wgrad=True,
-                 bucket_bytes=None, encoder=None, cuda_graph=False, overlap_exchange=False, rec=None, lr_rec=1e-5):
+                 bucket_bytes=None, encoder=None, cuda_graph=False, overlap_exchange=False, rec=None, lr_rec=1e-5,
+                 wgrad_stream=True):
         import warnings
         with warnings.catch_warnings():
             if rec is None:
@@ -76,6 +77,8 @@ class Trainer:
         # zero_grad (main_run.py:148-163); skipping them changes nothing observable
         self.skip_unused_wgrad = skip_unused_wgrad
         self.cuda_graph = bool(cuda_graph)
+        # weight-gradient GEMMs on a second stream beside the dgrad / normalisation chain (ops.wgrad_side_stream)
+        self.wgrad_stream = bool(wgrad_stream) and os.environ.get("AFFGW_WGRAD_STREAM", "1") != "0"
         self._graphs = None           # {name: (CUDAGraph, static outputs)}
         self._static_in = None
         self._eager_steps = 0
@@ -89,6 +92,9 @@ class Trainer:
     # ------------------------------------------------------------------------------------------------ sub-steps
     def _fwd_bwd(self, name, batch, epoch):
         """zero_grad + forward + backward of one sub-step; returns its loss tensors."""
+        if self.wgrad_stream:
+            with ops.wgrad_side_stream():       # forked inside every backward pass, joined before the losses are returned
+                return self._fwd_bwd_inner(name, batch, epoch)
         with ops.accumulate_into_grad(True):
             return self._fwd_bwd_inner(name, batch, epoch)
 

@@ -281,7 +281,7 @@ def test_cuda_graph_replay_matches_eager_iterations(specs):
         batch = LD.batch_to_device(bench.synthetic_batch(4, 50, 7), torch.device('cuda'))
         torch.manual_seed(0)
         a = Trainer(num_writers=500, device=dev)
-        b = Trainer(num_writers=500, device=dev)
+        b = Trainer(num_writers=500, device=dev, wgrad_stream=False)       # single-stream weight gradients
         g = Trainer(num_writers=500, device=dev, cuda_graph=True)
         g.GRAPH_WARMUP = 1                     # capture at iteration 1, pure replays from iteration 2 on
         # same, with the generator's / classifier's exchange + Adam on a side stream under the next graph replay
@@ -390,6 +390,75 @@ def test_accumulate_into_grad_matches_autograd_accumulation():
         assert out[True][2]                                       # accumulated in place
         assert float((out[True][0] - out[False][0]).abs().max()) <= 1e-6 * float(out[False][0].abs().max())
         assert float((out[True][1] - out[False][1]).abs().max()) <= 1e-5 * float(out[False][1].abs().max())
+    finally:
+        A.set_precision("fp32")
+
+
+def test_wgrad_side_stream_matches_main_stream():
+    """ops.wgrad_side_stream: weight-gradient GEMMs forked onto a second stream (first use creates .grad, second use accumulates
+    into it inside the kernel) give the gradients of the single-stream path once the context has exited."""
+    from affganwriting_b200 import ops
+    A.set_precision("f16")
+    try:
+        g = torch.Generator(device="cuda").manual_seed(9)
+        x1 = ops.to_internal(torch.randn(4, 64, 16, 54, device="cuda", generator=g))
+        x2 = ops.to_internal(torch.randn(4, 64, 16, 54, device="cuda", generator=g))
+        out = {}
+        for flag in (False, True):
+            gw = torch.Generator(device="cuda").manual_seed(1)
+            w = torch.nn.Parameter(torch.randn(96, 64, 3, 3, device="cuda", generator=gw) * 0.05)
+            w2 = torch.nn.Parameter(torch.randn(64, 96, 3, 3, device="cuda", generator=gw) * 0.05)
+            wl = torch.nn.Parameter(torch.randn(32, 64, device="cuda", generator=gw) * 0.05)
+            b = torch.nn.Parameter(torch.zeros(96, device="cuda"))
+            xin = x1.clone().requires_grad_()
+            with ops.wgrad_side_stream(flag):
+                for rep in range(3):                                # enough work that the side stream runs behind
+                    h = ops.conv2d(xin, w, b, pad=1, pad_mode="reflect")
+                    h = ops.conv2d(ops.instance_norm(h, act="relu"), w2, None, pad=1)
+                    (h.square().mean() * (rep + 1)).backward()
+                (ops.conv2d(x2, w, b, pad=1, pad_mode="reflect").square().mean() * 3).backward()
+                ops.linear(x1.permute(0, 2, 3, 1).reshape(-1, 64), wl, None).square().mean().backward()
+            out[flag] = [t.grad.clone() for t in (w, w2, wl, b, xin)]
+        torch.cuda.synchronize()
+        for a, r in zip(out[True], out[False]):
+            assert float((a - r).abs().max()) <= 2e-5 * float(r.abs().max())
+    finally:
+        A.set_precision("fp32")
+
+
+def test_trainer_wgrad_stream_matches_single_stream(specs):
+    """Trainer(wgrad_stream=True) (default: weight-gradient GEMMs on a second stream) against wgrad_stream=False: the same
+    first iteration (losses, and the weights after the three Adam steps) up to the order of the fp32 atomics."""
+    from affganwriting_b200.trainer import Trainer
+    import bench
+    from affganwriting_b200 import load_data as LD
+    A.set_precision("f16")
+    try:
+        dev = torch.device("cuda", 0)
+        batch = LD.batch_to_device(bench.synthetic_batch(4, 50, 7), torch.device('cuda'))
+        torch.manual_seed(0)
+        a = Trainer(num_writers=500, device=dev, wgrad_stream=False)
+        b = Trainer(num_writers=500, device=dev, wgrad_stream=False)
+        s = Trainer(num_writers=500, device=dev, wgrad_stream=True)
+        assert s.wgrad_stream and not a.wgrad_stream
+        b.model.load_state_dict(a.model.state_dict())
+        s.model.load_state_dict(a.model.state_dict())
+        la, lb, ls = a.train_step(batch), b.train_step(batch), s.train_step(batch)
+        torch.cuda.synchronize()
+        for k in la:
+            assert abs(float(la[k]) - float(ls[k])) <= 1e-3 * max(1.0, abs(float(la[k]))), (k, float(la[k]), float(ls[k]))
+
+        def rel(x, y):
+            sx, sy = x.model.state_dict(), y.model.state_dict()
+            return max(float((v - sy[k]).norm()) / max(float(v.norm()), 1e-20) for k, v in sx.items()
+                       if v.is_floating_point() and v.numel() > 1)
+        noise, diff = rel(a, b), rel(a, s)
+        print(f"\nweights after one iteration: single/single {noise:.2e}, single/side-stream {diff:.2e}")
+        assert diff <= 10 * noise + 1e-4
+        # every parameter that has a gradient in the single-stream trainer has one in the side-stream trainer
+        ga = {n for n, p in a.model.named_parameters() if p.grad is not None}
+        gs = {n for n, p in s.model.named_parameters() if p.grad is not None}
+        assert ga == gs
     finally:
         A.set_precision("fp32")
 
