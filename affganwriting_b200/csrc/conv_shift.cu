@@ -118,7 +118,7 @@ conv_shift_tcgen05_kernel(const __grid_constant__ ShArgs a) {
     auto a_smem = [&](int s) { return smem_base + s * stage_bytes; };
     auto b_smem = [&](int s) { return smem_base + s * stage_bytes + a.a_bytes; };
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
     const int KG = a.K / a.KYG;               // stages per channel block
     const uint32_t plane_pitch = (uint32_t)a.NPa * 16u;
 
@@ -176,52 +176,55 @@ conv_shift_tcgen05_kernel(const __grid_constant__ ShArgs a) {
         }
     } else if (warp == MMA_WARP) {
         // ============================== MMA issuer ==============================
-        {   // every lane runs the loops (warp-uniform), one elected lane issues: see umma_bf16_elect
+        {   // every lane runs the loops (warp-uniform), one elected lane issues: see umma_f16_elect32.  Stage / accumulator
+            // cursors are counters (no modulo) and descriptors are (low word, constant high word) pairs so that the whole
+            // address arithmetic of the issue loop stays on 32-bit warp-uniform values.
             const uint32_t idesc = make_idesc(BN, false, a.fmt);
             const uint32_t idesc2 = make_idesc(PK ? 2 * BN : BN, false, a.fmt);
-            const uint32_t b_tap = (uint32_t)NPL * 2u * BN * 16u;   // bytes of one tap's [cgroup][plane][BN][8] weight image
-            uint32_t it = 0, tl = 0;
-            for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x, ++tl) {
-                const uint32_t acc = tl % NBUF, acc_ph = (tl / NBUF) & 1u;
+            const uint32_t b_tap16 = ((uint32_t)NPL * 2u * BN * 16u) >> 4;   // one tap's [cgroup][plane][BN][8] weight image
+            // K-major: LBO (bits 16-29) = next 8 channels, SBO (bits 32-45) = next 8 rows = 128 B, version bit 46
+            const uint32_t desc_hi = (128u >> 4) | (1u << 14);
+            const uint32_t a_lbo = ((plane_pitch >> 4) & 0x3FFFu) << 16;
+            const uint32_t b_lbo = ((((uint32_t)NPL * BN * 16u) >> 4) & 0x3FFFu) << 16;
+            const uint32_t a_lo_off = (2u * plane_pitch) >> 4, b_lo_off = (BN * 16u) >> 4;   // lo rows follow the hi rows
+            uint32_t s = 0, ph = 0, acc = 0, acc_ph = 0;
+            for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
                 mbar_wait(tmem_empty_bar(acc), acc_ph ^ 1u);
                 tc_fence_after();
                 const uint32_t d0 = tmem_base + acc * (MT * ACC_W);
-                for (int st = 0; st < KG * a.CB; ++st, ++it) {
-                    const int s = it % stages;
-                    const uint32_t ph = (it / stages) & 1u;
+                for (int st = 0; st < KG * a.CB; ++st) {
                     mbar_wait(full_bar(s), ph);
                     tc_fence_after();
-                    // descriptors differ only in their start address: add (byte offset >> 4) to the low word
-                    const uint64_t a_base = make_nosw_desc(a_smem(s), plane_pitch, 128u);           // K-major: LBO = next 8
-                    const uint64_t b_base = make_nosw_desc(b_smem(s), NPL * BN * 16u, 128u);        // channels, SBO = next 8 rows
-                    const uint32_t a_lo_off = (2u * plane_pitch) >> 4, b_lo_off = (BN * 16u) >> 4;   // lo rows follow the hi rows
-                    uint32_t tap = 0;
+                    const uint32_t a_base = a_lbo | ((a_smem(s) & 0x3FFFFu) >> 4);
+                    const uint32_t b_base = b_lbo | ((b_smem(s) & 0x3FFFFu) >> 4);
+                    uint32_t b_t = b_base;
                     for (int r = 0; r < a.KYG; ++r) {
-                        const uint32_t row = (uint32_t)(r * a.Wp);
+                        const uint32_t a_r = a_base + (uint32_t)(r * a.Wp);
 #pragma unroll 1
-                        for (int kx = 0; kx < a.K; ++kx, ++tap) {
-                            const uint64_t b_hi = b_base + (uint64_t)(tap * (b_tap >> 4));
-                            const uint64_t a_t = a_base + (uint64_t)(row + (uint32_t)kx);
-                            const uint32_t accum = (uint32_t)((st | (int)tap) != 0);
+                        for (int kx = 0; kx < a.K; ++kx, b_t += b_tap16) {
+                            const uint32_t accum = (uint32_t)((st | r | kx) != 0);
 #pragma unroll
                             for (int mt = 0; mt < MT; ++mt) {
-                                const uint64_t a_hi = a_t + (uint64_t)(mt * 128);
+                                const uint32_t a_t = a_r + (uint32_t)kx + (uint32_t)(mt * 128);
+                                const uint32_t d = d0 + mt * ACC_W;
                                 if (PK) {       // columns [0, BN): a_hi w_hi + a_lo w_hi, columns [BN, 2 BN): a_hi w_lo
-                                    umma_bf16_elect(d0 + mt * ACC_W, a_hi, b_hi, idesc2, accum);
-                                    umma_bf16_elect(d0 + mt * ACC_W, a_hi + a_lo_off, b_hi, idesc, 1u);
+                                    umma_f16_elect32(d, a_t, desc_hi, b_t, desc_hi, idesc2, accum);
+                                    umma_f16_elect32(d, a_t + a_lo_off, desc_hi, b_t, desc_hi, idesc, 1u);
                                 } else {
-                                    umma_bf16_elect(d0 + mt * ACC_W, a_hi, b_hi, idesc, accum);
+                                    umma_f16_elect32(d, a_t, desc_hi, b_t, desc_hi, idesc, accum);
                                     if (NPASS == 3) {
-                                        umma_bf16_elect(d0 + mt * ACC_W, a_hi + a_lo_off, b_hi, idesc, 1u);
-                                        umma_bf16_elect(d0 + mt * ACC_W, a_hi, b_hi + b_lo_off, idesc, 1u);
+                                        umma_f16_elect32(d, a_t + a_lo_off, desc_hi, b_t, desc_hi, idesc, 1u);
+                                        umma_f16_elect32(d, a_t, desc_hi, b_t + b_lo_off, desc_hi, idesc, 1u);
                                     }
                                 }
                             }
                         }
                     }
                     umma_commit_elect(empty_bar(s));
+                    if (++s == (uint32_t)stages) { s = 0; ph ^= 1u; }
                 }
                 umma_commit_elect(tmem_full_bar(acc));
+                if (++acc == (uint32_t)NBUF) { acc = 0; acc_ph ^= 1u; }
             }
         }
     } else {
@@ -753,7 +756,7 @@ conv_wgrad_shift_kernel(const __grid_constant__ WsArgs a, const __grid_constant_
     auto a_smem = [&](int s) { return smem_base + s * stage_bytes; };
     auto b_smem = [&](int s) { return smem_base + s * stage_bytes + a.a_bytes; };
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
     const int kxg = blockIdx.x % a.n_kxg;
     const int ky = (blockIdx.x / a.n_kxg) % a.K;
     const int cob = (blockIdx.x / (a.n_kxg * a.K)) % a.n_co_blocks;

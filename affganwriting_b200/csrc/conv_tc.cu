@@ -145,7 +145,7 @@ conv_igemm_tcgen05_kernel(const __grid_constant__ TcArgs a) {
     auto b_smem = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES + Cfg::A_BYTES; };
 
     const ConvGeom& g = a.g;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
     const int KB = a.KB;
 
     if (tid == MMA_WARP * 32) {

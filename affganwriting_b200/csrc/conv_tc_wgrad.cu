@@ -104,7 +104,7 @@ conv_wgrad_tcgen05_kernel(const __grid_constant__ WgArgs a) {
     auto b_smem = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES + Cfg::A_BYTES; };
 
     const ConvGeom& g = a.g;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
     const int ktot = g.KH * g.KW * g.Cin;               // flattened (tap, stored channel) extent = rows of dW^T
     const int n0 = blockIdx.y * BN;
     const long long mbeg = (long long)blockIdx.z * a.m_per_split;

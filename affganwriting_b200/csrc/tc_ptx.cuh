@@ -96,6 +96,24 @@ __device__ __forceinline__ void umma_bf16_elect(uint32_t tmem_d, uint64_t adesc,
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// Same, with both shared-memory descriptors given as (low word, high word): the kernels keep the constant high words and do all
+// per-tap address arithmetic on the 32-bit low words (start address field: bits 0-13 in 16-byte units, no carry out of it),
+// which ptxas keeps on the uniform datapath - half the register moves per issued MMA of the 64-bit form.
+__device__ __forceinline__ void umma_f16_elect32(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                                 uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p, e;\n"
+        ".reg .b64 da, db;\n"
+        "elect.sync _|e, 0xffffffff;\n"
+        "setp.ne.b32 p, %6, 0;\n"
+        "mov.b64 da, {%1, %2};\n"
+        "mov.b64 db, {%3, %4};\n"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 __device__ __forceinline__ void umma_commit_elect(uint32_t bar) {
     asm volatile(
         "{\n"

@@ -15,6 +15,8 @@ from . import _lib as L  # noqa: N812
 import os as _os
 _FUSE_DB = _os.environ.get("AFFGW_FUSE_DB", "1") != "0"
 _THIN = _os.environ.get("AFFGW_THIN", "1") != "0"
+_WGRAD_LATE = _os.environ.get("AFFGW_WGRAD_FORK", "late") == "late"
+_WGRAD_PRIO = int(_os.environ.get("AFFGW_WGRAD_PRIO", "0"))
 # "passes": tensor-core MMAs per product of (forward, input-gradient, weight-gradient) GEMMs: 3 = split operands, 1 = single
 _state = {"mode": "fp32", "passes": (3, 3, 3), "force_simt": False, "simt_wgrad": False, "fmt": None, "grad_accum": False,
           "wgrad_side": None}
@@ -209,7 +211,7 @@ class wgrad_side_stream:
             dev = torch.cuda.current_device()
             st = wgrad_side_stream._streams.get(dev)
             if st is None:
-                st = wgrad_side_stream._streams[dev] = torch.cuda.Stream(device=dev)
+                st = wgrad_side_stream._streams[dev] = torch.cuda.Stream(device=dev, priority=_WGRAD_PRIO)
             _state["wgrad_side"] = {"stream": st, "keep": [], "forked": False}
             _state["grad_accum"] = True
         return self
@@ -710,6 +712,7 @@ class _Conv2d(Function):
             da = dz if (ctx.has_addend and need_a) else None
             return dx, dw, db, da, None
         dw_ret = True
+        deferred = None
         if need_w:
             tc_w = use_tc and not _state["simt_wgrad"]
             dw = _grad_slot(weight) if tc_w else None   # the unpack kernel accumulates: dw += partials
@@ -728,11 +731,18 @@ class _Conv2d(Function):
                 if ws_bytes <= 0:
                     raise RuntimeError("conv2d_wgrad: tcgen05 kernel refused the shape: " + L.last_error())
                 wsb = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-                with _on_wgrad_stream(side, (planes, dzp, dy_scale, wsb)):
-                    with _timed("conv_wgrad_tcgen05", flops,
-                                (ctx.tag, _kernel_name(d, 2, pw)) if _profile["records"] is not None else ctx.tag):
-                        L.call("affgw_conv2d_wgrad_scaled", planes.data_ptr(), dzp.data_ptr(), dw.data_ptr(), wsb.data_ptr(),
-                               C.byref(d), None if dy_scale is None else dy_scale.data_ptr() + 4, L.stream())
+                dwg = d
+
+                def launch_wgrad():
+                    with _on_wgrad_stream(side, (planes, dzp, dy_scale, wsb)):
+                        with _timed("conv_wgrad_tcgen05", flops,
+                                    (ctx.tag, _kernel_name(dwg, 2, pw)) if _profile["records"] is not None else ctx.tag):
+                            L.call("affgw_conv2d_wgrad_scaled", planes.data_ptr(), dzp.data_ptr(), dw.data_ptr(), wsb.data_ptr(),
+                                   C.byref(dwg), None if dy_scale is None else dy_scale.data_ptr() + 4, L.stream())
+                if side is not None and need_x and _WGRAD_LATE:
+                    deferred = launch_wgrad     # fork AFTER this layer's dgrad: the side stream starts when the dgrad CTAs drain
+                else:
+                    launch_wgrad()
             else:
                 if x is None:
                     raise RuntimeError("conv2d backward: the CUDA-core wgrad needs the saved fp32 input")
@@ -779,6 +789,8 @@ class _Conv2d(Function):
                     if len(ctx.x_meta[0]) == 4 else torch.zeros(ctx.x_meta[0], dtype=torch.float32, device=dev)
                 full[:, :cin] = dx
                 dx = full
+        if deferred is not None:
+            deferred()
         da = dz if (ctx.has_addend and need_a) else None
         return dx, (dw if dw_ret else None), (db if db_ret else None), da, None
 

@@ -26,6 +26,8 @@ graph's gradient buffers, which the side stream is still reading.  `join()` make
 pending; train_step() leaves the generator's step in flight, so call join() before reading weights, evaluating,
 checkpointing or switching to another path.
 """
+import os
+
 import torch
 
 from . import ops
@@ -175,7 +177,7 @@ class Trainer:
                 # iteration (AccumulateGrad) belong to that stream
                 self._eager_steps += 1
                 if self._side is None:
-                    self._side = torch.cuda.Stream(device=self.model.device_)
+                    self._side = torch.cuda.Stream(device=self.model.device_, priority=int(os.environ.get("AFFGW_MAIN_PRIO", "-1")))
                 self._side.wait_stream(torch.cuda.current_stream())
                 with torch.cuda.stream(self._side):
                     out = self.train_step_eager(batch, epoch)
