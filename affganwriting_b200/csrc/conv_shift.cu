@@ -38,7 +38,11 @@ namespace {
 using namespace tcptx;
 
 constexpr int MMA_WARP = 1;
-constexpr int NUM_THREADS = 32 * 6;          // producer warp, MMA warp, 4 epilogue warps
+#ifndef AFFGW_EPI_WARPS
+#define AFFGW_EPI_WARPS 8
+#endif
+constexpr int EPI_WARPS = AFFGW_EPI_WARPS;   // 4 or 8: one or two per TMEM lane quarter (a warp reads the quarter warp_id % 4)
+constexpr int NUM_THREADS = 32 * (2 + EPI_WARPS);   // producer warp, MMA warp, epilogue warps
 constexpr int MAX_TILE_POS = 512;            // largest CTA tile in positions (frames keep that much tail)
 // CTA tile = MT M-tiles of 128 positions x BN output channels; NBUF TMEM accumulator buffers of MT*BN columns.
 // Wide N amortises the 4 KB A read of a 128-row MMA over more tensor clocks (the shared-memory pipe delivers 128 B/clk):
@@ -50,7 +54,7 @@ __host__ __device__ constexpr bool tile_packed(int bn, int npl) { return npl == 
 __host__ __device__ constexpr int tile_acc_w(int bn, int npl) { return tile_packed(bn, npl) ? 2 * bn : bn; }
 __host__ __device__ constexpr int tile_mt(int bn, int npl) { return bn <= 32 ? 4 : (bn == 64 ? (npl == 2 ? 2 : 4) : 2); }
 __host__ __device__ constexpr int tile_nbuf(int acc_cols) { return 2 * acc_cols <= 512 ? 2 : 1; }   // accumulator buffers in TMEM
-constexpr int MAX_STAGES = 4;
+constexpr int MAX_STAGES = 6;
 constexpr int SMEM_LIMIT = 227 * 1024;
 
 struct ShArgs {
@@ -76,6 +80,7 @@ struct ShArgs {
     int fmt;                   // operand format of the planes / packed weights: 0 = bf16, 1 = fp16
     float alpha;               // result = accumulator * alpha * (alpha_dev ? *alpha_dev : 1): undoes the power-of-two operand
     const float* alpha_dev;    // scales of the fp16 planes (weights x 2^8, dY x a per-tensor scale kept in device memory)
+    FastDiv div_wp, div_hp;    // multiply-shift division by the frame's row pitch / height
 };
 
 // un-swizzled shared-memory matrix descriptors (core matrices of 8 rows x 16 bytes)
@@ -129,7 +134,7 @@ conv_shift_tcgen05_kernel(const __grid_constant__ ShArgs a) {
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(tmem_full_bar(i), 1);
-            mbar_init(tmem_empty_bar(i), 4);
+            mbar_init(tmem_empty_bar(i), EPI_WARPS);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -229,67 +234,91 @@ conv_shift_tcgen05_kernel(const __grid_constant__ ShArgs a) {
         }
     } else {
         // ============================== epilogue ==============================
+        // Eight warps, two per TMEM lane quarter: the (M-tile, 16-column block) units of a CTA tile alternate between the two
+        // warps of a quarter.  On the thin (16/32-channel) layers the epilogue, not the MMAs, is the critical path (ncu: the
+        // issuing warp waits for tmem_empty), so a unit is kept short: multiply-shift position decomposition, both column
+        // blocks of a packed tile loaded before one wait, bias as four vector loads.
         const int wq = warp & 3;          // TMEM lane quarter this warp may read
+        const int half = (warp - 2) >> 2; // which of the quarter's two warps
+        constexpr int NJ = BN / 16;
         const float alpha = a.alpha * (a.alpha_dev ? __ldg(a.alpha_dev) : 1.f);
-        uint32_t tl = 0;
-        for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x, ++tl) {
-            const uint32_t acc = tl % NBUF, acc_ph = (tl / NBUF) & 1u;
+        uint32_t acc = 0, acc_ph = 0;
+        for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
             const int n0 = (t % a.n_tiles) * BN;
             const int q0 = (t / a.n_tiles) * TILE_POS;
             mbar_wait(tmem_full_bar(acc), acc_ph);
             tc_fence_after();
+            int mt_cur = -1;
+            bool valid = false, any = false;
+            long long m = 0;
 #pragma unroll 1
-            for (int mt = 0; mt < MT; ++mt) {
-                const int q = q0 + mt * 128 + wq * 32 + lane;
-                const int xp = q % a.Wp - a.ox0;
-                const int r = q / a.Wp;
-                const int yp = r % a.Hp - a.oy0;
-                const int n = r / a.Hp;
-                const bool valid = n < a.N && (unsigned)yp < (unsigned)a.OH && (unsigned)xp < (unsigned)a.OW;
-                const long long m = ((long long)n * a.OH + yp) * a.OW + xp;
-                if (__ballot_sync(0xffffffffu, valid) == 0u) continue;      // warp-uniform: a run of padding positions
-#pragma unroll 1
-                for (int j = 0; j < BN / 16; ++j) {
-                    const int nb = n0 + j * 16;
-                    if (nb >= a.Cout) break;                                // warp-uniform
-                    uint32_t raw[16];
-                    const uint32_t tcol = tmem_base + ((uint32_t)(wq * 32) << 16) + acc * (MT * ACC_W) + (uint32_t)(mt * ACC_W + j * 16);
-                    tmem_ld16(tcol, raw);
-                    if (PK) {
-                        uint32_t raw2[16];
-                        tmem_ld16(tcol + BN, raw2);
+            for (int u = half; u < MT * NJ; u += EPI_WARPS / 4) {
+                const int mt = u / NJ, j = u - mt * NJ;
+                if (mt != mt_cur) {
+                    mt_cur = mt;
+                    const int q = q0 + mt * 128 + wq * 32 + lane;
+                    const int r = (int)fast_div((uint32_t)q, a.div_wp);
+                    const int xp = q - r * a.Wp - a.ox0;
+                    const int n = (int)fast_div((uint32_t)r, a.div_hp);
+                    const int yp = r - n * a.Hp - a.oy0;
+                    valid = n < a.N && (unsigned)yp < (unsigned)a.OH && (unsigned)xp < (unsigned)a.OW;
+                    m = ((long long)n * a.OH + yp) * a.OW + xp;
+                    any = __ballot_sync(0xffffffffu, valid) != 0u;
+                }
+                if (!any) continue;                                     // warp-uniform: a run of padding positions
+                const int nb = n0 + j * 16;
+                if (nb >= a.Cout) continue;                             // warp-uniform
+                uint32_t raw[16];
+                const uint32_t tcol = tmem_base + ((uint32_t)(wq * 32) << 16) + acc * (MT * ACC_W) + (uint32_t)(mt * ACC_W + j * 16);
+                tmem_ld16_issue(tcol, raw);
+                if (PK) {
+                    uint32_t raw2[16];
+                    tmem_ld16_issue(tcol + BN, raw2);
+                    tmem_ld_wait();
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) raw[i] = __float_as_uint(__uint_as_float(raw[i]) + __uint_as_float(raw2[i]));
-                    }
-                    if (valid) {
-                        float* yrow = a.y + m * a.out_pitch + nb;
-                        if (a.vec_ok) {
-                            float v[16];
+                    for (int i = 0; i < 16; ++i) raw[i] = __float_as_uint(__uint_as_float(raw[i]) + __uint_as_float(raw2[i]));
+                } else {
+                    tmem_ld_wait();
+                }
+                if (valid) {
+                    float* yrow = a.y + m * a.out_pitch + nb;
+                    if (a.vec_ok) {
+                        float v[16];
+                        if (a.bias) {
 #pragma unroll
-                            for (int i = 0; i < 16; ++i) v[i] = fmaf(__uint_as_float(raw[i]), alpha, a.bias ? __ldg(a.bias + nb + i) : 0.f);
-                            if (a.addend) {
-                                const float4* ad = reinterpret_cast<const float4*>(a.addend + m * a.out_pitch + nb);
-#pragma unroll
-                                for (int i = 0; i < 4; ++i) {
-                                    const float4 f = ad[i];
-                                    v[4 * i] += f.x; v[4 * i + 1] += f.y; v[4 * i + 2] += f.z; v[4 * i + 3] += f.w;
-                                }
+                            for (int i = 0; i < 4; ++i) {
+                                const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.bias + nb) + i);
+                                v[4 * i] = fmaf(__uint_as_float(raw[4 * i]), alpha, b4.x);
+                                v[4 * i + 1] = fmaf(__uint_as_float(raw[4 * i + 1]), alpha, b4.y);
+                                v[4 * i + 2] = fmaf(__uint_as_float(raw[4 * i + 2]), alpha, b4.z);
+                                v[4 * i + 3] = fmaf(__uint_as_float(raw[4 * i + 3]), alpha, b4.w);
                             }
-                            if (a.post_act != ACT_NONE) {
-#pragma unroll
-                                for (int i = 0; i < 16; ++i) v[i] = act_apply(v[i], a.post_act);
-                            }
-#pragma unroll
-                            for (int i = 0; i < 4; ++i)
-                                reinterpret_cast<float4*>(yrow)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
                         } else {
 #pragma unroll
-                            for (int i = 0; i < 16; ++i) {
-                                if (nb + i < a.Cout) {
-                                    float rr = fmaf(__uint_as_float(raw[i]), alpha, a.bias ? __ldg(a.bias + nb + i) : 0.f);
-                                    if (a.addend) rr += a.addend[m * a.out_pitch + nb + i];
-                                    yrow[i] = act_apply(rr, a.post_act);
-                                }
+                            for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(raw[i]) * alpha;
+                        }
+                        if (a.addend) {
+                            const float4* ad = reinterpret_cast<const float4*>(a.addend + m * a.out_pitch + nb);
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const float4 f = ad[i];
+                                v[4 * i] += f.x; v[4 * i + 1] += f.y; v[4 * i + 2] += f.z; v[4 * i + 3] += f.w;
+                            }
+                        }
+                        if (a.post_act != ACT_NONE) {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) v[i] = act_apply(v[i], a.post_act);
+                        }
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            reinterpret_cast<float4*>(yrow)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            if (nb + i < a.Cout) {
+                                float rr = fmaf(__uint_as_float(raw[i]), alpha, a.bias ? __ldg(a.bias + nb + i) : 0.f);
+                                if (a.addend) rr += a.addend[m * a.out_pitch + nb + i];
+                                yrow[i] = act_apply(rr, a.post_act);
                             }
                         }
                     }
@@ -298,6 +327,7 @@ conv_shift_tcgen05_kernel(const __grid_constant__ ShArgs a) {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
+            if (++acc == (uint32_t)NBUF) { acc = 0; acc_ph ^= 1u; }
         }
     }
     tc_fence_before();
@@ -679,7 +709,9 @@ int conv_pos_tc(const void* x_planes, const PosFrame& f, const void* w_packed, c
     a.n_tiles = (Cout + p.bn - 1) / p.bn;
     a.total_tiles = (int)((q_last / (mt * 128) + 1) * a.n_tiles);
     a.vec_ok = (Cout % 16 == 0) && (out_pitch % 4 == 0) && (((uintptr_t)y) % 16 == 0) &&
-               (!addend || ((uintptr_t)addend) % 16 == 0);
+               (!addend || ((uintptr_t)addend) % 16 == 0) && (!bias || ((uintptr_t)bias) % 16 == 0);
+    a.div_wp = make_fastdiv(f.Wp);
+    a.div_hp = make_fastdiv(f.Hp);
     a.fmt = fmt;
     a.alpha = fmt ? 1.f / F16_W_SCALE : 1.f;        // the packed fp16 weights carry 2^8
     a.alpha_dev = alpha_dev;
@@ -800,9 +832,9 @@ conv_wgrad_shift_kernel(const __grid_constant__ WsArgs a, const __grid_constant_
             tma_prefetch_desc(&tmdy);
             const uint32_t copies = a.TPM == 1 ? 1u : (uint32_t)nkx;
             const uint32_t tx = (uint32_t)NPL * 16u * (copies * (uint32_t)a.rowsA * (uint32_t)a.pitchA16 + (uint32_t)a.rowsB * (uint32_t)a.pitchB16);
+            int s = 0;
+            uint32_t ph = 0;
             for (int st = 0; st < nst; ++st) {
-                const int s = st % stages;
-                const uint32_t ph = (uint32_t)(st / stages) & 1u;
                 mbar_wait(empty_bar(s), ph ^ 1u);
                 mbar_arrive_expect_tx(full_bar(s), tx);
                 const int q0 = (cbeg + st) * a.KP + a.lead;
@@ -818,6 +850,7 @@ conv_wgrad_shift_kernel(const __grid_constant__ WsArgs a, const __grid_constant_
                     }
                     tma_load_2d(b_smem(s) + (uint32_t)(pl * GB) * pitchB, &tmdy, 2 * q0, pl * a.Gy + cob * GB, full_bar(s));
                 }
+                if (++s == stages) { s = 0; ph ^= 1u; }
             }
         }
     } else if (warp == MMA_WARP) {
@@ -825,9 +858,9 @@ conv_wgrad_shift_kernel(const __grid_constant__ WsArgs a, const __grid_constant_
         {   // every lane runs the loops (warp-uniform), one elected lane issues: see umma_bf16_elect
             const uint32_t idesc = make_idesc(BN, true, a.fmt);
             const uint32_t idesc2 = make_idesc(PK ? 2 * BN : BN, true, a.fmt);
+            int s = 0;
+            uint32_t ph = 0;
             for (int st = 0; st < nst; ++st) {
-                const int s = st % stages;
-                const uint32_t ph = (uint32_t)(st / stages) & 1u;
                 mbar_wait(full_bar(s), ph);
                 tc_fence_after();
                 // MN-major: LBO = to the next 8 positions (k), SBO = to the next 8 channels (m / n); descriptors differ only
@@ -860,6 +893,7 @@ conv_wgrad_shift_kernel(const __grid_constant__ WsArgs a, const __grid_constant_
                     }
                 }
                 umma_commit_elect(empty_bar(s));
+                if (++s == stages) { s = 0; ph ^= 1u; }
             }
             umma_commit_elect(tmem_full_bar);
         }
@@ -999,7 +1033,12 @@ int conv_wgrad_pos_tc(const void* x_planes, const PosFrame& fx, const void* dy_p
     // thin layers are bound by the per-stage hand-shake, not by bytes: 128 positions per stage (the TMA box limit of 256
     // uint64 elements) when three such stages fit
     if (packed && npl * (a.slots + bn / 8) * 128 * 16 * 3 <= SMEM_LIMIT - 1024) a.KP = 128;
-    a.pitchA16 = a.KP == 128 ? 128 : (packed ? a.KP + 4 : a.KP + K - 1);     // dense TMA boxes: pitch = box width
+    // Group pitches in 16-byte units; TMA boxes are dense (pitch = box width) and land 128-byte aligned.  An MN-major MMA reads,
+    // per position, one 16-byte chunk from each of its 16 (A) / BN / 8 (B) group slots, so the pitch decides which banks those
+    // chunks start in: the shared window of the wide layers takes the smallest ODD width that holds it (consecutive slots 16
+    // bytes apart: vgg 256->256 weight gradient 1297 -> 1404 TFLOP/s against the even 66).  Packed (thin) tiles hold several
+    // boxes per stage whose starts must stay 128-byte aligned: multiples of 4.
+    a.pitchA16 = a.KP == 128 ? 128 : (packed ? a.KP + 4 : ((a.KP + K - 1) | 1));
     a.pitchB16 = a.KP == 128 ? 128 : a.KP + (bn >= 64 ? 1 : bn == 32 ? 2 : 4);  // planes start 128-byte aligned (TMA destination)
     a.a_bytes = npl * a.slots * a.pitchA16 * 16;
     a.b_bytes = npl * (bn / 8) * a.pitchB16 * 16;
