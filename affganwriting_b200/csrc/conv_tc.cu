@@ -174,7 +174,9 @@ conv_igemm_tcgen05_kernel(const __grid_constant__ TcArgs a) {
         const int chunk = tid & 7;        // 16-byte chunk (8 k elements) of the 128-byte row
         const int rg = tid >> 3;          // rows rg, rg+16, ..., rg+112
         const bool uniform_tap = (g.Cin % BK) == 0;     // all 64 k of a block belong to one filter tap
-        constexpr int LAG = STAGES - 1;
+        // signal stage i - LAG after issuing stage i; one stage of slack (not STAGES - 1) so that issuing the next stage does not
+        // have to wait for the MMAs of the stage just signalled (see conv_tc_wgrad.cu)
+        constexpr int LAG = STAGES > 2 ? STAGES - 2 : 1;
         uint32_t it = 0;                  // k-block counter across tiles: stage = it % STAGES
         for (long long t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
             const int ks = (int)(t % a.ksplit);

@@ -156,7 +156,10 @@ conv_wgrad_tcgen05_kernel(const __grid_constant__ WgArgs a) {
 #pragma unroll
         for (int i = 0; i < BNI; ++i) ncol[i] = n0 + i * 64 + chunk * 8;
         const int HW = g.H * g.W;
-        constexpr int LAG = STAGES - 1;
+        // signal stage i - LAG after issuing stage i.  LAG = STAGES - 1 would keep every stage either in flight or waiting for its
+        // MMAs, so the next issue had to wait for the MMAs of the stage just signalled (issue and MMA alternated: 3260 clocks
+        // per 768-clock k-block on the 2 x 7 maps); one stage of slack lets them overlap
+        constexpr int LAG = STAGES > 2 ? STAGES - 2 : 1;
         for (int st = 0; st < nstages; ++st) {
             const int s = st % STAGES;
             const uint32_t ph = (uint32_t)(st / STAGES) & 1u;

@@ -346,11 +346,15 @@ def main():
             dist.destroy_process_group()
         return
     # ---- instrumented pass: per-launch CUDA events (on the launching stream) around every convolution kernel
+    # (single stream here: with the weight-gradient GEMMs on their side stream a kernel's events would also cover whatever ran
+    # beside it - each kernel is timed ALONE for its roofline figure; the step numbers above come from the two-stream replay)
+    ws_flag, trainer.wgrad_stream = trainer.wgrad_stream, False
     trainer.train_step_eager(resident)                   # eager: events cannot sit inside a graph replay
     ops.start_kernel_timing()
     timed(lambda: trainer.train_step_eager(resident), 2)
     streams = ops.stop_stream_timing()
     kern = ops.stop_kernel_timing(by_kernel=True)
+    trainer.wgrad_stream = ws_flag
     instr_steps = 2
 
     prefetch.stage(host)
@@ -513,6 +517,7 @@ def main():
                        "configs[1]", "configs[2] (%s style encoder)" % args.encoder),
                    "encoder": args.encoder, "precision_mode": args.precision, "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
                    "cuda_graph": bool(trainer.graph_launches), "overlap_exchange": bool(trainer.overlap_exchange),
+                   "wgrad_side_stream": bool(trainer.wgrad_stream),
                    "l2": "inputs larger than L2: 177 MB of style images are re-read every step (L2 is 126 MB)",
                    "samples_per_sec": value * B},
         "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 12,
