@@ -46,3 +46,45 @@ class GraphedGenerator:
         self._lab.copy_(label, non_blocking=True)
         self._graph.replay()
         return self._out
+
+
+class GraphedForward:
+    """Any no-grad forward `module(*tensors)` of this package replayed as a CUDA graph (the line-level generator,
+    line_generation/generate.py's loop; GenModel_FC with the DINOv2 encoder): same contract as GraphedGenerator - fixed
+    input shapes per captured graph, inputs copied into static tensors, the output lives in a static tensor, weights read
+    at replay time.  Random draws inside the forward (the line generator's noise injections, pure_gen.py:199,205) come from
+    torch's graph-safe generator: every replay draws fresh noise."""
+
+    def __init__(self, module, warmup=2):
+        self.module = module
+        self.warmup = int(warmup)
+        self._graph = None
+        self._key = None
+        self._calls = 0
+        self._side = None
+
+    @torch.no_grad()
+    def __call__(self, *tensors):
+        key = tuple((tuple(t.shape), t.dtype) for t in tensors) + (self.module.training,)
+        if self._graph is None or key != self._key:
+            if self._key != key:
+                self._graph, self._calls, self._key = None, 0, key
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=tensors[0].device)
+            if self._calls < self.warmup:
+                self._calls += 1
+                self._side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(self._side):
+                    out = self.module(*tensors)
+                torch.cuda.current_stream().wait_stream(self._side)
+                return out
+            self._in = tuple(t.clone() for t in tensors)
+            torch.cuda.synchronize()
+            ops.clear_weight_cache(self.module)
+            self._graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._graph, stream=self._side):
+                self._out = self.module(*self._in)
+        for dst, src in zip(self._in, tensors):
+            dst.copy_(src, non_blocking=True)
+        self._graph.replay()
+        return self._out

@@ -405,11 +405,15 @@ def main():
         idx = torch.randint(0, 80, (256, 32), device=dev, generator=gl)
         content = torch.zeros(256, 32, 80, device=dev).scatter_(2, idx.unsqueeze(2), 1.0)
         style = torch.randn(32, 128, device=dev, generator=gl)
-        for _ in range(3):
-            lg(content, style)
-        ms_line = timed(lambda: lg(content, style), 10) / 10
+        from affganwriting_b200.inference import GraphedForward
+        lg_fn = lg if args.no_graph else GraphedForward(lg)
+        with torch.no_grad():
+            for _ in range(4):
+                lg_fn(content, style)
+            ms_line = timed(lambda: lg_fn(content, style), 10) / 10
         line_gen = {"images_per_sec": world * 32 / (ms_line / 1e3), "ms_per_batch": ms_line, "batch_per_gpu": 32,
-                    "image": "64x1024", "note": "SpacedGenerator forward (line_generation/model/pure_gen.py:42-50), eager launches, noise drawn on the device"}
+                    "image": "64x1024", "note": "SpacedGenerator forward (line_generation/model/pure_gen.py:42-50), " +
+                    ("eager launches" if args.no_graph else "CUDA-graph replay (inference.GraphedForward)") + ", noise drawn on the device"}
         del lg
     except Exception as e:
         line_gen = {"error": repr(e)[:300]}
@@ -421,12 +425,14 @@ def main():
         torch.manual_seed(1)
         dg = M.GenModel_FC(12, encoder="dino").to(dev).eval()
         big = LD.batch_to_device(synthetic_batch(256, NUM_CHANNEL, seed=99 + rank), dev)
+        dg_fn = dg if args.no_graph else GraphedGenerator(dg)
         with torch.no_grad():
-            for _ in range(2):
-                dg(big[3], big[7])
-            ms_dino = timed(lambda: dg(big[3], big[7]), 3) / 3
+            for _ in range(4):
+                dg_fn(big[3], big[7])
+            ms_dino = timed(lambda: dg_fn(big[3], big[7]), 3) / 3
         dino_gen = {"images_per_sec": world * 256 / (ms_dino / 1e3), "ms_per_batch": ms_dino, "batch_per_gpu": 256,
-                    "note": "GenModel_FC(encoder=ImageEncoderDINOv2 vitl14, taps [4, 8, 16, 23]) forward under eval(), random weights, eager launches"}
+                    "note": "GenModel_FC(encoder=ImageEncoderDINOv2 vitl14, taps [4, 8, 16, 23]) forward under eval(), random weights, " +
+                    ("eager launches" if args.no_graph else "CUDA-graph replay")}
         del dg, big
     except Exception as e:
         dino_gen = {"error": repr(e)[:300]}

@@ -65,7 +65,7 @@ def main():
         ktot = sum(r[0] for r in krows)
         print(f"CUPTI: {ktot:.1f} ms of kernels / memcpys in one step")
         out["kernels"] = []
-        for ms, k, n in krows[:40]:
+        for ms, k, n in krows[:75]:
             print(f"  {ms:8.3f} ms  x{n:4d}  {k[:110]}")
             out["kernels"].append({"name": k, "launches": n, "ms": ms})
     if args.out:

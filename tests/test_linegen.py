@@ -101,3 +101,60 @@ def test_linegen_full_size_line():
         assert float((a - b).abs().max()) <= 1e-3 * float(a.abs().max())
     finally:
         A.set_precision("fp32")
+
+
+@pytest.mark.gpu
+def test_linegen_graph_replay_matches_eager():
+    """inference.GraphedForward around the line generator: with the noise tensors passed in (no random draw inside) a replay
+    returns the eager image; with device-drawn noise two replays differ (fresh noise per replay) and stay in range."""
+    import affganwriting_b200 as A
+    from affganwriting_b200.linegen import SpacedGenerator
+    from affganwriting_b200.inference import GraphedForward
+    _, sd = _state()
+    A.set_precision("f16")
+    try:
+        g = SpacedGenerator(80, 128, 256, append_style=True)
+        g.load_state_dict(sd)
+        g = g.cuda().eval()
+        content, style, _ = LG.synthetic_inputs(4, 64)
+        content, style = content.cuda(), style.cuda()
+        fast = GraphedForward(g)
+        with torch.no_grad():
+            outs = [fast(content, style).clone() for _ in range(5)]
+        assert fast._graph is not None
+        a, b = outs[-2], outs[-1]
+        assert a.shape[0] == 4 and torch.isfinite(b).all() and float(b.abs().max()) <= 1.0
+        assert float((a - b).abs().max()) > 1e-4                     # every replay draws its own noise
+
+        class Fixed(torch.nn.Module):                                # same generator, noise as an input
+            def __init__(self, gen, noise):
+                super().__init__()
+                self.gen, self.noise = gen, noise
+
+            def forward(self, c, s):
+                return self.gen(c, s, noise=self.noise)
+        with torch.no_grad():
+            probe = []
+            for blk in g.gen if hasattr(g, "gen") else []:
+                probe.append(blk)
+            ref0 = g(content, style, return_intermediate=False)
+        # noise shapes: run once eagerly and record the shapes the injections see
+        shapes = []
+        hooks = [m.register_forward_pre_hook(lambda mod, inp: shapes.append(tuple(inp[1].shape)))
+                 for m in g.modules() if type(m).__name__ == "NoiseInjection"]
+        with torch.no_grad():
+            g(content, style)
+        for h in hooks:
+            h.remove()
+        gen_ = torch.Generator(device="cuda").manual_seed(11)
+        noise = [torch.randn(s, device="cuda", generator=gen_) for s in shapes]
+        fixed = Fixed(g, noise).eval()
+        fast2 = GraphedForward(fixed)
+        with torch.no_grad():
+            ref = fixed(content, style).clone()
+            for _ in range(4):
+                out = fast2(content, style)
+        assert fast2._graph is not None
+        assert float((out - ref).abs().max()) <= 2e-3 * max(1.0, float(ref.abs().max()))
+    finally:
+        A.set_precision("fp32")
