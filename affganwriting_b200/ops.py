@@ -416,19 +416,27 @@ ConvCfg = collections.namedtuple("ConvCfg", "stride pad pad_mode upsample pre_ac
 
 
 class _WeightCache:
-    """Packed operand copies of a parameter, rebuilt when the parameter's version counter moves."""
+    """Packed operand copies of a parameter, rebuilt when the parameter's version counter moves.  An entry is a mutable list
+    [version key, parameter address, packed tensor, builder, parameter]; `builder(out)` re-packs in place when given the old
+    tensor, so a CUDA graph that read the packed copy keeps seeing the current weights (refresh_packed)."""
+
+    @staticmethod
+    def version(weight):
+        # autograd's version counter catches ordinary in-place updates; fused / multi-tensor optimiser kernels do not always
+        # bump it (torch.optim.Adam(fused=True) does not), so an explicit per-parameter epoch (weights_updated) is part of
+        # the key as well
+        return (weight._version, weight.__dict__.get("_affgw_epoch", 0))
 
     @staticmethod
     def get(weight, kind, builder):
         cache = weight.__dict__.setdefault("_affgw_packed", {})
         ent = cache.get(kind)
-        # autograd's version counter catches ordinary in-place updates; fused / multi-tensor optimiser kernels do not always
-        # bump it (torch.optim.Adam(fused=True) does not), so an explicit per-parameter epoch (weights_updated) is part of
-        # the key as well
-        ver = (weight._version, weight.__dict__.get("_affgw_epoch", 0))
-        if ent is None or ent[0] != ver or ent[1] != weight.data_ptr():
-            ent = (ver, weight.data_ptr(), builder())
-            cache[kind] = ent
+        ver = _WeightCache.version(weight)
+        if ent is None or ent[1] != weight.data_ptr():
+            ent = cache[kind] = [ver, weight.data_ptr(), builder(None), builder, weight]
+        elif ent[0] != ver:
+            ent[2] = builder(ent[2])            # same buffer, new contents
+            ent[0] = ver
         return ent[2]
 
 
@@ -441,10 +449,32 @@ def weights_updated(module_or_params):
 
 
 def clear_weight_cache(module):
-    """Drop every packed operand copy of `module`'s parameters.  Trainer calls this before capturing CUDA graphs so that
-    each graph re-packs the weights it reads instead of pointing at a copy an earlier eager iteration made."""
+    """Drop every packed operand copy of `module`'s parameters.  The graphed generators call this before capturing so that
+    their graph re-packs the weights it reads on every replay instead of pointing at a copy an earlier eager call made."""
     for p in module.parameters():
         p.__dict__.pop("_affgw_packed", None)
+
+
+def packed_entries(module_or_params):
+    """Every packed operand copy currently cached for these parameters (a list of cache entries to hand to refresh_packed).
+    trainer.Trainer collects them when it captures its CUDA graphs: the graphs read these buffers and contain no packing
+    kernels; the packing runs once per optimiser step, next to the step (off the critical path when the step is overlapped)."""
+    params = module_or_params.parameters() if hasattr(module_or_params, "parameters") else module_or_params
+    return [ent for p in params for ent in p.__dict__.get("_affgw_packed", {}).values()]
+
+
+def refresh_packed(entries):
+    """Re-pack, in place and on the current stream, every entry whose parameter has changed since it was packed; returns the
+    number of packing kernels launched."""
+    n = 0
+    for ent in entries:
+        w = ent[4]
+        ver = _WeightCache.version(w)
+        if ent[0] != ver and ent[1] == w.data_ptr():
+            ent[2] = ent[3](ent[2])
+            ent[0] = ver
+            n += 1
+    return n
 
 
 def _w4(weight):
@@ -455,9 +485,10 @@ def _pack(weight, dtype, ipad, flip):
     w4 = _w4(weight.detach())
     co, ci, kh, kw = w4.shape
 
-    def build():
+    def build(out):
         rows = ci if flip else co
-        out = torch.empty((rows, kh, kw, ipad), dtype=dtype, device=weight.device)
+        if out is None:
+            out = torch.empty((rows, kh, kw, ipad), dtype=dtype, device=weight.device)
         L.call("affgw_pack_weight", w4.contiguous().data_ptr(), out.data_ptr(), L.dt(out), co, ci, kh, kw, ipad,
                int(flip), L.stream())
         return out
@@ -468,11 +499,12 @@ def _pack_tc(weight, ipad, flip, passes, layout, fmt=0):
     w4 = _w4(weight.detach())
     co, ci, kh, kw = w4.shape
 
-    def build():
-        nbytes = L.lib().affgw_pack_weight_tc_bytes(co, ci, kh, kw, ipad, int(flip), passes, layout)
-        if nbytes <= 0:
-            raise RuntimeError("affgw_pack_weight_tc_bytes: bad configuration")
-        out = torch.empty(nbytes // 2, dtype=torch.bfloat16, device=weight.device)      # 16-bit storage (bf16 or fp16 bits)
+    def build(out):
+        if out is None:
+            nbytes = L.lib().affgw_pack_weight_tc_bytes(co, ci, kh, kw, ipad, int(flip), passes, layout)
+            if nbytes <= 0:
+                raise RuntimeError("affgw_pack_weight_tc_bytes: bad configuration")
+            out = torch.empty(nbytes // 2, dtype=torch.bfloat16, device=weight.device)  # 16-bit storage (bf16 or fp16 bits)
         L.call("affgw_pack_weight_tc_fmt", w4.contiguous().data_ptr(), out.data_ptr(), co, ci, kh, kw, ipad, int(flip), passes,
                layout, fmt, L.stream())
         return out

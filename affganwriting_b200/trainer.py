@@ -82,6 +82,7 @@ class Trainer:
         # weight-gradient GEMMs on a second stream beside the dgrad / normalisation chain (ops.wgrad_side_stream)
         self.wgrad_stream = bool(wgrad_stream) and os.environ.get("AFFGW_WGRAD_STREAM", "1") != "0"
         self._graphs = None           # {name: (CUDAGraph, static outputs)}
+        self._packed = {}             # sub-network -> packed operand copies its graphs read (ops.packed_entries), set at capture
         self._static_in = None
         self._eager_steps = 0
         self._side = None
@@ -128,6 +129,16 @@ class Trainer:
         self.opt[name].step()           # optim.Adam invalidates the packed-weight cache itself (ops.weights_updated)
         if not isinstance(self.opt[name], Adam):
             ops.weights_updated(p for grp in self.opt[name].param_groups for p in grp["params"])   # torch fused Adam
+        # re-pack the tensor-core operand copies of the stepped weights here, next to the step (in place: the CUDA graphs read
+        # these buffers and contain no packing kernels).  With overlap_exchange this runs on the side stream under the next
+        # graph replay instead of in front of the first convolution that needs each weight.
+        self._refresh_packed(name)
+
+    def _refresh_packed(self, name):
+        ents = self._packed.get(name)
+        if ents is None:
+            ents = ops.packed_entries(p for grp in self.opt[name].param_groups for p in grp["params"])
+        return ops.refresh_packed(ents)
 
     @staticmethod
     def _pack(outs):
@@ -192,6 +203,12 @@ class Trainer:
         for dst, src in zip(self._static_in, batch):
             if torch.is_tensor(dst) and dst.data_ptr() != src.data_ptr():
                 dst.copy_(src, non_blocking=True)
+        # weights changed behind the trainer's back (load_state_dict between iterations): the graphs do not re-pack.  Normally
+        # nothing is stale here (every step re-packs its own sub-network) and this is a host-side version check.
+        for name in self.names:
+            if any(e[0] != ops._WeightCache.version(e[4]) for e in self._packed.get(name, ())):
+                self.join(name)
+                self._refresh_packed(name)
         outs = {}
         for name in self.names:
             # dis_update reads the generator stepped by the previous iteration, gen_update also the classifier stepped by this
@@ -246,7 +263,10 @@ class Trainer:
         dev = self.model.device_
         self._static_in = tuple(t.to(dev).clone() if torch.is_tensor(t) else t for t in batch)
         torch.cuda.synchronize()
-        ops.clear_weight_cache(self.model)          # every packed weight a graph reads must be packed inside a graph
+        # the graphs read the packed operand copies of the weights in place; every copy is (re)built outside the graphs, by the
+        # optimiser step of its sub-network (_finish) - make all of them current before the first capture
+        for name in self.names:
+            self._refresh_packed(name)
         # the three graphs always replay in capture order: one shared pool - unless the exchange overlaps the next replay
         pool = None if self.overlap_exchange else torch.cuda.graph_pool_handle()
         graphs, outs = {}, {}
@@ -271,5 +291,7 @@ class Trainer:
             self.graph_launches += n_captured
             n0 = _lib.launch_count()
         torch.cuda.synchronize()
+        self._packed = {name: ops.packed_entries(p for grp in self.opt[name].param_groups for p in grp["params"])
+                        for name in self.names}
         self._graphs = graphs                       # (iter_num was advanced by the captured gen_update's Python side)
         return self._pack(outs)

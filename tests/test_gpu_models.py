@@ -563,3 +563,34 @@ def test_contran_model_modes_match_oracle(specs):
     cos = dots / (na ** 0.5 * nb ** 0.5)
     print(f"\nConTranModel gen_update vs oracle: l_total {float(got_t):.6f} / {float(lt):.6f}, gradient cosine {cos:.6f}")
     assert cos >= 0.999
+
+
+def test_graph_replay_sees_weights_loaded_between_iterations(specs):
+    """The captured sub-steps read the packed operand copies of the weights in place and do not re-pack them (the optimiser
+    step does): weights written behind the trainer's back - load_state_dict between two iterations - must still reach the
+    next replay."""
+    from affganwriting_b200.trainer import Trainer
+    import bench
+    from affganwriting_b200 import load_data as LD
+    A.set_precision("f16")
+    try:
+        dev = torch.device("cuda", 0)
+        batch = LD.batch_to_device(bench.synthetic_batch(4, 50, 7), torch.device('cuda'))
+        torch.manual_seed(0)
+        t = Trainer(num_writers=500, device=dev, cuda_graph=True, overlap_exchange=True)
+        t.GRAPH_WARMUP = 1
+        e = Trainer(num_writers=500, device=dev)
+        for _ in range(3):
+            t.train_step(batch)                                       # eager, capture, replay
+        assert t._graphs is not None and all(t._packed[n] for n in t.names)
+        n_graph = t.graph_launches
+        sd = {k: v.clone() for k, v in e.model.state_dict().items()}   # other weights
+        t.join()
+        t.model.load_state_dict(sd)
+        lt = t.train_step(batch)                                      # a replay on the loaded weights
+        le = e.train_step(batch)                                      # the eager trainer that owns them
+        for k in le:
+            assert abs(float(lt[k]) - float(le[k])) <= 2e-3 * max(1.0, abs(float(le[k]))), (k, float(lt[k]), float(le[k]))
+        assert n_graph == t.graph_launches
+    finally:
+        A.set_precision("fp32")
