@@ -19,7 +19,7 @@ _WGRAD_LATE = _os.environ.get("AFFGW_WGRAD_FORK", "late") == "late"
 _WGRAD_PRIO = int(_os.environ.get("AFFGW_WGRAD_PRIO", "0"))
 # "passes": tensor-core MMAs per product of (forward, input-gradient, weight-gradient) GEMMs: 3 = split operands, 1 = single
 _state = {"mode": "fp32", "passes": (3, 3, 3), "force_simt": False, "simt_wgrad": False, "fmt": None, "grad_accum": False,
-          "wgrad_side": None}
+          "wgrad_side": None, "scratch_tag": None}
 _MODES = {"fp32": (3, 3, 3), "f16": (3, 1, 1), "bf16": (3, 1, 1), "bf16x3": (3, 3, 3), "bf16x1": (1, 1, 1)}
 _err_flag = {}
 _profile = {"records": None}
@@ -228,6 +228,22 @@ class wgrad_side_stream:
         if self.flag:
             self.join()
         _state["wgrad_side"], _state["grad_accum"] = self.prev
+
+
+class scratch_scope:
+    """Context manager: the small self-resetting device scratch words of the launches issued inside (the running maximum of
+    ops._amax_scale) are private to `tag`.  Two CUDA graphs captured on the same stream but replayed CONCURRENTLY (Trainer's
+    cla_update beside dis_update) must not share them."""
+
+    def __init__(self, tag):
+        self.tag = tag
+
+    def __enter__(self):
+        self.prev = _state["scratch_tag"]
+        _state["scratch_tag"] = self.tag
+
+    def __exit__(self, *a):
+        _state["scratch_tag"] = self.prev
 
 
 class _on_wgrad_stream:
@@ -552,7 +568,7 @@ def _split_positions(src, frame, hs, ws, c, pitch, up, origin, pad_mode, pre_act
 def _amax_scale(t):
     """Device-side per-tensor power-of-two scale of an fp16 operand: -> float32 [2] = (2^k, 2^-k), no host synchronisation."""
     out = torch.empty(2, dtype=torch.float32, device=t.device)
-    key = (t.device.index, torch.cuda.current_stream().cuda_stream)
+    key = (t.device.index, torch.cuda.current_stream().cuda_stream, _state["scratch_tag"])
     ws = _amax_ws.get(key)
     if ws is None:                      # 8 bytes of scratch per (device, stream): zero on entry, left zero by the kernel
         ws = _amax_ws[key] = torch.zeros(2, dtype=torch.int32, device=t.device)

@@ -41,7 +41,7 @@ class Trainer:
 
     def __init__(self, num_writers=500, lr_gen=1e-4, lr_dis=1e-4, lr_cla=1e-5, device=None, skip_unused_wgrad=True,
                  bucket_bytes=None, encoder=None, cuda_graph=False, overlap_exchange=False, rec=None, lr_rec=1e-5,
-                 wgrad_stream=True):
+                 wgrad_stream=True, concurrent_cla_dis=True):
         import warnings
         with warnings.catch_warnings():
             if rec is None:
@@ -89,12 +89,21 @@ class Trainer:
         self.graph_launches = 0       # libaffgw launches recorded in the three graphs (= launches per replayed iteration)
         self.overlap_exchange = bool(overlap_exchange) and self.cuda_graph
         self._comm = None             # side stream of the overlapped exchange
+        # cla_update touches only the classifier and dis_update never reads it: with private graph pools (overlap_exchange)
+        # the two captured sub-steps replay side by side on two streams and fill each other's idle SMs / launch gaps
+        self.concurrent_cla_dis = bool(concurrent_cla_dis) and self.overlap_exchange and \
+            os.environ.get("AFFGW_CONCURRENT_CLA_DIS", "1") != "0"
+        self._aux = None              # stream of the concurrent cla_update replay
         self._pending = {}            # sub-network -> event of its exchange + Adam queued on the side stream
         broadcast_module(m)
 
     # ------------------------------------------------------------------------------------------------ sub-steps
     def _fwd_bwd(self, name, batch, epoch):
         """zero_grad + forward + backward of one sub-step; returns its loss tensors."""
+        with ops.scratch_scope(name):
+            return self._fwd_bwd_streams(name, batch, epoch)
+
+    def _fwd_bwd_streams(self, name, batch, epoch):
         if self.wgrad_stream:
             with ops.wgrad_side_stream():       # forked inside every backward pass, joined before the losses are returned
                 return self._fwd_bwd_inner(name, batch, epoch)
@@ -210,7 +219,22 @@ class Trainer:
                 self.join(name)
                 self._refresh_packed(name)
         outs = {}
+        side_by_side = self.concurrent_cla_dis and "cla" in self._graphs and "dis" in self._graphs
         for name in self.names:
+            if name == "cla" and side_by_side:
+                # cla_update on its own stream, dis_update follows on the main stream without waiting for it; gen_update's
+                # join() below waits for the classifier's step like it always does
+                if self._aux is None:
+                    self._aux = torch.cuda.Stream(device=self.model.device_)
+                self._aux.wait_stream(torch.cuda.current_stream())          # the batch copy above
+                with torch.cuda.stream(self._aux):
+                    graph, static_out, grads = self._graphs[name]
+                    graph.replay()
+                    for p, g in grads:
+                        p.grad = g
+                    outs[name] = static_out
+                    self._finish_on_side_stream(name)                        # exchange + Adam behind the replay, on _comm
+                continue
             # dis_update reads the generator stepped by the previous iteration, gen_update also the classifier stepped by this
             # one; cla_update reads neither, so the generator's exchange + Adam overlap it (and the classifier's dis_update)
             if name == "dis":
