@@ -518,6 +518,9 @@ def main():
                          "statistics, gradients and parameters are stored in fp32.  fp16 planes carry 11 significant bits against "
                          "bf16's 8 at the same tensor throughput; their range is handled by exact power-of-two scales "
                          "(DESIGN.md section 3)" % ("fp16" if args.precision == "f16" else "bf16")),
+        "value_note": "whole-job aggregate under weak scaling: every rank completes one batch-%d training step per step time, value = "
+                      "n_gpus / step time (rank-steps/s; one optimiser step of global batch n_gpus x %d per step time); "
+                      "config.samples_per_sec = value x batch_per_gpu" % (B, B),
         "data": "synthetic (seeded uint8 grey-level canvases normalised on the GPU like load_data.py:152-166; random-init weights)",
         "config": {"workload": WORKLOAD if args.encoder == "vgg" else WORKLOAD.replace(
                        "configs[1]", "configs[2] (%s style encoder)" % args.encoder),

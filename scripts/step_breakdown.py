@@ -24,7 +24,7 @@ def main():
     torch.cuda.set_device(dev)
     A.set_precision(args.mode)
     torch.manual_seed(0)
-    tr = Trainer(num_writers=500, device=dev)
+    tr = Trainer(num_writers=500, device=dev, wgrad_stream=False)     # one stream: every kernel is timed alone (the step number is the eager single-stream step)
     batch = LD.batch_to_device(bench.synthetic_batch(args.batch, 50, 1234), dev)
     for _ in range(3):
         tr.train_step(batch)

@@ -12,7 +12,7 @@ import bench
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 A.set_precision("f16")
 dev = torch.device("cuda", 0)
-t = Trainer(num_writers=500, device=dev)
+t = Trainer(num_writers=500, device=dev, wgrad_stream=False)     # one stream: every kernel is timed alone
 batch = LD.batch_to_device(bench.synthetic_batch(B, 50, 1234), dev)
 for _ in range(2):
     t.train_step_eager(batch)
