@@ -77,7 +77,13 @@ class ConTranModel(nn.Module):
         target = label[:, 1:]                                     # remove <GO>  (network_tro.py:44,90-91)
         return crit(log_softmax(pred.reshape(-1, vocab_size)), target.reshape(-1)), target
 
-    def forward(self, train_data_list, epoch, mode, cer_func=None):
+    def forward(self, train_data_list, epoch, mode, cer_func=None, shared=None):
+        """`shared` (optional, not in the reference): a dict the caller passes to BOTH `dis_update` and the `gen_update` that
+        follows it.  The reference generates the fake pair twice per iteration - under no_grad in dis_update
+        (network_tro.py:117-118) and again, from the same generator weights and the same batch, in gen_update (:59-63).  With
+        `shared`, dis_update runs that forward once WITH its autograd graph (BatchNorm running statistics advanced twice), trains
+        the discriminator on the detached images, and gen_update back-propagates through the kept graph: same losses, same
+        gradients, one generator forward less."""
         tr_domain, tr_wid, tr_idx, tr_img, tr_img_width, tr_label, img_xt, label_xt, label_xt_swap = train_data_list
         tr_wid, tr_img = self._to(tr_wid), self._to(tr_img)
         img_xt, label_xt, label_xt_swap = self._to(img_xt), self._to(label_xt), self._to(label_xt_swap)
@@ -104,7 +110,10 @@ class ConTranModel(nn.Module):
 
         if mode == "gen_update":                                  # network_tro.py:57-103 without the l_rec term
             self.iter_num += 1
-            xg, xg_swap = self._generate_pair(tr_img, label_xt, label_xt_swap)
+            if shared is not None and "pair" in shared:
+                xg, xg_swap = shared.pop("pair")                  # generated by the dis_update of this iteration
+            else:
+                xg, xg_swap = self._generate_pair(tr_img, label_xt, label_xt_swap)
             both, wid2 = self._pair(xg, xg_swap), self._pair(tr_wid, tr_wid)
             l_dis = self.dis.calc_gen_loss(both)
             l_cla = self.cla(both, wid2)
@@ -131,8 +140,15 @@ class ConTranModel(nn.Module):
             s2 = tr_img[:, 1:2, :, :]
             l_real = self.dis.calc_dis_real_loss(self._pair(s1, s2))
             l_real.backward(retain_graph=True)
-            with torch.no_grad():
-                xg, xg_swap = self._generate_pair(tr_img, label_xt, label_xt_swap)
+            if shared is not None:
+                from . import ops
+                with ops.bn_updates_twice():
+                    xg, xg_swap = self._generate_pair(tr_img, label_xt, label_xt_swap)
+                shared["pair"] = (xg, xg_swap)
+                xg, xg_swap = xg.detach(), xg_swap.detach()
+            else:
+                with torch.no_grad():
+                    xg, xg_swap = self._generate_pair(tr_img, label_xt, label_xt_swap)
             l_fake = self.dis.calc_dis_fake_loss(self._pair(xg, xg_swap))
             l_fake.backward()
             return l_real + l_fake

@@ -19,7 +19,7 @@ _WGRAD_LATE = _os.environ.get("AFFGW_WGRAD_FORK", "late") == "late"
 _WGRAD_PRIO = int(_os.environ.get("AFFGW_WGRAD_PRIO", "0"))
 # "passes": tensor-core MMAs per product of (forward, input-gradient, weight-gradient) GEMMs: 3 = split operands, 1 = single
 _state = {"mode": "fp32", "passes": (3, 3, 3), "force_simt": False, "simt_wgrad": False, "fmt": None, "grad_accum": False,
-          "wgrad_side": None, "scratch_tag": None}
+          "wgrad_side": None, "scratch_tag": None, "bn_record": None}
 _MODES = {"fp32": (3, 3, 3), "f16": (3, 1, 1), "bf16": (3, 1, 1), "bf16x3": (3, 3, 3), "bf16x1": (1, 1, 1)}
 _err_flag = {}
 _profile = {"records": None}
@@ -228,6 +228,26 @@ class wgrad_side_stream:
         if self.flag:
             self.join()
         _state["wgrad_side"], _state["grad_accum"] = self.prev
+
+
+class bn_updates_twice:
+    """Context manager: the running-statistics updates of the train-mode BatchNorm forwards issued inside are applied a second
+    time, in the same order, when the context exits - what a second, identical run of the same forward would leave behind (the
+    exponential average is order-dependent when one layer is called with several inputs: text encoder and iAFF see the
+    label and the swapped label, modules_tro.py:230-259).  Used when one generator forward stands for the two the reference
+    runs per iteration (Trainer(share_generator_forward=True))."""
+
+    def __enter__(self):
+        self.prev = _state["bn_record"]
+        _state["bn_record"] = []
+        return self
+
+    def __exit__(self, exc_type, *a):
+        rec, _state["bn_record"] = _state["bn_record"], self.prev
+        if exc_type is None:
+            for rm, rv, nbt, mean, var, cc, mom in rec:
+                L.call("affgw_bn_update_running", rm.data_ptr(), rv.data_ptr(), L.ptr(nbt), mean.data_ptr(), var.data_ptr(), cc,
+                       mom, L.stream())
 
 
 class scratch_scope:
@@ -933,6 +953,8 @@ class _BatchNorm(Function):
             if running_mean is not None:
                 L.call("affgw_bn_update_running", running_mean.data_ptr(), running_var.data_ptr(), L.ptr(nbt),
                        mean.data_ptr(), var.data_ptr(), Cc, float(momentum), L.stream())
+                if _state["bn_record"] is not None:         # ops.bn_updates_twice: replayed in order when the context exits
+                    _state["bn_record"].append((running_mean, running_var, nbt, mean, var, Cc, float(momentum)))
         else:
             mean = torch.empty(Cc, dtype=torch.float32, device=x.device)
             rstd = torch.empty(Cc, dtype=torch.float32, device=x.device)

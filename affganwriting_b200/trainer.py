@@ -41,7 +41,7 @@ class Trainer:
 
     def __init__(self, num_writers=500, lr_gen=1e-4, lr_dis=1e-4, lr_cla=1e-5, device=None, skip_unused_wgrad=True,
                  bucket_bytes=None, encoder=None, cuda_graph=False, overlap_exchange=False, rec=None, lr_rec=1e-5,
-                 wgrad_stream=True, concurrent_cla_dis=True):
+                 wgrad_stream=True, concurrent_cla_dis=True, share_generator_forward=False):
         import warnings
         with warnings.catch_warnings():
             if rec is None:
@@ -94,6 +94,11 @@ class Trainer:
         self.concurrent_cla_dis = bool(concurrent_cla_dis) and self.overlap_exchange and \
             os.environ.get("AFFGW_CONCURRENT_CLA_DIS", "1") != "0"
         self._aux = None              # stream of the concurrent cla_update replay
+        # OFF by default (bench.py times the reference's iteration as the reference composes it): one generator forward per
+        # iteration instead of the reference's two identical ones (network_tro.ConTranModel.forward, `shared`).  Not with a
+        # recogniser in graph mode: its gen_update is issued eagerly and cannot walk an autograd graph recorded at capture.
+        self.share_generator_forward = bool(share_generator_forward) and not (rec is not None and self.cuda_graph)
+        self._shared = {} if self.share_generator_forward else None
         self._pending = {}            # sub-network -> event of its exchange + Adam queued on the side stream
         broadcast_module(m)
 
@@ -118,7 +123,7 @@ class Trainer:
         if name == "cla":
             return (m(batch, epoch, "cla_update"),)
         if name == "dis":
-            return (m(batch, epoch, "dis_update"),)
+            return (m(batch, epoch, "dis_update", shared=self._shared),)
         frozen = []
         if self.skip_unused_wgrad:
             others = list(m.dis.parameters()) + list(m.cla.parameters()) + (list(m.rec.parameters()) if m.rec is not None else [])
@@ -127,7 +132,8 @@ class Trainer:
                     p.requires_grad_(False)
                     frozen.append(p)
         try:
-            l_total, l_dis_g, l_cla_g, _, l_rec_g = m(batch, epoch, "gen_update", self.cer[1:] if self.cer else None)
+            l_total, l_dis_g, l_cla_g, _, l_rec_g = m(batch, epoch, "gen_update", self.cer[1:] if self.cer else None,
+                                                      shared=self._shared)
         finally:
             for p in frozen:
                 p.requires_grad_(True)

@@ -396,6 +396,29 @@ def main():
         except Exception as e:           # never fatal for the headline
             full_iter = {"error": repr(e)[:300]}
 
+    # ---- the same iteration with ONE generator forward: dis_update and gen_update of the reference each run the generator on the
+    # same batch with the same weights; Trainer(share_generator_forward=True) keeps the first one's autograd graph.  NOT the
+    # headline: `value` times the reference's composition.
+    shared_fwd = None
+    if not args.no_rec_extra and args.encoder == "vgg":
+        try:
+            trainer.join()
+            torch.cuda.synchronize()
+            t3 = Trainer(num_writers=500, device=dev, cuda_graph=not args.no_graph, overlap_exchange=not args.no_overlap,
+                         share_generator_forward=True)
+            for _ in range(Trainer.GRAPH_WARMUP + 2):
+                t3.train_step(resident)
+            ms_sh = timed(lambda: t3.train_step(resident), 5) / 5
+            t3.join()
+            shared_fwd = {"ms_per_step": ms_sh, "steps_per_sec": world / (ms_sh / 1e3),
+                          "note": "Trainer(share_generator_forward=True): same losses / gradients / BatchNorm buffers "
+                                  "(tests/test_gpu_models.py::test_shared_generator_forward_matches_the_reference_composition), "
+                                  "one generator forward per iteration instead of the reference's two"}
+            del t3
+            torch.cuda.empty_cache()
+        except Exception as e:
+            shared_fwd = {"error": repr(e)[:300]}
+
     # ---- BASELINE.json configs[4]: line-level generator, 64 x 1024 lines (T = 256 spaced characters), batch 32 per GPU
     line_gen = None
     try:
@@ -550,7 +573,7 @@ def main():
             "launched_tflops_per_gpu": launched_tflop / (ms_step / 1e3),
             "launched_frac_of_peak": launched_tflop / (ms_step / 1e3) / tf_peak},
         "cpu_baseline": cpu_baseline,
-        "extra": {"full_iteration_with_recogniser": full_iter, "line_generator": line_gen, "dino_generation": dino_gen, "gen_images_per_sec": gen_img_s, "gen_batch_per_gpu": B, "gen_ms_per_batch": ms_gen,
+        "extra": {"full_iteration_with_recogniser": full_iter, "iteration_with_shared_generator_forward": shared_fwd, "line_generator": line_gen, "dino_generation": dino_gen, "gen_images_per_sec": gen_img_s, "gen_batch_per_gpu": B, "gen_ms_per_batch": ms_gen,
                   "gen_frac_of_peak": None if args.encoder != "vgg" else 62.17e-3 * gen_img_s / world / tf_peak},
     }
     print(json.dumps(line), flush=True)

@@ -594,3 +594,87 @@ def test_graph_replay_sees_weights_loaded_between_iterations(specs):
         assert n_graph == t.graph_launches
     finally:
         A.set_precision("fp32")
+
+
+def test_shared_generator_forward_matches_the_reference_composition(specs):
+    """Trainer(share_generator_forward=True): dis_update generates the fake pair once WITH its autograd graph and gen_update
+    back-propagates through it, instead of the reference's two identical generator forwards per iteration
+    (network_tro.py:59-63,117-118).  Same losses, same gradients, same BatchNorm buffers (running statistics advanced twice):
+    checked in fp32 mode, where run-to-run noise is ~1e-6, and as CUDA-graph replays in the benchmarked mode (the generator's
+    autograd graph then spans two captured graphs)."""
+    from affganwriting_b200.trainer import Trainer
+    import bench
+    from affganwriting_b200 import load_data as LD
+    dev = torch.device("cuda", 0)
+    batch = LD.batch_to_device(bench.synthetic_batch(4, 50, 7), torch.device('cuda'))
+
+    def cos(x, y, sub):
+        gx = torch.cat([p.grad.flatten() for p in getattr(x.model, sub).parameters() if p.grad is not None])
+        gy = torch.cat([p.grad.flatten() for p in getattr(y.model, sub).parameters() if p.grad is not None])
+        assert gx.numel() == gy.numel()
+        return float(torch.dot(gx.double(), gy.double()) / (gx.double().norm() * gy.double().norm()))
+
+    A.set_precision("fp32")
+    torch.manual_seed(0)
+    a = Trainer(num_writers=500, device=dev)
+    b = Trainer(num_writers=500, device=dev)
+    s = Trainer(num_writers=500, device=dev, share_generator_forward=True)
+    assert s.share_generator_forward and not a.share_generator_forward
+    s.model.load_state_dict(a.model.state_dict())
+    b.model.load_state_dict(a.model.state_dict())
+    b.train_step(batch)                                           # a second default run: the noise yardstick
+    n0 = A.launch_count()
+    la = a.train_step(batch)
+    n_a = A.launch_count() - n0
+    n0 = A.launch_count()
+    ls = s.train_step(batch)
+    n_s = A.launch_count() - n0
+    assert n_s < n_a - 200                                        # one generator forward less
+    assert not s._shared                                          # consumed by gen_update
+    for k in la:
+        assert abs(float(la[k]) - float(ls[k])) <= 1e-5 * max(1.0, abs(float(la[k]))), (k, float(la[k]), float(ls[k]))
+    for sub in ("gen", "dis", "cla"):
+        c, c_noise = cos(a, s, sub), cos(a, b, sub)
+        print(f"\nfp32 {sub}: gradient cosine default/default {c_noise:.9f}, default / shared-forward {c:.9f}")
+        # (fp32 run-to-run noise: order of the fp32 atomics in the statistics / weight-gradient reductions, amplified by the
+        # un-normalised discriminator on a batch of 4)
+        assert 1.0 - c <= 10 * (1.0 - c_noise) + 1e-5
+    sa, ss = a.state_dict(), s.state_dict()
+    for k, v in sa.items():
+        if not v.is_floating_point():
+            assert torch.equal(v, ss[k]), k                       # num_batches_tracked: advanced twice per iteration
+        elif "running_" in k:
+            assert float((v - ss[k]).abs().max()) <= 1e-5 * max(1.0, float(v.abs().max())), k
+    del a, b, s
+
+    A.set_precision("f16")
+    try:
+        torch.manual_seed(0)
+        a = Trainer(num_writers=500, device=dev)
+        b = Trainer(num_writers=500, device=dev)
+        g = Trainer(num_writers=500, device=dev, cuda_graph=True, overlap_exchange=True, share_generator_forward=True)
+        g.GRAPH_WARMUP = 1
+        for t in (b, g):
+            t.model.load_state_dict(a.model.state_dict())
+        drift = drift_ee = 0.0
+        for it in range(5):                                           # eager, capture pass, then pure replays
+            la, lb, lg = a.train_step(batch), b.train_step(batch), g.train_step(batch)
+            drift = max(drift, max(abs(float(la[k]) - float(lg[k])) for k in la))
+            drift_ee = max(drift_ee, max(abs(float(la[k]) - float(lb[k])) for k in la))
+            if it < 3:
+                assert all(abs(float(la[k]) - float(lg[k])) <= 2e-3 * max(1.0, abs(float(la[k]))) for k in la), \
+                    (it, {k: (float(la[k]), float(lg[k])) for k in la})
+        assert g._graphs is not None and all(torch.isfinite(v) for v in lg.values())
+        print(f"f16: loss drift over 5 iterations eager/eager {drift_ee:.2e}, eager / graph shared-forward {drift:.2e}")
+        assert drift <= 10 * drift_ee + 2e-2
+
+        def absdrift(x, y):                                           # (Adam turns noise-level gradients into +-lr steps: absolute)
+            sx, sy = x.state_dict(), y.state_dict()
+            for k, v in sx.items():
+                if not v.is_floating_point():
+                    assert torch.equal(v, sy[k]), k
+            return max(float((v - sy[k]).abs().max()) for k, v in sx.items() if v.is_floating_point())
+        g.join()
+        assert absdrift(a, g) <= 10 * absdrift(a, b) + 0.3
+    finally:
+        A.set_precision("fp32")
