@@ -388,10 +388,14 @@ def main():
             for _ in range(Trainer.GRAPH_WARMUP + 2):
                 t2.train_step(resident)
             n0 = A.launch_count()
-            ms_full = timed(lambda: t2.train_step(resident), 3) / 3
-            full_iter = {"ms_per_step": ms_full, "steps_per_sec": world / (ms_full / 1e3),
-                         "eager_launches_per_step": (A.launch_count() - n0) / 3, "recogniser": "affganwriting_b200.recognizer.RecModel",
-                         "note": "rec_update + cla_update + dis_update + gen_update(l_dis + l_cla + l_rec), batch %d per GPU" % B}
+            # host-bound (thousands of eager launches and Python objects per iteration): single iterations jitter by +-50 %
+            # with the interpreter's garbage collector, so five are timed one by one and the median is reported
+            each = sorted(timed(lambda: t2.train_step(resident), 1) for _ in range(5))
+            ms_full = each[2]
+            full_iter = {"ms_per_step": ms_full, "steps_per_sec": world / (ms_full / 1e3), "ms_min_max": [each[0], each[-1]],
+                         "eager_launches_per_step": (A.launch_count() - n0) / 5, "recogniser": "affganwriting_b200.recognizer.RecModel",
+                         "note": "rec_update + cla_update + dis_update + gen_update(l_dis + l_cla + l_rec), batch %d per GPU; "
+                                 "median of 5 iterations timed one by one" % B}
             del t2
         except Exception as e:           # never fatal for the headline
             full_iter = {"error": repr(e)[:300]}
