@@ -16,9 +16,13 @@ import numpy as np
 import torch
 import torch.nn as nn
 
+from . import ops
 from .load_data import IMG_WIDTH, OUTPUT_MAX_LEN, vocab_size
 from .loss_tro import crit, log_softmax, recon_criterion
 from .modules_tro import DisModel, GenModel_FC, WriterClaModel
+
+import os as _os
+_MERGED_DIS_PASS = _os.environ.get("AFFGW_MERGED_DIS_PASS", "1") != "0"
 
 w_dis = 1.
 w_cla = 1.
@@ -136,12 +140,13 @@ class ConTranModel(nn.Module):
 
         if mode == "dis_update":                                  # network_tro.py:105-138
             # as above: network_tro.py:108-109 sets requires_grad_ on both real samples, nobody reads .grad
+            # One discriminator pass over [real pair | fake pair] (4B images) instead of the reference's two passes with two
+            # backward calls (network_tro.py:110-129): the discriminator has no batch-coupled layer and both losses are means
+            # over their own half, so losses and accumulated gradients are the same numbers - half the launches of the
+            # latency-bound small-map layers, one weight-gradient GEMM per layer over twice the positions.
             s1 = tr_img[:, 0:1, :, :]
             s2 = tr_img[:, 1:2, :, :]
-            l_real = self.dis.calc_dis_real_loss(self._pair(s1, s2))
-            l_real.backward(retain_graph=True)
             if shared is not None:
-                from . import ops
                 with ops.bn_updates_twice():
                     xg, xg_swap = self._generate_pair(tr_img, label_xt, label_xt_swap)
                 shared["pair"] = (xg, xg_swap)
@@ -149,9 +154,19 @@ class ConTranModel(nn.Module):
             else:
                 with torch.no_grad():
                     xg, xg_swap = self._generate_pair(tr_img, label_xt, label_xt_swap)
-            l_fake = self.dis.calc_dis_fake_loss(self._pair(xg, xg_swap))
-            l_fake.backward()
-            return l_real + l_fake
+            if not _MERGED_DIS_PASS:                                # the reference's literal sequence (A/B measurements)
+                l_real = self.dis.calc_dis_real_loss(self._pair(s1, s2))
+                l_real.backward(retain_graph=True)
+                l_fake = self.dis.calc_dis_fake_loss(self._pair(xg, xg_swap))
+                l_fake.backward()
+                return l_real + l_fake
+            n_real = 2 * s1.shape[0]
+            logits = self.dis(torch.cat([s1, s2, xg, xg_swap], dim=0))
+            l_real = ops.bce_with_logits_const(logits[:n_real], 1.0)
+            l_fake = ops.bce_with_logits_const(logits[n_real:], 0.0)
+            l_dis = l_real + l_fake
+            l_dis.backward()
+            return l_dis
 
         if mode == "eval":                                        # network_tro.py:140-177 (the PNG dump of :151 is the caller's)
             with torch.no_grad():
