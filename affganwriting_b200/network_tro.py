@@ -23,6 +23,16 @@ from .modules_tro import DisModel, GenModel_FC, WriterClaModel
 
 import os as _os
 _MERGED_DIS_PASS = _os.environ.get("AFFGW_MERGED_DIS_PASS", "1") != "0"
+_DIS_STREAM_PRIO = int(_os.environ.get("AFFGW_DIS_PRIO", "0"))
+_dis_streams = {}
+
+
+def _dis_stream(dev):
+    """The second stream of `shared={"early": True}` (one per device)."""
+    st = _dis_streams.get(dev.index)
+    if st is None:
+        st = _dis_streams[dev.index] = torch.cuda.Stream(device=dev, priority=_DIS_STREAM_PRIO)
+    return st
 
 w_dis = 1.
 w_cla = 1.
@@ -71,6 +81,22 @@ class ConTranModel(nn.Module):
     def _pair(a, b):
         return torch.cat([a, b], dim=0)
 
+    def _dis_losses(self, s1, s2, xg, xg_swap):
+        """Discriminator forward + backward of dis_update on two real and two (detached) generated samples."""
+        if not _MERGED_DIS_PASS:                                # the reference's literal sequence (A/B measurements)
+            l_real = self.dis.calc_dis_real_loss(self._pair(s1, s2))
+            l_real.backward(retain_graph=True)
+            l_fake = self.dis.calc_dis_fake_loss(self._pair(xg, xg_swap))
+            l_fake.backward()
+            return l_real + l_fake
+        n_real = 2 * s1.shape[0]
+        logits = self.dis(torch.cat([s1, s2, xg, xg_swap], dim=0))
+        l_real = ops.bce_with_logits_const(logits[:n_real], 1.0)
+        l_fake = ops.bce_with_logits_const(logits[n_real:], 0.0)
+        l_dis = l_real + l_fake
+        l_dis.backward()
+        return l_dis
+
     def _recognise(self, img, label):
         """RecModel call of network_tro.py:43,88-89: every image spans the full width."""
         widths = torch.from_numpy(np.array([IMG_WIDTH] * img.shape[0]))
@@ -87,7 +113,13 @@ class ConTranModel(nn.Module):
         (network_tro.py:117-118) and again, from the same generator weights and the same batch, in gen_update (:59-63).  With
         `shared`, dis_update runs that forward once WITH its autograd graph (BatchNorm running statistics advanced twice), trains
         the discriminator on the detached images, and gen_update back-propagates through the kept graph: same losses, same
-        gradients, one generator forward less."""
+        gradients, one generator forward less.
+
+        `shared = {"early": True}` keeps BOTH of the reference's generator forwards and only moves the second one: dis_update
+        generates the fake pair under no_grad as always, then issues gen_update's own generator forward (with its autograd graph,
+        kept in `shared["pair"]`) on the launching stream while the discriminator's forward + backward over [real | fake] runs
+        beside it on a second stream - the discriminator pass is HBM-bound 16/32-channel work, the generator forward is
+        tensor-bound, and neither reads what the other writes.  Streams join before dis_update returns."""
         tr_domain, tr_wid, tr_idx, tr_img, tr_img_width, tr_label, img_xt, label_xt, label_xt_swap = train_data_list
         tr_wid, tr_img = self._to(tr_wid), self._to(tr_img)
         img_xt, label_xt, label_xt_swap = self._to(img_xt), self._to(label_xt), self._to(label_xt_swap)
@@ -146,6 +178,20 @@ class ConTranModel(nn.Module):
             # latency-bound small-map layers, one weight-gradient GEMM per layer over twice the positions.
             s1 = tr_img[:, 0:1, :, :]
             s2 = tr_img[:, 1:2, :, :]
+            early = shared is not None and shared.get("early", False)
+            if early:
+                with torch.no_grad():
+                    xg, xg_swap = self._generate_pair(tr_img, label_xt, label_xt_swap)
+                main = torch.cuda.current_stream()
+                aux = _dis_stream(xg.device)
+                aux.wait_stream(main)                               # the fake pair (and everything queued before it)
+                with torch.cuda.stream(aux):                        # autograd runs these nodes' backward on `aux` as well
+                    l_dis = self._dis_losses(s1, s2, xg, xg_swap)
+                # gen_update's generator forward, same weights and batch (network_tro.py:59-63), after the first one: the
+                # BatchNorm running statistics advance in the reference's order
+                shared["pair"] = self._generate_pair(tr_img, label_xt, label_xt_swap)
+                main.wait_stream(aux)
+                return l_dis
             if shared is not None:
                 with ops.bn_updates_twice():
                     xg, xg_swap = self._generate_pair(tr_img, label_xt, label_xt_swap)
@@ -154,19 +200,7 @@ class ConTranModel(nn.Module):
             else:
                 with torch.no_grad():
                     xg, xg_swap = self._generate_pair(tr_img, label_xt, label_xt_swap)
-            if not _MERGED_DIS_PASS:                                # the reference's literal sequence (A/B measurements)
-                l_real = self.dis.calc_dis_real_loss(self._pair(s1, s2))
-                l_real.backward(retain_graph=True)
-                l_fake = self.dis.calc_dis_fake_loss(self._pair(xg, xg_swap))
-                l_fake.backward()
-                return l_real + l_fake
-            n_real = 2 * s1.shape[0]
-            logits = self.dis(torch.cat([s1, s2, xg, xg_swap], dim=0))
-            l_real = ops.bce_with_logits_const(logits[:n_real], 1.0)
-            l_fake = ops.bce_with_logits_const(logits[n_real:], 0.0)
-            l_dis = l_real + l_fake
-            l_dis.backward()
-            return l_dis
+            return self._dis_losses(s1, s2, xg, xg_swap)
 
         if mode == "eval":                                        # network_tro.py:140-177 (the PNG dump of :151 is the caller's)
             with torch.no_grad():

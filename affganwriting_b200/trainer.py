@@ -41,7 +41,7 @@ class Trainer:
 
     def __init__(self, num_writers=500, lr_gen=1e-4, lr_dis=1e-4, lr_cla=1e-5, device=None, skip_unused_wgrad=True,
                  bucket_bytes=None, encoder=None, cuda_graph=False, overlap_exchange=False, rec=None, lr_rec=1e-5,
-                 wgrad_stream=True, concurrent_cla_dis=True, share_generator_forward=False):
+                 wgrad_stream=True, concurrent_cla_dis=True, share_generator_forward=False, early_generator_forward=None):
         import warnings
         with warnings.catch_warnings():
             if rec is None:
@@ -99,6 +99,16 @@ class Trainer:
         # recogniser in graph mode: its gen_update is issued eagerly and cannot walk an autograd graph recorded at capture.
         self.share_generator_forward = bool(share_generator_forward) and not (rec is not None and self.cuda_graph)
         self._shared = {} if self.share_generator_forward else None
+        # Both generator forwards of the reference's iteration are executed, but gen_update's is issued inside dis_update, right
+        # after the no_grad one, and the discriminator's forward + backward runs beside it on a second stream
+        # (network_tro.ConTranModel.forward, shared={"early": True}): HBM-bound 16/32-channel work next to tensor-bound work.
+        # Default: on in the replayed configuration (graphs + overlapped exchange), like concurrent_cla_dis.
+        if early_generator_forward is None:
+            early_generator_forward = self.overlap_exchange and os.environ.get("AFFGW_EARLY_GEN", "1") != "0"
+        self.early_generator_forward = bool(early_generator_forward) and not self.share_generator_forward and \
+            not (rec is not None and self.cuda_graph)
+        if self.early_generator_forward:
+            self._shared = {"early": True}
         self._pending = {}            # sub-network -> event of its exchange + Adam queued on the side stream
         broadcast_module(m)
 

@@ -555,6 +555,7 @@ def main():
                    "encoder": args.encoder, "precision_mode": args.precision, "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
                    "cuda_graph": bool(trainer.graph_launches), "overlap_exchange": bool(trainer.overlap_exchange),
                    "wgrad_side_stream": bool(trainer.wgrad_stream), "concurrent_cla_dis": bool(trainer.concurrent_cla_dis),
+                   "early_generator_forward": bool(trainer.early_generator_forward),
                    "l2": "inputs larger than L2: 177 MB of style images are re-read every step (L2 is 126 MB)",
                    "samples_per_sec": value * B},
         "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 12,

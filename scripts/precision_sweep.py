@@ -41,12 +41,42 @@ def rnd(t, fmt, passes, scale=1.0):
     return hi / scale
 
 
+def e4m3(t, scale):
+    """saturating round to fp8 e4m3 of t * scale (scale a power of two), returned unscaled"""
+    return (t * scale).clamp(-448.0, 448.0).to(torch.float8_e4m3fn).float() / scale
+
+
+def pow2_scale(t, top):
+    amax = float(t.abs().max())
+    return 2.0 ** int(torch.floor(torch.log2(torch.tensor(top / max(amax, 1e-30)))))
+
+
+def fp8_corrected_conv(x, w, b, stride, padding, mode):
+    """a*w ~= f16(a)*f16(w) [kind::f16, 1 MMA] + e4m3(a_lo)*e4m3(w) + e4m3(a)*e4m3(w_lo) [kind::f8f6f4: 2 MMAs at twice the rate].
+    mode "f8c": per-tensor amax scales for all four fp8 planes; "f8cfix": fixed activation scales (no amax pass):
+    a * 8 (saturates above 56), a_lo * 2^14."""
+    half = lambda v: v.clamp(-65504, 65504).half().float()
+    x16, w16 = half(x), half(w * W_SCALE) / W_SCALE
+    xl, wl = x - x16, w - w16
+    if mode == "f8cfix":
+        sx, sxl = 8.0, 8.0 * 2048.0
+    else:
+        sx, sxl = pow2_scale(x, 256.0), pow2_scale(xl, 256.0)
+    sw, swl = pow2_scale(w, 256.0), pow2_scale(wl, 256.0)
+    y = F.conv2d(x16, w16, b, stride=stride, padding=padding)
+    y = y + F.conv2d(e4m3(xl, sxl), e4m3(w, sw), None, stride=stride, padding=padding)
+    y = y + F.conv2d(e4m3(x, sx), e4m3(wl, swl), None, stride=stride, padding=padding)
+    return y
+
+
 class SimConv(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w, b, stride, padding, spec):
         fx, fw, fg, pf, pd, pw = spec
         ctx.save_for_backward(x, w)
         ctx.cfg = (stride, padding, spec, b is not None)
+        if isinstance(pf, str):                                   # "f8c<bits>": one fp16 MMA + the two correction products in fp8
+            return fp8_corrected_conv(x, w, b, stride, padding, pf)
         pfx, pfw = pf if isinstance(pf, tuple) else (pf, pf)      # (planes of x, planes of w): (3, 1) = two MMAs, x split only
         return F.conv2d(rnd(x, fx, pfx), rnd(w, fw, pfw, W_SCALE if fw == "f16" else 1.0), b, stride=stride, padding=padding)
 
@@ -237,6 +267,17 @@ def main():
         show("  + dis/cla fwd 1", Policy(f3, {**{n: f1 for n in dec_up + dec_res}, "dis.": f1, "cla.": f1}))
         show("  + last 4 VGG fwd 1", Policy(f3, {n: f1 for n in dec_up + dec_res + vgg[12:]}))
         show("  + last 8 VGG fwd 1", Policy(f3, {n: f1 for n in dec_up + dec_res + vgg[8:]}))
+    elif exp == "fp8corr":
+        dec_up = ["gen.dec.model.%d.conv." % i for i in (2, 4, 6)]
+        vgg = ["gen.enc_image.model.features.%d." % i for i in (0, 3, 6, 9, 13, 16, 19, 22, 26, 29, 32, 35, 39, 42, 45, 48)]
+        f3, f1 = ("f16", "f16", "f16", 3, 1, 1), ("f16", "f16", "f16", 1, 1, 1)
+        c8, c8f = ("f16", "f16", "f16", "f8c", 1, 1), ("f16", "f16", "f16", "f8cfix", 1, 1)
+        base = {n: f1 for n in dec_up}
+        show("shipping f16: 3/1/1, ups 1", Policy(f3, base))
+        show("  all other fwd: f16 + 2 fp8 corrections (amax)", Policy(c8, base))
+        show("  all other fwd: f16 + 2 fp8 corrections (fixed)", Policy(c8f, base))
+        show("  VGG only fp8 corrections (amax)", Policy(f3, {**base, **{n: c8 for n in vgg}}))
+        show("  VGG only fp8 corrections (fixed)", Policy(f3, {**base, **{n: c8f for n in vgg}}))
     elif exp == "plans5":
         dec_up = ["gen.dec.model.%d.conv." % i for i in (2, 4, 6)]
         dec_res = ["gen.dec.model.0.model.%d.model.%d.conv." % (i, j) for i in (0, 1) for j in (0, 1)]

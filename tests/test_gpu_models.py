@@ -596,6 +596,89 @@ def test_graph_replay_sees_weights_loaded_between_iterations(specs):
         A.set_precision("fp32")
 
 
+def test_early_generator_forward_matches_the_single_stream_iteration(specs):
+    """Trainer(early_generator_forward=True) - the default of the replayed configuration: gen_update's generator forward is
+    issued inside dis_update, beside the discriminator pass on a second stream.  Same launches, same losses, same gradients
+    and BatchNorm buffers as the single-stream iteration; checked eagerly in fp32 (run-to-run noise ~1e-6) and as CUDA-graph
+    replays in the benchmarked mode against an eager trainer with the option off."""
+    from affganwriting_b200.trainer import Trainer
+    import bench
+    from affganwriting_b200 import load_data as LD
+    dev = torch.device("cuda", 0)
+    batch = LD.batch_to_device(bench.synthetic_batch(4, 50, 7), torch.device('cuda'))
+
+    def cos(x, y, sub):
+        gx = torch.cat([p.grad.flatten() for p in getattr(x.model, sub).parameters() if p.grad is not None])
+        gy = torch.cat([p.grad.flatten() for p in getattr(y.model, sub).parameters() if p.grad is not None])
+        assert gx.numel() == gy.numel()
+        return float(torch.dot(gx.double(), gy.double()) / (gx.double().norm() * gy.double().norm()))
+
+    A.set_precision("fp32")
+    torch.manual_seed(0)
+    a = Trainer(num_writers=500, device=dev)
+    b = Trainer(num_writers=500, device=dev)
+    s = Trainer(num_writers=500, device=dev, early_generator_forward=True)
+    assert s.early_generator_forward and not a.early_generator_forward and not a.share_generator_forward
+    s.model.load_state_dict(a.model.state_dict())
+    b.model.load_state_dict(a.model.state_dict())
+    b.train_step(batch)                                           # a second default run: the noise yardstick
+    n0 = A.launch_count()
+    la = a.train_step(batch)
+    n_a = A.launch_count() - n0
+    n0 = A.launch_count()
+    ls = s.train_step(batch)
+    n_s = A.launch_count() - n0
+    assert n_s == n_a                                             # nothing skipped: both generator forwards run
+    assert "pair" not in s._shared                                # consumed by gen_update
+    torch.cuda.synchronize()
+    for k in la:
+        assert abs(float(la[k]) - float(ls[k])) <= 1e-5 * max(1.0, abs(float(la[k]))), (k, float(la[k]), float(ls[k]))
+    for sub in ("gen", "dis", "cla"):
+        c, c_noise = cos(a, s, sub), cos(a, b, sub)
+        print(f"\nfp32 {sub}: gradient cosine default/default {c_noise:.9f}, default / early generator forward {c:.9f}")
+        assert 1.0 - c <= 10 * (1.0 - c_noise) + 1e-5
+    sa, ss = a.state_dict(), s.state_dict()
+    for k, v in sa.items():
+        if not v.is_floating_point():
+            assert torch.equal(v, ss[k]), k
+        elif "running_" in k:
+            assert float((v - ss[k]).abs().max()) <= 1e-5 * max(1.0, float(v.abs().max())), k
+    del a, b, s
+
+    A.set_precision("f16")
+    try:
+        torch.manual_seed(0)
+        a = Trainer(num_writers=500, device=dev)
+        b = Trainer(num_writers=500, device=dev)
+        g = Trainer(num_writers=500, device=dev, cuda_graph=True, overlap_exchange=True)
+        assert g.early_generator_forward and not a.early_generator_forward
+        g.GRAPH_WARMUP = 1
+        for t in (b, g):
+            t.model.load_state_dict(a.model.state_dict())
+        drift = drift_ee = 0.0
+        for it in range(5):                                           # eager, capture pass, then pure replays
+            la, lb, lg = a.train_step(batch), b.train_step(batch), g.train_step(batch)
+            drift = max(drift, max(abs(float(la[k]) - float(lg[k])) for k in la))
+            drift_ee = max(drift_ee, max(abs(float(la[k]) - float(lb[k])) for k in la))
+            if it < 3:
+                assert all(abs(float(la[k]) - float(lg[k])) <= 2e-3 * max(1.0, abs(float(la[k]))) for k in la), \
+                    (it, {k: (float(la[k]), float(lg[k])) for k in la})
+        assert g._graphs is not None and all(torch.isfinite(v) for v in lg.values())
+        print(f"f16: loss drift over 5 iterations eager/eager {drift_ee:.2e}, eager / graph with early generator forward {drift:.2e}")
+        assert drift <= 10 * drift_ee + 2e-2
+
+        def absdrift(x, y):
+            sx, sy = x.state_dict(), y.state_dict()
+            for k, v in sx.items():
+                if not v.is_floating_point():
+                    assert torch.equal(v, sy[k]), k
+            return max(float((v - sy[k]).abs().max()) for k, v in sx.items() if v.is_floating_point())
+        g.join()
+        assert absdrift(a, g) <= 10 * absdrift(a, b) + 0.3
+    finally:
+        A.set_precision("fp32")
+
+
 def test_shared_generator_forward_matches_the_reference_composition(specs):
     """Trainer(share_generator_forward=True): dis_update generates the fake pair once WITH its autograd graph and gen_update
     back-propagates through it, instead of the reference's two identical generator forwards per iteration
