@@ -119,7 +119,10 @@ class ConTranModel(nn.Module):
         generates the fake pair under no_grad as always, then issues gen_update's own generator forward (with its autograd graph,
         kept in `shared["pair"]`) on the launching stream while the discriminator's forward + backward over [real | fake] runs
         beside it on a second stream - the discriminator pass is HBM-bound 16/32-channel work, the generator forward is
-        tensor-bound, and neither reads what the other writes.  Streams join before dis_update returns."""
+        tensor-bound, and neither reads what the other writes.  Streams join before dis_update returns.
+        `shared = {"heads": True, ...}`: in gen_update the writer classifier's pass over the generated pair runs on the second
+        stream beside the discriminator's.  `"share": False` switches the single-forward behaviour off for a dict that only
+        carries the stream flags."""
         tr_domain, tr_wid, tr_idx, tr_img, tr_img_width, tr_label, img_xt, label_xt, label_xt_swap = train_data_list
         tr_wid, tr_img = self._to(tr_wid), self._to(tr_img)
         img_xt, label_xt, label_xt_swap = self._to(img_xt), self._to(label_xt), self._to(label_xt_swap)
@@ -151,8 +154,19 @@ class ConTranModel(nn.Module):
             else:
                 xg, xg_swap = self._generate_pair(tr_img, label_xt, label_xt_swap)
             both, wid2 = self._pair(xg, xg_swap), self._pair(tr_wid, tr_wid)
-            l_dis = self.dis.calc_gen_loss(both)
-            l_cla = self.cla(both, wid2)
+            if shared is not None and shared.get("heads", False):
+                # the two critics of the generated pair are independent of each other: the classifier's forward (and, because
+                # autograd runs a node's backward on the stream of its forward, its backward) on the second stream
+                main = torch.cuda.current_stream()
+                aux = _dis_stream(both.device)
+                aux.wait_stream(main)
+                with torch.cuda.stream(aux):
+                    l_cla = self.cla(both, wid2)
+                l_dis = self.dis.calc_gen_loss(both)
+                main.wait_stream(aux)
+            else:
+                l_dis = self.dis.calc_gen_loss(both)
+                l_cla = self.cla(both, wid2)
             l_l1 = torch.zeros((), device=xg.device) if self.oov else recon_criterion(xg, img_xt)   # network_tro.py:82-85
             if self.rec is not None:                              # network_tro.py:87-97
                 pred_xt = self._recognise(xg, label_xt)
@@ -192,7 +206,7 @@ class ConTranModel(nn.Module):
                 shared["pair"] = self._generate_pair(tr_img, label_xt, label_xt_swap)
                 main.wait_stream(aux)
                 return l_dis
-            if shared is not None:
+            if shared is not None and shared.get("share", True):
                 with ops.bn_updates_twice():
                     xg, xg_swap = self._generate_pair(tr_img, label_xt, label_xt_swap)
                 shared["pair"] = (xg, xg_swap)

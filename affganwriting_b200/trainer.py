@@ -41,7 +41,8 @@ class Trainer:
 
     def __init__(self, num_writers=500, lr_gen=1e-4, lr_dis=1e-4, lr_cla=1e-5, device=None, skip_unused_wgrad=True,
                  bucket_bytes=None, encoder=None, cuda_graph=False, overlap_exchange=False, rec=None, lr_rec=1e-5,
-                 wgrad_stream=True, concurrent_cla_dis=True, share_generator_forward=False, early_generator_forward=None):
+                 wgrad_stream=True, concurrent_cla_dis=True, share_generator_forward=False, early_generator_forward=None,
+                 concurrent_gen_heads=None):
         import warnings
         with warnings.catch_warnings():
             if rec is None:
@@ -109,6 +110,14 @@ class Trainer:
             not (rec is not None and self.cuda_graph)
         if self.early_generator_forward:
             self._shared = {"early": True}
+        # gen_update: the classifier's pass over the generated pair beside the discriminator's (two independent critics)
+        if concurrent_gen_heads is None:
+            concurrent_gen_heads = self.overlap_exchange and os.environ.get("AFFGW_GEN_HEADS", "1") != "0"
+        self.concurrent_gen_heads = bool(concurrent_gen_heads) and rec is None
+        if self.concurrent_gen_heads:
+            if self._shared is None:
+                self._shared = {"share": False}
+            self._shared["heads"] = True
         self._pending = {}            # sub-network -> event of its exchange + Adam queued on the side stream
         broadcast_module(m)
 

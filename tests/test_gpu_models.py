@@ -597,8 +597,9 @@ def test_graph_replay_sees_weights_loaded_between_iterations(specs):
 
 
 def test_early_generator_forward_matches_the_single_stream_iteration(specs):
-    """Trainer(early_generator_forward=True) - the default of the replayed configuration: gen_update's generator forward is
-    issued inside dis_update, beside the discriminator pass on a second stream.  Same launches, same losses, same gradients
+    """Trainer(early_generator_forward=True, concurrent_gen_heads=True) - the defaults of the replayed configuration:
+    gen_update's generator forward is issued inside dis_update, beside the discriminator pass on a second stream, and in
+    gen_update the classifier's pass over the generated pair runs beside the discriminator's.  Same launches, same losses, same gradients
     and BatchNorm buffers as the single-stream iteration; checked eagerly in fp32 (run-to-run noise ~1e-6) and as CUDA-graph
     replays in the benchmarked mode against an eager trainer with the option off."""
     from affganwriting_b200.trainer import Trainer
@@ -617,8 +618,9 @@ def test_early_generator_forward_matches_the_single_stream_iteration(specs):
     torch.manual_seed(0)
     a = Trainer(num_writers=500, device=dev)
     b = Trainer(num_writers=500, device=dev)
-    s = Trainer(num_writers=500, device=dev, early_generator_forward=True)
-    assert s.early_generator_forward and not a.early_generator_forward and not a.share_generator_forward
+    s = Trainer(num_writers=500, device=dev, early_generator_forward=True, concurrent_gen_heads=True)
+    assert s.early_generator_forward and s.concurrent_gen_heads
+    assert not a.early_generator_forward and not a.concurrent_gen_heads and not a.share_generator_forward
     s.model.load_state_dict(a.model.state_dict())
     b.model.load_state_dict(a.model.state_dict())
     b.train_step(batch)                                           # a second default run: the noise yardstick
@@ -651,7 +653,7 @@ def test_early_generator_forward_matches_the_single_stream_iteration(specs):
         a = Trainer(num_writers=500, device=dev)
         b = Trainer(num_writers=500, device=dev)
         g = Trainer(num_writers=500, device=dev, cuda_graph=True, overlap_exchange=True)
-        assert g.early_generator_forward and not a.early_generator_forward
+        assert g.early_generator_forward and g.concurrent_gen_heads and not a.early_generator_forward
         g.GRAPH_WARMUP = 1
         for t in (b, g):
             t.model.load_state_dict(a.model.state_dict())
