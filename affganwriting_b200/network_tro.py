@@ -25,6 +25,15 @@ import os as _os
 _MERGED_DIS_PASS = _os.environ.get("AFFGW_MERGED_DIS_PASS", "1") != "0"
 _DIS_STREAM_PRIO = int(_os.environ.get("AFFGW_DIS_PRIO", "0"))
 _dis_streams = {}
+_text_streams = {}
+
+
+def _text_stream(dev):
+    """The text encoder's stream of ConTranModel.side_text_encoder (one per device)."""
+    st = _text_streams.get(dev.index)
+    if st is None:
+        st = _text_streams[dev.index] = torch.cuda.Stream(device=dev)
+    return st
 
 
 def _dis_stream(dev):
@@ -59,12 +68,31 @@ class ConTranModel(nn.Module):
         self.show_iter_num = show_iter_num
         self.oov = oov
         self.device_ = dev
+        self.side_text_encoder = False      # set by trainer.Trainer: text encoder beside the image encoder (_generate_pair)
 
     def _to(self, t):
         return t.to(self.device_, non_blocking=True)
 
     def _generate_pair(self, tr_img, label_xt, label_xt_swap):
         g = self.gen
+        if self.side_text_encoder:
+            # the text encoder (a chain of ~15 latency-bound launches per label) depends on nothing the image encoder computes:
+            # both calls run on their own stream, forked in front of the image encoder, and join before `mix` (their
+            # BatchNorm1d statistics advance label first, swapped label second, as in the reference)
+            main = torch.cuda.current_stream()
+            aux = _text_stream(tr_img.device)
+            fork = torch.cuda.Event()
+            fork.record(main)
+            f_xss = g.enc_image(tr_img)
+            f_xs = f_xss[-1]
+            aux.wait_event(fork)
+            with torch.cuda.stream(aux):
+                f_xt, f_embed = g.enc_text(label_xt, f_xs.shape)
+                f_xt_s, f_embed_s = g.enc_text(label_xt_swap, f_xs.shape)
+            main.wait_stream(aux)
+            xg = g.decode(g.mix(f_xss, f_embed), f_xss, f_embed, f_xt)
+            xg_swap = g.decode(g.mix(f_xss, f_embed_s), f_xss, f_embed_s, f_xt_s)
+            return xg, xg_swap
         f_xss = g.enc_image(tr_img)
         f_xs = f_xss[-1]
         f_xt, f_embed = g.enc_text(label_xt, f_xs.shape)

@@ -119,6 +119,8 @@ class Trainer:
                 self._shared = {"share": False}
             self._shared["heads"] = True
         self._pending = {}            # sub-network -> event of its exchange + Adam queued on the side stream
+        # the generator's text encoder on its own stream beside the image encoder (ConTranModel._generate_pair)
+        m.side_text_encoder = self.overlap_exchange and os.environ.get("AFFGW_SIDE_TEXT", "1") != "0"
         broadcast_module(m)
 
     # ------------------------------------------------------------------------------------------------ sub-steps

@@ -557,6 +557,7 @@ def main():
                    "wgrad_side_stream": bool(trainer.wgrad_stream), "concurrent_cla_dis": bool(trainer.concurrent_cla_dis),
                    "early_generator_forward": bool(trainer.early_generator_forward),
                    "concurrent_gen_heads": bool(trainer.concurrent_gen_heads),
+                   "side_text_encoder": bool(trainer.model.side_text_encoder),
                    "l2": "inputs larger than L2: 177 MB of style images are re-read every step (L2 is 126 MB)",
                    "samples_per_sec": value * B},
         "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 12,

@@ -3,10 +3,10 @@
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_gpu_models.py -q --no-header -p no:cacheprovider -x -s \
     -k "early_generator or shared_generator or graph or short_final" > gpurun_out/t_early.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/t_early.log
-for v in "0 0" "1 0" "1 1"; do
+for v in "1 0" "1 1"; do
     set -- $v
-    AFFGW_EARLY_GEN=$1 AFFGW_GEN_HEADS=$2 timeout 600 python bench.py --quick --steps 20 --warmup 3 > gpurun_out/ab_early_$1_$2.json 2> gpurun_out/ab_early_$1_$2.err
-    echo "early=$1 heads=$2 rc=$?"
+    AFFGW_EARLY_GEN=$1 AFFGW_SIDE_TEXT=$2 timeout 600 python bench.py --quick --steps 20 --warmup 3 > gpurun_out/ab_early_$1_$2.json 2> gpurun_out/ab_early_$1_$2.err
+    echo "early=$1 side_text=$2 rc=$?"
     python - "$1" "$2" <<'PY'
 import json, sys
 try:

@@ -620,6 +620,7 @@ def test_early_generator_forward_matches_the_single_stream_iteration(specs):
     b = Trainer(num_writers=500, device=dev)
     s = Trainer(num_writers=500, device=dev, early_generator_forward=True, concurrent_gen_heads=True)
     assert s.early_generator_forward and s.concurrent_gen_heads
+    s.model.side_text_encoder = True                              # (the Trainer switches it on with overlap_exchange)
     assert not a.early_generator_forward and not a.concurrent_gen_heads and not a.share_generator_forward
     s.model.load_state_dict(a.model.state_dict())
     b.model.load_state_dict(a.model.state_dict())
@@ -654,6 +655,7 @@ def test_early_generator_forward_matches_the_single_stream_iteration(specs):
         b = Trainer(num_writers=500, device=dev)
         g = Trainer(num_writers=500, device=dev, cuda_graph=True, overlap_exchange=True)
         assert g.early_generator_forward and g.concurrent_gen_heads and not a.early_generator_forward
+        assert g.model.side_text_encoder and not a.model.side_text_encoder
         g.GRAPH_WARMUP = 1
         for t in (b, g):
             t.model.load_state_dict(a.model.state_dict())
