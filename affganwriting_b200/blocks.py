@@ -15,6 +15,9 @@ from torch import nn
 
 from . import ops
 
+import os as _os
+_RELAXED_RES = _os.environ.get("AFFGW_RELAXED_RES", "1") != "0"
+
 _ACTS = ("relu", "lrelu", "tanh", "none")
 _PADS = ("reflect", "replicate", "zero")
 
@@ -54,9 +57,14 @@ class ResBlock(nn.Module):
 
     def forward(self, x):
         x = ops.input_to_internal(x)
-        h = self.model[0](x)
-        # `out += residual` (blocks.py:38) is fused into the second block's normalisation epilogue
-        return self.model[1](h, residual=x)
+        if ops.relaxed() and _RELAXED_RES:          # ops.relaxed_forward: the two 3x3 convolutions (not the iAFF 1x1s) single-pass
+            self.model[0].fwd_passes = self.model[1].fwd_passes = 1
+        try:
+            h = self.model[0](x)
+            # `out += residual` (blocks.py:38) is fused into the second block's normalisation epilogue
+            return self.model[1](h, residual=x)
+        finally:
+            self.model[0].fwd_passes = self.model[1].fwd_passes = None
 
 
 class ActFirstResBlock(nn.Module):
@@ -150,15 +158,17 @@ class Conv2dBlock(nn.Module):
         self._pad, self._pad_type, self._st = int(padding), pad_type, int(st)
         self._norm_kind, self._act = norm, activation
         self.upsample = 1   # Decoder folds the preceding nn.Upsample(scale_factor=2) into the gather
+        self.fwd_passes = None   # set to 1 by ResBlock inside ops.relaxed_forward()
 
     def forward(self, x, residual=None, addend=None, out_dtype=None):
         """residual: added after norm+activation (ResBlock); addend: added to the raw conv result (shortcut)."""
         x = ops.input_to_internal(x)
         act, first = self._act, self.activation_first
         fuse_post = (self._norm_kind == "none" and not first)
-        y = ops.conv2d(x, self.conv.weight, self.conv.bias, stride=self._st, pad=self._pad, pad_mode=self._pad_type,
-                       upsample=self.upsample, pre_act=act if first else "none",
-                       post_act=act if fuse_post else "none", addend=addend, out_dtype=out_dtype)
+        with ops.conv_passes(fwd=self.fwd_passes):      # None keeps the mode's pass count
+            y = ops.conv2d(x, self.conv.weight, self.conv.bias, stride=self._st, pad=self._pad, pad_mode=self._pad_type,
+                           upsample=self.upsample, pre_act=act if first else "none",
+                           post_act=act if fuse_post else "none", addend=addend, out_dtype=out_dtype)
         post = "none" if first else act
         if self._norm_kind == "in":
             y = ops.instance_norm(y, act=post, residual=residual, eps=self.norm.eps)

@@ -23,6 +23,7 @@ from .modules_tro import DisModel, GenModel_FC, WriterClaModel
 
 import os as _os
 _MERGED_DIS_PASS = _os.environ.get("AFFGW_MERGED_DIS_PASS", "1") != "0"
+_RELAXED_DIS_FWD = _os.environ.get("AFFGW_RELAXED_DIS_FWD", "1") != "0"
 _DIS_STREAM_PRIO = int(_os.environ.get("AFFGW_DIS_PRIO", "0"))
 _dis_streams = {}
 _text_streams = {}
@@ -222,7 +223,7 @@ class ConTranModel(nn.Module):
             s2 = tr_img[:, 1:2, :, :]
             early = shared is not None and shared.get("early", False)
             if early:
-                with torch.no_grad():
+                with torch.no_grad(), ops.relaxed_forward(_RELAXED_DIS_FWD):
                     xg, xg_swap = self._generate_pair(tr_img, label_xt, label_xt_swap)
                 main = torch.cuda.current_stream()
                 aux = _dis_stream(xg.device)
@@ -240,7 +241,8 @@ class ConTranModel(nn.Module):
                 shared["pair"] = (xg, xg_swap)
                 xg, xg_swap = xg.detach(), xg_swap.detach()
             else:
-                with torch.no_grad():
+                # this pair only feeds the discriminator: the layers that tolerate it run one tensor-core pass (ops.relaxed_forward)
+                with torch.no_grad(), ops.relaxed_forward(_RELAXED_DIS_FWD):
                     xg, xg_swap = self._generate_pair(tr_img, label_xt, label_xt_swap)
             return self._dis_losses(s1, s2, xg, xg_swap)
 

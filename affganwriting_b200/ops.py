@@ -146,6 +146,29 @@ class conv_passes:
         _state["passes"] = self.prev
 
 
+class relaxed_forward:
+    """Context manager for a generator forward whose image only FEEDS the discriminator (dis_update's no_grad pair,
+    network_tro.py:117-118): inside, the layers that declare themselves tolerant (`relaxed()` is true for them) run their forward
+    GEMM with one fp16 MMA per product instead of three.  Which layers tolerate it is decided by the discriminator's gradients
+    (scripts/precision_sweep.py disfwd, then measured on B200 at the benchmarked shapes): VGG convolutions 5-16 and the decoder's
+    ResBlock convolutions leave the worst discriminator tensor at cosine 0.99994, every layer single-pass 0.9994 (the first four
+    VGG layers stay at three passes).  Mode 'f16' only."""
+
+    def __init__(self, flag=True):
+        self.flag = bool(flag)
+
+    def __enter__(self):
+        self.prev = _state.get("relaxed", False)
+        _state["relaxed"] = self.flag and _state["mode"] == "f16"
+
+    def __exit__(self, *a):
+        _state["relaxed"] = self.prev
+
+
+def relaxed():
+    return bool(_state.get("relaxed", False))
+
+
 class operand_format:
     """Context manager: the position-space convolutions whose forward is issued inside run on FP16 operand planes, one MMA per
     product in all three GEMMs (fmt = "f16"), instead of the mode's bf16 planes.  fp16 carries 11 significant bits per plane

@@ -8,6 +8,14 @@ import torch.nn as nn
 
 from . import load_data, ops
 
+import os as _os
+
+# `features` index of the first convolution that runs single-pass inside ops.relaxed_forward(): 14 = conv3_1, i.e. convolutions
+# 5-16 (80 % of the encoder's FLOPs).  Measured on B200 at 50 planes, batch 8 (tests/test_gpu_parity_c50.py, complete dis_update,
+# worst discriminator tensor): from 26 -> 0.999985, 19 -> 0.99992, 14 -> 0.99994, 7 -> 0.99969, 0 (every layer) -> 0.99938;
+# a value past the last convolution (48) switches the relaxation off
+RELAXED_FROM = int(_os.environ.get("AFFGW_RELAXED_VGG_FROM", "14"))
+
 cfg = {
     "E": [64, 64, 128, 128, "M", 256, 256, 256, 256, "M", 512, 512, 512, 512, "M", 512, 512, 512, 512],
 }
@@ -48,7 +56,11 @@ class VGG(nn.Module):
         while i < stop:
             m = feats[i]
             if isinstance(m, nn.Conv2d):
-                x = ops.conv2d(x, m.weight, m.bias, stride=1, pad=1, pad_mode="zero")
+                if ops.relaxed() and i >= RELAXED_FROM:         # ops.relaxed_forward: one fp16 pass for the deep layers
+                    with ops.conv_passes(fwd=1):
+                        x = ops.conv2d(x, m.weight, m.bias, stride=1, pad=1, pad_mode="zero")
+                else:
+                    x = ops.conv2d(x, m.weight, m.bias, stride=1, pad=1, pad_mode="zero")
                 nxt = feats[i + 1] if i + 1 < stop else None
                 if isinstance(nxt, nn.InstanceNorm2d):
                     has_relu = i + 2 < stop and isinstance(feats[i + 2], nn.ReLU)

@@ -266,7 +266,7 @@ def main():
     import torch.distributed as dist
 
     import affganwriting_b200 as A
-    from affganwriting_b200 import _lib, ops
+    from affganwriting_b200 import _lib, network_tro, ops
     from affganwriting_b200 import load_data as LD
     from affganwriting_b200.trainer import Trainer
 
@@ -542,7 +542,9 @@ def main():
         "metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16" if args.precision == "f16" else "bf16",
         "dtype_detail": ("tcgen05 kind::f16 MMAs on %s operand planes with fp32 TMEM accumulation (forward: split operands, 3 MMAs per "
-                         "product - 1 in the decoder's up-convolutions in mode f16; backward: 1 MMA per product); activations, "
+                         "product - 1 in the decoder's up-convolutions in mode f16 and, in the no_grad generator forward of dis_update whose image "
+                         "only feeds the discriminator, in the deep half of the VGG encoder and the decoder ResBlocks "
+                         "(ops.relaxed_forward); backward: 1 MMA per product); activations, "
                          "statistics, gradients and parameters are stored in fp32.  fp16 planes carry 11 significant bits against "
                          "bf16's 8 at the same tensor throughput; their range is handled by exact power-of-two scales "
                          "(DESIGN.md section 3)" % ("fp16" if args.precision == "f16" else "bf16")),
@@ -558,6 +560,7 @@ def main():
                    "early_generator_forward": bool(trainer.early_generator_forward),
                    "concurrent_gen_heads": bool(trainer.concurrent_gen_heads),
                    "side_text_encoder": bool(trainer.model.side_text_encoder),
+                   "relaxed_dis_update_forward": bool(network_tro._RELAXED_DIS_FWD and args.precision == "f16"),
                    "l2": "inputs larger than L2: 177 MB of style images are re-read every step (L2 is 126 MB)",
                    "samples_per_sec": value * B},
         "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 12,

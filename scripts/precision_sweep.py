@@ -140,10 +140,13 @@ def cosine(a, b):
     return float((a @ b) / (a.norm() * b.norm() + 1e-300))
 
 
-def run(full, batch, policy):
-    """gen_update + dis_update + cla_update under `policy`; returns images and gradients."""
+def run(full, batch, policy, dis_policy=None):
+    """gen_update + dis_update + cla_update under `policy` (dis_update under `dis_policy` when given); returns images and
+    gradients."""
     POLICY[0] = policy
     policy.bind(full)
+    if dis_policy is not None:
+        dis_policy.bind(full)
     for p in full.values():
         p.grad = None
     lt, ld, lc, xg, xgs = O.gen_update(batch, full)
@@ -151,7 +154,10 @@ def run(full, batch, policy):
     gg = {k: v.grad.clone() for k, v in full.items() if k.startswith("gen.") and v.grad is not None}
     for p in full.values():
         p.grad = None
+    if dis_policy is not None:
+        POLICY[0] = dis_policy
     l_real, l_fake = O.dis_update(batch, full)
+    POLICY[0] = policy
     (l_real + l_fake).backward()
     dg = {k: v.grad.clone() for k, v in full.items() if k.startswith("dis.") and v.grad is not None}
     for p in full.values():
@@ -267,6 +273,29 @@ def main():
         show("  + dis/cla fwd 1", Policy(f3, {**{n: f1 for n in dec_up + dec_res}, "dis.": f1, "cla.": f1}))
         show("  + last 4 VGG fwd 1", Policy(f3, {n: f1 for n in dec_up + dec_res + vgg[12:]}))
         show("  + last 8 VGG fwd 1", Policy(f3, {n: f1 for n in dec_up + dec_res + vgg[8:]}))
+    elif exp == "disfwd":
+        # the generator forward of dis_update runs under no_grad and only feeds the discriminator: how few passes does IT need?
+        dec_up = ["gen.dec.model.%d.conv." % i for i in (2, 4, 6)]
+        f3, f1 = ("f16", "f16", "f16", 3, 1, 1), ("f16", "f16", "f16", 1, 1, 1)
+        base = {n: f1 for n in dec_up}
+        ship = Policy(f3, base)
+        def show2(tag, dis_policy):
+            r = compare(ref, run(full, batch, ship, dis_policy), noise)
+            print("%-44s %s" % (tag, fmt(r)), flush=True)
+        show2("shipping everywhere", None)
+        if len(sys.argv) <= 4:
+            show2("dis_update: generator fwd 1 pass (f16)", Policy(f3, {"gen.": f1}))
+            show2("dis_update: generator fwd 1 pass (bf16)", Policy(f3, {"gen.": ("bf16", "bf16", "bf16", 1, 1, 1)}))
+        vgg = ["gen.enc_image.model.features.%d." % i for i in (0, 3, 6, 9, 13, 16, 19, 22, 26, 29, 32, 35, 39, 42, 45, 48)]
+        show2("dis_update: VGG fwd 1 pass, decoder as shipped", Policy(f3, {**base, **{n: f1 for n in vgg}}))
+        dec_res = ["gen.dec.model.0.model.%d.model.%d.conv." % (i, j) for i in (0, 1) for j in (0, 1)]
+        if len(sys.argv) > 5:
+            for k in (2, 4, 6, 8):
+                show2("dis_update: VGG[%d:] + decoder ResBlocks fwd 1 pass" % k, Policy(f3, {**base, **{n: f1 for n in vgg[k:] + dec_res}}))
+            return
+        for k in (8, 12):
+            show2("dis_update: VGG[%d:] fwd 1 pass" % k, Policy(f3, {**base, **{n: f1 for n in vgg[k:]}}))
+        show2("dis_update: decoder ResBlocks fwd 1 pass", Policy(f3, {**base, **{n: f1 for n in dec_res}}))
     elif exp == "fp8corr":
         dec_up = ["gen.dec.model.%d.conv." % i for i in (2, 4, 6)]
         vgg = ["gen.enc_image.model.features.%d." % i for i in (0, 3, 6, 9, 13, 16, 19, 22, 26, 29, 32, 35, 39, 42, 45, 48)]

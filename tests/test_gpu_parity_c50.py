@@ -141,6 +141,32 @@ def test_c50_b8_dis_and_cla_update_gradients(bf16, specs):
     assert gc >= COS_BAR and rows_c[0][0] >= COS_BAR, rows_c[:4]
 
 
+def test_c50_b8_dis_update_with_its_own_generator_forward(bf16, specs):
+    """The COMPLETE dis_update (network_tro.py:105-138) through ConTranModel.forward: the fake pair comes from this package's
+    generator under no_grad - in mode 'f16' with ops.relaxed_forward (one tensor-core pass in the deep half of the VGG encoder
+    and in the decoder's ResBlock convolutions; that image feeds nothing but the discriminator).  The discriminator's gradients
+    against the fp32 oracle, per tensor: the bar is north_star's 0.999, the relaxation must leave at least a 2x margin."""
+    from affganwriting_b200.network_tro import ConTranModel
+    cpu = O.synthetic_batch(8, 50)
+    full = _full_state(specs)
+    l_real, l_fake = O.dis_update(cpu, full)
+    (l_real + l_fake).backward()
+    ref_d = {k[4:]: v.grad for k, v in full.items() if k.startswith("dis.") and v.grad is not None}
+    model = ConTranModel(O.NUM_WRITERS, device=torch.device("cuda", 0))
+    model.load_state_dict({k: v.detach() for k, v in full.items()})
+    model.train()
+    batch = (None, cpu["tr_wid"], None, cpu["tr_img"], None, None, cpu["img_xt"], cpu["label_xt"], cpu["label_xt_swap"])
+    got = model(batch, 0, "dis_update")
+    assert abs(float(got) - float(l_real + l_fake)) <= 4e-3, (float(got), float(l_real + l_fake))
+    gd, rows = _compare(model.dis.named_parameters(), ref_d)
+    relaxed = bf16 == "f16"
+    print(f"\n[{bf16}, C_s=50, B=8] complete dis_update ({'relaxed' if relaxed else 'three-pass'} generator forward): gradient cosine "
+          f"global {gd:.6f}, worst tensors: " + ", ".join(f"{c:.6f} {k}" for c, k in rows[:3]))
+    assert gd >= COS_BAR
+    assert 1.0 - rows[0][0] <= (1.0 - COS_BAR) / 2, rows[:4]
+    A.check_device_errors()
+
+
 def test_b64_samples_are_independent_in_the_style_encoder(bf16, specs):
     """Batch 64 (the benchmarked batch) without a batch-64 oracle run: the VGG-IN encoder has per-sample statistics only
     (vgg_tro_channel3_modi.py:47-50), so sample i of a 64-sample forward must equal the same sample encoded in a batch of 8
