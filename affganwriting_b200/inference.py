@@ -13,8 +13,14 @@ from . import ops
 
 
 class GraphedGenerator:
-    def __init__(self, gen, warmup=2):
+    """`relaxed=True` (mode 'f16', VGG encoder; off by default): VGG convolutions 9-16 and the decoder's ResBlock convolutions
+    run one tensor-core pass instead of three (ops.relaxed_forward) - the image moves from 1.5e-3 to 6e-3 of the fp32
+    reference's (bar 2e-2, tests/test_gpu_parity_c50.py) for 1.4x the images per second."""
+    RELAXED_VGG_FROM = 26
+
+    def __init__(self, gen, warmup=2, relaxed=False):
         self.gen = gen
+        self.relaxed = bool(relaxed)
         self.warmup = int(warmup)
         self._graph = None
         self._shape = None
@@ -32,7 +38,7 @@ class GraphedGenerator:
             if self._calls < self.warmup:                 # eager calls on the capture stream: lazy initialisation, allocator
                 self._calls += 1
                 self._side.wait_stream(torch.cuda.current_stream())
-                with torch.cuda.stream(self._side):
+                with torch.cuda.stream(self._side), ops.relaxed_forward(self.relaxed, self.RELAXED_VGG_FROM):
                     out = self.gen(tr_img, label)
                 torch.cuda.current_stream().wait_stream(self._side)
                 return out
@@ -40,7 +46,7 @@ class GraphedGenerator:
             torch.cuda.synchronize()
             ops.clear_weight_cache(self.gen)              # every packed weight the graph reads is packed inside it
             self._graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self._graph, stream=self._side):
+            with torch.cuda.graph(self._graph, stream=self._side), ops.relaxed_forward(self.relaxed, self.RELAXED_VGG_FROM):
                 self._out = self.gen(self._img, self._lab)
         self._img.copy_(tr_img, non_blocking=True)
         self._lab.copy_(label, non_blocking=True)

@@ -154,19 +154,26 @@ class relaxed_forward:
     ResBlock convolutions leave the worst discriminator tensor at cosine 0.99994, every layer single-pass 0.9994 (the first four
     VGG layers stay at three passes).  Mode 'f16' only."""
 
-    def __init__(self, flag=True):
+    def __init__(self, flag=True, vgg_from=None):
         self.flag = bool(flag)
+        self.vgg_from = vgg_from        # `features` index of the first single-pass VGG convolution; None = the encoder's default
 
     def __enter__(self):
-        self.prev = _state.get("relaxed", False)
+        self.prev = (_state.get("relaxed", False), _state.get("relaxed_from"))
         _state["relaxed"] = self.flag and _state["mode"] == "f16"
+        _state["relaxed_from"] = self.vgg_from
 
     def __exit__(self, *a):
-        _state["relaxed"] = self.prev
+        _state["relaxed"], _state["relaxed_from"] = self.prev
 
 
 def relaxed():
     return bool(_state.get("relaxed", False))
+
+
+def relaxed_from(default):
+    v = _state.get("relaxed_from")
+    return default if v is None else v
 
 
 class operand_format:

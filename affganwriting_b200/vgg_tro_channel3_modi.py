@@ -56,7 +56,7 @@ class VGG(nn.Module):
         while i < stop:
             m = feats[i]
             if isinstance(m, nn.Conv2d):
-                if ops.relaxed() and i >= RELAXED_FROM:         # ops.relaxed_forward: one fp16 pass for the deep layers
+                if ops.relaxed() and i >= ops.relaxed_from(RELAXED_FROM):         # ops.relaxed_forward: one fp16 pass for the deep layers
                     with ops.conv_passes(fwd=1):
                         x = ops.conv2d(x, m.weight, m.bias, stride=1, pad=1, pad_mode="zero")
                 else:

@@ -372,6 +372,19 @@ def main():
         for _ in range(4):
             gen_fn(resident[3], resident[7])
         ms_gen = timed(lambda: gen_fn(resident[3], resident[7]), 10) / 10
+    # opt-in: one tensor-core pass in VGG convolutions 9-16 and the decoder ResBlocks (image 6e-3 instead of 1.5e-3 of the fp32
+    # reference's, bar 2e-2: tests/test_gpu_parity_c50.py::test_c50_b8_relaxed_generation_image)
+    gen_relaxed = None
+    if not args.no_graph and args.encoder == "vgg" and args.precision == "f16":
+        fast_fn = GraphedGenerator(gen, relaxed=True)
+        with torch.no_grad():
+            for _ in range(4):
+                fast_fn(resident[3], resident[7])
+            ms_fast = timed(lambda: fast_fn(resident[3], resident[7]), 10) / 10
+        gen_relaxed = {"images_per_sec": world * B / (ms_fast / 1e3), "ms_per_batch": ms_fast,
+                       "note": "inference.GraphedGenerator(gen, relaxed=True): generated image within 6e-3 of the fp32 reference "
+                               "(three passes: 1.5e-3; bar 2e-2)"}
+        del fast_fn
     gen.train()
     gen_img_s = world * B / (ms_gen / 1e3)
 
@@ -583,7 +596,7 @@ def main():
             "launched_tflops_per_gpu": launched_tflop / (ms_step / 1e3),
             "launched_frac_of_peak": launched_tflop / (ms_step / 1e3) / tf_peak},
         "cpu_baseline": cpu_baseline,
-        "extra": {"full_iteration_with_recogniser": full_iter, "iteration_with_shared_generator_forward": shared_fwd, "line_generator": line_gen, "dino_generation": dino_gen, "gen_images_per_sec": gen_img_s, "gen_batch_per_gpu": B, "gen_ms_per_batch": ms_gen,
+        "extra": {"full_iteration_with_recogniser": full_iter, "iteration_with_shared_generator_forward": shared_fwd, "line_generator": line_gen, "dino_generation": dino_gen, "gen_images_per_sec": gen_img_s, "gen_images_relaxed": gen_relaxed, "gen_batch_per_gpu": B, "gen_ms_per_batch": ms_gen,
                   "gen_frac_of_peak": None if args.encoder != "vgg" else 62.17e-3 * gen_img_s / world / tf_peak},
     }
     print(json.dumps(line), flush=True)

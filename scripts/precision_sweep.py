@@ -289,6 +289,13 @@ def main():
         vgg = ["gen.enc_image.model.features.%d." % i for i in (0, 3, 6, 9, 13, 16, 19, 22, 26, 29, 32, 35, 39, 42, 45, 48)]
         show2("dis_update: VGG fwd 1 pass, decoder as shipped", Policy(f3, {**base, **{n: f1 for n in vgg}}))
         dec_res = ["gen.dec.model.0.model.%d.model.%d.conv." % (i, j) for i in (0, 1) for j in (0, 1)]
+        if len(sys.argv) > 5 and sys.argv[5] == "disnet":
+            # the discriminator's own forward inside dis_update (its weight gradients are what the sub-step produces)
+            rel = {**base, **{n: f1 for n in vgg[4:] + dec_res}}
+            show2("shipped relaxed generator forward", Policy(f3, rel))
+            show2("  + discriminator forward 1 pass", Policy(f3, {**rel, "dis.": f1}))
+            show2("  + discriminator fwd 1, wgrad 3", Policy(f3, {**rel, "dis.": ("f16", "f16", "f16", 1, 1, 3)}))
+            return
         if len(sys.argv) > 5:
             for k in (2, 4, 6, 8):
                 show2("dis_update: VGG[%d:] + decoder ResBlocks fwd 1 pass" % k, Policy(f3, {**base, **{n: f1 for n in vgg[k:] + dec_res}}))
@@ -296,6 +303,17 @@ def main():
         for k in (8, 12):
             show2("dis_update: VGG[%d:] fwd 1 pass" % k, Policy(f3, {**base, **{n: f1 for n in vgg[k:]}}))
         show2("dis_update: decoder ResBlocks fwd 1 pass", Policy(f3, {**base, **{n: f1 for n in dec_res}}))
+    elif exp == "genimg":
+        # generation only (no gradients): the bar is the image, 2e-2 max-abs
+        dec_up = ["gen.dec.model.%d.conv." % i for i in (2, 4, 6)]
+        dec_res = ["gen.dec.model.0.model.%d.model.%d.conv." % (i, j) for i in (0, 1) for j in (0, 1)]
+        vgg = ["gen.enc_image.model.features.%d." % i for i in (0, 3, 6, 9, 13, 16, 19, 22, 26, 29, 32, 35, 39, 42, 45, 48)]
+        f3, f1 = ("f16", "f16", "f16", 3, 1, 1), ("f16", "f16", "f16", 1, 1, 1)
+        base = {n: f1 for n in dec_up}
+        show("shipping", Policy(f3, base))
+        for k in (12, 8, 4, 2, 0):
+            show("VGG[%d:] + decoder ResBlocks fwd 1 pass" % k, Policy(f3, {**base, **{n: f1 for n in vgg[k:] + dec_res}}))
+        show("every generator layer fwd 1 pass", Policy(f3, {"gen.": f1}))
     elif exp == "fp8corr":
         dec_up = ["gen.dec.model.%d.conv." % i for i in (2, 4, 6)]
         vgg = ["gen.enc_image.model.features.%d." % i for i in (0, 3, 6, 9, 13, 16, 19, 22, 26, 29, 32, 35, 39, 42, 45, 48)]

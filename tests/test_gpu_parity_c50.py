@@ -167,6 +167,37 @@ def test_c50_b8_dis_update_with_its_own_generator_forward(bf16, specs):
     A.check_device_errors()
 
 
+def test_c50_b8_relaxed_generation_image(specs):
+    """inference.GraphedGenerator(relaxed=True) / ops.relaxed_forward(True, 26): generation with one tensor-core pass in VGG
+    convolutions 9-16 and the decoder ResBlock convolutions.  Only the image is produced, so only the image bar applies (2e-2);
+    the option must keep a 2x margin.  (CPU model, 15 planes: 5.9e-3; three passes: 1.4e-3.)"""
+    from affganwriting_b200.inference import GraphedGenerator
+    A.set_precision("f16")
+    try:
+        cpu = O.synthetic_batch(8, 50)
+        full = _full_state(specs)
+        with torch.no_grad():
+            g = O._sub(full, "gen.")
+            res = O.image_encoder(cpu["tr_img"], g)
+            ref = O.gen_forward(None, cpu["label_xt"], g, results=res)
+        gen, _, _ = _models(specs)
+        b = _cuda(cpu)
+        with torch.no_grad():
+            plain = gen(b["tr_img"], b["label_xt"]).clone()
+            n0 = A.launch_count()
+            with ops.relaxed_forward(True, GraphedGenerator.RELAXED_VGG_FROM):
+                fast = gen(b["tr_img"], b["label_xt"]).clone()
+            assert A.launch_count() > n0
+        e_plain = float((plain.cpu() - ref).abs().max())
+        e_fast = float((fast.cpu() - ref).abs().max())
+        print(f"\n[f16, C_s=50, B=8] generated image vs fp32 oracle: three passes {e_plain:.3e}, relaxed {e_fast:.3e} (bar {IMAGE_BAR:g})")
+        assert e_plain <= IMAGE_BAR and e_fast <= IMAGE_BAR / 2
+        assert e_fast > e_plain                    # (the relaxed route really ran)
+        A.check_device_errors()
+    finally:
+        A.set_precision("fp32")
+
+
 def test_b64_samples_are_independent_in_the_style_encoder(bf16, specs):
     """Batch 64 (the benchmarked batch) without a batch-64 oracle run: the VGG-IN encoder has per-sample statistics only
     (vgg_tro_channel3_modi.py:47-50), so sample i of a 64-sample forward must equal the same sample encoded in a batch of 8
