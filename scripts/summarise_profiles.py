@@ -14,6 +14,15 @@ BENCH = {"r01": "bench.json"}.get(R, f"bench_{R}.json")
 MODE = {"r01": "bf16 mode (3 MMAs per product)"}.get(R, "f16 mode (forward 3 MMAs per product, backward 1)")
 
 
+# algorithmic bytes of one launch on the profiled layer (two fp16 planes of 122.6 MB for the split forward, one for the single-pass
+# backward GEMMs; 226.5 MB of fp32 activations / 2.4 MB of fp32 weight gradients written)
+ALGO_BYTES = {
+    "conv_shift_tcgen05_kernel<256, 1, 2>": {"operand plane read (dY, one fp16 plane)": 122552320, "fp32 output written": 226492416},
+    "conv_wgrad_shift_kernel<128, 1>": {"operand planes read (x and dY, one fp16 plane each)": 245104640,
+                                        "fp32 weight-gradient partials written": 2359296},
+}
+
+
 def short(name):
     name = re.sub(r"\(anonymous namespace\)::|<unnamed>::|void ", "", name)
     return name.split("(")[0]
@@ -85,7 +94,7 @@ def full_capture():
     for name, d in out.items():
         n = d["launches_profiled"]
         res[name] = {"layer": d["layer"], "launches_profiled": n, "dram_bytes_per_launch": d["dram"] / n,
-                     "algorithmic_bytes_per_launch": {"operand planes read": 245104640, "fp32 output written": 226492416},
+                     "algorithmic_bytes_per_launch": ALGO_BYTES.get(name, {"operand planes read": 245104640, "fp32 output written": 226492416}),
                      "us_per_launch_under_ncu": d["us"] / n, "tensor_pipe_active_pct": d["tensor"] / n,
                      "l1tex_throughput_pct": d["l1"] / n}
         print(name, {k: (round(v, 1) if isinstance(v, float) else v) for k, v in res[name].items() if k != "layer"})
