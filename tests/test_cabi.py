@@ -192,3 +192,36 @@ def test_host_side_validation_of_optimiser_and_wire_format_needs_no_gpu():
     with pytest.raises(RuntimeError):
         LD.decode_u8(torch.zeros(16, dtype=torch.uint8))         # CPU tensor
     assert LD.batch_to_device(("src", 3), "cpu") == ("src", 3)   # non-tensor members pass through untouched
+
+
+def test_pass_selection_contexts_need_no_gpu():
+    """Host-side state of the per-layer tensor-core pass selection: ops.conv_passes and ops.relaxed_forward (the no_grad
+    generator forward of dis_update / GraphedGenerator(relaxed=True)) - mode gating, nesting, restoration."""
+    from affganwriting_b200 import ops
+    from affganwriting_b200.vgg_tro_channel3_modi import RELAXED_FROM
+    assert ops.precision() == "fp32" and not ops.relaxed()
+    with ops.relaxed_forward(True):
+        assert not ops.relaxed()                              # fp32 / bf16 modes: never relaxed
+    ops.set_precision("bf16")
+    try:
+        with ops.relaxed_forward(True):
+            assert not ops.relaxed()
+        ops.set_precision("f16")
+        assert ops._state["passes"] == (3, 1, 1)
+        with ops.relaxed_forward(False):
+            assert not ops.relaxed()
+        with ops.relaxed_forward(True):
+            assert ops.relaxed() and ops.relaxed_from(RELAXED_FROM) == RELAXED_FROM
+            with ops.relaxed_forward(True, 26):               # generation: a shallower relaxation (inference.GraphedGenerator)
+                assert ops.relaxed_from(RELAXED_FROM) == 26
+                with ops.conv_passes(fwd=1):
+                    assert ops._state["passes"] == (1, 1, 1)
+                with ops.conv_passes(fwd=None):               # Conv2dBlock.fwd_passes = None keeps the mode's counts
+                    assert ops._state["passes"] == (3, 1, 1)
+                assert ops._state["passes"] == (3, 1, 1)
+            assert ops.relaxed_from(RELAXED_FROM) == RELAXED_FROM
+        assert not ops.relaxed()
+        # the VGG layers that stay at three passes are the first four convolutions (features 0, 3, 6, 9)
+        assert RELAXED_FROM == 14
+    finally:
+        ops.set_precision("fp32")
