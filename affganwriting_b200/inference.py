@@ -14,8 +14,8 @@ from . import ops
 
 class GraphedGenerator:
     """`relaxed=True` (mode 'f16', VGG encoder; off by default): VGG convolutions 9-16 and the decoder's ResBlock convolutions
-    run one tensor-core pass instead of three (ops.relaxed_forward) - the image moves from 1.5e-3 to 6e-3 of the fp32
-    reference's (bar 2e-2, tests/test_gpu_parity_c50.py) for 1.4x the images per second."""
+    run one tensor-core pass instead of three (ops.relaxed_forward) - the image moves from 1.4e-3 to 5.4e-3 of the fp32
+    reference's (bar 2e-2, tests/test_gpu_parity_c50.py) for 1.2x the images per second."""
     RELAXED_VGG_FROM = 26
 
     def __init__(self, gen, warmup=2, relaxed=False):

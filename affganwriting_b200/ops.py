@@ -150,8 +150,8 @@ class relaxed_forward:
     """Context manager for a generator forward whose image only FEEDS the discriminator (dis_update's no_grad pair,
     network_tro.py:117-118): inside, the layers that declare themselves tolerant (`relaxed()` is true for them) run their forward
     GEMM with one fp16 MMA per product instead of three.  Which layers tolerate it is decided by the discriminator's gradients
-    (scripts/precision_sweep.py disfwd, then measured on B200 at the benchmarked shapes): VGG convolutions 5-16 and the decoder's
-    ResBlock convolutions leave the worst discriminator tensor at cosine 0.99994, every layer single-pass 0.9994 (the first four
+    (scripts/precision_sweep.py disfwd, then measured on B200 at the benchmarked shapes): VGG convolutions 6-16 and the decoder's
+    ResBlock convolutions leave the worst discriminator tensor at cosine 0.99994, every layer single-pass 0.9994 (the first five
     VGG layers stay at three passes).  Mode 'f16' only."""
 
     def __init__(self, flag=True, vgg_from=None):

@@ -10,9 +10,11 @@ from . import load_data, ops
 
 import os as _os
 
-# `features` index of the first convolution that runs single-pass inside ops.relaxed_forward(): 14 = conv3_1, i.e. convolutions
-# 5-16 (80 % of the encoder's FLOPs).  Measured on B200 at 50 planes, batch 8 (tests/test_gpu_parity_c50.py, complete dis_update,
-# worst discriminator tensor): from 26 -> 0.999985, 19 -> 0.99992, 14 -> 0.99994, 7 -> 0.99969, 0 (every layer) -> 0.99938;
+# Convolutions sit at `features` indices 0, 3, 6, 9 | 13, 16, 19, 22 | 26, 29, 32, 35 | 39, 42, 45, 48.  Inside
+# ops.relaxed_forward() the ones at index >= RELAXED_FROM run single-pass: 14 -> from index 16 on, i.e. convolutions 6-16
+# (75 % of the encoder's FLOPs; the first five keep three passes).  Measured on B200 at 50 planes, batch 8 (tests/test_gpu_parity_c50.py, complete dis_update,
+# worst discriminator tensor): from 26 (convolution 9 on) -> 0.999985, 19 (7 on) -> 0.99992, 14 (6 on) -> 0.99994, 7 (4 on) -> 0.99969,
+# 0 (every layer) -> 0.99938;
 # a value past the last convolution (48) switches the relaxation off
 RELAXED_FROM = int(_os.environ.get("AFFGW_RELAXED_VGG_FROM", "14"))
 

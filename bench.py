@@ -556,7 +556,7 @@ def main():
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16" if args.precision == "f16" else "bf16",
         "dtype_detail": ("tcgen05 kind::f16 MMAs on %s operand planes with fp32 TMEM accumulation (forward: split operands, 3 MMAs per "
                          "product - 1 in the decoder's up-convolutions in mode f16 and, in the no_grad generator forward of dis_update whose image "
-                         "only feeds the discriminator, in the deep half of the VGG encoder and the decoder ResBlocks "
+                         "only feeds the discriminator, in VGG convolutions 6-16 and the decoder ResBlock convolutions "
                          "(ops.relaxed_forward); backward: 1 MMA per product); activations, "
                          "statistics, gradients and parameters are stored in fp32.  fp16 planes carry 11 significant bits against "
                          "bf16's 8 at the same tensor throughput; their range is handled by exact power-of-two scales "

@@ -221,7 +221,7 @@ def test_pass_selection_contexts_need_no_gpu():
                 assert ops._state["passes"] == (3, 1, 1)
             assert ops.relaxed_from(RELAXED_FROM) == RELAXED_FROM
         assert not ops.relaxed()
-        # the VGG layers that stay at three passes are the first four convolutions (features 0, 3, 6, 9)
+        # the VGG layers that stay at three passes are the first five convolutions (features 0, 3, 6, 9, 13)
         assert RELAXED_FROM == 14
     finally:
         ops.set_precision("fp32")

@@ -143,7 +143,7 @@ def test_c50_b8_dis_and_cla_update_gradients(bf16, specs):
 
 def test_c50_b8_dis_update_with_its_own_generator_forward(bf16, specs):
     """The COMPLETE dis_update (network_tro.py:105-138) through ConTranModel.forward: the fake pair comes from this package's
-    generator under no_grad - in mode 'f16' with ops.relaxed_forward (one tensor-core pass in the deep half of the VGG encoder
+    generator under no_grad - in mode 'f16' with ops.relaxed_forward (one tensor-core pass in VGG convolutions 6-16
     and in the decoder's ResBlock convolutions; that image feeds nothing but the discriminator).  The discriminator's gradients
     against the fp32 oracle, per tensor: the bar is north_star's 0.999, the relaxation must leave at least a 2x margin."""
     from affganwriting_b200.network_tro import ConTranModel
