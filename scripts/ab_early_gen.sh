@@ -1,5 +1,7 @@
 #!/bin/bash
-# A/B of Trainer(early_generator_forward): gen_update's generator forward issued inside dis_update beside the discriminator pass
+# A/B of the trainer's stream options on one box: AFFGW_EARLY_GEN (gen_update's generator forward issued inside dis_update beside the
+# discriminator pass), AFFGW_GEN_HEADS (classifier beside discriminator in gen_update), AFFGW_SIDE_TEXT (text encoder beside the image
+# encoder) - edit the variable pair of the loop for the option under test
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_gpu_models.py -q --no-header -p no:cacheprovider -x -s \
     -k "early_generator or shared_generator or graph or short_final" > gpurun_out/t_early.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/t_early.log
