@@ -345,4 +345,5 @@ class Trainer:
         self._packed = {name: ops.packed_entries(p for grp in self.opt[name].param_groups for p in grp["params"])
                         for name in self.names}
         self._graphs = graphs                       # (iter_num was advanced by the captured gen_update's Python side)
-        return self._pack(outs)
+        # static graph outputs, overwritten by the first replay: hand out copies here too
+        return {k: v.clone() for k, v in self._pack(outs).items()}
