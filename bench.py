@@ -1,9 +1,10 @@
 """Benchmark of the hot path: one full GAN training iteration (cla_update -> dis_update -> gen_update, forward + backward
-+ Adam, no recogniser) at batch 64 per GPU, 50 style planes, 64x216 synthetic IAM-shaped words, bf16 storage with
-tcgen05 tensor-core convolutions (BASELINE.json configs[1]).
++ Adam, no recogniser) at batch 64 per GPU, 50 style planes, 64x216 synthetic IAM-shaped words (BASELINE.json configs[1]).
+Activations, gradients and parameters are fp32 in HBM; the convolutions run on tcgen05 tensor cores over 16-bit operand
+planes (fp16 by default, `--precision bf16` for bf16 planes).
 
     python bench.py --gpus N --steps K --warmup W            # this implementation (torchrun for N > 1)
-    python bench.py --impl reference ...                      # the reference algorithm on the host cores (CPU oracle port)
+    python bench.py --impl reference ...                      # the reference's own nn.Modules (staged in oracle/_ref) on the host cores
 
 Prints ONE JSON line on rank 0 (see DESIGN.md "measurement" for every field).
 """
