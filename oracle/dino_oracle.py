@@ -6,7 +6,10 @@ appendix E).  So there are two layers of evidence:
 
   * `StandInViT` restates the PUBLIC DINOv2 ViT definition (pre-LayerNorm blocks with eps 1e-6, qkv bias, LayerScale on both
     residual branches, erf-GELU MLP, no register tokens, flat `blocks`) with the hub model's attribute / parameter names, at any
-    size.  PARITY OF THE BACKBONE IS UNPINNED: it cannot be compared with the real hub module in this container.
+    size.  It cannot be compared with the real hub module in this container; it IS pinned against an independent implementation
+    of the same published model - transformers.Dinov2Model (the implementation that loads the official checkpoints through
+    convert_dinov2_to_hf.py's key map) - by oracle/make_golden_dino_hf.py: every block output 1e-7, and HF's layers + the
+    wrapper's reducers reproduce the UNMODIFIED reference wrapper's golden maps to 1.6e-7 (tests/golden/dino_hf.npz).
   * the reference WRAPPER itself is pinned: oracle/make_golden_dino.py runs the UNMODIFIED dinomodel.ImageEncoderDINOv2 with
     `torch.hub.load` answered by a small StandInViT, and `dino_encoder` below (a functional restatement of wrapper + blocks over
     the state_dict) is checked against it (tests/golden/dino.npz).
