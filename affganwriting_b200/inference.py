@@ -29,7 +29,7 @@ class GraphedGenerator:
 
     @torch.no_grad()
     def __call__(self, tr_img, label):
-        key = (tuple(tr_img.shape), tuple(label.shape), self.gen.training)
+        key = (tuple(tr_img.shape), tuple(label.shape), self.gen.training, ops.precision())     # a graph holds one mode's kernels
         if self._graph is None or key != self._shape:
             if self._shape != key:
                 self._graph, self._calls, self._shape = None, 0, key
@@ -71,7 +71,7 @@ class GraphedForward:
 
     @torch.no_grad()
     def __call__(self, *tensors):
-        key = tuple((tuple(t.shape), t.dtype) for t in tensors) + (self.module.training,)
+        key = tuple((tuple(t.shape), t.dtype) for t in tensors) + (self.module.training, ops.precision())
         if self._graph is None or key != self._key:
             if self._key != key:
                 self._graph, self._calls, self._key = None, 0, key
