@@ -9,7 +9,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from affganwriting_b200.parallel import GradientReducer, plan_buckets, shard_batch
+from affganwriting_b200.parallel import GradientReducer, broadcast_module, plan_buckets, shard_batch
 
 
 class _CpuPacker:                      # test infrastructure only
@@ -56,6 +56,28 @@ def _worker(rank, world, port, q):
         for i, p in enumerate(params):
             if i != 1:
                 ok = ok and torch.allclose(p.grad, torch.full_like(p, 1.5 * (i + 1)))   # mean over ranks of (rank+1)*(i+1)
+        # broadcast_module: rank 1 starts from other weights AND other BatchNorm buffers; afterwards both hold rank 0's
+        torch.manual_seed(100 + rank)
+        net = torch.nn.Sequential(torch.nn.Linear(6, 4), torch.nn.BatchNorm1d(4), torch.nn.Linear(4, 1))
+        net[1].running_mean.normal_()
+        broadcast_module(net)
+        torch.manual_seed(100)
+        want = torch.nn.Sequential(torch.nn.Linear(6, 4), torch.nn.BatchNorm1d(4), torch.nn.Linear(4, 1))
+        want[1].running_mean.normal_()
+        ok = ok and all(torch.equal(a, b) for a, b in zip(net.state_dict().values(), want.state_dict().values()))
+        # equal shards of dim 0 + mean-reduced loss per rank + mean all-reduce == the full-batch gradient;
+        # layers without cross-sample coupling only (BatchNorm statistics stay per rank by design)
+        lin = torch.nn.Linear(6, 3)
+        broadcast_module(lin)
+        g = torch.Generator().manual_seed(7)
+        xs, ys = torch.randn(8, 6, generator=g), torch.randn(8, 3, generator=g)
+        x, y = shard_batch((xs, ys), rank, world)
+        torch.nn.functional.mse_loss(lin(x), y).backward()
+        GradientReducer(lin.parameters(), packer=_CpuPacker()).reduce()
+        full = torch.nn.Linear(6, 3)
+        full.load_state_dict(lin.state_dict())
+        torch.nn.functional.mse_loss(full(xs), ys).backward()
+        ok = ok and all(torch.allclose(a.grad, b.grad, atol=1e-6) for a, b in zip(lin.parameters(), full.parameters()))
         q.put((rank, bool(ok)))
     finally:
         dist.destroy_process_group()
