@@ -225,3 +225,19 @@ def test_pass_selection_contexts_need_no_gpu():
         assert RELAXED_FROM == 14
     finally:
         ops.set_precision("fp32")
+
+
+def test_compute_entry_points_fail_loudly_without_a_device():
+    """No CPU fallback (include/affgw.h conventions): on a host without a GPU the library reports that and a compute entry
+    point returns a negative code with a message - it never touches the (host) buffers it was handed."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("only meaningful on a GPU-less host")
+    from affganwriting_b200 import _lib
+    h = _lib.lib()
+    assert h.affgw_device_ok() == 0 and h.affgw_last_error()
+    buf = (ctypes.c_float * 64)(*([1.5] * 64))
+    p = ctypes.addressof(buf)
+    with pytest.raises(RuntimeError, match="affgw_act_bwd failed"):
+        _lib.call("affgw_act_bwd", p, p, p, 0, 64, 1, None)
+    assert list(buf) == [1.5] * 64
