@@ -241,3 +241,31 @@ def test_compute_entry_points_fail_loudly_without_a_device():
     with pytest.raises(RuntimeError, match="affgw_act_bwd failed"):
         _lib.call("affgw_act_bwd", p, p, p, 0, 64, 1, None)
     assert list(buf) == [1.5] * 64
+
+
+@pytest.mark.parametrize("shape", [(32, 108, 256, 256, 3, 1, 1), (8, 27, 512, 512, 3, 1, 1), (64, 216, 16, 16, 3, 1, 1),
+                                   (8, 27, 512, 256, 5, 2, 2), (64, 216, 50, 64, 3, 1, 1), (4, 14, 256, 256, 3, 1, 1)])
+def test_position_frames_hold_every_window_for_any_batch(shape):
+    """Storage geometry of the planar operand planes (host code - no GPU): for every batch size a short final
+    batch can have (and the 2B / 4B concatenations of the discriminator passes), the frame a position-space kernel reads keeps
+    (a) a zero lead as long as the filter window's reach backwards, (b) room behind the last position for the rounding of the
+    position range to whole CTA tiles plus the window's reach forwards, (c) 8-position (one 128-byte core matrix) granularity."""
+    from affganwriting_b200 import _lib
+    h = _lib.lib()
+    H, W, cin, cout, k, pad, up = shape
+    for n in list(range(1, 66)) + [127, 128, 192, 255, 256]:
+        d = _conv_desc(n, H, W, cin, cout, k, pad, upsample=up)
+        if h.affgw_conv_tc_layout(ctypes.byref(d), 0) != _lib.WLAYOUT_SHIFT:
+            continue
+        fx, fy = _lib.PosFrame(), _lib.PosFrame()
+        assert h.affgw_conv_pos_frames(ctypes.byref(d), ctypes.byref(fx), ctypes.byref(fy)) == 0
+        for f, c in ((fx, cin), (fy, cout)):
+            assert (f.N, f.Hp, f.Wp) == (n, H * up + 2 * pad, W * up + 2 * pad)
+            assert f.G == 2 * ((c + 15) // 16)                                     # 8-channel groups, even
+            span = (k - 1) * (f.Wp + 1)                                            # reach of the filter window in positions
+            q = f.N * f.Hp * f.Wp
+            tile = max(h.affgw_conv_tc_tile_m(ctypes.byref(d), 0), h.affgw_conv_tc_tile_m(ctypes.byref(d), 1))
+            assert f.lead >= span and f.lead % 8 == 0
+            assert f.QA % 32 == 0 and f.QA - f.lead >= (q + tile - 1) // tile * tile + span
+            for passes in (1, 3):
+                assert h.affgw_position_planes_bytes(ctypes.byref(f), passes) == (2 if passes == 3 else 1) * f.G * f.QA * 16
