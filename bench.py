@@ -478,6 +478,34 @@ def main():
     except Exception as e:
         dino_gen = {"error": repr(e)[:300]}
 
+    # ---- BASELINE.json configs[2]: the same training step with the ResNet-18 style encoder (torchvision wrapper wiring,
+    # modules_tro2.py:447-516), so that the driver's N = 1, 2, 4, 8 runs of this file also carry that configuration.  Last of
+    # the extras and never fatal.  dis_update's generator forward keeps three passes everywhere here: the relaxed forward
+    # (ops.relaxed_forward) was validated against the oracle with the VGG encoder only.
+    r18_step = None
+    if not args.no_rec_extra and args.encoder == "vgg":
+        relaxed_was = network_tro._RELAXED_DIS_FWD
+        try:
+            trainer.join()
+            torch.cuda.synchronize()
+            network_tro._RELAXED_DIS_FWD = False
+            t4 = Trainer(num_writers=500, device=dev, encoder="resnet18", cuda_graph=not args.no_graph,
+                         overlap_exchange=not args.no_overlap)
+            for _ in range(Trainer.GRAPH_WARMUP + 2):
+                t4.train_step(resident)
+            ms_r18 = timed(lambda: t4.train_step(resident), 5) / 5
+            t4.join()
+            r18_step = {"ms_per_step": ms_r18, "steps_per_sec": world / (ms_r18 / 1e3), "n_gpus": world, "batch_per_gpu": B,
+                        "note": "configs[2]: full GAN training step (cla_update -> dis_update -> gen_update + Adam, no recogniser) with "
+                                "GenModel_FC(encoder='resnet18'), same batch / precision mode / stream options as the headline, "
+                                "5 timed CUDA-graph iterations, max over ranks; relaxed dis_update forward off"}
+            del t4
+            torch.cuda.empty_cache()
+        except Exception as e:
+            r18_step = {"error": repr(e)[:300]}
+        finally:
+            network_tro._RELAXED_DIS_FWD = relaxed_was
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -597,7 +625,7 @@ def main():
             "launched_tflops_per_gpu": launched_tflop / (ms_step / 1e3),
             "launched_frac_of_peak": launched_tflop / (ms_step / 1e3) / tf_peak},
         "cpu_baseline": cpu_baseline,
-        "extra": {"full_iteration_with_recogniser": full_iter, "iteration_with_shared_generator_forward": shared_fwd, "line_generator": line_gen, "dino_generation": dino_gen, "gen_images_per_sec": gen_img_s, "gen_images_relaxed": gen_relaxed, "gen_batch_per_gpu": B, "gen_ms_per_batch": ms_gen,
+        "extra": {"full_iteration_with_recogniser": full_iter, "iteration_with_shared_generator_forward": shared_fwd, "line_generator": line_gen, "dino_generation": dino_gen, "resnet18_encoder_step": r18_step, "gen_images_per_sec": gen_img_s, "gen_images_relaxed": gen_relaxed, "gen_batch_per_gpu": B, "gen_ms_per_batch": ms_gen,
                   "gen_frac_of_peak": None if args.encoder != "vgg" else 62.17e-3 * gen_img_s / world / tf_peak},
     }
     print(json.dumps(line), flush=True)
